@@ -1,0 +1,84 @@
+"""ctypes binding of libegorear_b200.so (the C-ABI declared in include/egorear_b200.h).
+
+This is the stub a maintainer of the reference would add.  It fails loudly:
+a missing library or a non-B200 device raises, there is no CPU / eager fallback anywhere in the
+package.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libegorear_b200.so")
+
+_lib = None
+
+
+class EgrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("egorear_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "egr_last_error": (c_char_p, []),
+    "egr_version": (c_int, []),
+    "egr_device_check": (c_int, [POINTER(c_int), POINTER(c_int)]),
+    "egr_launch_count": (c_int64, []),
+    "egr_generate_target": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_double, c_void_p, c_void_p]),
+    "egr_decode_argmax": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "egr_msda_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                                 c_void_p, c_void_p]),
+    "egr_reproject_fisheye": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    "egr_heatmap_head_1x1": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "egr_mvfex_create": (c_int, [c_int, c_int, c_float, c_int, POINTER(c_void_p)]),
+    "egr_mvfex_destroy": (c_int, [c_void_p]),
+    "egr_mvfex_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "egr_mvfex_prepack": (c_int, [c_void_p, c_void_p]),
+    "egr_mvfex_workspace_bytes": (c_int64, [c_void_p, c_int]),
+    "egr_mvfex_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "egr_mvfex_refiner_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "egr_mvfex_debug_buffer": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
+    "egr_pose3d_debug_buffer": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
+    "egr_set_option": (c_int, [c_char_p, c_int]),
+    "egr_pose3d_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "egr_pose3d_destroy": (c_int, [c_void_p]),
+    "egr_pose3d_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "egr_pose3d_prepack": (c_int, [c_void_p, c_void_p]),
+    "egr_pose3d_workspace_bytes": (c_int64, [c_void_p, c_int]),
+    "egr_pose3d_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                   c_void_p]),
+    "egr_pack_joints": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+
+
+def load():
+    """Load the shared library once; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "egorear_b200: %s not found. Build it with `python -m egorear_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the .so is stale: loud on purpose
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EgrError(rc, load().egr_last_error().decode("utf-8", "replace"))
+
+
+def launch_count():
+    return int(load().egr_launch_count())

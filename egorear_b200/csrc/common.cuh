@@ -1,0 +1,71 @@
+// Shared helpers for the egorear_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string>
+#include <atomic>
+
+#include "../../include/egorear_b200.h"
+
+namespace egr {
+
+// ---- error plumbing -------------------------------------------------------------------------
+std::string& last_error();                       // thread-local
+int fail(int code, const char* fmt, ...);        // formats into last_error(), returns code
+extern std::atomic<int64_t> g_launches;          // kernels launched by this library
+
+#define EGR_CUDA_OK(expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ::egr::fail(EGR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                                \
+    } while (0)
+
+#define EGR_CHECK(cond, code, ...)                                                                 \
+    do {                                                                                           \
+        if (!(cond)) return ::egr::fail((code), __VA_ARGS__);                                      \
+    } while (0)
+
+// count + check a kernel launch
+#define EGR_LAUNCHED()                                                                             \
+    do {                                                                                           \
+        ::egr::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return ::egr::fail(EGR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                                \
+    } while (0)
+
+int require_device();   // EGR_OK iff current device is sm_100; caches the answer
+int sm_count();
+
+// ---- device helpers -------------------------------------------------------------------------
+template <typename T> struct ActT;
+template <> struct ActT<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct ActT<__nv_bfloat16> {
+    static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace egr

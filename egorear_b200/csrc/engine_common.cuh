@@ -1,0 +1,103 @@
+// Pieces shared by the two engines: parameter registry, library-owned device buffers, workspace carving.
+#pragma once
+#include "common.cuh"
+#include "gemm.cuh"
+#include "layout_ops.cuh"
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace egr {
+
+struct ParamRef {
+    const float* ptr = nullptr;
+    int64_t numel = 0;
+};
+
+struct ParamTable {
+    std::unordered_map<std::string, ParamRef> map;
+    int set(const char* key, const float* ptr, int64_t numel) {
+        if (!key || !ptr || numel <= 0) return fail(EGR_ERR_INVALID, "set_param: bad argument for '%s'", key ? key : "(null)");
+        map[key] = ParamRef{ptr, numel};
+        return EGR_OK;
+    }
+    // fetch with a size check; returns nullptr and sets the error on failure
+    const float* get(const std::string& key, int64_t numel, int* rc) const {
+        auto it = map.find(key);
+        if (it == map.end()) {
+            *rc = fail(EGR_ERR_STATE, "missing parameter '%s' (state_dict key not registered)", key.c_str());
+            return nullptr;
+        }
+        if (it->second.numel != numel) {
+            *rc = fail(EGR_ERR_INVALID, "parameter '%s' has %lld elements, expected %lld", key.c_str(),
+                       (long long)it->second.numel, (long long)numel);
+            return nullptr;
+        }
+        return it->second.ptr;
+    }
+};
+
+// library-owned device allocations of a handle (derived weights); freed with the handle / on re-prepack
+struct DevPool {
+    std::vector<void*> blocks;
+    int64_t bytes = 0;
+    template <typename T>
+    int alloc(T** out, int64_t n) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (size_t)(n * (int64_t)sizeof(T)));
+        if (e != cudaSuccess) return fail(EGR_ERR_CUDA, "cudaMalloc(%lld B) failed: %s", (long long)(n * sizeof(T)), cudaGetErrorString(e));
+        blocks.push_back(p);
+        bytes += n * (int64_t)sizeof(T);
+        *out = reinterpret_cast<T*>(p);
+        return EGR_OK;
+    }
+    void release() {
+        for (void* p : blocks) cudaFree(p);
+        blocks.clear();
+        bytes = 0;
+    }
+};
+
+// bump allocator over the caller-provided workspace
+struct Carver {
+    char* base;
+    int64_t off = 0, cap;
+    Carver(void* b, int64_t c) : base(reinterpret_cast<char*>(b)), cap(c) {}
+    void* take(int64_t bytes) {
+        off = (off + 255) & ~int64_t(255);
+        void* p = base ? base + off : nullptr;
+        off += bytes;
+        return p;
+    }
+    bool ok() const { return off <= cap; }
+};
+
+// a weight matrix [N][K] kept as fp32 and (bf16 mode) as a bf16 copy, `sets` weight sets at constant stride
+struct WMat {
+    float* f32 = nullptr;
+    __nv_bfloat16* bf16 = nullptr;
+    float* bias = nullptr;    // [sets][N]
+    int N = 0, K = 0, sets = 0;
+    const void* w(int prec_bf16_tc) const { return prec_bf16_tc ? (const void*)bf16 : (const void*)f32; }
+    int64_t stride() const { return (int64_t)N * K; }
+};
+
+extern int g_opt_tc;   // 1: bf16 precision uses the tcgen05 kernel; 0: bf16 activations through the SIMT kernel (debug)
+
+// run one dense stage in the handle's precision.  `out_f32`: the output stays fp32 even in bf16 mode.
+inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out_f32, cudaStream_t st) {
+    const bool bf = (prec == EGR_PREC_BF16);
+    const bool tc = bf && g_opt_tc;
+    d.N = w.N;
+    d.K = w.K;
+    d.W = tc ? (const void*)(w.bf16 + (int64_t)set_begin * w.stride())
+             : (const void*)(w.f32 + (int64_t)set_begin * w.stride());
+    d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
+    d.w_gs = w.stride();
+    d.b_gs = w.N;
+    const int d_bf16 = (bf && !out_f32) ? 1 : 0;
+    if (tc) return gemm_tc(d, d_bf16, st);
+    return gemm_simt(d, bf ? 1 : 0, d_bf16, st);
+}
+
+}  // namespace egr

@@ -1,0 +1,481 @@
+// mvfex engine: orchestration of the multi-view heatmap refinement hot path
+// (EgoPoseFormerHeatmapMVFEX.forward after the backbones, estimator/egoposeformer_heatmap_mvf_ex.py:262-437).
+//
+// HBM layout.  Activations are channels-last and VIEW-MAJOR ([V][B][H*W][C]) so that every dense stage is a
+// row-major [M, K] x [N, K]^T GEMM over a contiguous block of rows per weight set (front/back heads: two views
+// each; the four per-view refiners: one view each) and the `groups` of one launch sit at a constant stride.
+// Stage dtype is fp32 (EGR_PREC_FP32) or bf16 (EGR_PREC_BF16); module outputs are always fp32 NCHW.
+#include "engine_common.cuh"
+#include "token_kernels.cuh"
+
+namespace egr {
+int g_opt_tc = 1;
+}
+using namespace egr;
+
+static const char* kRefiner4[4] = {"heatmap_refiner_front_left", "heatmap_refiner_front_right",
+                                   "heatmap_refiner_back_left", "heatmap_refiner_back_right"};
+static const char* kHead[2] = {"conv_heatmap_layers_stereo_front", "conv_heatmap_layers_stereo_back"};
+
+constexpr int FH = 64, FW = 64, FHW = 4096, FC = 128;   // feature map geometry of every shipped config
+constexpr int EMB = 256, NPOS = 256;
+
+struct egr_mvfex {
+    int V = 4, J = 15, prec = EGR_PREC_FP32;
+    float thr = 0.5f;
+    int head_sets = 2;
+    bool packed = false;
+    ParamTable params;
+    DevPool pool;
+    // dense stage weights
+    WMat h1_0, h1_2, h1_4, h1_7;              // init heads (sets = head_sets)
+    float *h1_9w = nullptr, *h1_9b = nullptr;  // [sets][J][128], [sets][J]
+    WMat hp0;                                  // heatmap_proj.0 [256][4096]          (sets = V)
+    WMat f1_0, f1_2, f1_4;                     // frame_feat_proj_layers
+    WMat t1_0, t1_3;                           // head_layers.0.head.{0,3}  ([64][16] padded, [128][64])
+    WMat r1_0, r1_3;                           // frame_feat_refined_proj_layers.0.{0,3}
+    WMat h2_0, h2_2, h2_5;                     // conv_heatmap_layers.0.{0,2,5}
+    float *h2_7w = nullptr, *h2_7b = nullptr;  // [V][J][128], [V][J]
+    MvfTokenW* d_tokw = nullptr;               // device [V]
+    bool has_heads = false, has_ref[4] = {false, false, false, false};   // parameter groups present at prepack
+    std::unordered_map<std::string, std::pair<void*, int64_t>> dbg;
+};
+
+namespace {
+
+enum WKind { W_PLAIN, W_CONV3, W_PAD16 };
+
+// builds one WMat from `sets` parameters "<prefix(set)>.weight/.bias"
+template <typename KeyFn>
+int make_wmat(egr_mvfex* h, WMat& m, int sets, int N, int K, WKind kind, KeyFn key, const bool* present, cudaStream_t st) {
+    m.N = N; m.K = K; m.sets = sets;
+    if (int rc = h->pool.alloc(&m.f32, (int64_t)sets * N * K)) return rc;
+    if (int rc = h->pool.alloc(&m.bias, (int64_t)sets * N)) return rc;
+    EGR_CUDA_OK(cudaMemsetAsync(m.f32, 0, sizeof(float) * sets * N * K, st));
+    EGR_CUDA_OK(cudaMemsetAsync(m.bias, 0, sizeof(float) * sets * N, st));
+    for (int s = 0; s < sets; ++s) {
+        if (present && !present[s]) continue;
+        int rc = EGR_OK;
+        const std::string k = key(s);
+        float* dst = m.f32 + (int64_t)s * N * K;
+        if (kind == W_PLAIN) {
+            const float* w = h->params.get(k + ".weight", (int64_t)N * K, &rc);
+            if (!w) return rc;
+            EGR_CUDA_OK(cudaMemcpyAsync(dst, w, sizeof(float) * N * K, cudaMemcpyDeviceToDevice, st));
+        } else if (kind == W_CONV3) {
+            const int Cin = K / 9;
+            const float* w = h->params.get(k + ".weight", (int64_t)N * K, &rc);
+            if (!w) return rc;
+            if ((rc = repack_conv3(w, dst, N, Cin, st))) return rc;
+        } else {   // [N][15] -> [N][16], zero padded
+            const float* w = h->params.get(k + ".weight", (int64_t)N * (K - 1), &rc);
+            if (!w) return rc;
+            EGR_CUDA_OK(cudaMemsetAsync(dst, 0, sizeof(float) * N * K, st));
+            EGR_CUDA_OK(cudaMemcpy2DAsync(dst, sizeof(float) * K, w, sizeof(float) * (K - 1), sizeof(float) * (K - 1), N,
+                                          cudaMemcpyDeviceToDevice, st));
+        }
+        const float* b = h->params.get(k + ".bias", N, &rc);
+        if (!b) return rc;
+        EGR_CUDA_OK(cudaMemcpyAsync(m.bias + (int64_t)s * N, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    }
+    if (h->prec == EGR_PREC_BF16) {
+        if (int rc = h->pool.alloc(&m.bf16, (int64_t)sets * N * K)) return rc;
+        if (int rc = cast_bf16(m.f32, m.bf16, (int64_t)sets * N * K, st)) return rc;
+    }
+    return EGR_OK;
+}
+
+// transposed fp32 copy [K][N] of parameter "<key>.weight" ([N][K])
+int make_T(egr_mvfex* h, const std::string& key, int N, int K, const float** out, cudaStream_t st) {
+    int rc = EGR_OK;
+    const float* w = h->params.get(key + ".weight", (int64_t)N * K, &rc);
+    if (!w) return rc;
+    float* t = nullptr;
+    if ((rc = h->pool.alloc(&t, (int64_t)N * K))) return rc;
+    if ((rc = transpose2d(w, t, N, K, st))) return rc;
+    *out = t;
+    return EGR_OK;
+}
+int get_vec(egr_mvfex* h, const std::string& key, int n, const float** out) {
+    int rc = EGR_OK;
+    *out = h->params.get(key, n, &rc);
+    return rc;
+}
+
+int build_layer(egr_mvfex* h, const std::string& p, const std::string& refiner, LayerW& L, cudaStream_t st) {
+    const int E = EMB, V = h->V;
+    int rc;
+#define T_(field, name, N, K) if ((rc = make_T(h, p + name, N, K, &L.field, st))) return rc
+#define V_(field, name, n) if ((rc = get_vec(h, p + name, n, &L.field))) return rc
+    T_(so_T, ".cross_attn.sampling_offsets", TOK_NH * TOK_P * 2, E);   V_(so_b, ".cross_attn.sampling_offsets.bias", TOK_NH * TOK_P * 2);
+    T_(aw_T, ".cross_attn.attention_weights", TOK_NH * TOK_P, E);      V_(aw_b, ".cross_attn.attention_weights.bias", TOK_NH * TOK_P);
+    T_(op_T, ".cross_attn.output_proj", E, E);                         V_(op_b, ".cross_attn.output_proj.bias", E);
+    T_(fuse_T, ".fuse_mlp", E, V * E);                                  V_(fuse_b, ".fuse_mlp.bias", E);
+    V_(lnc_w, ".norm_cross.weight", E);                                 V_(lnc_b, ".norm_cross.bias", E);
+    T_(q_T, ".spatial_attn.q_proj", E, E);                              V_(q_b, ".spatial_attn.q_proj.bias", E);
+    T_(k_T, ".spatial_attn.k_proj", E, E);                              V_(k_b, ".spatial_attn.k_proj.bias", E);
+    T_(v_T, ".spatial_attn.v_proj", E, E);                              V_(v_b, ".spatial_attn.v_proj.bias", E);
+    T_(o_T, ".spatial_attn.out_proj", E, E);                            V_(o_b, ".spatial_attn.out_proj.bias", E);
+    V_(lns_w, ".norm_spatial.weight", E);                               V_(lns_b, ".norm_spatial.bias", E);
+    T_(f1_T, ".ffn.layers.0.0", TOK_FF, E);                             V_(f1_b, ".ffn.layers.0.0.bias", TOK_FF);
+    T_(f2_T, ".ffn.layers.1", E, TOK_FF);                               V_(f2_b, ".ffn.layers.1.bias", E);
+    V_(lnf_w, ".norm_ffn.weight", E);                                   V_(lnf_b, ".norm_ffn.bias", E);
+#undef T_
+#undef V_
+    // folded memory projection: mfold_T [128][E] = Wp^T · Wv^T ; ptab [V][HW][E] = (pos + bp) · Wv^T + bv
+    const float *Wv, *bv, *Wp, *bp, *pos;
+    if ((rc = get_vec(h, p + ".cross_attn.value_proj.weight", E * E, &Wv))) return rc;
+    if ((rc = get_vec(h, p + ".cross_attn.value_proj.bias", E, &bv))) return rc;
+    if ((rc = get_vec(h, refiner + ".frame_feat_multi_view_proj.weight", E * FC, &Wp))) return rc;
+    if ((rc = get_vec(h, refiner + ".frame_feat_multi_view_proj.bias", E, &bp))) return rc;
+    if ((rc = get_vec(h, refiner + ".frame_feat_multi_view_pos_embed", (int64_t)V * FHW * E, &pos))) return rc;
+    float *WvT, *WpT, *mf, *pp, *pt;
+    if ((rc = h->pool.alloc(&WvT, E * E))) return rc;
+    if ((rc = h->pool.alloc(&WpT, FC * E))) return rc;
+    if ((rc = h->pool.alloc(&mf, FC * E))) return rc;
+    if ((rc = h->pool.alloc(&pp, (int64_t)V * FHW * E))) return rc;
+    if ((rc = h->pool.alloc(&pt, (int64_t)V * FHW * E))) return rc;
+    if ((rc = transpose2d(Wv, WvT, E, E, st))) return rc;
+    if ((rc = transpose2d(Wp, WpT, E, FC, st))) return rc;          // [E][128] -> [128][E]
+    if ((rc = small_matmul(WpT, WvT, nullptr, mf, FC, E, E, st))) return rc;
+    if ((rc = add_rowvec(pos, bp, pp, (int64_t)V * FHW, E, st))) return rc;
+    if ((rc = small_matmul(pp, WvT, bv, pt, V * FHW, E, E, st))) return rc;
+    L.mfold_T = mf;
+    L.ptab = pt;
+    L.bfold = nullptr;
+    return EGR_OK;
+}
+
+struct Bufs {
+    void *Xh, *Xown, *h1a, *a1, *b1, *c1, *z, *ff, *r1a, *refn, *hmT, *xT, *h1t, *t1;
+    float *q1, *anch, *maxv;
+    uint8_t* valid;
+};
+
+// carve the workspace for B frames and G refiner groups (G = V for the full forward, 1 for one refiner)
+int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, void* base, int64_t cap, Bufs* o) {
+    const int64_t s = (h->prec == EGR_PREC_BF16) ? 2 : 4;
+    const int V = h->V, J = h->J;
+    const int Gh = with_heads ? (V > G ? V : G) : G;   // heads run over all views
+    Carver c(base, cap);
+    Bufs b{};
+    b.Xh = c.take((int64_t)V * B * FHW * FC * s);
+    b.Xown = own_copy ? c.take((int64_t)G * B * FHW * FC * s) : nullptr;
+    b.h1a = with_heads ? c.take((int64_t)V * B * FHW * FC * s) : nullptr;
+    b.a1 = c.take((int64_t)G * B * FHW * 256 * s);
+    b.b1 = c.take((int64_t)Gh * B * 1024 * 512 * s);
+    b.c1 = c.take((int64_t)Gh * B * 1024 * 256 * s);
+    b.z = c.take((int64_t)Gh * B * 1024 * 128 * s);
+    b.ff = c.take((int64_t)G * B * 1024 * 128 * s);
+    b.r1a = c.take((int64_t)G * B * 1024 * 128 * s);
+    b.refn = c.take((int64_t)G * B * FHW * FC * s);
+    b.hmT = c.take((int64_t)Gh * B * J * FHW * s);
+    b.xT = c.take((int64_t)G * B * NPOS * 16 * s);
+    b.h1t = c.take((int64_t)G * B * NPOS * 64 * s);
+    b.t1 = c.take((int64_t)G * B * NPOS * 128 * s);
+    b.q1 = (float*)c.take((int64_t)G * B * J * EMB * 4);
+    b.anch = (float*)c.take((int64_t)B * V * J * 2 * 4);
+    b.maxv = (float*)c.take((int64_t)B * V * J * 4);
+    b.valid = (uint8_t*)c.take((int64_t)B * V * J);
+    if (o) *o = b;
+    return c.off + 256;
+}
+
+// the refiner chain for G groups whose weights start at refiner r0
+int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* Xown, const float* bfb, int64_t bfb_bs,
+                 int64_t bfb_gs, const float* anchors, const uint8_t* valid, float* hm_refined, int64_t hm_bs,
+                 int64_t hm_gs, float* feat_refined, int64_t ft_bs, int64_t ft_gs, cudaStream_t st) {
+    const int prec = h->prec, J = h->J;
+    const int bf = (prec == EGR_PREC_BF16);
+    int rc;
+    GemmDesc d;
+    // Q1a: relu(heatmap_proj.0(heatmap))  [G][B*J][4096] -> [G][B*J][256] fp32
+    d = GemmDesc();
+    d.A = w.hmT; d.lda = FHW; d.M = B * J; d.D = w.q1; d.ldd = EMB; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = (int64_t)B * J * FHW; d.d_gs = (int64_t)B * J * EMB;
+    if ((rc = run_gemm(d, h->hp0, r0, prec, /*out_f32=*/true, st))) return rc;
+    // Q1 rest + A1 A2 A3 + post_norm
+    MvfTokenArgs ta{};
+    ta.B = B; ta.V = h->V; ta.J = J; ta.H = FH; ta.W = FW; ta.r0 = r0; ta.G = G;
+    ta.q1 = w.q1; ta.bfb = bfb; ta.bfb_bs = bfb_bs; ta.bfb_gs = bfb_gs; ta.bfb_hw = 64;
+    ta.anchors = anchors; ta.valid = valid; ta.X = w.Xh; ta.xT = w.xT; ta.w = h->d_tokw;
+    if ((rc = launch_mvf_tokens(ta, bf, st))) return rc;
+    // T1: 1x1(15->64) ReLU, then the 1x1(64->128) commuted in front of the bilinear x2 (both linear)
+    d = GemmDesc();
+    d.A = w.xT; d.lda = 16; d.M = B * NPOS; d.D = w.h1t; d.ldd = 64; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = (int64_t)B * NPOS * 16; d.d_gs = (int64_t)B * NPOS * 64;
+    {
+        GemmDesc t = d; t.N = 64; t.K = 16; t.W = h->t1_0.f32 + (int64_t)r0 * 64 * 16; t.bias = h->t1_0.bias + r0 * 64;
+        t.w_gs = 64 * 16; t.b_gs = 64;
+        if ((rc = gemm_simt(t, bf, bf, st))) return rc;
+        t = GemmDesc();
+        t.A = w.h1t; t.lda = 64; t.M = B * NPOS; t.D = w.t1; t.ldd = 128; t.epi = EPI_NONE; t.N = 128; t.K = 64;
+        t.groups = G; t.a_gs = (int64_t)B * NPOS * 64; t.d_gs = (int64_t)B * NPOS * 128;
+        t.W = h->t1_3.f32 + (int64_t)r0 * 128 * 64; t.bias = h->t1_3.bias + r0 * 128; t.w_gs = 128 * 64; t.b_gs = 128;
+        if ((rc = gemm_simt(t, bf, bf, st))) return rc;
+    }
+    // F1a: 1x1(128->256) ReLU @64x64
+    d = GemmDesc();
+    d.A = Xown; d.lda = FC; d.M = B * FHW; d.D = w.a1; d.ldd = 256; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * FHW * 256;
+    if ((rc = run_gemm(d, h->f1_0, r0, prec, false, st))) return rc;
+    // F1b: 3x3 s2 (256->512) ReLU -> 32x32
+    d = GemmDesc();
+    d.A = w.a1; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = 256; d.M = B * 1024; d.D = w.b1; d.ldd = 512;
+    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * 256; d.d_gs = (int64_t)B * 1024 * 512;
+    if ((rc = run_gemm(d, h->f1_2, r0, prec, false, st))) return rc;
+    // F1c: 1x1(512->128) ReLU, fused with "+ offset_pred": + relu(up2(t1))   (:715 offset_pred + frame_feat)
+    d = GemmDesc();
+    d.A = w.b1; d.lda = 512; d.M = B * 1024; d.D = w.ff; d.ldd = 128; d.epi = EPI_RELU_ADDUP; d.aux = w.t1;
+    d.Hout = 32; d.Wout = 32; d.groups = G; d.a_gs = (int64_t)B * 1024 * 512; d.d_gs = (int64_t)B * 1024 * 128;
+    d.aux_gs = (int64_t)B * NPOS * 128;
+    if ((rc = run_gemm(d, h->f1_4, r0, prec, false, st))) return rc;
+    // R1a: 1x1(128->128) ReLU @32x32 ; R1b: second 1x1 commuted in front of the upsample
+    d = GemmDesc();
+    d.A = w.ff; d.lda = 128; d.M = B * 1024; d.D = w.r1a; d.ldd = 128; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128;
+    if ((rc = run_gemm(d, h->r1_0, r0, prec, false, st))) return rc;
+    d.A = w.r1a; d.D = w.z; d.epi = EPI_NONE;
+    if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st))) return rc;
+    // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output + channels-last copy for H2
+    if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, st))) return rc;
+    // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
+    d = GemmDesc();
+    d.A = w.refn; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = B * 1024; d.D = w.b1; d.ldd = 256;
+    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256;
+    if ((rc = run_gemm(d, h->h2_0, r0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.b1; d.lda = 256; d.M = B * 1024; d.D = w.c1; d.ldd = 256; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 256;
+    if ((rc = run_gemm(d, h->h2_2, r0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.c1; d.lda = 256; d.M = B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
+    d.groups = G; d.a_gs = (int64_t)B * 1024 * 256; d.d_gs = (int64_t)B * 1024 * 128;
+    if ((rc = run_gemm(d, h->h2_5, r0, prec, false, st))) return rc;
+    int wsel[4] = {r0, r0 + 1, r0 + 2, r0 + 3};
+    if ((rc = head_up_conv(w.z, bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
+        return rc;
+    return EGR_OK;
+}
+
+void note(egr_mvfex* h, const char* name, void* p, int64_t bytes) { h->dbg[name] = std::make_pair(p, bytes); }
+
+void note_all(egr_mvfex* h, const Bufs& w, int B, int G) {
+    const int64_t s = (h->prec == EGR_PREC_BF16) ? 2 : 4;
+    note(h, "Xh", w.Xh, (int64_t)h->V * B * FHW * FC * s);
+    note(h, "q1", w.q1, (int64_t)G * B * h->J * EMB * 4);
+    note(h, "xT", w.xT, (int64_t)G * B * NPOS * 16 * s);
+    note(h, "t1", w.t1, (int64_t)G * B * NPOS * 128 * s);
+    note(h, "ff", w.ff, (int64_t)G * B * 1024 * 128 * s);
+    note(h, "a1", w.a1, (int64_t)G * B * FHW * 256 * s);
+    note(h, "hmT", w.hmT, (int64_t)G * B * h->J * FHW * s);
+    note(h, "anchors", w.anch, (int64_t)B * h->V * h->J * 8);
+    note(h, "valid", w.valid, (int64_t)B * h->V * h->J);
+}
+
+}  // namespace
+
+extern "C" int egr_set_option(const char* key, int value) {
+    if (key && std::string(key) == "tc") { g_opt_tc = value ? 1 : 0; return EGR_OK; }
+    return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
+}
+
+extern "C" int egr_mvfex_create(int num_views, int num_heatmap, float heatmap_threshold, int precision, egr_mvfex** out) {
+    EGR_CHECK(out, EGR_ERR_INVALID, "mvfex_create: null out");
+    EGR_CHECK(num_views == 2 || num_views == 4, EGR_ERR_UNSUPPORTED,
+              "mvfex: num_views=%d (shipped configs use 4, or 2 for stereo-front)", num_views);
+    EGR_CHECK(num_heatmap == 15, EGR_ERR_UNSUPPORTED, "mvfex: num_heatmap=%d (shipped configs use 15)", num_heatmap);
+    EGR_CHECK(precision == EGR_PREC_FP32 || precision == EGR_PREC_BF16, EGR_ERR_INVALID, "mvfex: precision %d", precision);
+    if (int rc = require_device()) return rc;
+    egr_mvfex* h = new egr_mvfex();
+    h->V = num_views; h->J = num_heatmap; h->thr = heatmap_threshold; h->prec = precision;
+    h->head_sets = (num_views == 2) ? 1 : 2;
+    *out = h;
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_destroy(egr_mvfex* h) {
+    if (!h) return EGR_OK;
+    cudaDeviceSynchronize();
+    h->pool.release();
+    delete h;
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_set_param(egr_mvfex* h, const char* key, const float* ptr, int64_t numel) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_set_param: null handle");
+    h->packed = false;
+    return h->params.set(key, ptr, numel);
+}
+
+extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_prepack: null handle");
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    EGR_CUDA_OK(cudaStreamSynchronize(st));
+    h->pool.release();
+    h->packed = false;
+    const int V = h->V, J = h->J;
+    int rc;
+    if (h->prec == EGR_PREC_BF16 && g_opt_tc) {
+        if ((rc = gemm_tc_init())) return rc;
+    }
+    auto head = [&](const char* sub) { return [sub](int s) { return std::string(kHead[s]) + sub; }; };
+    auto ref = [&](const char* sub) { return [sub](int s) { return std::string(kRefiner4[s]) + sub; }; };
+    // a standalone HeatmapMVF registers one refiner only; the full module registers heads + all refiners
+    h->has_heads = h->params.map.count(std::string(kHead[0]) + ".0.weight") > 0;
+    bool any = h->has_heads;
+    for (int r = 0; r < 4; ++r) {
+        h->has_ref[r] = r < V && h->params.map.count(std::string(kRefiner4[r]) + ".heatmap_proj.0.weight") > 0;
+        any = any || h->has_ref[r];
+    }
+    EGR_CHECK(any, EGR_ERR_STATE, "mvfex_prepack: no parameters registered");
+    bool hp[2] = {h->has_heads, h->has_heads};
+    const bool* rp = h->has_ref;
+    if ((rc = make_wmat(h, h->h1_0, h->head_sets, 128, 128, W_PLAIN, head(".0"), hp, st))) return rc;
+    if ((rc = make_wmat(h, h->h1_2, h->head_sets, 256, 9 * 128, W_CONV3, head(".2"), hp, st))) return rc;
+    if ((rc = make_wmat(h, h->h1_4, h->head_sets, 256, 256, W_PLAIN, head(".4"), hp, st))) return rc;
+    if ((rc = make_wmat(h, h->h1_7, h->head_sets, 128, 256, W_PLAIN, head(".7"), hp, st))) return rc;
+    if ((rc = h->pool.alloc(&h->h1_9w, (int64_t)h->head_sets * J * 128))) return rc;
+    if ((rc = h->pool.alloc(&h->h1_9b, (int64_t)h->head_sets * J))) return rc;
+    for (int s = 0; s < h->head_sets && h->has_heads; ++s) {
+        const float* w = h->params.get(std::string(kHead[s]) + ".9.weight", J * 128, &rc); if (!w) return rc;
+        const float* b = h->params.get(std::string(kHead[s]) + ".9.bias", J, &rc); if (!b) return rc;
+        EGR_CUDA_OK(cudaMemcpyAsync(h->h1_9w + s * J * 128, w, sizeof(float) * J * 128, cudaMemcpyDeviceToDevice, st));
+        EGR_CUDA_OK(cudaMemcpyAsync(h->h1_9b + s * J, b, sizeof(float) * J, cudaMemcpyDeviceToDevice, st));
+    }
+    if ((rc = make_wmat(h, h->hp0, V, EMB, FHW, W_PLAIN, ref(".heatmap_proj.0"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->f1_0, V, 256, 128, W_PLAIN, ref(".frame_feat_proj_layers.0"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->f1_2, V, 512, 9 * 256, W_CONV3, ref(".frame_feat_proj_layers.2"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->f1_4, V, 128, 512, W_PLAIN, ref(".frame_feat_proj_layers.4"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->t1_0, V, 64, 16, W_PAD16, ref(".head_layers.0.head.0"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->t1_3, V, 128, 64, W_PLAIN, ref(".head_layers.0.head.3"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->r1_0, V, 128, 128, W_PLAIN, ref(".frame_feat_refined_proj_layers.0.0"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->r1_3, V, 128, 128, W_PLAIN, ref(".frame_feat_refined_proj_layers.0.3"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->h2_0, V, 256, 9 * 128, W_CONV3, ref(".conv_heatmap_layers.0.0"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->h2_2, V, 256, 256, W_PLAIN, ref(".conv_heatmap_layers.0.2"), rp, st))) return rc;
+    if ((rc = make_wmat(h, h->h2_5, V, 128, 256, W_PLAIN, ref(".conv_heatmap_layers.0.5"), rp, st))) return rc;
+    if ((rc = h->pool.alloc(&h->h2_7w, (int64_t)V * J * 128))) return rc;
+    if ((rc = h->pool.alloc(&h->h2_7b, (int64_t)V * J))) return rc;
+    std::vector<MvfTokenW> tok(V);
+    for (int r = 0; r < V; ++r) {
+        if (!h->has_ref[r]) continue;
+        const std::string p = kRefiner4[r];
+        const float* w = h->params.get(p + ".conv_heatmap_layers.0.7.weight", J * 128, &rc); if (!w) return rc;
+        const float* b = h->params.get(p + ".conv_heatmap_layers.0.7.bias", J, &rc); if (!b) return rc;
+        EGR_CUDA_OK(cudaMemcpyAsync(h->h2_7w + r * J * 128, w, sizeof(float) * J * 128, cudaMemcpyDeviceToDevice, st));
+        EGR_CUDA_OK(cudaMemcpyAsync(h->h2_7b + r * J, b, sizeof(float) * J, cudaMemcpyDeviceToDevice, st));
+        MvfTokenW& t = tok[r];
+        if ((rc = make_T(h, p + ".heatmap_proj.2", EMB, EMB, &t.hp2_T, st))) return rc;
+        if ((rc = get_vec(h, p + ".heatmap_proj.2.bias", EMB, &t.hp2_b))) return rc;
+        if ((rc = make_T(h, p + ".fc_bfb", EMB, 512, &t.bfb_T, st))) return rc;
+        if ((rc = get_vec(h, p + ".fc_bfb.bias", EMB, &t.bfb_b))) return rc;
+        if ((rc = get_vec(h, p + ".joint_query_embed.weight", J * EMB, &t.jq))) return rc;
+        if ((rc = make_T(h, p + ".fc_query.0", EMB, EMB, &t.fcq_T, st))) return rc;
+        if ((rc = get_vec(h, p + ".fc_query.0.bias", EMB, &t.fcq_b))) return rc;
+        if ((rc = get_vec(h, p + ".post_norm.0.weight", EMB, &t.pn_w))) return rc;
+        if ((rc = get_vec(h, p + ".post_norm.0.bias", EMB, &t.pn_b))) return rc;
+        if ((rc = build_layer(h, p + ".transformer_layers.0", p, t.layer, st))) return rc;
+    }
+    if ((rc = h->pool.alloc(&h->d_tokw, V))) return rc;
+    EGR_CUDA_OK(cudaMemcpyAsync(h->d_tokw, tok.data(), sizeof(MvfTokenW) * V, cudaMemcpyHostToDevice, st));
+    EGR_CUDA_OK(cudaStreamSynchronize(st));
+    h->packed = true;
+    return EGR_OK;
+}
+
+extern "C" int64_t egr_mvfex_workspace_bytes(egr_mvfex* h, int B) {
+    if (!h || B <= 0) return 0;
+    return carve(h, B, h->V, true, true, nullptr, 0, nullptr);
+}
+
+extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const float* bfb, const float* heatmap_for_anchor,
+                                 float* hm_init, float* hm_refined, float* feat_refined, float* anchors_2d,
+                                 uint8_t* anchors_valid, void* workspace, int64_t workspace_bytes, void* stream) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_forward: null handle");
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(h->packed, EGR_ERR_STATE, "mvfex_forward: parameters changed or never packed; call egr_mvfex_prepack");
+    EGR_CHECK(B > 0 && feat && bfb && hm_init && hm_refined && feat_refined && workspace, EGR_ERR_INVALID,
+              "mvfex_forward: null pointer / empty batch");
+    for (int r = 0; r < h->V; ++r)
+        EGR_CHECK(h->has_heads && h->has_ref[r], EGR_ERR_STATE, "mvfex_forward: parameters of the init heads / refiner %d were not registered", r);
+    Bufs w;
+    const int64_t need = carve(h, B, h->V, true, false, workspace, workspace_bytes, &w);
+    EGR_CHECK(need <= workspace_bytes, EGR_ERR_STATE, "mvfex_forward: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = h->V, J = h->J, prec = h->prec, bf = (prec == EGR_PREC_BF16);
+    int rc;
+    // S0: NCHW fp32 -> view-major channels-last staging copy
+    if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, bf, st))) return rc;
+    // H1: init heads, one group per weight set (front: views 0-1, back: views 2-3), two views per group
+    const int G1 = h->head_sets, vpg = V / G1;
+    GemmDesc d;
+    d.A = w.Xh; d.lda = FC; d.M = vpg * B * FHW; d.D = w.h1a; d.ldd = 128; d.epi = EPI_RELU;
+    d.groups = G1; d.a_gs = d.d_gs = (int64_t)vpg * B * FHW * FC;
+    if ((rc = run_gemm(d, h->h1_0, 0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.h1a; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = vpg * B * 1024; d.D = w.b1; d.ldd = 256;
+    d.epi = EPI_RELU; d.groups = G1; d.a_gs = (int64_t)vpg * B * FHW * FC; d.d_gs = (int64_t)vpg * B * 1024 * 256;
+    if ((rc = run_gemm(d, h->h1_2, 0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.b1; d.lda = 256; d.M = vpg * B * 1024; d.D = w.c1; d.ldd = 256; d.epi = EPI_RELU;
+    d.groups = G1; d.a_gs = d.d_gs = (int64_t)vpg * B * 1024 * 256;
+    if ((rc = run_gemm(d, h->h1_4, 0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.c1; d.lda = 256; d.M = vpg * B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
+    d.groups = G1; d.a_gs = (int64_t)vpg * B * 1024 * 256; d.d_gs = (int64_t)vpg * B * 1024 * 128;
+    if ((rc = run_gemm(d, h->h1_7, 0, prec, false, st))) return rc;
+    int wsel[4] = {0, 0, 1, 1};
+    if (G1 == 1) wsel[2] = wsel[3] = 0;
+    if ((rc = head_up_conv(w.z, bf, h->h1_9w, h->h1_9b, wsel, B, V, 32, 32, FC, J, hm_init, (int64_t)V * J * FHW,
+                           (int64_t)J * FHW, w.hmT, st))) return rc;
+    // D1: anchors from heatmap_for_anchor when given (:293-296), else from the init heatmap
+    const float* src = heatmap_for_anchor ? heatmap_for_anchor : hm_init;
+    float* anch = anchors_2d ? anchors_2d : w.anch;
+    uint8_t* val = anchors_valid ? anchors_valid : w.valid;
+    if ((rc = egr_decode_argmax(src, (int64_t)B * V, J, FH, FW, h->thr, 1, anch, w.maxv, val, nullptr, stream))) return rc;
+    // refiners (one group per view)
+    rc = run_refiners(h, B, V, 0, w, w.Xh, bfb, (int64_t)V * 512 * 64, (int64_t)512 * 64, anch, val, hm_refined,
+                      (int64_t)V * J * FHW, (int64_t)J * FHW, feat_refined, (int64_t)V * FC * FHW, (int64_t)FC * FHW, st);
+    if (rc) return rc;
+    note_all(h, w, B, V);
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, const float* frame_feat,
+                                         const float* feat_mv, const float* anchors_2d, const uint8_t* anchors_valid,
+                                         const float* bfb, float* hm_refined, float* feat_refined, void* workspace,
+                                         int64_t workspace_bytes, void* stream) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_refiner_forward: null handle");
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(h->packed, EGR_ERR_STATE, "mvfex_refiner_forward: call egr_mvfex_prepack first");
+    EGR_CHECK(r >= 0 && r < h->V, EGR_ERR_INVALID, "mvfex_refiner_forward: refiner %d of %d", r, h->V);
+    EGR_CHECK(h->has_ref[r], EGR_ERR_STATE, "mvfex_refiner_forward: parameters of refiner %d were not registered", r);
+    EGR_CHECK(B > 0 && heatmap && frame_feat && feat_mv && anchors_2d && anchors_valid && bfb && hm_refined &&
+              feat_refined && workspace, EGR_ERR_INVALID, "mvfex_refiner_forward: null pointer / empty batch");
+    Bufs w;
+    const int64_t need = carve(h, B, 1, false, true, workspace, workspace_bytes, &w);
+    EGR_CHECK(need <= workspace_bytes, EGR_ERR_STATE, "mvfex_refiner_forward: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int bf = (h->prec == EGR_PREC_BF16), J = h->J;
+    int rc;
+    if ((rc = nchw_to_nhwc(feat_mv, w.Xh, B, h->V, FC, FHW, bf, st))) return rc;
+    if ((rc = nchw_to_nhwc(frame_feat, w.Xown, B, 1, FC, FHW, bf, st))) return rc;
+    if ((rc = cast_act(heatmap, w.hmT, bf, (int64_t)B * J * FHW, st))) return rc;
+    rc = run_refiners(h, B, 1, r, w, w.Xown, bfb, (int64_t)512 * 64, 0, anchors_2d, anchors_valid, hm_refined,
+                      (int64_t)J * FHW, 0, feat_refined, (int64_t)FC * FHW, 0, st);
+    if (rc) return rc;
+    note_all(h, w, B, 1);
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_debug_buffer(egr_mvfex* h, const char* name, void** ptr, int64_t* bytes) {
+    EGR_CHECK(h && name && ptr && bytes, EGR_ERR_INVALID, "debug_buffer: null argument");
+    auto it = h->dbg.find(name);
+    EGR_CHECK(it != h->dbg.end(), EGR_ERR_INVALID, "debug_buffer: unknown buffer '%s'", name);
+    *ptr = it->second.first;
+    *bytes = it->second.second;
+    return EGR_OK;
+}

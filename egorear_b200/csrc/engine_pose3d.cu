@@ -1,0 +1,299 @@
+// pose3d engine: EgoPoseFormerPose3D.forward (estimator/egoposeformer_mvf_ex.py:422-452), conv-MLP proposal branch.
+//   P2  conv_frame_feat (:229-239) + mlp_pred (:241-253) on frame_feats_final  -> proposal [B,16,3]
+//   P3  fisheye reprojection (in the token kernel)   P1+P4  feat_proj folded into the deformable sampling,
+//   3 transformer layers + post_norm + reg_mlp       (token kernel)
+// Activations are channels-last, view-major ([V][B][H*W][C]); the flatten "(b v) c h w -> b (v c h w)" of :317
+// becomes a K-split GEMM over the 4 per-view [B][64*128] blocks with the weight columns permuted once at prepack.
+#include "engine_common.cuh"
+#include "token_kernels.cuh"
+
+namespace egr {
+CamCalib make_calib(int cam_id, const float* calib_host);
+}
+using namespace egr;
+
+constexpr int PH = 64, PW = 64, PHW = 4096, PC = 128, PE = 128;
+
+struct egr_pose3d {
+    int V = 4, J = 16, L = 3, cam_model = 0, use_init = 1, prec = EGR_PREC_FP32;
+    bool packed = false;
+    ParamTable params;
+    DevPool pool;
+    CamCalib cam[4];
+    int cam_id[4] = {0, 1, 2, 3};
+    WMat c0, c2, c5, c7;          // conv_frame_feat.{0,2,5,7}
+    WMat m0, m1, m2;              // mlp_pred.0.0 (permuted), mlp_pred.1.0, mlp_pred.2
+    PoseTokenW* d_w = nullptr;
+    std::unordered_map<std::string, std::pair<void*, int64_t>> dbg;
+};
+
+namespace {
+
+int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3 2 mlp-permute*/, const std::string& key,
+                cudaStream_t st) {
+    m.N = N; m.K = K; m.sets = 1;
+    int rc = EGR_OK;
+    if ((rc = h->pool.alloc(&m.f32, (int64_t)N * K))) return rc;
+    if ((rc = h->pool.alloc(&m.bias, N))) return rc;
+    const float* w = h->params.get(key + ".weight", (int64_t)N * K, &rc);
+    if (!w) return rc;
+    if (kind == 0) EGR_CUDA_OK(cudaMemcpyAsync(m.f32, w, sizeof(float) * N * K, cudaMemcpyDeviceToDevice, st));
+    else if (kind == 1) { if ((rc = repack_conv3(w, m.f32, N, K / 9, st))) return rc; }
+    else { if ((rc = permute_mlp_weight(w, m.f32, N, h->V, PC, 64, st))) return rc; }
+    const float* b = h->params.get(key + ".bias", N, &rc);
+    if (!b) return rc;
+    EGR_CUDA_OK(cudaMemcpyAsync(m.bias, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    if (h->prec == EGR_PREC_BF16) {
+        if ((rc = h->pool.alloc(&m.bf16, (int64_t)N * K))) return rc;
+        if ((rc = cast_bf16(m.f32, m.bf16, (int64_t)N * K, st))) return rc;
+    }
+    return EGR_OK;
+}
+
+int p_make_T(egr_pose3d* h, const std::string& key, int N, int K, const float** out, cudaStream_t st) {
+    int rc = EGR_OK;
+    const float* w = h->params.get(key + ".weight", (int64_t)N * K, &rc);
+    if (!w) return rc;
+    float* t = nullptr;
+    if ((rc = h->pool.alloc(&t, (int64_t)N * K))) return rc;
+    if ((rc = transpose2d(w, t, N, K, st))) return rc;
+    *out = t;
+    return EGR_OK;
+}
+int p_vec(egr_pose3d* h, const std::string& key, int n, const float** out) {
+    int rc = EGR_OK;
+    *out = h->params.get(key, n, &rc);
+    return rc;
+}
+
+int p_build_layer(egr_pose3d* h, const std::string& p, LayerW& L, cudaStream_t st) {
+    const int E = PE, V = h->V;
+    int rc;
+#define T_(field, name, N, K) if ((rc = p_make_T(h, p + name, N, K, &L.field, st))) return rc
+#define V_(field, name, n) if ((rc = p_vec(h, p + name, n, &L.field))) return rc
+    T_(so_T, ".cross_attn.sampling_offsets", TOK_NH * TOK_P * 2, E);   V_(so_b, ".cross_attn.sampling_offsets.bias", TOK_NH * TOK_P * 2);
+    T_(aw_T, ".cross_attn.attention_weights", TOK_NH * TOK_P, E);      V_(aw_b, ".cross_attn.attention_weights.bias", TOK_NH * TOK_P);
+    T_(op_T, ".cross_attn.output_proj", E, E);                         V_(op_b, ".cross_attn.output_proj.bias", E);
+    T_(fuse_T, ".fuse_mlp", E, V * E);                                  V_(fuse_b, ".fuse_mlp.bias", E);
+    V_(lnc_w, ".norm_cross.weight", E);                                 V_(lnc_b, ".norm_cross.bias", E);
+    T_(q_T, ".spatial_attn.q_proj", E, E);                              V_(q_b, ".spatial_attn.q_proj.bias", E);
+    T_(k_T, ".spatial_attn.k_proj", E, E);                              V_(k_b, ".spatial_attn.k_proj.bias", E);
+    T_(v_T, ".spatial_attn.v_proj", E, E);                              V_(v_b, ".spatial_attn.v_proj.bias", E);
+    T_(o_T, ".spatial_attn.out_proj", E, E);                            V_(o_b, ".spatial_attn.out_proj.bias", E);
+    V_(lns_w, ".norm_spatial.weight", E);                               V_(lns_b, ".norm_spatial.bias", E);
+    T_(f1_T, ".ffn.layers.0.0", TOK_FF, E);                             V_(f1_b, ".ffn.layers.0.0.bias", TOK_FF);
+    T_(f2_T, ".ffn.layers.1", E, TOK_FF);                               V_(f2_b, ".ffn.layers.1.bias", E);
+    V_(lnf_w, ".norm_ffn.weight", E);                                   V_(lnf_b, ".norm_ffn.bias", E);
+#undef T_
+#undef V_
+    // fold feat_proj (P1, :144/:431) into the sampling: mfold_T [128][E] = Wf^T · Wv^T, bfold = Wv·bf + bv
+    const float *Wv, *bv, *Wf, *bfp;
+    if ((rc = p_vec(h, p + ".cross_attn.value_proj.weight", E * E, &Wv))) return rc;
+    if ((rc = p_vec(h, p + ".cross_attn.value_proj.bias", E, &bv))) return rc;
+    if ((rc = p_vec(h, "feat_proj.weight", E * PC, &Wf))) return rc;
+    if ((rc = p_vec(h, "feat_proj.bias", E, &bfp))) return rc;
+    float *WvT, *WfT, *mf, *bfold;
+    if ((rc = h->pool.alloc(&WvT, E * E))) return rc;
+    if ((rc = h->pool.alloc(&WfT, PC * E))) return rc;
+    if ((rc = h->pool.alloc(&mf, PC * E))) return rc;
+    if ((rc = h->pool.alloc(&bfold, E))) return rc;
+    if ((rc = transpose2d(Wv, WvT, E, E, st))) return rc;
+    if ((rc = transpose2d(Wf, WfT, E, PC, st))) return rc;
+    if ((rc = small_matmul(WfT, WvT, nullptr, mf, PC, E, E, st))) return rc;
+    if ((rc = small_matmul(bfp, WvT, bv, bfold, 1, E, E, st))) return rc;
+    L.mfold_T = mf;
+    L.ptab = nullptr;
+    L.bfold = bfold;
+    return EGR_OK;
+}
+
+struct PBufs {
+    void *Xi, *Xf, *p0, *p2, *p3, *p5, *p7;
+    float *m0, *m1, *anch;
+    uint8_t* valid;
+};
+
+int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
+    const int64_t s = (h->prec == EGR_PREC_BF16) ? 2 : 4;
+    const int64_t VB = (int64_t)h->V * B;
+    Carver c(base, cap);
+    PBufs b{};
+    b.Xi = c.take(VB * PHW * PC * s);
+    b.Xf = c.take(VB * PHW * PC * s);
+    b.p0 = c.take(VB * PHW * 64 * s);       // 1x1 128->64 @64x64
+    b.p2 = c.take(VB * 1024 * 128 * s);     // 3x3 s2 64->128 @32x32
+    b.p3 = c.take(VB * 256 * 128 * s);      // maxpool @16x16
+    b.p5 = c.take(VB * 256 * 64 * s);       // 1x1 128->64 @16x16
+    b.p7 = c.take(VB * 64 * 128 * s);       // 3x3 s2 64->128 @8x8
+    b.m0 = (float*)c.take((int64_t)B * 2048 * 4);
+    b.m1 = (float*)c.take((int64_t)B * 128 * 4);
+    b.anch = (float*)c.take(VB * h->J * 2 * 4);
+    b.valid = (uint8_t*)c.take(VB * h->J);
+    if (o) *o = b;
+    return c.off + 256;
+}
+
+}  // namespace
+
+extern "C" int egr_pose3d_create(int num_views, int num_joints, int num_layers, int camera_model,
+                                 int use_pred_heatmap_init, int precision, const float* calib_host, egr_pose3d** out) {
+    EGR_CHECK(out, EGR_ERR_INVALID, "pose3d_create: null out");
+    EGR_CHECK(num_joints == 16, EGR_ERR_UNSUPPORTED, "pose3d: num_joints=%d (shipped configs use 16)", num_joints);
+    EGR_CHECK(num_layers >= 1 && num_layers <= 4, EGR_ERR_UNSUPPORTED, "pose3d: num_former_layers=%d", num_layers);
+    EGR_CHECK(camera_model >= 0 && camera_model <= 5, EGR_ERR_INVALID, "Unknown camera model !");
+    const int need_v = (camera_model <= 1) ? 4 : 2;
+    EGR_CHECK(num_views == need_v, EGR_ERR_INVALID, "pose3d: camera model %d needs num_views == %d", camera_model, need_v);
+    EGR_CHECK(precision == EGR_PREC_FP32 || precision == EGR_PREC_BF16, EGR_ERR_INVALID, "pose3d: precision %d", precision);
+    if (int rc = require_device()) return rc;
+    egr_pose3d* h = new egr_pose3d();
+    h->V = num_views; h->J = num_joints; h->L = num_layers; h->cam_model = camera_model;
+    h->use_init = use_pred_heatmap_init; h->prec = precision;
+    const int first = (camera_model >= 4) ? 2 : 0;   // stereo_back rigs start at back_left
+    for (int v = 0; v < 4; ++v) {
+        h->cam_id[v] = (v < num_views) ? first + v : 0;
+        h->cam[v] = make_calib(h->cam_id[v], calib_host);
+    }
+    *out = h;
+    return EGR_OK;
+}
+
+extern "C" int egr_pose3d_destroy(egr_pose3d* h) {
+    if (!h) return EGR_OK;
+    cudaDeviceSynchronize();
+    h->pool.release();
+    delete h;
+    return EGR_OK;
+}
+
+extern "C" int egr_pose3d_set_param(egr_pose3d* h, const char* key, const float* ptr, int64_t numel) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_set_param: null handle");
+    h->packed = false;
+    return h->params.set(key, ptr, numel);
+}
+
+extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_prepack: null handle");
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    EGR_CUDA_OK(cudaStreamSynchronize(st));
+    h->pool.release();
+    h->packed = false;
+    int rc;
+    if (h->prec == EGR_PREC_BF16 && g_opt_tc) {
+        if ((rc = gemm_tc_init())) return rc;
+    }
+    if ((rc = p_make_wmat(h, h->c0, 64, 128, 0, "conv_frame_feat.0", st))) return rc;
+    if ((rc = p_make_wmat(h, h->c2, 128, 9 * 64, 1, "conv_frame_feat.2", st))) return rc;
+    if ((rc = p_make_wmat(h, h->c5, 64, 128, 0, "conv_frame_feat.5", st))) return rc;
+    if ((rc = p_make_wmat(h, h->c7, 128, 9 * 64, 1, "conv_frame_feat.7", st))) return rc;
+    const int K0 = h->V * PC * 64;
+    if ((rc = p_make_wmat(h, h->m0, K0 / 16, K0, 2, "mlp_pred.0.0", st))) return rc;
+    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st))) return rc;
+    if ((rc = p_make_wmat(h, h->m2, 3 * h->J, K0 / 256, 0, "mlp_pred.2", st))) return rc;
+    PoseTokenW tw{};
+    if ((rc = p_make_T(h, "query_gen_mlp.0", PE, 4, &tw.g0_T, st))) return rc;
+    if ((rc = p_vec(h, "query_gen_mlp.0.bias", PE, &tw.g0_b))) return rc;
+    if ((rc = p_make_T(h, "query_gen_mlp.2", PE, PE, &tw.g2_T, st))) return rc;
+    if ((rc = p_vec(h, "query_gen_mlp.2.bias", PE, &tw.g2_b))) return rc;
+    if ((rc = p_make_T(h, "query_gen_mlp.4", PE, PE, &tw.g4_T, st))) return rc;
+    if ((rc = p_vec(h, "query_gen_mlp.4.bias", PE, &tw.g4_b))) return rc;
+    for (int l = 0; l < h->L; ++l) {
+        const std::string li = std::to_string(l);
+        if ((rc = p_build_layer(h, "layers." + li, tw.layer[l], st))) return rc;
+        if ((rc = p_vec(h, "post_norm." + li + ".weight", PE, &tw.pn_w[l]))) return rc;
+        if ((rc = p_vec(h, "post_norm." + li + ".bias", PE, &tw.pn_b[l]))) return rc;
+        if ((rc = p_make_T(h, "reg_mlp." + li + ".0", PE, PE, &tw.r0_T[l], st))) return rc;
+        if ((rc = p_vec(h, "reg_mlp." + li + ".0.bias", PE, &tw.r0_b[l]))) return rc;
+        if ((rc = p_make_T(h, "reg_mlp." + li + ".2", 3, PE, &tw.r2_T[l], st))) return rc;
+        if ((rc = p_vec(h, "reg_mlp." + li + ".2.bias", 3, &tw.r2_b[l]))) return rc;
+    }
+    if ((rc = h->pool.alloc(&h->d_w, 1))) return rc;
+    EGR_CUDA_OK(cudaMemcpyAsync(h->d_w, &tw, sizeof(PoseTokenW), cudaMemcpyHostToDevice, st));
+    EGR_CUDA_OK(cudaStreamSynchronize(st));
+    h->packed = true;
+    return EGR_OK;
+}
+
+extern "C" int64_t egr_pose3d_workspace_bytes(egr_pose3d* h, int B) {
+    if (!h || B <= 0) return 0;
+    return p_carve(h, B, nullptr, 0, nullptr);
+}
+
+extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init, const float* feats_final,
+                                  const float* coord_trans_mat, float* preds, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_forward: null handle");
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(h->packed, EGR_ERR_STATE, "pose3d_forward: parameters changed or never packed; call egr_pose3d_prepack");
+    EGR_CHECK(B > 0 && feats_init && feats_final && preds && workspace, EGR_ERR_INVALID, "pose3d_forward: null pointer");
+    const int is_rw = (h->cam_model & 1);
+    EGR_CHECK(!is_rw || coord_trans_mat, EGR_ERR_INVALID, "pose3d_forward: ego4view_rw* needs coord_trans_mat [B,V,4,4] fp32");
+    PBufs w;
+    const int64_t need = p_carve(h, B, workspace, workspace_bytes, &w);
+    EGR_CHECK(need <= workspace_bytes, EGR_ERR_STATE, "pose3d_forward: workspace %lld B < required %lld B",
+              (long long)workspace_bytes, (long long)need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = h->V, J = h->J, prec = h->prec, bf = (prec == EGR_PREC_BF16);
+    const int VB = V * B;
+    int rc;
+    // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
+    const float* sampled = h->use_init ? feats_init : feats_final;
+    if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, bf, st))) return rc;
+    const void* Xs = w.Xf;
+    if (sampled != feats_final) {
+        if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bf, st))) return rc;
+        Xs = w.Xi;
+    }
+    // P2 conv_frame_feat
+    GemmDesc d;
+    d.A = w.Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU;
+    if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.p0; d.amode = A_CONV3S2; d.Hin = 64; d.Win = 64; d.Cin = 64; d.M = VB * 1024; d.D = w.p2; d.ldd = 128; d.epi = EPI_RELU;
+    if ((rc = run_gemm(d, h->c2, 0, prec, false, st))) return rc;
+    if ((rc = maxpool2_nhwc(w.p2, w.p3, bf, VB, 32, 32, 128, st))) return rc;
+    d = GemmDesc();
+    d.A = w.p3; d.lda = 128; d.M = VB * 256; d.D = w.p5; d.ldd = 64; d.epi = EPI_RELU;
+    if ((rc = run_gemm(d, h->c5, 0, prec, false, st))) return rc;
+    d = GemmDesc();
+    d.A = w.p5; d.amode = A_CONV3S2; d.Hin = 16; d.Win = 16; d.Cin = 64; d.M = VB * 64; d.D = w.p7; d.ldd = 128; d.epi = EPI_RELU;
+    if ((rc = run_gemm(d, h->c7, 0, prec, false, st))) return rc;
+    // mlp_pred: K-split over the V view blocks of p7 ([V][B][64*128])
+    d = GemmDesc();
+    d.A = w.p7; d.lda = 64 * 128; d.kblk = 64 * 128; d.kblk_stride = (int64_t)B * 64 * 128; d.M = B; d.D = w.m0; d.ldd = h->m0.N;
+    d.epi = EPI_GELU;
+    if ((rc = run_gemm(d, h->m0, 0, prec, /*out_f32=*/true, st))) return rc;
+    {   // the two small Linears stay fp32 SIMT in every precision
+        GemmDesc t;
+        t.A = w.m0; t.lda = h->m1.K; t.M = B; t.N = h->m1.N; t.K = h->m1.K; t.W = h->m1.f32; t.bias = h->m1.bias;
+        t.D = w.m1; t.ldd = h->m1.N; t.epi = EPI_GELU;
+        if ((rc = gemm_simt(t, 0, 0, st))) return rc;
+        t = GemmDesc();
+        t.A = w.m1; t.lda = h->m2.K; t.M = B; t.N = h->m2.N; t.K = h->m2.K; t.W = h->m2.f32; t.bias = h->m2.bias;
+        t.D = preds; t.ldd = h->m2.N; t.epi = EPI_NONE;     // preds[0] = proposal
+        if ((rc = gemm_simt(t, 0, 0, st))) return rc;
+    }
+    // P3 + P4
+    PoseTokenArgs ta{};
+    ta.B = B; ta.V = V; ta.J = J; ta.H = PH; ta.W = PW; ta.L = h->L; ta.is_rw = is_rw;
+    for (int v = 0; v < 4; ++v) { ta.cam_id[v] = h->cam_id[v]; ta.cam[v] = h->cam[v]; }
+    ta.ctm = coord_trans_mat; ta.mlp_pred = preds; ta.preds = preds; ta.X = Xs; ta.w = h->d_w;
+    ta.dbg_anchors = w.anch; ta.dbg_valid = w.valid;
+    if ((rc = launch_pose_tokens(ta, bf, st))) return rc;
+    const int64_t s = bf ? 2 : 4;
+    h->dbg["p7"] = std::make_pair(w.p7, (int64_t)VB * 64 * 128 * s);
+    h->dbg["p0"] = std::make_pair(w.p0, (int64_t)VB * PHW * 64 * s);
+    h->dbg["m0"] = std::make_pair((void*)w.m0, (int64_t)B * 2048 * 4);
+    h->dbg["anchors"] = std::make_pair((void*)w.anch, (int64_t)VB * J * 8);
+    h->dbg["valid"] = std::make_pair((void*)w.valid, (int64_t)VB * J);
+    return EGR_OK;
+}
+
+extern "C" int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes) {
+    EGR_CHECK(h && name && ptr && bytes, EGR_ERR_INVALID, "debug_buffer: null argument");
+    auto it = h->dbg.find(name);
+    EGR_CHECK(it != h->dbg.end(), EGR_ERR_INVALID, "debug_buffer: unknown buffer '%s'", name);
+    *ptr = it->second.first;
+    *bytes = it->second.second;
+    return EGR_OK;
+}

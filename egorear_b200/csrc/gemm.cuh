@@ -1,0 +1,56 @@
+// Dense stage descriptor shared by the fp32 SIMT GEMM (gemm_simt.cu) and the tcgen05 bf16 GEMM (gemm_tc.cu).
+//
+// Every dense op on the hot path (1x1 conv, 3x3 stride-2 conv, Linear) is D = epi(A · W^T + bias) with
+//   A  [M, K]  activations, channels-last (NHWC), K contiguous           (implicit im2col for the 3x3)
+//   W  [N, K]  weights, K contiguous (PyTorch Linear / repacked conv weight [Cout][ky][kx][Cin])
+//   D  [M, N]  channels-last output
+// and `groups` independent problems (different weights: front/back heads, the 4 per-view refiners)
+// launched together through blockIdx.z with per-group element strides.
+#pragma once
+#include "common.cuh"
+
+namespace egr {
+
+enum AMode : int {
+    A_PLAIN = 0,      // A[m][k] = A[(k / kblk) * kblk_stride + m * lda + (k % kblk)]
+    A_CONV3S2 = 1,    // 3x3, stride 2, pad 1 over NHWC [img][Hin][Win][Cin]; k = (ky*3+kx)*Cin + ci
+};
+
+enum Epi : int {
+    EPI_NONE = 0,        // acc + bias
+    EPI_RELU = 1,        // relu(acc + bias)
+    EPI_GELU = 2,        // exact-erf gelu(acc + bias)
+    EPI_RELU_ADDUP = 3,  // relu(acc + bias) + relu(bilinear_x2_align_corners(aux))   (T1 -> R1 input)
+};
+
+struct GemmDesc {
+    const void* A = nullptr;      // activations (float or bf16, per kernel)
+    const void* W = nullptr;      // weights (float for SIMT, bf16 for tcgen05)
+    const float* bias = nullptr;  // [N] fp32 or null
+    void* D = nullptr;            // output (float or bf16)
+    const void* aux = nullptr;    // EPI_RELU_ADDUP: [img][(Hout/2)*(Wout/2)][N] pre-activation map
+    int M = 0, N = 0, K = 0;
+    int64_t lda = 0, ldd = 0;
+    int amode = A_PLAIN, epi = EPI_NONE;
+    // A_PLAIN K-split (pose3d flatten "(v c h w)"): k-blocks of kblk elements live kblk_stride apart
+    int kblk = 0;
+    int64_t kblk_stride = 0;
+    // A_CONV3S2 geometry
+    int Hin = 0, Win = 0, Cin = 0;   // output is (Hin/2) x (Win/2); M = n_img * Hout * Wout
+    // epilogue geometry for EPI_RELU_ADDUP: output positions form Hout x Wout images
+    int Hout = 0, Wout = 0;
+    // groups
+    int groups = 1;
+    int64_t a_gs = 0, w_gs = 0, b_gs = 0, d_gs = 0, aux_gs = 0;   // element strides between groups
+};
+
+// fp32 SIMT path (reference-grade parity).  TA/TO in {float, bf16}: 0 = float, 1 = bf16.
+int gemm_simt(const GemmDesc& d, int a_is_bf16, int d_is_bf16, cudaStream_t st);
+
+// tcgen05 + TMA bf16 path.  A, W bf16; D bf16 or fp32.
+int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st);
+int gemm_tc_init();   // resolves cuTensorMapEncodeTiled; EGR_OK or error
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+}  // namespace egr

@@ -1,0 +1,42 @@
+// HBM-bound layout / resampling stages around the dense GEMMs (declarations; see layout_ops.cu).
+#pragma once
+#include "common.cuh"
+
+namespace egr {
+
+// in  [B][V][C][HW] fp32 (NCHW per view)  ->  out [V][B][HW][C] (view-major, channels-last), T = float | bf16
+int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_bf16, cudaStream_t st);
+// fp32 -> activation dtype copy (float: plain copy)
+int cast_act(const float* in, void* out, int out_bf16, int64_t n, cudaStream_t st);
+
+// Heatmap head tail over G groups of B images:  z [g][B][Hs*Ws][C] (pre-activation, channels-last)
+//   hm[b*hm_bs + g*hm_gs + (j*H + y)*W + x] fp32 = W15 · relu(up2(z)) + b15, group g uses weight set wsel[g]
+//   optional copy hm_t [g][B][J][4HsWs] in the activation dtype (A operand of the jqa heatmap_proj GEMM)
+int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, const int* wsel_host, int B, int G,
+                 int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
+                 cudaStream_t st);
+
+// R1 tail: z [g][B][Hs*Ws][C] -> relu(up2(z)) written twice:
+//   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output) and
+//   out_nhwc [g][B][4HsWs][C] in the activation dtype (input of the H2 3x3 conv)
+int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
+                  int64_t o_gs, void* out_nhwc, cudaStream_t st);
+
+// nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C]
+int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, int W, int C, cudaStream_t st);
+
+// ---- one-time weight preparation (prepack) ----
+// conv weight [Cout][Cin][3][3] -> [Cout][ky][kx][Cin]
+int repack_conv3(const float* w, float* out, int Cout, int Cin, cudaStream_t st);
+// fp32 -> bf16 copy
+int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st);
+// [R][C] -> [C][R]
+int transpose2d(const float* in, float* out, int R, int C, cudaStream_t st);
+// C[M][N] = A[M][K] · B[K][N] (+ bias[N] broadcast when non-null); small prepack-time products, fp32
+int small_matmul(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, cudaStream_t st);
+// out[r][c] = in[r][c] + v[c]
+int add_rowvec(const float* in, const float* v, float* out, int64_t R, int C, cudaStream_t st);
+// pose3d big-MLP weight: [N][(v c h w)] -> [N][(v h w c)]   (HWp = 64 positions, C = 128 channels)
+int permute_mlp_weight(const float* w, float* out, int N, int V, int C, int HWp, cudaStream_t st);
+
+}  // namespace egr

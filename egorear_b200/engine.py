@@ -1,0 +1,185 @@
+"""Handle wrappers around the two C-ABI engines (egr_mvfex_*, egr_pose3d_*).
+
+The wrappers own nothing but (a) references to the parameter tensors they registered (so the device
+pointers stay alive), (b) a cached workspace tensor.  Derived weights live in the C library; they are
+rebuilt (`prepack`) lazily whenever a registered parameter changed (`load_state_dict`, optimizer step),
+detected through the tensors' version counters and data pointers.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .ops import _ptr, _stream, calib_table
+
+PREC = {"fp32": 0, "bf16": 1}
+CAMERA_MODEL_ID = {"ego4view_syn": 0, "ego4view_rw": 1, "ego4view_syn_stereo_front": 2, "ego4view_rw_stereo_front": 3,
+                   "ego4view_syn_stereo_back": 4, "ego4view_rw_stereo_back": 5}
+
+
+def set_option(key, value):
+    _lib.check(_lib.load().egr_set_option(key.encode(), int(value)))
+
+
+class _EngineBase:
+    _prefix = None
+
+    def __init__(self):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        self._tensors = {}
+        self._sig = None
+        self._ws = None
+        self.frozen = False
+
+    def _fn(self, name):
+        return getattr(self._lib, "egr_%s_%s" % (self._prefix, name))
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- parameters ----
+    def _signature(self):
+        return tuple((t.data_ptr(), t._version) for t in self._tensors.values())
+
+    def set_params(self, named_tensors):
+        """named_tensors: {state_dict key: fp32 CUDA tensor}.  Non-contiguous / non-fp32 tensors are copied."""
+        self._tensors = {}
+        for k, t in named_tensors.items():
+            if not t.is_cuda:
+                raise RuntimeError("egorear_b200: parameter '%s' is not on a CUDA device (no CPU fallback)" % k)
+            self._tensors[k] = t
+        self._sig = None
+
+    def _sync_params(self):
+        if self.frozen and self._sig is not None:
+            return
+        sig = self._signature()
+        if sig == self._sig:
+            return
+        keep = []
+        for k, t in self._tensors.items():
+            d = t.detach()
+            if d.dtype != torch.float32 or not d.is_contiguous():
+                d = d.float().contiguous()
+                keep.append(d)
+            _lib.check(self._fn("set_param")(self._h, k.encode(), _ptr(d), d.numel()))
+        self._keep = keep
+        _lib.check(self._fn("prepack")(self._h, _stream()))
+        self._sig = sig
+
+    def _workspace(self, B, device):
+        need = int(self._fn("workspace_bytes")(self._h, B))
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
+        return self._ws
+
+    def debug_buffer(self, name, dtype, shape):
+        """Copy of a named intermediate of the last forward (tests only)."""
+        p = ctypes.c_void_p()
+        n = ctypes.c_int64()
+        _lib.check(self._fn("debug_buffer")(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)))
+        off = p.value - self._ws.data_ptr()
+        raw = self._ws[off:off + n.value]
+        return raw.view(dtype)[: int(torch.tensor(shape).prod())].view(*shape).clone()
+
+
+class MvfexEngine(_EngineBase):
+    """Everything EgoPoseFormerHeatmapMVFEX.forward does after the backbones."""
+    _prefix = "mvfex"
+
+    def __init__(self, num_views=4, num_heatmap=15, heatmap_threshold=0.5, precision="bf16"):
+        super().__init__()
+        self.V, self.J, self.precision = num_views, num_heatmap, precision
+        _lib.check(self._lib.egr_mvfex_create(num_views, num_heatmap, float(heatmap_threshold), PREC[precision],
+                                              ctypes.byref(self._h)))
+
+    def forward(self, feat, bfb, heatmap_for_anchor=None):
+        """feat [B,V,128,64,64], bfb [B,V,512,8,8] fp32 CUDA ->
+        dict(hm_init, hm_refined [B,V,15,64,64], feat_refined [B,V,128,64,64], anchors_2d [B,V,15,2], anchors_valid)."""
+        self._sync_params()
+        B, V = feat.shape[:2]
+        assert V == self.V and tuple(feat.shape[2:]) == (128, 64, 64) and tuple(bfb.shape[1:]) == (V, 512, 8, 8)
+        feat = feat.detach().float().contiguous()
+        bfb = bfb.detach().float().contiguous()
+        hfa = heatmap_for_anchor.detach().float().contiguous() if isinstance(heatmap_for_anchor, torch.Tensor) else None
+        dev = feat.device
+        out = {
+            "hm_init": torch.empty((B, V, self.J, 64, 64), dtype=torch.float32, device=dev),
+            "hm_refined": torch.empty((B, V, self.J, 64, 64), dtype=torch.float32, device=dev),
+            "feat_refined": torch.empty((B, V, 128, 64, 64), dtype=torch.float32, device=dev),
+            "anchors_2d": torch.empty((B, V, self.J, 2), dtype=torch.float32, device=dev),
+            "anchors_valid": torch.empty((B, V, self.J), dtype=torch.bool, device=dev),
+        }
+        ws = self._workspace(B, dev)
+        _lib.check(self._lib.egr_mvfex_forward(self._h, B, _ptr(feat), _ptr(bfb), _ptr(hfa), _ptr(out["hm_init"]),
+                                               _ptr(out["hm_refined"]), _ptr(out["feat_refined"]),
+                                               _ptr(out["anchors_2d"]), _ptr(out["anchors_valid"]), _ptr(ws),
+                                               ws.numel(), _stream()))
+        return out
+
+    def refiner_forward(self, r, heatmap, frame_feat, feat_mv, anchors_2d, anchors_valid, bfb):
+        """One HeatmapMVF.forward: returns (hm_refined [B,15,64,64], feat_refined [B,128,64,64])."""
+        self._sync_params()
+        B = heatmap.shape[0]
+        dev = heatmap.device
+        heatmap = heatmap.detach().float().contiguous()
+        frame_feat = frame_feat.detach().float().contiguous()
+        feat_mv = feat_mv.detach().float().contiguous()
+        a2 = anchors_2d.detach().float().contiguous()
+        av = anchors_valid.detach().to(torch.bool).contiguous()
+        bfb = bfb.detach().float().contiguous()
+        hm = torch.empty((B, self.J, 64, 64), dtype=torch.float32, device=dev)
+        ft = torch.empty((B, 128, 64, 64), dtype=torch.float32, device=dev)
+        ws = self._workspace(B, dev)
+        _lib.check(self._lib.egr_mvfex_refiner_forward(self._h, r, B, _ptr(heatmap), _ptr(frame_feat), _ptr(feat_mv),
+                                                       _ptr(a2), _ptr(av), _ptr(bfb), _ptr(hm), _ptr(ft), _ptr(ws),
+                                                       ws.numel(), _stream()))
+        return hm, ft
+
+
+class Pose3DEngine(_EngineBase):
+    """EgoPoseFormerPose3D.forward."""
+    _prefix = "pose3d"
+
+    def __init__(self, num_views=4, num_joints=16, num_layers=3, camera_model="ego4view_syn", use_pred_heatmap_init=True,
+                 precision="bf16", calib=None):
+        super().__init__()
+        if camera_model not in CAMERA_MODEL_ID:
+            raise ValueError('Unknown camera model !')
+        self.V, self.J, self.L = num_views, num_joints, num_layers
+        self.camera_model, self.precision = camera_model, precision
+        tab = calib_table(calib) if calib is not None else None
+        _lib.check(self._lib.egr_pose3d_create(num_views, num_joints, num_layers, CAMERA_MODEL_ID[camera_model],
+                                               int(bool(use_pred_heatmap_init)), PREC[precision],
+                                               ctypes.c_void_p(tab.ctypes.data) if tab is not None else None,
+                                               ctypes.byref(self._h)))
+
+    def forward(self, feats_init, feats_final, coord_trans_mat=None):
+        """-> preds [L+1, B, 16, 3] fp32 (cm): preds[0] MLP proposal, preds[1:] transformer layers."""
+        self._sync_params()
+        B, V = feats_final.shape[:2]
+        assert V == self.V
+        fi = feats_init.detach().float().contiguous()
+        ff = feats_final.detach().float().contiguous()
+        ctm = None
+        if self.camera_model.startswith("ego4view_rw"):
+            if coord_trans_mat is None:
+                raise RuntimeError("ego4view_rw camera model needs coord_trans_mat")
+            if coord_trans_mat.dtype != torch.float32:
+                # the reference matmuls this against fp32 points (utils/camera_models.py:210): dtype error there too
+                raise RuntimeError("expected m1 and m2 to have the same dtype, but got: double != float")
+            ctm = coord_trans_mat.contiguous()
+        preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=ff.device)
+        ws = self._workspace(B, ff.device)
+        _lib.check(self._lib.egr_pose3d_forward(self._h, B, _ptr(fi), _ptr(ff), _ptr(ctm), _ptr(preds), _ptr(ws),
+                                                ws.numel(), _stream()))
+        return preds

@@ -1,0 +1,202 @@
+"""Python entry points over the C-ABI: the functions of the reference that the extension replaces.
+
+Same names, argument meaning and error behaviour as the reference functions:
+
+  get_max_preds     <- pose_estimation/utils/loss.py:122-142
+  generate_target   <- generate_heatmap.py:10-48
+  ms_deform_attn    <- mmcv MultiScaleDeformableAttnFunction (models/utils/deform_attn.py:155-162)
+  reproject_fisheye <- EgoPoseFormerPose3D._reproject_3d_to_2d (estimator/egoposeformer_mvf_ex.py:340-382)
+
+Everything runs on the current CUDA device through libegorear_b200.so; there is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .calib import CAMERA_NAMES, cameras_for
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(t, name):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError("egorear_b200.%s: expected a CUDA tensor (there is no CPU fallback)" % name)
+
+
+# ------------------------------------------------------------------------------------------------
+# D1
+# ------------------------------------------------------------------------------------------------
+def get_max_preds(heatmaps, threshold=0.5, normalize=False, return_index=False):
+    """Drop-in for pose_estimation.utils.loss.get_max_preds (same asserts, same squeeze quirk)."""
+    assert isinstance(heatmaps, torch.Tensor), 'heatmaps should be a torch.Tensor'
+    assert heatmaps.ndim == 4, 'heatmaps should be 4-ndim'
+    _need_cuda(heatmaps, "get_max_preds")
+    B, J, H, W = heatmaps.shape
+    hm = heatmaps.detach()
+    if hm.dtype != torch.float32 or not hm.is_contiguous():
+        hm = hm.float().contiguous()
+    preds = torch.empty((B, J, 2), dtype=torch.float32, device=hm.device)
+    maxvals = torch.empty((B, J, 1), dtype=torch.float32, device=hm.device)
+    valid = torch.empty((B, J, 1), dtype=torch.bool, device=hm.device)
+    idx = torch.empty((B, J), dtype=torch.int32, device=hm.device) if return_index else None
+    lib = _lib.load()
+    _lib.check(lib.egr_decode_argmax(_ptr(hm), B, J, H, W, float(threshold), int(bool(normalize)), _ptr(preds),
+                                     _ptr(maxvals), _ptr(valid), _ptr(idx), _stream()))
+    out = (preds, maxvals.squeeze(), valid.squeeze())      # loss.py:142 squeezes size-1 dims
+    return out + (idx,) if return_index else out
+
+
+# ------------------------------------------------------------------------------------------------
+# G1
+# ------------------------------------------------------------------------------------------------
+def _numpy_patch(sigma):
+    # the caller-side Gaussian patch, evaluated by numpy in float32 exactly like generate_heatmap.py:32-36
+    tmp_size = sigma * 3
+    size = 2 * tmp_size + 1
+    x = np.arange(0, size, 1, np.float32)
+    y = x[:, np.newaxis]
+    x0 = y0 = size // 2
+    return np.ascontiguousarray(np.exp(-((x - x0) ** 2 + (y - y0) ** 2) / (2 * sigma ** 2)), dtype=np.float32)
+
+
+def generate_target_batch(joints, image_size=872, heatmap_size=64, sigma=1, out=None):
+    """Batched on-GPU Gaussian heatmap synthesis.
+
+    joints: float64 [..., J, 2] (x, y) pixels — CUDA tensor, CPU tensor or numpy array.
+    Returns a CUDA float32 tensor [..., J, heatmap_size, heatmap_size] (or writes into `out`).
+    """
+    if isinstance(joints, np.ndarray):
+        joints = torch.from_numpy(np.ascontiguousarray(joints, dtype=np.float64))
+    joints = joints.to(dtype=torch.float64)
+    if not joints.is_cuda:
+        joints = joints.cuda(non_blocking=True)
+    joints = joints.contiguous()
+    assert joints.shape[-1] == 2 and joints.ndim >= 2
+    J = joints.shape[-2]
+    n_maps = joints.numel() // (J * 2)
+    shape = tuple(joints.shape[:-1]) + (heatmap_size, heatmap_size)
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=joints.device)
+    else:
+        assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n_maps * J * heatmap_size ** 2
+    patch = _numpy_patch(sigma)
+    lib = _lib.load()
+    _lib.check(lib.egr_generate_target(_ptr(joints), _ptr(out), n_maps, J, float(image_size), int(heatmap_size),
+                                       float(sigma), ctypes.c_void_p(patch.ctypes.data), _stream()))
+    return out
+
+
+def generate_target(joints, image_size=872, heatmap_size=64, num_joints=15, sigma=1):
+    """Drop-in for generate_heatmap.generate_target: numpy in, numpy float32 [num_joints, hs, hs] out."""
+    j = np.asarray([[joints[i][0], joints[i][1]] for i in range(num_joints)], dtype=np.float64)
+    return generate_target_batch(j, image_size, heatmap_size, sigma).cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# MSDA (mmcv op replacement)
+# ------------------------------------------------------------------------------------------------
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step=None):
+    """Forward of mmcv's MultiScaleDeformableAttnFunction for one feature level (the only case the
+    reference uses: DeformMultiViewAttn / DeformStereoAttn register spatial_shapes of shape (1, 2))."""
+    _need_cuda(value, "ms_deform_attn")
+    B, L, nh, hd = value.shape
+    _, Q, _, n_levels, P, _ = sampling_locations.shape
+    if n_levels != 1:
+        raise NotImplementedError("egorear_b200.ms_deform_attn: single-level only (n_levels=%d)" % n_levels)
+    if isinstance(spatial_shapes, torch.Tensor):
+        H, W = int(spatial_shapes[0, 0]), int(spatial_shapes[0, 1])
+    else:
+        H, W = int(spatial_shapes[0][0]), int(spatial_shapes[0][1])
+    assert H * W == L
+    value = value.float().contiguous()
+    loc = sampling_locations.float().contiguous()
+    aw = attention_weights.float().contiguous()
+    out = torch.empty((B, Q, nh * hd), dtype=torch.float32, device=value.device)
+    lib = _lib.load()
+    _lib.check(lib.egr_msda_forward(_ptr(value), B, H, W, nh, hd, _ptr(loc), _ptr(aw), Q, P, _ptr(out), _stream()))
+    return out
+
+
+class MultiScaleDeformableAttnFunction:
+    """Inference stand-in with mmcv's call signature: `MultiScaleDeformableAttnFunction.apply(...)`."""
+
+    @staticmethod
+    def apply(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
+        return ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights,
+                              im2col_step)
+
+
+# ------------------------------------------------------------------------------------------------
+# P3
+# ------------------------------------------------------------------------------------------------
+def calib_table(calib):
+    """{camera_name: {...}} -> float32 [4,16] host table for the C-ABI."""
+    t = np.zeros((4, 16), dtype=np.float32)
+    for i, name in enumerate(CAMERA_NAMES):
+        c = calib[name]
+        poly = c["polynomialW2C"]
+        assert len(poly) <= 11
+        t[i, 0:2] = c["image_center"]
+        t[i, 2:4] = c["size"]
+        t[i, 4] = len(poly)
+        t[i, 5:5 + len(poly)] = poly
+    return t
+
+
+def reproject_fisheye(pts3d, camera_model, coord_trans_mat=None, calib=None):
+    """anchors_2d [B,V,J,2], anchors_valid [B,V,J] bool.  `pts3d` [B,J,3] fp32 is mutated in place for the
+    synthetic rigs, reproducing utils/camera_models.py:57-63."""
+    _need_cuda(pts3d, "reproject_fisheye")
+    assert pts3d.dtype == torch.float32 and pts3d.is_contiguous() and pts3d.ndim == 3
+    names = cameras_for(camera_model)
+    ids = (ctypes.c_int * len(names))(*[CAMERA_NAMES.index(n) for n in names])
+    is_rw = camera_model.startswith("ego4view_rw")
+    B, J = pts3d.shape[:2]
+    if is_rw:
+        assert coord_trans_mat is not None
+        if coord_trans_mat.dtype != torch.float32:
+            # utils/camera_models.py:210 matmuls the matrix against fp32 points: a float64 matrix is a dtype error there
+            raise RuntimeError("expected m1 and m2 to have the same dtype, but got: double != float")
+        coord_trans_mat = coord_trans_mat.contiguous()
+    a2 = torch.empty((B, len(names), J, 2), dtype=torch.float32, device=pts3d.device)
+    av = torch.empty((B, len(names), J), dtype=torch.bool, device=pts3d.device)
+    tab = calib_table(calib) if calib is not None else None
+    lib = _lib.load()
+    _lib.check(lib.egr_reproject_fisheye(_ptr(pts3d), B, J, ids, len(names), int(is_rw),
+                                         _ptr(coord_trans_mat) if is_rw else None,
+                                         ctypes.c_void_p(tab.ctypes.data) if tab is not None else None,
+                                         _ptr(a2), _ptr(av), _stream()))
+    return a2, av
+
+
+def heatmap_head_1x1(feat, weight, bias):
+    """1x1 conv head of EgoPoseFormerHeatmap on [N,C,H,W] fp32 (estimator/egoposeformer_heatmap.py:34-39)."""
+    _need_cuda(feat, "heatmap_head_1x1")
+    N, C, H, W = feat.shape
+    J = weight.shape[0]
+    feat = feat.float().contiguous()
+    w = weight.detach().reshape(J, C).float().contiguous()
+    b = bias.detach().float().contiguous()
+    out = torch.empty((N, J, H, W), dtype=torch.float32, device=feat.device)
+    lib = _lib.load()
+    _lib.check(lib.egr_heatmap_head_1x1(_ptr(feat), _ptr(w), _ptr(b), N, C, H * W, J, _ptr(out), _stream()))
+    return out
+
+
+def pack_joints(preds2d, pose3d):
+    """[B, ...] 2D joints + [B, J3, 3] pose -> packed fp32 [B, n2d+n3d] row per frame (all-gather payload)."""
+    B = preds2d.shape[0]
+    p2 = preds2d.reshape(B, -1).float().contiguous()
+    p3 = pose3d.reshape(B, -1).float().contiguous()
+    out = torch.empty((B, p2.shape[1] + p3.shape[1]), dtype=torch.float32, device=p2.device)
+    lib = _lib.load()
+    _lib.check(lib.egr_pack_joints(_ptr(p2), _ptr(p3), B, p2.shape[1], p3.shape[1], _ptr(out), _stream()))
+    return out

@@ -1,0 +1,128 @@
+"""Deterministic synthetic weights and inputs (bench.py, smoke(), tests and tests/golden/make_golden.py).
+
+There is no network for checkpoints or datasets, so every run uses random-init weights of the shipped
+architectures and synthetic fisheye-shaped inputs.  Stock initialisation leaves the hot path degenerate
+(SURVEY §7 trap 7: zero sampling_offsets / attention_weights, anchors never valid), so `fill_state_dict`
+writes a NAME-SEEDED fill: each tensor depends only on its state_dict key and shape — not on module construction
+order — which makes the reference modules (built in the survey container) and this package's mirror modules
+carry bit-identical parameters without shipping 500 MB of weights.
+"""
+import math
+import zlib
+
+import numpy as np
+import torch
+
+
+def _gen(key, salt=0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed((zlib.crc32(key.encode()) + 7919 * salt) & 0x7FFFFFFF)
+    return g
+
+
+def _ring_bias(n_heads=4, n_points=16):
+    # stock MSDeformAttn offset bias (models/utils/deform_attn.py:69-81)
+    th = torch.arange(n_heads, dtype=torch.float32) * (2.0 * math.pi / n_heads)
+    g = torch.stack([th.cos(), th.sin()], -1)
+    g = (g / g.abs().max(-1, keepdim=True)[0]).view(n_heads, 1, 1, 2).repeat(1, 1, n_points, 1)
+    g = g * torch.arange(1, n_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
+    return g.reshape(-1)
+
+
+def synth_tensor(key, shape, dtype=torch.float32):
+    """Value of parameter `key` (hot-path keys only; see fill_state_dict)."""
+    g = _gen(key)
+    shape = tuple(shape)
+    n = lambda std: torch.randn(shape, generator=g, dtype=torch.float32) * std
+    u = lambda a: (torch.rand(shape, generator=g, dtype=torch.float32) * 2 - 1) * a
+    if key.endswith("sampling_offsets.weight"):
+        t = n(0.05)
+    elif key.endswith("sampling_offsets.bias"):
+        t = _ring_bias() + n(0.25)
+    elif key.endswith("attention_weights.weight"):
+        t = n(0.2)
+    elif key.endswith("attention_weights.bias"):
+        t = n(0.5)
+    elif key.endswith("frame_feat_multi_view_pos_embed"):
+        t = n(0.02)
+    elif key.endswith("joint_query_embed.weight"):
+        t = n(1.0)
+    elif key == "mlp_pred.2.bias" or key.endswith(".mlp_pred.2.bias"):
+        # plausible device-relative pose (cm).  The fisheye cameras look along +z (theta = atan(-z/norm), rho(0) = image
+        # circle radius), so body joints have z > 0: x,y ~ U(-50,50), z ~ U(-20,150) -> mixed in / out of FOV
+        r = torch.rand((shape[0] // 3, 3), generator=g)
+        t = torch.stack((r[:, 0] * 100 - 50, r[:, 1] * 100 - 50, r[:, 2] * 170 - 20), dim=1).reshape(shape)
+    elif key.endswith(".weight") and len(shape) == 1:
+        t = 1.0 + n(0.1)                           # every 1-D ".weight" on the hot path is a LayerNorm gain
+    elif key.endswith(".weight") and len(shape) >= 2:
+        fan_in = int(np.prod(shape[1:]))
+        t = u(math.sqrt(6.0 / fan_in))            # keeps activations O(1) through ReLU stacks
+    elif key.endswith(".bias"):
+        t = u(0.1)
+    else:
+        t = n(0.02)
+    return t.to(dtype)
+
+
+def is_hot_path_key(key):
+    return "heatmap_estimator_stereo" not in key and ".encoder." not in key
+
+
+def fill_state_dict(module, hot_path_only=True):
+    """Overwrite (in place) every floating-point hot-path entry of module.state_dict() with its name-seeded value."""
+    sd = module.state_dict()
+    with torch.no_grad():
+        for k, v in sd.items():
+            if not v.is_floating_point():
+                continue
+            if hot_path_only and not is_hot_path_key(k):
+                continue
+            v.copy_(synth_tensor(_strip_prefix(k), v.shape).to(v.device))
+    return module
+
+
+def _strip_prefix(k):
+    # EgoPoseFormerMVFEX nests the two estimators; the fill is defined on the estimators' own key names
+    for p in ("heatmap_estimator.", "pose3d_estimator."):
+        if k.startswith(p):
+            return k[len(p):]
+    return k
+
+
+def synth_state_dict(shapes):
+    """{key: shape} -> {key: tensor} without building a module."""
+    return {k: synth_tensor(k, s) for k, s in shapes.items()}
+
+
+# ------------------------------------------------------------------------------------------------------
+# inputs
+# ------------------------------------------------------------------------------------------------------
+def synth_features(B, V=4, seed=0, device="cpu"):
+    """Backbone outputs: FPN map [B,V,128,64,64] (>= 0: the FPN ends in ReLU, resnet.py:113-119) and the
+    stride-32 ResNet map [B,V,512,8,8] (>= 0: ends in a BasicBlock ReLU)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(1000 + seed)
+    feat = torch.relu(torch.randn((B, V, 128, 64, 64), generator=g))
+    bfb = torch.relu(torch.randn((B, V, 512, 8, 8), generator=g))
+    return feat.to(device), bfb.to(device)
+
+
+def synth_keypoints(n_frames, V=4, J=16, seed=0, lo=-60.0, hi=932.0):
+    """float64 [n_frames, V, J, 2] pixel coordinates, ~12 % off-image per axis."""
+    return np.random.default_rng(seed).uniform(lo, hi, size=(n_frames, V, J, 2))
+
+
+def synth_coord_trans_mat(B, seed=0, device="cpu"):
+    """fp32 [B,4,4,4] rigid device->camera transforms in metres mirroring the syn rig."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(2000 + seed)
+    M = torch.zeros((B, 4, 4, 4), dtype=torch.float32)
+    base_t = torch.tensor([[0.06, 0.0, 0.0], [-0.06, 0.0, 0.0], [-0.06, 0.37, 0.0], [0.06, 0.37, 0.0]])
+    for v in range(4):
+        R = torch.eye(3)
+        if v >= 2:
+            R = torch.diag(torch.tensor([-1.0, -1.0, 1.0]))     # 180 deg about z
+        M[:, v, :3, :3] = R
+        M[:, v, :3, 3] = base_t[v] + torch.randn((B, 3), generator=g) * 0.005
+        M[:, v, 3, 3] = 1.0
+    return M.to(device)

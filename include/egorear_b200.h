@@ -1,0 +1,178 @@
+/*
+ * egorear_b200 — C-ABI of the B200-native (sm_100a) EgoRear inference hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point
+ * names the reference interface it replaces (paths relative to the EgoRear checkout).
+ * The reference itself is pure Python; its only native operator is mmcv's
+ * MultiScaleDeformableAttnFunction (pose_estimation/models/utils/deform_attn.py:155-162), so the
+ * Python-side binding a maintainer adds is the ctypes stub shown in INTEGRATION.md
+ * (egorear_b200/_lib.py is that stub).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the parameter is documented as host;
+ *   - the caller (PyTorch) owns every input, output and workspace buffer; the library never
+ *     frees or retains them beyond the call, except parameter pointers registered through
+ *     egr_*_set_param, which must stay alive until the next egr_*_prepack / destroy;
+ *   - derived weights (folded / repacked / bf16 copies) are library-owned inside the handle;
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*);
+ *     no entry point synchronises the device except create/prepack/destroy;
+ *   - return value: 0 on success, otherwise an EGR_ERR_* code; egr_last_error() returns a
+ *     thread-local message.  Nothing throws or exits across the ABI;
+ *   - there is NO CPU fallback: every compute entry fails with EGR_ERR_NO_DEVICE when the
+ *     current device is not an sm_100 (B200) GPU.
+ */
+#ifndef EGOREAR_B200_H_
+#define EGOREAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGR_OK               0
+#define EGR_ERR_INVALID      1   /* bad shape / argument (the reference's Python asserts) */
+#define EGR_ERR_NO_DEVICE    2   /* no CUDA device, or not sm_100 */
+#define EGR_ERR_CUDA         3   /* CUDA runtime / launch error */
+#define EGR_ERR_UNSUPPORTED  4   /* configuration outside the shipped configs */
+#define EGR_ERR_STATE        5   /* missing parameter / prepack not run / workspace too small */
+
+/* precision of the dense conv/GEMM stages (token/attention math is always fp32) */
+#define EGR_PREC_FP32  0   /* fp32 SIMT kernels: reference-grade parity (<=1e-3 rel in fp32) */
+#define EGR_PREC_BF16  1   /* bf16 operands, fp32 accumulate in TMEM (tcgen05): stated looser bound */
+
+const char* egr_last_error(void);
+/* process-wide switches, for debugging: "tc" (default 1) = EGR_PREC_BF16 uses the tcgen05 kernels;
+ * 0 routes bf16 activations through the SIMT GEMM instead */
+int         egr_set_option(const char* key, int value);
+int         egr_version(void);
+/* 0 when the current CUDA device is an sm_100 GPU; fills *sm_count / *cc when non-NULL */
+int         egr_device_check(int* cc_major_minor, int* sm_count);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+int64_t     egr_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * G1  generate_target                                   replaces generate_heatmap.py:10-48
+ *   joints   [n_maps, J, 2] float64, (x, y) pixels in image space (n_maps = frames * views)
+ *   out      [n_maps, J, hs, hs] float32, fully written (zeros outside the Gaussian patch)
+ *   patch_host: HOST pointer to the (2*3*sigma+1)^2 float32 Gaussian patch exactly as the caller's
+ *               numpy evaluates generate_heatmap.py:33-36, or NULL: the library then uses the
+ *               recorded numpy values for sigma == 1 and expf otherwise.
+ *   3*sigma must be an integer (the reference's slicing breaks otherwise).
+ * ------------------------------------------------------------------------------------------- */
+int egr_generate_target(const double* joints, float* out, int64_t n_maps, int J, double image_size,
+                        int heatmap_size, double sigma, const float* patch_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D1  get_max_preds                       replaces pose_estimation/utils/loss.py:122-142
+ *   hm [N, J, H, W] float32 -> preds [N, J, 2] float32 (x, y), maxvals [N, J] float32,
+ *   valid [N, J] uint8 (torch.bool storage), idx [N, J] int32 flat argmax (may be NULL).
+ *   First index wins on ties; NaN propagates like torch.max.  H*W must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------- */
+int egr_decode_argmax(const float* hm, int64_t N, int J, int H, int W, float threshold, int normalize,
+                      float* preds, float* maxvals, uint8_t* valid, int32_t* idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MSDA  single-level multi-scale deformable attention forward
+ *       replaces mmcv.ops.multi_scale_deform_attn.MultiScaleDeformableAttnFunction.forward
+ *       (call site pose_estimation/models/utils/deform_attn.py:155-162; mmcv==2.2.0)
+ *   value [B, H*W, nh, hd] f32; loc [B, Q, nh, 1, P, 2] f32 (x, y in [0,1]);
+ *   aw [B, Q, nh, 1, P] f32 (already softmaxed); out [B, Q, nh*hd] f32.
+ *   No im2col_step batch-divisibility restriction.
+ * ------------------------------------------------------------------------------------------- */
+int egr_msda_forward(const float* value, int B, int H, int W, int nh, int hd, const float* loc,
+                     const float* aw, int Q, int P, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P3  fisheye reprojection     replaces EgoPoseFormerPose3D._reproject_3d_to_2d
+ *     (estimator/egoposeformer_mvf_ex.py:340-382) + FishEyeCameraCalibratedModel.world2camera_pytorch
+ *     (utils/camera_models.py:53-104)
+ *   pts3d [B, J, 3] f32 cm, MUTATED IN PLACE for syn rigs exactly like the reference
+ *   (after the call it holds the reference's left-behind tensor, e.g. p + (12,0,0) for 4-view syn).
+ *   cam_ids[n_cams] host ints: 0 FL, 1 FR, 2 BL, 3 BR.   is_rw: 0 syn offsets, 1 use coord_trans_mat
+ *   coord_trans_mat [B, n_cams, 4, 4] f32 (rw only, else NULL).
+ *   calib_host: HOST float array [4][16]: per camera {cx, cy, size_h, size_w, n_coef, a0..a10} or NULL
+ *   for the built-in Ego4View calibration.
+ *   anchors_2d [B, n_cams, J, 2] f32, anchors_valid [B, n_cams, J] uint8.
+ * ------------------------------------------------------------------------------------------- */
+int egr_reproject_fisheye(float* pts3d, int B, int J, const int* cam_ids_host, int n_cams, int is_rw,
+                          const float* coord_trans_mat, const float* calib_host, float* anchors_2d,
+                          uint8_t* anchors_valid, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * H1'  1x1 heatmap head of EgoPoseFormerHeatmap      replaces estimator/egoposeformer_heatmap.py:34-39
+ *   feat [N, C, H, W] f32 NCHW, weight [J, C], bias [J] -> out [N, J, H, W] f32
+ * ------------------------------------------------------------------------------------------- */
+int egr_heatmap_head_1x1(const float* feat, const float* weight, const float* bias, int64_t N, int C, int HW,
+                         int J, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * mvfex engine: everything EgoPoseFormerHeatmapMVFEX.forward does after the backbones
+ *   (estimator/egoposeformer_heatmap_mvf_ex.py:262-437, use_1by1_conv=False / jqa configs):
+ *   H1 init heads, D1 anchors, and per view HeatmapMVF.forward (:652-731) = Q1 M1 F1 A1 A2 A3 T1 R1 H2.
+ *
+ *   egr_mvfex_create:   num_views 2 or 4, embed 256 / 4 heads / ffn 512 / 1 layer / 16 points as in
+ *                       configs/ego4view_*_heatmap_mvfex-n1_jqa*.yaml (others: EGR_ERR_UNSUPPORTED).
+ *   egr_mvfex_set_param: register a parameter of the module's state_dict by its exact key
+ *                       (e.g. "heatmap_refiner_front_left.heatmap_proj.0.weight"), fp32 device ptr.
+ *   egr_mvfex_prepack:  builds derived weights (folded Wv*Wp, sampled position table, repacked /
+ *                       bf16 conv weights).  Must be re-run after parameters change.  Synchronises.
+ *   egr_mvfex_workspace_bytes: scratch the caller must provide for a batch of B frames.
+ *   egr_mvfex_forward:
+ *     feat  [B, V, 128, 64, 64] f32 (FPN output), bfb [B, V, 512, 8, 8] f32 (stride-32 ResNet map)
+ *     heatmap_for_anchor [B, V, 15, 64, 64] f32 or NULL (anchors then come from the init heatmap)
+ *     out: hm_init, hm_refined [B, V, 15, 64, 64] f32; feat_refined [B, V, 128, 64, 64] f32;
+ *          anchors_2d [B, V, 15, 2] f32; anchors_valid [B, V, 15] uint8 (either may be NULL)
+ *   egr_mvfex_refiner_forward: one HeatmapMVF.forward (:652-731) — refiner index r in module order
+ *     (front_left, front_right, back_left, back_right):
+ *     heatmap [B,15,64,64], frame_feat [B,128,64,64], feat_mv [B,V,128,64,64], anchors_2d [B,V,15,2],
+ *     anchors_valid [B,V,15] uint8, bfb [B,512,8,8]  ->  hm_refined [B,15,64,64], feat_refined [B,128,64,64]
+ * ------------------------------------------------------------------------------------------- */
+typedef struct egr_mvfex egr_mvfex;
+int egr_mvfex_create(int num_views, int num_heatmap, float heatmap_threshold, int precision, egr_mvfex** out);
+int egr_mvfex_destroy(egr_mvfex* h);
+int egr_mvfex_set_param(egr_mvfex* h, const char* key, const float* ptr, int64_t numel);
+int egr_mvfex_prepack(egr_mvfex* h, void* stream);
+int64_t egr_mvfex_workspace_bytes(egr_mvfex* h, int B);
+int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const float* bfb, const float* heatmap_for_anchor,
+                      float* hm_init, float* hm_refined, float* feat_refined, float* anchors_2d,
+                      uint8_t* anchors_valid, void* workspace, int64_t workspace_bytes, void* stream);
+int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, const float* frame_feat,
+                              const float* feat_mv, const float* anchors_2d, const uint8_t* anchors_valid,
+                              const float* bfb, float* hm_refined, float* feat_refined, void* workspace,
+                              int64_t workspace_bytes, void* stream);
+/* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
+ * ("q1", "xT", "t1", "ff", ...); EGR_ERR_INVALID for unknown names */
+int egr_mvfex_debug_buffer(egr_mvfex* h, const char* name, void** ptr, int64_t* bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * pose3d engine: EgoPoseFormerPose3D.forward (estimator/egoposeformer_mvf_ex.py:422-452),
+ *   conv-MLP proposal branch (use_mlp_avgpool=False, use_mlp_heatmap=False), P1 P2 P3 P4.
+ *   camera_model: 0 ego4view_syn, 1 ego4view_rw, 2 syn_stereo_front, 3 rw_stereo_front,
+ *                 4 syn_stereo_back, 5 rw_stereo_back
+ *   egr_pose3d_forward:
+ *     feats_init / feats_final [B, V, 128, 64, 64] f32; coord_trans_mat [B, V, 4, 4] f32 (rw) or NULL
+ *     preds [L+1, B, 16, 3] f32: preds[0] = MLP proposal, preds[1..L] = transformer layers (cm)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct egr_pose3d egr_pose3d;
+int egr_pose3d_create(int num_views, int num_joints, int num_layers, int camera_model, int use_pred_heatmap_init,
+                      int precision, const float* calib_host, egr_pose3d** out);
+int egr_pose3d_destroy(egr_pose3d* h);
+int egr_pose3d_set_param(egr_pose3d* h, const char* key, const float* ptr, int64_t numel);
+int egr_pose3d_prepack(egr_pose3d* h, void* stream);
+int64_t egr_pose3d_workspace_bytes(egr_pose3d* h, int B);
+int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init, const float* feats_final,
+                       const float* coord_trans_mat, float* preds, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes);
+
+/* ---------------------------------------------------------------------------------------------
+ * Result packing for the multi-GPU all-gather: 2D joints of the final heatmap and the
+ * final 3D pose into one fp32 row per frame  [B, V*J2*2 + J3*3]  (672 B/frame for 4 views).
+ * ------------------------------------------------------------------------------------------- */
+int egr_pack_joints(const float* preds2d, const float* pose3d, int B, int n2d, int n3d, float* packed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOREAR_B200_H_ */

@@ -1,0 +1,117 @@
+"""ORACLE helper (test infrastructure): import the LIVE reference from /root/reference on a CUDA-less host.
+
+Only usable in the build container (the GPU box has no /root/reference).  Used by
+tests/golden/make_golden.py to generate the committed fixtures and by tests/test_oracle_*.py (skipped
+when the checkout is absent) to pin oracle/model_ref.py and oracle/gt_decode.c against the reference.
+
+Shims, none of which touches the reference's arithmetic on the hot path:
+  * mmcv (un-vendored, no CPU kernel): MultiScaleDeformableAttnFunction -> the standard per-level
+    F.grid_sample(align_corners=False, padding_mode="zeros") restatement of ms_deform_attn_forward;
+  * timm.models.layers.to_2tuple (only used by dead PatchEmbed), natsort.natsorted (generate_heatmap import);
+  * utils/camera_models.py hard-codes device="cuda": torch.tensor is wrapped to drop that kwarg on CPU hosts.
+"""
+import os
+import sys
+import types
+
+import torch
+import torch.nn.functional as F
+
+REF = os.environ.get("EGOREAR_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "pose_estimation"))
+
+
+def _stub(name, **attrs):
+    m = types.ModuleType(name)
+    m.__dict__.update(attrs)
+    sys.modules[name] = m
+    return m
+
+
+class _MSDAGridSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, sampling_locations, attention_weights, im2col_step):
+        B, L, nh, hd = value.shape
+        _, Q, _, nl, P, _ = sampling_locations.shape
+        assert nl == 1
+        H, W = int(spatial_shapes[0, 0]), int(spatial_shapes[0, 1])
+        v = value.permute(0, 2, 3, 1).reshape(B * nh, hd, H, W)
+        grid = (2 * sampling_locations[:, :, :, 0] - 1).permute(0, 2, 1, 3, 4).reshape(B * nh, Q, P, 2)
+        s = F.grid_sample(v, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+        w = attention_weights[:, :, :, 0].permute(0, 2, 1, 3).reshape(B * nh, 1, Q, P)
+        return (s * w).sum(-1).view(B, nh * hd, Q).transpose(1, 2).contiguous()
+
+
+_done = False
+
+
+def install():
+    global _done
+    if _done:
+        return
+    if not available():
+        raise RuntimeError("reference checkout not found at %s" % REF)
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    if "mmcv" not in sys.modules:
+        _stub("mmcv")
+        _stub("mmcv.ops")
+        _stub("mmcv.ops.multi_scale_deform_attn", MultiScaleDeformableAttnFunction=_MSDAGridSample)
+    if "timm" not in sys.modules:
+        _stub("timm")
+        _stub("timm.models")
+        _stub("timm.models.layers", to_2tuple=lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x))
+    if "natsort" not in sys.modules:
+        _stub("natsort", natsorted=sorted)
+    _done = True
+
+
+def import_estimators():
+    install()
+    from pose_estimation.models.estimator import EgoPoseFormerHeatmap, EgoPoseFormerHeatmapMVFEX, EgoPoseFormerMVFEX
+    from pose_estimation.models.estimator.egoposeformer_mvf_ex import EgoPoseFormerPose3D
+    from pose_estimation.models.estimator.egoposeformer_heatmap_mvf_ex import HeatmapMVF
+    if not torch.cuda.is_available():
+        import pose_estimation.utils.camera_models as cm
+        if not getattr(cm, "_egr_cpu_shim", False):
+            real = torch.tensor
+
+            class _TorchProxy:
+                def __getattr__(self, k):
+                    return getattr(torch, k)
+
+                @staticmethod
+                def tensor(*a, **kw):
+                    kw.pop("device", None)
+                    return real(*a, **kw)
+            cm.torch = _TorchProxy()
+            cm._egr_cpu_shim = True
+    return dict(EgoPoseFormerHeatmap=EgoPoseFormerHeatmap, EgoPoseFormerHeatmapMVFEX=EgoPoseFormerHeatmapMVFEX,
+                EgoPoseFormerMVFEX=EgoPoseFormerMVFEX, EgoPoseFormerPose3D=EgoPoseFormerPose3D, HeatmapMVF=HeatmapMVF)
+
+
+def import_functions():
+    install()
+    from pose_estimation.utils.loss import get_max_preds
+    import generate_heatmap
+    return dict(get_max_preds=get_max_preds, generate_target=generate_heatmap.generate_target)
+
+
+def load_model_cfg(name):
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(REF, "configs", name)))["model"]["init_args"]["model_cfg"]
+
+    def _no_pretrain(d):
+        if isinstance(d, dict):
+            for k, v in d.items():
+                if k == "use_imagenet_pretrain":
+                    d[k] = False
+                else:
+                    _no_pretrain(v)
+    _no_pretrain(cfg)
+    if "pose3d_cfg" in cfg:
+        cfg["pose3d_cfg"]["camera_calib_file_dir_path"] = os.path.join(REF, "pose_estimation/utils/camera_calib_file/ego4view")
+    return cfg

@@ -1,0 +1,81 @@
+"""CPU: pins the C oracle (oracle/gt_decode.c) to the golden vectors produced by the live reference, and — when the
+reference checkout is present (build container) — to the reference functions themselves."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import dense_from_sparse, orc_generate_target, orc_get_max_preds
+from oracle import ref_import
+
+
+def test_generate_target_matches_golden(golden, oracle_lib):
+    g = golden["generate_target"]
+    want = dense_from_sparse(g["idx"], g["val"], g["shape"])
+    got = orc_generate_target(oracle_lib, g["joints"])
+    assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_generate_target_gaussian_table(golden, oracle_lib):
+    """the 10 distinct fp32 values of the sigma=1 patch and the edge-case KATs of §8c"""
+    out = orc_generate_target(oracle_lib, np.array([[[436.0, 436.0]]]))[0, 0]
+    bits = sorted(set(out[out != 0].view(np.uint32).tolist()), reverse=True)
+    assert bits == [0x3F800000, 0x3F1B4598, 0x3EBC5AB1, 0x3E0A9555, 0x3DA81C2F, 0x3C960AAE, 0x3C360282, 0x3BDCC9FE,
+                    0x3AC50F0C, 0x39016791]
+    kat = {(-100.0, -100.0): (0, 0.0), (-30.0, 400.0): (21, 0.60653067), (871.9, 871.9): (9, None), (900.0, 900.0): (1, 1.2340980e-4),
+           (915.0, 400.0): (0, 0.0), (0.0, 0.0): (16, 1.0)}
+    for (x, y), (nnz, mx) in kat.items():
+        o = orc_generate_target(oracle_lib, np.array([[[x, y]]]))[0, 0]
+        assert int((o != 0).sum()) == nnz, (x, y)
+        if mx is not None:
+            assert abs(float(o.max()) - mx) < 1e-7
+    # int() truncates toward zero: x = -20 -> mu 0
+    o = orc_generate_target(oracle_lib, np.array([[[-20.0, -20.0]]]))[0, 0]
+    assert o[0, 0] == 1.0
+
+
+def test_generate_target_general_geometry(golden, oracle_lib):
+    g = golden["generate_target"]
+    want = dense_from_sparse(g["idx2"], g["val2"], g["shape2"])
+    got = orc_generate_target(oracle_lib, g["joints2"], image_size=640, hs=48, sigma=2.0)
+    # sigma != 1 goes through expf: bit-exact on the support, values within 1 ulp of numpy's exp
+    assert np.array_equal(got != 0, want != 0)
+    assert np.max(np.abs(got.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))) <= 1
+
+
+def _decode_inputs():
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    # only the input factory is needed; avoid executing the reference import at module import time
+    src = open(spec.origin).read()
+    ns = {"torch": torch}
+    start = src.index("def decode_inputs()")
+    end = src.index("def golden_decode")
+    exec(src[start:end], ns)
+    return ns["decode_inputs"]()
+
+
+def test_get_max_preds_matches_golden(golden, oracle_lib):
+    g = golden["get_max_preds"]
+    hm = _decode_inputs().numpy()
+    for tag, (thr, norm) in {"model": (0.5, True), "eval": (1.0, False)}.items():
+        p, m, v, idx = orc_get_max_preds(oracle_lib, hm, thr, norm)
+        assert np.array_equal(p.view(np.uint32), g["preds_" + tag].view(np.uint32))
+        assert np.array_equal(m.view(np.uint32), g["maxvals_" + tag].view(np.uint32))   # NaN bit pattern included
+        assert np.array_equal(v, g["valid_" + tag])
+    # tie -> first index; all-equal -> 0; NaN wins
+    _, _, _, idx = orc_get_max_preds(oracle_lib, hm, 0.5, False)
+    assert idx[0, 0] == 0 and idx[0, 1] == 10 * 64 + 20 and idx[0, 2] == 4095 and idx[0, 3] == 7 * 64 + 9
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_oracle_vs_live_reference(oracle_lib):
+    fns = ref_import.import_functions()
+    rng = np.random.default_rng(5)
+    joints = rng.uniform(-80, 950, size=(200, 16, 2))
+    want = np.stack([fns["generate_target"](j, 872, 64, 16, 1.0) for j in joints])
+    got = orc_generate_target(oracle_lib, joints)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    hm = torch.randn(5, 15, 64, 64)
+    p, m, v = fns["get_max_preds"](hm.clone(), 0.5, True)
+    op, om, ov, _ = orc_get_max_preds(oracle_lib, hm.numpy(), 0.5, True)
+    assert np.array_equal(op, p.numpy()) and np.array_equal(om, m.numpy()) and np.array_equal(ov, v.numpy())
