@@ -9,6 +9,9 @@
 
 namespace egr {
 CamCalib make_calib(int cam_id, const float* calib_host);
+// P2 (conv_frame_feat + mlp_pred) feeds the 3D proposal directly: bf16 operands cost ~0.1 mm MPJPE on their own
+// (measured), which is the whole parity budget, so by default the branch stays fp32 even in EGR_PREC_BF16.
+int g_opt_pose_p2_bf16 = 0;
 }
 using namespace egr;
 
@@ -29,6 +32,8 @@ struct egr_pose3d {
 
 namespace {
 
+inline int p2_prec(const egr_pose3d* h) { return (h->prec == EGR_PREC_BF16 && g_opt_pose_p2_bf16) ? EGR_PREC_BF16 : EGR_PREC_FP32; }
+
 int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3 2 mlp-permute*/, const std::string& key,
                 cudaStream_t st) {
     m.N = N; m.K = K; m.sets = 1;
@@ -43,7 +48,7 @@ int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3
     const float* b = h->params.get(key + ".bias", N, &rc);
     if (!b) return rc;
     EGR_CUDA_OK(cudaMemcpyAsync(m.bias, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
-    if (h->prec == EGR_PREC_BF16) {
+    if (p2_prec(h) == EGR_PREC_BF16) {
         if ((rc = h->pool.alloc(&m.bf16, (int64_t)N * K))) return rc;
         if ((rc = cast_bf16(m.f32, m.bf16, (int64_t)N * K, st))) return rc;
     }
@@ -114,11 +119,12 @@ struct PBufs {
 };
 
 int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
-    const int64_t s = (h->prec == EGR_PREC_BF16) ? 2 : 4;
+    const int64_t si = (h->prec == EGR_PREC_BF16) ? 2 : 4;          // sampled map
+    const int64_t s = (p2_prec(h) == EGR_PREC_BF16) ? 2 : 4;        // proposal branch
     const int64_t VB = (int64_t)h->V * B;
     Carver c(base, cap);
     PBufs b{};
-    b.Xi = c.take(VB * PHW * PC * s);
+    b.Xi = c.take(VB * PHW * PC * si);
     b.Xf = c.take(VB * PHW * PC * s);
     b.p0 = c.take(VB * PHW * 64 * s);       // 1x1 128->64 @64x64
     b.p2 = c.take(VB * 1024 * 128 * s);     // 3x3 s2 64->128 @32x32
@@ -179,7 +185,7 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
     h->pool.release();
     h->packed = false;
     int rc;
-    if (h->prec == EGR_PREC_BF16 && g_opt_tc) {
+    if (p2_prec(h) == EGR_PREC_BF16 && g_opt_tc) {
         if ((rc = gemm_tc_init())) return rc;
     }
     if ((rc = p_make_wmat(h, h->c0, 64, 128, 0, "conv_frame_feat.0", st))) return rc;
@@ -233,15 +239,17 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     EGR_CHECK(need <= workspace_bytes, EGR_ERR_STATE, "pose3d_forward: workspace %lld B < required %lld B",
               (long long)workspace_bytes, (long long)need);
     cudaStream_t st = (cudaStream_t)stream;
-    const int V = h->V, J = h->J, prec = h->prec, bf = (prec == EGR_PREC_BF16);
+    const int V = h->V, J = h->J;
+    const int bfs = (h->prec == EGR_PREC_BF16);            // sampled-map dtype
+    const int prec = p2_prec(h), bf = (prec == EGR_PREC_BF16);   // proposal-branch dtype
     const int VB = V * B;
     int rc;
     // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
     const float* sampled = h->use_init ? feats_init : feats_final;
     if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, bf, st))) return rc;
     const void* Xs = w.Xf;
-    if (sampled != feats_final) {
-        if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bf, st))) return rc;
+    if (sampled != feats_final || bfs != bf) {
+        if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
         Xs = w.Xi;
     }
     // P2 conv_frame_feat
@@ -279,7 +287,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     for (int v = 0; v < 4; ++v) { ta.cam_id[v] = h->cam_id[v]; ta.cam[v] = h->cam[v]; }
     ta.ctm = coord_trans_mat; ta.mlp_pred = preds; ta.preds = preds; ta.X = Xs; ta.w = h->d_w;
     ta.dbg_anchors = w.anch; ta.dbg_valid = w.valid;
-    if ((rc = launch_pose_tokens(ta, bf, st))) return rc;
+    if ((rc = launch_pose_tokens(ta, bfs, st))) return rc;
     const int64_t s = bf ? 2 : 4;
     h->dbg["p7"] = std::make_pair(w.p7, (int64_t)VB * 64 * 128 * s);
     h->dbg["p0"] = std::make_pair(w.p0, (int64_t)VB * PHW * 64 * s);

@@ -6,6 +6,7 @@ rebuilt (`prepack`) lazily whenever a registered parameter changed (`load_state_
 detected through the tensors' version counters and data pointers.
 """
 import ctypes
+import os
 
 import torch
 
@@ -19,6 +20,10 @@ CAMERA_MODEL_ID = {"ego4view_syn": 0, "ego4view_rw": 1, "ego4view_syn_stereo_fro
 
 def set_option(key, value):
     _lib.check(_lib.load().egr_set_option(key.encode(), int(value)))
+
+
+if os.environ.get("EGR_TC") == "0":      # debugging: bf16 activations through the SIMT GEMM instead of tcgen05
+    set_option("tc", 0)
 
 
 class _EngineBase:

@@ -100,10 +100,13 @@ def synth_state_dict(shapes):
 def synth_features(B, V=4, seed=0, device="cpu"):
     """Backbone outputs: FPN map [B,V,128,64,64] (>= 0: the FPN ends in ReLU, resnet.py:113-119) and the
     stride-32 ResNet map [B,V,512,8,8] (>= 0: ends in a BasicBlock ReLU)."""
-    g = torch.Generator(device="cpu")
-    g.manual_seed(1000 + seed)
-    feat = torch.relu(torch.randn((B, V, 128, 64, 64), generator=g))
-    bfb = torch.relu(torch.randn((B, V, 512, 8, 8), generator=g))
+    feat = torch.empty((B, V, 128, 64, 64))
+    bfb = torch.empty((B, V, 512, 8, 8))
+    for b in range(B):                      # one stream per frame: frame b does not depend on the batch size
+        g = torch.Generator(device="cpu")
+        g.manual_seed((1000 + seed) * 100003 + b)
+        feat[b] = torch.relu(torch.randn((V, 128, 64, 64), generator=g))
+        bfb[b] = torch.relu(torch.randn((V, 512, 8, 8), generator=g))
     return feat.to(device), bfb.to(device)
 
 
@@ -114,8 +117,11 @@ def synth_keypoints(n_frames, V=4, J=16, seed=0, lo=-60.0, hi=932.0):
 
 def synth_coord_trans_mat(B, seed=0, device="cpu"):
     """fp32 [B,4,4,4] rigid device->camera transforms in metres mirroring the syn rig."""
-    g = torch.Generator(device="cpu")
-    g.manual_seed(2000 + seed)
+    noise = torch.empty((B, 4, 3))
+    for b in range(B):                      # one stream per frame: frame b does not depend on the batch size
+        g = torch.Generator(device="cpu")
+        g.manual_seed((2000 + seed) * 100003 + b)
+        noise[b] = torch.randn((4, 3), generator=g) * 0.005
     M = torch.zeros((B, 4, 4, 4), dtype=torch.float32)
     base_t = torch.tensor([[0.06, 0.0, 0.0], [-0.06, 0.0, 0.0], [-0.06, 0.37, 0.0], [0.06, 0.37, 0.0]])
     for v in range(4):
@@ -123,6 +129,6 @@ def synth_coord_trans_mat(B, seed=0, device="cpu"):
         if v >= 2:
             R = torch.diag(torch.tensor([-1.0, -1.0, 1.0]))     # 180 deg about z
         M[:, v, :3, :3] = R
-        M[:, v, :3, 3] = base_t[v] + torch.randn((B, 3), generator=g) * 0.005
+        M[:, v, :3, 3] = base_t[v] + noise[:, v]
         M[:, v, 3, 3] = 1.0
     return M.to(device)

@@ -1,0 +1,132 @@
+"""GPU: G1 generate_target, D1 get_max_preds, H1' head and P3 reprojection through the C-ABI vs the oracles / golden."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import dense_from_sparse, orc_generate_target, orc_get_max_preds, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from egorear_b200 import ops as o
+    return o
+
+
+def test_generate_target_golden_and_oracle(ops, golden, oracle_lib):
+    g = golden["generate_target"]
+    want = dense_from_sparse(g["idx"], g["val"], g["shape"])
+    got = ops.generate_target_batch(g["joints"], 872, 64, 1.0).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # drop-in signature: numpy in, numpy out, first num_joints rows
+    one = ops.generate_target(g["joints"][3], image_size=872, heatmap_size=64, num_joints=15, sigma=1)
+    assert one.shape == (15, 64, 64) and np.array_equal(one, want[3, :15])
+    # general geometry, sigma = 2 (patch comes from the caller's numpy: bit-exact too)
+    want2 = dense_from_sparse(g["idx2"], g["val2"], g["shape2"])
+    got2 = ops.generate_target_batch(g["joints2"], 640, 48, 2).cpu().numpy()
+    assert np.array_equal(got2.view(np.uint32), want2.view(np.uint32))
+    # seeded sweep vs the C oracle, incl. off-image joints (config 4 distribution)
+    from egorear_b200 import synth
+    kp = synth.synth_keypoints(2048, 4, 16, seed=1)
+    got = ops.generate_target_batch(kp).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), orc_generate_target(oracle_lib, kp).view(np.uint32))
+
+
+def test_generate_target_properties_full_size(ops):
+    """size-independent properties on a large batch: support <= 49, max == 1.0 or clipped, decode(render) == mu"""
+    from egorear_b200 import synth
+    N = 16384
+    kp = torch.from_numpy(synth.synth_keypoints(N, 4, 16, seed=2)).cuda()
+    hm = ops.generate_target_batch(kp)                                    # [N,4,16,64,64] = 17 GB? no: 4.3 GB
+    nnz = (hm != 0).flatten(3).sum(-1)
+    assert int(nnz.max()) <= 49
+    mu = torch.trunc(kp / 13.625 + 0.5)                                  # int() truncation
+    inside = ((mu >= 0) & (mu < 64)).all(-1)
+    preds, maxv, valid = ops.get_max_preds(hm.view(N * 4, 16, 64, 64), threshold=1.0, normalize=False)
+    preds = preds.view(N, 4, 16, 2)
+    assert torch.equal(preds[inside], mu[inside].float())                 # peak sits on mu, value exactly 1.0
+    assert bool((maxv.view(N, 4, 16)[inside] == 1.0).all()) and bool(valid.view(N, 4, 16)[inside].all())
+    gone = ((mu - 3 >= 64) | (mu + 4 < 0)).any(-1)
+    assert int(nnz[gone].sum()) == 0                                      # the skip branch leaves an all-zero map
+
+
+def test_generate_target_rejects_bad_sigma(ops):
+    from egorear_b200._lib import EgrError
+    with pytest.raises(EgrError):
+        ops.generate_target_batch(np.zeros((1, 1, 2)), sigma=0.5)
+
+
+def test_get_max_preds_golden_and_edges(ops, golden, oracle_lib):
+    from test_oracle import _decode_inputs
+    g = golden["get_max_preds"]
+    hm = _decode_inputs().cuda()
+    for tag, (thr, norm) in {"model": (0.5, True), "eval": (1.0, False)}.items():
+        p, m, v = ops.get_max_preds(hm, threshold=thr, normalize=norm)
+        assert np.array_equal(p.cpu().numpy().view(np.uint32), g["preds_" + tag].view(np.uint32))
+        assert np.array_equal(m.cpu().numpy().view(np.uint32), g["maxvals_" + tag].view(np.uint32))
+        assert np.array_equal(v.cpu().numpy(), g["valid_" + tag])
+    # squeeze quirk of loss.py:142 and the asserts
+    p, m, v = ops.get_max_preds(hm[:1, :1])
+    assert m.shape == () and v.shape == ()
+    with pytest.raises(AssertionError):
+        ops.get_max_preds(hm[0])
+    # bit-exact indices vs torch.max on the device and vs the C oracle, at a large size
+    g2 = torch.Generator(device="cuda").manual_seed(3)
+    big = torch.randn((4096, 15, 64, 64), generator=g2, device="cuda")
+    big[::7, 3] = big[::7, 3].round()                                     # many exact ties
+    p, m, v, idx = ops.get_max_preds(big, 0.5, True, return_index=True)
+    tm, ti = torch.max(big.view(4096, 15, -1), dim=2)
+    assert torch.equal(idx.long(), ti) and torch.equal(m, tm)
+    op, om, ov, oi = orc_get_max_preds(oracle_lib, big[:64].cpu().numpy(), 0.5, True)
+    assert np.array_equal(p[:64].cpu().numpy(), op) and np.array_equal(idx[:64].cpu().numpy(), oi)
+    assert np.array_equal(v[:64].cpu().numpy(), ov)
+
+
+def test_heatmap_head_1x1(ops):
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn((8, 128, 64, 64), generator=g)
+    w = torch.randn((15, 128, 1, 1), generator=g) * 0.1
+    b = torch.randn((15,), generator=g)
+    want = torch.nn.functional.conv2d(feat, w, b)
+    got = ops.heatmap_head_1x1(feat.cuda(), w.cuda(), b.cuda()).cpu()
+    assert rel_err(got.numpy(), want.numpy()) < 1e-5
+
+
+def test_reproject_fisheye_vs_oracle(ops):
+    from egorear_b200 import calib, synth
+    from oracle import model_ref
+    g = torch.Generator().manual_seed(4)
+    B = 64
+    pts = torch.stack((torch.rand((B, 16), generator=g) * 120 - 60, torch.rand((B, 16), generator=g) * 120 - 60,
+                       torch.rand((B, 16), generator=g) * 190 - 30), dim=-1)
+    cams = calib.load_calibration(None)
+    for cam in ("ego4view_syn", "ego4view_rw", "ego4view_syn_stereo_front", "ego4view_syn_stereo_back", "ego4view_rw_stereo_back"):
+        V = 4 if cam in ("ego4view_syn", "ego4view_rw") else 2
+        ctm = synth.synth_coord_trans_mat(B, seed=1)[:, :V].contiguous() if "rw" in cam else None
+        p_ref = pts.clone()
+        a_ref, v_ref = model_ref.reproject(p_ref, cams, cam, ctm)
+        p_gpu = pts.clone().cuda()
+        a, v = ops.reproject_fisheye(p_gpu, cam, ctm.cuda() if ctm is not None else None)
+        assert float((a.cpu() - a_ref).abs().max()) < 2e-6, cam
+        flips = (v.cpu() != v_ref)
+        assert int(flips.sum()) == 0 or float((a_ref[flips] * (1 - a_ref[flips])).abs().max()) < 1e-5   # only on the border
+        assert torch.allclose(p_gpu.cpu(), p_ref, atol=1e-5), cam         # the in-place quirk is reproduced
+        assert 0.05 < float(v_ref.float().mean()) < 0.95
+    with pytest.raises(ValueError):
+        ops.reproject_fisheye(pts.cuda(), "pinhole")
+    with pytest.raises(RuntimeError):
+        ops.reproject_fisheye(pts.cuda(), "ego4view_rw", synth.synth_coord_trans_mat(B).double().cuda())
+
+
+def test_msda_op_vs_oracle(ops):
+    from oracle import model_ref
+    g = torch.Generator().manual_seed(3)
+    for (B, nh, hd, Q) in ((3, 4, 64, 15), (37, 4, 32, 16)):              # odd batch: no im2col_step restriction
+        value = torch.randn((B, 4096, nh, hd), generator=g)
+        loc = torch.rand((B, Q, nh, 1, 16, 2), generator=g) * 1.3 - 0.15
+        aw = torch.softmax(torch.randn((B, Q, nh, 16), generator=g), -1).view(B, Q, nh, 1, 16)
+        want = model_ref.ms_deform_attn(value, 64, 64, loc, aw)
+        got = ops.MultiScaleDeformableAttnFunction.apply(value.cuda(), torch.tensor([[64, 64]]).cuda(), torch.tensor([0]).cuda(),
+                                                         loc.cuda(), aw.cuda(), 32).cpu()
+        assert rel_err(got.numpy(), want.numpy()) < 1e-5
