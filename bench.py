@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — EgoRear hot path on B200: 4-view frames/s of the mvfex-n1_jqa heatmap + pose3d forward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload W] [--batch B]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A step is one pass of the hot path over one batch of synthetic backbone features per GPU
+(configs[1] of BASELINE.json: ego4view_syn_heatmap_mvfex-n1_jqa, batch 64, + the pose3d lifting of the metric):
+H1 D1 Q1 M1 F1 A1-3 T1 R1 H2 -> decode -> P1-P4 -> pack -> (N>1) one NCCL all-gather of 672 B/frame.
+Frames shard across ranks with no other collective ("scaling": "weak", fixed 64 frames per GPU).
+
+Rank 0 prints ONE JSON line: value = whole-job frames/s with inputs resident in HBM; e2e = the same through the
+public API with pinned-host inputs (H2D + D2H inside the timed region); roofline = dominant kernel (CUDA events,
+stage profiler of the library) against MEASURED_PEAKS.json; cpu_baseline = the CPU implementation on the host cores
+(live reference when /root/reference exists, else the oracle port) on a bounded sample.
+
+Other workloads (parity-test configs, not the headline): --workload generate_target | decode | pose3d | mvfex.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "4-view frames/sec (heatmap+pose3d fwd)"
+UNIT = "frames/s"
+
+# algorithmic FLOPs per 4-view frame of every dense stage (2*M*N*K, with the 1x1 convs that follow a bilinear x2
+# commuted in front of it), and algorithmic HBM bytes per frame in bf16 mode
+STAGE_FLOPS = {
+    "H1a": 4 * 2 * 4096 * 128 * 128, "H1b": 4 * 2 * 1024 * 256 * 1152, "H1c": 4 * 2 * 1024 * 256 * 256,
+    "H1d": 4 * 2 * 1024 * 128 * 256, "Q1a": 4 * 2 * 15 * 256 * 4096, "F1a": 4 * 2 * 4096 * 256 * 128,
+    "F1b": 4 * 2 * 1024 * 512 * 2304, "F1c": 4 * 2 * 1024 * 128 * 512, "R1a": 4 * 2 * 1024 * 128 * 128,
+    "R1b": 4 * 2 * 1024 * 128 * 128, "H2a": 4 * 2 * 1024 * 256 * 1152, "H2b": 4 * 2 * 1024 * 256 * 256,
+    "H2c": 4 * 2 * 1024 * 128 * 256,
+    "P2a": 4 * 2 * 4096 * 64 * 128, "P2b": 4 * 2 * 1024 * 128 * 576, "P2c": 4 * 2 * 256 * 64 * 128,
+    "P2d": 4 * 2 * 64 * 128 * 576, "P2mlp0": 2 * 2048 * 32768,
+}
+# HBM-bound stages: algorithmic bytes per frame (fp32 in / activation dtype out), act = bytes per activation element
+STAGE_BYTES = {
+    "stage_nhwc": lambda act: 4 * 4096 * 128 * (4 + act),
+    "H1tail": lambda act: 4 * (1024 * 128 * act + 15 * 4096 * (4 + act)),
+    "H2tail": lambda act: 4 * (1024 * 128 * act + 15 * 4096 * 4),
+    "R1tail": lambda act: 4 * (1024 * 128 * act + 4096 * 128 * (4 + act)),
+    "D1": lambda act: 4 * 15 * 4096 * 4,
+    "P_stage_nhwc": lambda act: 4 * 4096 * 128 * (4 + 4) + 4 * 4096 * 128 * (4 + act),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")   # B200_PROFILING.md fallback
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock + throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = get(h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+                time.sleep(0.02)
+        except Exception as e:      # NVML missing: report that instead of dying
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU implementation of the path (cpu_baseline leg and --impl reference arm)
+# --------------------------------------------------------------------------------------------------------
+class CpuPath:
+    """the reference's own modules when /root/reference exists (kind 'reference'), else the oracle port (kind 'port')"""
+
+    def __init__(self, workload="mvfex_pose3d"):
+        import torch
+        from egorear_b200 import calib, synth
+        from egorear_b200.configs import heatmap_mvfex_cfg, pose3d_cfg
+        from egorear_b200.modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
+        from oracle import model_ref, ref_import     # cpu_baseline / reference arm: the one place bench.py runs oracle/
+        self.torch, self.model_ref = torch, model_ref
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.calib = calib.load_calibration(None)
+        self.kind = "port"
+        hm = synth.fill_state_dict(EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(), precision="fp32", build_backbone=False))
+        p3 = synth.fill_state_dict(EgoPoseFormerPose3D(**pose3d_cfg(), precision="fp32"))
+        self.sd_h, self.sd_p = hm.state_dict(), p3.state_dict()
+        self.ref_h = self.ref_p = None
+        if ref_import.available():
+            try:
+                import copy
+                cls = ref_import.import_estimators()
+                cfg = ref_import.load_model_cfg("ego4view_syn_heatmap_mvfex-n1_jqa.yaml")
+                self.ref_h = cls["EgoPoseFormerHeatmapMVFEX"](**copy.deepcopy(cfg)).eval()
+                self.ref_h.load_state_dict({**self.ref_h.state_dict(), **self.sd_h}, strict=True)
+                c3 = ref_import.load_model_cfg("ego4view_syn_pose3d.yaml")["pose3d_cfg"]
+                c3.update(dict(num_views=4, image_size=[256, 256], use_pred_heatmap_init=True, camera_model="ego4view_syn"))
+                self.ref_p = cls["EgoPoseFormerPose3D"](**c3).eval()
+                self.ref_p.load_state_dict(self.sd_p, strict=True)
+                self.get_max_preds = ref_import.import_functions()["get_max_preds"]
+                self.kind = "reference"
+            except Exception as e:      # fall back to the port, say why
+                sys.stderr.write("bench: live reference unusable (%s); timing the oracle port\n" % e)
+                self.ref_h = self.ref_p = None
+
+    def step(self, feat, bfb):
+        torch = self.torch
+        with torch.no_grad():
+            if self.ref_h is not None:
+                self.ref_h.forward_heatmap_feat_estimation = lambda img: (feat, [None, None, None, bfb])
+                lh, lf = self.ref_h(torch.zeros(feat.shape[0], 4, 3, 1, 1))
+                B, V, J, H, W = lh[-1].shape
+                self.get_max_preds(lh[-1].view(B * V, J, H, W), 0.5, False)
+                return self.ref_p(lf[0], lf[-1], lh[-1])[-1]
+            lh, lf, _, _ = self.model_ref.mvfex_hot_path(self.sd_h, feat, bfb)
+            B, V, J, H, W = lh[-1].shape
+            self.model_ref.get_max_preds(lh[-1].view(B * V, J, H, W), 0.5, False)
+            return self.model_ref.pose3d_forward(self.sd_p, lf[0], lf[-1], self.calib, "ego4view_syn")[-1]
+
+
+def cpu_baseline(budget_s=15.0, frames_per_step=2):
+    from egorear_b200 import synth
+    cp = CpuPath()
+    feat, bfb = synth.synth_features(frames_per_step, 4, seed=0)
+    cp.step(feat, bfb)                           # warm-up
+    n, t0 = 0, time.time()
+    while True:
+        cp.step(feat, bfb)
+        n += frames_per_step
+        if time.time() - t0 > budget_s or n >= 64:
+            break
+    dt = time.time() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cp.cores, "kind": cp.kind,
+            "sample": "%d frames (steps of %d) of the same workload, %.1f s, torch fp32 on %d host threads" % (n, frames_per_step, dt, cp.cores)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    from egorear_b200 import synth
+    cp = CpuPath()
+    fps = 2
+    feat, bfb = synth.synth_features(fps, 4, seed=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cp.step(feat, bfb)
+    steps = max(1, min(args.steps, 8))           # bounded: each step is a 2-frame sample of the workload
+    t0 = time.time()
+    for _ in range(steps):
+        cp.step(feat, bfb)
+    dt = time.time() - t0
+    v = steps * fps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample_frames_per_step": fps, "note": "CPU implementation on host cores"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cp.cores, "kind": cp.kind,
+                             "sample": "%d steps x %d frames, torch fp32, %d host threads" % (steps, fps, cp.cores)},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(args):
+    return {"mvfex_pose3d": "ego4view_syn_heatmap_mvfex-n1_jqa + ego4view_syn_pose3d forward (hot path, backbone features as inputs), "
+                            "4 views, batch %d/GPU" % args.batch,
+            "mvfex": "ego4view_syn_heatmap_mvfex-n1_jqa hot path, batch %d/GPU" % args.batch,
+            "pose3d": "ego4view_syn_pose3d lifting, batch %d/GPU" % args.batch,
+            "generate_target": "generate_target sweep, 4 views x 16 joints, %d frames/step/GPU" % args.batch,
+            "decode": "get_max_preds, 4 views x 15 joints, %d frames/step/GPU" % args.batch}[args.workload]
+
+
+# --------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode"])
+    ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
+    ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = {"mvfex_pose3d": 64, "mvfex": 64, "pose3d": 1024, "generate_target": 8192, "decode": 8192}[args.workload]
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    from egorear_b200 import _lib, dist as egd, ops, synth
+    from egorear_b200.pipeline import HotPathPipeline
+
+    rank, local_rank, world = egd.init()
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    peaks = load_peaks()
+    B = args.batch
+    act = 2 if args.precision == "bf16" else 4
+    e2e_fn = None
+
+    if args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
+        pipe = HotPathPipeline(4, "ego4view_syn", args.precision, dev)
+        nb = min(B, 64)
+        feat_h, bfb_h = synth.synth_features(nb, 4, seed=100 + rank)        # [nb,4,128,64,64] = 8.4 MB/frame
+        if nb < B:
+            feat_h, bfb_h = feat_h.repeat(B // nb, 1, 1, 1, 1), bfb_h.repeat(B // nb, 1, 1, 1, 1)
+        feat_h, bfb_h = feat_h.pin_memory(), bfb_h.pin_memory()
+        feat, bfb = feat_h.to(dev), bfb_h.to(dev)
+        if args.workload == "pose3d":
+            with torch.no_grad():
+                ff = torch.relu(torch.randn_like(feat))
+
+            def step(f=feat, b=bfb):
+                preds = pipe.pose3d(f, ff, None)
+                return egd.gather_rows(preds[-1].reshape(B, -1), world)
+        elif args.workload == "mvfex":
+            def step(f=feat, b=bfb):
+                lh, lf = pipe.heatmap.forward_from_feats(f, b)
+                p, _, _ = ops.get_max_preds(lh[-1].view(B * 4, 15, 64, 64), 0.5, False)
+                return egd.gather_rows(p.reshape(B, -1), world)
+        else:
+            def step(f=feat, b=bfb):
+                return egd.gather_rows(pipe(f, b)["packed"], world)
+        pipe.freeze() if args.workload != "pose3d" else None
+        in_bytes = feat_h.numel() * 4 + bfb_h.numel() * 4
+        l2_note = "inputs %.0f MB + activations >> 126 MB L2 (no flush needed)" % (in_bytes / 1e6)
+
+        def e2e_fn():
+            f = feat_h.to(dev, non_blocking=True)
+            b = bfb_h.to(dev, non_blocking=True)
+            return step(f, b).cpu()
+    elif args.workload == "generate_target":
+        kp_h = torch.from_numpy(synth.synth_keypoints(B, 4, 16, seed=rank)).pin_memory()
+        kp = kp_h.to(dev)
+        ring = [torch.empty((B, 4, 16, 64, 64), dtype=torch.float32, device=dev) for _ in range(2)]   # 2 x 8.6 GB at B=8192
+        cnt = [0]
+
+        def step(k=kp):
+            cnt[0] += 1
+            return ops.generate_target_batch(k, 872, 64, 1.0, out=ring[cnt[0] & 1])
+        in_bytes = kp_h.numel() * 8
+        l2_note = "output ring 2 x %.1f GB >> L2" % (ring[0].numel() * 4 / 1e9)
+
+        def e2e_fn():
+            out = step(kp_h.to(dev, non_blocking=True))
+            return out[:, :, :, 0, 0].sum().cpu()                            # checksum read-back; maps stay on device
+    else:  # decode
+        kp = torch.from_numpy(synth.synth_keypoints(B, 4, 15, seed=rank)).to(dev)
+        hm = ops.generate_target_batch(kp).view(B * 4, 15, 64, 64)
+        hm_h = None
+        in_bytes = hm.numel() * 4
+        l2_note = "input %.1f GB >> L2" % (in_bytes / 1e9)
+
+        def step(h=hm):
+            return ops.get_max_preds(h, 0.5, True)[0]
+
+    torch.cuda.synchronize(dev)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    egd.barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    sampler.start()
+    time.sleep(0.05)
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    egd.barrier()
+    launches = _lib.launch_count() - l0
+    ms = egd.max_over_ranks(ev0.elapsed_time(ev1), dev)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- e2e: pinned host inputs -> H2D -> hot path -> D2H of the step's result, every step ----
+    e2e = None
+    if e2e_fn is not None:
+        for _ in range(2):
+            r = e2e_fn()
+        torch.cuda.synchronize(dev)
+        egd.barrier()
+        n_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            r = e2e_fn()
+        torch.cuda.synchronize(dev)
+        egd.barrier()
+        dt = egd.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+        e2e = {"value": world * B * n_e2e / (dt / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(in_bytes),
+               "d2h_bytes_per_step": int(r.numel() * r.element_size()), "steps": n_e2e}
+
+    # ---- per-stage timing of the same step through the library's stage profiler (rank 0) ----
+    roofline, stages = None, None
+    if rank == 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
+        import ctypes
+        lib.egr_profile_enable(1)
+        n_prof = 5
+        for _ in range(n_prof):
+            step()
+        torch.cuda.synchronize(dev)
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(lib.egr_profile_read(buf, len(buf)))
+        lib.egr_profile_enable(0)
+        stages = {}
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, tot, cnt = item.split(":")
+                stages[name] = float(tot) / n_prof           # ms per step
+        total = sum(stages.values())
+        top = max(stages, key=stages.get)
+        t_s = stages[top] / 1e3
+        if top in STAGE_FLOPS:
+            ach = STAGE_FLOPS[top] * B / t_s / 1e12
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tf_sust"], "traffic": None}
+        elif top in STAGE_BYTES:
+            ach = STAGE_BYTES[top](act) * B / t_s / 1e9
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm"], "traffic": None}
+        else:
+            roofline = {"kernel": top, "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
+        roofline.update({"peak_source": peaks["src"] + (" (sustained bf16 GEMM)" if roofline["bound"] == "tensor" else ""),
+                         "share_of_step": stages[top] / total, "ms_per_launch": stages[top]})
+    elif rank == 0:
+        t_s = ms / 1e3 / args.steps
+        per_frame = 4 * 16 * 4096 * 4 + 4 * 16 * 16 if args.workload == "generate_target" else 4 * 15 * 4096 * 4 + 4 * 15 * 13
+        ach = per_frame * B / t_s / 1e9
+        roofline = {"kernel": args.workload, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "share_of_step": 1.0,
+                    "ms_per_launch": t_s * 1e3}
+
+    if rank != 0:
+        return 0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and args.workload == "mvfex_pose3d":
+        cpu = cpu_baseline()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision if args.workload in ("mvfex_pose3d", "mvfex", "pose3d") else "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "frames_per_gpu_per_step": B, "precision": args.precision,
+                       "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
+                       "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
+            "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "stages_ms": stages}
+    print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

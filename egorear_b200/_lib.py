@@ -24,6 +24,8 @@ class EgrError(RuntimeError):
 SIGNATURES = {
     "egr_last_error": (c_char_p, []),
     "egr_version": (c_int, []),
+    "egr_profile_enable": (c_int, [c_int]),
+    "egr_profile_read": (c_int, [ctypes.c_char_p, c_int]),
     "egr_device_check": (c_int, [POINTER(c_int), POINTER(c_int)]),
     "egr_launch_count": (c_int64, []),
     "egr_generate_target": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_double, c_void_p, c_void_p]),

@@ -40,6 +40,12 @@ extern std::atomic<int64_t> g_launches;          // kernels launched by this lib
                                __FILE__, __LINE__);                                                \
     } while (0)
 
+// Stage profiler (bench.py roofline): when enabled, prof_mark(name, stream) records a CUDA event on the launch
+// stream; the time between a mark and the next one is attributed to `name` (nullptr closes the last interval).
+void prof_mark(const char* name, cudaStream_t st);
+extern int g_prof_on;
+#define EGR_MARK(name, st) do { if (::egr::g_prof_on) ::egr::prof_mark((name), (st)); } while (0)
+
 int require_device();   // EGR_OK iff current device is sm_100; caches the answer
 int sm_count();
 

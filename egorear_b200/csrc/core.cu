@@ -1,6 +1,8 @@
 // Error plumbing, device check and misc C-ABI entry points.
 #include "common.cuh"
 #include <mutex>
+#include <vector>
+#include <map>
 
 namespace egr {
 
@@ -52,6 +54,22 @@ int require_device() {
 
 int sm_count() { return g_sm_count; }
 
+// ---- stage profiler ----
+int g_prof_on = 0;
+struct Mark { std::string name; cudaEvent_t ev; bool closing; };
+static std::vector<Mark> g_marks;
+static std::vector<cudaEvent_t> g_ev_pool;
+static std::mutex g_prof_mu;
+
+void prof_mark(const char* name, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t ev;
+    if (!g_ev_pool.empty()) { ev = g_ev_pool.back(); g_ev_pool.pop_back(); }
+    else if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    g_marks.push_back(Mark{name ? name : "", ev, name == nullptr});
+}
+
 }  // namespace egr
 
 extern "C" const char* egr_last_error(void) { return egr::last_error().c_str(); }
@@ -62,4 +80,39 @@ extern "C" int egr_device_check(int* cc, int* sms) {
     if (cc) *cc = egr::g_cc;
     if (sms) *sms = egr::g_sm_count;
     return rc;
+}
+
+extern "C" int egr_profile_enable(int on) {
+    egr::g_prof_on = on ? 1 : 0;
+    return EGR_OK;
+}
+
+// Aggregates the recorded intervals as "name:total_ms:count;" pairs into buf (NUL terminated), clears the marks.
+// Synchronises on the last recorded event.
+extern "C" int egr_profile_read(char* buf, int cap) {
+    using namespace egr;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    std::map<std::string, std::pair<double, int>> agg;
+    std::vector<std::string> order;
+    if (!g_marks.empty()) cudaEventSynchronize(g_marks.back().ev);
+    for (size_t i = 0; i + 1 < g_marks.size(); ++i) {
+        if (g_marks[i].closing) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_marks[i].ev, g_marks[i + 1].ev) != cudaSuccess) { cudaGetLastError(); continue; }
+        auto it = agg.find(g_marks[i].name);
+        if (it == agg.end()) { agg[g_marks[i].name] = std::make_pair((double)ms, 1); order.push_back(g_marks[i].name); }
+        else { it->second.first += ms; it->second.second += 1; }
+    }
+    for (auto& m : g_marks) g_ev_pool.push_back(m.ev);
+    g_marks.clear();
+    std::string out;
+    char tmp[256];
+    for (auto& n : order) {
+        snprintf(tmp, sizeof(tmp), "%s:%.6f:%d;", n.c_str(), agg[n].first, agg[n].second);
+        out += tmp;
+    }
+    if (!buf || cap <= 0) return EGR_OK;
+    if ((int)out.size() >= cap) return egr::fail(EGR_ERR_INVALID, "profile_read: buffer too small (%d needed)", (int)out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return EGR_OK;
 }

@@ -190,17 +190,20 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     const int bf = (prec == EGR_PREC_BF16);
     int rc;
     GemmDesc d;
+    EGR_MARK("Q1a", st);
     // Q1a: relu(heatmap_proj.0(heatmap))  [G][B*J][4096] -> [G][B*J][256] fp32
     d = GemmDesc();
     d.A = w.hmT; d.lda = FHW; d.M = B * J; d.D = w.q1; d.ldd = EMB; d.epi = EPI_RELU;
     d.groups = G; d.a_gs = (int64_t)B * J * FHW; d.d_gs = (int64_t)B * J * EMB;
     if ((rc = run_gemm(d, h->hp0, r0, prec, /*out_f32=*/true, st))) return rc;
+    EGR_MARK("tokens", st);
     // Q1 rest + A1 A2 A3 + post_norm
     MvfTokenArgs ta{};
     ta.B = B; ta.V = h->V; ta.J = J; ta.H = FH; ta.W = FW; ta.r0 = r0; ta.G = G;
     ta.q1 = w.q1; ta.bfb = bfb; ta.bfb_bs = bfb_bs; ta.bfb_gs = bfb_gs; ta.bfb_hw = 64;
     ta.anchors = anchors; ta.valid = valid; ta.X = w.Xh; ta.xT = w.xT; ta.w = h->d_tokw;
     if ((rc = launch_mvf_tokens(ta, bf, st))) return rc;
+    EGR_MARK("T1", st);
     // T1: 1x1(15->64) ReLU, then the 1x1(64->128) commuted in front of the bilinear x2 (both linear)
     d = GemmDesc();
     d.A = w.xT; d.lda = 16; d.M = B * NPOS; d.D = w.h1t; d.ldd = 64; d.epi = EPI_RELU;
@@ -215,47 +218,58 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
         t.W = h->t1_3.f32 + (int64_t)r0 * 128 * 64; t.bias = h->t1_3.bias + r0 * 128; t.w_gs = 128 * 64; t.b_gs = 128;
         if ((rc = gemm_simt(t, bf, bf, st))) return rc;
     }
+    EGR_MARK("F1a", st);
     // F1a: 1x1(128->256) ReLU @64x64
     d = GemmDesc();
     d.A = Xown; d.lda = FC; d.M = B * FHW; d.D = w.a1; d.ldd = 256; d.epi = EPI_RELU;
     d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * FHW * 256;
     if ((rc = run_gemm(d, h->f1_0, r0, prec, false, st))) return rc;
+    EGR_MARK("F1b", st);
     // F1b: 3x3 s2 (256->512) ReLU -> 32x32
     d = GemmDesc();
     d.A = w.a1; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = 256; d.M = B * 1024; d.D = w.b1; d.ldd = 512;
     d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * 256; d.d_gs = (int64_t)B * 1024 * 512;
     if ((rc = run_gemm(d, h->f1_2, r0, prec, false, st))) return rc;
+    EGR_MARK("F1c", st);
     // F1c: 1x1(512->128) ReLU, fused with "+ offset_pred": + relu(up2(t1))   (:715 offset_pred + frame_feat)
     d = GemmDesc();
     d.A = w.b1; d.lda = 512; d.M = B * 1024; d.D = w.ff; d.ldd = 128; d.epi = EPI_RELU_ADDUP; d.aux = w.t1;
     d.Hout = 32; d.Wout = 32; d.groups = G; d.a_gs = (int64_t)B * 1024 * 512; d.d_gs = (int64_t)B * 1024 * 128;
     d.aux_gs = (int64_t)B * NPOS * 128;
     if ((rc = run_gemm(d, h->f1_4, r0, prec, false, st))) return rc;
+    EGR_MARK("R1a", st);
     // R1a: 1x1(128->128) ReLU @32x32 ; R1b: second 1x1 commuted in front of the upsample
     d = GemmDesc();
     d.A = w.ff; d.lda = 128; d.M = B * 1024; d.D = w.r1a; d.ldd = 128; d.epi = EPI_RELU;
     d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128;
     if ((rc = run_gemm(d, h->r1_0, r0, prec, false, st))) return rc;
+    EGR_MARK("R1b", st);
     d.A = w.r1a; d.D = w.z; d.epi = EPI_NONE;
     if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st))) return rc;
+    EGR_MARK("R1tail", st);
     // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output + channels-last copy for H2
     if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, st))) return rc;
+    EGR_MARK("H2a", st);
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
     d.A = w.refn; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = B * 1024; d.D = w.b1; d.ldd = 256;
     d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256;
     if ((rc = run_gemm(d, h->h2_0, r0, prec, false, st))) return rc;
+    EGR_MARK("H2b", st);
     d = GemmDesc();
     d.A = w.b1; d.lda = 256; d.M = B * 1024; d.D = w.c1; d.ldd = 256; d.epi = EPI_RELU;
     d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 256;
     if ((rc = run_gemm(d, h->h2_2, r0, prec, false, st))) return rc;
+    EGR_MARK("H2c", st);
     d = GemmDesc();
     d.A = w.c1; d.lda = 256; d.M = B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
     d.groups = G; d.a_gs = (int64_t)B * 1024 * 256; d.d_gs = (int64_t)B * 1024 * 128;
     if ((rc = run_gemm(d, h->h2_5, r0, prec, false, st))) return rc;
+    EGR_MARK("H2tail", st);
     int wsel[4] = {r0, r0 + 1, r0 + 2, r0 + 3};
     if ((rc = head_up_conv(w.z, bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
         return rc;
+    EGR_MARK(nullptr, st);
     return EGR_OK;
 }
 
@@ -408,30 +422,37 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     cudaStream_t st = (cudaStream_t)stream;
     const int V = h->V, J = h->J, prec = h->prec, bf = (prec == EGR_PREC_BF16);
     int rc;
+    EGR_MARK("stage_nhwc", st);
     // S0: NCHW fp32 -> view-major channels-last staging copy
     if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, bf, st))) return rc;
+    EGR_MARK("H1a", st);
     // H1: init heads, one group per weight set (front: views 0-1, back: views 2-3), two views per group
     const int G1 = h->head_sets, vpg = V / G1;
     GemmDesc d;
     d.A = w.Xh; d.lda = FC; d.M = vpg * B * FHW; d.D = w.h1a; d.ldd = 128; d.epi = EPI_RELU;
     d.groups = G1; d.a_gs = d.d_gs = (int64_t)vpg * B * FHW * FC;
     if ((rc = run_gemm(d, h->h1_0, 0, prec, false, st))) return rc;
+    EGR_MARK("H1b", st);
     d = GemmDesc();
     d.A = w.h1a; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = vpg * B * 1024; d.D = w.b1; d.ldd = 256;
     d.epi = EPI_RELU; d.groups = G1; d.a_gs = (int64_t)vpg * B * FHW * FC; d.d_gs = (int64_t)vpg * B * 1024 * 256;
     if ((rc = run_gemm(d, h->h1_2, 0, prec, false, st))) return rc;
+    EGR_MARK("H1c", st);
     d = GemmDesc();
     d.A = w.b1; d.lda = 256; d.M = vpg * B * 1024; d.D = w.c1; d.ldd = 256; d.epi = EPI_RELU;
     d.groups = G1; d.a_gs = d.d_gs = (int64_t)vpg * B * 1024 * 256;
     if ((rc = run_gemm(d, h->h1_4, 0, prec, false, st))) return rc;
+    EGR_MARK("H1d", st);
     d = GemmDesc();
     d.A = w.c1; d.lda = 256; d.M = vpg * B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
     d.groups = G1; d.a_gs = (int64_t)vpg * B * 1024 * 256; d.d_gs = (int64_t)vpg * B * 1024 * 128;
     if ((rc = run_gemm(d, h->h1_7, 0, prec, false, st))) return rc;
+    EGR_MARK("H1tail", st);
     int wsel[4] = {0, 0, 1, 1};
     if (G1 == 1) wsel[2] = wsel[3] = 0;
     if ((rc = head_up_conv(w.z, bf, h->h1_9w, h->h1_9b, wsel, B, V, 32, 32, FC, J, hm_init, (int64_t)V * J * FHW,
                            (int64_t)J * FHW, w.hmT, st))) return rc;
+    EGR_MARK("D1", st);
     // D1: anchors from heatmap_for_anchor when given (:293-296), else from the init heatmap
     const float* src = heatmap_for_anchor ? heatmap_for_anchor : hm_init;
     float* anch = anchors_2d ? anchors_2d : w.anch;

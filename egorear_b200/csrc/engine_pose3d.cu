@@ -244,6 +244,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     const int prec = p2_prec(h), bf = (prec == EGR_PREC_BF16);   // proposal-branch dtype
     const int VB = V * B;
     int rc;
+    EGR_MARK("P_stage_nhwc", st);
     // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
     const float* sampled = h->use_init ? feats_init : feats_final;
     if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, bf, st))) return rc;
@@ -252,25 +253,32 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
         if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
         Xs = w.Xi;
     }
+    EGR_MARK("P2a", st);
     // P2 conv_frame_feat
     GemmDesc d;
     d.A = w.Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU;
     if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
+    EGR_MARK("P2b", st);
     d = GemmDesc();
     d.A = w.p0; d.amode = A_CONV3S2; d.Hin = 64; d.Win = 64; d.Cin = 64; d.M = VB * 1024; d.D = w.p2; d.ldd = 128; d.epi = EPI_RELU;
     if ((rc = run_gemm(d, h->c2, 0, prec, false, st))) return rc;
+    EGR_MARK("P2pool", st);
     if ((rc = maxpool2_nhwc(w.p2, w.p3, bf, VB, 32, 32, 128, st))) return rc;
+    EGR_MARK("P2c", st);
     d = GemmDesc();
     d.A = w.p3; d.lda = 128; d.M = VB * 256; d.D = w.p5; d.ldd = 64; d.epi = EPI_RELU;
     if ((rc = run_gemm(d, h->c5, 0, prec, false, st))) return rc;
+    EGR_MARK("P2d", st);
     d = GemmDesc();
     d.A = w.p5; d.amode = A_CONV3S2; d.Hin = 16; d.Win = 16; d.Cin = 64; d.M = VB * 64; d.D = w.p7; d.ldd = 128; d.epi = EPI_RELU;
     if ((rc = run_gemm(d, h->c7, 0, prec, false, st))) return rc;
+    EGR_MARK("P2mlp0", st);
     // mlp_pred: K-split over the V view blocks of p7 ([V][B][64*128])
     d = GemmDesc();
     d.A = w.p7; d.lda = 64 * 128; d.kblk = 64 * 128; d.kblk_stride = (int64_t)B * 64 * 128; d.M = B; d.D = w.m0; d.ldd = h->m0.N;
     d.epi = EPI_GELU;
     if ((rc = run_gemm(d, h->m0, 0, prec, /*out_f32=*/true, st))) return rc;
+    EGR_MARK("P2mlp12", st);
     {   // the two small Linears stay fp32 SIMT in every precision
         GemmDesc t;
         t.A = w.m0; t.lda = h->m1.K; t.M = B; t.N = h->m1.N; t.K = h->m1.K; t.W = h->m1.f32; t.bias = h->m1.bias;
@@ -281,6 +289,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
         t.D = preds; t.ldd = h->m2.N; t.epi = EPI_NONE;     // preds[0] = proposal
         if ((rc = gemm_simt(t, 0, 0, st))) return rc;
     }
+    EGR_MARK("P4tokens", st);
     // P3 + P4
     PoseTokenArgs ta{};
     ta.B = B; ta.V = V; ta.J = J; ta.H = PH; ta.W = PW; ta.L = h->L; ta.is_rw = is_rw;
@@ -288,6 +297,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     ta.ctm = coord_trans_mat; ta.mlp_pred = preds; ta.preds = preds; ta.X = Xs; ta.w = h->d_w;
     ta.dbg_anchors = w.anch; ta.dbg_valid = w.valid;
     if ((rc = launch_pose_tokens(ta, bfs, st))) return rc;
+    EGR_MARK(nullptr, st);
     const int64_t s = bf ? 2 : 4;
     h->dbg["p7"] = std::make_pair(w.p7, (int64_t)VB * 64 * 128 * s);
     h->dbg["p0"] = std::make_pair(w.p0, (int64_t)VB * PHW * 64 * s);

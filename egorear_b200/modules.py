@@ -442,7 +442,11 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         if self._engine is not None:       # tensors were re-created (.cuda(), .float(), ...): re-register
-            self._engine.set_params(self.hot_path_state())
+            st = self.hot_path_state()
+            if all(v.is_cuda for v in st.values()):
+                self._engine.set_params(st)
+            else:
+                self._engine = None        # moved off the GPU: the engine is rebuilt when it comes back
         return out
 
     def get_anchors_2d_from_hm(self, heatmap):           # :128-143
@@ -541,7 +545,11 @@ class EgoPoseFormerPose3D(nn.Module):
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         if self._engine is not None:
-            self._engine.set_params(self.hot_path_state())
+            st = self.hot_path_state()
+            if all(v.is_cuda for v in st.values()):
+                self._engine.set_params(st)
+            else:
+                self._engine = None
         return out
 
     def forward(self, frame_feats_init, frame_feats_final, heatmap, coord_trans_mat=None, origin_3d=None):

@@ -1,0 +1,44 @@
+"""The frame-sharded inference hot path as one callable: backbone features in, 2D + 3D joints out.
+
+    mvfex refinement (H1 D1 Q1 M1 F1 A1-3 T1 R1 H2)  ->  decode of the refined heatmap (D1)
+    -> pose3d lifting (P1-P4)  ->  packed [B, V*15*2 + 16*3] fp32 row per frame (the all-gather payload)
+
+Used by bench.py, __graft_entry__.smoke() and the multi-GPU harness (egorear_b200/dist.py).
+"""
+import torch
+
+from . import ops, synth
+from .configs import heatmap_mvfex_cfg, pose3d_cfg
+from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
+
+
+class HotPathPipeline:
+    def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True):
+        self.V, self.camera_model, self.precision = num_views, camera_model, precision
+        self.heatmap = EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(num_views, camera_model), precision=precision,
+                                                 build_backbone=False)
+        self.pose3d = EgoPoseFormerPose3D(**pose3d_cfg(num_views, camera_model), precision=precision)
+        if synthetic_weights:
+            synth.fill_state_dict(self.heatmap)
+            synth.fill_state_dict(self.pose3d)
+        self.heatmap = self.heatmap.to(device).eval()
+        self.pose3d = self.pose3d.to(device).eval()
+
+    def freeze(self):
+        """weights will not change any more: skip the per-call parameter-version check"""
+        for m in (self.heatmap, self.pose3d):
+            m.engine()._sync_params()
+            m.engine().frozen = True
+        return self
+
+    @torch.no_grad()
+    def forward(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None):
+        list_hm, list_ff = self.heatmap.forward_from_feats(feat, bfb, heatmap_for_anchor)
+        B, V, J, H, W = list_hm[-1].shape
+        pts2d, maxvals, valid = ops.get_max_preds(list_hm[-1].view(B * V, J, H, W), threshold=0.5, normalize=False)
+        preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat)
+        packed = ops.pack_joints(pts2d.view(B, V * J * 2), preds3d[-1])
+        return dict(packed=packed, joints2d=pts2d.view(B, V, J, 2), pose3d=preds3d[-1], list_hm=list_hm, list_ff=list_ff,
+                    list_pose3d=preds3d)
+
+    __call__ = forward

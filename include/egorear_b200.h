@@ -46,6 +46,10 @@ const char* egr_last_error(void);
  * 0 routes bf16 activations through the SIMT GEMM instead */
 int         egr_set_option(const char* key, int value);
 int         egr_version(void);
+/* stage profiler for bench.py: while enabled the engines record CUDA events between their stages on the launch
+ * stream; egr_profile_read aggregates them as "stage:total_ms:count;" into buf (synchronises) and clears them */
+int         egr_profile_enable(int on);
+int         egr_profile_read(char* buf, int cap);
 /* 0 when the current CUDA device is an sm_100 GPU; fills *sm_count / *cc when non-NULL */
 int         egr_device_check(int* cc_major_minor, int* sm_count);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */

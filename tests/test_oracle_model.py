@@ -7,17 +7,7 @@ from conftest import orc_generate_target, rel_err
 from egorear_b200 import calib, modules, synth
 from oracle import model_ref, ref_import
 
-MVF_CFG = dict(input_dims=128, embed_dims=256, num_former_layers=1, joint_query_adaptation=True,
-               mvf_transformer_cfg=dict(cross_attn_cfg=dict(num_heads=4, batch_first=True),
-                                        spatial_attn_cfg=dict(num_heads=4, batch_first=True),
-                                        ffn_cfg=dict(feedforward_dims=512, num_fcs=2, ffn_drop=0.0)))
-POSE_CFG = dict(num_joints=16, input_dims=128, embed_dims=128, mlp_dims=1024, mlp_dropout=0.0, num_mlp_layers=2,
-                num_former_layers=3, num_pred_mlp_layers=2, feat_down_stride=4, norm_mlp_pred=False, coor_norm_max=None,
-                coor_norm_min=None, conv_heatmap_dim_init=32, use_mlp_avgpool=False, use_mlp_heatmap=False,
-                camera_calib_file_dir_path=None,
-                transformer_cfg=dict(cross_attn_cfg=dict(num_heads=4, batch_first=True),
-                                     spatial_attn_cfg=dict(num_heads=4, batch_first=True),
-                                     ffn_cfg=dict(feedforward_dims=512, num_fcs=2, ffn_drop=0.0)))
+from egorear_b200.configs import MVF_CFG, POSE3D_CFG as POSE_CFG
 
 
 def build_mvfex(V=4, precision="fp32"):
