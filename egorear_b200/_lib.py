@@ -14,6 +14,20 @@ LIB_PATH = os.path.join(_HERE, "libegorear_b200.so")
 _lib = None
 
 
+class DenseDesc(ctypes.Structure):
+    """struct egr_dense_desc (include/egorear_b200.h)"""
+    _fields_ = [("A", c_void_p), ("W", c_void_p), ("bias", c_void_p), ("D", c_void_p), ("aux", c_void_p),
+                ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("lda", c_int64), ("ldd", c_int64),
+                ("amode", ctypes.c_int32), ("epi", ctypes.c_int32),
+                ("kblk", ctypes.c_int32), ("kblk_stride", c_int64),
+                ("Hin", ctypes.c_int32), ("Win", ctypes.c_int32), ("Cin", ctypes.c_int32),
+                ("Hout", ctypes.c_int32), ("Wout", ctypes.c_int32),
+                ("groups", ctypes.c_int32),
+                ("a_gs", c_int64), ("w_gs", c_int64), ("b_gs", c_int64), ("d_gs", c_int64), ("aux_gs", c_int64),
+                ("a_is_bf16", ctypes.c_int32), ("d_is_bf16", ctypes.c_int32), ("use_tc", ctypes.c_int32)]
+
+
 class EgrError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("egorear_b200 error %d: %s" % (code, msg))
@@ -36,6 +50,7 @@ SIGNATURES = {
     "egr_reproject_fisheye": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
     "egr_heatmap_head_1x1": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "egr_dense_stage": (c_int, [POINTER(DenseDesc), c_void_p]),
     "egr_mvfex_create": (c_int, [c_int, c_int, c_float, c_int, POINTER(c_void_p)]),
     "egr_mvfex_destroy": (c_int, [c_void_p]),
     "egr_mvfex_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),

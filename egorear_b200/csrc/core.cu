@@ -1,5 +1,6 @@
 // Error plumbing, device check and misc C-ABI entry points.
 #include "common.cuh"
+#include "gemm.cuh"
 #include <mutex>
 #include <vector>
 #include <map>
@@ -115,4 +116,25 @@ extern "C" int egr_profile_read(char* buf, int cap) {
     if ((int)out.size() >= cap) return egr::fail(EGR_ERR_INVALID, "profile_read: buffer too small (%d needed)", (int)out.size() + 1);
     memcpy(buf, out.c_str(), out.size() + 1);
     return EGR_OK;
+}
+
+extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
+    using namespace egr;
+    EGR_CHECK(c && c->A && c->W && c->D, EGR_ERR_INVALID, "dense_stage: null descriptor / operand");
+    if (int rc = require_device()) return rc;
+    GemmDesc d;
+    d.A = c->A; d.W = c->W; d.bias = c->bias; d.D = c->D; d.aux = c->aux;
+    d.M = c->M; d.N = c->N; d.K = c->K; d.lda = c->lda; d.ldd = c->ldd; d.amode = c->amode; d.epi = c->epi;
+    d.kblk = c->kblk; d.kblk_stride = c->kblk_stride;
+    d.Hin = c->Hin; d.Win = c->Win; d.Cin = c->Cin; d.Hout = c->Hout; d.Wout = c->Wout;
+    d.groups = c->groups > 0 ? c->groups : 1;
+    d.a_gs = c->a_gs; d.w_gs = c->w_gs; d.b_gs = c->b_gs; d.d_gs = c->d_gs; d.aux_gs = c->aux_gs;
+    EGR_CHECK(d.amode == A_PLAIN || d.amode == A_CONV3S2, EGR_ERR_INVALID, "dense_stage: amode %d", d.amode);
+    EGR_CHECK(d.epi >= EPI_NONE && d.epi <= EPI_RELU_ADDUP, EGR_ERR_INVALID, "dense_stage: epi %d", d.epi);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (c->use_tc) {
+        EGR_CHECK(c->a_is_bf16, EGR_ERR_INVALID, "dense_stage: the tcgen05 kernel takes bf16 A and W");
+        return gemm_tc(d, c->d_is_bf16, st);
+    }
+    return gemm_simt(d, c->a_is_bf16, c->d_is_bf16, st);
 }

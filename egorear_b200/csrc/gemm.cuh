@@ -51,6 +51,22 @@ int gemm_simt(const GemmDesc& d, int a_is_bf16, int d_is_bf16, cudaStream_t st);
 int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled; EGR_OK or error
 
+struct Up2Coef {
+    int i0, i1;
+    float l0, l1;
+};
+// nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True): src = dst * (in-1)/(out-1)
+__device__ __forceinline__ Up2Coef up2_coef(int dst, int in_size) {
+    const float scale = (float)(in_size - 1) / (float)(2 * in_size - 1);
+    const float s = scale * (float)dst;
+    Up2Coef c;
+    c.i0 = (int)s;
+    c.i1 = c.i0 + ((c.i0 < in_size - 1) ? 1 : 0);
+    c.l1 = s - (float)c.i0;
+    c.l0 = 1.f - c.l1;
+    return c;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 }  // namespace egr

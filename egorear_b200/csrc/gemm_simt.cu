@@ -6,22 +6,6 @@ namespace egr {
 
 constexpr int SBM = 128, SBN = 64, SBK = 16, STHREADS = 256;
 
-struct Up2Coef {
-    int i0, i1;
-    float l0, l1;
-};
-// nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True): src = dst * (in-1)/(out-1)
-__device__ __forceinline__ Up2Coef up2_coef(int dst, int in_size) {
-    const float scale = (float)(in_size - 1) / (float)(2 * in_size - 1);
-    const float s = scale * (float)dst;
-    Up2Coef c;
-    c.i0 = (int)s;
-    c.i1 = c.i0 + ((c.i0 < in_size - 1) ? 1 : 0);
-    c.l1 = s - (float)c.i0;
-    c.l0 = 1.f - c.l1;
-    return c;
-}
-
 template <typename T> __device__ __forceinline__ float4 ld4(const T* p);
 template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
 template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {

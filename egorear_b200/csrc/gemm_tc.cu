@@ -1,6 +1,547 @@
-// tcgen05 + TMA bf16 GEMM / implicit-GEMM conv (EGR_PREC_BF16 dense stage).  PLACEHOLDER: filled in next.
+// tcgen05 + TMA bf16 GEMM / implicit-GEMM conv: the EGR_PREC_BF16 dense stage (sm_100a only).
+//
+//   D[M,N] = epi(A[M,K] · W[N,K]^T + bias)      A, W bf16 (K contiguous), fp32 accumulate in TMEM
+//
+// One persistent CTA per SM walks a static tile list (n fastest, so the CTAs that share an A tile run together
+// and hit L2).  Roles (warp-specialised, mbarrier pipelines, no __syncthreads in the main loop):
+//   warp 0      TMA producer: A tile 128x64 and W tile BNx64 per k-block into a SWIZZLE_128B smem ring
+//   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block,
+//               tcgen05.commit releases the smem slot / publishes the accumulator
+//   warps 2-9   epilogue: tcgen05.ld the 128xBN fp32 accumulator (two TMEM buffers, so the epilogue of tile i
+//               overlaps the MMAs of tile i+1), bias + activation (+ fused bilinear-x2 residual), 16-byte stores
+// The 3x3 stride-2 pad-1 conv is an implicit GEMM: the NHWC input is described to TMA as a 5-D tensor
+// (2*Cin, W/2, 2, H/2, img) so that tap (ky,kx) of 128 consecutive output pixels is ONE box load whose
+// out-of-bounds part (the zero padding) is filled by the TMA unit.
 #include "gemm.cuh"
+#include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
+#include <mutex>
+
 namespace egr {
-int gemm_tc_init() { return fail(EGR_ERR_UNSUPPORTED, "tcgen05 GEMM not built yet; use egr_set_option(\"tc\", 0)"); }
-int gemm_tc(const GemmDesc&, int, cudaStream_t) { return fail(EGR_ERR_UNSUPPORTED, "tcgen05 GEMM not built yet"); }
+namespace {
+
+constexpr int BM = 128, BK = 64;                    // 64 bf16 = 128 B = one swizzle row
+constexpr int EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
+constexpr int SMEM_RING = 192 * 1024;
+
+template <int BN> struct TcCfg {
+    static constexpr int STAGE_A = BM * BK * 2;
+    static constexpr int STAGE_B = BN * BK * 2;
+    static constexpr int STAGE = STAGE_A + STAGE_B;
+    static constexpr int STAGES = SMEM_RING / STAGE;          // 256: 4, 128: 6, 64: 8
+    static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+    int M, N, K;
+    int m_tiles, n_tiles, groups, ksplit, kb_total, kb_per_split;
+    int amode;
+    int kblk;                 // A_PLAIN: elements per outer k block (== K when there is no K split of A)
+    int Cin, Wout, HWout;     // A_CONV3S2
+    int epi;
+    int partial;              // split-K: raw fp32 partial sums to D + ks * part_stride, no bias / activation
+    int64_t part_stride;
+    const float* bias;
+    int64_t b_gs;
+    void* D;
+    int64_t ldd, d_gs;
+    const void* aux;
+    int64_t aux_gs;
+    int Hout_e, Wout_e;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: a pipeline bug must surface as a launch error, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) {
+            printf("egorear_b200 gemm_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): rows of 128 B, 8-row atoms 1024 B apart.
+// bits [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 | [46,48) version = 1 |
+// [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32 (bit 4), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <typename TO> __device__ __forceinline__ void store8(TO* p, const float* v);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+template <typename TO> __device__ __forceinline__ void load8(const TO* p, float* v);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float* v) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+
+struct TileCoord { int g, mt, nt, ks; };
+__device__ __forceinline__ TileCoord decode_tile(int t, const TcParams& p) {
+    TileCoord c;
+    c.nt = t % p.n_tiles; t /= p.n_tiles;
+    c.ks = t % p.ksplit;  t /= p.ksplit;
+    c.mt = t % p.m_tiles;
+    c.g = t / p.m_tiles;
+    return c;
+}
+
+template <int BN, typename TO>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using C = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
+    const uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.groups * p.m_tiles * p.n_tiles * p.ksplit;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(t, p);
+                const int kb0 = tc.ks * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                // conv tile geometry (rows of all groups form one contiguous image list)
+                int img0 = 0, oy0 = 0;
+                if (p.amode == A_CONV3S2) {
+                    const long long gm0 = (long long)tc.g * p.M + (long long)tc.mt * BM;
+                    img0 = (int)(gm0 / p.HWout);
+                    oy0 = (int)(gm0 % p.HWout) / p.Wout;
+                }
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    const uint32_t full = full0 + 8 * stage;
+                    mbar_expect_tx(full, C::STAGE);
+                    const uint32_t sa = smem_base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                    const int k = kb * BK;
+                    if (p.amode == A_PLAIN) {
+                        tma_load_4d(sa, &tmA, full, k % p.kblk, tc.mt * BM, k / p.kblk, tc.g);
+                    } else {
+                        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        // input pixel (2*oy + ky - 1, 2*ox + kx - 1) = pair index (oy + dy, ox + dx), parity (hp, wp)
+                        const int wp = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
+                        const int hp = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
+                        tma_load_5d(sa, &tmA, full, ci + wp * p.Cin, dx, hp, oy0 + dy, img0);
+                    }
+                    tma_load_3d(sb, &tmB, full, k, tc.nt * BN, tc.g);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            int stage = 0, phase = 0, it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const TileCoord tc = decode_tile(t, p);
+                const int kb0 = tc.ks * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(full0 + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+#pragma unroll
+                    for (int kk = 0; kk < BK / 16; ++kk) {
+                        // +32 B per K=16 step inside the 128 B swizzle row (encoded >> 4)
+                        tc_mma(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty0 + 8 * stage);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull0 + 8 * acc);
+            }
+        }
+    } else {
+        // ================= epilogue =================
+        const int e = warp - 2;
+        const int q = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = e >> 2;           // column half
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const TileCoord tc = decode_tile(t, p);
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int m = tc.mt * BM + row;
+            const bool row_ok = m < p.M;
+            const int n_base = tc.nt * BN + half * (BN / 2);
+            const float* bias = p.bias ? p.bias + (int64_t)tc.g * p.b_gs : nullptr;
+            // ADDUP geometry of this row
+            int src00 = 0, src01 = 0, src10 = 0, src11 = 0;
+            float wy0 = 0.f, wy1 = 0.f, wx0 = 0.f, wx1 = 0.f;
+            const TO* aux = nullptr;
+            if (p.epi == EPI_RELU_ADDUP && row_ok) {
+                const int hw = p.Hout_e * p.Wout_e;
+                const int im = m / hw, r = m - im * hw;
+                const int y = r / p.Wout_e, x = r - y * p.Wout_e;
+                const int hs = p.Hout_e >> 1, ws = p.Wout_e >> 1;
+                const Up2Coef cy = up2_coef(y, hs), cx = up2_coef(x, ws);
+                wy0 = cy.l0; wy1 = cy.l1; wx0 = cx.l0; wx1 = cx.l1;
+                src00 = cy.i0 * ws + cx.i0; src01 = cy.i0 * ws + cx.i1;
+                src10 = cy.i1 * ws + cx.i0; src11 = cy.i1 * ws + cx.i1;
+                aux = reinterpret_cast<const TO*>(p.aux) + (int64_t)tc.g * p.aux_gs + (int64_t)im * hs * ws * p.N;
+            }
+            mbar_wait(tfull0 + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                uint32_t v[32];
+                __syncwarp();
+                tc_ld32(taddr + c0, v);
+                if (!row_ok) continue;
+                const int n0 = n_base + c0;
+                if (p.partial) {
+                    float* dst = reinterpret_cast<float*>(p.D) + (int64_t)tc.ks * p.part_stride + (int64_t)tc.g * p.d_gs +
+                                 (int64_t)m * p.ldd + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    continue;
+                }
+                TO* dst = reinterpret_cast<TO*>(p.D) + (int64_t)tc.g * p.d_gs + (int64_t)m * p.ldd + n0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float x[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j + i]);
+                    if (bias) {
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j + 4));
+                        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                    }
+                    if (p.epi == EPI_RELU || p.epi == EPI_RELU_ADDUP) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+                    } else if (p.epi == EPI_GELU) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+                    }
+                    if (p.epi == EPI_RELU_ADDUP) {
+                        float a00[8], a01[8], a10[8], a11[8];
+                        load8<TO>(aux + (int64_t)src00 * p.N + n0 + j, a00);
+                        load8<TO>(aux + (int64_t)src01 * p.N + n0 + j, a01);
+                        load8<TO>(aux + (int64_t)src10 * p.N + n0 + j, a10);
+                        load8<TO>(aux + (int64_t)src11 * p.N + n0 + j, a11);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
+                            x[i] += fmaxf(u, 0.f);
+                        }
+                    }
+                    store8<TO>(dst + j, x);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// split-K finalize: out = epi(sum_s part[s] + bias)
+template <typename TO>
+__global__ void splitk_finalize_kernel(const float* part, int64_t part_stride, int ksplit, const float* bias, TO* out,
+                                       int64_t total, int N, int epi) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    float s = 0.f;
+    for (int k = 0; k < ksplit; ++k) s += part[(int64_t)k * part_stride + i];
+    if (bias) s += bias[i % N];
+    if (epi == EPI_RELU) s = fmaxf(s, 0.f);
+    else if (epi == EPI_GELU) s = gelu_erf(s);
+    ActT<TO>::st(out + i, s);
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::mutex g_tc_mu;
+bool g_tc_ready = false;
+float* g_splitk_scratch = nullptr;
+constexpr int64_t SPLITK_SCRATCH_FLOATS = 8ll << 20;   // 32 MB
+
+int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, const char* what) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(EGR_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
+                    what, (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                    (unsigned long long)(rank > 2 ? dims[2] : 0), box[0], box[1], rank > 2 ? box[2] : 0);
+    return EGR_OK;
+}
+
+template <int BN, typename TO>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
+    gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+template <int BN, typename TO>
+int set_smem_attr() {
+    EGR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    return EGR_OK;
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+    std::lock_guard<std::mutex> lk(g_tc_mu);
+    if (g_tc_ready) return EGR_OK;
+    if (int rc = require_device()) return rc;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    EGR_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    EGR_CHECK(fn && qres == cudaDriverEntryPointSuccess, EGR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    int rc;
+    if ((rc = set_smem_attr<64, float>()) || (rc = set_smem_attr<64, __nv_bfloat16>()) ||
+        (rc = set_smem_attr<128, float>()) || (rc = set_smem_attr<128, __nv_bfloat16>()) ||
+        (rc = set_smem_attr<256, float>()) || (rc = set_smem_attr<256, __nv_bfloat16>()))
+        return rc;
+    EGR_CUDA_OK(cudaMalloc(&g_splitk_scratch, SPLITK_SCRATCH_FLOATS * sizeof(float)));
+    g_tc_ready = true;
+    return EGR_OK;
+}
+
+int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st) {
+    if (!g_tc_ready) {
+        if (int rc = gemm_tc_init()) return rc;
+    }
+    EGR_CHECK(d.M > 0 && d.N > 0 && d.K > 0 && d.groups > 0, EGR_ERR_INVALID, "gemm_tc: empty problem %d %d %d", d.M, d.N, d.K);
+    EGR_CHECK(d.K % BK == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d", d.K, BK);
+    EGR_CHECK(d.N % 64 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: N=%d must be a multiple of 64", d.N);
+    EGR_CHECK((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0 &&
+              (reinterpret_cast<uintptr_t>(d.D) & 15) == 0, EGR_ERR_INVALID, "gemm_tc: operands must be 16-byte aligned");
+    EGR_CHECK(d.ldd % 8 == 0 && d.d_gs % 8 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: ldd / d_gs must be multiples of 8 elements");
+    if (d.epi == EPI_RELU_ADDUP) EGR_CHECK(d.aux && d.Hout > 0 && d.Wout > 0, EGR_ERR_INVALID, "gemm_tc: ADDUP needs aux + geometry");
+
+    const int nsm = sm_count();
+    const int m_tiles = ceil_div(d.M, BM);
+    int bn = 64;
+    const int cands[3] = {256, 128, 64};
+    for (int c : cands) {
+        if (d.N % c) continue;
+        const int64_t tiles = (int64_t)d.groups * m_tiles * (d.N / c);
+        if (tiles >= nsm || c == 64) { bn = c; break; }
+    }
+    TcParams p{};
+    p.M = d.M; p.N = d.N; p.K = d.K;
+    p.m_tiles = m_tiles; p.n_tiles = d.N / bn; p.groups = d.groups;
+    p.kb_total = d.K / BK;
+    p.ksplit = 1; p.kb_per_split = p.kb_total;
+    p.amode = d.amode; p.epi = d.epi;
+    p.bias = d.bias; p.b_gs = d.b_gs;
+    p.D = d.D; p.ldd = d.ldd; p.d_gs = d.d_gs;
+    p.aux = d.aux; p.aux_gs = d.aux_gs; p.Hout_e = d.Hout; p.Wout_e = d.Wout;
+
+    // deterministic split-K for skinny problems (pose3d Linear(32768 -> 2048) at small batch): partial sums go to a
+    // library-owned scratch [ks][M][N], a finalize kernel adds them in a fixed order and applies bias + activation
+    const int64_t base_tiles = (int64_t)d.groups * m_tiles * p.n_tiles;
+    if (d.epi != EPI_RELU_ADDUP && d.groups == 1 && d.ldd == d.N && base_tiles * 4 <= nsm && p.kb_total >= 32) {
+        const int64_t span = (int64_t)d.M * d.N;
+        int ks = (int)(nsm / base_tiles);
+        if (ks > p.kb_total / 8) ks = p.kb_total / 8;
+        while (ks > 1 && span * ks > SPLITK_SCRATCH_FLOATS) --ks;
+        if (ks > 1) {
+            p.kb_per_split = ceil_div(p.kb_total, ks);
+            p.ksplit = ceil_div(p.kb_total, p.kb_per_split);
+            p.partial = 1;
+            p.part_stride = span;
+            p.D = g_splitk_scratch;
+        }
+    }
+
+    // ---- tensor maps ----
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (d.amode == A_PLAIN) {
+        const int kblk = d.kblk > 0 ? d.kblk : d.K;
+        EGR_CHECK(kblk % BK == 0 && d.K % kblk == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: kblk=%d", kblk);
+        EGR_CHECK(d.lda % 8 == 0 && d.a_gs % 8 == 0 && d.kblk_stride % 8 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: A strides must be multiples of 8 elements");
+        p.kblk = kblk;
+        const cuuint64_t dims[4] = {(cuuint64_t)kblk, (cuuint64_t)d.M, (cuuint64_t)(d.K / kblk), (cuuint64_t)d.groups};
+        // strides of size-1 dims are irrelevant but must be valid (multiple of 16 B)
+        const cuuint64_t str[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)(d.K / kblk > 1 ? d.kblk_stride : d.lda) * 2,
+                                   (cuuint64_t)(d.groups > 1 ? d.a_gs : d.lda) * 2};
+        const cuuint32_t box[4] = {BK, BM, 1, 1};
+        if ((rc = encode(&tmA, d.A, 4, dims, str, box, "A"))) return rc;
+    } else {
+        const int Hout = d.Hin / 2, Wout = d.Win / 2, HW = Hout * Wout;
+        EGR_CHECK(d.Cin % BK == 0 && d.K == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
+                  "gemm_tc: conv geometry Cin=%d K=%d", d.Cin, d.K);
+        EGR_CHECK(BM % Wout == 0 && (HW % BM == 0 || BM % HW == 0), EGR_ERR_UNSUPPORTED, "gemm_tc: conv output %dx%d does not tile by %d rows", Hout, Wout, BM);
+        EGR_CHECK(d.M % HW == 0, EGR_ERR_INVALID, "gemm_tc: conv M=%d is not a whole number of %dx%d images", d.M, Hout, Wout);
+        EGR_CHECK(d.groups == 1 || (d.a_gs == (int64_t)(d.M / HW) * d.Hin * d.Win * d.Cin && d.M % BM == 0), EGR_ERR_UNSUPPORTED,
+                  "gemm_tc: conv groups must be contiguous image blocks");
+        const int bh = (HW >= BM) ? BM / Wout : Hout;
+        const int bimg = (HW >= BM) ? 1 : BM / HW;
+        p.Cin = d.Cin; p.Wout = Wout; p.HWout = HW;
+        const int64_t n_img = (int64_t)d.groups * (d.M / HW);
+        const cuuint64_t dims[5] = {(cuuint64_t)2 * d.Cin, (cuuint64_t)Wout, 2, (cuuint64_t)Hout, (cuuint64_t)n_img};
+        const cuuint64_t str[4] = {(cuuint64_t)2 * d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)2 * d.Win * d.Cin * 2,
+                                   (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
+        const cuuint32_t box[5] = {BK, (cuuint32_t)Wout, 1, (cuuint32_t)bh, (cuuint32_t)bimg};
+        if ((rc = encode(&tmA, d.A, 5, dims, str, box, "A(conv3s2)"))) return rc;
+    }
+    {
+        const cuuint64_t dims[3] = {(cuuint64_t)d.K, (cuuint64_t)d.N, (cuuint64_t)d.groups};
+        const cuuint64_t str[2] = {(cuuint64_t)d.K * 2, (cuuint64_t)(d.groups > 1 ? d.w_gs : (int64_t)d.N * d.K) * 2};
+        const cuuint32_t box[3] = {BK, (cuuint32_t)bn, 1};
+        if ((rc = encode(&tmB, d.W, 3, dims, str, box, "W"))) return rc;
+    }
+
+    const int64_t total = (int64_t)d.groups * m_tiles * p.n_tiles * p.ksplit;
+    const int grid = (int)(total < nsm ? total : nsm);
+    const bool out_bf16 = d_is_bf16 && !p.partial;
+    if (bn == 256) rc = out_bf16 ? launch_tc<256, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<256, float>(tmA, tmB, p, grid, st);
+    else if (bn == 128) rc = out_bf16 ? launch_tc<128, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<128, float>(tmA, tmB, p, grid, st);
+    else rc = out_bf16 ? launch_tc<64, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<64, float>(tmA, tmB, p, grid, st);
+    if (rc) return rc;
+    if (p.partial) {
+        const int64_t tot = (int64_t)d.M * d.N;
+        const int blocks = (int)ceil_div64(tot, 256);
+        if (d_is_bf16)
+            splitk_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
+                                                                         reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi);
+        else
+            splitk_finalize_kernel<float><<<blocks, 256, 0, st>>>(g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
+                                                                  reinterpret_cast<float*>(d.D), tot, d.N, d.epi);
+        EGR_LAUNCHED();
+    }
+    return EGR_OK;
+}
+
 }  // namespace egr

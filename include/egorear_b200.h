@@ -111,6 +111,32 @@ int egr_heatmap_head_1x1(const float* feat, const float* weight, const float* bi
                          int J, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Dense stage (building block of both engines, exported for parity tests and for callers that want a
+ * single fused conv/Linear):  D[M,N] = epi(A[M,K] * W[N,K]^T + bias)   replaces one nn.Conv2d(1x1 | 3x3 s2 p1)
+ * / nn.Linear + activation of the reference stacks (e.g. estimator/egoposeformer_heatmap_mvf_ex.py:525-532).
+ *   activations are channels-last: A row m = pixel (img, y, x), K = channels; W is [N][K] (3x3: [N][ky][kx][Cin]).
+ *   amode 0: plain rows (lda); with kblk > 0 the K axis is split in blocks of kblk elements kblk_stride apart.
+ *   amode 1: implicit 3x3 stride-2 pad-1 conv over [img][Hin][Win][Cin]; M = n_img*(Hin/2)*(Win/2), K = 9*Cin.
+ *   epi 0 none, 1 ReLU, 2 exact-erf GELU, 3 ReLU then + relu(bilinear_x2_align_corners(aux)) with
+ *       aux [img][(Hout/2)*(Wout/2)][N] in D's dtype (the "offset_pred + frame_feat" of :715).
+ *   groups independent problems at element strides a_gs / w_gs / b_gs / d_gs / aux_gs.
+ *   use_tc 1: tcgen05 + TMA kernel, A and W bf16, fp32 accumulate in TMEM (a_is_bf16 must be 1, W bf16);
+ *   use_tc 0: fp32 SIMT kernel, W fp32, A fp32 or bf16.   d_is_bf16 selects the output dtype.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct egr_dense_desc {
+    const void* A; const void* W; const float* bias; void* D; const void* aux;
+    int32_t M, N, K;
+    int64_t lda, ldd;
+    int32_t amode, epi;
+    int32_t kblk; int64_t kblk_stride;
+    int32_t Hin, Win, Cin, Hout, Wout;
+    int32_t groups;
+    int64_t a_gs, w_gs, b_gs, d_gs, aux_gs;
+    int32_t a_is_bf16, d_is_bf16, use_tc;
+} egr_dense_desc;
+int egr_dense_stage(const egr_dense_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * mvfex engine: everything EgoPoseFormerHeatmapMVFEX.forward does after the backbones
  *   (estimator/egoposeformer_heatmap_mvf_ex.py:262-437, use_1by1_conv=False / jqa configs):
  *   H1 init heads, D1 anchors, and per view HeatmapMVF.forward (:652-731) = Q1 M1 F1 A1 A2 A3 T1 R1 H2.

@@ -1,0 +1,160 @@
+"""GPU: one dense stage (egr_dense_stage) — the tcgen05 + TMA bf16 kernel and the fp32 SIMT kernel vs plain torch fp32
+on the same bf16-rounded operands.
+
+The tensor-core kernel accumulates bf16 x bf16 products in fp32 (TMEM); on operands that are already bf16 values the only
+difference from the fp32 torch reference is summation order, so the bound is tight (2e-3 relative to the output range for
+bf16 outputs = one bf16 ulp, 1e-4 for fp32 outputs).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def dense(A, W, bias, D, M, N, K, lda, ldd, amode=0, epi=0, aux=None, kblk=0, kblk_stride=0, Hin=0, Win=0, Cin=0, Hout=0,
+          Wout=0, groups=1, a_gs=0, w_gs=0, b_gs=0, d_gs=0, aux_gs=0, use_tc=1):
+    from egorear_b200 import _lib
+    lib = _lib.load()
+    d = _lib.DenseDesc()
+    d.A, d.W, d.bias, d.D, d.aux = _ptr(A), _ptr(W), _ptr(bias), _ptr(D), _ptr(aux)
+    d.M, d.N, d.K, d.lda, d.ldd, d.amode, d.epi = M, N, K, lda, ldd, amode, epi
+    d.kblk, d.kblk_stride = kblk, kblk_stride
+    d.Hin, d.Win, d.Cin, d.Hout, d.Wout = Hin, Win, Cin, Hout, Wout
+    d.groups, d.a_gs, d.w_gs, d.b_gs, d.d_gs, d.aux_gs = groups, a_gs, w_gs, b_gs, d_gs, aux_gs
+    d.a_is_bf16 = int(A.dtype == torch.bfloat16)
+    d.d_is_bf16 = int(D.dtype == torch.bfloat16)
+    d.use_tc = use_tc
+    _lib.check(lib.egr_dense_stage(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+
+
+def act(x, epi):
+    if epi in (1, 3):
+        return torch.relu(x)
+    if epi == 2:
+        return F.gelu(x)
+    return x
+
+
+def check(got, want, out_dtype):
+    tol = 6e-3 if out_dtype == torch.bfloat16 else 2e-4
+    err = float((got.float() - want).abs().max() / want.abs().max().clamp_min(1e-20))
+    assert err < tol, "rel err %.3e" % err
+    return err
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K,groups,epi,out_dtype", [
+    (128, 64, 64, 1, 0, torch.float32),          # one tile, one k-block
+    (256, 128, 128, 1, 1, torch.bfloat16),
+    (960, 256, 4096, 4, 1, torch.float32),       # Q1a: ragged M (960 = 7.5 tiles), long K, 4 weight sets
+    (4096, 256, 128, 2, 1, torch.bfloat16),      # F1a-like
+    (2048, 512, 256, 1, 2, torch.bfloat16),      # BN=256 path when tiles are plentiful / GELU
+    (148 * 128 * 2, 256, 192, 1, 1, torch.bfloat16),   # >= 148 tiles at BN=256, 3 k-blocks, several tiles per CTA
+    (37 * 128 + 5, 128, 576, 3, 0, torch.float32),
+])
+def test_tc_plain(M, N, K, groups, epi, out_dtype):
+    A = rnd((groups, M, K), 1)
+    W = rnd((groups, N, K), 2, K ** -0.5)
+    bias = torch.randn((groups, N), device="cuda")
+    D = torch.full((groups, M, N), float("nan"), device="cuda", dtype=out_dtype)
+    dense(A, W, bias, D, M, N, K, K, N, epi=epi, groups=groups, a_gs=M * K, w_gs=N * K, b_gs=N, d_gs=M * N)
+    want = act(torch.einsum("gmk,gnk->gmn", A.float(), W.float()) + bias[:, None, :], epi)
+    check(D, want, out_dtype)
+
+
+def test_tc_strided_rows_and_output():
+    """lda > K and ldd > N (a stage writing into a wider buffer)"""
+    M, N, K = 512, 64, 128
+    Abuf = rnd((M, 256), 3)
+    W = rnd((N, K), 4, K ** -0.5)
+    Dbuf = torch.zeros((M, 192), device="cuda", dtype=torch.bfloat16)
+    dense(Abuf[:, 64:], W, None, Dbuf[:, 128:], M, N, K, 256, 192)
+    want = Abuf[:, 64:64 + K].float() @ W.float().t()
+    check(Dbuf[:, 128:], want, torch.bfloat16)
+    assert float(Dbuf[:, :128].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B", [2, 64])
+def test_tc_ksplit_blocks_and_splitk(B):
+    """pose3d Linear(32768 -> 2048): A is [V][B][8192] (k blocks of 8192 one view apart); small M triggers split-K"""
+    V, KB, N = 4, 8192, 2048
+    A = rnd((V, B, KB), 5)
+    W = rnd((N, V * KB), 6, (V * KB) ** -0.5)
+    bias = torch.randn((N,), device="cuda")
+    D = torch.full((B, N), float("nan"), device="cuda")
+    dense(A, W, bias, D, B, N, V * KB, KB, N, epi=2, kblk=KB, kblk_stride=B * KB)
+    want = F.gelu(A.float().permute(1, 0, 2).reshape(B, V * KB) @ W.float().t() + bias)
+    check(D, want, torch.float32)
+
+
+@pytest.mark.parametrize("Hin,Cin,N,n_img,groups,out_dtype", [
+    (64, 128, 256, 2, 1, torch.bfloat16),       # H1b / H2a geometry
+    (64, 256, 512, 1, 2, torch.bfloat16),       # F1b geometry, two weight sets
+    (64, 64, 128, 3, 1, torch.float32),         # P2b
+    (16, 64, 128, 4, 1, torch.bfloat16),        # P2d: 8x8 outputs, two images per tile
+])
+def test_tc_conv3s2(Hin, Cin, N, n_img, groups, out_dtype):
+    x = rnd((groups, n_img, Hin, Hin, Cin), 7)                       # NHWC
+    w = rnd((groups, N, Cin, 3, 3), 8, (9 * Cin) ** -0.5)            # torch conv layout
+    bias = torch.randn((groups, N), device="cuda")
+    Wp = w.permute(0, 1, 3, 4, 2).contiguous().reshape(groups, N, 9 * Cin)   # [N][ky][kx][Cin]
+    Ho = Hin // 2
+    M = n_img * Ho * Ho
+    D = torch.full((groups, M, N), float("nan"), device="cuda", dtype=out_dtype)
+    dense(x, Wp, bias, D, M, N, 9 * Cin, 0, N, amode=1, epi=1, Hin=Hin, Win=Hin, Cin=Cin, groups=groups,
+          a_gs=n_img * Hin * Hin * Cin, w_gs=N * 9 * Cin, b_gs=N, d_gs=M * N)
+    for g in range(groups):
+        ref = F.conv2d(x[g].float().permute(0, 3, 1, 2), w[g].float(), bias[g], stride=2, padding=1)
+        want = torch.relu(ref).permute(0, 2, 3, 1).reshape(M, N)
+        check(D[g], want, out_dtype)
+
+
+def test_tc_relu_addup():
+    """F1c epilogue: relu(acc + bias) + relu(bilinear_x2_align_corners(aux))"""
+    n_img, Ho, N, K = 3, 32, 128, 512
+    M = n_img * Ho * Ho
+    A = rnd((M, K), 9)
+    W = rnd((N, K), 10, K ** -0.5)
+    bias = torch.randn((N,), device="cuda")
+    aux = rnd((n_img, 16 * 16, N), 11)
+    D = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    dense(A, W, bias, D, M, N, K, K, N, epi=3, aux=aux, Hout=Ho, Wout=Ho)
+    up = F.interpolate(aux.float().reshape(n_img, 16, 16, N).permute(0, 3, 1, 2), scale_factor=2, mode="bilinear",
+                       align_corners=True)
+    want = torch.relu(A.float() @ W.float().t() + bias) + torch.relu(up).permute(0, 2, 3, 1).reshape(M, N)
+    check(D, want, torch.bfloat16)
+
+
+def test_tc_matches_simt_kernel():
+    """the two dense kernels agree on the same operands (fp32 SIMT on bf16-valued inputs)"""
+    M, N, K = 1000, 128, 256
+    A = rnd((M, K), 12)
+    W = rnd((N, K), 13, K ** -0.5)
+    bias = torch.randn((N,), device="cuda")
+    D1 = torch.empty((M, N), device="cuda")
+    D2 = torch.empty((M, N), device="cuda")
+    dense(A, W, bias, D1, M, N, K, K, N, epi=1, use_tc=1)
+    dense(A, W.float().contiguous(), bias, D2, M, N, K, K, N, epi=1, use_tc=0)
+    check(D1, D2, torch.float32)
+
+
+def test_tc_rejects_bad_shapes():
+    from egorear_b200 import _lib
+    A = rnd((128, 96), 1)
+    W = rnd((64, 96), 2)
+    D = torch.empty((128, 64), device="cuda")
+    with pytest.raises(_lib.EgrError):
+        dense(A, W, None, D, 128, 64, 96, 96, 64)        # K not a multiple of 64
