@@ -133,8 +133,7 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
     EGR_CHECK(d.epi >= EPI_NONE && d.epi <= EPI_RELU_ADDUP, EGR_ERR_INVALID, "dense_stage: epi %d", d.epi);
     cudaStream_t st = (cudaStream_t)stream;
     if (c->use_tc) {
-        EGR_CHECK(c->a_is_bf16, EGR_ERR_INVALID, "dense_stage: the tcgen05 kernel takes bf16 A and W");
-        return gemm_tc(d, c->d_is_bf16, st);
+        return gemm_tc(d, c->a_is_bf16 ? 0 : 1, c->d_is_bf16, st);
     }
     return gemm_simt(d, c->a_is_bf16, c->d_is_bf16, st);
 }

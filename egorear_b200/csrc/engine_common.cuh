@@ -84,19 +84,30 @@ struct WMat {
 
 extern int g_opt_tc;   // 1: bf16 precision uses the tcgen05 kernel; 0: bf16 activations through the SIMT kernel (debug)
 
+// internal stage precision on top of the public EGR_PREC_*: fp32 activations and weights through the tensor cores as
+// TF32 (10-bit mantissa, fp32 accumulate) — used where bf16 operands would eat the 0.1 mm MPJPE budget (pose3d P2)
+constexpr int PREC_TF32 = 2;
+
 // run one dense stage in the handle's precision.  `out_f32`: the output stays fp32 even in bf16 mode.
 inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out_f32, cudaStream_t st) {
     const bool bf = (prec == EGR_PREC_BF16);
     const bool tc = bf && g_opt_tc;
     d.N = w.N;
     d.K = w.K;
+    if (prec == PREC_TF32 && g_opt_tc) {
+        d.W = w.f32 + (int64_t)set_begin * w.stride();
+        d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
+        d.w_gs = w.stride();
+        d.b_gs = w.N;
+        return gemm_tc(d, /*in_is_f32=*/1, /*d_is_bf16=*/0, st);
+    }
     d.W = tc ? (const void*)(w.bf16 + (int64_t)set_begin * w.stride())
              : (const void*)(w.f32 + (int64_t)set_begin * w.stride());
     d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
     d.w_gs = w.stride();
     d.b_gs = w.N;
     const int d_bf16 = (bf && !out_f32) ? 1 : 0;
-    if (tc) return gemm_tc(d, d_bf16, st);
+    if (tc) return gemm_tc(d, 0, d_bf16, st);
     return gemm_simt(d, bf ? 1 : 0, d_bf16, st);
 }
 

@@ -10,7 +10,8 @@
 namespace egr {
 CamCalib make_calib(int cam_id, const float* calib_host);
 // P2 (conv_frame_feat + mlp_pred) feeds the 3D proposal directly: bf16 operands cost ~0.1 mm MPJPE on their own
-// (measured), which is the whole parity budget, so by default the branch stays fp32 even in EGR_PREC_BF16.
+// (measured), which is the whole parity budget, so in EGR_PREC_BF16 the branch keeps fp32 activations and weights and
+// multiplies them as TF32 on the tensor cores (PREC_TF32); option "pose_p2_bf16" forces bf16 operands instead.
 int g_opt_pose_p2_bf16 = 0;
 }
 using namespace egr;
@@ -32,10 +33,14 @@ struct egr_pose3d {
 
 namespace {
 
-inline int p2_prec(const egr_pose3d* h) { return (h->prec == EGR_PREC_BF16 && g_opt_pose_p2_bf16) ? EGR_PREC_BF16 : EGR_PREC_FP32; }
+inline int p2_prec(const egr_pose3d* h) {
+    if (h->prec != EGR_PREC_BF16) return EGR_PREC_FP32;
+    if (g_opt_pose_p2_bf16) return EGR_PREC_BF16;
+    return g_opt_tc ? PREC_TF32 : EGR_PREC_FP32;
+}
 
 int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3 2 mlp-permute*/, const std::string& key,
-                cudaStream_t st) {
+                cudaStream_t st, bool tf32_operand = true) {
     m.N = N; m.K = K; m.sets = 1;
     int rc = EGR_OK;
     if ((rc = h->pool.alloc(&m.f32, (int64_t)N * K))) return rc;
@@ -51,6 +56,8 @@ int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3
     if (p2_prec(h) == EGR_PREC_BF16) {
         if ((rc = h->pool.alloc(&m.bf16, (int64_t)N * K))) return rc;
         if ((rc = cast_bf16(m.f32, m.bf16, (int64_t)N * K, st))) return rc;
+    } else if (p2_prec(h) == PREC_TF32 && tf32_operand) {
+        if ((rc = round_tf32_inplace(m.f32, (int64_t)N * K, st))) return rc;
     }
     return EGR_OK;
 }
@@ -185,7 +192,7 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
     h->pool.release();
     h->packed = false;
     int rc;
-    if (p2_prec(h) == EGR_PREC_BF16 && g_opt_tc) {
+    if (p2_prec(h) != EGR_PREC_FP32 && g_opt_tc) {
         if ((rc = gemm_tc_init())) return rc;
     }
     if ((rc = p_make_wmat(h, h->c0, 64, 128, 0, "conv_frame_feat.0", st))) return rc;
@@ -194,8 +201,8 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
     if ((rc = p_make_wmat(h, h->c7, 128, 9 * 64, 1, "conv_frame_feat.7", st))) return rc;
     const int K0 = h->V * PC * 64;
     if ((rc = p_make_wmat(h, h->m0, K0 / 16, K0, 2, "mlp_pred.0.0", st))) return rc;
-    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st))) return rc;
-    if ((rc = p_make_wmat(h, h->m2, 3 * h->J, K0 / 256, 0, "mlp_pred.2", st))) return rc;
+    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st, false))) return rc;
+    if ((rc = p_make_wmat(h, h->m2, 3 * h->J, K0 / 256, 0, "mlp_pred.2", st, false))) return rc;
     PoseTokenW tw{};
     if ((rc = p_make_T(h, "query_gen_mlp.0", PE, 4, &tw.g0_T, st))) return rc;
     if ((rc = p_vec(h, "query_gen_mlp.0.bias", PE, &tw.g0_b))) return rc;
@@ -247,30 +254,31 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     EGR_MARK("P_stage_nhwc", st);
     // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
     const float* sampled = h->use_init ? feats_init : feats_final;
-    if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, bf, st))) return rc;
+    const int rnd = (prec == PREC_TF32);      // every operand of a tf32 stage is pre-rounded to the nearest TF32 value
+    if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
     const void* Xs = w.Xf;
-    if (sampled != feats_final || bfs != bf) {
+    if (sampled != feats_final || bfs != bf || rnd) {
         if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
         Xs = w.Xi;
     }
     EGR_MARK("P2a", st);
     // P2 conv_frame_feat
     GemmDesc d;
-    d.A = w.Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU;
+    d.A = w.Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
     EGR_MARK("P2b", st);
     d = GemmDesc();
-    d.A = w.p0; d.amode = A_CONV3S2; d.Hin = 64; d.Win = 64; d.Cin = 64; d.M = VB * 1024; d.D = w.p2; d.ldd = 128; d.epi = EPI_RELU;
+    d.A = w.p0; d.amode = A_CONV3S2; d.Hin = 64; d.Win = 64; d.Cin = 64; d.M = VB * 1024; d.D = w.p2; d.ldd = 128; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->c2, 0, prec, false, st))) return rc;
     EGR_MARK("P2pool", st);
     if ((rc = maxpool2_nhwc(w.p2, w.p3, bf, VB, 32, 32, 128, st))) return rc;
     EGR_MARK("P2c", st);
     d = GemmDesc();
-    d.A = w.p3; d.lda = 128; d.M = VB * 256; d.D = w.p5; d.ldd = 64; d.epi = EPI_RELU;
+    d.A = w.p3; d.lda = 128; d.M = VB * 256; d.D = w.p5; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->c5, 0, prec, false, st))) return rc;
     EGR_MARK("P2d", st);
     d = GemmDesc();
-    d.A = w.p5; d.amode = A_CONV3S2; d.Hin = 16; d.Win = 16; d.Cin = 64; d.M = VB * 64; d.D = w.p7; d.ldd = 128; d.epi = EPI_RELU;
+    d.A = w.p5; d.amode = A_CONV3S2; d.Hin = 16; d.Win = 16; d.Cin = 64; d.M = VB * 64; d.D = w.p7; d.ldd = 128; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->c7, 0, prec, false, st))) return rc;
     EGR_MARK("P2mlp0", st);
     // mlp_pred: K-split over the V view blocks of p7 ([V][B][64*128])

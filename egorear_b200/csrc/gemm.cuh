@@ -32,6 +32,7 @@ struct GemmDesc {
     int M = 0, N = 0, K = 0;
     int64_t lda = 0, ldd = 0;
     int amode = A_PLAIN, epi = EPI_NONE;
+    int round_tf32 = 0;           // tcgen05 path, fp32 output: round to the nearest TF32 value (operand of the next tf32 stage)
     // A_PLAIN K-split (pose3d flatten "(v c h w)"): k-blocks of kblk elements live kblk_stride apart
     int kblk = 0;
     int64_t kblk_stride = 0;
@@ -47,8 +48,8 @@ struct GemmDesc {
 // fp32 SIMT path (reference-grade parity).  TA/TO in {float, bf16}: 0 = float, 1 = bf16.
 int gemm_simt(const GemmDesc& d, int a_is_bf16, int d_is_bf16, cudaStream_t st);
 
-// tcgen05 + TMA bf16 path.  A, W bf16; D bf16 or fp32.
-int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st);
+// tcgen05 + TMA path.  A, W both bf16 (kind::f16) or both fp32 read as TF32 (kind::tf32, in_is_f32); D bf16 or fp32.
+int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled; EGR_OK or error
 
 struct Up2Coef {

@@ -1,6 +1,7 @@
-// tcgen05 + TMA bf16 GEMM / implicit-GEMM conv: the EGR_PREC_BF16 dense stage (sm_100a only).
+// tcgen05 + TMA GEMM / implicit-GEMM conv: the EGR_PREC_BF16 dense stage (sm_100a only).
 //
-//   D[M,N] = epi(A[M,K] · W[N,K]^T + bias)      A, W bf16 (K contiguous), fp32 accumulate in TMEM
+//   D[M,N] = epi(A[M,K] · W[N,K]^T + bias)      A, W bf16 (kind::f16) or fp32 read as TF32 (kind::tf32),
+//                                               K contiguous, fp32 accumulate in TMEM
 //
 // One persistent CTA per SM walks a static tile list (n fastest, so the CTAs that share an A tile run together
 // and hit L2).  Roles (warp-specialised, mbarrier pipelines, no __syncthreads in the main loop):
@@ -19,14 +20,15 @@
 namespace egr {
 namespace {
 
-constexpr int BM = 128, BK = 64;                    // 64 bf16 = 128 B = one swizzle row
+constexpr int BM = 128;
+constexpr int ROW_BYTES = 128;                       // one SWIZZLE_128B row = one k-block: 64 bf16 or 32 fp32
 constexpr int EPI_WARPS = 8;
 constexpr int TC_THREADS = 64 + EPI_WARPS * 32;
 constexpr int SMEM_RING = 192 * 1024;
 
 template <int BN> struct TcCfg {
-    static constexpr int STAGE_A = BM * BK * 2;
-    static constexpr int STAGE_B = BN * BK * 2;
+    static constexpr int STAGE_A = BM * ROW_BYTES;
+    static constexpr int STAGE_B = BN * ROW_BYTES;
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int STAGES = SMEM_RING / STAGE;          // 256: 4, 128: 6, 64: 8
     static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
@@ -40,6 +42,7 @@ struct TcParams {
     int kblk;                 // A_PLAIN: elements per outer k block (== K when there is no K split of A)
     int Cin, Wout, HWout;     // A_CONV3S2
     int epi;
+    int round_out;            // fp32 output rounded to the nearest TF32 value
     int partial;              // split-K: raw fp32 partial sums to D + ks * part_stride, no bias / activation
     int64_t part_stride;
     const float* bias;
@@ -102,12 +105,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+template <bool TF32>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    if (TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -134,10 +145,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// kind::f16 instruction descriptor: D fp32 (bit 4), A bf16 (bits 7-9 = 1), B bf16 (bits 10-12 = 1), both K-major,
+// instruction descriptor: D fp32 (bit 4), A format bits 7-9 and B format bits 10-12 (1 = bf16, 2 = tf32), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool tf32) {
+    return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 template <typename TO> __device__ __forceinline__ void store8(TO* p, const float* v);
@@ -175,10 +186,12 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const TcParams& p) {
     return c;
 }
 
-template <int BN, typename TO>
+template <int BN, typename TI, typename TO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
     using C = TcCfg<BN>;
+    constexpr int BK = ROW_BYTES / (int)sizeof(TI);      // elements per k-block
+    constexpr bool TF32 = sizeof(TI) == 4;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
@@ -245,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN);
+            constexpr uint32_t idesc = make_idesc(BN, TF32);
             int stage = 0, phase = 0, it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const TileCoord tc = decode_tile(t, p);
@@ -261,9 +274,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = smem_base + stage * C::STAGE, sb = sa + C::STAGE_A;
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 16; ++kk) {
-                        // +32 B per K=16 step inside the 128 B swizzle row (encoded >> 4)
-                        tc_mma(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        // one MMA consumes 32 B of K (16 bf16 / 8 tf32): +32 B inside the 128 B swizzle row (encoded >> 4)
+                        tc_mma<TF32>(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                     }
                     tc_commit(empty0 + 8 * stage);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -350,6 +363,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             x[i] += fmaxf(u, 0.f);
                         }
                     }
+                    if (sizeof(TO) == 4 && p.round_out) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) x[i] = round_tf32(x[i]);
+                    }
                     store8<TO>(dst + j, x);
                 }
             }
@@ -390,10 +407,10 @@ bool g_tc_ready = false;
 float* g_splitk_scratch = nullptr;
 constexpr int64_t SPLITK_SCRATCH_FLOATS = 8ll << 20;   // 32 MB
 
-int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
            const cuuint32_t* box, const char* what) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+    CUresult r = g_encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -403,15 +420,33 @@ int encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, 
     return EGR_OK;
 }
 
-template <int BN, typename TO>
+template <int BN, typename TI, typename TO>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
-    gemm_tc_kernel<BN, TO><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    gemm_tc_kernel<BN, TI, TO><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, p);
     EGR_LAUNCHED();
     return EGR_OK;
 }
-template <int BN, typename TO>
+template <int BN, typename TI>
+int launch_tc_bn(bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
+    return out_bf16 ? launch_tc<BN, TI, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<BN, TI, float>(tmA, tmB, p, grid, st);
+}
+template <typename TI>
+int launch_tc_any(int bn, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
+    if (bn == 256) return launch_tc_bn<256, TI>(out_bf16, tmA, tmB, p, grid, st);
+    if (bn == 128) return launch_tc_bn<128, TI>(out_bf16, tmA, tmB, p, grid, st);
+    return launch_tc_bn<64, TI>(out_bf16, tmA, tmB, p, grid, st);
+}
+template <int BN, typename TI, typename TO>
 int set_smem_attr() {
-    EGR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    EGR_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN>::SMEM));
+    return EGR_OK;
+}
+template <int BN>
+int set_smem_attr_bn() {
+    int rc;
+    if ((rc = set_smem_attr<BN, __nv_bfloat16, float>()) || (rc = set_smem_attr<BN, __nv_bfloat16, __nv_bfloat16>()) ||
+        (rc = set_smem_attr<BN, float, float>()) || (rc = set_smem_attr<BN, float, __nv_bfloat16>()))
+        return rc;
     return EGR_OK;
 }
 
@@ -427,20 +462,21 @@ int gemm_tc_init() {
     EGR_CHECK(fn && qres == cudaDriverEntryPointSuccess, EGR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     int rc;
-    if ((rc = set_smem_attr<64, float>()) || (rc = set_smem_attr<64, __nv_bfloat16>()) ||
-        (rc = set_smem_attr<128, float>()) || (rc = set_smem_attr<128, __nv_bfloat16>()) ||
-        (rc = set_smem_attr<256, float>()) || (rc = set_smem_attr<256, __nv_bfloat16>()))
-        return rc;
+    if ((rc = set_smem_attr_bn<64>()) || (rc = set_smem_attr_bn<128>()) || (rc = set_smem_attr_bn<256>())) return rc;
     EGR_CUDA_OK(cudaMalloc(&g_splitk_scratch, SPLITK_SCRATCH_FLOATS * sizeof(float)));
     g_tc_ready = true;
     return EGR_OK;
 }
 
-int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st) {
+int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
     if (!g_tc_ready) {
         if (int rc = gemm_tc_init()) return rc;
     }
     EGR_CHECK(d.M > 0 && d.N > 0 && d.K > 0 && d.groups > 0, EGR_ERR_INVALID, "gemm_tc: empty problem %d %d %d", d.M, d.N, d.K);
+    const bool f32 = in_is_f32 != 0;
+    const int ES = f32 ? 4 : 2;                 // operand element size
+    const int BK = ROW_BYTES / ES;              // elements per k-block
+    const int AL = 16 / ES;                     // elements per 16 bytes (TMA stride granularity)
     EGR_CHECK(d.K % BK == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d", d.K, BK);
     EGR_CHECK(d.N % 64 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: N=%d must be a multiple of 64", d.N);
     EGR_CHECK((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0 &&
@@ -462,7 +498,7 @@ int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st) {
     p.m_tiles = m_tiles; p.n_tiles = d.N / bn; p.groups = d.groups;
     p.kb_total = d.K / BK;
     p.ksplit = 1; p.kb_per_split = p.kb_total;
-    p.amode = d.amode; p.epi = d.epi;
+    p.amode = d.amode; p.epi = d.epi; p.round_out = d.round_tf32;
     p.bias = d.bias; p.b_gs = d.b_gs;
     p.D = d.D; p.ldd = d.ldd; p.d_gs = d.d_gs;
     p.aux = d.aux; p.aux_gs = d.aux_gs; p.Hout_e = d.Hout; p.Wout_e = d.Wout;
@@ -490,14 +526,14 @@ int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st) {
     if (d.amode == A_PLAIN) {
         const int kblk = d.kblk > 0 ? d.kblk : d.K;
         EGR_CHECK(kblk % BK == 0 && d.K % kblk == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: kblk=%d", kblk);
-        EGR_CHECK(d.lda % 8 == 0 && d.a_gs % 8 == 0 && d.kblk_stride % 8 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: A strides must be multiples of 8 elements");
+        EGR_CHECK(d.lda % AL == 0 && d.a_gs % AL == 0 && d.kblk_stride % AL == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: A strides must be multiples of 16 bytes");
         p.kblk = kblk;
         const cuuint64_t dims[4] = {(cuuint64_t)kblk, (cuuint64_t)d.M, (cuuint64_t)(d.K / kblk), (cuuint64_t)d.groups};
         // strides of size-1 dims are irrelevant but must be valid (multiple of 16 B)
-        const cuuint64_t str[3] = {(cuuint64_t)d.lda * 2, (cuuint64_t)(d.K / kblk > 1 ? d.kblk_stride : d.lda) * 2,
-                                   (cuuint64_t)(d.groups > 1 ? d.a_gs : d.lda) * 2};
-        const cuuint32_t box[4] = {BK, BM, 1, 1};
-        if ((rc = encode(&tmA, d.A, 4, dims, str, box, "A"))) return rc;
+        const cuuint64_t str[3] = {(cuuint64_t)d.lda * ES, (cuuint64_t)(d.K / kblk > 1 ? d.kblk_stride : d.lda) * ES,
+                                   (cuuint64_t)(d.groups > 1 ? d.a_gs : d.lda) * ES};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, BM, 1, 1};
+        if ((rc = encode(&tmA, f32, d.A, 4, dims, str, box, "A"))) return rc;
     } else {
         const int Hout = d.Hin / 2, Wout = d.Win / 2, HW = Hout * Wout;
         EGR_CHECK(d.Cin % BK == 0 && d.K == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
@@ -511,24 +547,23 @@ int gemm_tc(const GemmDesc& d, int d_is_bf16, cudaStream_t st) {
         p.Cin = d.Cin; p.Wout = Wout; p.HWout = HW;
         const int64_t n_img = (int64_t)d.groups * (d.M / HW);
         const cuuint64_t dims[5] = {(cuuint64_t)2 * d.Cin, (cuuint64_t)Wout, 2, (cuuint64_t)Hout, (cuuint64_t)n_img};
-        const cuuint64_t str[4] = {(cuuint64_t)2 * d.Cin * 2, (cuuint64_t)d.Win * d.Cin * 2, (cuuint64_t)2 * d.Win * d.Cin * 2,
-                                   (cuuint64_t)d.Hin * d.Win * d.Cin * 2};
-        const cuuint32_t box[5] = {BK, (cuuint32_t)Wout, 1, (cuuint32_t)bh, (cuuint32_t)bimg};
-        if ((rc = encode(&tmA, d.A, 5, dims, str, box, "A(conv3s2)"))) return rc;
+        const cuuint64_t str[4] = {(cuuint64_t)2 * d.Cin * ES, (cuuint64_t)d.Win * d.Cin * ES, (cuuint64_t)2 * d.Win * d.Cin * ES,
+                                   (cuuint64_t)d.Hin * d.Win * d.Cin * ES};
+        const cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)Wout, 1, (cuuint32_t)bh, (cuuint32_t)bimg};
+        if ((rc = encode(&tmA, f32, d.A, 5, dims, str, box, "A(conv3s2)"))) return rc;
     }
     {
         const cuuint64_t dims[3] = {(cuuint64_t)d.K, (cuuint64_t)d.N, (cuuint64_t)d.groups};
-        const cuuint64_t str[2] = {(cuuint64_t)d.K * 2, (cuuint64_t)(d.groups > 1 ? d.w_gs : (int64_t)d.N * d.K) * 2};
-        const cuuint32_t box[3] = {BK, (cuuint32_t)bn, 1};
-        if ((rc = encode(&tmB, d.W, 3, dims, str, box, "W"))) return rc;
+        const cuuint64_t str[2] = {(cuuint64_t)d.K * ES, (cuuint64_t)(d.groups > 1 ? d.w_gs : (int64_t)d.N * d.K) * ES};
+        const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
+        if ((rc = encode(&tmB, f32, d.W, 3, dims, str, box, "W"))) return rc;
     }
 
     const int64_t total = (int64_t)d.groups * m_tiles * p.n_tiles * p.ksplit;
     const int grid = (int)(total < nsm ? total : nsm);
     const bool out_bf16 = d_is_bf16 && !p.partial;
-    if (bn == 256) rc = out_bf16 ? launch_tc<256, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<256, float>(tmA, tmB, p, grid, st);
-    else if (bn == 128) rc = out_bf16 ? launch_tc<128, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<128, float>(tmA, tmB, p, grid, st);
-    else rc = out_bf16 ? launch_tc<64, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<64, float>(tmA, tmB, p, grid, st);
+    rc = f32 ? launch_tc_any<float>(bn, out_bf16, tmA, tmB, p, grid, st)
+             : launch_tc_any<__nv_bfloat16>(bn, out_bf16, tmA, tmB, p, grid, st);
     if (rc) return rc;
     if (p.partial) {
         const int64_t tot = (int64_t)d.M * d.N;

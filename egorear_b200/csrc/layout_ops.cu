@@ -23,7 +23,7 @@ __device__ __forceinline__ UpC upc(int dst, int in_size) {
 // ---------------------------------------------------------------------------------------------
 // NCHW fp32 -> view-major NHWC (float | bf16)
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool RND>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int V, int C, int HW) {
     extern __shared__ float tile[];   // [C][33]
@@ -36,15 +36,19 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, in
     __syncthreads();
     T* dst = out + (((int64_t)v * B + b) * HW + p0) * C;
     for (int p = warp; p < 32; p += 8)
-        for (int c = lane; c < C; c += 32) ActT<T>::st(dst + (int64_t)p * C + c, tile[c * 33 + p]);
+        for (int c = lane; c < C; c += 32) {
+            const float x = tile[c * 33 + p];
+            ActT<T>::st(dst + (int64_t)p * C + c, RND ? round_tf32(x) : x);
+        }
 }
 
-int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_bf16, cudaStream_t st) {
+int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_mode, cudaStream_t st) {
     EGR_CHECK(HW % 32 == 0 && C * 33 * 4 <= 48 * 1024, EGR_ERR_UNSUPPORTED, "nchw_to_nhwc: HW=%d C=%d", HW, C);
     dim3 grid(HW / 32, B * V);
     const size_t smem = sizeof(float) * C * 33;
-    if (out_bf16) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, 256, smem, st>>>(in, (__nv_bfloat16*)out, B, V, C, HW);
-    else nchw_to_nhwc_kernel<float><<<grid, 256, smem, st>>>(in, (float*)out, B, V, C, HW);
+    if (out_mode == 1) nchw_to_nhwc_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>(in, (__nv_bfloat16*)out, B, V, C, HW);
+    else if (out_mode == 2) nchw_to_nhwc_kernel<float, true><<<grid, 256, smem, st>>>(in, (float*)out, B, V, C, HW);
+    else nchw_to_nhwc_kernel<float, false><<<grid, 256, smem, st>>>(in, (float*)out, B, V, C, HW);
     EGR_LAUNCHED();
     return EGR_OK;
 }
@@ -262,6 +266,18 @@ __global__ void repack_conv3_kernel(const float* __restrict__ w, float* __restri
 }
 int repack_conv3(const float* w, float* out, int Cout, int Cin, cudaStream_t st) {
     repack_conv3_kernel<<<(int)ceil_div64((int64_t)Cout * Cin * 9, 256), 256, 0, st>>>(w, out, Cout, Cin);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+__global__ void round_tf32_kernel(float* __restrict__ p, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = round_tf32(p[i]);
+}
+int round_tf32_inplace(float* p, int64_t n, cudaStream_t st) {
+    if (n == 0) return EGR_OK;
+    const int64_t g = ceil_div64(n, 256);
+    round_tf32_kernel<<<(int)(g < 148 * 64 ? g : 148 * 64), 256, 0, st>>>(p, n);
     EGR_LAUNCHED();
     return EGR_OK;
 }

@@ -4,8 +4,9 @@
 
 namespace egr {
 
-// in  [B][V][C][HW] fp32 (NCHW per view)  ->  out [V][B][HW][C] (view-major, channels-last), T = float | bf16
-int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_bf16, cudaStream_t st);
+// in  [B][V][C][HW] fp32 (NCHW per view)  ->  out [V][B][HW][C] (view-major, channels-last)
+// out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to the nearest TF32 value (operand of a kind::tf32 stage)
+int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_mode, cudaStream_t st);
 // fp32 -> activation dtype copy (float: plain copy)
 int cast_act(const float* in, void* out, int out_bf16, int64_t n, cudaStream_t st);
 
@@ -28,6 +29,8 @@ int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, 
 // ---- one-time weight preparation (prepack) ----
 // conv weight [Cout][Cin][3][3] -> [Cout][ky][kx][Cin]
 int repack_conv3(const float* w, float* out, int Cout, int Cin, cudaStream_t st);
+// in-place fp32 -> nearest TF32 value
+int round_tf32_inplace(float* p, int64_t n, cudaStream_t st);
 // fp32 -> bf16 copy
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st);
 // [R][C] -> [C][R]

@@ -158,3 +158,40 @@ def test_tc_rejects_bad_shapes():
     D = torch.empty((128, 64), device="cuda")
     with pytest.raises(_lib.EgrError):
         dense(A, W, None, D, 128, 64, 96, 96, 64)        # K not a multiple of 64
+
+
+def tf32_trunc(x):
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(4096, 64, 128, 1), (700, 128, 96, 0), (64, 2048, 4096, 2)])
+def test_tc_tf32_plain(M, N, K, epi):
+    """fp32 operands through kind::tf32 (pose3d proposal branch): 10-bit mantissa products, fp32 accumulate"""
+    g = torch.Generator(device="cuda").manual_seed(21)
+    A = torch.randn((M, K), generator=g, device="cuda")
+    W = torch.randn((N, K), generator=g, device="cuda") * K ** -0.5
+    bias = torch.randn((N,), device="cuda")
+    D = torch.full((M, N), float("nan"), device="cuda")
+    dense(A, W, bias, D, M, N, K, K, N, epi=epi)
+    want = act(A.double() @ W.double().t() + bias.double(), epi).float()
+    err = float((D - want).abs().max() / want.abs().max())
+    want_t = act(tf32_trunc(A).double() @ tf32_trunc(W).double().t() + bias.double(), epi).float()
+    err_t = float((D - want_t).abs().max() / want_t.abs().max())
+    print("tf32 rel err vs fp64 %.2e, vs truncated-operand fp64 %.2e" % (err, err_t))
+    assert err < 2e-3
+
+
+def test_tc_tf32_conv3s2():
+    Hin, Cin, N, n_img = 64, 64, 128, 2
+    g = torch.Generator(device="cuda").manual_seed(22)
+    x = torch.randn((n_img, Hin, Hin, Cin), generator=g, device="cuda")
+    w = torch.randn((N, Cin, 3, 3), generator=g, device="cuda") * (9 * Cin) ** -0.5
+    bias = torch.randn((N,), device="cuda")
+    Wp = w.permute(0, 2, 3, 1).contiguous().reshape(N, 9 * Cin)
+    M = n_img * (Hin // 2) ** 2
+    D = torch.full((M, N), float("nan"), device="cuda")
+    dense(x, Wp, bias, D, M, N, 9 * Cin, 0, N, amode=1, epi=1, Hin=Hin, Win=Hin, Cin=Cin)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), stride=2, padding=1)
+    want = torch.relu(ref).permute(0, 2, 3, 1).reshape(M, N).float()
+    err = float((D - want).abs().max() / want.abs().max())
+    assert err < 2e-3, err
