@@ -141,10 +141,230 @@ head_up_conv_kernel(const TZ* __restrict__ z, const float* __restrict__ w, const
     }
 }
 
+// =============================================================================================
+// Fast paths for the shipped geometry: 32x32 -> 64x64, C = 128 (every use on the hot path).
+// One block = one image x 4 output rows; the (at most) 4 source rows they touch live in shared memory.
+// Bilinear coefficients come from a 64-entry table built with the same fp32 formula as upc().
+// =============================================================================================
+constexpr int FS = 32, FO = 64, FCH = 128, FSTRIP = 4, FROWS = 4;
+
+struct UpTab {
+    int8_t i0[FO], i1[FO];
+    float l0[FO], l1[FO];
+};
+__device__ __forceinline__ void build_uptab(UpTab* t) {
+    if (threadIdx.x < FO) {
+        const UpC c = upc(threadIdx.x, FS);
+        t->i0[threadIdx.x] = (int8_t)c.i0; t->i1[threadIdx.x] = (int8_t)c.i1;
+        t->l0[threadIdx.x] = c.l0; t->l1[threadIdx.x] = c.l1;
+    }
+}
+template <typename T> __device__ __forceinline__ void unpack8(const T* p, float* v);
+template <> __device__ __forceinline__ void unpack8<float>(const float* p, float* v) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <typename T> __device__ __forceinline__ void pack8_store(T* p, const float* v);
+template <> __device__ __forceinline__ void pack8_store<float>(float* p, const float* v) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void pack8_store<__nv_bfloat16>(__nv_bfloat16* p, const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+
+// R1 tail, fast: relu(up2(z)) -> fp32 NCHW (float4 streaming stores) + channels-last TZ copy (16-byte stores)
+template <typename TZ>
+__global__ void __launch_bounds__(256)
+up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ out_nchw, int64_t o_bs, int64_t o_gs,
+                          TZ* __restrict__ out_nhwc) {
+    constexpr int SLD = 130;                               // transposed tile row stride: conflict-free both ways
+    extern __shared__ __align__(16) uint8_t fsm[];
+    TZ* s1 = reinterpret_cast<TZ*>(fsm);                   // [FROWS*FS px][FCH]   as loaded
+    TZ* s2 = s1 + FROWS * FS * FCH;                        // [FCH][SLD]           transposed
+    __shared__ UpTab tab;
+    const int y0 = blockIdx.x * FSTRIP;
+    const int g = blockIdx.y / B, b = blockIdx.y - g * B;
+    const int img = g * B + b;
+    const int sr0 = upc(y0, FS).i0;
+    const int nsr = upc(y0 + FSTRIP - 1, FS).i1 - sr0 + 1;
+    const int npix = nsr * FS;
+    build_uptab(&tab);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(z + ((int64_t)img * FS * FS + (int64_t)sr0 * FS) * FCH);
+        uint4* dst = reinterpret_cast<uint4*>(s1);
+        const int n16 = npix * FCH * (int)sizeof(TZ) / 16;
+        for (int i = threadIdx.x; i < n16; i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npix * FCH; i += 256) {
+        const int p = i / FCH, c = i - p * FCH;
+        s2[c * SLD + p] = s1[i];
+    }
+    // ---- channels-last copy: item = (pixel, 8 channels) ----
+    if (out_nhwc) {
+        TZ* o = out_nhwc + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH;
+#pragma unroll 2
+        for (int it = threadIdx.x; it < FSTRIP * FO * (FCH / 8); it += 256) {
+            const int c8 = it & 15, px = it >> 4;
+            const int yy = px >> 6, x = px & 63;
+            const int r0 = tab.i0[y0 + yy] - sr0, r1 = tab.i1[y0 + yy] - sr0;
+            const float ly0 = tab.l0[y0 + yy], ly1 = tab.l1[y0 + yy];
+            const int xa = tab.i0[x], xb = tab.i1[x];
+            const float lx0 = tab.l0[x], lx1 = tab.l1[x];
+            float a[8], bb[8], c[8], d[8], r[8];
+            unpack8<TZ>(s1 + (r0 * FS + xa) * FCH + c8 * 8, a);
+            unpack8<TZ>(s1 + (r0 * FS + xb) * FCH + c8 * 8, bb);
+            unpack8<TZ>(s1 + (r1 * FS + xa) * FCH + c8 * 8, c);
+            unpack8<TZ>(s1 + (r1 * FS + xb) * FCH + c8 * 8, d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = fmaxf(ly0 * (lx0 * a[i] + lx1 * bb[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]), 0.f);
+            pack8_store<TZ>(o + (int64_t)px * FCH + c8 * 8, r);
+        }
+    }
+    __syncthreads();
+    // ---- NCHW: item = (channel, row, 4 consecutive x) ----
+    if (out_nchw) {
+        float* o = out_nchw + (int64_t)b * o_bs + (int64_t)g * o_gs + (int64_t)y0 * FO;
+#pragma unroll 2
+        for (int it = threadIdx.x; it < FCH * FSTRIP * (FO / 4); it += 256) {
+            const int x4 = it & 15, yy = (it >> 4) & 3, c = it >> 6;
+            const int r0 = tab.i0[y0 + yy] - sr0, r1 = tab.i1[y0 + yy] - sr0;
+            const float ly0 = tab.l0[y0 + yy], ly1 = tab.l1[y0 + yy];
+            const TZ* t0 = s2 + c * SLD + r0 * FS;
+            const TZ* t1 = s2 + c * SLD + r1 * FS;
+            float r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int x = x4 * 4 + i;
+                const int xa = tab.i0[x], xb = tab.i1[x];
+                const float lx0 = tab.l0[x], lx1 = tab.l1[x];
+                r[i] = fmaxf(ly0 * (lx0 * ActT<TZ>::ld(t0 + xa) + lx1 * ActT<TZ>::ld(t0 + xb)) +
+                             ly1 * (lx0 * ActT<TZ>::ld(t1 + xa) + lx1 * ActT<TZ>::ld(t1 + xb)), 0.f);
+            }
+            __stcs(reinterpret_cast<float4*>(o + ((int64_t)c * FO + yy) * FO + x4 * 4), make_float4(r[0], r[1], r[2], r[3]));
+        }
+    }
+}
+
+// head tail, fast: up2 + ReLU + 1x1 C->J.  One thread = one output pixel, all J outputs; the source tile is stored
+// pixel-major with a 130-element pixel stride so that the per-pixel gathers of a warp never share a bank.
+template <typename TZ, typename TH>
+__global__ void __launch_bounds__(256)
+head_up_conv_fast_kernel(const TZ* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias, int4 wsel,
+                         int B, int J, float* __restrict__ hm, int64_t hm_bs, int64_t hm_gs, TH* __restrict__ hm_t) {
+    constexpr int PST = 130;
+    extern __shared__ __align__(16) uint8_t fsm[];
+    float* sw = reinterpret_cast<float*>(fsm);             // [FCH][HJ]
+    TZ* s = reinterpret_cast<TZ*>(sw + FCH * HJ);          // [FROWS*FS px][PST]
+    __shared__ float sb[HJ];
+    const int y0 = blockIdx.x * FSTRIP;
+    const int g = blockIdx.y / B, b = blockIdx.y - g * B;
+    const int img = g * B + b;
+    const int sel = (g == 0) ? wsel.x : (g == 1) ? wsel.y : (g == 2) ? wsel.z : wsel.w;
+    const float* wv = w + (int64_t)sel * J * FCH;
+    for (int i = threadIdx.x; i < FCH * HJ; i += 256) {
+        const int c = i / HJ, j = i - c * HJ;
+        sw[i] = (j < J) ? wv[j * FCH + c] : 0.f;
+    }
+    if (threadIdx.x < HJ) sb[threadIdx.x] = (threadIdx.x < J) ? bias[(int64_t)sel * J + threadIdx.x] : 0.f;
+    const int sr0 = upc(y0, FS).i0;
+    const int nsr = upc(y0 + FSTRIP - 1, FS).i1 - sr0 + 1;
+    {
+        // 8-byte pieces: 4 bf16 or 2 floats; the padded pixel stride keeps them 4-byte aligned only -> 32-bit stores
+        const uint2* src = reinterpret_cast<const uint2*>(z + ((int64_t)img * FS * FS + (int64_t)sr0 * FS) * FCH);
+        constexpr int PER8 = 8 / (int)sizeof(TZ);          // elements per piece
+        constexpr int PPP = FCH / PER8;                    // pieces per pixel
+        uint32_t* dst = reinterpret_cast<uint32_t*>(s);
+        for (int i = threadIdx.x; i < nsr * FS * PPP; i += 256) {
+            const int p = i / PPP, q = i - p * PPP;
+            const uint2 u = __ldg(src + i);
+            const int word = (p * PST + q * PER8) * (int)sizeof(TZ) / 4;
+            dst[word] = u.x; dst[word + 1] = u.y;
+        }
+    }
+    __syncthreads();
+    const int yy = threadIdx.x >> 6, x = threadIdx.x & 63;
+    const int y = y0 + yy;
+    const UpC cy = upc(y, FS), cx = upc(x, FS);
+    const TZ* p00 = s + ((cy.i0 - sr0) * FS + cx.i0) * PST;
+    const TZ* p01 = s + ((cy.i0 - sr0) * FS + cx.i1) * PST;
+    const TZ* p10 = s + ((cy.i1 - sr0) * FS + cx.i0) * PST;
+    const TZ* p11 = s + ((cy.i1 - sr0) * FS + cx.i1) * PST;
+    float acc[HJ];
+#pragma unroll
+    for (int j = 0; j < HJ; ++j) acc[j] = sb[j];
+#pragma unroll 4
+    for (int c = 0; c < FCH; c += 2) {
+        float a0, a1, b0, b1, c0, c1, d0, d1;
+        if (sizeof(TZ) == 2) {
+            const uint32_t ua = *reinterpret_cast<const uint32_t*>(p00 + c), ub = *reinterpret_cast<const uint32_t*>(p01 + c);
+            const uint32_t uc = *reinterpret_cast<const uint32_t*>(p10 + c), ud = *reinterpret_cast<const uint32_t*>(p11 + c);
+            a0 = __uint_as_float(ua << 16); a1 = __uint_as_float(ua & 0xffff0000u);
+            b0 = __uint_as_float(ub << 16); b1 = __uint_as_float(ub & 0xffff0000u);
+            c0 = __uint_as_float(uc << 16); c1 = __uint_as_float(uc & 0xffff0000u);
+            d0 = __uint_as_float(ud << 16); d1 = __uint_as_float(ud & 0xffff0000u);
+        } else {
+            const float2 fa = *reinterpret_cast<const float2*>(p00 + c), fb = *reinterpret_cast<const float2*>(p01 + c);
+            const float2 fc = *reinterpret_cast<const float2*>(p10 + c), fd = *reinterpret_cast<const float2*>(p11 + c);
+            a0 = fa.x; a1 = fa.y; b0 = fb.x; b1 = fb.y; c0 = fc.x; c1 = fc.y; d0 = fd.x; d1 = fd.y;
+        }
+        const float u0 = fmaxf(cy.l0 * (cx.l0 * a0 + cx.l1 * b0) + cy.l1 * (cx.l0 * c0 + cx.l1 * d0), 0.f);
+        const float u1 = fmaxf(cy.l0 * (cx.l0 * a1 + cx.l1 * b1) + cy.l1 * (cx.l0 * c1 + cx.l1 * d1), 0.f);
+        const float4* w0 = reinterpret_cast<const float4*>(sw + c * HJ);
+#pragma unroll
+        for (int q = 0; q < HJ / 4; ++q) {
+            const float4 wa = w0[q], wb = w0[q + HJ / 4];
+            acc[q * 4 + 0] = fmaf(wa.x, u0, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(wa.y, u0, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(wa.z, u0, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(wa.w, u0, acc[q * 4 + 3]);
+            acc[q * 4 + 0] = fmaf(wb.x, u1, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(wb.y, u1, acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(wb.z, u1, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(wb.w, u1, acc[q * 4 + 3]);
+        }
+    }
+    float* o = hm + (int64_t)b * hm_bs + (int64_t)g * hm_gs + (int64_t)y * FO + x;
+#pragma unroll
+    for (int j = 0; j < HJ; ++j)
+        if (j < J) o[(int64_t)j * FO * FO] = acc[j];
+    if (hm_t) {
+        TH* ot = hm_t + ((int64_t)img * J) * FO * FO + (int64_t)y * FO + x;
+#pragma unroll
+        for (int j = 0; j < HJ; ++j)
+            if (j < J) ActT<TH>::st(ot + (int64_t)j * FO * FO, acc[j]);
+    }
+}
+
 int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, const int* wsel_host, int B, int G,
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st) {
     EGR_CHECK(J <= HJ && (2 * Hs) % STRIP == 0 && G <= 4, EGR_ERR_UNSUPPORTED, "head_up_conv: J=%d Hs=%d G=%d", J, Hs, G);
+    if (Hs == FS && Ws == FS && C == FCH) {
+        const size_t es = z_bf16 ? 2 : 4;
+        const size_t fsmem = sizeof(float) * FCH * HJ + es * FROWS * FS * 130;
+        dim3 fgrid(FO / FSTRIP, G * B);
+        int4 fsel = make_int4(wsel_host[0], wsel_host[1], wsel_host[2], wsel_host[3]);
+        if (z_bf16) {
+            auto k = head_up_conv_fast_kernel<__nv_bfloat16, __nv_bfloat16>;
+            EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k<<<fgrid, 256, fsmem, st>>>((const __nv_bfloat16*)z, w, bias, fsel, B, J, hm, hm_bs, hm_gs, (__nv_bfloat16*)hm_t);
+        } else {
+            auto k = head_up_conv_fast_kernel<float, float>;
+            EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k<<<fgrid, 256, fsmem, st>>>((const float*)z, w, bias, fsel, B, J, hm, hm_bs, hm_gs, (float*)hm_t);
+        }
+        EGR_LAUNCHED();
+        return EGR_OK;
+    }
     const size_t smem = sizeof(float) * ((size_t)C * (STRIP * Ws + 1) + (size_t)C * HJ);
     dim3 grid(2 * Hs / STRIP, G * B);
     int4 wsel = make_int4(wsel_host[0], wsel_host[1], wsel_host[2], wsel_host[3]);
@@ -207,6 +427,22 @@ up2_relu_dual_kernel(const TZ* __restrict__ z, int B, int Hs, int Ws, int C, flo
 int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
                   int64_t o_gs, void* out_nhwc, cudaStream_t st) {
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
+    if (Hs == FS && Ws == FS && C == FCH) {
+        const size_t es = z_bf16 ? 2 : 4;
+        const size_t fsmem = es * (FROWS * FS * FCH + FCH * 130);
+        dim3 fgrid(FO / FSTRIP, G * B);
+        if (z_bf16) {
+            auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
+            EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k<<<fgrid, 256, fsmem, st>>>((const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc);
+        } else {
+            auto k = up2_relu_dual_fast_kernel<float>;
+            EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            k<<<fgrid, 256, fsmem, st>>>((const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc);
+        }
+        EGR_LAUNCHED();
+        return EGR_OK;
+    }
     const size_t smem = sizeof(float) * (size_t)C * (STRIP * Ws + 1);
     dim3 grid(2 * Hs / STRIP, G * B);
     if (z_bf16) {
