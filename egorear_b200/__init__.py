@@ -1,0 +1,76 @@
+"""egorear_b200 — B200-native (sm_100a) hot path of EgoRear behind the reference's module interfaces.
+
+    import egorear_b200
+    egorear_b200.patch(precision="bf16")      # swap the hot path under an imported EgoRear checkout
+
+Everything computes through egorear_b200/libegorear_b200.so (C-ABI, include/egorear_b200.h); there is no CPU fallback.
+"""
+import functools
+import importlib
+
+__all__ = ["patch", "PATCH_TABLE"]
+
+# reference module -> names rebound by patch() (reference file:line in INTEGRATION.md)
+PATCH_TABLE = {
+    "pose_estimation.utils.loss": ["get_max_preds"],
+    "generate_heatmap": ["generate_target"],
+    "pose_estimation.models.utils.deform_attn": ["MSDeformAttn"],
+    "pose_estimation.models.estimator.egoposeformer_heatmap": ["EgoPoseFormerHeatmap"],
+    "pose_estimation.models.estimator.egoposeformer_heatmap_mvf_ex": [
+        "EgoPoseFormerHeatmapMVFEX", "HeatmapMVF", "MultiViewTransformerLayer", "DeformMultiViewAttn", "SpatialMHA",
+        "TransformerHeadLayer", "EgoPoseFormerHeatmap", "get_max_preds"],
+    "pose_estimation.models.estimator.egoposeformer_mvf_ex": [
+        "EgoPoseFormerMVFEX", "EgoPoseFormerPose3D", "EgoPoseFormerTransformerLayer", "DeformStereoAttn",
+        "EgoformerSpatialMHA", "EgoPoseFormerHeatmapMVFEX"],
+    "pose_estimation.models.estimator": ["EgoPoseFormerHeatmap", "EgoPoseFormerHeatmapMVFEX", "EgoPoseFormerMVFEX"],
+    "pose_estimation.pl_wrappers.egoposeformer.heatmap": ["EgoPoseFormerHeatmap", "get_max_preds"],
+    "pose_estimation.pl_wrappers.egoposeformer.heatmap_mvf_ex": ["EgoPoseFormerHeatmapMVFEX", "get_max_preds"],
+    "pose_estimation.pl_wrappers.egoposeformer.pose_3d_mvf_ex": ["EgoPoseFormerMVFEX"],
+}
+
+_PRECISION_CLASSES = ("EgoPoseFormerHeatmapMVFEX", "HeatmapMVF", "EgoPoseFormerPose3D", "EgoPoseFormerMVFEX")
+
+
+def _with_precision(cls, precision):
+    """subclass whose constructor defaults `precision` (the one kwarg the reference's YAML does not carry)"""
+    @functools.wraps(cls, updated=())
+    class _P(cls):
+        def __init__(self, *a, **k):
+            k.setdefault("precision", precision)
+            super().__init__(*a, **k)
+    _P.__name__, _P.__qualname__ = cls.__name__, cls.__qualname__
+    return _P
+
+
+def patch(precision="bf16", modules=None, strict=False):
+    """Rebind the hot-path names inside the reference's modules to the B200 implementations.
+
+    Only modules that can be imported (or are already in sys.modules) are touched; with strict=True a module of
+    PATCH_TABLE that fails to import raises.  Returns {module name: [names rebound]}.
+    Fails loudly (ImportError) when libegorear_b200.so has not been built.
+    """
+    if precision not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    from . import _lib, modules as M, ops
+    _lib.load()
+    repl = {"get_max_preds": ops.get_max_preds, "generate_target": ops.generate_target}
+    for name in set(n for names in PATCH_TABLE.values() for n in names):
+        if name in repl:
+            continue
+        cls = getattr(M, name)
+        repl[name] = _with_precision(cls, precision) if name in _PRECISION_CLASSES else cls
+    done = {}
+    for modname, names in PATCH_TABLE.items():
+        if modules is not None and modname not in modules:
+            continue
+        try:
+            mod = importlib.import_module(modname)
+        except Exception:
+            if strict:
+                raise
+            continue
+        for n in names:
+            if hasattr(mod, n) or strict:
+                setattr(mod, n, repl[n])
+                done.setdefault(modname, []).append(n)
+    return done
