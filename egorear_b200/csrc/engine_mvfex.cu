@@ -7,9 +7,11 @@
 // Stage dtype is fp32 (EGR_PREC_FP32) or bf16 (EGR_PREC_BF16); module outputs are always fp32 NCHW.
 #include "engine_common.cuh"
 #include "token_kernels.cuh"
+#include "token_batched.cuh"
 
 namespace egr {
 int g_opt_tc = 1;
+int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
 extern int g_opt_pose_p2_bf16;
 }
 using namespace egr;
@@ -38,6 +40,11 @@ struct egr_mvfex {
     WMat h2_0, h2_2, h2_5;                     // conv_heatmap_layers.0.{0,2,5}
     float *h2_7w = nullptr, *h2_7b = nullptr;  // [V][J][128], [V][J]
     MvfTokenW* d_tokw = nullptr;               // device [V]
+    // batched token path (bf16 precision): token GEMM weights (fp32 rounded to TF32, sets = V) + per-refiner pointer tables
+    bool tokb = false;
+    WMat tk_hp2, tk_fcq, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
+    const float** d_ptrs = nullptr;            // device [TP_COUNT][4]
+    int KA = 0;
     bool has_heads = false, has_ref[4] = {false, false, false, false};   // parameter groups present at prepack
     std::unordered_map<std::string, std::pair<void*, int64_t>> dbg;
 };
@@ -151,7 +158,11 @@ struct Bufs {
     void *Xh, *Xown, *h1a, *a1, *b1, *c1, *z, *ff, *r1a, *refn, *hmT, *xT, *h1t, *t1;
     float *q1, *anch, *maxv;
     uint8_t* valid;
+    float *tx, *tz, *toa, *tA, *tqkv, *to, *thid;     // batched token path
 };
+
+enum TokPtr { TP_LNC_W, TP_LNC_B, TP_LNS_W, TP_LNS_B, TP_LNF_W, TP_LNF_B, TP_PN_W, TP_PN_B, TP_PTAB, TP_BFB_T, TP_BFB_B, TP_JQ,
+              TP_COUNT };
 
 // carve the workspace for B frames and G refiner groups (G = V for the full forward, 1 for one refiner)
 int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, void* base, int64_t cap, Bufs* o) {
@@ -178,8 +189,132 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.anch = (float*)c.take((int64_t)B * V * J * 2 * 4);
     b.maxv = (float*)c.take((int64_t)B * V * J * 4);
     b.valid = (uint8_t*)c.take((int64_t)B * V * J);
+    if (h->tokb) {
+        const int64_t T = (int64_t)B * J;
+        b.tx = (float*)c.take(G * T * EMB * 4);
+        b.tz = (float*)c.take(G * T * EMB * 4);
+        b.toa = (float*)c.take(G * T * TOK_OA * 4);
+        b.tA = (float*)c.take(G * T * V * h->KA * 4);
+        b.tqkv = (float*)c.take(G * T * 3 * EMB * 4);
+        b.to = (float*)c.take(G * T * EMB * 4);
+        b.thid = (float*)c.take(G * T * TOK_FF * 4);
+    }
     if (o) *o = b;
     return c.off + 256;
+}
+
+// fp32 weight matrix [sets][N][K] + bias [sets][N] without a bf16 copy (TF32 token GEMMs)
+int alloc_wmat(egr_mvfex* h, WMat& m, int sets, int N, int K, cudaStream_t st) {
+    m.N = N; m.K = K; m.sets = sets; m.bf16 = nullptr;
+    if (int rc = h->pool.alloc(&m.f32, (int64_t)sets * N * K)) return rc;
+    if (int rc = h->pool.alloc(&m.bias, (int64_t)sets * N)) return rc;
+    EGR_CUDA_OK(cudaMemsetAsync(m.f32, 0, sizeof(float) * sets * N * K, st));
+    EGR_CUDA_OK(cudaMemsetAsync(m.bias, 0, sizeof(float) * sets * N, st));
+    return EGR_OK;
+}
+int copy_rows(egr_mvfex* h, const std::string& key, float* dst_w, float* dst_b, int N, int K, cudaStream_t st) {
+    int rc = EGR_OK;
+    const float* w = h->params.get(key + ".weight", (int64_t)N * K, &rc);
+    if (!w) return rc;
+    const float* b = h->params.get(key + ".bias", N, &rc);
+    if (!b) return rc;
+    EGR_CUDA_OK(cudaMemcpyAsync(dst_w, w, sizeof(float) * N * K, cudaMemcpyDeviceToDevice, st));
+    EGR_CUDA_OK(cudaMemcpyAsync(dst_b, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    return EGR_OK;
+}
+
+// derived weights of the batched token path for refiner r (see token_batched.cuh for the algebra)
+int build_tokb(egr_mvfex* h, int r, const std::string& refiner, cudaStream_t st) {
+    const int E = EMB, V = h->V, KA = h->KA, HD = E / TOK_NH;
+    const std::string L = refiner + ".transformer_layers.0";
+    int rc;
+    if ((rc = copy_rows(h, refiner + ".heatmap_proj.2", h->tk_hp2.f32 + (int64_t)r * E * E, h->tk_hp2.bias + r * E, E, E, st))) return rc;
+    if ((rc = copy_rows(h, refiner + ".fc_query.0", h->tk_fcq.f32 + (int64_t)r * E * E, h->tk_fcq.bias + r * E, E, E, st))) return rc;
+    float* sa = h->tk_sa.f32 + (int64_t)r * TOK_OA * E;
+    float* sab = h->tk_sa.bias + r * TOK_OA;
+    if ((rc = copy_rows(h, L + ".cross_attn.sampling_offsets", sa, sab, TOK_NH * TOK_P * 2, E, st))) return rc;
+    if ((rc = copy_rows(h, L + ".cross_attn.attention_weights", sa + (int64_t)TOK_NH * TOK_P * 2 * E, sab + TOK_NH * TOK_P * 2, TOK_NH * TOK_P, E, st))) return rc;
+    float* qkv = h->tk_qkv.f32 + (int64_t)r * 3 * E * E;
+    float* qkvb = h->tk_qkv.bias + r * 3 * E;
+    if ((rc = copy_rows(h, L + ".spatial_attn.q_proj", qkv, qkvb, E, E, st))) return rc;
+    if ((rc = copy_rows(h, L + ".spatial_attn.k_proj", qkv + (int64_t)E * E, qkvb + E, E, E, st))) return rc;
+    if ((rc = copy_rows(h, L + ".spatial_attn.v_proj", qkv + (int64_t)2 * E * E, qkvb + 2 * E, E, E, st))) return rc;
+    if ((rc = copy_rows(h, L + ".spatial_attn.out_proj", h->tk_o.f32 + (int64_t)r * E * E, h->tk_o.bias + r * E, E, E, st))) return rc;
+    if ((rc = copy_rows(h, L + ".ffn.layers.0.0", h->tk_f1.f32 + (int64_t)r * TOK_FF * E, h->tk_f1.bias + r * TOK_FF, TOK_FF, E, st))) return rc;
+    if ((rc = copy_rows(h, L + ".ffn.layers.1", h->tk_f2.f32 + (int64_t)r * E * TOK_FF, h->tk_f2.bias + r * E, E, TOK_FF, st))) return rc;
+    // cross-attention fold
+    const float *Wv, *Wp, *Wop, *bop, *Wfuse, *bfuse;
+    if ((rc = get_vec(h, L + ".cross_attn.value_proj.weight", E * E, &Wv))) return rc;
+    if ((rc = get_vec(h, refiner + ".frame_feat_multi_view_proj.weight", E * FC, &Wp))) return rc;
+    if ((rc = get_vec(h, L + ".cross_attn.output_proj.weight", E * E, &Wop))) return rc;
+    if ((rc = get_vec(h, L + ".cross_attn.output_proj.bias", E, &bop))) return rc;
+    if ((rc = get_vec(h, L + ".fuse_mlp.weight", (int64_t)E * V * E, &Wfuse))) return rc;
+    if ((rc = get_vec(h, L + ".fuse_mlp.bias", E, &bfuse))) return rc;
+    float *mfold, *M1;
+    if ((rc = h->pool.alloc(&mfold, (int64_t)E * FC))) return rc;       // [E][128] = Wv · Wp
+    if ((rc = h->pool.alloc(&M1, (int64_t)V * E * E))) return rc;       // per view [E][E] = Wfuse_v · Wop
+    if ((rc = small_matmul_ex(Wv, E, Wp, FC, nullptr, mfold, FC, E, FC, E, st))) return rc;
+    float* Wc = h->tk_c.f32 + (int64_t)r * E * V * KA;
+    const int64_t ldc = (int64_t)V * KA;
+    for (int v = 0; v < V; ++v) {
+        float* M1v = M1 + (int64_t)v * E * E;
+        if ((rc = small_matmul_ex(Wfuse + (int64_t)v * E, (int64_t)V * E, Wop, E, nullptr, M1v, E, E, E, E, st))) return rc;
+        float* Wcv = Wc + (int64_t)v * KA;
+        for (int hh = 0; hh < TOK_NH; ++hh)      // raw-channel block of head hh: M1[:, head] · mfold[head, :]
+            if ((rc = small_matmul_ex(M1v + hh * HD, E, mfold + (int64_t)hh * HD * FC, FC, nullptr, Wcv + hh * TOK_RAWC, ldc, E,
+                                      TOK_RAWC, HD, st))) return rc;
+        // E-term block (sampled position table P'): M1 itself
+        EGR_CUDA_OK(cudaMemcpy2DAsync(Wcv + TOK_NH * TOK_RAWC, sizeof(float) * ldc, M1v, sizeof(float) * E, sizeof(float) * E, E,
+                                      cudaMemcpyDeviceToDevice, st));
+        // validity column: Wfuse_v · b_op
+        if ((rc = small_matmul_ex(Wfuse + (int64_t)v * E, (int64_t)V * E, bop, 1, nullptr, Wcv + TOK_NH * TOK_RAWC + E, ldc, E, 1, E, st)))
+            return rc;
+    }
+    EGR_CUDA_OK(cudaMemcpyAsync(h->tk_c.bias + r * E, bfuse, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    return EGR_OK;
+}
+
+// Q1 rest + A1 A2 A3 + post_norm over all tokens of G refiner groups (weights from refiner r0 on)
+int run_tokens_batched(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const float* bfb, int64_t bfb_bs, int64_t bfb_gs,
+                       const float* anchors, const uint8_t* valid, cudaStream_t st) {
+    const int J = h->J, V = h->V, E = EMB, KA = h->KA;
+    const int T = B * J;
+    const int bf = (h->prec == EGR_PREC_BF16);
+    const float* const* P = h->d_ptrs;
+    auto ptr = [&](int which) { return P + which * 4 + r0; };
+    int rc;
+    auto gemm = [&](const float* A, int K, const WMat& W, float* D, int epi, int rnd) {
+        GemmDesc d;
+        d.A = A; d.lda = K; d.M = T; d.D = D; d.ldd = W.N; d.epi = epi; d.round_tf32 = rnd;
+        d.groups = G; d.a_gs = (int64_t)T * K; d.d_gs = (int64_t)T * W.N;
+        return run_gemm(d, W, r0, PREC_TF32, true, st);
+    };
+    // heatmap_proj.2, + fc_bfb(avgpool) + joint embed, fc_query + ReLU
+    if ((rc = gemm(w.q1, E, h->tk_hp2, w.tz, EPI_NONE, 0))) return rc;
+    TokQueryArgs qa{};
+    qa.G = G; qa.B = B; qa.J = J; qa.E = E; qa.hw = 64; qa.y0 = w.tz; qa.bfb = bfb; qa.bfb_bs = bfb_bs; qa.bfb_gs = bfb_gs;
+    qa.bfb_T = ptr(TP_BFB_T); qa.bfb_b = ptr(TP_BFB_B); qa.jq = ptr(TP_JQ); qa.x0 = w.to;
+    if ((rc = tok_jqa_query(qa, st))) return rc;
+    if ((rc = gemm(w.to, E, h->tk_fcq, w.tx, EPI_RELU, 1))) return rc;
+    // A1: offsets + logits, sampling, folded value/output/fuse GEMM, residual + LN
+    if ((rc = gemm(w.tx, E, h->tk_sa, w.toa, EPI_NONE, 0))) return rc;
+    TokSampleArgs sa{};
+    sa.G = G; sa.B = B; sa.V = V; sa.J = J; sa.H = FH; sa.W = FW; sa.E = E; sa.KA = KA; sa.oa = w.toa; sa.anchors = anchors;
+    sa.valid = valid; sa.X = w.Xh; sa.ptab = ptr(TP_PTAB); sa.A = w.tA;
+    if ((rc = tok_sample(sa, bf, st))) return rc;
+    if ((rc = gemm(w.tA, V * KA, h->tk_c, w.tz, EPI_NONE, 0))) return rc;
+    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNC_W), ptr(TP_LNC_B), st))) return rc;
+    // A2: joint self-attention
+    if ((rc = gemm(w.tx, E, h->tk_qkv, w.tqkv, EPI_NONE, 0))) return rc;
+    if ((rc = tok_attn(w.tqkv, w.to, G * B, J, E, st))) return rc;
+    if ((rc = gemm(w.to, E, h->tk_o, w.tz, EPI_NONE, 0))) return rc;
+    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNS_W), ptr(TP_LNS_B), st))) return rc;
+    // A3: FFN
+    if ((rc = gemm(w.tx, E, h->tk_f1, w.thid, EPI_GELU, 1))) return rc;
+    if ((rc = gemm(w.thid, TOK_FF, h->tk_f2, w.tz, EPI_NONE, 0))) return rc;
+    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNF_W), ptr(TP_LNF_B), st))) return rc;
+    // post_norm + transposed token image for T1
+    return tok_ln_image(w.tx, w.xT, bf, G, B, J, E, ptr(TP_PN_W), ptr(TP_PN_B), st);
 }
 
 // the refiner chain for G groups whose weights start at refiner r0
@@ -193,7 +328,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     EGR_MARK("Q1a", st);
     // Q1a: relu(heatmap_proj.0(heatmap))  [G][B*J][4096] -> [G][B*J][256] fp32
     d = GemmDesc();
-    d.A = w.hmT; d.lda = FHW; d.M = B * J; d.D = w.q1; d.ldd = EMB; d.epi = EPI_RELU;
+    d.A = w.hmT; d.lda = FHW; d.M = B * J; d.D = w.q1; d.ldd = EMB; d.epi = EPI_RELU; d.round_tf32 = h->tokb ? 1 : 0;
     d.groups = G; d.a_gs = (int64_t)B * J * FHW; d.d_gs = (int64_t)B * J * EMB;
     if ((rc = run_gemm(d, h->hp0, r0, prec, /*out_f32=*/true, st))) return rc;
     EGR_MARK("tokens", st);
@@ -202,7 +337,11 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     ta.B = B; ta.V = h->V; ta.J = J; ta.H = FH; ta.W = FW; ta.r0 = r0; ta.G = G;
     ta.q1 = w.q1; ta.bfb = bfb; ta.bfb_bs = bfb_bs; ta.bfb_gs = bfb_gs; ta.bfb_hw = 64;
     ta.anchors = anchors; ta.valid = valid; ta.X = w.Xh; ta.xT = w.xT; ta.w = h->d_tokw;
-    if ((rc = launch_mvf_tokens(ta, bf, st))) return rc;
+    if (h->tokb) {
+        if ((rc = run_tokens_batched(h, B, G, r0, w, bfb, bfb_bs, bfb_gs, anchors, valid, st))) return rc;
+    } else {
+        if ((rc = launch_mvf_tokens(ta, bf, st))) return rc;
+    }
     EGR_MARK("T1", st);
     // T1: 1x1(15->64) ReLU, then the 1x1(64->128) commuted in front of the bilinear x2 (both linear)
     d = GemmDesc();
@@ -293,6 +432,7 @@ void note_all(egr_mvfex* h, const Bufs& w, int B, int G) {
 extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "tc") { g_opt_tc = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pose_p2_bf16") { g_opt_pose_p2_bf16 = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "tok_batched") { g_opt_tok_batched = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }
 
@@ -306,6 +446,8 @@ extern "C" int egr_mvfex_create(int num_views, int num_heatmap, float heatmap_th
     egr_mvfex* h = new egr_mvfex();
     h->V = num_views; h->J = num_heatmap; h->thr = heatmap_threshold; h->prec = precision;
     h->head_sets = (num_views == 2) ? 1 : 2;
+    h->tokb = (precision == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    h->KA = tok_ka(EMB, true);
     *out = h;
     return EGR_OK;
 }
@@ -336,6 +478,8 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
     if (h->prec == EGR_PREC_BF16 && g_opt_tc) {
         if ((rc = gemm_tc_init())) return rc;
     }
+    h->tokb = (h->prec == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    h->KA = tok_ka(EMB, true);
     auto head = [&](const char* sub) { return [sub](int s) { return std::string(kHead[s]) + sub; }; };
     auto ref = [&](const char* sub) { return [sub](int s) { return std::string(kRefiner4[s]) + sub; }; };
     // a standalone HeatmapMVF registers one refiner only; the full module registers heads + all refiners
@@ -395,6 +539,32 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
     }
     if ((rc = h->pool.alloc(&h->d_tokw, V))) return rc;
     EGR_CUDA_OK(cudaMemcpyAsync(h->d_tokw, tok.data(), sizeof(MvfTokenW) * V, cudaMemcpyHostToDevice, st));
+    if (h->tokb) {
+        const int E = EMB;
+        if ((rc = alloc_wmat(h, h->tk_hp2, V, E, E, st)) || (rc = alloc_wmat(h, h->tk_fcq, V, E, E, st)) ||
+            (rc = alloc_wmat(h, h->tk_sa, V, TOK_OA, E, st)) || (rc = alloc_wmat(h, h->tk_c, V, E, V * h->KA, st)) ||
+            (rc = alloc_wmat(h, h->tk_qkv, V, 3 * E, E, st)) || (rc = alloc_wmat(h, h->tk_o, V, E, E, st)) ||
+            (rc = alloc_wmat(h, h->tk_f1, V, TOK_FF, E, st)) || (rc = alloc_wmat(h, h->tk_f2, V, E, TOK_FF, st)))
+            return rc;
+        std::vector<const float*> ptrs(TP_COUNT * 4, nullptr);
+        for (int r = 0; r < V; ++r) {
+            if (!h->has_ref[r]) continue;
+            if ((rc = build_tokb(h, r, kRefiner4[r], st))) return rc;
+            const MvfTokenW& t = tok[r];
+            ptrs[TP_LNC_W * 4 + r] = t.layer.lnc_w; ptrs[TP_LNC_B * 4 + r] = t.layer.lnc_b;
+            ptrs[TP_LNS_W * 4 + r] = t.layer.lns_w; ptrs[TP_LNS_B * 4 + r] = t.layer.lns_b;
+            ptrs[TP_LNF_W * 4 + r] = t.layer.lnf_w; ptrs[TP_LNF_B * 4 + r] = t.layer.lnf_b;
+            ptrs[TP_PN_W * 4 + r] = t.pn_w; ptrs[TP_PN_B * 4 + r] = t.pn_b;
+            ptrs[TP_PTAB * 4 + r] = t.layer.ptab;
+            ptrs[TP_BFB_T * 4 + r] = t.bfb_T; ptrs[TP_BFB_B * 4 + r] = t.bfb_b; ptrs[TP_JQ * 4 + r] = t.jq;
+        }
+        WMat* all[8] = {&h->tk_hp2, &h->tk_fcq, &h->tk_sa, &h->tk_c, &h->tk_qkv, &h->tk_o, &h->tk_f1, &h->tk_f2};
+        for (WMat* m : all)
+            if ((rc = round_tf32_inplace(m->f32, (int64_t)m->sets * m->N * m->K, st))) return rc;
+        if ((rc = h->pool.alloc(&h->d_ptrs, TP_COUNT * 4))) return rc;
+        EGR_CUDA_OK(cudaMemcpyAsync(h->d_ptrs, ptrs.data(), sizeof(const float*) * TP_COUNT * 4, cudaMemcpyHostToDevice, st));
+        EGR_CUDA_OK(cudaStreamSynchronize(st));      // ptrs / tok are host locals
+    }
     EGR_CUDA_OK(cudaStreamSynchronize(st));
     h->packed = true;
     return EGR_OK;

@@ -6,8 +6,10 @@
 // becomes a K-split GEMM over the 4 per-view [B][64*128] blocks with the weight columns permuted once at prepack.
 #include "engine_common.cuh"
 #include "token_kernels.cuh"
+#include "token_batched.cuh"
 
 namespace egr {
+extern int g_opt_tok_batched;
 CamCalib make_calib(int cam_id, const float* calib_host);
 // P2 (conv_frame_feat + mlp_pred) feeds the 3D proposal directly: bf16 operands cost ~0.1 mm MPJPE on their own
 // (measured), which is the whole parity budget, so in EGR_PREC_BF16 the branch keeps fp32 activations and weights and
@@ -17,6 +19,10 @@ int g_opt_pose_p2_bf16 = 0;
 using namespace egr;
 
 constexpr int PH = 64, PW = 64, PHW = 4096, PC = 128, PE = 128;
+
+struct PoseTokB {       // token GEMM weights of one layer (fp32 rounded to TF32)
+    WMat sa, c, qkv, o, f1, f2, r0;
+};
 
 struct egr_pose3d {
     int V = 4, J = 16, L = 3, cam_model = 0, use_init = 1, prec = EGR_PREC_FP32;
@@ -28,6 +34,13 @@ struct egr_pose3d {
     WMat c0, c2, c5, c7;          // conv_frame_feat.{0,2,5,7}
     WMat m0, m1, m2;              // mlp_pred.0.0 (permuted), mlp_pred.1.0, mlp_pred.2
     PoseTokenW* d_w = nullptr;
+    // batched token path (bf16 precision)
+    bool tokb = false;
+    int KA = 0;
+    PoseTokenW tw_host;
+    WMat tk_g2, tk_g4;
+    PoseTokB tb[4];
+    const float** d_ptrs = nullptr;     // device [L][8]: lnc w,b  lns w,b  lnf w,b  post_norm w,b
     std::unordered_map<std::string, std::pair<void*, int64_t>> dbg;
 };
 
@@ -123,6 +136,7 @@ struct PBufs {
     void *Xi, *Xf, *p0, *p2, *p3, *p5, *p7;
     float *m0, *m1, *anch;
     uint8_t* valid;
+    float *tx, *tz, *toa, *tA, *tqkv, *to, *thid, *tp3;     // batched token path
 };
 
 int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
@@ -142,8 +156,134 @@ int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
     b.m1 = (float*)c.take((int64_t)B * 128 * 4);
     b.anch = (float*)c.take(VB * h->J * 2 * 4);
     b.valid = (uint8_t*)c.take(VB * h->J);
+    if (h->tokb) {
+        const int64_t T = (int64_t)B * h->J;
+        b.tx = (float*)c.take(T * PE * 4);
+        b.tz = (float*)c.take(T * PE * 4);
+        b.toa = (float*)c.take(T * TOK_OA * 4);
+        b.tA = (float*)c.take(T * h->V * h->KA * 4);
+        b.tqkv = (float*)c.take(T * 3 * PE * 4);
+        b.to = (float*)c.take(T * PE * 4);
+        b.thid = (float*)c.take(T * TOK_FF * 4);
+        b.tp3 = (float*)c.take(T * 4 * 4);
+    }
     if (o) *o = b;
     return c.off + 256;
+}
+
+// ---- batched token path (EGR_PREC_BF16): derived weights + orchestration (algebra in token_batched.cuh) ----
+int p_alloc_wmat(egr_pose3d* h, WMat& m, int N, int K, cudaStream_t st) {
+    m.N = N; m.K = K; m.sets = 1; m.bf16 = nullptr;
+    if (int rc = h->pool.alloc(&m.f32, (int64_t)N * K)) return rc;
+    if (int rc = h->pool.alloc(&m.bias, N)) return rc;
+    EGR_CUDA_OK(cudaMemsetAsync(m.f32, 0, sizeof(float) * N * K, st));
+    EGR_CUDA_OK(cudaMemsetAsync(m.bias, 0, sizeof(float) * N, st));
+    return EGR_OK;
+}
+int p_copy_rows(egr_pose3d* h, const std::string& key, float* dst_w, float* dst_b, int N, int K, cudaStream_t st) {
+    int rc = EGR_OK;
+    const float* w = h->params.get(key + ".weight", (int64_t)N * K, &rc);
+    if (!w) return rc;
+    const float* b = h->params.get(key + ".bias", N, &rc);
+    if (!b) return rc;
+    EGR_CUDA_OK(cudaMemcpyAsync(dst_w, w, sizeof(float) * N * K, cudaMemcpyDeviceToDevice, st));
+    EGR_CUDA_OK(cudaMemcpyAsync(dst_b, b, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+    return EGR_OK;
+}
+
+int p_build_tokb_layer(egr_pose3d* h, int l, const LayerW& lw, cudaStream_t st) {
+    const int E = PE, V = h->V, KA = h->KA, HD = E / TOK_NH;
+    const std::string L = "layers." + std::to_string(l);
+    PoseTokB& t = h->tb[l];
+    int rc;
+    if ((rc = p_alloc_wmat(h, t.sa, TOK_OA, E, st)) || (rc = p_alloc_wmat(h, t.c, E, V * KA, st)) ||
+        (rc = p_alloc_wmat(h, t.qkv, 3 * E, E, st)) || (rc = p_alloc_wmat(h, t.o, E, E, st)) ||
+        (rc = p_alloc_wmat(h, t.f1, TOK_FF, E, st)) || (rc = p_alloc_wmat(h, t.f2, E, TOK_FF, st)) ||
+        (rc = p_alloc_wmat(h, t.r0, E, E, st)))
+        return rc;
+    if ((rc = p_copy_rows(h, L + ".cross_attn.sampling_offsets", t.sa.f32, t.sa.bias, TOK_NH * TOK_P * 2, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".cross_attn.attention_weights", t.sa.f32 + (int64_t)TOK_NH * TOK_P * 2 * E,
+                          t.sa.bias + TOK_NH * TOK_P * 2, TOK_NH * TOK_P, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".spatial_attn.q_proj", t.qkv.f32, t.qkv.bias, E, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".spatial_attn.k_proj", t.qkv.f32 + (int64_t)E * E, t.qkv.bias + E, E, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".spatial_attn.v_proj", t.qkv.f32 + (int64_t)2 * E * E, t.qkv.bias + 2 * E, E, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".spatial_attn.out_proj", t.o.f32, t.o.bias, E, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".ffn.layers.0.0", t.f1.f32, t.f1.bias, TOK_FF, E, st))) return rc;
+    if ((rc = p_copy_rows(h, L + ".ffn.layers.1", t.f2.f32, t.f2.bias, E, TOK_FF, st))) return rc;
+    if ((rc = p_copy_rows(h, "reg_mlp." + std::to_string(l) + ".0", t.r0.f32, t.r0.bias, E, E, st))) return rc;
+    const float *Wv, *Wf, *Wop, *bop, *Wfuse, *bfuse;
+    if ((rc = p_vec(h, L + ".cross_attn.value_proj.weight", E * E, &Wv))) return rc;
+    if ((rc = p_vec(h, "feat_proj.weight", E * PC, &Wf))) return rc;
+    if ((rc = p_vec(h, L + ".cross_attn.output_proj.weight", E * E, &Wop))) return rc;
+    if ((rc = p_vec(h, L + ".cross_attn.output_proj.bias", E, &bop))) return rc;
+    if ((rc = p_vec(h, L + ".fuse_mlp.weight", (int64_t)E * V * E, &Wfuse))) return rc;
+    if ((rc = p_vec(h, L + ".fuse_mlp.bias", E, &bfuse))) return rc;
+    float *mfold, *M1;
+    if ((rc = h->pool.alloc(&mfold, (int64_t)E * PC))) return rc;       // [E][128] = Wv · Wf
+    if ((rc = h->pool.alloc(&M1, (int64_t)V * E * E))) return rc;
+    if ((rc = small_matmul_ex(Wv, E, Wf, PC, nullptr, mfold, PC, E, PC, E, st))) return rc;
+    const int64_t ldc = (int64_t)V * KA;
+    for (int v = 0; v < V; ++v) {
+        float* M1v = M1 + (int64_t)v * E * E;
+        if ((rc = small_matmul_ex(Wfuse + (int64_t)v * E, (int64_t)V * E, Wop, E, nullptr, M1v, E, E, E, E, st))) return rc;
+        float* Wcv = t.c.f32 + (int64_t)v * KA;
+        for (int hh = 0; hh < TOK_NH; ++hh) {
+            if ((rc = small_matmul_ex(M1v + hh * HD, E, mfold + (int64_t)hh * HD * PC, PC, nullptr, Wcv + hh * TOK_RAWC, ldc, E,
+                                      TOK_RAWC, HD, st))) return rc;
+            // in-map bilinear weight mass of head hh times (Wv·bf + bv) restricted to the head's channels
+            if ((rc = small_matmul_ex(M1v + hh * HD, E, lw.bfold + hh * HD, 1, nullptr, Wcv + TOK_NH * TOK_RAWC + hh, ldc, E, 1, HD, st)))
+                return rc;
+        }
+        if ((rc = small_matmul_ex(Wfuse + (int64_t)v * E, (int64_t)V * E, bop, 1, nullptr, Wcv + TOK_NH * TOK_RAWC + TOK_NH, ldc, E, 1, E, st)))
+            return rc;
+    }
+    EGR_CUDA_OK(cudaMemcpyAsync(t.c.bias, bfuse, sizeof(float) * E, cudaMemcpyDeviceToDevice, st));
+    WMat* all[7] = {&t.sa, &t.c, &t.qkv, &t.o, &t.f1, &t.f2, &t.r0};
+    for (WMat* m : all)
+        if ((rc = round_tf32_inplace(m->f32, (int64_t)m->N * m->K, st))) return rc;
+    return EGR_OK;
+}
+
+int p_run_tokens_batched(egr_pose3d* h, int B, const PBufs& w, const void* Xs, int bfs, const float* ctm, float* preds,
+                         const PoseTokenW& tw, cudaStream_t st) {
+    const int J = h->J, V = h->V, E = PE, KA = h->KA, T = B * J;
+    int rc;
+    auto gemm = [&](const float* A, int K, const WMat& W, float* D, int epi, int rnd) {
+        GemmDesc d;
+        d.A = A; d.lda = K; d.M = T; d.D = D; d.ldd = W.N; d.epi = epi; d.round_tf32 = rnd;
+        return run_gemm(d, W, 0, PREC_TF32, true, st);
+    };
+    PoseQueryArgs qa{};
+    qa.B = B; qa.V = V; qa.J = J; qa.E = E; qa.is_rw = (h->cam_model & 1);
+    for (int v = 0; v < 4; ++v) { qa.cam_id[v] = h->cam_id[v]; qa.cam[v] = h->cam[v]; }
+    qa.ctm = ctm; qa.mlp_pred = preds; qa.g0_T = tw.g0_T; qa.g0_b = tw.g0_b;
+    qa.anchors = w.anch; qa.valid = w.valid; qa.p3 = w.tp3; qa.x0 = w.to;
+    if ((rc = pose_query0(qa, st))) return rc;
+    if ((rc = gemm(w.to, E, h->tk_g2, w.tz, EPI_RELU, 1))) return rc;
+    if ((rc = gemm(w.tz, E, h->tk_g4, w.tx, EPI_NONE, 1))) return rc;
+    for (int l = 0; l < h->L; ++l) {
+        const PoseTokB& t = h->tb[l];
+        const float* const* P = h->d_ptrs + l * 8;
+        if ((rc = gemm(w.tx, E, t.sa, w.toa, EPI_NONE, 0))) return rc;
+        TokSampleArgs sa{};
+        sa.G = 1; sa.B = B; sa.V = V; sa.J = J; sa.H = PH; sa.W = PW; sa.E = E; sa.KA = KA; sa.oa = w.toa; sa.anchors = w.anch;
+        sa.valid = w.valid; sa.X = Xs; sa.ptab = nullptr; sa.A = w.tA;
+        if ((rc = tok_sample(sa, bfs, st))) return rc;
+        if ((rc = gemm(w.tA, V * KA, t.c, w.tz, EPI_NONE, 0))) return rc;
+        if ((rc = tok_add_ln(w.tx, w.tz, w.tx, 1, T, E, P + 0, P + 1, st))) return rc;
+        if ((rc = gemm(w.tx, E, t.qkv, w.tqkv, EPI_NONE, 0))) return rc;
+        if ((rc = tok_attn(w.tqkv, w.to, B, J, E, st))) return rc;
+        if ((rc = gemm(w.to, E, t.o, w.tz, EPI_NONE, 0))) return rc;
+        if ((rc = tok_add_ln(w.tx, w.tz, w.tx, 1, T, E, P + 2, P + 3, st))) return rc;
+        if ((rc = gemm(w.tx, E, t.f1, w.thid, EPI_GELU, 1))) return rc;
+        if ((rc = gemm(w.thid, TOK_FF, t.f2, w.tz, EPI_NONE, 0))) return rc;
+        if ((rc = tok_add_ln(w.tx, w.tz, w.tx, 1, T, E, P + 4, P + 5, st))) return rc;
+        // post_norm[l] -> reg_mlp[l] -> + anchors (after the in-place quirk)
+        if ((rc = tok_add_ln(nullptr, w.tx, w.to, 1, T, E, P + 6, P + 7, st))) return rc;
+        if ((rc = gemm(w.to, E, t.r0, w.tz, EPI_GELU, 0))) return rc;
+        if ((rc = pose_reg_out(w.tz, tw.r2_T[l], tw.r2_b[l], w.tp3, preds + (int64_t)(l + 1) * T * 3, T, E, st))) return rc;
+    }
+    return EGR_OK;
 }
 
 }  // namespace
@@ -161,6 +301,8 @@ extern "C" int egr_pose3d_create(int num_views, int num_joints, int num_layers, 
     egr_pose3d* h = new egr_pose3d();
     h->V = num_views; h->J = num_joints; h->L = num_layers; h->cam_model = camera_model;
     h->use_init = use_pred_heatmap_init; h->prec = precision;
+    h->tokb = (precision == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    h->KA = tok_ka(PE, false);
     const int first = (camera_model >= 4) ? 2 : 0;   // stereo_back rigs start at back_left
     for (int v = 0; v < 4; ++v) {
         h->cam_id[v] = (v < num_views) ? first + v : 0;
@@ -222,6 +364,25 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
     }
     if ((rc = h->pool.alloc(&h->d_w, 1))) return rc;
     EGR_CUDA_OK(cudaMemcpyAsync(h->d_w, &tw, sizeof(PoseTokenW), cudaMemcpyHostToDevice, st));
+    h->tw_host = tw;
+    h->tokb = (h->prec == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    if (h->tokb) {
+        if ((rc = gemm_tc_init())) return rc;
+        if ((rc = p_alloc_wmat(h, h->tk_g2, PE, PE, st)) || (rc = p_alloc_wmat(h, h->tk_g4, PE, PE, st))) return rc;
+        if ((rc = p_copy_rows(h, "query_gen_mlp.2", h->tk_g2.f32, h->tk_g2.bias, PE, PE, st))) return rc;
+        if ((rc = p_copy_rows(h, "query_gen_mlp.4", h->tk_g4.f32, h->tk_g4.bias, PE, PE, st))) return rc;
+        if ((rc = round_tf32_inplace(h->tk_g2.f32, PE * PE, st)) || (rc = round_tf32_inplace(h->tk_g4.f32, PE * PE, st))) return rc;
+        std::vector<const float*> ptrs(4 * 8, nullptr);
+        for (int l = 0; l < h->L; ++l) {
+            if ((rc = p_build_tokb_layer(h, l, tw.layer[l], st))) return rc;
+            const LayerW& lw = tw.layer[l];
+            const float* arr[8] = {lw.lnc_w, lw.lnc_b, lw.lns_w, lw.lns_b, lw.lnf_w, lw.lnf_b, tw.pn_w[l], tw.pn_b[l]};
+            for (int i = 0; i < 8; ++i) ptrs[l * 8 + i] = arr[i];
+        }
+        if ((rc = h->pool.alloc(&h->d_ptrs, 4 * 8))) return rc;
+        EGR_CUDA_OK(cudaMemcpyAsync(h->d_ptrs, ptrs.data(), sizeof(const float*) * 4 * 8, cudaMemcpyHostToDevice, st));
+        EGR_CUDA_OK(cudaStreamSynchronize(st));
+    }
     EGR_CUDA_OK(cudaStreamSynchronize(st));
     h->packed = true;
     return EGR_OK;
@@ -304,7 +465,11 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     for (int v = 0; v < 4; ++v) { ta.cam_id[v] = h->cam_id[v]; ta.cam[v] = h->cam[v]; }
     ta.ctm = coord_trans_mat; ta.mlp_pred = preds; ta.preds = preds; ta.X = Xs; ta.w = h->d_w;
     ta.dbg_anchors = w.anch; ta.dbg_valid = w.valid;
-    if ((rc = launch_pose_tokens(ta, bfs, st))) return rc;
+    if (h->tokb) {
+        if ((rc = p_run_tokens_batched(h, B, w, Xs, bfs, coord_trans_mat, preds, h->tw_host, st))) return rc;
+    } else {
+        if ((rc = launch_pose_tokens(ta, bfs, st))) return rc;
+    }
     EGR_MARK(nullptr, st);
     const int64_t s = bf ? 2 : 4;
     h->dbg["p7"] = std::make_pair(w.p7, (int64_t)VB * 64 * 128 * s);

@@ -1,0 +1,404 @@
+// Batched token path: the small kernels between the token GEMMs (see token_batched.cuh).
+#include "token_batched.cuh"
+
+namespace egr {
+
+// =====================================================================================================
+// deformable sampling: one warp per (group, frame, joint, view, head)
+// =====================================================================================================
+template <typename T, bool HAS_PTAB, int E>
+__global__ void __launch_bounds__(256)
+tok_sample_kernel(TokSampleArgs a) {
+    constexpr int NH = TOK_NH, P = TOK_P, HD = E / NH, RAWC = TOK_RAWC;
+    constexpr int EX = HAS_PTAB ? E : NH;
+    const int lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t total = (int64_t)a.G * a.B * a.J * a.V * NH;
+    if (unit >= total) return;
+    int64_t r = unit;
+    const int h = (int)(r % NH); r /= NH;
+    const int v = (int)(r % a.V); r /= a.V;
+    const int j = (int)(r % a.J); r /= a.J;
+    const int b = (int)(r % a.B);
+    const int g = (int)(r / a.B);
+    const int64_t t = (int64_t)b * a.J + j, T_ = (int64_t)a.B * a.J;
+    float* Arow = a.A + (((int64_t)g * T_ + t) * a.V + v) * a.KA;
+    const bool ok = a.valid[((int64_t)b * a.V + v) * a.J + j] != 0;
+    if (h == 0) {     // validity column (carries output_proj's bias through the fold) + zero padding
+        if (lane == 0) Arow[NH * RAWC + EX] = ok ? 1.f : 0.f;
+        for (int c = NH * RAWC + EX + 1 + lane; c < a.KA; c += 32) Arow[c] = 0.f;
+    }
+    if (!ok) {        // masked_fill(~anchors_valid, 0) after output_proj (:910 / :563): the whole row is zero
+        *reinterpret_cast<float4*>(Arow + h * RAWC + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (HAS_PTAB) *reinterpret_cast<float2*>(Arow + NH * RAWC + h * HD + lane * 2) = make_float2(0.f, 0.f);
+        else if (lane == 0) Arow[NH * RAWC + h] = 0.f;
+        return;
+    }
+    const float* oa = a.oa + ((int64_t)g * T_ + t) * TOK_OA;
+    const int p = lane & (P - 1);
+    // softmax over the 16 points of this head (deform_attn.py:125-130)
+    const float logit = (lane < P) ? oa[NH * P * 2 + h * P + p] : -INFINITY;
+    const float m = warp_max(logit);
+    const float e = (lane < P) ? expf(logit - m) : 0.f;
+    const float inv = 1.f / warp_sum(e);
+    const float aw = e * inv;
+    // loc = anchor + offset / (W, H)   (deform_attn.py:133-139), corners as in mmcv's kernel
+    const float ax = a.anchors[(((int64_t)b * a.V + v) * a.J + j) * 2 + 0];
+    const float ay = a.anchors[(((int64_t)b * a.V + v) * a.J + j) * 2 + 1];
+    const float lx = ax + oa[h * P * 2 + p * 2 + 0] / (float)a.W;
+    const float ly = ay + oa[h * P * 2 + p * 2 + 1] / (float)a.H;
+    const Corners c = msda_corners(lx, ly, a.H, a.W);
+    float cw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cw[q] = aw * c.w[q];
+
+    const int64_t HW = (int64_t)a.H * a.W;
+    const T* Xb = reinterpret_cast<const T*>(a.X) + ((int64_t)v * a.B + b) * HW * RAWC + lane * 4;
+    const float* pt = HAS_PTAB ? (a.ptab[g] + (int64_t)v * HW * E + h * HD + lane * 2) : nullptr;
+    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float2 e2 = make_float2(0.f, 0.f);
+    float wsum = 0.f;
+#pragma unroll 4
+    for (int pp = 0; pp < P; ++pp) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float coef = __shfl_sync(0xffffffffu, cw[q], pp);
+            const int idx = __shfl_sync(0xffffffffu, c.idx[q], pp);
+            if (coef == 0.f) continue;                       // out-of-map corner / point: contributes exactly 0
+            const float4 x = ldg4<T>(Xb + (int64_t)idx * RAWC);
+            s4.x = fmaf(coef, x.x, s4.x); s4.y = fmaf(coef, x.y, s4.y);
+            s4.z = fmaf(coef, x.z, s4.z); s4.w = fmaf(coef, x.w, s4.w);
+            if (HAS_PTAB) {
+                const float2 pv = __ldg(reinterpret_cast<const float2*>(pt + (int64_t)idx * E));
+                e2.x = fmaf(coef, pv.x, e2.x); e2.y = fmaf(coef, pv.y, e2.y);
+            } else {
+                wsum += coef;
+            }
+        }
+    }
+    *reinterpret_cast<float4*>(Arow + h * RAWC + lane * 4) =
+        make_float4(round_tf32(s4.x), round_tf32(s4.y), round_tf32(s4.z), round_tf32(s4.w));
+    if (HAS_PTAB) *reinterpret_cast<float2*>(Arow + NH * RAWC + h * HD + lane * 2) = make_float2(round_tf32(e2.x), round_tf32(e2.y));
+    else if (lane == 0) Arow[NH * RAWC + h] = round_tf32(wsum);
+}
+
+int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st) {
+    const bool ptab = a.ptab != nullptr;
+    EGR_CHECK((a.E == 256 && ptab) || (a.E == 128 && !ptab), EGR_ERR_UNSUPPORTED, "tok_sample: E=%d ptab=%d", a.E, (int)ptab);
+    EGR_CHECK(a.KA == tok_ka(a.E, ptab), EGR_ERR_INVALID, "tok_sample: KA=%d", a.KA);
+    const int64_t total = (int64_t)a.G * a.B * a.J * a.V * TOK_NH;
+    const int blocks = (int)ceil_div64(total, 8);
+    if (ptab) {
+        if (act_bf16) tok_sample_kernel<__nv_bfloat16, true, 256><<<blocks, 256, 0, st>>>(a);
+        else tok_sample_kernel<float, true, 256><<<blocks, 256, 0, st>>>(a);
+    } else {
+        if (act_bf16) tok_sample_kernel<__nv_bfloat16, false, 128><<<blocks, 256, 0, st>>>(a);
+        else tok_sample_kernel<float, false, 128><<<blocks, 256, 0, st>>>(a);
+    }
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+// =====================================================================================================
+// joint self-attention: one CTA per frame, one warp per head
+// =====================================================================================================
+template <int E>
+__global__ void __launch_bounds__(128)
+tok_attn_kernel(const float* __restrict__ qkv, float* __restrict__ o, int J) {
+    constexpr int NH = TOK_NH, HD = E / NH, LD = HD + 1, MJ = 16;
+    extern __shared__ float sm[];
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* q = sm + h * (3 * MJ * LD + MJ * MJ);
+    float* k = q + MJ * LD;
+    float* v = k + MJ * LD;
+    float* pr = v + MJ * LD;      // [MJ][MJ]
+    const int64_t t0 = (int64_t)blockIdx.x * J;
+    for (int i = lane; i < J * HD; i += 32) {
+        const int j = i / HD, d = i - j * HD;
+        const float* row = qkv + (t0 + j) * 3 * E + h * HD + d;
+        q[j * LD + d] = row[0];
+        k[j * LD + d] = row[E];
+        v[j * LD + d] = row[2 * E];
+    }
+    __syncwarp();
+    const float scale = (float)(1.0 / sqrt((double)HD));      // head_dims ** -0.5 (transformer.py:66)
+    const int jq = lane & 15, kh = lane >> 4;
+    float sc[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int jk = kh * 8 + i;
+        float dot = 0.f;
+        if (jq < J && jk < J) {
+#pragma unroll 8
+            for (int d = 0; d < HD; ++d) dot = fmaf(q[jq * LD + d], k[jk * LD + d], dot);
+            sc[i] = dot * scale;
+            mx = fmaxf(mx, sc[i]);
+        } else {
+            sc[i] = -INFINITY;
+        }
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = (sc[i] == -INFINITY) ? 0.f : expf(sc[i] - mx); s += sc[i]; }
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    const float inv = 1.f / s;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pr[jq * MJ + kh * 8 + i] = sc[i] * inv;
+    __syncwarp();
+    for (int j = 0; j < J; ++j) {
+#pragma unroll
+        for (int d = lane; d < HD; d += 32) {
+            float acc = 0.f;
+            for (int jk = 0; jk < J; ++jk) acc = fmaf(pr[j * MJ + jk], v[jk * LD + d], acc);
+            o[(t0 + j) * E + h * HD + d] = round_tf32(acc);
+        }
+    }
+}
+
+int tok_attn(const float* qkv, float* o, int n_frames, int J, int E, cudaStream_t st) {
+    EGR_CHECK(J <= 16 && (E == 128 || E == 256), EGR_ERR_UNSUPPORTED, "tok_attn: J=%d E=%d", J, E);
+    const int HD = E / TOK_NH;
+    const size_t smem = sizeof(float) * TOK_NH * (3 * 16 * (HD + 1) + 16 * 16);
+    if (E == 256) {
+        auto kfn = tok_attn_kernel<256>;
+        EGR_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kfn<<<n_frames, 128, smem, st>>>(qkv, o, J);
+    } else {
+        auto kfn = tok_attn_kernel<128>;
+        EGR_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kfn<<<n_frames, 128, smem, st>>>(qkv, o, J);
+    }
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+// =====================================================================================================
+// residual + LayerNorm (eps 1e-5, biased variance), one warp per token row
+// =====================================================================================================
+template <int E>
+__device__ __forceinline__ void ln_row(const float* v_in, float (&v)[E / 32], float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < E / 32; ++i) s += v[i];
+    mean = warp_sum(s) * (1.f / E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < E / 32; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    rstd = rsqrtf(warp_sum(q) * (1.f / E) + 1e-5f);
+}
+
+template <int E>
+__global__ void __launch_bounds__(256)
+tok_add_ln_kernel(const float* __restrict__ res, const float* __restrict__ z, float* __restrict__ out, int64_t rows,
+                  int rows_per_group, const float* const* __restrict__ gamma, const float* const* __restrict__ beta) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int g = (int)(row / rows_per_group);
+    const float* ga = gamma[g];
+    const float* be = beta[g];
+    float v[E / 32];
+#pragma unroll
+    for (int i = 0; i < E / 32; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = z[row * E + c] + (res ? res[row * E + c] : 0.f);
+    }
+    float mean, rstd;
+    ln_row<E>(nullptr, v, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < E / 32; ++i) {
+        const int c = lane + 32 * i;
+        out[row * E + c] = round_tf32((v[i] - mean) * rstd * __ldg(ga + c) + __ldg(be + c));
+    }
+}
+
+int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per_group, int E, const float* const* gamma,
+               const float* const* beta, cudaStream_t st) {
+    const int64_t rows = (int64_t)G * rows_per_group;
+    const int blocks = (int)ceil_div64(rows, 8);
+    if (E == 256) tok_add_ln_kernel<256><<<blocks, 256, 0, st>>>(res, z, out, rows, rows_per_group, gamma, beta);
+    else if (E == 128) tok_add_ln_kernel<128><<<blocks, 256, 0, st>>>(res, z, out, rows, rows_per_group, gamma, beta);
+    else return fail(EGR_ERR_UNSUPPORTED, "tok_add_ln: E=%d", E);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+// post_norm + [J][16x16] token image written transposed: xT[pos][j], j padded to 16 (egoposeformer_heatmap_mvf_ex.py:707-711)
+template <typename T>
+__global__ void __launch_bounds__(256)
+tok_ln_image_kernel(const float* __restrict__ x, T* __restrict__ xT, int B, int J, const float* const* __restrict__ gamma,
+                    const float* const* __restrict__ beta) {
+    constexpr int E = 256;
+    __shared__ float ys[16 * E];
+    const int g = blockIdx.x / B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* xin = x + (int64_t)blockIdx.x * J * E;
+    const float* ga = gamma[g];
+    const float* be = beta[g];
+    for (int j = warp; j < J; j += 8) {
+        float v[E / 32];
+#pragma unroll
+        for (int i = 0; i < E / 32; ++i) v[i] = xin[j * E + lane + 32 * i];
+        float mean, rstd;
+        ln_row<E>(nullptr, v, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < E / 32; ++i) {
+            const int c = lane + 32 * i;
+            ys[j * E + c] = (v[i] - mean) * rstd * __ldg(ga + c) + __ldg(be + c);
+        }
+    }
+    __syncthreads();
+    T* out = xT + (int64_t)blockIdx.x * E * 16;
+    for (int i = threadIdx.x; i < E * 16; i += 256) {
+        const int pos = i >> 4, j = i & 15;
+        ActT<T>::st(out + i, (j < J) ? ys[j * E + pos] : 0.f);
+    }
+}
+
+int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int E, const float* const* gamma,
+                 const float* const* beta, cudaStream_t st) {
+    EGR_CHECK(E == 256 && J <= 16, EGR_ERR_UNSUPPORTED, "tok_ln_image: E=%d J=%d", E, J);
+    if (xT_bf16) tok_ln_image_kernel<__nv_bfloat16><<<G * B, 256, 0, st>>>(x, (__nv_bfloat16*)xT, B, J, gamma, beta);
+    else tok_ln_image_kernel<float><<<G * B, 256, 0, st>>>(x, (float*)xT, B, J, gamma, beta);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+// =====================================================================================================
+// mvfex jqa query input (HeatmapMVF.forward :655-665): x0 = embed_j + fc_bfb(avgpool(bfb)) + heatmap_proj(heatmap_j)
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+tok_jqa_query_kernel(TokQueryArgs a) {
+    constexpr int E = 256;
+    __shared__ float pool[512];
+    const int g = blockIdx.x / a.B, b = blockIdx.x - g * a.B;
+    const int n = threadIdx.x;
+    const float* bf = a.bfb + (int64_t)g * a.bfb_gs + (int64_t)b * a.bfb_bs;
+    // adaptive_avg_pool2d(bfb, 1): a warp per channel, lanes over the hw positions
+    const int lane = n & 31, warp = n >> 5;
+    for (int c = warp; c < 512; c += 8) {
+        float s = 0.f;
+        for (int i = lane; i < a.hw; i += 32) s += bf[(int64_t)c * a.hw + i];
+        s = warp_sum(s);
+        if (lane == 0) pool[c] = s / (float)a.hw;
+    }
+    __syncthreads();
+    const float* wT = a.bfb_T[g];
+    float gv = __ldg(a.bfb_b[g] + n);
+    for (int k = 0; k < 512; ++k) gv = fmaf(__ldg(wT + (int64_t)k * E + n), pool[k], gv);
+    const float* jq = a.jq[g];
+    const int64_t base = ((int64_t)g * a.B + b) * a.J * E;
+    for (int j = 0; j < a.J; ++j)
+        a.x0[base + j * E + n] = round_tf32(__ldg(jq + j * E + n) + gv + a.y0[base + j * E + n]);
+}
+
+int tok_jqa_query(const TokQueryArgs& a, cudaStream_t st) {
+    EGR_CHECK(a.E == 256, EGR_ERR_UNSUPPORTED, "tok_jqa_query: E=%d", a.E);
+    tok_jqa_query_kernel<<<a.G * a.B, 256, 0, st>>>(a);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+// =====================================================================================================
+// pose3d: reprojection (P3) + query_gen_mlp.0 + ReLU           egoposeformer_mvf_ex.py:340-382, :400-406
+// =====================================================================================================
+__global__ void __launch_bounds__(128)
+pose_query0_kernel(PoseQueryArgs a) {
+    constexpr int E = 128, MJ = 16;
+    __shared__ float s_p3[MJ * 4];
+    const int b = blockIdx.x, tid = threadIdx.x, J = a.J;
+    if (tid < J) {
+        const int j = tid;
+        float px = a.mlp_pred[((int64_t)b * J + j) * 3 + 0];
+        float py = a.mlp_pred[((int64_t)b * J + j) * 3 + 1];
+        float pz = a.mlp_pred[((int64_t)b * J + j) * 3 + 2];
+        for (int v = 0; v < a.V; ++v) {
+            float cx_, cy_, cz_;
+            if (a.is_rw) {
+                const float* M = a.ctm + ((int64_t)b * a.V + v) * 16;
+                const float hx = px * 0.01f, hy = py * 0.01f, hz = pz * 0.01f;
+                cx_ = (M[0] * hx + M[1] * hy + M[2] * hz + M[3]) * 100.f;
+                cy_ = (M[4] * hx + M[5] * hy + M[6] * hz + M[7]) * 100.f;
+                cz_ = (M[8] * hx + M[9] * hy + M[10] * hz + M[11]) * 100.f;
+            } else {
+                float ox, oy;
+                bool flip;
+                syn_offset(a.cam_id[v], ox, oy, flip);
+                if (flip) { px = -px; py = -py; }
+                px = __fadd_rn(px, ox);
+                py = __fadd_rn(py, oy);
+                cx_ = px; cy_ = py; cz_ = pz;
+            }
+            float u, vv;
+            bool fov;
+            fisheye_project(cx_, cy_, cz_, a.cam[v], u, vv, fov);
+            a.anchors[(((int64_t)b * a.V + v) * J + j) * 2 + 0] = u;
+            a.anchors[(((int64_t)b * a.V + v) * J + j) * 2 + 1] = vv;
+            a.valid[((int64_t)b * a.V + v) * J + j] = fov ? 1 : 0;
+        }
+        s_p3[j * 4 + 0] = (float)(j + 1) / (float)J;
+        s_p3[j * 4 + 1] = px; s_p3[j * 4 + 2] = py; s_p3[j * 4 + 3] = pz;
+        float* o = a.p3 + ((int64_t)b * J + j) * 4;
+        o[0] = s_p3[j * 4 + 0]; o[1] = px; o[2] = py; o[3] = pz;
+    }
+    __syncthreads();
+    const int n = tid;
+    const float w0 = __ldg(a.g0_T + 0 * E + n), w1 = __ldg(a.g0_T + 1 * E + n);
+    const float w2 = __ldg(a.g0_T + 2 * E + n), w3 = __ldg(a.g0_T + 3 * E + n);
+    const float b0 = __ldg(a.g0_b + n);
+    for (int j = 0; j < J; ++j) {
+        float acc = 0.f;
+        acc = fmaf(w0, s_p3[j * 4 + 0], acc);
+        acc = fmaf(w1, s_p3[j * 4 + 1], acc);
+        acc = fmaf(w2, s_p3[j * 4 + 2], acc);
+        acc = fmaf(w3, s_p3[j * 4 + 3], acc);
+        a.x0[((int64_t)b * J + j) * E + n] = round_tf32(fmaxf(acc + b0, 0.f));
+    }
+}
+
+int pose_query0(const PoseQueryArgs& a, cudaStream_t st) {
+    EGR_CHECK(a.E == 128 && a.J <= 16 && a.V <= 4, EGR_ERR_UNSUPPORTED, "pose_query0: E=%d J=%d V=%d", a.E, a.J, a.V);
+    pose_query0_kernel<<<a.B, 128, 0, st>>>(a);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+__global__ void pose_reg_out_kernel(const float* __restrict__ r, const float* __restrict__ w2_T, const float* __restrict__ b2,
+                                    const float* __restrict__ p3, float* __restrict__ preds, int T, int E) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * 3) return;
+    const int t = i / 3, c = i - t * 3;
+    float acc = __ldg(b2 + c);
+    for (int k = 0; k < E; ++k) acc = fmaf(__ldg(w2_T + k * 3 + c), r[(int64_t)t * E + k], acc);
+    preds[i] = acc + p3[(int64_t)t * 4 + 1 + c];
+}
+
+int pose_reg_out(const float* r, const float* w2_T, const float* b2, const float* p3, float* preds, int T, int E, cudaStream_t st) {
+    pose_reg_out_kernel<<<ceil_div(T * 3, 128), 128, 0, st>>>(r, w2_T, b2, p3, preds, T, E);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+// =====================================================================================================
+__global__ void small_matmul_ex_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                                       const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / N;
+        const int n = (int)(i - m * N);
+        float acc = bias ? bias[n] : 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(A[m * lda + k], B[(int64_t)k * ldb + n], acc);
+        C[m * ldc + n] = acc;
+    }
+}
+int small_matmul_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                    int M, int N, int K, cudaStream_t st) {
+    const int64_t g = ceil_div64((int64_t)M * N, 256);
+    small_matmul_ex_kernel<<<(int)(g < 148 * 64 ? g : 148 * 64), 256, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+}  // namespace egr
