@@ -41,8 +41,12 @@ struct egr_mvfex {
     float *h2_7w = nullptr, *h2_7b = nullptr;  // [V][J][128], [V][J]
     MvfTokenW* d_tokw = nullptr;               // device [V]
     // batched token path (bf16 precision): token GEMM weights (fp32 rounded to TF32, sets = V) + per-refiner pointer tables
+    bool export_staged = false;                // keep channels-last copies for a chained pose3d forward
+    const void *st_init = nullptr, *st_refined = nullptr;
+    const float* st_refined_tf32 = nullptr;
     bool tokb = false;
-    WMat tk_hp2, tk_fcq, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
+    WMat tk_hp2, tk_fcq, tk_bfb, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
+    const __nv_bfloat16** d_ptab16 = nullptr;  // device [4]: bf16 copies of the sampled position tables
     const float** d_ptrs = nullptr;            // device [TP_COUNT][4]
     int KA = 0;
     bool has_heads = false, has_ref[4] = {false, false, false, false};   // parameter groups present at prepack
@@ -158,7 +162,8 @@ struct Bufs {
     void *Xh, *Xown, *h1a, *a1, *b1, *c1, *z, *ff, *r1a, *refn, *hmT, *xT, *h1t, *t1;
     float *q1, *anch, *maxv;
     uint8_t* valid;
-    float *tx, *tz, *toa, *tA, *tqkv, *to, *thid;     // batched token path
+    float *tx, *tz, *toa, *tA, *tqkv, *to, *thid, *tpool, *tvb;     // batched token path
+    float* refn32;                                                  // exported TF32 channels-last refined features
 };
 
 enum TokPtr { TP_LNC_W, TP_LNC_B, TP_LNS_W, TP_LNS_B, TP_LNF_W, TP_LNF_B, TP_PN_W, TP_PN_B, TP_PTAB, TP_BFB_T, TP_BFB_B, TP_JQ,
@@ -189,6 +194,7 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.anch = (float*)c.take((int64_t)B * V * J * 2 * 4);
     b.maxv = (float*)c.take((int64_t)B * V * J * 4);
     b.valid = (uint8_t*)c.take((int64_t)B * V * J);
+    b.refn32 = (h->export_staged && G == V) ? (float*)c.take((int64_t)G * B * FHW * FC * 4) : nullptr;
     if (h->tokb) {
         const int64_t T = (int64_t)B * J;
         b.tx = (float*)c.take(G * T * EMB * 4);
@@ -198,6 +204,8 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
         b.tqkv = (float*)c.take(G * T * 3 * EMB * 4);
         b.to = (float*)c.take(G * T * EMB * 4);
         b.thid = (float*)c.take(G * T * TOK_FF * 4);
+        b.tpool = (float*)c.take((int64_t)G * B * 512 * 4);
+        b.tvb = (float*)c.take((int64_t)G * B * EMB * 4);
     }
     if (o) *o = b;
     return c.off + 256;
@@ -230,6 +238,7 @@ int build_tokb(egr_mvfex* h, int r, const std::string& refiner, cudaStream_t st)
     int rc;
     if ((rc = copy_rows(h, refiner + ".heatmap_proj.2", h->tk_hp2.f32 + (int64_t)r * E * E, h->tk_hp2.bias + r * E, E, E, st))) return rc;
     if ((rc = copy_rows(h, refiner + ".fc_query.0", h->tk_fcq.f32 + (int64_t)r * E * E, h->tk_fcq.bias + r * E, E, E, st))) return rc;
+    if ((rc = copy_rows(h, refiner + ".fc_bfb", h->tk_bfb.f32 + (int64_t)r * E * 512, h->tk_bfb.bias + r * E, E, 512, st))) return rc;
     float* sa = h->tk_sa.f32 + (int64_t)r * TOK_OA * E;
     float* sab = h->tk_sa.bias + r * TOK_OA;
     if ((rc = copy_rows(h, L + ".cross_attn.sampling_offsets", sa, sab, TOK_NH * TOK_P * 2, E, st))) return rc;
@@ -291,16 +300,19 @@ int run_tokens_batched(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const 
     };
     // heatmap_proj.2, + fc_bfb(avgpool) + joint embed, fc_query + ReLU
     if ((rc = gemm(w.q1, E, h->tk_hp2, w.tz, EPI_NONE, 0))) return rc;
-    TokQueryArgs qa{};
-    qa.G = G; qa.B = B; qa.J = J; qa.E = E; qa.hw = 64; qa.y0 = w.tz; qa.bfb = bfb; qa.bfb_bs = bfb_bs; qa.bfb_gs = bfb_gs;
-    qa.bfb_T = ptr(TP_BFB_T); qa.bfb_b = ptr(TP_BFB_B); qa.jq = ptr(TP_JQ); qa.x0 = w.to;
-    if ((rc = tok_jqa_query(qa, st))) return rc;
+    if ((rc = tok_avgpool(bfb, bfb_bs, bfb_gs, 64, w.tpool, G, B, 512, st))) return rc;
+    {
+        GemmDesc d;
+        d.A = w.tpool; d.lda = 512; d.M = B; d.D = w.tvb; d.ldd = E; d.groups = G; d.a_gs = (int64_t)B * 512; d.d_gs = (int64_t)B * E;
+        if ((rc = run_gemm(d, h->tk_bfb, r0, PREC_TF32, true, st))) return rc;
+    }
+    if ((rc = tok_add_query(w.tz, w.tvb, ptr(TP_JQ), w.to, G, B, J, E, st))) return rc;
     if ((rc = gemm(w.to, E, h->tk_fcq, w.tx, EPI_RELU, 1))) return rc;
     // A1: offsets + logits, sampling, folded value/output/fuse GEMM, residual + LN
     if ((rc = gemm(w.tx, E, h->tk_sa, w.toa, EPI_NONE, 0))) return rc;
     TokSampleArgs sa{};
     sa.G = G; sa.B = B; sa.V = V; sa.J = J; sa.H = FH; sa.W = FW; sa.E = E; sa.KA = KA; sa.oa = w.toa; sa.anchors = anchors;
-    sa.valid = valid; sa.X = w.Xh; sa.ptab = ptr(TP_PTAB); sa.A = w.tA;
+    sa.valid = valid; sa.X = w.Xh; sa.ptab = h->d_ptab16 + r0; sa.A = w.tA;
     if ((rc = tok_sample(sa, bf, st))) return rc;
     if ((rc = gemm(w.tA, V * KA, h->tk_c, w.tz, EPI_NONE, 0))) return rc;
     if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNC_W), ptr(TP_LNC_B), st))) return rc;
@@ -387,7 +399,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st))) return rc;
     EGR_MARK("R1tail", st);
     // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output + channels-last copy for H2
-    if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, st))) return rc;
+    if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, w.refn32, st))) return rc;
     EGR_MARK("H2a", st);
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
@@ -542,6 +554,7 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
     if (h->tokb) {
         const int E = EMB;
         if ((rc = alloc_wmat(h, h->tk_hp2, V, E, E, st)) || (rc = alloc_wmat(h, h->tk_fcq, V, E, E, st)) ||
+            (rc = alloc_wmat(h, h->tk_bfb, V, E, 512, st)) ||
             (rc = alloc_wmat(h, h->tk_sa, V, TOK_OA, E, st)) || (rc = alloc_wmat(h, h->tk_c, V, E, V * h->KA, st)) ||
             (rc = alloc_wmat(h, h->tk_qkv, V, 3 * E, E, st)) || (rc = alloc_wmat(h, h->tk_o, V, E, E, st)) ||
             (rc = alloc_wmat(h, h->tk_f1, V, TOK_FF, E, st)) || (rc = alloc_wmat(h, h->tk_f2, V, E, TOK_FF, st)))
@@ -558,7 +571,18 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
             ptrs[TP_PTAB * 4 + r] = t.layer.ptab;
             ptrs[TP_BFB_T * 4 + r] = t.bfb_T; ptrs[TP_BFB_B * 4 + r] = t.bfb_b; ptrs[TP_JQ * 4 + r] = t.jq;
         }
-        WMat* all[8] = {&h->tk_hp2, &h->tk_fcq, &h->tk_sa, &h->tk_c, &h->tk_qkv, &h->tk_o, &h->tk_f1, &h->tk_f2};
+        std::vector<const __nv_bfloat16*> pt16(4, nullptr);
+        for (int r = 0; r < V; ++r) {
+            if (!h->has_ref[r]) continue;
+            __nv_bfloat16* t16 = nullptr;
+            if ((rc = h->pool.alloc(&t16, (int64_t)V * FHW * E))) return rc;
+            if ((rc = cast_bf16(tok[r].layer.ptab, t16, (int64_t)V * FHW * E, st))) return rc;
+            pt16[r] = t16;
+        }
+        if ((rc = h->pool.alloc(&h->d_ptab16, 4))) return rc;
+        EGR_CUDA_OK(cudaMemcpyAsync(h->d_ptab16, pt16.data(), sizeof(void*) * 4, cudaMemcpyHostToDevice, st));
+        EGR_CUDA_OK(cudaStreamSynchronize(st));
+        WMat* all[9] = {&h->tk_hp2, &h->tk_fcq, &h->tk_bfb, &h->tk_sa, &h->tk_c, &h->tk_qkv, &h->tk_o, &h->tk_f1, &h->tk_f2};
         for (WMat* m : all)
             if ((rc = round_tf32_inplace(m->f32, (int64_t)m->sets * m->N * m->K, st))) return rc;
         if ((rc = h->pool.alloc(&h->d_ptrs, TP_COUNT * 4))) return rc;
@@ -633,6 +657,23 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
                       (int64_t)V * J * FHW, (int64_t)J * FHW, feat_refined, (int64_t)V * FC * FHW, (int64_t)FC * FHW, st);
     if (rc) return rc;
     note_all(h, w, B, V);
+    h->st_init = w.Xh; h->st_refined = w.refn; h->st_refined_tf32 = w.refn32;
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_export_staged(egr_mvfex* h, int enable) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_export_staged: null handle");
+    h->export_staged = enable != 0;
+    h->st_init = h->st_refined = nullptr; h->st_refined_tf32 = nullptr;
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const float** refined_nhwc_tf32,
+                                int* act_is_bf16) {
+    EGR_CHECK(h && init_nhwc && refined_nhwc && refined_nhwc_tf32 && act_is_bf16, EGR_ERR_INVALID, "mvfex_staged: null argument");
+    EGR_CHECK(h->st_init, EGR_ERR_STATE, "mvfex_staged: no forward has run since export was enabled");
+    *init_nhwc = h->st_init; *refined_nhwc = h->st_refined; *refined_nhwc_tf32 = h->st_refined_tf32;
+    *act_is_bf16 = (h->prec == EGR_PREC_BF16);
     return EGR_OK;
 }
 

@@ -34,6 +34,10 @@ struct egr_pose3d {
     WMat c0, c2, c5, c7;          // conv_frame_feat.{0,2,5,7}
     WMat m0, m1, m2;              // mlp_pred.0.0 (permuted), mlp_pred.1.0, mlp_pred.2
     PoseTokenW* d_w = nullptr;
+    // one-shot staged inputs for the next forward (egr_pose3d_use_staged)
+    const void* st_sampled = nullptr;
+    int st_sampled_bf16 = 0;
+    const float* st_final_tf32 = nullptr;
     // batched token path (bf16 precision)
     bool tokb = false;
     int KA = 0;
@@ -343,7 +347,7 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
     if ((rc = p_make_wmat(h, h->c7, 128, 9 * 64, 1, "conv_frame_feat.7", st))) return rc;
     const int K0 = h->V * PC * 64;
     if ((rc = p_make_wmat(h, h->m0, K0 / 16, K0, 2, "mlp_pred.0.0", st))) return rc;
-    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st, false))) return rc;
+    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st, true))) return rc;
     if ((rc = p_make_wmat(h, h->m2, 3 * h->J, K0 / 256, 0, "mlp_pred.2", st, false))) return rc;
     PoseTokenW tw{};
     if ((rc = p_make_T(h, "query_gen_mlp.0", PE, 4, &tw.g0_T, st))) return rc;
@@ -416,16 +420,24 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
     const float* sampled = h->use_init ? feats_init : feats_final;
     const int rnd = (prec == PREC_TF32);      // every operand of a tf32 stage is pre-rounded to the nearest TF32 value
-    if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
-    const void* Xs = w.Xf;
-    if (sampled != feats_final || bfs != bf || rnd) {
+    // staged copies left by a chained mvfex forward replace the staging passes (one-shot)
+    const void* st_s = h->st_sampled;
+    const float* st_f = h->st_final_tf32;
+    const int st_s_bf16 = h->st_sampled_bf16;
+    h->st_sampled = nullptr; h->st_final_tf32 = nullptr;
+    const void* Xf = w.Xf;
+    if (st_f && rnd) Xf = st_f;
+    else if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
+    const void* Xs = Xf;
+    if (st_s && st_s_bf16 == bfs) Xs = st_s;
+    else if (sampled != feats_final || bfs != bf || rnd) {
         if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
         Xs = w.Xi;
     }
     EGR_MARK("P2a", st);
     // P2 conv_frame_feat
     GemmDesc d;
-    d.A = w.Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
+    d.A = Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
     EGR_MARK("P2b", st);
     d = GemmDesc();
@@ -445,14 +457,18 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     // mlp_pred: K-split over the V view blocks of p7 ([V][B][64*128])
     d = GemmDesc();
     d.A = w.p7; d.lda = 64 * 128; d.kblk = 64 * 128; d.kblk_stride = (int64_t)B * 64 * 128; d.M = B; d.D = w.m0; d.ldd = h->m0.N;
-    d.epi = EPI_GELU;
+    d.epi = EPI_GELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->m0, 0, prec, /*out_f32=*/true, st))) return rc;
     EGR_MARK("P2mlp12", st);
-    {   // the two small Linears stay fp32 SIMT in every precision
+    {   // Linear(2048 -> 128) GELU on the tensor cores in the tf32 branch; the last Linear(128 -> 48) stays fp32 SIMT
         GemmDesc t;
-        t.A = w.m0; t.lda = h->m1.K; t.M = B; t.N = h->m1.N; t.K = h->m1.K; t.W = h->m1.f32; t.bias = h->m1.bias;
-        t.D = w.m1; t.ldd = h->m1.N; t.epi = EPI_GELU;
-        if ((rc = gemm_simt(t, 0, 0, st))) return rc;
+        t.A = w.m0; t.lda = h->m1.K; t.M = B; t.D = w.m1; t.ldd = h->m1.N; t.epi = EPI_GELU;
+        if (rnd) {
+            if ((rc = run_gemm(t, h->m1, 0, PREC_TF32, true, st))) return rc;
+        } else {
+            t.N = h->m1.N; t.K = h->m1.K; t.W = h->m1.f32; t.bias = h->m1.bias;
+            if ((rc = gemm_simt(t, 0, 0, st))) return rc;
+        }
         t = GemmDesc();
         t.A = w.m1; t.lda = h->m2.K; t.M = B; t.N = h->m2.N; t.K = h->m2.K; t.W = h->m2.f32; t.bias = h->m2.bias;
         t.D = preds; t.ldd = h->m2.N; t.epi = EPI_NONE;     // preds[0] = proposal
@@ -477,6 +493,12 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     h->dbg["m0"] = std::make_pair((void*)w.m0, (int64_t)B * 2048 * 4);
     h->dbg["anchors"] = std::make_pair((void*)w.anch, (int64_t)VB * J * 8);
     h->dbg["valid"] = std::make_pair((void*)w.valid, (int64_t)VB * J);
+    return EGR_OK;
+}
+
+extern "C" int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_use_staged: null handle");
+    h->st_sampled = sampled_nhwc; h->st_sampled_bf16 = sampled_is_bf16 ? 1 : 0; h->st_final_tf32 = final_nhwc_tf32;
     return EGR_OK;
 }
 

@@ -9,7 +9,8 @@
 //   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block,
 //               tcgen05.commit releases the smem slot / publishes the accumulator
 //   warps 2-9   epilogue: tcgen05.ld the 128xBN fp32 accumulator (two TMEM buffers, so the epilogue of tile i
-//               overlaps the MMAs of tile i+1), bias + activation (+ fused bilinear-x2 residual), 16-byte stores
+//               overlaps the MMAs of tile i+1), bias + activation (+ fused bilinear-x2 residual); rows are staged in
+//               a swizzled smem tile so that every global store instruction writes whole 128 B row segments
 // The 3x3 stride-2 pad-1 conv is an implicit GEMM: the NHWC input is described to TMA as a 5-D tensor
 // (2*Cin, W/2, 2, H/2, img) so that tap (ky,kx) of 128 consecutive output pixels is ONE box load whose
 // out-of-bounds part (the zero padding) is filled by the TMA unit.
@@ -32,7 +33,7 @@ template <int BN> struct TcCfg {
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int STAGES = SMEM_RING / STAGE;          // 256: 4, 128: 6, 64: 8
     static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 4096 /*store staging*/;
 };
 
 struct TcParams {
@@ -290,6 +291,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q = warp & 3;            // TMEM lane quarter this warp may read
         const int half = e >> 2;           // column half
         const int row = q * 32 + lane;
+        constexpr int PIECES = 32 * (int)sizeof(TO) / 16;                  // 16 B pieces per 32-column chunk (4 bf16, 8 fp32)
+        constexpr int NCH = BN / 64;                                       // chunks per warp
+        constexpr int GRP = (8 / PIECES < NCH) ? 8 / PIECES : NCH;         // chunks staged per flush
+        constexpr int PR = PIECES * GRP;                                   // pieces per staged row (4 or 8)
+        uint8_t* stage = smem + C::STAGES * C::STAGE + 256 + e * 4096;     // [32 rows][128 B], private to this warp
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(t, p);
@@ -316,58 +322,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
+            // Each thread owns one accumulator row; a row-per-thread store would touch 32 different lines per instruction.
+            // Stage 128 B per row in a per-warp XOR-swizzled smem tile, then store whole rows: 8 lanes x 16 B per row.
+            TO* Dg = reinterpret_cast<TO*>(p.D) + (int64_t)tc.g * p.d_gs;
+            if (p.partial) Dg = reinterpret_cast<TO*>(reinterpret_cast<float*>(p.D) + (int64_t)tc.ks * p.part_stride);
+            const int m_w0 = tc.mt * BM + q * 32;           // first row of this warp
 #pragma unroll 1
             for (int c0 = 0; c0 < BN / 2; c0 += 32) {
                 uint32_t v[32];
                 __syncwarp();
                 tc_ld32(taddr + c0, v);
-                if (!row_ok) continue;
                 const int n0 = n_base + c0;
-                if (p.partial) {
-                    float* dst = reinterpret_cast<float*>(p.D) + (int64_t)tc.ks * p.part_stride + (int64_t)tc.g * p.d_gs +
-                                 (int64_t)m * p.ldd + n0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    continue;
-                }
-                TO* dst = reinterpret_cast<TO*>(p.D) + (int64_t)tc.g * p.d_gs + (int64_t)m * p.ldd + n0;
+                const int sub = (c0 / 32) % GRP;            // position of this chunk inside the staged row
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     float x[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j + i]);
-                    if (bias) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j + 4));
-                        x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                        x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                    }
-                    if (p.epi == EPI_RELU || p.epi == EPI_RELU_ADDUP) {
+                    if (!p.partial) {
+                        if (bias) {
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
+                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j + 4));
+                            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+                            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+                        }
+                        if (p.epi == EPI_RELU || p.epi == EPI_RELU_ADDUP) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-                    } else if (p.epi == EPI_GELU) {
+                            for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+                        } else if (p.epi == EPI_GELU) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
-                    }
-                    if (p.epi == EPI_RELU_ADDUP) {
-                        float a00[8], a01[8], a10[8], a11[8];
-                        load8<TO>(aux + (int64_t)src00 * p.N + n0 + j, a00);
-                        load8<TO>(aux + (int64_t)src01 * p.N + n0 + j, a01);
-                        load8<TO>(aux + (int64_t)src10 * p.N + n0 + j, a10);
-                        load8<TO>(aux + (int64_t)src11 * p.N + n0 + j, a11);
+                            for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+                        }
+                        if (p.epi == EPI_RELU_ADDUP && row_ok) {
+                            float a00[8], a01[8], a10[8], a11[8];
+                            load8<TO>(aux + (int64_t)src00 * p.N + n0 + j, a00);
+                            load8<TO>(aux + (int64_t)src01 * p.N + n0 + j, a01);
+                            load8<TO>(aux + (int64_t)src10 * p.N + n0 + j, a10);
+                            load8<TO>(aux + (int64_t)src11 * p.N + n0 + j, a11);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
-                            x[i] += fmaxf(u, 0.f);
+                            for (int i = 0; i < 8; ++i) {
+                                const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
+                                x[i] += fmaxf(u, 0.f);
+                            }
+                        }
+                        if (sizeof(TO) == 4 && p.round_out) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x[i] = round_tf32(x[i]);
                         }
                     }
-                    if (sizeof(TO) == 4 && p.round_out) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) x[i] = round_tf32(x[i]);
+                    // staged row of this lane: piece k lives at ((k ^ (lane & 7)) * 16)
+                    if (sizeof(TO) == 2) {
+                        const int k = sub * PIECES + j / 8;
+                        store8<TO>(reinterpret_cast<TO*>(stage + lane * 128 + ((k ^ (lane & 7)) << 4)), x);
+                    } else {
+                        const int k = sub * PIECES + (j / 8) * 2;
+                        *reinterpret_cast<float4*>(stage + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
+                        *reinterpret_cast<float4*>(stage + lane * 128 + (((k + 1) ^ (lane & 7)) << 4)) = make_float4(x[4], x[5], x[6], x[7]);
                     }
-                    store8<TO>(dst + j, x);
+                }
+                if (sub == GRP - 1) {
+                    __syncwarp();
+                    const int nf0 = n0 - sub * 32;          // first column of the staged group
+#pragma unroll
+                    for (int i = 0; i < PR; ++i) {
+                        const int rr = i * (32 / PR) + lane / PR, k = lane % PR;
+                        const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((k ^ (rr & 7)) << 4));
+                        const int mm = m_w0 + rr;
+                        if (mm < p.M)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Dg + (int64_t)mm * p.ldd + nf0) + k * 16) = val;
+                    }
                 }
             }
             tc_fence_before();
@@ -386,7 +409,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // split-K finalize: out = epi(sum_s part[s] + bias)
 template <typename TO>
 __global__ void splitk_finalize_kernel(const float* part, int64_t part_stride, int ksplit, const float* bias, TO* out,
-                                       int64_t total, int N, int epi) {
+                                       int64_t total, int N, int epi, int round_out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     float s = 0.f;
@@ -394,6 +417,7 @@ __global__ void splitk_finalize_kernel(const float* part, int64_t part_stride, i
     if (bias) s += bias[i % N];
     if (epi == EPI_RELU) s = fmaxf(s, 0.f);
     else if (epi == EPI_GELU) s = gelu_erf(s);
+    if (sizeof(TO) == 4 && round_out) s = round_tf32(s);
     ActT<TO>::st(out + i, s);
 }
 
@@ -570,10 +594,10 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         const int blocks = (int)ceil_div64(tot, 256);
         if (d_is_bf16)
             splitk_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
-                                                                         reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi);
+                                                                         reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi, 0);
         else
             splitk_finalize_kernel<float><<<blocks, 256, 0, st>>>(g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
-                                                                  reinterpret_cast<float*>(d.D), tot, d.N, d.epi);
+                                                                  reinterpret_cast<float*>(d.D), tot, d.N, d.epi, d.round_tf32);
         EGR_LAUNCHED();
     }
     return EGR_OK;

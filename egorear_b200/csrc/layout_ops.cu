@@ -188,7 +188,7 @@ template <> __device__ __forceinline__ void pack8_store<__nv_bfloat16>(__nv_bflo
 template <typename TZ>
 __global__ void __launch_bounds__(256)
 up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ out_nchw, int64_t o_bs, int64_t o_gs,
-                          TZ* __restrict__ out_nhwc) {
+                          TZ* __restrict__ out_nhwc, float* __restrict__ out_nhwc_tf32) {
     constexpr int SLD = 130;                               // transposed tile row stride: conflict-free both ways
     extern __shared__ __align__(16) uint8_t fsm[];
     TZ* s1 = reinterpret_cast<TZ*>(fsm);                   // [FROWS*FS px][FCH]   as loaded
@@ -213,8 +213,9 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
         s2[c * SLD + p] = s1[i];
     }
     // ---- channels-last copy: item = (pixel, 8 channels) ----
-    if (out_nhwc) {
-        TZ* o = out_nhwc + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH;
+    if (out_nhwc || out_nhwc_tf32) {
+        TZ* o = out_nhwc ? out_nhwc + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH : nullptr;
+        float* o32 = out_nhwc_tf32 ? out_nhwc_tf32 + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH : nullptr;
 #pragma unroll 2
         for (int it = threadIdx.x; it < FSTRIP * FO * (FCH / 8); it += 256) {
             const int c8 = it & 15, px = it >> 4;
@@ -230,7 +231,12 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
             unpack8<TZ>(s1 + (r1 * FS + xb) * FCH + c8 * 8, d);
 #pragma unroll
             for (int i = 0; i < 8; ++i) r[i] = fmaxf(ly0 * (lx0 * a[i] + lx1 * bb[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]), 0.f);
-            pack8_store<TZ>(o + (int64_t)px * FCH + c8 * 8, r);
+            if (o) pack8_store<TZ>(o + (int64_t)px * FCH + c8 * 8, r);
+            if (o32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = round_tf32(r[i]);
+                pack8_store<float>(o32 + (int64_t)px * FCH + c8 * 8, r);
+            }
         }
     }
     __syncthreads();
@@ -425,7 +431,7 @@ up2_relu_dual_kernel(const TZ* __restrict__ z, int B, int Hs, int Ws, int C, flo
 }
 
 int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* out_nhwc, cudaStream_t st) {
+                  int64_t o_gs, void* out_nhwc, float* out_nhwc_tf32, cudaStream_t st) {
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;
@@ -434,15 +440,16 @@ int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C
         if (z_bf16) {
             auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k<<<fgrid, 256, fsmem, st>>>((const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc);
+            k<<<fgrid, 256, fsmem, st>>>((const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc, out_nhwc_tf32);
         } else {
             auto k = up2_relu_dual_fast_kernel<float>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k<<<fgrid, 256, fsmem, st>>>((const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc);
+            k<<<fgrid, 256, fsmem, st>>>((const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc, out_nhwc_tf32);
         }
         EGR_LAUNCHED();
         return EGR_OK;
     }
+    EGR_CHECK(!out_nhwc_tf32, EGR_ERR_UNSUPPORTED, "up2_relu_dual: the TF32 channels-last export needs the 32x32x128 geometry");
     const size_t smem = sizeof(float) * (size_t)C * (STRIP * Ws + 1);
     dim3 grid(2 * Hs / STRIP, G * B);
     if (z_bf16) {
@@ -459,24 +466,48 @@ int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C
 }
 
 // ---------------------------------------------------------------------------------------------
+// 16 bytes (4 floats / 8 bf16) of channels per thread
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) {
+        uint4 r;
+        r.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x)));
+        r.y = __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y)));
+        r.z = __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z)));
+        r.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w)));
+        return r;
+    }
+};
+template <> struct Vec16<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ uint32_t m2(uint32_t a, uint32_t b) {
+        const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) { return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w)); }
+};
+
 template <typename T>
-__global__ void maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t total, int H, int W, int C) {
-    const int Ho = H >> 1, Wo = W >> 1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C);
-        int64_t r = i / C;
+__global__ void maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t total_vec, int H, int W, int C) {
+    constexpr int VN = Vec16<T>::N;
+    const int Ho = H >> 1, Wo = W >> 1, CV = C / VN;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        int64_t r = i / CV;
         const int ox = (int)(r % Wo); r /= Wo;
         const int oy = (int)(r % Ho);
         const int64_t img = r / Ho;
-        const T* p = in + ((img * H + 2 * oy) * W + 2 * ox) * C + c;
-        const float a = ActT<T>::ld(p), b = ActT<T>::ld(p + C), cc = ActT<T>::ld(p + (int64_t)W * C),
-                    d = ActT<T>::ld(p + (int64_t)W * C + C);
-        ActT<T>::st(out + i, fmaxf(fmaxf(a, b), fmaxf(cc, d)));
+        const uint4* p = reinterpret_cast<const uint4*>(in + ((img * H + 2 * oy) * W + 2 * ox) * C) + cv;
+        const uint4 a = __ldg(p), b = __ldg(p + CV), c = __ldg(p + (int64_t)W * CV), d = __ldg(p + (int64_t)W * CV + CV);
+        reinterpret_cast<uint4*>(out)[i] = Vec16<T>::vmax(Vec16<T>::vmax(a, b), Vec16<T>::vmax(c, d));
     }
 }
 
 int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, int W, int C, cudaStream_t st) {
-    const int64_t total = n_img * (H / 2) * (W / 2) * C;
+    const int vn = is_bf16 ? 8 : 4;
+    EGR_CHECK(C % vn == 0, EGR_ERR_UNSUPPORTED, "maxpool2: C=%d", C);
+    const int64_t total = n_img * (H / 2) * (W / 2) * (C / vn);
     if (total == 0) return EGR_OK;
     const int grid = (int)(ceil_div64(total, 256) < 148 * 32 ? ceil_div64(total, 256) : 148 * 32);
     if (is_bf16) maxpool2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C);

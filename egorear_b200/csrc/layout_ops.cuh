@@ -20,8 +20,9 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
 // R1 tail: z [g][B][Hs*Ws][C] -> relu(up2(z)) written twice:
 //   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output) and
 //   out_nhwc [g][B][4HsWs][C] in the activation dtype (input of the H2 3x3 conv)
+//   out_nhwc_tf32 (optional) [g][B][4HsWs][C] fp32 rounded to TF32 (operand of the pose3d proposal branch when chained)
 int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* out_nhwc, cudaStream_t st);
+                  int64_t o_gs, void* out_nhwc, float* out_nhwc_tf32, cudaStream_t st);
 
 // nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C]
 int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, int W, int C, cudaStream_t st);

@@ -54,7 +54,7 @@ tok_sample_kernel(TokSampleArgs a) {
 
     const int64_t HW = (int64_t)a.H * a.W;
     const T* Xb = reinterpret_cast<const T*>(a.X) + ((int64_t)v * a.B + b) * HW * RAWC + lane * 4;
-    const float* pt = HAS_PTAB ? (a.ptab[g] + (int64_t)v * HW * E + h * HD + lane * 2) : nullptr;
+    const __nv_bfloat16* pt = HAS_PTAB ? (a.ptab[g] + (int64_t)v * HW * E + h * HD + lane * 2) : nullptr;
     float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float2 e2 = make_float2(0.f, 0.f);
     float wsum = 0.f;
@@ -69,8 +69,8 @@ tok_sample_kernel(TokSampleArgs a) {
             s4.x = fmaf(coef, x.x, s4.x); s4.y = fmaf(coef, x.y, s4.y);
             s4.z = fmaf(coef, x.z, s4.z); s4.w = fmaf(coef, x.w, s4.w);
             if (HAS_PTAB) {
-                const float2 pv = __ldg(reinterpret_cast<const float2*>(pt + (int64_t)idx * E));
-                e2.x = fmaf(coef, pv.x, e2.x); e2.y = fmaf(coef, pv.y, e2.y);
+                const uint32_t pu = __ldg(reinterpret_cast<const uint32_t*>(pt + (int64_t)idx * E));
+                e2.x = fmaf(coef, __uint_as_float(pu << 16), e2.x); e2.y = fmaf(coef, __uint_as_float(pu & 0xffff0000u), e2.y);
             } else {
                 wsum += coef;
             }
@@ -270,33 +270,36 @@ int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int
 // mvfex jqa query input (HeatmapMVF.forward :655-665): x0 = embed_j + fc_bfb(avgpool(bfb)) + heatmap_proj(heatmap_j)
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-tok_jqa_query_kernel(TokQueryArgs a) {
-    constexpr int E = 256;
-    __shared__ float pool[512];
-    const int g = blockIdx.x / a.B, b = blockIdx.x - g * a.B;
-    const int n = threadIdx.x;
-    const float* bf = a.bfb + (int64_t)g * a.bfb_gs + (int64_t)b * a.bfb_bs;
-    // adaptive_avg_pool2d(bfb, 1): a warp per channel, lanes over the hw positions
-    const int lane = n & 31, warp = n >> 5;
-    for (int c = warp; c < 512; c += 8) {
+tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* __restrict__ pooled, int B, int C) {
+    const int g = blockIdx.x / B, b = blockIdx.x - g * B;
+    const float* bf = bfb + (int64_t)g * bfb_gs + (int64_t)b * bfb_bs;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = warp; c < C; c += 8) {       // a warp per channel, lanes over the hw positions
         float s = 0.f;
-        for (int i = lane; i < a.hw; i += 32) s += bf[(int64_t)c * a.hw + i];
+        for (int i = lane; i < hw; i += 32) s += bf[(int64_t)c * hw + i];
         s = warp_sum(s);
-        if (lane == 0) pool[c] = s / (float)a.hw;
+        if (lane == 0) pooled[(int64_t)blockIdx.x * C + c] = round_tf32(s / (float)hw);
     }
-    __syncthreads();
-    const float* wT = a.bfb_T[g];
-    float gv = __ldg(a.bfb_b[g] + n);
-    for (int k = 0; k < 512; ++k) gv = fmaf(__ldg(wT + (int64_t)k * E + n), pool[k], gv);
-    const float* jq = a.jq[g];
-    const int64_t base = ((int64_t)g * a.B + b) * a.J * E;
-    for (int j = 0; j < a.J; ++j)
-        a.x0[base + j * E + n] = round_tf32(__ldg(jq + j * E + n) + gv + a.y0[base + j * E + n]);
+}
+int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st) {
+    tok_avgpool_kernel<<<G * B, 256, 0, st>>>(bfb, bfb_bs, bfb_gs, hw, pooled, B, C);
+    EGR_LAUNCHED();
+    return EGR_OK;
 }
 
-int tok_jqa_query(const TokQueryArgs& a, cudaStream_t st) {
-    EGR_CHECK(a.E == 256, EGR_ERR_UNSUPPORTED, "tok_jqa_query: E=%d", a.E);
-    tok_jqa_query_kernel<<<a.G * a.B, 256, 0, st>>>(a);
+__global__ void __launch_bounds__(256)
+tok_add_query_kernel(const float* __restrict__ y0, const float* __restrict__ vb, const float* const* __restrict__ jq,
+                     float* __restrict__ x0, int B, int J, int E) {
+    const int g = blockIdx.x / B;
+    const float* q = jq[g];
+    const int64_t base = (int64_t)blockIdx.x * J * E;
+    for (int i = threadIdx.x; i < J * E; i += 256) {
+        const int n = i % E;
+        x0[base + i] = round_tf32(__ldg(q + i) + vb[(int64_t)blockIdx.x * E + n] + y0[base + i]);
+    }
+}
+int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st) {
+    tok_add_query_kernel<<<G * B, 256, 0, st>>>(y0, vb, jq, x0, B, J, E);
     EGR_LAUNCHED();
     return EGR_OK;
 }

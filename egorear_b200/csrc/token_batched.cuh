@@ -30,7 +30,7 @@ __host__ __device__ constexpr int tok_ka(int E, bool has_ptab) {
 //   oa      [G][T][192] fp32: offsets [h][p][2] then logits [h][p]
 //   anchors [B][V][J][2], valid [B][V][J]
 //   X       [V][B][H*W][128] channels-last features (float | bf16)
-//   ptab    per group [V][H*W][E] (mvfex) or null;  group g uses ptab[g] (device array of pointers)
+//   ptab    per group [V][H*W][E] bf16 (mvfex) or null;  group g uses ptab[g] (device array of pointers)
 //   A       [G][T][V][KA] fp32, rounded to TF32
 struct TokSampleArgs {
     int G, B, V, J, H, W, E, KA;
@@ -38,7 +38,7 @@ struct TokSampleArgs {
     const float* anchors;
     const uint8_t* valid;
     const void* X;
-    const float* const* ptab;     // device array [G] or null
+    const __nv_bfloat16* const* ptab;   // device array [G] of bf16 tables, or null
     float* A;
 };
 int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st);
@@ -55,19 +55,13 @@ int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per
 int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int E, const float* const* gamma,
                  const float* const* beta, cudaStream_t st);
 
-// mvfex jqa query input: x0[g][b][j][:] = y0[g][b][j][:] + fc_bfb(avgpool(bfb[g][b])) + joint_query_embed[j]   (rounded)
-//   bfb of group g, frame b at bfb + g*bfb_gs + b*bfb_bs: [512][hw];  bfbT[g] [512][E], bfbb[g] [E], jq[g] [J][E]
-struct TokQueryArgs {
-    int G, B, J, E, hw;
-    const float* y0;
-    const float* bfb;
-    int64_t bfb_bs, bfb_gs;
-    const float* const* bfb_T;
-    const float* const* bfb_b;
-    const float* const* jq;
-    float* x0;
-};
-int tok_jqa_query(const TokQueryArgs& a, cudaStream_t st);
+// mvfex jqa query input (HeatmapMVF.forward :655-665), in three steps:
+//   tok_avgpool:   pooled[g][b][512] = adaptive_avg_pool2d(bfb[g][b], 1), rounded     (bfb of group g, frame b at
+//                  bfb + g*bfb_gs + b*bfb_bs: [512][hw])
+//   (token GEMM)   vb[g][b][E] = fc_bfb(pooled)
+//   tok_add_query: x0[g][b][j][:] = y0[g][b][j][:] + vb[g][b][:] + joint_query_embed[g][j][:], rounded
+int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st);
+int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st);
 
 // pose3d: P3 reprojection of the proposal + first query_gen Linear(4 -> E) + ReLU
 struct PoseQueryArgs {

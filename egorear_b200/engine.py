@@ -107,12 +107,18 @@ class MvfexEngine(_EngineBase):
         _lib.check(self._lib.egr_mvfex_create(num_views, num_heatmap, float(heatmap_threshold), PREC[precision],
                                               ctypes.byref(self._h)))
 
+    def export_staged(self, enable=True):
+        """keep channels-last copies of the input / refined features for a chained Pose3DEngine.forward(staged=...)"""
+        _lib.check(self._lib.egr_mvfex_export_staged(self._h, int(bool(enable))))
+        self._export = bool(enable)
+
     def forward(self, feat, bfb, heatmap_for_anchor=None):
         """feat [B,V,128,64,64], bfb [B,V,512,8,8] fp32 CUDA ->
         dict(hm_init, hm_refined [B,V,15,64,64], feat_refined [B,V,128,64,64], anchors_2d [B,V,15,2], anchors_valid)."""
         self._sync_params()
         B, V = feat.shape[:2]
         assert V == self.V and tuple(feat.shape[2:]) == (128, 64, 64) and tuple(bfb.shape[1:]) == (V, 512, 8, 8)
+        feat_arg = feat
         feat = feat.detach().float().contiguous()
         bfb = bfb.detach().float().contiguous()
         hfa = heatmap_for_anchor.detach().float().contiguous() if isinstance(heatmap_for_anchor, torch.Tensor) else None
@@ -129,6 +135,12 @@ class MvfexEngine(_EngineBase):
                                                _ptr(out["hm_refined"]), _ptr(out["feat_refined"]),
                                                _ptr(out["anchors_2d"]), _ptr(out["anchors_valid"]), _ptr(ws),
                                                ws.numel(), _stream()))
+        if getattr(self, "_export", False):
+            pi, pr, pt, bf = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+            _lib.check(self._lib.egr_mvfex_staged(self._h, ctypes.byref(pi), ctypes.byref(pr), ctypes.byref(pt), ctypes.byref(bf)))
+            # device pointers into this engine's workspace: valid until its next forward
+            out["staged"] = {"init": pi.value, "refined": pr.value, "refined_tf32": pt.value, "bf16": bf.value,
+                             "feat": feat_arg, "feat_refined": out["feat_refined"]}
         return out
 
     def refiner_forward(self, r, heatmap, frame_feat, feat_mv, anchors_2d, anchors_valid, bfb):
@@ -168,8 +180,9 @@ class Pose3DEngine(_EngineBase):
                                                ctypes.c_void_p(tab.ctypes.data) if tab is not None else None,
                                                ctypes.byref(self._h)))
 
-    def forward(self, feats_init, feats_final, coord_trans_mat=None):
-        """-> preds [L+1, B, 16, 3] fp32 (cm): preds[0] MLP proposal, preds[1:] transformer layers."""
+    def forward(self, feats_init, feats_final, coord_trans_mat=None, staged=None, use_init=True):
+        """-> preds [L+1, B, 16, 3] fp32 (cm): preds[0] MLP proposal, preds[1:] transformer layers.
+        staged: MvfexEngine.forward(...)["staged"] of the SAME tensors (chained forward): skips the re-staging passes."""
         self._sync_params()
         B, V = feats_final.shape[:2]
         assert V == self.V
@@ -185,6 +198,10 @@ class Pose3DEngine(_EngineBase):
             ctm = coord_trans_mat.contiguous()
         preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=ff.device)
         ws = self._workspace(B, ff.device)
+        if staged is not None and staged["feat_refined"] is feats_final and (staged["feat"] is feats_init or not use_init):
+            sampled = staged["init"] if use_init else staged["refined"]
+            _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),
+                                                       ctypes.c_void_p(staged["refined_tf32"]) if staged["refined_tf32"] else None))
         _lib.check(self._lib.egr_pose3d_forward(self._h, B, _ptr(fi), _ptr(ff), _ptr(ctm), _ptr(preds), _ptr(ws),
                                                 ws.numel(), _stream()))
         return preds

@@ -469,6 +469,7 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
         hfa = heatmap_for_anchor if isinstance(heatmap_for_anchor, torch.Tensor) else None
         out = self.engine().forward(frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa)
         self.last_anchors = (out["anchors_2d"], out["anchors_valid"])
+        self.last_staged = out.get("staged")
         return [out["hm_init"], out["hm_refined"]], [frame_feat_multi_view, out["feat_refined"]]
 
     def forward(self, img, heatmap_for_anchor=None):
@@ -552,9 +553,11 @@ class EgoPoseFormerPose3D(nn.Module):
                 self._engine = None
         return out
 
-    def forward(self, frame_feats_init, frame_feats_final, heatmap, coord_trans_mat=None, origin_3d=None):
+    def forward(self, frame_feats_init, frame_feats_final, heatmap, coord_trans_mat=None, origin_3d=None, staged=None):
         # `heatmap` and `origin_3d` are accepted and unused, as in the reference's shipped configuration (:434-439)
-        preds = self.engine().forward(frame_feats_init, frame_feats_final, coord_trans_mat)
+        # `staged` (not in the reference): channels-last copies left by a chained EgoPoseFormerHeatmapMVFEX forward
+        preds = self.engine().forward(frame_feats_init, frame_feats_final, coord_trans_mat, staged=staged,
+                                      use_init=self.use_pred_heatmap_init)
         return [preds[i] for i in range(preds.shape[0])]
 
 
@@ -569,10 +572,14 @@ class EgoPoseFormerMVFEX(nn.Module):
         p.update({"num_views": num_views, "image_size": image_size, "use_pred_heatmap_init": self.use_pred_heatmap_init,
                   "camera_model": camera_model, "precision": precision})
         self.pose3d_estimator = EgoPoseFormerPose3D(**p)
+        self._chain = True      # hand the heatmap engine's channels-last copies to the pose3d engine
 
     def forward_from_feats(self, feat, bfb, coord_trans_mat=None, origin_3d=None):
+        if self._chain:
+            self.heatmap_estimator.engine().export_staged(True)
         list_hm, list_ff = self.heatmap_estimator.forward_from_feats(feat, bfb)
-        return self.pose3d_estimator(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, origin_3d), list_hm
+        return self.pose3d_estimator(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, origin_3d,
+                                     staged=self.heatmap_estimator.last_staged), list_hm
 
     def forward(self, img, coord_trans_mat=None, origin_3d=None):
         list_hm, list_ff = self.heatmap_estimator(img)

@@ -23,6 +23,7 @@ class HotPathPipeline:
             synth.fill_state_dict(self.pose3d)
         self.heatmap = self.heatmap.to(device).eval()
         self.pose3d = self.pose3d.to(device).eval()
+        self.heatmap.engine().export_staged(True)      # chained forward: pose3d reuses the channels-last copies
 
     def freeze(self):
         """weights will not change any more: skip the per-call parameter-version check"""
@@ -36,7 +37,7 @@ class HotPathPipeline:
         list_hm, list_ff = self.heatmap.forward_from_feats(feat, bfb, heatmap_for_anchor)
         B, V, J, H, W = list_hm[-1].shape
         pts2d, maxvals, valid = ops.get_max_preds(list_hm[-1].view(B * V, J, H, W), threshold=0.5, normalize=False)
-        preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat)
+        preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, staged=self.heatmap.last_staged)
         packed = ops.pack_joints(pts2d.view(B, V * J * 2), preds3d[-1])
         return dict(packed=packed, joints2d=pts2d.view(B, V, J, 2), pose3d=preds3d[-1], list_hm=list_hm, list_ff=list_ff,
                     list_pose3d=preds3d)

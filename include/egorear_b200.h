@@ -172,6 +172,15 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
                               const float* feat_mv, const float* anchors_2d, const uint8_t* anchors_valid,
                               const float* bfb, float* hm_refined, float* feat_refined, void* workspace,
                               int64_t workspace_bytes, void* stream);
+/* Chaining (EgoPoseFormerMVFEX.forward, estimator/egoposeformer_mvf_ex.py:50-58: heatmap estimator -> pose3d):
+ * with export enabled, egr_mvfex_forward keeps channels-last copies of its input features (activation dtype), of the
+ * refined features (activation dtype) and of the refined features as fp32 rounded to TF32 in ITS workspace;
+ * egr_mvfex_staged returns them (valid until the next forward on this handle / workspace).  Passing them to
+ * egr_pose3d_use_staged lets the NEXT egr_pose3d_forward skip re-staging its NCHW inputs (the hint is consumed by that
+ * call; the NCHW pointers must still be the same tensors).  [V][B][64*64][128] layout. */
+int egr_mvfex_export_staged(egr_mvfex* h, int enable);
+int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const float** refined_nhwc_tf32,
+                     int* act_is_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
  * ("q1", "xT", "t1", "ff", ...); EGR_ERR_INVALID for unknown names */
 int egr_mvfex_debug_buffer(egr_mvfex* h, const char* name, void** ptr, int64_t* bytes);
@@ -195,6 +204,10 @@ int64_t egr_pose3d_workspace_bytes(egr_pose3d* h, int B);
 int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init, const float* feats_final,
                        const float* coord_trans_mat, float* preds, void* workspace, int64_t workspace_bytes,
                        void* stream);
+/* sampled_nhwc: channels-last copy of the map the transformer samples (feats_init when use_pred_heatmap_init, else
+ * feats_final), bf16 or fp32 as flagged; final_nhwc_tf32: channels-last fp32 copy of feats_final rounded to TF32.
+ * Either may be NULL.  One-shot: consumed by the next egr_pose3d_forward. */
+int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32);
 int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes);
 
 /* ---------------------------------------------------------------------------------------------
