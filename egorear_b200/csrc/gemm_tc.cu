@@ -9,8 +9,9 @@
 //   warp 1      TMEM allocator + MMA issuer: one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per k-block,
 //               tcgen05.commit releases the smem slot / publishes the accumulator
 //   warps 2-9   epilogue: tcgen05.ld the 128xBN fp32 accumulator (two TMEM buffers, so the epilogue of tile i
-//               overlaps the MMAs of tile i+1), bias + activation (+ fused bilinear-x2 residual); rows are staged in
-//               a swizzled smem tile so that every global store instruction writes whole 128 B row segments
+//               overlaps the MMAs of tile i+1; the load of the next 32-column chunk is in flight while one is
+//               processed), bias from smem + activation (+ fused bilinear-x2 residual); rows are staged in a
+//               swizzled smem tile and leave through TMA stores (whole 128 B row segments, rows >= M clipped)
 // The 3x3 stride-2 pad-1 conv is an implicit GEMM: the NHWC input is described to TMA as a 5-D tensor
 // (2*Cin, W/2, 2, H/2, img) so that tap (ky,kx) of 128 consecutive output pixels is ONE box load whose
 // out-of-bounds part (the zero padding) is filled by the TMA unit.
@@ -33,8 +34,13 @@ template <int BN> struct TcCfg {
     static constexpr int STAGE = STAGE_A + STAGE_B;
     static constexpr int STAGES = SMEM_RING / STAGE;          // 256: 4, 128: 6, 64: 8
     static constexpr int TMEM_COLS = 2 * BN;                  // double-buffered accumulator
-    static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 4096 /*store staging*/;
+    // ring | store staging (8 warps x 4 KB, 1024-aligned: TMA-store source) | barriers | bias tile
+    static constexpr int OFF_STAGING = STAGES * STAGE;
+    static constexpr int OFF_BARS = OFF_STAGING + EPI_WARPS * 4096;
+    static constexpr int OFF_BIAS = OFF_BARS + 256;
+    static constexpr int SMEM = OFF_BIAS + 1024 /*bias[BN <= 256]*/ + 1024 /*align*/;
 };
+static_assert(TcCfg<256>::SMEM <= 227 * 1024 && TcCfg<128>::SMEM <= 227 * 1024 && TcCfg<64>::SMEM <= 227 * 1024, "smem budget");
 
 struct TcParams {
     int M, N, K;
@@ -121,7 +127,7 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
             ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -131,8 +137,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the registers of an in-flight tcgen05.ld are operands of the wait, so no use of them can be scheduled above it
+__device__ __forceinline__ void tc_ld32_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 UMMA): rows of 128 B, 8-row atoms 1024 B apart.
 // bits [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4 | [46,48) version = 1 |
@@ -187,16 +210,132 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const TcParams& p) {
     return c;
 }
 
+// ---- epilogue of one 128 x BN tile, one warp = 32 accumulator rows x BN/2 columns ------------------------------
+// TMEM -> registers in 32-column chunks (the load of chunk c+1 is in flight while chunk c is processed), bias from a
+// shared-memory copy of the tile's bias slice, activation, conversion, 16-byte st.shared into a swizzled staging tile
+// [32 rows][SW bytes], and one TMA store per staged group: the async proxy writes whole 128-byte row segments and
+// clips rows >= M, so the epilogue warps spend no instructions on global addressing.
+template <int BN, typename TO, int EPI, bool ROUND>
+__device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* tmD, const TileCoord& tc, uint32_t taddr,
+                                         const float* sbias, uint8_t* stage, uint32_t tempty_bar, int lane, int q,
+                                         int half) {
+    constexpr int OUT_B = (int)sizeof(TO);
+    constexpr int HALF = BN / 2;                                           // columns per warp
+    constexpr int BOX_COLS = (HALF * OUT_B >= 128) ? 128 / OUT_B : HALF;   // columns per TMA-store box
+    constexpr int SW = BOX_COLS * OUT_B;                                   // staged row bytes: 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+    constexpr int NCH = HALF / 32;                                         // 32-column chunks per warp
+    constexpr int CPG = BOX_COLS / 32;                                     // chunks per store group
+    static_assert(SW == 128 || SW == 64, "staging row");
+    const int swz = (SW == 128) ? (lane & 7) : ((lane >> 1) & 3);
+    const int m_w0 = tc.mt * BM + q * 32;                                  // first row of this warp
+    const int n_base = tc.nt * BN + half * HALF;
+    const int dz = p.partial ? tc.ks : tc.g;
+    // ADDUP geometry of this thread's row
+    int src00 = 0, src01 = 0, src10 = 0, src11 = 0;
+    float wy0 = 0.f, wy1 = 0.f, wx0 = 0.f, wx1 = 0.f;
+    const TO* aux = nullptr;
+    bool row_ok = false;
+    if (EPI == EPI_RELU_ADDUP) {
+        const int m = m_w0 + lane;
+        row_ok = m < p.M;
+        if (row_ok) {
+            const int hw = p.Hout_e * p.Wout_e;
+            const int im = m / hw, r = m - im * hw;
+            const int y = r / p.Wout_e, x = r - y * p.Wout_e;
+            const int hs = p.Hout_e >> 1, ws = p.Wout_e >> 1;
+            const Up2Coef cy = up2_coef(y, hs), cx = up2_coef(x, ws);
+            wy0 = cy.l0; wy1 = cy.l1; wx0 = cx.l0; wx1 = cx.l1;
+            src00 = cy.i0 * ws + cx.i0; src01 = cy.i0 * ws + cx.i1;
+            src10 = cy.i1 * ws + cx.i0; src11 = cy.i1 * ws + cx.i1;
+            aux = reinterpret_cast<const TO*>(p.aux) + (int64_t)tc.g * p.aux_gs + (int64_t)im * hs * ws * p.N;
+        }
+    }
+    uint32_t v[2][32];
+    tc_ld32_issue(taddr, v[0]);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t (&cur)[32] = v[c & 1];
+        tc_ld32_wait(cur);
+        if (c + 1 < NCH) {
+            tc_ld32_issue(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        } else {
+            // every accumulator column of this warp is in registers: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+        }
+        const int sub = c % CPG;
+        if (sub == 0) {
+            // the staging tile is the source of the previous group's TMA store: wait until it has been read
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+        }
+        const float* sb = sbias + half * HALF + c * 32;
+        const int n0 = n_base + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            float x[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(sb + j);
+            const float4 b1 = *reinterpret_cast<const float4*>(sb + j + 4);
+            x[0] = __uint_as_float(cur[j + 0]) + b0.x; x[1] = __uint_as_float(cur[j + 1]) + b0.y;
+            x[2] = __uint_as_float(cur[j + 2]) + b0.z; x[3] = __uint_as_float(cur[j + 3]) + b0.w;
+            x[4] = __uint_as_float(cur[j + 4]) + b1.x; x[5] = __uint_as_float(cur[j + 5]) + b1.y;
+            x[6] = __uint_as_float(cur[j + 6]) + b1.z; x[7] = __uint_as_float(cur[j + 7]) + b1.w;
+            if (EPI == EPI_RELU || EPI == EPI_RELU_ADDUP) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+            } else if (EPI == EPI_GELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
+            }
+            if (EPI == EPI_RELU_ADDUP) {
+                if (row_ok) {
+                    float a00[8], a01[8], a10[8], a11[8];
+                    load8<TO>(aux + (int64_t)src00 * p.N + n0 + j, a00);
+                    load8<TO>(aux + (int64_t)src01 * p.N + n0 + j, a01);
+                    load8<TO>(aux + (int64_t)src10 * p.N + n0 + j, a10);
+                    load8<TO>(aux + (int64_t)src11 * p.N + n0 + j, a11);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
+                        x[i] += fmaxf(u, 0.f);
+                    }
+                }
+            }
+            if (ROUND) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = round_tf32(x[i]);
+            }
+            // staged row of this lane: 16-byte piece k lives at ((k ^ swz) * 16)
+            if (OUT_B == 2) {
+                const int k = sub * 4 + j / 8;
+                store8<TO>(reinterpret_cast<TO*>(stage + lane * SW + ((k ^ swz) << 4)), x);
+            } else {
+                const int k = j / 4;
+                *reinterpret_cast<float4*>(stage + lane * SW + ((k ^ swz) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(stage + lane * SW + (((k + 1) ^ swz) << 4)) = make_float4(x[4], x[5], x[6], x[7]);
+            }
+        }
+        if (sub == CPG - 1) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_3d(tmD, smem_u32(stage), n0 - sub * 32, m_w0, dz);
+        }
+    }
+}
+
 template <int BN, typename TI, typename TO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const TcParams p) {
     using C = TcCfg<BN>;
     constexpr int BK = ROW_BYTES / (int)sizeof(TI);      // elements per k-block
     constexpr bool TF32 = sizeof(TI) == 4;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BARS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
     const uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
@@ -210,6 +349,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmD)) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)C::TMEM_COLS) : "memory");
@@ -290,113 +430,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int e = warp - 2;
         const int q = warp & 3;            // TMEM lane quarter this warp may read
         const int half = e >> 2;           // column half
-        const int row = q * 32 + lane;
-        constexpr int PIECES = 32 * (int)sizeof(TO) / 16;                  // 16 B pieces per 32-column chunk (4 bf16, 8 fp32)
-        constexpr int NCH = BN / 64;                                       // chunks per warp
-        constexpr int GRP = (8 / PIECES < NCH) ? 8 / PIECES : NCH;         // chunks staged per flush
-        constexpr int PR = PIECES * GRP;                                   // pieces per staged row (4 or 8)
-        uint8_t* stage = smem + C::STAGES * C::STAGE + 256 + e * 4096;     // [32 rows][128 B], private to this warp
-        int it = 0;
+        uint8_t* stage = smem + C::OFF_STAGING + e * 4096;                 // [32 rows][<= 128 B], private to this warp
+        int it = 0, bias_key = -1;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const TileCoord tc = decode_tile(t, p);
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int m = tc.mt * BM + row;
-            const bool row_ok = m < p.M;
-            const int n_base = tc.nt * BN + half * (BN / 2);
-            const float* bias = p.bias ? p.bias + (int64_t)tc.g * p.b_gs : nullptr;
-            // ADDUP geometry of this row
-            int src00 = 0, src01 = 0, src10 = 0, src11 = 0;
-            float wy0 = 0.f, wy1 = 0.f, wx0 = 0.f, wx1 = 0.f;
-            const TO* aux = nullptr;
-            if (p.epi == EPI_RELU_ADDUP && row_ok) {
-                const int hw = p.Hout_e * p.Wout_e;
-                const int im = m / hw, r = m - im * hw;
-                const int y = r / p.Wout_e, x = r - y * p.Wout_e;
-                const int hs = p.Hout_e >> 1, ws = p.Wout_e >> 1;
-                const Up2Coef cy = up2_coef(y, hs), cx = up2_coef(x, ws);
-                wy0 = cy.l0; wy1 = cy.l1; wx0 = cx.l0; wx1 = cx.l1;
-                src00 = cy.i0 * ws + cx.i0; src01 = cy.i0 * ws + cx.i1;
-                src10 = cy.i1 * ws + cx.i0; src11 = cy.i1 * ws + cx.i1;
-                aux = reinterpret_cast<const TO*>(p.aux) + (int64_t)tc.g * p.aux_gs + (int64_t)im * hs * ws * p.N;
+            // bias slice of this (group, n-tile), shared by the epilogue warps; zeros for split-K partials / no bias
+            const int key = tc.g * p.n_tiles + tc.nt;
+            if (key != bias_key) {
+                bias_key = key;
+                epi_bar_sync();            // nobody still reads the previous slice
+                const int i = e * 32 + lane;
+                if (i < BN) sbias[i] = (p.bias && !p.partial) ? __ldg(p.bias + (int64_t)tc.g * p.b_gs + tc.nt * BN + i) : 0.f;
+                epi_bar_sync();
             }
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + half * (BN / 2);
-            // Each thread owns one accumulator row; a row-per-thread store would touch 32 different lines per instruction.
-            // Stage 128 B per row in a per-warp XOR-swizzled smem tile, then store whole rows: 8 lanes x 16 B per row.
-            TO* Dg = reinterpret_cast<TO*>(p.D) + (int64_t)tc.g * p.d_gs;
-            if (p.partial) Dg = reinterpret_cast<TO*>(reinterpret_cast<float*>(p.D) + (int64_t)tc.ks * p.part_stride);
-            const int m_w0 = tc.mt * BM + q * 32;           // first row of this warp
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN / 2; c0 += 32) {
-                uint32_t v[32];
-                __syncwarp();
-                tc_ld32(taddr + c0, v);
-                const int n0 = n_base + c0;
-                const int sub = (c0 / 32) % GRP;            // position of this chunk inside the staged row
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float x[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(v[j + i]);
-                    if (!p.partial) {
-                        if (bias) {
-                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j));
-                            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + j + 4));
-                            x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                            x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-                        }
-                        if (p.epi == EPI_RELU || p.epi == EPI_RELU_ADDUP) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
-                        } else if (p.epi == EPI_GELU) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
-                        }
-                        if (p.epi == EPI_RELU_ADDUP && row_ok) {
-                            float a00[8], a01[8], a10[8], a11[8];
-                            load8<TO>(aux + (int64_t)src00 * p.N + n0 + j, a00);
-                            load8<TO>(aux + (int64_t)src01 * p.N + n0 + j, a01);
-                            load8<TO>(aux + (int64_t)src10 * p.N + n0 + j, a10);
-                            load8<TO>(aux + (int64_t)src11 * p.N + n0 + j, a11);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
-                                x[i] += fmaxf(u, 0.f);
-                            }
-                        }
-                        if (sizeof(TO) == 4 && p.round_out) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) x[i] = round_tf32(x[i]);
-                        }
-                    }
-                    // staged row of this lane: piece k lives at ((k ^ (lane & 7)) * 16)
-                    if (sizeof(TO) == 2) {
-                        const int k = sub * PIECES + j / 8;
-                        store8<TO>(reinterpret_cast<TO*>(stage + lane * 128 + ((k ^ (lane & 7)) << 4)), x);
-                    } else {
-                        const int k = sub * PIECES + (j / 8) * 2;
-                        *reinterpret_cast<float4*>(stage + lane * 128 + ((k ^ (lane & 7)) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
-                        *reinterpret_cast<float4*>(stage + lane * 128 + (((k + 1) ^ (lane & 7)) << 4)) = make_float4(x[4], x[5], x[6], x[7]);
-                    }
-                }
-                if (sub == GRP - 1) {
-                    __syncwarp();
-                    const int nf0 = n0 - sub * 32;          // first column of the staged group
-#pragma unroll
-                    for (int i = 0; i < PR; ++i) {
-                        const int rr = i * (32 / PR) + lane / PR, k = lane % PR;
-                        const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((k ^ (rr & 7)) << 4));
-                        const int mm = m_w0 + rr;
-                        if (mm < p.M)
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(Dg + (int64_t)mm * p.ldd + nf0) + k * 16) = val;
-                    }
-                }
+            const uint32_t tempty = tempty0 + 8 * acc;
+            const int epi = p.partial ? (int)EPI_NONE : p.epi;
+            const bool rnd = sizeof(TO) == 4 && p.round_out && !p.partial;
+#define EGR_EPI(E_, R_) epi_tile<BN, TO, E_, R_>(p, &tmD, tc, taddr, sbias, stage, tempty, lane, q, half)
+            if (sizeof(TO) == 4 && rnd) {
+                if (epi == EPI_RELU) EGR_EPI(EPI_RELU, (sizeof(TO) == 4));
+                else if (epi == EPI_GELU) EGR_EPI(EPI_GELU, (sizeof(TO) == 4));
+                else if (epi == EPI_RELU_ADDUP) EGR_EPI(EPI_RELU_ADDUP, (sizeof(TO) == 4));
+                else EGR_EPI(EPI_NONE, (sizeof(TO) == 4));
+            } else {
+                if (epi == EPI_RELU) EGR_EPI(EPI_RELU, false);
+                else if (epi == EPI_GELU) EGR_EPI(EPI_GELU, false);
+                else if (epi == EPI_RELU_ADDUP) EGR_EPI(EPI_RELU_ADDUP, false);
+                else EGR_EPI(EPI_NONE, false);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+#undef EGR_EPI
         }
+        if (lane == 0) tma_store_wait_all();      // the staging tiles must outlive the last bulk stores
     }
     tc_fence_before();
     __syncthreads();
@@ -432,10 +500,10 @@ float* g_splitk_scratch = nullptr;
 constexpr int64_t SPLITK_SCRATCH_FLOATS = 8ll << 20;   // 32 MB
 
 int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box, const char* what) {
+           const cuuint32_t* box, const char* what, bool swizzle64 = false) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(EGR_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
@@ -445,20 +513,20 @@ int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64
 }
 
 template <int BN, typename TI, typename TO>
-int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
-    gemm_tc_kernel<BN, TI, TO><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, p);
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
+    gemm_tc_kernel<BN, TI, TO><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, tmD, p);
     EGR_LAUNCHED();
     return EGR_OK;
 }
 template <int BN, typename TI>
-int launch_tc_bn(bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
-    return out_bf16 ? launch_tc<BN, TI, __nv_bfloat16>(tmA, tmB, p, grid, st) : launch_tc<BN, TI, float>(tmA, tmB, p, grid, st);
+int launch_tc_bn(bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
+    return out_bf16 ? launch_tc<BN, TI, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st) : launch_tc<BN, TI, float>(tmA, tmB, tmD, p, grid, st);
 }
 template <typename TI>
-int launch_tc_any(int bn, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, int grid, cudaStream_t st) {
-    if (bn == 256) return launch_tc_bn<256, TI>(out_bf16, tmA, tmB, p, grid, st);
-    if (bn == 128) return launch_tc_bn<128, TI>(out_bf16, tmA, tmB, p, grid, st);
-    return launch_tc_bn<64, TI>(out_bf16, tmA, tmB, p, grid, st);
+int launch_tc_any(int bn, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
+    if (bn == 256) return launch_tc_bn<256, TI>(out_bf16, tmA, tmB, tmD, p, grid, st);
+    if (bn == 128) return launch_tc_bn<128, TI>(out_bf16, tmA, tmB, tmD, p, grid, st);
+    return launch_tc_bn<64, TI>(out_bf16, tmA, tmB, tmD, p, grid, st);
 }
 template <int BN, typename TI, typename TO>
 int set_smem_attr() {
@@ -583,11 +651,25 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         if ((rc = encode(&tmB, f32, d.W, 3, dims, str, box, "W"))) return rc;
     }
 
+    const bool out_bf16 = d_is_bf16 && !p.partial;
+    CUtensorMap tmD;
+    {
+        // output [groups | ksplit][M][ldd]: one TMA-store box = 32 rows x (128 B, or the warp's BN/2 columns when narrower)
+        const int OB = out_bf16 ? 2 : 4;
+        const int box_cols = ((bn / 2) * OB >= 128) ? 128 / OB : bn / 2;
+        const int64_t ldd = p.partial ? d.N : d.ldd;
+        const int nz = p.partial ? p.ksplit : d.groups;
+        const int64_t zs = p.partial ? p.part_stride : d.d_gs;
+        EGR_CHECK((ldd * OB) % 16 == 0 && (nz == 1 || (zs * OB) % 16 == 0), EGR_ERR_UNSUPPORTED, "gemm_tc: D strides must be multiples of 16 bytes");
+        const cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)d.M, (cuuint64_t)nz};
+        const cuuint64_t str[2] = {(cuuint64_t)ldd * OB, (cuuint64_t)(nz > 1 ? zs : (int64_t)d.M * ldd) * OB};
+        const cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
+        if ((rc = encode(&tmD, !out_bf16, p.D, 3, dims, str, box, "D", box_cols * OB == 64))) return rc;
+    }
     const int64_t total = (int64_t)d.groups * m_tiles * p.n_tiles * p.ksplit;
     const int grid = (int)(total < nsm ? total : nsm);
-    const bool out_bf16 = d_is_bf16 && !p.partial;
-    rc = f32 ? launch_tc_any<float>(bn, out_bf16, tmA, tmB, p, grid, st)
-             : launch_tc_any<__nv_bfloat16>(bn, out_bf16, tmA, tmB, p, grid, st);
+    rc = f32 ? launch_tc_any<float>(bn, out_bf16, tmA, tmB, tmD, p, grid, st)
+             : launch_tc_any<__nv_bfloat16>(bn, out_bf16, tmA, tmB, tmD, p, grid, st);
     if (rc) return rc;
     if (p.partial) {
         const int64_t tot = (int64_t)d.M * d.N;
