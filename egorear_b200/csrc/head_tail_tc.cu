@@ -1,0 +1,200 @@
+// Heatmap-head tail on the tensor cores (EGR_PREC_BF16, shipped geometry 32x32 -> 64x64, C = 128):
+//
+//   hm[j][y][x] = sum_c W[j][c] * relu(up2_bilinear_align_corners(z)[y][x][c]) + b[j]        j < 15
+//
+// (the `nn.Upsample, ReLU, Conv2d(128, 15, 1)` end of conv_heatmap_layers*, egoposeformer_heatmap_mvf_ex.py:108-110,
+// :579-583, with the preceding 1x1 conv commuted in front of the upsample).  The SIMT version spends 16 FMAs per
+// interpolated value on the 1x1 conv; here one CTA = 4 output rows = 256 pixels = two M=128 tcgen05 tiles:
+//   1. the (at most) 4 source rows of z are staged in shared memory (padded pixel stride, conflict-free LDS.128)
+//   2. thread t interpolates pixel t for all 128 channels in fp32, applies ReLU and writes the bf16 row straight
+//      into the K-major SWIZZLE_128B A tile
+//   3. one thread issues 2 x 8 tcgen05.mma (M=128, N=16, K=16) against the bf16 weight tile, accumulators in TMEM
+//   4. tcgen05.ld gives thread t the 16 joint values of pixel t; 32 lanes = 32 consecutive x -> 128 B stores per joint
+#include "layout_ops.cuh"
+#include "tc_ptx.cuh"
+
+namespace egr {
+using namespace tcx;
+namespace {
+
+constexpr int HT_FS = 32, HT_FO = 64, HT_C = 128, HT_STRIP = 4, HT_ROWS = 4, HT_NJ = 16;
+constexpr int HT_PST = 272;                                  // bytes per staged source pixel: 256 + 16
+constexpr int HT_OFF_A = 0;                                  // [2 M-tiles][2 k-blocks][128 rows][128 B] = 64 KB
+constexpr int HT_OFF_W = 2 * 2 * 128 * 128;                  // [2 k-blocks][16 rows][128 B]             =  4 KB
+constexpr int HT_OFF_SRC = HT_OFF_W + 2 * 16 * 128;          // [4 rows x 32 px][272 B]
+constexpr int HT_OFF_BAR = HT_OFF_SRC + HT_ROWS * HT_FS * HT_PST;
+constexpr int HT_SMEM = HT_OFF_BAR + 64 + 1024 /*align*/;
+constexpr uint32_t HT_TMEM_COLS = 32;
+
+struct HtUp {
+    int i0, i1;
+    float l0, l1;
+};
+__device__ __forceinline__ HtUp ht_up(int dst) {
+    // nn.Upsample(scale_factor=2, bilinear, align_corners=True): src = dst * (in-1)/(out-1)
+    const float scale = (float)(HT_FS - 1) / (float)(HT_FO - 1);
+    const float s = scale * (float)dst;
+    HtUp c;
+    c.i0 = (int)s;
+    c.i1 = c.i0 + ((c.i0 < HT_FS - 1) ? 1 : 0);
+    c.l1 = s - (float)c.i0;
+    c.l0 = 1.f - c.l1;
+    return c;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// relu(w00*a + w01*b + w10*c + w11*d) for the two bf16 halves of one 32-bit word each
+__device__ __forceinline__ uint32_t interp_word(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float w00, float w01,
+                                                float w10, float w11) {
+    float lo = w00 * __uint_as_float(a << 16);
+    float hi = w00 * __uint_as_float(a & 0xffff0000u);
+    lo = fmaf(w01, __uint_as_float(b << 16), lo);
+    hi = fmaf(w01, __uint_as_float(b & 0xffff0000u), hi);
+    lo = fmaf(w10, __uint_as_float(c << 16), lo);
+    hi = fmaf(w10, __uint_as_float(c & 0xffff0000u), hi);
+    lo = fmaf(w11, __uint_as_float(d << 16), lo);
+    hi = fmaf(w11, __uint_as_float(d & 0xffff0000u), hi);
+    return pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+}
+
+__global__ void __launch_bounds__(256, 2)
+head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias, int4 wsel,
+                    int B, int J, float* __restrict__ hm, int64_t hm_bs, int64_t hm_gs, __nv_bfloat16* __restrict__ hm_t) {
+    extern __shared__ __align__(1024) uint8_t ht_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ht_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem + HT_OFF_A;
+    uint8_t* sW = smem + HT_OFF_W;
+    uint8_t* sS = smem + HT_OFF_SRC;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + HT_OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+    float* sb = reinterpret_cast<float*>(bar + 2);           // [16]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int y0 = blockIdx.x * HT_STRIP;
+    const int g = blockIdx.y / B, b = blockIdx.y - g * B;
+    const int img = g * B + b;
+    const int sel = (g == 0) ? wsel.x : (g == 1) ? wsel.y : (g == 2) ? wsel.z : wsel.w;
+
+    if (tid == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), HT_TMEM_COLS);
+    if (tid < HT_NJ) sb[tid] = (tid < J) ? __ldg(bias + (int64_t)sel * J + tid) : 0.f;
+    {   // weight tile: fp32 [J][128] -> bf16 [2 k-blocks][16 rows][64], rows >= J zero
+        const int n = tid >> 4, piece = tid & 15;
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (n < J) {
+            const float4* src = reinterpret_cast<const float4*>(w + ((int64_t)sel * J + n) * HT_C + piece * 8);
+            const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
+            u = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f1.z, f1.w));
+        }
+        const int kb = piece >> 3, pp = piece & 7;
+        *reinterpret_cast<uint4*>(sW + kb * 2048 + n * 128 + ((pp ^ (n & 7)) << 4)) = u;
+    }
+    const int sr0 = ht_up(y0).i0;
+    const int nsr = ht_up(y0 + HT_STRIP - 1).i1 - sr0 + 1;
+    {   // source rows [sr0, sr0 + nsr) of this image
+        const uint4* src = reinterpret_cast<const uint4*>(z + ((int64_t)img * HT_FS * HT_FS + (int64_t)sr0 * HT_FS) * HT_C);
+        for (int i = tid; i < nsr * HT_FS * 16; i += 256) {
+            const int px = i >> 4, pc = i & 15;
+            *reinterpret_cast<uint4*>(sS + px * HT_PST + pc * 16) = __ldg(src + i);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- interpolate + ReLU: pixel `tid` -> row (tid & 127) of A tile (tid >> 7) ----
+    const int yy = tid >> 6, x = tid & 63;
+    const int y = y0 + yy;
+    {
+        const HtUp cy = ht_up(y), cx = ht_up(x);
+        const uint8_t* p00 = sS + ((cy.i0 - sr0) * HT_FS + cx.i0) * HT_PST;
+        const uint8_t* p01 = sS + ((cy.i0 - sr0) * HT_FS + cx.i1) * HT_PST;
+        const uint8_t* p10 = sS + ((cy.i1 - sr0) * HT_FS + cx.i0) * HT_PST;
+        const uint8_t* p11 = sS + ((cy.i1 - sr0) * HT_FS + cx.i1) * HT_PST;
+        const float w00 = cy.l0 * cx.l0, w01 = cy.l0 * cx.l1, w10 = cy.l1 * cx.l0, w11 = cy.l1 * cx.l1;
+        const int r = tid & 127;
+        uint8_t* arow = sA + (tid >> 7) * 32768 + r * 128;
+        const int sw = r & 7;
+#pragma unroll 4
+        for (int pc = 0; pc < 16; ++pc) {
+            const uint4 a = *reinterpret_cast<const uint4*>(p00 + pc * 16);
+            const uint4 bb = *reinterpret_cast<const uint4*>(p01 + pc * 16);
+            const uint4 c = *reinterpret_cast<const uint4*>(p10 + pc * 16);
+            const uint4 d = *reinterpret_cast<const uint4*>(p11 + pc * 16);
+            uint4 o;
+            o.x = interp_word(a.x, bb.x, c.x, d.x, w00, w01, w10, w11);
+            o.y = interp_word(a.y, bb.y, c.y, d.y, w00, w01, w10, w11);
+            o.z = interp_word(a.z, bb.z, c.z, d.z, w00, w01, w10, w11);
+            o.w = interp_word(a.w, bb.w, c.w, d.w, w00, w01, w10, w11);
+            *reinterpret_cast<uint4*>(arow + (pc >> 3) * 16384 + (((pc & 7) ^ sw) << 4)) = o;
+        }
+    }
+    fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc(128, HT_NJ, false);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb) {
+                const uint64_t da = make_smem_desc(smem_u32(sA + mt * 32768 + kb * 16384));
+                const uint64_t db = make_smem_desc(smem_u32(sW + kb * 2048));
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    tc_mma<false>(tmem_base + mt * HT_NJ, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+            }
+        tc_commit(smem_u32(bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(bar), 0);
+    tc_fence_after();
+    uint32_t v[16];
+    tc_ld16_issue(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * HT_NJ, v);
+    tc_ld16_wait(v);
+    // thread `tid` now holds the joints of pixel `tid`; lanes = consecutive x
+    float* o = hm + (int64_t)b * hm_bs + (int64_t)g * hm_gs + (int64_t)y * HT_FO + x;
+#pragma unroll
+    for (int j = 0; j < HT_NJ; ++j)
+        if (j < J) o[(int64_t)j * HT_FO * HT_FO] = __uint_as_float(v[j]) + sb[j];
+    if (hm_t) {
+        __nv_bfloat16* ot = hm_t + ((int64_t)img * J) * HT_FO * HT_FO + (int64_t)y * HT_FO + x;
+#pragma unroll
+        for (int j = 0; j < HT_NJ; ++j)
+            if (j < J) ot[(int64_t)j * HT_FO * HT_FO] = __float2bfloat16_rn(__uint_as_float(v[j]) + sb[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, HT_TMEM_COLS);
+    }
+}
+
+}  // namespace
+
+int head_tail_tc(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
+                 int64_t hm_bs, int64_t hm_gs, void* hm_t, cudaStream_t st) {
+    EGR_CHECK(J <= HT_NJ && G <= 4, EGR_ERR_UNSUPPORTED, "head_tail_tc: J=%d G=%d", J, G);
+    static bool attr_set = false;
+    if (!attr_set) {
+        EGR_CUDA_OK(cudaFuncSetAttribute(head_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+        attr_set = true;
+    }
+    dim3 grid(HT_FO / HT_STRIP, G * B);
+    const int4 sel = make_int4(wsel_host[0], wsel_host[1], wsel_host[2], wsel_host[3]);
+    head_tail_tc_kernel<<<grid, 256, HT_SMEM, st>>>((const __nv_bfloat16*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs,
+                                                    (__nv_bfloat16*)hm_t);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
+}  // namespace egr

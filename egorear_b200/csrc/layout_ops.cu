@@ -4,6 +4,8 @@
 
 namespace egr {
 
+extern int g_opt_tc;
+
 struct UpC {
     int i0, i1;
     float l0, l1;
@@ -354,6 +356,8 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st) {
     EGR_CHECK(J <= HJ && (2 * Hs) % STRIP == 0 && G <= 4, EGR_ERR_UNSUPPORTED, "head_up_conv: J=%d Hs=%d G=%d", J, Hs, G);
+    if (Hs == FS && Ws == FS && C == FCH && z_bf16 && g_opt_tc)      // tensor-core tail (head_tail_tc.cu)
+        return head_tail_tc(z, w, bias, wsel_host, B, G, J, hm, hm_bs, hm_gs, hm_t, st);
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;
         const size_t fsmem = sizeof(float) * FCH * HJ + es * FROWS * FS * 130;

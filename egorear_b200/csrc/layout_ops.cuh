@@ -17,6 +17,10 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st);
 
+// the same tail on the tensor cores: bf16 z, 32x32 -> 64x64, C = 128 (head_tail_tc.cu); hm_t bf16
+int head_tail_tc(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
+                 int64_t hm_bs, int64_t hm_gs, void* hm_t, cudaStream_t st);
+
 // R1 tail: z [g][B][Hs*Ws][C] -> relu(up2(z)) written twice:
 //   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output) and
 //   out_nhwc [g][B][4HsWs][C] in the activation dtype (input of the H2 3x3 conv)

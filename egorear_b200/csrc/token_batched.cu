@@ -271,18 +271,22 @@ int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
 tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* __restrict__ pooled, int B, int C) {
+    // hw == 64: a half-warp per channel, one float4 per lane (256 B per channel, coalesced), 4 shuffle steps
     const int g = blockIdx.x / B, b = blockIdx.x - g * B;
     const float* bf = bfb + (int64_t)g * bfb_gs + (int64_t)b * bfb_bs;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = warp; c < C; c += 8) {       // a warp per channel, lanes over the hw positions
-        float s = 0.f;
-        for (int i = lane; i < hw; i += 32) s += bf[(int64_t)c * hw + i];
-        s = warp_sum(s);
-        if (lane == 0) pooled[(int64_t)blockIdx.x * C + c] = round_tf32(s / (float)hw);
+    const int l16 = threadIdx.x & 15, hwarp = threadIdx.x >> 4;
+    const int c0 = blockIdx.y * (C / gridDim.y), c1 = c0 + C / gridDim.y;
+    for (int c = c0 + hwarp; c < c1; c += 16) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(bf + (int64_t)c * hw) + l16);
+        float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (l16 == 0) pooled[(int64_t)blockIdx.x * C + c] = round_tf32(s / (float)hw);
     }
 }
 int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st) {
-    tok_avgpool_kernel<<<G * B, 256, 0, st>>>(bfb, bfb_bs, bfb_gs, hw, pooled, B, C);
+    EGR_CHECK(hw == 64 && C % 64 == 0, EGR_ERR_UNSUPPORTED, "tok_avgpool: hw=%d C=%d (stride-32 map of a 256x256 image is 8x8)", hw, C);
+    tok_avgpool_kernel<<<dim3(G * B, 4), 256, 0, st>>>(bfb, bfb_bs, bfb_gs, hw, pooled, B, C);
     EGR_LAUNCHED();
     return EGR_OK;
 }
