@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=int (egr_set_option), e.g. pdl=0")
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {"mvfex_pose3d": 64, "mvfex": 64, "pose3d": 1024, "generate_target": 8192, "decode": 8192}[args.workload]
@@ -224,6 +225,9 @@ def main():
     rank, local_rank, world = egd.init()
     dev = torch.device("cuda", local_rank)
     lib = _lib.load()
+    for kv in args.opt:
+        k, v = kv.split("=")
+        _lib.check(lib.egr_set_option(k.encode(), int(v)))
     peaks = load_peaks()
     B = args.batch
     act = 2 if args.precision == "bf16" else 4

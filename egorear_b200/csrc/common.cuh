@@ -40,6 +40,39 @@ extern std::atomic<int64_t> g_launches;          // kernels launched by this lib
                                __FILE__, __LINE__);                                                \
     } while (0)
 
+// Programmatic dependent launch (PDL): every hot-path kernel starts with pdl_trigger() (the next kernel of the stream may
+// begin launching: its CTAs become resident and run their prologue as this grid drains) and executes pdl_wait() before its
+// first global-memory access (returns once ALL earlier grids have completed and flushed).  Because every kernel waits
+// before touching memory, ordering is exactly that of plain stream serialisation; only launch latency and prologues
+// (barrier init, TMEM allocation, descriptor prefetch) overlap.  Kernels that allocate TMEM trigger only AFTER their own
+// allocation, so a dependent CTA can never hold TMEM columns that an unfinished primary CTA still needs.
+extern int g_opt_pdl;
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_opt_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+// launch + count + check; a templated kernel name goes in parentheses: EGR_LAUNCH((k<A, B>), grid, block, smem, st, args...)
+#define EGR_LAUNCH(kernel, grid, block, smem, st, ...)                                             \
+    do {                                                                                           \
+        cudaError_t _e = ::egr::launch_k(kernel, dim3(grid), dim3(block), (size_t)(smem), (st), __VA_ARGS__); \
+        ::egr::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+        if (_e == cudaSuccess) _e = cudaGetLastError();                                            \
+        if (_e != cudaSuccess)                                                                     \
+            return ::egr::fail(EGR_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                               __FILE__, __LINE__);                                                \
+    } while (0)
+
 // Stage profiler (bench.py roofline): when enabled, prof_mark(name, stream) records a CUDA event on the launch
 // stream; the time between a mark and the next one is attributed to `name` (nullptr closes the last interval).
 void prof_mark(const char* name, cudaStream_t st);

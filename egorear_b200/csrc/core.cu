@@ -57,6 +57,7 @@ int sm_count() { return g_sm_count; }
 
 // ---- stage profiler ----
 int g_prof_on = 0;
+int g_opt_pdl = 1;
 struct Mark { std::string name; cudaEvent_t ev; bool closing; };
 static std::vector<Mark> g_marks;
 static std::vector<cudaEvent_t> g_ev_pool;

@@ -444,6 +444,7 @@ void note_all(egr_mvfex* h, const Bufs& w, int B, int G) {
 extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "tc") { g_opt_tc = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pose_p2_bf16") { g_opt_pose_p2_bf16 = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "pdl") { g_opt_pdl = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "tok_batched") { g_opt_tok_batched = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }

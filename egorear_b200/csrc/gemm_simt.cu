@@ -29,6 +29,8 @@ __global__ void __launch_bounds__(STHREADS)
 gemm_simt_kernel(GemmDesc d) {
     __shared__ __align__(16) float As[SBK][SBM + 4];
     __shared__ __align__(16) float Bs[SBK][SBN + 4];
+    pdl_trigger();
+    pdl_wait();
 
     const int g = blockIdx.z;
     const TA* A = reinterpret_cast<const TA*>(d.A) + (int64_t)g * d.a_gs;
@@ -159,9 +161,8 @@ gemm_simt_kernel(GemmDesc d) {
 template <typename TA, typename TO>
 static int launch_simt(const GemmDesc& d, cudaStream_t st) {
     dim3 grid(ceil_div(d.M, SBM), ceil_div(d.N, SBN), d.groups);
-    if (d.amode == A_PLAIN) gemm_simt_kernel<TA, TO, A_PLAIN><<<grid, STHREADS, 0, st>>>(d);
-    else gemm_simt_kernel<TA, TO, A_CONV3S2><<<grid, STHREADS, 0, st>>>(d);
-    EGR_LAUNCHED();
+    if (d.amode == A_PLAIN) EGR_LAUNCH((gemm_simt_kernel<TA, TO, A_PLAIN>), grid, STHREADS, 0, st, d);
+    else EGR_LAUNCH((gemm_simt_kernel<TA, TO, A_CONV3S2>), grid, STHREADS, 0, st, d);
     return EGR_OK;
 }
 

@@ -245,6 +245,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();      // after the TMEM allocation (see common.cuh)
+    pdl_wait();         // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -364,6 +366,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename TO>
 __global__ void splitk_finalize_kernel(const float* part, int64_t part_stride, int ksplit, const float* bias, TO* out,
                                        int64_t total, int N, int epi, int round_out) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     float s = 0.f;
@@ -400,8 +404,7 @@ int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64
 
 template <int BN, typename TI, typename TO>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
-    gemm_tc_kernel<BN, TI, TO><<<grid, TC_THREADS, TcCfg<BN>::SMEM, st>>>(tmA, tmB, tmD, p);
-    EGR_LAUNCHED();
+    EGR_LAUNCH((gemm_tc_kernel<BN, TI, TO>), grid, TC_THREADS, TcCfg<BN>::SMEM, st, tmA, tmB, tmD, p);
     return EGR_OK;
 }
 template <int BN, typename TI>
@@ -561,12 +564,11 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         const int64_t tot = (int64_t)d.M * d.N;
         const int blocks = (int)ceil_div64(tot, 256);
         if (d_is_bf16)
-            splitk_finalize_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
-                                                                         reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi, 0);
+            EGR_LAUNCH(splitk_finalize_kernel<__nv_bfloat16>, blocks, 256, 0, st, g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
+                       reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi, 0);
         else
-            splitk_finalize_kernel<float><<<blocks, 256, 0, st>>>(g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
-                                                                  reinterpret_cast<float*>(d.D), tot, d.N, d.epi, d.round_tf32);
-        EGR_LAUNCHED();
+            EGR_LAUNCH(splitk_finalize_kernel<float>, blocks, 256, 0, st, g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
+                       reinterpret_cast<float*>(d.D), tot, d.N, d.epi, d.round_tf32);
     }
     return EGR_OK;
 }

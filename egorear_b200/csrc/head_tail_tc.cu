@@ -72,7 +72,7 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + HT_OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
     float* sb = reinterpret_cast<float*>(bar + 2);           // [16]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int y0 = blockIdx.x * HT_STRIP;
     const int g = blockIdx.y / B, b = blockIdx.y - g * B;
     const int img = g * B + b;
@@ -82,7 +82,11 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
         mbar_init(smem_u32(bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), HT_TMEM_COLS);
+    if (warp == 0) {
+        tmem_alloc(smem_u32(tmem_slot), HT_TMEM_COLS);
+        pdl_trigger();          // only after this CTA owns its TMEM columns (common.cuh)
+    }
+    pdl_wait();
     if (tid < HT_NJ) sb[tid] = (tid < J) ? __ldg(bias + (int64_t)sel * J + tid) : 0.f;
     {   // weight tile: fp32 [J][128] -> bf16 [2 k-blocks][16 rows][64], rows >= J zero
         const int n = tid >> 4, piece = tid & 15;
@@ -191,9 +195,8 @@ int head_tail_tc(const void* z, const float* w, const float* bias, const int* ws
     }
     dim3 grid(HT_FO / HT_STRIP, G * B);
     const int4 sel = make_int4(wsel_host[0], wsel_host[1], wsel_host[2], wsel_host[3]);
-    head_tail_tc_kernel<<<grid, 256, HT_SMEM, st>>>((const __nv_bfloat16*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs,
-                                                    (__nv_bfloat16*)hm_t);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(head_tail_tc_kernel, grid, 256, HT_SMEM, st, (const __nv_bfloat16*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs,
+               (__nv_bfloat16*)hm_t);
     return EGR_OK;
 }
 

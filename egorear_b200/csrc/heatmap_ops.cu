@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32)
 decode_argmax_kernel(const float* __restrict__ hm, int64_t n_hm, int HW, int W, float inv_w, float inv_h,
                      int H, float threshold, int normalize, float* __restrict__ preds,
                      float* __restrict__ maxvals, uint8_t* __restrict__ valid, int32_t* __restrict__ idx_out) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_v4 = HW >> 2;
@@ -180,6 +182,8 @@ heatmap_head_1x1_kernel(const float* __restrict__ feat, const float* __restrict_
 
 __global__ void pack_joints_kernel(const float* __restrict__ p2, const float* __restrict__ p3, int B, int n2, int n3,
                                    float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
     const int row = n2 + n3;
     const int64_t total = (int64_t)B * row;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -270,9 +274,8 @@ extern "C" int egr_decode_argmax(const float* hm, int64_t N, int J, int H, int W
     const int64_t n_hm = N * J;
     const int64_t want = ceil_div64(n_hm, DEC_WARPS);
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
-    decode_argmax_kernel<<<grid, DEC_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        hm, n_hm, H * W, W, 1.f / W, 1.f / H, H, threshold, normalize, preds, maxvals, valid, idx);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(decode_argmax_kernel, grid, DEC_WARPS * 32, 0, (cudaStream_t)stream,
+               hm, n_hm, H * W, W, 1.f / W, 1.f / H, H, threshold, normalize, preds, maxvals, valid, idx);
     return EGR_OK;
 }
 
@@ -297,7 +300,6 @@ extern "C" int egr_pack_joints(const float* preds2d, const float* pose3d, int B,
     if (int rc = require_device()) return rc;
     if (B == 0) return EGR_OK;
     const int64_t total = (int64_t)B * (n2d + n3d);
-    pack_joints_kernel<<<(int)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream>>>(preds2d, pose3d, B, n2d, n3d, packed);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(pack_joints_kernel, (int)ceil_div64(total, 256), 256, 0, (cudaStream_t)stream, preds2d, pose3d, B, n2d, n3d, packed);
     return EGR_OK;
 }

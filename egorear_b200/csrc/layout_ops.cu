@@ -29,6 +29,8 @@ template <typename T, bool RND>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int V, int C, int HW) {
     extern __shared__ float tile[];   // [C][33]
+    pdl_trigger();
+    pdl_wait();
     const int p0 = blockIdx.x * 32;
     const int bv = blockIdx.y;        // b * V + v
     const int b = bv / V, v = bv - b * V;
@@ -48,10 +50,9 @@ int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int ou
     EGR_CHECK(HW % 32 == 0 && C * 33 * 4 <= 48 * 1024, EGR_ERR_UNSUPPORTED, "nchw_to_nhwc: HW=%d C=%d", HW, C);
     dim3 grid(HW / 32, B * V);
     const size_t smem = sizeof(float) * C * 33;
-    if (out_mode == 1) nchw_to_nhwc_kernel<__nv_bfloat16, false><<<grid, 256, smem, st>>>(in, (__nv_bfloat16*)out, B, V, C, HW);
-    else if (out_mode == 2) nchw_to_nhwc_kernel<float, true><<<grid, 256, smem, st>>>(in, (float*)out, B, V, C, HW);
-    else nchw_to_nhwc_kernel<float, false><<<grid, 256, smem, st>>>(in, (float*)out, B, V, C, HW);
-    EGR_LAUNCHED();
+    if (out_mode == 1) EGR_LAUNCH((nchw_to_nhwc_kernel<__nv_bfloat16, false>), grid, 256, smem, st, in, (__nv_bfloat16*)out, B, V, C, HW);
+    else if (out_mode == 2) EGR_LAUNCH((nchw_to_nhwc_kernel<float, true>), grid, 256, smem, st, in, (float*)out, B, V, C, HW);
+    else EGR_LAUNCH((nchw_to_nhwc_kernel<float, false>), grid, 256, smem, st, in, (float*)out, B, V, C, HW);
     return EGR_OK;
 }
 
@@ -196,6 +197,7 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
     TZ* s1 = reinterpret_cast<TZ*>(fsm);                   // [FROWS*FS px][FCH]   as loaded
     TZ* s2 = s1 + FROWS * FS * FCH;                        // [FCH][SLD]           transposed
     __shared__ UpTab tab;
+    pdl_trigger();
     const int y0 = blockIdx.x * FSTRIP;
     const int g = blockIdx.y / B, b = blockIdx.y - g * B;
     const int img = g * B + b;
@@ -203,6 +205,7 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
     const int nsr = upc(y0 + FSTRIP - 1, FS).i1 - sr0 + 1;
     const int npix = nsr * FS;
     build_uptab(&tab);
+    pdl_wait();
     {
         const uint4* src = reinterpret_cast<const uint4*>(z + ((int64_t)img * FS * FS + (int64_t)sr0 * FS) * FCH);
         uint4* dst = reinterpret_cast<uint4*>(s1);
@@ -444,13 +447,12 @@ int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C
         if (z_bf16) {
             auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k<<<fgrid, 256, fsmem, st>>>((const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc, out_nhwc_tf32);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc, out_nhwc_tf32);
         } else {
             auto k = up2_relu_dual_fast_kernel<float>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            k<<<fgrid, 256, fsmem, st>>>((const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc, out_nhwc_tf32);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc, out_nhwc_tf32);
         }
-        EGR_LAUNCHED();
         return EGR_OK;
     }
     EGR_CHECK(!out_nhwc_tf32, EGR_ERR_UNSUPPORTED, "up2_relu_dual: the TF32 channels-last export needs the 32x32x128 geometry");
@@ -495,6 +497,8 @@ template <> struct Vec16<__nv_bfloat16> {
 template <typename T>
 __global__ void maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t total_vec, int H, int W, int C) {
     constexpr int VN = Vec16<T>::N;
+    pdl_trigger();
+    pdl_wait();
     const int Ho = H >> 1, Wo = W >> 1, CV = C / VN;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
         const int cv = (int)(i % CV);
@@ -514,9 +518,8 @@ int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, 
     const int64_t total = n_img * (H / 2) * (W / 2) * (C / vn);
     if (total == 0) return EGR_OK;
     const int grid = (int)(ceil_div64(total, 256) < 148 * 32 ? ceil_div64(total, 256) : 148 * 32);
-    if (is_bf16) maxpool2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C);
-    else maxpool2_kernel<float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, total, H, W, C);
-    EGR_LAUNCHED();
+    if (is_bf16) EGR_LAUNCH(maxpool2_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C);
+    else EGR_LAUNCH(maxpool2_kernel<float>, grid, 256, 0, st, (const float*)in, (float*)out, total, H, W, C);
     return EGR_OK;
 }
 

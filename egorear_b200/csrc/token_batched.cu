@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(256)
 tok_sample_kernel(TokSampleArgs a) {
     constexpr int NH = TOK_NH, P = TOK_P, HD = E / NH, RAWC = TOK_RAWC;
     constexpr int EX = HAS_PTAB ? E : NH;
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t unit = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int64_t total = (int64_t)a.G * a.B * a.J * a.V * NH;
@@ -89,13 +91,12 @@ int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st) {
     const int64_t total = (int64_t)a.G * a.B * a.J * a.V * TOK_NH;
     const int blocks = (int)ceil_div64(total, 8);
     if (ptab) {
-        if (act_bf16) tok_sample_kernel<__nv_bfloat16, true, 256><<<blocks, 256, 0, st>>>(a);
-        else tok_sample_kernel<float, true, 256><<<blocks, 256, 0, st>>>(a);
+        if (act_bf16) EGR_LAUNCH((tok_sample_kernel<__nv_bfloat16, true, 256>), blocks, 256, 0, st, a);
+        else EGR_LAUNCH((tok_sample_kernel<float, true, 256>), blocks, 256, 0, st, a);
     } else {
-        if (act_bf16) tok_sample_kernel<__nv_bfloat16, false, 128><<<blocks, 256, 0, st>>>(a);
-        else tok_sample_kernel<float, false, 128><<<blocks, 256, 0, st>>>(a);
+        if (act_bf16) EGR_LAUNCH((tok_sample_kernel<__nv_bfloat16, false, 128>), blocks, 256, 0, st, a);
+        else EGR_LAUNCH((tok_sample_kernel<float, false, 128>), blocks, 256, 0, st, a);
     }
-    EGR_LAUNCHED();
     return EGR_OK;
 }
 
@@ -107,6 +108,8 @@ __global__ void __launch_bounds__(128)
 tok_attn_kernel(const float* __restrict__ qkv, float* __restrict__ o, int J) {
     constexpr int NH = TOK_NH, HD = E / NH, LD = HD + 1, MJ = 16;
     extern __shared__ float sm[];
+    pdl_trigger();
+    pdl_wait();
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* q = sm + h * (3 * MJ * LD + MJ * MJ);
     float* k = q + MJ * LD;
@@ -164,13 +167,12 @@ int tok_attn(const float* qkv, float* o, int n_frames, int J, int E, cudaStream_
     if (E == 256) {
         auto kfn = tok_attn_kernel<256>;
         EGR_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kfn<<<n_frames, 128, smem, st>>>(qkv, o, J);
+        EGR_LAUNCH(kfn, n_frames, 128, smem, st, qkv, o, J);
     } else {
         auto kfn = tok_attn_kernel<128>;
         EGR_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kfn<<<n_frames, 128, smem, st>>>(qkv, o, J);
+        EGR_LAUNCH(kfn, n_frames, 128, smem, st, qkv, o, J);
     }
-    EGR_LAUNCHED();
     return EGR_OK;
 }
 
@@ -193,6 +195,8 @@ template <int E>
 __global__ void __launch_bounds__(256)
 tok_add_ln_kernel(const float* __restrict__ res, const float* __restrict__ z, float* __restrict__ out, int64_t rows,
                   int rows_per_group, const float* const* __restrict__ gamma, const float* const* __restrict__ beta) {
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -218,10 +222,9 @@ int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per
                const float* const* beta, cudaStream_t st) {
     const int64_t rows = (int64_t)G * rows_per_group;
     const int blocks = (int)ceil_div64(rows, 8);
-    if (E == 256) tok_add_ln_kernel<256><<<blocks, 256, 0, st>>>(res, z, out, rows, rows_per_group, gamma, beta);
-    else if (E == 128) tok_add_ln_kernel<128><<<blocks, 256, 0, st>>>(res, z, out, rows, rows_per_group, gamma, beta);
+    if (E == 256) EGR_LAUNCH(tok_add_ln_kernel<256>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta);
+    else if (E == 128) EGR_LAUNCH(tok_add_ln_kernel<128>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta);
     else return fail(EGR_ERR_UNSUPPORTED, "tok_add_ln: E=%d", E);
-    EGR_LAUNCHED();
     return EGR_OK;
 }
 
@@ -232,6 +235,8 @@ tok_ln_image_kernel(const float* __restrict__ x, T* __restrict__ xT, int B, int 
                     const float* const* __restrict__ beta) {
     constexpr int E = 256;
     __shared__ float ys[16 * E];
+    pdl_trigger();
+    pdl_wait();
     const int g = blockIdx.x / B;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float* xin = x + (int64_t)blockIdx.x * J * E;
@@ -260,9 +265,8 @@ tok_ln_image_kernel(const float* __restrict__ x, T* __restrict__ xT, int B, int 
 int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int E, const float* const* gamma,
                  const float* const* beta, cudaStream_t st) {
     EGR_CHECK(E == 256 && J <= 16, EGR_ERR_UNSUPPORTED, "tok_ln_image: E=%d J=%d", E, J);
-    if (xT_bf16) tok_ln_image_kernel<__nv_bfloat16><<<G * B, 256, 0, st>>>(x, (__nv_bfloat16*)xT, B, J, gamma, beta);
-    else tok_ln_image_kernel<float><<<G * B, 256, 0, st>>>(x, (float*)xT, B, J, gamma, beta);
-    EGR_LAUNCHED();
+    if (xT_bf16) EGR_LAUNCH(tok_ln_image_kernel<__nv_bfloat16>, G * B, 256, 0, st, x, (__nv_bfloat16*)xT, B, J, gamma, beta);
+    else EGR_LAUNCH(tok_ln_image_kernel<float>, G * B, 256, 0, st, x, (float*)xT, B, J, gamma, beta);
     return EGR_OK;
 }
 
@@ -272,6 +276,8 @@ int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int
 __global__ void __launch_bounds__(256)
 tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* __restrict__ pooled, int B, int C) {
     // hw == 64: a half-warp per channel, one float4 per lane (256 B per channel, coalesced), 4 shuffle steps
+    pdl_trigger();
+    pdl_wait();
     const int g = blockIdx.x / B, b = blockIdx.x - g * B;
     const float* bf = bfb + (int64_t)g * bfb_gs + (int64_t)b * bfb_bs;
     const int l16 = threadIdx.x & 15, hwarp = threadIdx.x >> 4;
@@ -286,14 +292,15 @@ tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs
 }
 int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st) {
     EGR_CHECK(hw == 64 && C % 64 == 0, EGR_ERR_UNSUPPORTED, "tok_avgpool: hw=%d C=%d (stride-32 map of a 256x256 image is 8x8)", hw, C);
-    tok_avgpool_kernel<<<dim3(G * B, 4), 256, 0, st>>>(bfb, bfb_bs, bfb_gs, hw, pooled, B, C);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(tok_avgpool_kernel, dim3(G * B, 4), 256, 0, st, bfb, bfb_bs, bfb_gs, hw, pooled, B, C);
     return EGR_OK;
 }
 
 __global__ void __launch_bounds__(256)
 tok_add_query_kernel(const float* __restrict__ y0, const float* __restrict__ vb, const float* const* __restrict__ jq,
                      float* __restrict__ x0, int B, int J, int E) {
+    pdl_trigger();
+    pdl_wait();
     const int g = blockIdx.x / B;
     const float* q = jq[g];
     const int64_t base = (int64_t)blockIdx.x * J * E;
@@ -303,8 +310,7 @@ tok_add_query_kernel(const float* __restrict__ y0, const float* __restrict__ vb,
     }
 }
 int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st) {
-    tok_add_query_kernel<<<G * B, 256, 0, st>>>(y0, vb, jq, x0, B, J, E);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(tok_add_query_kernel, G * B, 256, 0, st, y0, vb, jq, x0, B, J, E);
     return EGR_OK;
 }
 
@@ -315,6 +321,8 @@ __global__ void __launch_bounds__(128)
 pose_query0_kernel(PoseQueryArgs a) {
     constexpr int E = 128, MJ = 16;
     __shared__ float s_p3[MJ * 4];
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x, tid = threadIdx.x, J = a.J;
     if (tid < J) {
         const int j = tid;
@@ -367,13 +375,14 @@ pose_query0_kernel(PoseQueryArgs a) {
 
 int pose_query0(const PoseQueryArgs& a, cudaStream_t st) {
     EGR_CHECK(a.E == 128 && a.J <= 16 && a.V <= 4, EGR_ERR_UNSUPPORTED, "pose_query0: E=%d J=%d V=%d", a.E, a.J, a.V);
-    pose_query0_kernel<<<a.B, 128, 0, st>>>(a);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(pose_query0_kernel, a.B, 128, 0, st, a);
     return EGR_OK;
 }
 
 __global__ void pose_reg_out_kernel(const float* __restrict__ r, const float* __restrict__ w2_T, const float* __restrict__ b2,
                                     const float* __restrict__ p3, float* __restrict__ preds, int T, int E) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= T * 3) return;
     const int t = i / 3, c = i - t * 3;
@@ -383,8 +392,7 @@ __global__ void pose_reg_out_kernel(const float* __restrict__ r, const float* __
 }
 
 int pose_reg_out(const float* r, const float* w2_T, const float* b2, const float* p3, float* preds, int T, int E, cudaStream_t st) {
-    pose_reg_out_kernel<<<ceil_div(T * 3, 128), 128, 0, st>>>(r, w2_T, b2, p3, preds, T, E);
-    EGR_LAUNCHED();
+    EGR_LAUNCH(pose_reg_out_kernel, ceil_div(T * 3, 128), 128, 0, st, r, w2_T, b2, p3, preds, T, E);
     return EGR_OK;
 }
 
