@@ -87,6 +87,23 @@ template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bflo
     for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
 }
 
+// 8 consecutive elements of TO as loaded (the ADDUP epilogue keeps gathers in flight in this raw form)
+template <typename TO> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 u;
+    __device__ __forceinline__ void ld(const __nv_bfloat16* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void unpack(float* v) const {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+};
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void ld(const float* p) { a = __ldg(reinterpret_cast<const float4*>(p)); b = __ldg(reinterpret_cast<const float4*>(p) + 1); }
+    __device__ __forceinline__ void unpack(float* v) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
+
 struct TileCoord { int g, mt, nt, ks; };
 __device__ __forceinline__ TileCoord decode_tile(int t, const TcParams& p) {
     TileCoord c;
@@ -142,6 +159,18 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
         uint32_t (&cur)[32] = v[c & 1];
+        // ADDUP: the 4 bilinear sources of the chunk's columns are gathered (L2) while the TMEM load is in flight;
+        // bf16 keeps the whole chunk in flight (16 x 16 B), fp32 one 8-column group at a time
+        constexpr int PF = (EPI == EPI_RELU_ADDUP) ? ((OUT_B == 2) ? 4 : 1) : 1;
+        Raw8<TO> ax[PF][4];
+        if (EPI == EPI_RELU_ADDUP && PF == 4 && row_ok) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                const int col = n_base + c * 32 + gq * 8;
+                ax[gq][0].ld(aux + (int64_t)src00 * p.N + col); ax[gq][1].ld(aux + (int64_t)src01 * p.N + col);
+                ax[gq][2].ld(aux + (int64_t)src10 * p.N + col); ax[gq][3].ld(aux + (int64_t)src11 * p.N + col);
+            }
+        }
         tc_ld32_wait(cur);
         if (c + 1 < NCH) {
             tc_ld32_issue(taddr + (c + 1) * 32, v[(c + 1) & 1]);
@@ -178,10 +207,13 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
             if (EPI == EPI_RELU_ADDUP) {
                 if (row_ok) {
                     float a00[8], a01[8], a10[8], a11[8];
-                    load8<TO>(aux + (int64_t)src00 * p.N + n0 + j, a00);
-                    load8<TO>(aux + (int64_t)src01 * p.N + n0 + j, a01);
-                    load8<TO>(aux + (int64_t)src10 * p.N + n0 + j, a10);
-                    load8<TO>(aux + (int64_t)src11 * p.N + n0 + j, a11);
+                    constexpr int PFI = (PF == 4) ? 1 : 0;
+                    const int gq = PFI * (j / 8);
+                    if (PF == 1) {
+                        ax[0][0].ld(aux + (int64_t)src00 * p.N + n0 + j); ax[0][1].ld(aux + (int64_t)src01 * p.N + n0 + j);
+                        ax[0][2].ld(aux + (int64_t)src10 * p.N + n0 + j); ax[0][3].ld(aux + (int64_t)src11 * p.N + n0 + j);
+                    }
+                    ax[gq][0].unpack(a00); ax[gq][1].unpack(a01); ax[gq][2].unpack(a10); ax[gq][3].unpack(a11);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
@@ -467,17 +499,39 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
 
     const int nsm = sm_count();
     const int m_tiles = ceil_div(d.M, BM);
-    int bn = 64;
+    const int kb_total = d.K / BK;
+    const bool can_split = d.epi != EPI_RELU_ADDUP && d.groups == 1 && d.ldd == d.N && kb_total >= 32;
+    auto split_of = [&](int64_t base_tiles) {      // deterministic split-K factor for a skinny problem (1 = none)
+        if (!can_split || base_tiles * 4 > nsm) return 1;
+        int ks = (int)(nsm / base_tiles);
+        if (ks > kb_total / 8) ks = kb_total / 8;
+        while (ks > 1 && (int64_t)d.M * d.N * ks > SPLITK_SCRATCH_FLOATS) --ks;
+        if (ks < 1) ks = 1;
+        const int per = ceil_div(kb_total, ks);
+        return ceil_div(kb_total, per);
+    };
+    // tile width: the widest BN whose tile list fills the SMs; for problems too small for that, the BN whose
+    // (tiles x split-K) CTA count is largest, wider first (fewer re-reads of A, more weight bytes in flight per SM)
+    int bn = 0;
     const int cands[3] = {256, 128, 64};
     for (int c : cands) {
         if (d.N % c) continue;
-        const int64_t tiles = (int64_t)d.groups * m_tiles * (d.N / c);
-        if (tiles >= nsm || c == 64) { bn = c; break; }
+        if ((int64_t)d.groups * m_tiles * (d.N / c) >= nsm) { bn = c; break; }
+    }
+    if (!bn) {
+        int64_t best = -1;
+        for (int c : cands) {
+            if (d.N % c) continue;
+            const int64_t base = (int64_t)d.groups * m_tiles * (d.N / c);
+            int64_t ctas = base * split_of(base);
+            if (ctas > nsm) ctas = nsm;
+            if (ctas > best) { best = ctas; bn = c; }
+        }
     }
     TcParams p{};
     p.M = d.M; p.N = d.N; p.K = d.K;
     p.m_tiles = m_tiles; p.n_tiles = d.N / bn; p.groups = d.groups;
-    p.kb_total = d.K / BK;
+    p.kb_total = kb_total;
     p.ksplit = 1; p.kb_per_split = p.kb_total;
     p.amode = d.amode; p.epi = d.epi; p.round_out = d.round_tf32;
     p.bias = d.bias; p.b_gs = d.b_gs;
@@ -487,18 +541,13 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
     // deterministic split-K for skinny problems (pose3d Linear(32768 -> 2048) at small batch): partial sums go to a
     // library-owned scratch [ks][M][N], a finalize kernel adds them in a fixed order and applies bias + activation
     const int64_t base_tiles = (int64_t)d.groups * m_tiles * p.n_tiles;
-    if (d.epi != EPI_RELU_ADDUP && d.groups == 1 && d.ldd == d.N && base_tiles * 4 <= nsm && p.kb_total >= 32) {
-        const int64_t span = (int64_t)d.M * d.N;
-        int ks = (int)(nsm / base_tiles);
-        if (ks > p.kb_total / 8) ks = p.kb_total / 8;
-        while (ks > 1 && span * ks > SPLITK_SCRATCH_FLOATS) --ks;
-        if (ks > 1) {
-            p.kb_per_split = ceil_div(p.kb_total, ks);
-            p.ksplit = ceil_div(p.kb_total, p.kb_per_split);
-            p.partial = 1;
-            p.part_stride = span;
-            p.D = g_splitk_scratch;
-        }
+    const int ks = split_of(base_tiles);
+    if (ks > 1) {
+        p.kb_per_split = ceil_div(p.kb_total, ks);
+        p.ksplit = ks;
+        p.partial = 1;
+        p.part_stride = (int64_t)d.M * d.N;
+        p.D = g_splitk_scratch;
     }
 
     // ---- tensor maps ----
