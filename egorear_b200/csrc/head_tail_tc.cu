@@ -42,6 +42,23 @@ __device__ __forceinline__ HtUp ht_up(int dst) {
     return c;
 }
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+// relu folded into the conversion
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -58,7 +75,7 @@ __device__ __forceinline__ uint32_t interp_word(uint32_t a, uint32_t b, uint32_t
     hi = fmaf(w10, __uint_as_float(c & 0xffff0000u), hi);
     lo = fmaf(w11, __uint_as_float(d << 16), lo);
     hi = fmaf(w11, __uint_as_float(d & 0xffff0000u), hi);
-    return pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+    return pack_relu_bf16x2(lo, hi);
 }
 
 __global__ void __launch_bounds__(256, 2)
@@ -103,11 +120,14 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
     const int nsr = ht_up(y0 + HT_STRIP - 1).i1 - sr0 + 1;
     {   // source rows [sr0, sr0 + nsr) of this image
         const uint4* src = reinterpret_cast<const uint4*>(z + ((int64_t)img * HT_FS * HT_FS + (int64_t)sr0 * HT_FS) * HT_C);
+        const uint32_t sS32 = smem_u32(sS);
         for (int i = tid; i < nsr * HT_FS * 16; i += 256) {
             const int px = i >> 4, pc = i & 15;
-            *reinterpret_cast<uint4*>(sS + px * HT_PST + pc * 16) = __ldg(src + i);
+            cp_async16(sS32 + px * HT_PST + pc * 16, src + i);
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -118,26 +138,25 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
     const int y = y0 + yy;
     {
         const HtUp cy = ht_up(y), cx = ht_up(x);
-        const uint8_t* p00 = sS + ((cy.i0 - sr0) * HT_FS + cx.i0) * HT_PST;
-        const uint8_t* p01 = sS + ((cy.i0 - sr0) * HT_FS + cx.i1) * HT_PST;
-        const uint8_t* p10 = sS + ((cy.i1 - sr0) * HT_FS + cx.i0) * HT_PST;
-        const uint8_t* p11 = sS + ((cy.i1 - sr0) * HT_FS + cx.i1) * HT_PST;
+        const uint32_t sS32 = smem_u32(sS);
+        const uint32_t p00 = sS32 + ((cy.i0 - sr0) * HT_FS + cx.i0) * HT_PST;
+        const uint32_t p01 = sS32 + ((cy.i0 - sr0) * HT_FS + cx.i1) * HT_PST;
+        const uint32_t p10 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i0) * HT_PST;
+        const uint32_t p11 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i1) * HT_PST;
         const float w00 = cy.l0 * cx.l0, w01 = cy.l0 * cx.l1, w10 = cy.l1 * cx.l0, w11 = cy.l1 * cx.l1;
         const int r = tid & 127;
-        uint8_t* arow = sA + (tid >> 7) * 32768 + r * 128;
+        const uint32_t arow = smem_u32(sA) + (tid >> 7) * 32768 + r * 128;
         const int sw = r & 7;
-#pragma unroll 4
+#pragma unroll
         for (int pc = 0; pc < 16; ++pc) {
-            const uint4 a = *reinterpret_cast<const uint4*>(p00 + pc * 16);
-            const uint4 bb = *reinterpret_cast<const uint4*>(p01 + pc * 16);
-            const uint4 c = *reinterpret_cast<const uint4*>(p10 + pc * 16);
-            const uint4 d = *reinterpret_cast<const uint4*>(p11 + pc * 16);
+            const uint4 a = lds128(p00 + pc * 16), bb = lds128(p01 + pc * 16);
+            const uint4 c = lds128(p10 + pc * 16), d = lds128(p11 + pc * 16);
             uint4 o;
             o.x = interp_word(a.x, bb.x, c.x, d.x, w00, w01, w10, w11);
             o.y = interp_word(a.y, bb.y, c.y, d.y, w00, w01, w10, w11);
             o.z = interp_word(a.z, bb.z, c.z, d.z, w00, w01, w10, w11);
             o.w = interp_word(a.w, bb.w, c.w, d.w, w00, w01, w10, w11);
-            *reinterpret_cast<uint4*>(arow + (pc >> 3) * 16384 + (((pc & 7) ^ sw) << 4)) = o;
+            sts128(arow + (pc >> 3) * 16384 + (((pc & 7) ^ sw) << 4), o);
         }
     }
     fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
@@ -165,15 +184,22 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
     tc_ld16_issue(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * HT_NJ, v);
     tc_ld16_wait(v);
     // thread `tid` now holds the joints of pixel `tid`; lanes = consecutive x
+    float r[HT_NJ];
+#pragma unroll
+    for (int j4 = 0; j4 < HT_NJ; j4 += 4) {
+        const uint4 bq = lds128(smem_u32(sb + j4));
+        r[j4 + 0] = __uint_as_float(v[j4 + 0]) + __uint_as_float(bq.x); r[j4 + 1] = __uint_as_float(v[j4 + 1]) + __uint_as_float(bq.y);
+        r[j4 + 2] = __uint_as_float(v[j4 + 2]) + __uint_as_float(bq.z); r[j4 + 3] = __uint_as_float(v[j4 + 3]) + __uint_as_float(bq.w);
+    }
     float* o = hm + (int64_t)b * hm_bs + (int64_t)g * hm_gs + (int64_t)y * HT_FO + x;
 #pragma unroll
     for (int j = 0; j < HT_NJ; ++j)
-        if (j < J) o[(int64_t)j * HT_FO * HT_FO] = __uint_as_float(v[j]) + sb[j];
+        if (j < J) o[(int64_t)j * HT_FO * HT_FO] = r[j];
     if (hm_t) {
         __nv_bfloat16* ot = hm_t + ((int64_t)img * J) * HT_FO * HT_FO + (int64_t)y * HT_FO + x;
 #pragma unroll
         for (int j = 0; j < HT_NJ; ++j)
-            if (j < J) ot[(int64_t)j * HT_FO * HT_FO] = __float2bfloat16_rn(__uint_as_float(v[j]) + sb[j]);
+            if (j < J) ot[(int64_t)j * HT_FO * HT_FO] = __float2bfloat16_rn(r[j]);
     }
     tc_fence_before();
     __syncthreads();

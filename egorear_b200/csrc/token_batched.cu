@@ -5,16 +5,36 @@ namespace egr {
 
 // =====================================================================================================
 // deformable sampling: one warp per (group, frame, joint, view, head)
+//
+// Lanes 0-15 each own one of the head's 16 points: softmax of the logits, the 4 bilinear corners (flat index, attention
+// x bilinear weight, 0 for out-of-map corners) -> 64 (index, weight) pairs in shared memory.  The gather is branch-free
+// (indices are clamped in-map, a zero weight contributes exactly 0) and split over the half-warps: each half takes every
+// other corner, a lane loads 16 B = 8 of the 128 raw channels (and 8 B of the head's 64 position-table channels), so a
+// warp-level load covers two corners and 16 corner loads are in flight per lane.  Halves are summed with one shuffle.
 // =====================================================================================================
-template <typename T, bool HAS_PTAB, int E>
-__global__ void __launch_bounds__(256)
+// volatile: the batch of gathers is issued back to back, ahead of the arithmetic that consumes it
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+template <bool HAS_PTAB, int E>
+__global__ void __launch_bounds__(256, 4)
 tok_sample_kernel(TokSampleArgs a) {
     constexpr int NH = TOK_NH, P = TOK_P, HD = E / NH, RAWC = TOK_RAWC;
     constexpr int EX = HAS_PTAB ? E : NH;
+    static_assert(P == 16 && RAWC == 128 && (!HAS_PTAB || HD == 64), "lane mapping");
+    __shared__ uint2 s_pairs[8][P * 4];
     pdl_trigger();
     pdl_wait();
-    const int lane = threadIdx.x & 31;
-    const int64_t unit = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t unit = (int64_t)blockIdx.x * 8 + wib;
     const int64_t total = (int64_t)a.G * a.B * a.J * a.V * NH;
     if (unit >= total) return;
     int64_t r = unit;
@@ -44,59 +64,81 @@ tok_sample_kernel(TokSampleArgs a) {
     const float e = (lane < P) ? expf(logit - m) : 0.f;
     const float inv = 1.f / warp_sum(e);
     const float aw = e * inv;
-    // loc = anchor + offset / (W, H)   (deform_attn.py:133-139), corners as in mmcv's kernel
-    const float ax = a.anchors[(((int64_t)b * a.V + v) * a.J + j) * 2 + 0];
-    const float ay = a.anchors[(((int64_t)b * a.V + v) * a.J + j) * 2 + 1];
-    const float lx = ax + oa[h * P * 2 + p * 2 + 0] / (float)a.W;
-    const float ly = ay + oa[h * P * 2 + p * 2 + 1] / (float)a.H;
-    const Corners c = msda_corners(lx, ly, a.H, a.W);
-    float cw[4];
+    if (lane < P) {
+        // loc = anchor + offset / (W, H)   (deform_attn.py:133-139), corners as in mmcv's kernel
+        const float ax = a.anchors[(((int64_t)b * a.V + v) * a.J + j) * 2 + 0];
+        const float ay = a.anchors[(((int64_t)b * a.V + v) * a.J + j) * 2 + 1];
+        const float lx = ax + oa[h * P * 2 + p * 2 + 0] / (float)a.W;
+        const float ly = ay + oa[h * P * 2 + p * 2 + 1] / (float)a.H;
+        const Corners c = msda_corners(lx, ly, a.H, a.W);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) cw[q] = aw * c.w[q];
+        for (int q = 0; q < 4; ++q) s_pairs[wib][p * 4 + q] = make_uint2((uint32_t)c.idx[q], __float_as_uint(aw * c.w[q]));
+    }
+    __syncwarp();
 
+    const int half = lane >> 4, l16 = lane & 15;
     const int64_t HW = (int64_t)a.H * a.W;
-    const T* Xb = reinterpret_cast<const T*>(a.X) + ((int64_t)v * a.B + b) * HW * RAWC + lane * 4;
-    const __nv_bfloat16* pt = HAS_PTAB ? (a.ptab[g] + (int64_t)v * HW * E + h * HD + lane * 2) : nullptr;
-    float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float2 e2 = make_float2(0.f, 0.f);
+    const __nv_bfloat16* Xb = reinterpret_cast<const __nv_bfloat16*>(a.X) + ((int64_t)v * a.B + b) * HW * RAWC + l16 * 8;
+    const __nv_bfloat16* pt = HAS_PTAB ? (a.ptab[g] + (int64_t)v * HW * E + h * HD + l16 * 4) : nullptr;
+    float s8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float e4[4] = {0.f, 0.f, 0.f, 0.f};
     float wsum = 0.f;
-#pragma unroll 4
-    for (int pp = 0; pp < P; ++pp) {
+    constexpr int UN = 8;                 // corner loads in flight per lane
+#pragma unroll 1
+    for (int i0 = 0; i0 < P * 2; i0 += UN) {
+        uint4 x[UN];
+        uint2 pu[UN];
+        float cf[UN];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float coef = __shfl_sync(0xffffffffu, cw[q], pp);
-            const int idx = __shfl_sync(0xffffffffu, c.idx[q], pp);
-            if (coef == 0.f) continue;                       // out-of-map corner / point: contributes exactly 0
-            const float4 x = ldg4<T>(Xb + (int64_t)idx * RAWC);
-            s4.x = fmaf(coef, x.x, s4.x); s4.y = fmaf(coef, x.y, s4.y);
-            s4.z = fmaf(coef, x.z, s4.z); s4.w = fmaf(coef, x.w, s4.w);
+        for (int u = 0; u < UN; ++u) {
+            const uint2 pr = s_pairs[wib][2 * (i0 + u) + half];
+            cf[u] = __uint_as_float(pr.y);
+            x[u] = ldg_nc_v4(Xb + (int64_t)pr.x * RAWC);
+            if (HAS_PTAB) pu[u] = ldg_nc_v2(pt + (int64_t)pr.x * E);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const float coef = cf[u];
+            s8[0] = fmaf(coef, __uint_as_float(x[u].x << 16), s8[0]); s8[1] = fmaf(coef, __uint_as_float(x[u].x & 0xffff0000u), s8[1]);
+            s8[2] = fmaf(coef, __uint_as_float(x[u].y << 16), s8[2]); s8[3] = fmaf(coef, __uint_as_float(x[u].y & 0xffff0000u), s8[3]);
+            s8[4] = fmaf(coef, __uint_as_float(x[u].z << 16), s8[4]); s8[5] = fmaf(coef, __uint_as_float(x[u].z & 0xffff0000u), s8[5]);
+            s8[6] = fmaf(coef, __uint_as_float(x[u].w << 16), s8[6]); s8[7] = fmaf(coef, __uint_as_float(x[u].w & 0xffff0000u), s8[7]);
             if (HAS_PTAB) {
-                const uint32_t pu = __ldg(reinterpret_cast<const uint32_t*>(pt + (int64_t)idx * E));
-                e2.x = fmaf(coef, __uint_as_float(pu << 16), e2.x); e2.y = fmaf(coef, __uint_as_float(pu & 0xffff0000u), e2.y);
+                e4[0] = fmaf(coef, __uint_as_float(pu[u].x << 16), e4[0]); e4[1] = fmaf(coef, __uint_as_float(pu[u].x & 0xffff0000u), e4[1]);
+                e4[2] = fmaf(coef, __uint_as_float(pu[u].y << 16), e4[2]); e4[3] = fmaf(coef, __uint_as_float(pu[u].y & 0xffff0000u), e4[3]);
             } else {
                 wsum += coef;
             }
         }
     }
-    *reinterpret_cast<float4*>(Arow + h * RAWC + lane * 4) =
-        make_float4(round_tf32(s4.x), round_tf32(s4.y), round_tf32(s4.z), round_tf32(s4.w));
-    if (HAS_PTAB) *reinterpret_cast<float2*>(Arow + NH * RAWC + h * HD + lane * 2) = make_float2(round_tf32(e2.x), round_tf32(e2.y));
-    else if (lane == 0) Arow[NH * RAWC + h] = round_tf32(wsum);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s8[i] += __shfl_xor_sync(0xffffffffu, s8[i], 16);
+    if (HAS_PTAB) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e4[i] += __shfl_xor_sync(0xffffffffu, e4[i], 16);
+    } else {
+        wsum += __shfl_xor_sync(0xffffffffu, wsum, 16);
+    }
+    if (half == 0) {
+        float4* o = reinterpret_cast<float4*>(Arow + h * RAWC + l16 * 8);
+        o[0] = make_float4(round_tf32(s8[0]), round_tf32(s8[1]), round_tf32(s8[2]), round_tf32(s8[3]));
+        o[1] = make_float4(round_tf32(s8[4]), round_tf32(s8[5]), round_tf32(s8[6]), round_tf32(s8[7]));
+        if (HAS_PTAB)
+            *reinterpret_cast<float4*>(Arow + NH * RAWC + h * HD + l16 * 4) =
+                make_float4(round_tf32(e4[0]), round_tf32(e4[1]), round_tf32(e4[2]), round_tf32(e4[3]));
+        else if (l16 == 0) Arow[NH * RAWC + h] = round_tf32(wsum);
+    }
 }
 
 int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st) {
     const bool ptab = a.ptab != nullptr;
     EGR_CHECK((a.E == 256 && ptab) || (a.E == 128 && !ptab), EGR_ERR_UNSUPPORTED, "tok_sample: E=%d ptab=%d", a.E, (int)ptab);
     EGR_CHECK(a.KA == tok_ka(a.E, ptab), EGR_ERR_INVALID, "tok_sample: KA=%d", a.KA);
+    EGR_CHECK(act_bf16, EGR_ERR_UNSUPPORTED, "tok_sample: the batched token path samples the bf16 channels-last copy");
     const int64_t total = (int64_t)a.G * a.B * a.J * a.V * TOK_NH;
     const int blocks = (int)ceil_div64(total, 8);
-    if (ptab) {
-        if (act_bf16) EGR_LAUNCH((tok_sample_kernel<__nv_bfloat16, true, 256>), blocks, 256, 0, st, a);
-        else EGR_LAUNCH((tok_sample_kernel<float, true, 256>), blocks, 256, 0, st, a);
-    } else {
-        if (act_bf16) EGR_LAUNCH((tok_sample_kernel<__nv_bfloat16, false, 128>), blocks, 256, 0, st, a);
-        else EGR_LAUNCH((tok_sample_kernel<float, false, 128>), blocks, 256, 0, st, a);
-    }
+    if (ptab) EGR_LAUNCH((tok_sample_kernel<true, 256>), blocks, 256, 0, st, a);
+    else EGR_LAUNCH((tok_sample_kernel<false, 128>), blocks, 256, 0, st, a);
     return EGR_OK;
 }
 
