@@ -40,15 +40,58 @@ STAGE_FLOPS = {
     "P2a": 4 * 2 * 4096 * 64 * 128, "P2b": 4 * 2 * 1024 * 128 * 576, "P2c": 4 * 2 * 256 * 64 * 128,
     "P2d": 4 * 2 * 64 * 128 * 576, "P2mlp0": 2 * 2048 * 32768,
 }
-# HBM-bound stages: algorithmic bytes per frame (fp32 in / activation dtype out), act = bytes per activation element
+# algorithmic HBM bytes per 4-view frame of every stage (act = bytes per activation element: 2 in bf16 mode; the pose3d
+# proposal branch P2* keeps fp32/TF32 activations; weights are counted once per batch for the one stage where they
+# dominate, P2mlp0).  `exp` = 1 when the chained forward also exports the TF32 channels-last refined features.
 STAGE_BYTES = {
-    "stage_nhwc": lambda act: 4 * 4096 * 128 * (4 + act),
-    "H1tail": lambda act: 4 * (1024 * 128 * act + 15 * 4096 * (4 + act)),
-    "H2tail": lambda act: 4 * (1024 * 128 * act + 15 * 4096 * 4),
-    "R1tail": lambda act: 4 * (1024 * 128 * act + 4096 * 128 * (4 + act)),
-    "D1": lambda act: 4 * 15 * 4096 * 4,
-    "P_stage_nhwc": lambda act: 4 * 4096 * 128 * (4 + 4) + 4 * 4096 * 128 * (4 + act),
+    "stage_nhwc": lambda act, exp, B: 4 * 4096 * 128 * (4 + act),
+    "H1a": lambda act, exp, B: 4 * 4096 * 128 * act * 2,
+    "H1b": lambda act, exp, B: 4 * (4096 * 128 + 1024 * 256) * act,
+    "H1c": lambda act, exp, B: 4 * 1024 * 256 * act * 2,
+    "H1d": lambda act, exp, B: 4 * 1024 * (256 + 128) * act,
+    "H1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 15 * 4096 * (4 + act)),
+    "D1": lambda act, exp, B: 4 * 15 * 4096 * 4,
+    "Q1a": lambda act, exp, B: 4 * 15 * 4096 * act + 4 * 256 * 4096 * act // B,
+    "F1a": lambda act, exp, B: 4 * 4096 * (128 + 256) * act,
+    "F1b": lambda act, exp, B: 4 * (4096 * 256 + 1024 * 512) * act,
+    "F1c": lambda act, exp, B: 4 * 1024 * (512 + 128) * act,
+    "R1a": lambda act, exp, B: 4 * 1024 * 256 * act,
+    "R1b": lambda act, exp, B: 4 * 1024 * 256 * act,
+    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * (4 + act + 4 * exp)),
+    "H2a": lambda act, exp, B: 4 * (4096 * 128 + 1024 * 256) * act,
+    "H2b": lambda act, exp, B: 4 * 1024 * 512 * act,
+    "H2c": lambda act, exp, B: 4 * 1024 * 384 * act,
+    "H2tail": lambda act, exp, B: 4 * (1024 * 128 * act + 15 * 4096 * 4),
+    "P_stage_nhwc": lambda act, exp, B: 0 if exp else 4 * 4096 * 128 * (4 + 4) + 4 * 4096 * 128 * (4 + act),
+    "P2a": lambda act, exp, B: 4 * 4096 * (128 + 64) * 4,
+    "P2b": lambda act, exp, B: 4 * (4096 * 64 + 1024 * 128) * 4,
+    "P2pool": lambda act, exp, B: 4 * (1024 + 256) * 128 * 4,
+    "P2c": lambda act, exp, B: 4 * 256 * (128 + 64) * 4,
+    "P2d": lambda act, exp, B: 4 * (256 * 64 + 64 * 128) * 4,
+    "P2mlp0": lambda act, exp, B: 2048 * 32768 * 4 // B + 4 * 64 * 128 * 4,
 }
+TF32_STAGES = ("P2a", "P2b", "P2c", "P2d", "P2mlp0")     # kind::tf32: half the bf16 tensor rate (nominal ratio)
+
+
+def stage_roofline(name, ms, B, act, exp, peaks):
+    """roofline of one stage: the binding resource is whichever of (FLOPs / tensor peak, bytes / HBM peak) takes longer"""
+    fl = STAGE_FLOPS.get(name, 0) * B
+    by = STAGE_BYTES[name](act, exp, B) * B if name in STAGE_BYTES else 0
+    if not fl and not by:
+        return None
+    tf_peak = peaks["tf_sust"] * (0.5 if name in TF32_STAGES else 1.0)
+    t_tensor = fl / (tf_peak * 1e12) if fl else 0.0
+    t_hbm = by / (peaks["hbm"] * 1e9) if by else 0.0
+    t_s = ms / 1e3
+    if t_tensor >= t_hbm:
+        ach = fl / t_s / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak}
+    ach = by / t_s / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"]}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
+NCU_TRAFFIC = {"F1b": 546566656 + 235312128}
 
 
 def load_peaks():
@@ -186,7 +229,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cp.cores, "kind": cp.kind,
                              "sample": "%d steps x %d frames, torch fp32, %d host threads" % (steps, fps, cp.cores)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -200,7 +243,26 @@ def workload_name(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Route fd 1 to stderr for the run (NCCL prints its version banner to stdout); the JSON line goes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -260,10 +322,19 @@ def main():
         in_bytes = feat_h.numel() * 4 + bfb_h.numel() * 4
         l2_note = "inputs %.0f MB + activations >> 126 MB L2 (no flush needed)" % (in_bytes / 1e6)
 
-        def e2e_fn():
-            f = feat_h.to(dev, non_blocking=True)
-            b = bfb_h.to(dev, non_blocking=True)
-            return step(f, b).cpu()
+        if args.workload == "mvfex_pose3d":
+            e2e_api = "HotPathPipeline.infer_host_batches (H2D of batch i+1 overlaps the forward of batch i)"
+
+            def e2e_fn(n):
+                return pipe.infer_host_batches(((feat_h, bfb_h) for _ in range(n)), world)
+        else:
+            e2e_api = "module forward on freshly uploaded inputs"
+
+            def e2e_fn(n):
+                for _ in range(n):
+                    f = feat_h.to(dev, non_blocking=True)
+                    b = bfb_h.to(dev, non_blocking=True)
+                    yield step(f, b).cpu()
     elif args.workload == "generate_target":
         kp_h = torch.from_numpy(synth.synth_keypoints(B, 4, 16, seed=rank)).pin_memory()
         kp = kp_h.to(dev)
@@ -276,9 +347,12 @@ def main():
         in_bytes = kp_h.numel() * 8
         l2_note = "output ring 2 x %.1f GB >> L2" % (ring[0].numel() * 4 / 1e9)
 
-        def e2e_fn():
-            out = step(kp_h.to(dev, non_blocking=True))
-            return out[:, :, :, 0, 0].sum().cpu()                            # checksum read-back; maps stay on device
+        e2e_api = "ops.generate_target_batch on uploaded keypoints, checksum read-back"
+
+        def e2e_fn(n):
+            for _ in range(n):
+                out = step(kp_h.to(dev, non_blocking=True))
+                yield out[:, :, :, 0, 0].sum().cpu()                         # checksum read-back; maps stay on device
     else:  # decode
         kp = torch.from_numpy(synth.synth_keypoints(B, 4, 15, seed=rank)).to(dev)
         hm = ops.generate_target_batch(kp).view(B * 4, 15, 64, 64)
@@ -312,32 +386,39 @@ def main():
     sampler.join(timeout=2)
     value = world * B * args.steps / (ms / 1e3)
 
-    # ---- e2e: pinned host inputs -> H2D -> hot path -> D2H of the step's result, every step ----
+    # ---- e2e: pinned host inputs -> H2D -> hot path -> D2H of the step's result, every step (device-timed) ----
     e2e = None
     if e2e_fn is not None:
-        for _ in range(2):
-            r = e2e_fn()
-        torch.cuda.synchronize(dev)
-        egd.barrier()
         n_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            r = e2e_fn()
+        for _ in e2e_fn(2):
+            pass
         torch.cuda.synchronize(dev)
         egd.barrier()
-        dt = egd.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in e2e_fn(n_e2e):
+            pass
+        e1.record()
+        torch.cuda.synchronize(dev)
+        egd.barrier()
+        dt = egd.max_over_ranks(e0.elapsed_time(e1), dev)
         e2e = {"value": world * B * n_e2e / (dt / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(in_bytes),
-               "d2h_bytes_per_step": int(r.numel() * r.element_size()), "steps": n_e2e}
+               "d2h_bytes_per_step": int(r.numel() * r.element_size()), "steps": n_e2e,
+               "api": e2e_api}
 
     # ---- per-stage timing of the same step through the library's stage profiler (rank 0) ----
-    roofline, stages = None, None
-    if rank == 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
-        import ctypes
-        lib.egr_profile_enable(1)
-        n_prof = 5
+    roofline, stages, stage_fracs = None, None, None
+    n_prof = 5
+    if args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
+        # every rank runs the profiled steps (the step ends in the all-gather); only rank 0 records stage events
+        if rank == 0:
+            lib.egr_profile_enable(1)
         for _ in range(n_prof):
             step()
         torch.cuda.synchronize(dev)
+        egd.barrier()
+    if rank == 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
+        import ctypes
         buf = ctypes.create_string_buffer(1 << 16)
         _lib.check(lib.egr_profile_read(buf, len(buf)))
         lib.egr_profile_enable(0)
@@ -347,20 +428,17 @@ def main():
                 name, tot, cnt = item.split(":")
                 stages[name] = float(tot) / n_prof           # ms per step
         total = sum(stages.values())
-        top = max(stages, key=stages.get)
-        t_s = stages[top] / 1e3
-        if top in STAGE_FLOPS:
-            ach = STAGE_FLOPS[top] * B / t_s / 1e12
-            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tf_sust"], "traffic": None}
-        elif top in STAGE_BYTES:
-            ach = STAGE_BYTES[top](act) * B / t_s / 1e9
-            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm"], "traffic": None}
-        else:
-            roofline = {"kernel": top, "bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
-        roofline.update({"peak_source": peaks["src"] + (" (sustained bf16 GEMM)" if roofline["bound"] == "tensor" else ""),
+        exp = 1 if args.workload in ("mvfex_pose3d", "mvfex") else 0     # HotPathPipeline exports the staged copies
+        per_stage = {k: stage_roofline(k, v, B, act, exp, peaks) for k, v in stages.items()}
+        # the roofline line is for the dominant kernel that HAS a roofline (the token phases are chains of ~15-45
+        # latency-bound launches, reported in stages_ms)
+        dense = [k for k in stages if per_stage[k] is not None]
+        top = max(dense, key=stages.get)
+        roofline = dict(per_stage[top])
+        roofline.update({"kernel": top, "traffic": NCU_TRAFFIC.get(top),
+                         "peak_source": peaks["src"] + (" (sustained bf16 GEMM)" if roofline["bound"] == "tensor" else " (copy)"),
                          "share_of_step": stages[top] / total, "ms_per_launch": stages[top]})
+        stage_fracs = {k: {"bound": r["bound"], "frac": round(r["frac"], 3)} for k, r in per_stage.items() if r}
     elif rank == 0:
         t_s = ms / 1e3 / args.steps
         per_frame = 4 * 16 * 4096 * 4 + 4 * 16 * 16 if args.workload == "generate_target" else 4 * 15 * 4096 * 4 + 4 * 15 * 13
@@ -370,6 +448,7 @@ def main():
                     "ms_per_launch": t_s * 1e3}
 
     if rank != 0:
+        egd.shutdown()
         return 0
     cpu = None
     if world == 1 and not args.no_cpu_baseline and args.workload == "mvfex_pose3d":
@@ -381,8 +460,9 @@ def main():
                        "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
                        "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "stages_ms": stages}
-    print(json.dumps(line))
+            "cpu_baseline": cpu, "stages_ms": stages, "stage_roofline": stage_fracs}
+    emit(line)
+    egd.shutdown()
     return 0
 
 

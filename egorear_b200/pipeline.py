@@ -43,3 +43,50 @@ class HotPathPipeline:
                     list_pose3d=preds3d)
 
     __call__ = forward
+
+    @torch.no_grad()
+    def infer_host_batches(self, batches, world=1):
+        """End-to-end serving loop over HOST batches: yields the packed joints of every batch as a CPU tensor.
+
+        `batches` iterates (feat, bfb) pinned-host fp32 tensors.  The host->device copy of batch i+1 runs on a copy stream
+        while batch i is computed (two device input slots, events both ways), so a step costs max(copy, compute) instead
+        of their sum; the device->host read of the packed joints is the only synchronisation per batch.
+        """
+        from . import dist as egd
+        dev = next(self.heatmap.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:      # persistent: the allocator pools are per stream
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._slots = [None, None]
+        copy, slots = self._copy_stream, self._slots
+        copy.wait_stream(main)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def upload(i, hb):
+            s = i & 1
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(consumed[s])         # the slot's previous batch has been read by the forward
+                if slots[s] is None or slots[s][0].shape != hb[0].shape:
+                    slots[s] = (torch.empty(hb[0].shape, dtype=hb[0].dtype, device=dev),
+                                torch.empty(hb[1].shape, dtype=hb[1].dtype, device=dev))
+                slots[s][0].copy_(hb[0], non_blocking=True)
+                slots[s][1].copy_(hb[1], non_blocking=True)
+                copied[s].record(copy)
+
+        it = iter(batches)
+        nxt = next(it, None)
+        i = 0
+        if nxt is not None:
+            upload(0, nxt)
+        while nxt is not None:
+            cur_i, nxt = i, next(it, None)
+            if nxt is not None:
+                upload(cur_i + 1, nxt)                   # overlaps with the forward below
+            s = cur_i & 1
+            main.wait_event(copied[s])
+            packed = self.forward(slots[s][0], slots[s][1])["packed"]
+            consumed[s].record(main)
+            yield egd.gather_rows(packed, world).cpu()   # D2H of the step's result (synchronises the main stream)
+            i += 1
