@@ -271,6 +271,7 @@ def main():
     ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode"])
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--lanes", type=int, default=3, help="streams alternated by the throughput loop (1 = one stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=int (egr_set_option), e.g. pdl=0")
     args = ap.parse_args()
@@ -316,8 +317,12 @@ def main():
                 p, _, _ = ops.get_max_preds(lh[-1].view(B * 4, 15, 64, 64), 0.5, False)
                 return egd.gather_rows(p.reshape(B, -1), world)
         else:
-            def step(f=feat, b=bfb):
+            def step_sync(f=feat, b=bfb):
                 return egd.gather_rows(pipe(f, b)["packed"], world)
+
+            def step(f=feat, b=bfb):
+                # throughput loop: independent batches alternate between two internal streams (pipeline.forward_async)
+                return pipe.forward_async(f, b, world=world, lanes=args.lanes)["gathered"] if args.lanes > 1 else step_sync(f, b)
         pipe.freeze() if args.workload != "pose3d" else None
         in_bytes = feat_h.numel() * 4 + bfb_h.numel() * 4
         l2_note = "inputs %.0f MB + activations >> 126 MB L2 (no flush needed)" % (in_bytes / 1e6)
@@ -363,6 +368,8 @@ def main():
         def step(h=hm):
             return ops.get_max_preds(h, 0.5, True)[0]
 
+    join = pipe.join if args.workload == "mvfex_pose3d" and args.lanes > 1 else None
+    step_prof = step_sync if args.workload == "mvfex_pose3d" else step
     torch.cuda.synchronize(dev)
     for _ in range(args.warmup):
         step()
@@ -377,6 +384,8 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         step()
+    if join is not None:
+        join()                       # the timing stream waits for every lane before the closing event
     ev1.record()
     torch.cuda.synchronize(dev)
     egd.barrier()
@@ -414,7 +423,7 @@ def main():
         if rank == 0:
             lib.egr_profile_enable(1)
         for _ in range(n_prof):
-            step()
+            step_prof()
         torch.cuda.synchronize(dev)
         egd.barrier()
     if rank == 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
@@ -458,6 +467,8 @@ def main():
             "dtype": args.precision if args.workload in ("mvfex_pose3d", "mvfex", "pose3d") else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "frames_per_gpu_per_step": B, "precision": args.precision,
                        "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
+                       "streams": ("%d lanes: independent batches alternate between internal streams" % args.lanes)
+                       if join is not None else "1",
                        "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "stages_ms": stages, "stage_roofline": stage_fracs}

@@ -18,6 +18,7 @@
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
 #include <mutex>
+#include <unordered_map>
 
 namespace egr {
 using namespace tcx;
@@ -418,7 +419,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 std::mutex g_tc_mu;
 bool g_tc_ready = false;
-float* g_splitk_scratch = nullptr;
+// split-K partial sums: one scratch buffer per launch stream (forwards of different streams may overlap)
+std::unordered_map<cudaStream_t, float*> g_splitk_scratch;
 constexpr int64_t SPLITK_SCRATCH_FLOATS = 8ll << 20;   // 32 MB
 
 int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -476,7 +478,6 @@ int gemm_tc_init() {
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     int rc;
     if ((rc = set_smem_attr_bn<64>()) || (rc = set_smem_attr_bn<128>()) || (rc = set_smem_attr_bn<256>())) return rc;
-    EGR_CUDA_OK(cudaMalloc(&g_splitk_scratch, SPLITK_SCRATCH_FLOATS * sizeof(float)));
     g_tc_ready = true;
     return EGR_OK;
 }
@@ -547,7 +548,12 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         p.ksplit = ks;
         p.partial = 1;
         p.part_stride = (int64_t)d.M * d.N;
-        p.D = g_splitk_scratch;
+        {
+            std::lock_guard<std::mutex> lk(g_tc_mu);
+            float*& sc = g_splitk_scratch[st];
+            if (!sc) EGR_CUDA_OK(cudaMalloc(&sc, SPLITK_SCRATCH_FLOATS * sizeof(float)));
+            p.D = sc;
+        }
     }
 
     // ---- tensor maps ----
@@ -613,10 +619,10 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         const int64_t tot = (int64_t)d.M * d.N;
         const int blocks = (int)ceil_div64(tot, 256);
         if (d_is_bf16)
-            EGR_LAUNCH(splitk_finalize_kernel<__nv_bfloat16>, blocks, 256, 0, st, g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
+            EGR_LAUNCH(splitk_finalize_kernel<__nv_bfloat16>, blocks, 256, 0, st, reinterpret_cast<const float*>(p.D), p.part_stride, p.ksplit, d.bias,
                        reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi, 0);
         else
-            EGR_LAUNCH(splitk_finalize_kernel<float>, blocks, 256, 0, st, g_splitk_scratch, p.part_stride, p.ksplit, d.bias,
+            EGR_LAUNCH(splitk_finalize_kernel<float>, blocks, 256, 0, st, reinterpret_cast<const float*>(p.D), p.part_stride, p.ksplit, d.bias,
                        reinterpret_cast<float*>(d.D), tot, d.N, d.epi, d.round_tf32);
     }
     return EGR_OK;

@@ -34,7 +34,8 @@ class _EngineBase:
         self._h = ctypes.c_void_p()
         self._tensors = {}
         self._sig = None
-        self._ws = None
+        self._ws_lanes = {}          # lane -> cached workspace tensor (concurrent forwards on different streams)
+        self.lane = 0
         self.frozen = False
 
     def _fn(self, name):
@@ -83,9 +84,14 @@ class _EngineBase:
 
     def _workspace(self, B, device):
         need = int(self._fn("workspace_bytes")(self._h, B))
-        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
-            self._ws = torch.empty(need, dtype=torch.uint8, device=device)
-        return self._ws
+        ws = self._ws_lanes.get(self.lane)
+        if ws is None or ws.numel() < need or ws.device != device:
+            ws = self._ws_lanes[self.lane] = torch.empty(need, dtype=torch.uint8, device=device)
+        return ws
+
+    @property
+    def _ws(self):
+        return self._ws_lanes.get(self.lane)
 
     def debug_buffer(self, name, dtype, shape):
         """Copy of a named intermediate of the last forward (tests only)."""

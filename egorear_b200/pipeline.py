@@ -24,6 +24,7 @@ class HotPathPipeline:
         self.heatmap = self.heatmap.to(device).eval()
         self.pose3d = self.pose3d.to(device).eval()
         self.heatmap.engine().export_staged(True)      # chained forward: pose3d reuses the channels-last copies
+        self._lanes, self._next_lane, self._pending = None, 0, []
 
     def freeze(self):
         """weights will not change any more: skip the per-call parameter-version check"""
@@ -43,6 +44,46 @@ class HotPathPipeline:
                     list_pose3d=preds3d)
 
     __call__ = forward
+
+    # ---- throughput mode: independent batches on alternating streams ----
+    def forward_async(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None, world=1, lanes=2):
+        """Same computation as forward(), enqueued on one of `lanes` internal streams (round robin), each with its own
+        workspace.  Batches are independent, so the latency-bound token phases of one batch (chains of small kernels that
+        leave most SMs idle) overlap with the dense stages of the next one.  The results belong to the lane's stream:
+        call wait(out) before consuming them on the current stream, or join() to wait for everything in flight.
+        With world > 1 the packed joints are all-gathered inside the lane (out["gathered"])."""
+        from . import dist as egd
+        dev = feat.device
+        cur = torch.cuda.current_stream(dev)
+        if self._lanes is None or len(self._lanes) != lanes:
+            self._lanes = [torch.cuda.Stream(dev) for _ in range(lanes)]
+        k = self._next_lane
+        self._next_lane = (k + 1) % lanes
+        st = self._lanes[k]
+        st.wait_stream(cur)                                # inputs were produced on the caller's stream
+        eh, ep = self.heatmap.engine(), self.pose3d.engine()
+        eh.lane = ep.lane = k + 1                          # lane 0 is the synchronous forward()
+        try:
+            with torch.cuda.stream(st):
+                out = self.forward(feat, bfb, coord_trans_mat, heatmap_for_anchor)
+                out["gathered"] = egd.gather_rows(out["packed"], world)
+                ev = torch.cuda.Event()
+                ev.record(st)
+        finally:
+            eh.lane = ep.lane = 0
+        out["event"] = ev
+        return out
+
+    def wait(self, out):
+        torch.cuda.current_stream().wait_event(out["event"])
+        return out
+
+    def join(self):
+        """the current stream waits for every lane"""
+        if self._lanes:
+            cur = torch.cuda.current_stream()
+            for st in self._lanes:
+                cur.wait_stream(st)
 
     @torch.no_grad()
     def infer_host_batches(self, batches, world=1):

@@ -165,3 +165,34 @@ def test_full_chain_and_reload(case):
         lh2, _ = m.forward_from_feats(case["feat"].cuda(), case["bfb"].cuda(), case["hfa"].cuda())
     d = (lh2[0] - lh[0]).cpu()
     assert torch.allclose(d[:, :2], torch.ones_like(d[:, :2]), atol=1e-4) and float(d[:, 2:].abs().max()) < 1e-6
+
+
+def test_pipeline_lanes_match_sync_forward():
+    """HotPathPipeline.forward_async (batches alternating between internal streams, one workspace per lane) returns
+    bit-identical results to the synchronous forward, also when several batches are in flight."""
+    from egorear_b200 import synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    pipe = HotPathPipeline(4, "ego4view_syn", "bf16", dev)
+    batches = [tuple(t.to(dev) for t in synth.synth_features(3, 4, seed=40 + i)) for i in range(4)]
+    want = [pipe(f, b)["packed"].clone() for f, b in batches]
+    outs = [pipe.forward_async(f, b, lanes=2) for f, b in batches]      # all four enqueued before any is consumed
+    for o, w in zip(outs, want):
+        pipe.wait(o)
+        assert torch.equal(o["packed"], w)
+    pipe.join()
+    torch.cuda.synchronize()
+
+
+def test_pipeline_host_batches_match_sync_forward():
+    """infer_host_batches (H2D prefetch on a copy stream, two device slots) yields what forward() gives per batch"""
+    from egorear_b200 import synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    pipe = HotPathPipeline(4, "ego4view_syn", "bf16", dev)
+    host = [tuple(t.pin_memory() for t in synth.synth_features(2, 4, seed=60 + i)) for i in range(5)]
+    want = [pipe(f.to(dev), b.to(dev))["packed"].cpu() for f, b in host]
+    got = list(pipe.infer_host_batches(iter(host)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
