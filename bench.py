@@ -239,7 +239,9 @@ def workload_name(args):
             "mvfex": "ego4view_syn_heatmap_mvfex-n1_jqa hot path, batch %d/GPU" % args.batch,
             "pose3d": "ego4view_syn_pose3d lifting, batch %d/GPU" % args.batch,
             "generate_target": "generate_target sweep, 4 views x 16 joints, %d frames/step/GPU" % args.batch,
-            "decode": "get_max_preds, 4 views x 15 joints, %d frames/step/GPU" % args.batch}[args.workload]
+            "decode": "get_max_preds, 4 views x 15 joints, %d frames/step/GPU" % args.batch,
+            "rw_e2e": "ego4view_rw_heatmap_mvfex-n1_jqa + ego4view_rw_pose3d from images (PyTorch bf16-autocast backbone + hot path), "
+                      "batch %d/GPU" % args.batch}[args.workload]
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -268,7 +270,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode"])
+    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode", "rw_e2e"])
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--lanes", type=int, default=3, help="streams alternated by the throughput loop (1 = one stream)")
@@ -276,7 +278,8 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option key=int (egr_set_option), e.g. pdl=0")
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = {"mvfex_pose3d": 64, "mvfex": 64, "pose3d": 1024, "generate_target": 8192, "decode": 8192}[args.workload]
+        args.batch = {"mvfex_pose3d": 64, "mvfex": 64, "pose3d": 1024, "generate_target": 8192, "decode": 8192,
+                      "rw_e2e": 512}[args.workload]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -340,6 +343,32 @@ def main():
                     f = feat_h.to(dev, non_blocking=True)
                     b = bfb_h.to(dev, non_blocking=True)
                     yield step(f, b).cpu()
+    elif args.workload == "rw_e2e":
+        # BASELINE config 5: images -> backbone (PyTorch) -> hot path (rw cameras, per-frame device->camera transforms)
+        pipe = HotPathPipeline(4, "ego4view_rw", args.precision, dev, with_backbone=True)
+        g = torch.Generator().manual_seed(rank)
+        img_h = torch.randn(B, 4, 3, 256, 256, generator=g).pin_memory()
+        ctm_h = synth.synth_coord_trans_mat(B, seed=rank).pin_memory()
+        img, ctm = img_h.to(dev), ctm_h.to(dev)
+        split = {}
+
+        def step(im=img, cm=ctm):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            f, b = pipe.backbone(im)
+            e[1].record()
+            out = egd.gather_rows(pipe(f, b, cm)["packed"], world)
+            e[2].record()
+            split["ev"] = e
+            return out
+        pipe.freeze()
+        in_bytes = img_h.numel() * 4 + ctm_h.numel() * 4
+        l2_note = "images %.0f MB + activations >> 126 MB L2" % (in_bytes / 1e6)
+        e2e_api = "backbone + HotPathPipeline.forward on freshly uploaded images"
+
+        def e2e_fn(n):
+            for _ in range(n):
+                yield step(img_h.to(dev, non_blocking=True), ctm_h.to(dev, non_blocking=True)).cpu()
     elif args.workload == "generate_target":
         kp_h = torch.from_numpy(synth.synth_keypoints(B, 4, 16, seed=rank)).pin_memory()
         kp = kp_h.to(dev)
@@ -394,6 +423,11 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = world * B * args.steps / (ms / 1e3)
+    extra = {}
+    if args.workload == "rw_e2e":
+        e = split["ev"]
+        extra = {"backbone_ms": e[0].elapsed_time(e[1]), "hot_path_ms": e[1].elapsed_time(e[2]),
+                 "hot_path_frames_per_s": world * B / (e[1].elapsed_time(e[2]) / 1e3)}
 
     # ---- e2e: pinned host inputs -> H2D -> hot path -> D2H of the step's result, every step (device-timed) ----
     e2e = None
@@ -448,7 +482,7 @@ def main():
                          "peak_source": peaks["src"] + (" (sustained bf16 GEMM)" if roofline["bound"] == "tensor" else " (copy)"),
                          "share_of_step": stages[top] / total, "ms_per_launch": stages[top]})
         stage_fracs = {k: {"bound": r["bound"], "frac": round(r["frac"], 3)} for k, r in per_stage.items() if r}
-    elif rank == 0:
+    elif rank == 0 and args.workload in ("generate_target", "decode"):
         t_s = ms / 1e3 / args.steps
         per_frame = 4 * 16 * 4096 * 4 + 4 * 16 * 16 if args.workload == "generate_target" else 4 * 15 * 4096 * 4 + 4 * 15 * 13
         ach = per_frame * B / t_s / 1e9
@@ -464,7 +498,7 @@ def main():
         cpu = cpu_baseline()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision if args.workload in ("mvfex_pose3d", "mvfex", "pose3d") else "f32", "data": "synthetic",
+            "dtype": args.precision if args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e") else "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "frames_per_gpu_per_step": B, "precision": args.precision,
                        "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
                        "streams": ("%d lanes: independent batches alternate between internal streams" % args.lanes)
@@ -472,6 +506,7 @@ def main():
                        "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "stages_ms": stages, "stage_roofline": stage_fracs}
+    line.update(extra)
     emit(line)
     egd.shutdown()
     return 0

@@ -13,10 +13,11 @@ from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
 
 
 class HotPathPipeline:
-    def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True):
+    def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True,
+                 with_backbone=False):
         self.V, self.camera_model, self.precision = num_views, camera_model, precision
         self.heatmap = EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(num_views, camera_model), precision=precision,
-                                                 build_backbone=False)
+                                                 build_backbone=with_backbone)
         self.pose3d = EgoPoseFormerPose3D(**pose3d_cfg(num_views, camera_model), precision=precision)
         if synthetic_weights:
             synth.fill_state_dict(self.heatmap)
@@ -44,6 +45,25 @@ class HotPathPipeline:
                     list_pose3d=preds3d)
 
     __call__ = forward
+
+    @torch.no_grad()
+    def backbone(self, img, chunk=128, autocast=True):
+        """The PyTorch ResNet18+FPN backbones (out of the hot path's scope): img [B,V,3,256,256] ->
+        (feat [B,V,128,64,64], bfb [B,V,512,8,8]) fp32.  bf16 autocast + frame chunks keep it off the critical memory path."""
+        if not getattr(self, "_bb_cl", False):           # cuDNN's tensor-core kernels want channels-last weights
+            for n in ("heatmap_estimator_stereo_front", "heatmap_estimator_stereo_back"):
+                if hasattr(self.heatmap, n):
+                    getattr(self.heatmap, n).to(memory_format=torch.channels_last)
+            self._bb_cl = True
+        B = img.shape[0]
+        feat = torch.empty((B, self.V, 128, 64, 64), dtype=torch.float32, device=img.device)
+        bfb = torch.empty((B, self.V, 512, 8, 8), dtype=torch.float32, device=img.device)
+        for i in range(0, B, chunk):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                f, bb = self.heatmap.forward_heatmap_feat_estimation(img[i:i + chunk])
+            feat[i:i + chunk].copy_(f)                   # cast + back to the NCHW layout of the module interface
+            bfb[i:i + chunk].copy_(bb[-1])
+        return feat, bfb
 
     # ---- throughput mode: independent batches on alternating streams ----
     def forward_async(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None, world=1, lanes=2):
