@@ -325,8 +325,9 @@ int run_tokens_batched(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const 
     if ((rc = gemm(w.tx, E, h->tk_f1, w.thid, EPI_GELU, 1))) return rc;
     if ((rc = gemm(w.thid, TOK_FF, h->tk_f2, w.tz, EPI_NONE, 0))) return rc;
     if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNF_W), ptr(TP_LNF_B), st))) return rc;
-    // post_norm + transposed token image for T1
-    return tok_ln_image(w.tx, w.xT, bf, G, B, J, E, ptr(TP_PN_W), ptr(TP_PN_B), st);
+    // post_norm + token image + T1 (1x1 15->64 ReLU, 1x1 64->128) in one tensor-core kernel
+    return tok_head_tc(w.tx, G, B, J, ptr(TP_PN_W), ptr(TP_PN_B), h->t1_0.f32, h->t1_0.bias, h->t1_3.f32, h->t1_3.bias, r0,
+                       w.t1, st);
 }
 
 // the refiner chain for G groups whose weights start at refiner r0
@@ -355,7 +356,9 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
         if ((rc = launch_mvf_tokens(ta, bf, st))) return rc;
     }
     EGR_MARK("T1", st);
-    // T1: 1x1(15->64) ReLU, then the 1x1(64->128) commuted in front of the bilinear x2 (both linear)
+    // T1: 1x1(15->64) ReLU, then the 1x1(64->128) commuted in front of the bilinear x2 (both linear);
+    // the batched token path has already produced t1 (tok_head_tc)
+    if (!h->tokb) {
     d = GemmDesc();
     d.A = w.xT; d.lda = 16; d.M = B * NPOS; d.D = w.h1t; d.ldd = 64; d.epi = EPI_RELU;
     d.groups = G; d.a_gs = (int64_t)B * NPOS * 16; d.d_gs = (int64_t)B * NPOS * 64;
@@ -368,6 +371,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
         t.groups = G; t.a_gs = (int64_t)B * NPOS * 64; t.d_gs = (int64_t)B * NPOS * 128;
         t.W = h->t1_3.f32 + (int64_t)r0 * 128 * 64; t.bias = h->t1_3.bias + r0 * 128; t.w_gs = 128 * 64; t.b_gs = 128;
         if ((rc = gemm_simt(t, bf, bf, st))) return rc;
+    }
     }
     EGR_MARK("F1a", st);
     // F1a: 1x1(128->256) ReLU @64x64

@@ -46,7 +46,42 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, in
         }
 }
 
+// bf16 output, C = 128: 64-pixel tiles.  Two channel rows are packed into bf16x2 words on the way into shared memory
+// (tile[pair][pixel], odd stride), so the write phase reads conflict-free and every store instruction writes one full
+// 128 B line of a pixel's 256 B channel vector; reads are 2 x 128 B per channel row.
+constexpr int NT_PX = 64, NT_C = 128, NT_LD = NT_PX + 1;
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int V, int HW) {
+    __shared__ uint32_t tile[(NT_C / 2) * NT_LD];
+    pdl_trigger();
+    pdl_wait();
+    const int p0 = blockIdx.x * NT_PX;
+    const int bv = blockIdx.y;        // b * V + v
+    const int b = bv / V, v = bv - b * V;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* src = in + (int64_t)bv * NT_C * HW + p0 + lane;
+#pragma unroll 4
+    for (int cp = warp; cp < NT_C / 2; cp += 8) {
+        const float* r0 = src + (int64_t)(2 * cp) * HW;
+        const float a0 = __ldcs(r0), a1 = __ldcs(r0 + 32), b0 = __ldcs(r0 + HW), b1 = __ldcs(r0 + HW + 32);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(a0, b0), hi = __floats2bfloat162_rn(a1, b1);
+        tile[cp * NT_LD + lane] = *reinterpret_cast<uint32_t*>(&lo);
+        tile[cp * NT_LD + lane + 32] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    __syncthreads();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (((int64_t)v * B + b) * HW + p0) * NT_C);
+#pragma unroll 4
+    for (int p = warp; p < NT_PX; p += 8) {
+        dst[(int64_t)p * (NT_C / 2) + lane] = tile[lane * NT_LD + p];
+        dst[(int64_t)p * (NT_C / 2) + lane + 32] = tile[(lane + 32) * NT_LD + p];
+    }
+}
+
 int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_mode, cudaStream_t st) {
+    if (out_mode == 1 && C == NT_C && HW % NT_PX == 0) {
+        EGR_LAUNCH(nchw_to_nhwc_bf16_kernel, dim3(HW / NT_PX, B * V), 256, 0, st, in, (__nv_bfloat16*)out, B, V, HW);
+        return EGR_OK;
+    }
     EGR_CHECK(HW % 32 == 0 && C * 33 * 4 <= 48 * 1024, EGR_ERR_UNSUPPORTED, "nchw_to_nhwc: HW=%d C=%d", HW, C);
     dim3 grid(HW / 32, B * V);
     const size_t smem = sizeof(float) * C * 33;

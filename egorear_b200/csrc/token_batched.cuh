@@ -55,6 +55,12 @@ int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per
 int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int E, const float* const* gamma,
                  const float* const* beta, cudaStream_t st);
 
+// the same post_norm + token image followed by TransformerHeadLayer's two 1x1 convs (the second commuted in front of the
+// upsample) in one tcgen05 kernel (token_head_tc.cu):  x [G][B][J][256] -> t1 [G][B][256 pos][128] bf16
+//   w0 [sets][64][16] (15 padded to 16), b0 [sets][64], w3 [sets][128][64], b3 [sets][128]; group g uses set r0 + g
+int tok_head_tc(const float* x, int G, int B, int J, const float* const* gamma, const float* const* beta, const float* w0,
+                const float* b0, const float* w3, const float* b3, int r0, void* t1, cudaStream_t st);
+
 // mvfex jqa query input (HeatmapMVF.forward :655-665), in three steps:
 //   tok_avgpool:   pooled[g][b][512] = adaptive_avg_pool2d(bfb[g][b], 1), rounded     (bfb of group g, frame b at
 //                  bfb + g*bfb_gs + b*bfb_bs: [512][hw])
