@@ -42,6 +42,7 @@ struct egr_mvfex {
     MvfTokenW* d_tokw = nullptr;               // device [V]
     // batched token path (bf16 precision): token GEMM weights (fp32 rounded to TF32, sets = V) + per-refiner pointer tables
     bool export_staged = false;                // keep channels-last copies for a chained pose3d forward
+    bool export_tf32 = true;                   // ... including the TF32 copy of the refined features
     const void *st_init = nullptr, *st_refined = nullptr;
     const float* st_refined_tf32 = nullptr;
     bool tokb = false;
@@ -194,7 +195,7 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.anch = (float*)c.take((int64_t)B * V * J * 2 * 4);
     b.maxv = (float*)c.take((int64_t)B * V * J * 4);
     b.valid = (uint8_t*)c.take((int64_t)B * V * J);
-    b.refn32 = (h->export_staged && G == V) ? (float*)c.take((int64_t)G * B * FHW * FC * 4) : nullptr;
+    b.refn32 = (h->export_staged && h->export_tf32 && G == V) ? (float*)c.take((int64_t)G * B * FHW * FC * 4) : nullptr;
     if (h->tokb) {
         const int64_t T = (int64_t)B * J;
         b.tx = (float*)c.take(G * T * EMB * 4);
@@ -669,6 +670,7 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
 extern "C" int egr_mvfex_export_staged(egr_mvfex* h, int enable) {
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_export_staged: null handle");
     h->export_staged = enable != 0;
+    h->export_tf32 = enable != 2;
     h->st_init = h->st_refined = nullptr; h->st_refined_tf32 = nullptr;
     return EGR_OK;
 }

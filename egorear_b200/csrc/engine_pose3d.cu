@@ -38,6 +38,8 @@ struct egr_pose3d {
     const void* st_sampled = nullptr;
     int st_sampled_bf16 = 0;
     const float* st_final_tf32 = nullptr;
+    const void* st_final_bf16 = nullptr;
+    __nv_bfloat16* c0_bf16 = nullptr;   // conv_frame_feat.0 weight for the bf16-input variant of P2a
     // batched token path (bf16 precision)
     bool tokb = false;
     int KA = 0;
@@ -342,6 +344,12 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
         if ((rc = gemm_tc_init())) return rc;
     }
     if ((rc = p_make_wmat(h, h->c0, 64, 128, 0, "conv_frame_feat.0", st))) return rc;
+    if (p2_prec(h) == PREC_TF32) {
+        const float* w0 = h->params.get("conv_frame_feat.0.weight", 64 * 128, &rc);
+        if (!w0) return rc;
+        if ((rc = h->pool.alloc(&h->c0_bf16, 64 * 128))) return rc;
+        if ((rc = cast_bf16(w0, h->c0_bf16, 64 * 128, st))) return rc;
+    }
     if ((rc = p_make_wmat(h, h->c2, 128, 9 * 64, 1, "conv_frame_feat.2", st))) return rc;
     if ((rc = p_make_wmat(h, h->c5, 64, 128, 0, "conv_frame_feat.5", st))) return rc;
     if ((rc = p_make_wmat(h, h->c7, 128, 9 * 64, 1, "conv_frame_feat.7", st))) return rc;
@@ -424,9 +432,12 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     const void* st_s = h->st_sampled;
     const float* st_f = h->st_final_tf32;
     const int st_s_bf16 = h->st_sampled_bf16;
-    h->st_sampled = nullptr; h->st_final_tf32 = nullptr;
+    const void* st_fb = h->st_final_bf16;
+    h->st_sampled = nullptr; h->st_final_tf32 = nullptr; h->st_final_bf16 = nullptr;
     const void* Xf = w.Xf;
+    const bool p2a_bf16_in = st_fb && rnd && h->c0_bf16 && !st_f;     // chained forward without the TF32 copy
     if (st_f && rnd) Xf = st_f;
+    else if (p2a_bf16_in) Xf = st_fb;
     else if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
     const void* Xs = Xf;
     if (st_s && st_s_bf16 == bfs) Xs = st_s;
@@ -438,7 +449,10 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     // P2 conv_frame_feat
     GemmDesc d;
     d.A = Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
-    if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
+    if (p2a_bf16_in) {      // bf16 x bf16 -> fp32 (rounded to TF32 for P2b)
+        d.N = 64; d.K = PC; d.W = h->c0_bf16; d.bias = h->c0.bias;
+        if ((rc = gemm_tc(d, /*in_is_f32=*/0, /*d_is_bf16=*/0, st))) return rc;
+    } else if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
     EGR_MARK("P2b", st);
     d = GemmDesc();
     d.A = w.p0; d.amode = A_CONV3S2; d.Hin = 64; d.Win = 64; d.Cin = 64; d.M = VB * 1024; d.D = w.p2; d.ldd = 128; d.epi = EPI_RELU; d.round_tf32 = rnd;
@@ -499,6 +513,12 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
 extern "C" int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32) {
     EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_use_staged: null handle");
     h->st_sampled = sampled_nhwc; h->st_sampled_bf16 = sampled_is_bf16 ? 1 : 0; h->st_final_tf32 = final_nhwc_tf32;
+    return EGR_OK;
+}
+
+extern "C" int egr_pose3d_use_staged_final_bf16(egr_pose3d* h, const void* final_nhwc_bf16) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_use_staged_final_bf16: null handle");
+    h->st_final_bf16 = final_nhwc_bf16;
     return EGR_OK;
 }
 

@@ -113,9 +113,10 @@ class MvfexEngine(_EngineBase):
         _lib.check(self._lib.egr_mvfex_create(num_views, num_heatmap, float(heatmap_threshold), PREC[precision],
                                               ctypes.byref(self._h)))
 
-    def export_staged(self, enable=True):
-        """keep channels-last copies of the input / refined features for a chained Pose3DEngine.forward(staged=...)"""
-        _lib.check(self._lib.egr_mvfex_export_staged(self._h, int(bool(enable))))
+    def export_staged(self, enable=True, tf32_final=True):
+        """keep channels-last copies of the input / refined features for a chained Pose3DEngine.forward(staged=...);
+        tf32_final=False drops the fp32/TF32 copy of the refined features (pose3d's first conv then reads the bf16 copy)"""
+        _lib.check(self._lib.egr_mvfex_export_staged(self._h, (1 if tf32_final else 2) if enable else 0))
         self._export = bool(enable)
 
     def forward(self, feat, bfb, heatmap_for_anchor=None):
@@ -208,6 +209,8 @@ class Pose3DEngine(_EngineBase):
             sampled = staged["init"] if use_init else staged["refined"]
             _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),
                                                        ctypes.c_void_p(staged["refined_tf32"]) if staged["refined_tf32"] else None))
+            if not staged["refined_tf32"] and staged["bf16"] and staged["refined"]:
+                _lib.check(self._lib.egr_pose3d_use_staged_final_bf16(self._h, ctypes.c_void_p(staged["refined"])))
         _lib.check(self._lib.egr_pose3d_forward(self._h, B, _ptr(fi), _ptr(ff), _ptr(ctm), _ptr(preds), _ptr(ws),
                                                 ws.numel(), _stream()))
         return preds

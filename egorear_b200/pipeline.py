@@ -14,7 +14,7 @@ from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
 
 class HotPathPipeline:
     def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True,
-                 with_backbone=False):
+                 with_backbone=False, tf32_final=True):
         self.V, self.camera_model, self.precision = num_views, camera_model, precision
         self.heatmap = EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(num_views, camera_model), precision=precision,
                                                  build_backbone=with_backbone)
@@ -24,7 +24,9 @@ class HotPathPipeline:
             synth.fill_state_dict(self.pose3d)
         self.heatmap = self.heatmap.to(device).eval()
         self.pose3d = self.pose3d.to(device).eval()
-        self.heatmap.engine().export_staged(True)      # chained forward: pose3d reuses the channels-last copies
+        # chained forward: pose3d reuses the channels-last copies; tf32_final=False drops the TF32 copy of the refined
+        # features (537 MB per 64 frames): conv_frame_feat.0 then reads the bf16 copy
+        self.heatmap.engine().export_staged(True, tf32_final=tf32_final)
         self._lanes, self._next_lane, self._pending = None, 0, []
 
     def freeze(self):

@@ -178,7 +178,7 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
  * egr_mvfex_staged returns them (valid until the next forward on this handle / workspace).  Passing them to
  * egr_pose3d_use_staged lets the NEXT egr_pose3d_forward skip re-staging its NCHW inputs (the hint is consumed by that
  * call; the NCHW pointers must still be the same tensors).  [V][B][64*64][128] layout. */
-int egr_mvfex_export_staged(egr_mvfex* h, int enable);
+int egr_mvfex_export_staged(egr_mvfex* h, int enable);   /* 0 off, 1 all three copies, 2 without the TF32 copy */
 int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const float** refined_nhwc_tf32,
                      int* act_is_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
@@ -208,6 +208,9 @@ int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init, const floa
  * feats_final), bf16 or fp32 as flagged; final_nhwc_tf32: channels-last fp32 copy of feats_final rounded to TF32.
  * Either may be NULL.  One-shot: consumed by the next egr_pose3d_forward. */
 int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32);
+/* Alternative hint for feats_final: its channels-last bf16 copy (what egr_mvfex_export_staged(h, 2) leaves).  The first
+ * proposal conv (conv_frame_feat.0) then multiplies bf16 operands; everything after it stays TF32.  One-shot. */
+int egr_pose3d_use_staged_final_bf16(egr_pose3d* h, const void* final_nhwc_bf16);
 int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes);
 
 /* ---------------------------------------------------------------------------------------------
