@@ -13,6 +13,7 @@ namespace egr {
 int g_opt_tc = 1;
 int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
 extern int g_opt_pose_p2_bf16;
+extern int g_opt_ws;
 }
 using namespace egr;
 
@@ -449,6 +450,7 @@ void note_all(egr_mvfex* h, const Bufs& w, int B, int G) {
 extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "tc") { g_opt_tc = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pose_p2_bf16") { g_opt_pose_p2_bf16 = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "ws") { g_opt_ws = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pdl") { g_opt_pdl = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "tok_batched") { g_opt_tok_batched = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");

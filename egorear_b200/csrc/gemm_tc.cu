@@ -22,6 +22,7 @@
 
 namespace egr {
 using namespace tcx;
+int g_opt_ws = 0;      // weight-stationary mode of gemm_tc (option "ws"): measured no gain on B200, off by default
 namespace {
 
 constexpr int BM = 128;
@@ -61,7 +62,11 @@ struct TcParams {
     const void* aux;
     int64_t aux_gs;
     int Hout_e, Wout_e;
+    // weight-stationary mode: the whole [BN x K] weight slab of the current group stays in shared memory (loaded once per
+    // group change), the ring carries A tiles only (ws_stages of them)
+    int ws, ws_stages;
 };
+constexpr int MAX_STAGES = 12;     // barrier slots (weight-stationary rings are deeper than the A+B rings)
 
 template <typename TO> __device__ __forceinline__ void store8(TO* p, const float* v);
 template <> __device__ __forceinline__ void store8<float>(float* p, const float* v) {
@@ -254,18 +259,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BARS);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 6);
     float* sbias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * C::STAGES;
-    const uint32_t tfull0 = empty0 + 8 * C::STAGES, tempty0 = tfull0 + 16;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * MAX_STAGES;
+    const uint32_t tfull0 = empty0 + 8 * MAX_STAGES, tempty0 = tfull0 + 16;
+    const uint32_t wfull = tempty0 + 16, wempty = wfull + 8;
+    const int n_stages = p.ws ? p.ws_stages : C::STAGES;
+    const uint32_t w_bytes = p.ws ? (uint32_t)p.kb_total * C::STAGE_B : 0u;      // resident weight slab in front of the ring
+    const uint32_t stage_bytes = p.ws ? (uint32_t)C::STAGE_A : (uint32_t)C::STAGE;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.groups * p.m_tiles * p.n_tiles * p.ksplit;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < n_stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, EPI_WARPS); }
+        mbar_init(wfull, 1); mbar_init(wempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
@@ -284,11 +294,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int stage = 0, phase = 0;
+            int stage = 0, phase = 0, w_group = -1, w_loads = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
                 const int kb0 = tc.ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+                if (p.ws && tc.g != w_group) {
+                    // new weight set: wait until every MMA that read the previous slab has completed, then reload it
+                    if (w_loads > 0) mbar_wait(wempty, (w_loads - 1) & 1);
+                    mbar_expect_tx(wfull, w_bytes);
+                    for (int kb = 0; kb < p.kb_total; ++kb)
+                        tma_load_3d(smem_base + kb * C::STAGE_B, &tmB, wfull, kb * BK, tc.nt * BN, tc.g);
+                    w_group = tc.g;
+                    ++w_loads;
+                }
                 // conv tile geometry (rows of all groups form one contiguous image list)
                 int img0 = 0, oy0 = 0;
                 if (p.amode == A_CONV3S2) {
@@ -299,8 +318,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t full = full0 + 8 * stage;
-                    mbar_expect_tx(full, C::STAGE);
-                    const uint32_t sa = smem_base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                    mbar_expect_tx(full, stage_bytes);
+                    const uint32_t sa = smem_base + w_bytes + stage * stage_bytes, sb = sa + C::STAGE_A;
                     const int k = kb * BK;
                     if (p.amode == A_PLAIN) {
                         tma_load_4d(sa, &tmA, full, k % p.kblk, tc.mt * BM, k / p.kblk, tc.g);
@@ -312,8 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int hp = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
                         tma_load_5d(sa, &tmA, full, ci + wp * p.Cin, dx, hp, oy0 + dy, img0);
                     }
-                    tma_load_3d(sb, &tmB, full, k, tc.nt * BN, tc.g);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (!p.ws) tma_load_3d(sb, &tmB, full, k, tc.nt * BN, tc.g);
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -321,19 +340,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN, TF32);
-            int stage = 0, phase = 0, it = 0;
+            int stage = 0, phase = 0, it = 0, w_group = -1, w_loads = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const TileCoord tc = decode_tile(t, p);
                 const int kb0 = tc.ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
                 const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                if (p.ws && tc.g != w_group) {
+                    mbar_wait(wfull, w_loads & 1);
+                    w_group = tc.g;
+                    ++w_loads;
+                }
                 mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(full0 + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * C::STAGE, sb = sa + C::STAGE_A;
+                    const uint32_t sa = smem_base + w_bytes + stage * stage_bytes;
+                    const uint32_t sb = p.ws ? smem_base + kb * C::STAGE_B : sa + C::STAGE_A;
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {
@@ -341,9 +366,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_mma<TF32>(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
                     }
                     tc_commit(empty0 + 8 * stage);
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull0 + 8 * acc);
+                if (p.ws) {
+                    // last tile of this CTA that uses the resident slab: release it once these MMAs have completed
+                    const int tn = t + gridDim.x;
+                    if (tn < total_tiles && decode_tile(tn, p).g != tc.g) tc_commit(wempty);
+                }
             }
         }
     } else {
@@ -612,6 +642,17 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
     }
     const int64_t total = (int64_t)d.groups * m_tiles * p.n_tiles * p.ksplit;
     const int grid = (int)(total < nsm ? total : nsm);
+    // weight-stationary when the group's whole weight slab fits beside >= 4 A stages and every CTA walks several tiles:
+    // the slab is fetched once per CTA (and group) instead of once per tile, and the ring becomes A-only and deeper
+    {
+        const int64_t w_bytes = (int64_t)p.kb_total * bn * ROW_BYTES;
+        const int64_t a_stages = (SMEM_RING - w_bytes) / (BM * ROW_BYTES);
+        if (g_opt_ws && d.amode == A_PLAIN && p.kblk == d.K && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
+            total >= 2 * (int64_t)grid) {
+            p.ws = 1;
+            p.ws_stages = (int)(a_stages < MAX_STAGES ? a_stages : MAX_STAGES);
+        }
+    }
     rc = f32 ? launch_tc_any<float>(bn, out_bf16, tmA, tmB, tmD, p, grid, st)
              : launch_tc_any<__nv_bfloat16>(bn, out_bf16, tmA, tmB, tmD, p, grid, st);
     if (rc) return rc;
