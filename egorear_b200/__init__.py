@@ -12,7 +12,7 @@ __all__ = ["patch", "PATCH_TABLE"]
 
 # reference module -> names rebound by patch() (reference file:line in INTEGRATION.md)
 PATCH_TABLE = {
-    "pose_estimation.utils.loss": ["get_max_preds"],
+    "pose_estimation.utils.loss": ["get_max_preds", "get_max_preds_soft_pytorch"],
     "generate_heatmap": ["generate_target"],
     "pose_estimation.models.utils.deform_attn": ["MSDeformAttn"],
     "pose_estimation.models.estimator.egoposeformer_heatmap": ["EgoPoseFormerHeatmap"],
@@ -53,7 +53,8 @@ def patch(precision="bf16", modules=None, strict=False):
         raise ValueError("precision must be 'bf16' or 'fp32'")
     from . import _lib, modules as M, ops
     _lib.load()
-    repl = {"get_max_preds": ops.get_max_preds, "generate_target": ops.generate_target}
+    repl = {"get_max_preds": ops.get_max_preds, "generate_target": ops.generate_target,
+            "get_max_preds_soft_pytorch": ops.get_max_preds_soft_pytorch}
     for name in set(n for names in PATCH_TABLE.values() for n in names):
         if name in repl:
             continue

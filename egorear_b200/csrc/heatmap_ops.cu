@@ -132,6 +132,50 @@ decode_argmax_kernel(const float* __restrict__ hm, int64_t n_hm, int HW, int W, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// D1s  soft-argmax decoder: get_max_preds_soft_pytorch (pose_estimation/utils/loss.py:145-177)
+//   p = softmax over the H*W values of a map; x = sum_w w * sum_h p[h][w], y = sum_h h * sum_w p[h][w]; maxvals = max.
+//   One warp per map, two passes (the 16 KB map of the second pass comes from L1/L2): pass 1 max (128-bit loads, shuffle
+//   reduction), pass 2 the three sums sum e, sum e*w, sum e*h with e = exp(v - max) in fp32, one division at the end.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+decode_soft_argmax_kernel(const float* __restrict__ hm, int64_t n_hm, int H, int W, int normalize,
+                          float* __restrict__ preds, float* __restrict__ maxvals) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int HW = H * W, n_v4 = HW >> 2;
+    for (int64_t m = (int64_t)blockIdx.x * DEC_WARPS + warp; m < n_hm; m += (int64_t)gridDim.x * DEC_WARPS) {
+        const float4* src = reinterpret_cast<const float4*>(hm + m * (int64_t)HW);
+        float mx = -INFINITY;
+        for (int i = lane; i < n_v4; i += 32) {
+            const float4 v = __ldg(src + i);
+            mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+        }
+        mx = warp_max(mx);
+        float s = 0.f, sx = 0.f, sy = 0.f;
+        for (int i = lane; i < n_v4; i += 32) {
+            const float4 v = __ldg(src + i);
+            const int base = i << 2;                 // W % 4 == 0: the 4 values share a row
+            const int h = base / W, w0 = base - h * W;
+            const float e0 = expf(v.x - mx), e1 = expf(v.y - mx), e2 = expf(v.z - mx), e3 = expf(v.w - mx);
+            const float es = (e0 + e1) + (e2 + e3);
+            s += es;
+            sy = fmaf(es, (float)h, sy);
+            sx += e0 * (float)w0 + e1 * (float)(w0 + 1) + e2 * (float)(w0 + 2) + e3 * (float)(w0 + 3);
+        }
+        s = warp_sum(s); sx = warp_sum(sx); sy = warp_sum(sy);
+        if (lane == 0) {
+            float x = sx / s, y = sy / s;
+            if (normalize) { x = x / (float)W; y = y / (float)H; }
+            preds[m * 2 + 0] = x;
+            preds[m * 2 + 1] = y;
+            maxvals[m] = mx;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // H1'  1x1 conv C->J on NCHW fp32 (estimator/egoposeformer_heatmap.py:23,34-39)
 //   thread = 4 consecutive positions; loads are float4-coalesced per channel; weights broadcast from smem
 // ---------------------------------------------------------------------------------------------
@@ -276,6 +320,20 @@ extern "C" int egr_decode_argmax(const float* hm, int64_t N, int J, int H, int W
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
     EGR_LAUNCH(decode_argmax_kernel, grid, DEC_WARPS * 32, 0, (cudaStream_t)stream,
                hm, n_hm, H * W, W, 1.f / W, 1.f / H, H, threshold, normalize, preds, maxvals, valid, idx);
+    return EGR_OK;
+}
+
+extern "C" int egr_decode_soft_argmax(const float* hm, int64_t N, int J, int H, int W, int normalize, float* preds,
+                                      float* maxvals, void* stream) {
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(N >= 0 && J > 0 && H > 0 && W > 0, EGR_ERR_INVALID, "decode_soft: batch_images should be 4-ndim (B, J, H, W)");
+    EGR_CHECK(W % 4 == 0, EGR_ERR_UNSUPPORTED, "decode_soft: W must be a multiple of 4");
+    if (N == 0) return EGR_OK;
+    EGR_CHECK(hm && preds && maxvals, EGR_ERR_INVALID, "decode_soft: null pointer");
+    const int64_t n_hm = N * J;
+    const int64_t want = ceil_div64(n_hm, DEC_WARPS);
+    const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
+    EGR_LAUNCH(decode_soft_argmax_kernel, grid, DEC_WARPS * 32, 0, (cudaStream_t)stream, hm, n_hm, H, W, normalize, preds, maxvals);
     return EGR_OK;
 }
 

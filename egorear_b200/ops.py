@@ -54,6 +54,22 @@ def get_max_preds(heatmaps, threshold=0.5, normalize=False, return_index=False):
     return out + (idx,) if return_index else out
 
 
+def get_max_preds_soft_pytorch(batch_heatmaps, normalize=False):
+    """Drop-in for pose_estimation.utils.loss.get_max_preds_soft_pytorch (:145-177): soft-argmax joint decoding.
+    -> preds [B, J, 2] (expected x, y under softmax over H*W), maxvals [B, J, 1]."""
+    assert len(batch_heatmaps.shape) == 4, 'batch_images should be 4-ndim (B, J, H, W)'
+    _need_cuda(batch_heatmaps, "get_max_preds_soft_pytorch")
+    B, J, H, W = batch_heatmaps.shape
+    hm = batch_heatmaps.detach()
+    if hm.dtype != torch.float32 or not hm.is_contiguous():
+        hm = hm.float().contiguous()
+    preds = torch.empty((B, J, 2), dtype=torch.float32, device=hm.device)
+    maxvals = torch.empty((B, J, 1), dtype=torch.float32, device=hm.device)
+    _lib.check(_lib.load().egr_decode_soft_argmax(_ptr(hm), B, J, H, W, int(bool(normalize)), _ptr(preds), _ptr(maxvals),
+                                                  _stream()))
+    return preds, maxvals
+
+
 # ------------------------------------------------------------------------------------------------
 # G1
 # ------------------------------------------------------------------------------------------------

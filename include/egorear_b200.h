@@ -68,6 +68,14 @@ int egr_generate_target(const double* joints, float* out, int64_t n_maps, int J,
                         int heatmap_size, double sigma, const float* patch_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * D1s get_max_preds_soft_pytorch          replaces pose_estimation/utils/loss.py:145-177 (soft-argmax decoder)
+ *   hm [N, J, H, W] float32 -> preds [N, J, 2] float32 = expectation of (x, y) under softmax over H*W,
+ *   maxvals [N, J] float32 (the caller views it as [N, J, 1]).  W must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------- */
+int egr_decode_soft_argmax(const float* hm, int64_t N, int J, int H, int W, int normalize, float* preds, float* maxvals,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * D1  get_max_preds                       replaces pose_estimation/utils/loss.py:122-142
  *   hm [N, J, H, W] float32 -> preds [N, J, 2] float32 (x, y), maxvals [N, J] float32,
  *   valid [N, J] uint8 (torch.bool storage), idx [N, J] int32 flat argmax (may be NULL).

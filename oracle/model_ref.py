@@ -68,6 +68,20 @@ def get_max_preds(heatmaps: Tensor, threshold: float = 0.5, normalize: bool = Fa
     return preds, maxvals.squeeze(), valid.squeeze()
 
 
+def get_max_preds_soft_pytorch(batch_heatmaps: Tensor, normalize: bool = False):
+    """soft-argmax decoder, utils/loss.py:145-177: softmax over H*W, marginals, expected column / row index"""
+    assert batch_heatmaps.ndim == 4
+    B, J, H, W = batch_heatmaps.shape
+    flat = batch_heatmaps.reshape(B, J, -1)
+    maxvals = flat.max(dim=2)[0].view(B, J, 1)
+    p = F.softmax(flat, dim=2).view(B, J, H, W)
+    x = (p.sum(dim=2) * torch.arange(W, dtype=torch.float32).view(1, 1, W)).sum(dim=2, keepdim=True)
+    y = (p.sum(dim=3) * torch.arange(H, dtype=torch.float32).view(1, 1, H)).sum(dim=2, keepdim=True)
+    if normalize:
+        x, y = x / W, y / H
+    return torch.cat([x, y], dim=2), maxvals
+
+
 # ----------------------------------------------------------------------------------------------
 # mmcv ms_deform_attn_forward, single level            models/utils/deform_attn.py:155-162
 # ----------------------------------------------------------------------------------------------

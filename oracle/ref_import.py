@@ -95,9 +95,25 @@ def import_estimators():
 
 def import_functions():
     install()
-    from pose_estimation.utils.loss import get_max_preds
+    from pose_estimation.utils import loss as ref_loss
     import generate_heatmap
-    return dict(get_max_preds=get_max_preds, generate_target=generate_heatmap.generate_target)
+
+    def soft(batch_heatmaps, normalize=False):
+        # utils/loss.py:160-161 builds its index vectors with torch.cuda.comm.broadcast / torch.cuda.FloatTensor;
+        # on a CUDA-less host both are shimmed to their CPU equivalents for the duration of the call
+        import torch
+        if torch.cuda.is_available():
+            return ref_loss.get_max_preds_soft_pytorch(batch_heatmaps, normalize)
+        import torch.cuda.comm as comm          # not imported by `import torch` itself
+        old = (comm.broadcast, torch.cuda.FloatTensor)
+        comm.broadcast = lambda t, devices=None: [t]
+        torch.cuda.FloatTensor = torch.FloatTensor
+        try:
+            return ref_loss.get_max_preds_soft_pytorch(batch_heatmaps, normalize)
+        finally:
+            comm.broadcast, torch.cuda.FloatTensor = old
+    return dict(get_max_preds=ref_loss.get_max_preds, generate_target=generate_heatmap.generate_target,
+                get_max_preds_soft_pytorch=soft)
 
 
 def load_model_cfg(name):

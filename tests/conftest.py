@@ -16,7 +16,20 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "models")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models")}
+
+
+def soft_inputs():
+    """the heatmaps of tests/golden/make_golden.py::soft_inputs (kept in sync by test_oracle.py)"""
+    import torch
+    g = torch.Generator().manual_seed(12)
+    hm = torch.randn((4, 15, 64, 64), generator=g)
+    hm[1] *= 8.0
+    hm[2] *= 0.05
+    hm[3, 0] = 0.25
+    hm[3, 1] = 0.0; hm[3, 1, 5, 60] = 30.0
+    hm[3, 2] = -50.0; hm[3, 2, 63, 0] = 40.0; hm[3, 2, 0, 63] = 40.0
+    return hm
 
 
 @pytest.fixture(scope="session")

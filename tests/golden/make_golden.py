@@ -74,6 +74,28 @@ def golden_decode(fn):
     print("get_max_preds:", {k: v.shape for k, v in out.items()})
 
 
+def soft_inputs():
+    """finite heatmaps: random logits at several temperatures, rendered-Gaussian-like peaks, a constant map"""
+    g = torch.Generator().manual_seed(12)
+    hm = torch.randn((4, 15, 64, 64), generator=g)
+    hm[1] *= 8.0                                      # peaky softmax
+    hm[2] *= 0.05                                     # nearly uniform
+    hm[3, 0] = 0.25                                   # constant -> centre of mass (31.5, 31.5)
+    hm[3, 1] = 0.0; hm[3, 1, 5, 60] = 30.0            # one dominant cell
+    hm[3, 2] = -50.0; hm[3, 2, 63, 0] = 40.0; hm[3, 2, 0, 63] = 40.0   # two equal peaks
+    return hm
+
+
+def golden_soft(fn):
+    hm = soft_inputs()
+    out = {}
+    for tag, norm in (("raw", False), ("norm", True)):
+        p, m = fn(hm.clone(), normalize=norm)
+        out["preds_" + tag], out["maxvals_" + tag] = p.numpy(), m.numpy()
+    np.savez_compressed(os.path.join(HERE, "get_max_preds_soft.npz"), **out)
+    print("get_max_preds_soft:", {k: v.shape for k, v in out.items()})
+
+
 def golden_models(cls, gen_target):
     B = 1
     feat, bfb = synth.synth_features(B, 4, seed=0)
@@ -126,4 +148,5 @@ if __name__ == "__main__":
     fns = ref_import.import_functions()
     golden_generate_target(fns["generate_target"])
     golden_decode(fns["get_max_preds"])
+    golden_soft(fns["get_max_preds_soft_pytorch"])
     golden_models(ref_import.import_estimators(), fns["generate_target"])

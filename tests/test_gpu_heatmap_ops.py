@@ -130,3 +130,29 @@ def test_msda_op_vs_oracle(ops):
         got = ops.MultiScaleDeformableAttnFunction.apply(value.cuda(), torch.tensor([[64, 64]]).cuda(), torch.tensor([0]).cuda(),
                                                          loc.cuda(), aw.cuda(), 32).cpu()
         assert rel_err(got.numpy(), want.numpy()) < 1e-5
+
+
+def test_soft_argmax_decoder(ops, golden):
+    """D1s get_max_preds_soft_pytorch through the C ABI vs the golden vectors of the live reference and the oracle.
+    Floating point: coordinates within 1e-3 relative of the map size (64), i.e. 1e-4 px measured margin below."""
+    import torch
+    from conftest import soft_inputs
+    from oracle import model_ref
+    g = golden["get_max_preds_soft"]
+    hm = soft_inputs()
+    for tag, norm in (("raw", False), ("norm", True)):
+        p, m = ops.get_max_preds_soft_pytorch(hm.cuda(), normalize=norm)
+        assert p.shape == (4, 15, 2) and m.shape == (4, 15, 1)
+        scale = 1.0 if norm else 64.0
+        assert float(np.abs(p.cpu().numpy() - g["preds_" + tag]).max()) < 1e-4 * scale
+        assert np.array_equal(m.cpu().numpy(), g["maxvals_" + tag])
+    # larger random batch incl. a non-square map, vs the oracle
+    gen = torch.Generator().manual_seed(3)
+    big = torch.randn((37, 16, 48, 64), generator=gen) * 3.0
+    p, m = ops.get_max_preds_soft_pytorch(big.cuda())
+    rp, rm = model_ref.get_max_preds_soft_pytorch(big)
+    assert float((p.cpu() - rp).abs().max()) < 5e-3 and torch.equal(m.cpu(), rm)
+    with pytest.raises(AssertionError):
+        ops.get_max_preds_soft_pytorch(big[0].cuda())
+    e, _ = ops.get_max_preds_soft_pytorch(big[:0].cuda())
+    assert e.shape == (0, 16, 2)

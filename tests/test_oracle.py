@@ -79,3 +79,23 @@ def test_oracle_vs_live_reference(oracle_lib):
     p, m, v = fns["get_max_preds"](hm.clone(), 0.5, True)
     op, om, ov, _ = orc_get_max_preds(oracle_lib, hm.numpy(), 0.5, True)
     assert np.array_equal(op, p.numpy()) and np.array_equal(om, m.numpy()) and np.array_equal(ov, v.numpy())
+
+
+def test_soft_argmax_oracle_matches_golden(golden):
+    """oracle restatement of get_max_preds_soft_pytorch (utils/loss.py:145-177) vs vectors from the live reference"""
+    from conftest import soft_inputs
+    from oracle import model_ref
+    g = golden["get_max_preds_soft"]
+    hm = soft_inputs()
+    for tag, norm in (("raw", False), ("norm", True)):
+        p, m = model_ref.get_max_preds_soft_pytorch(hm, norm)
+        assert p.shape == (4, 15, 2) and m.shape == (4, 15, 1)
+        assert np.allclose(p.numpy(), g["preds_" + tag], rtol=0, atol=1e-5)
+        assert np.array_equal(m.numpy(), g["maxvals_" + tag])
+    # known answers: constant map and two equal opposite peaks -> the centre; one dominant cell -> that cell
+    assert np.allclose(g["preds_raw"][3, 0], [31.5, 31.5], atol=1e-4) and np.allclose(g["preds_raw"][3, 2], [31.5, 31.5], atol=1e-4)
+    assert np.allclose(g["preds_raw"][3, 1], [60.0, 5.0], atol=1e-4)
+    if ref_import.available():
+        fn = ref_import.import_functions()["get_max_preds_soft_pytorch"]
+        p2, m2 = fn(hm.clone(), False)
+        assert np.array_equal(p2.numpy(), g["preds_raw"]) and np.array_equal(m2.numpy(), g["maxvals_raw"])
