@@ -42,7 +42,8 @@ STAGE_FLOPS = {
 }
 # algorithmic HBM bytes per 4-view frame of every stage (act = bytes per activation element: 2 in bf16 mode; the pose3d
 # proposal branch P2* keeps fp32/TF32 activations; weights are counted once per batch for the one stage where they
-# dominate, P2mlp0).  `exp` = 1 when the chained forward also exports the TF32 channels-last refined features.
+# dominate, P2mlp0).  `exp` = 1 when the forward also exports the TF32 channels-last refined features, 2 when in addition the NCHW fp32 refined
+# features are not materialised (chained model).
 STAGE_BYTES = {
     "stage_nhwc": lambda act, exp, B: 4 * 4096 * 128 * (4 + act),
     "H1a": lambda act, exp, B: 4 * 4096 * 128 * act * 2,
@@ -57,7 +58,7 @@ STAGE_BYTES = {
     "F1c": lambda act, exp, B: 4 * 1024 * (512 + 128) * act,
     "R1a": lambda act, exp, B: 4 * 1024 * 256 * act,
     "R1b": lambda act, exp, B: 4 * 1024 * 256 * act,
-    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * (4 + act + 4 * exp)),
+    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * ((0 if exp == 2 else 4) + act + (4 if exp else 0))),
     "H2a": lambda act, exp, B: 4 * (4096 * 128 + 1024 * 256) * act,
     "H2b": lambda act, exp, B: 4 * 1024 * 512 * act,
     "H2c": lambda act, exp, B: 4 * 1024 * 384 * act,
@@ -301,7 +302,8 @@ def main():
     e2e_fn = None
 
     if args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
-        pipe = HotPathPipeline(4, "ego4view_syn", args.precision, dev)
+        # mvfex_pose3d = the chained model (EgoPoseFormerMVFEX.forward returns poses + heatmaps): refined features internal
+        pipe = HotPathPipeline(4, "ego4view_syn", args.precision, dev, materialize_features=(args.workload != "mvfex_pose3d"))
         nb = min(B, 64)
         feat_h, bfb_h = synth.synth_features(nb, 4, seed=100 + rank)        # [nb,4,128,64,64] = 8.4 MB/frame
         if nb < B:
@@ -346,7 +348,7 @@ def main():
                     yield step(f, b).cpu()
     elif args.workload == "rw_e2e":
         # BASELINE config 5: images -> backbone (PyTorch) -> hot path (rw cameras, per-frame device->camera transforms)
-        pipe = HotPathPipeline(4, "ego4view_rw", args.precision, dev, with_backbone=True)
+        pipe = HotPathPipeline(4, "ego4view_rw", args.precision, dev, with_backbone=True, materialize_features=False)
         g = torch.Generator().manual_seed(rank)
         img_h = torch.randn(B, 4, 3, 256, 256, generator=g).pin_memory()
         ctm_h = synth.synth_coord_trans_mat(B, seed=rank).pin_memory()
@@ -472,7 +474,8 @@ def main():
                 name, tot, cnt = item.split(":")
                 stages[name] = float(tot) / n_prof           # ms per step
         total = sum(stages.values())
-        exp = 1 if args.workload in ("mvfex_pose3d", "mvfex") else 0     # HotPathPipeline exports the staged copies
+        # HotPathPipeline exports the staged copies (1); the chained workload does not materialise the NCHW features (2)
+        exp = 2 if args.workload == "mvfex_pose3d" else 1 if args.workload == "mvfex" else 0
         per_stage = {k: stage_roofline(k, v, B, act, exp, peaks) for k, v in stages.items()}
         # the roofline line is for the dominant kernel that HAS a roofline (the token phases are chains of ~15-45
         # latency-bound launches, reported in stages_ms)

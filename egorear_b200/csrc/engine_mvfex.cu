@@ -613,8 +613,10 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_forward: null handle");
     if (int rc = require_device()) return rc;
     EGR_CHECK(h->packed, EGR_ERR_STATE, "mvfex_forward: parameters changed or never packed; call egr_mvfex_prepack");
-    EGR_CHECK(B > 0 && feat && bfb && hm_init && hm_refined && feat_refined && workspace, EGR_ERR_INVALID,
+    EGR_CHECK(B > 0 && feat && bfb && hm_init && hm_refined && workspace, EGR_ERR_INVALID,
               "mvfex_forward: null pointer / empty batch");
+    EGR_CHECK(feat_refined || h->export_staged, EGR_ERR_INVALID,
+              "mvfex_forward: feat_refined may be NULL only when the channels-last copies are exported (egr_mvfex_export_staged)");
     for (int r = 0; r < h->V; ++r)
         EGR_CHECK(h->has_heads && h->has_ref[r], EGR_ERR_STATE, "mvfex_forward: parameters of the init heads / refiner %d were not registered", r);
     Bufs w;

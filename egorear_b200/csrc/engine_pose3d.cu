@@ -411,7 +411,9 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_forward: null handle");
     if (int rc = require_device()) return rc;
     EGR_CHECK(h->packed, EGR_ERR_STATE, "pose3d_forward: parameters changed or never packed; call egr_pose3d_prepack");
-    EGR_CHECK(B > 0 && feats_init && feats_final && preds && workspace, EGR_ERR_INVALID, "pose3d_forward: null pointer");
+    EGR_CHECK(B > 0 && preds && workspace, EGR_ERR_INVALID, "pose3d_forward: null pointer");
+    EGR_CHECK((feats_final || h->st_final_tf32 || h->st_final_bf16) && (feats_init || feats_final || h->st_sampled), EGR_ERR_INVALID,
+              "pose3d_forward: a NULL NCHW input needs its staged channels-last copy (egr_pose3d_use_staged)");
     const int is_rw = (h->cam_model & 1);
     EGR_CHECK(!is_rw || coord_trans_mat, EGR_ERR_INVALID, "pose3d_forward: ego4view_rw* needs coord_trans_mat [B,V,4,4] fp32");
     PBufs w;
@@ -438,10 +440,14 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     const bool p2a_bf16_in = st_fb && rnd && h->c0_bf16 && !st_f;     // chained forward without the TF32 copy
     if (st_f && rnd) Xf = st_f;
     else if (p2a_bf16_in) Xf = st_fb;
-    else if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
+    else {
+        EGR_CHECK(feats_final, EGR_ERR_INVALID, "pose3d_forward: feats_final is NULL and its staged copy does not fit this precision");
+        if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
+    }
     const void* Xs = Xf;
     if (st_s && st_s_bf16 == bfs) Xs = st_s;
     else if (sampled != feats_final || bfs != bf || rnd) {
+        EGR_CHECK(sampled, EGR_ERR_INVALID, "pose3d_forward: the sampled map is NULL and its staged copy does not fit this precision");
         if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
         Xs = w.Xi;
     }

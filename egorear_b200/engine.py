@@ -119,9 +119,10 @@ class MvfexEngine(_EngineBase):
         _lib.check(self._lib.egr_mvfex_export_staged(self._h, (1 if tf32_final else 2) if enable else 0))
         self._export = bool(enable)
 
-    def forward(self, feat, bfb, heatmap_for_anchor=None):
+    def forward(self, feat, bfb, heatmap_for_anchor=None, want_feat_refined=True):
         """feat [B,V,128,64,64], bfb [B,V,512,8,8] fp32 CUDA ->
-        dict(hm_init, hm_refined [B,V,15,64,64], feat_refined [B,V,128,64,64], anchors_2d [B,V,15,2], anchors_valid)."""
+        dict(hm_init, hm_refined [B,V,15,64,64], feat_refined [B,V,128,64,64], anchors_2d [B,V,15,2], anchors_valid).
+        want_feat_refined=False (needs export_staged): the NCHW fp32 refined features are not materialised (None)."""
         self._sync_params()
         B, V = feat.shape[:2]
         assert V == self.V and tuple(feat.shape[2:]) == (128, 64, 64) and tuple(bfb.shape[1:]) == (V, 512, 8, 8)
@@ -133,7 +134,7 @@ class MvfexEngine(_EngineBase):
         out = {
             "hm_init": torch.empty((B, V, self.J, 64, 64), dtype=torch.float32, device=dev),
             "hm_refined": torch.empty((B, V, self.J, 64, 64), dtype=torch.float32, device=dev),
-            "feat_refined": torch.empty((B, V, 128, 64, 64), dtype=torch.float32, device=dev),
+            "feat_refined": torch.empty((B, V, 128, 64, 64), dtype=torch.float32, device=dev) if want_feat_refined else None,
             "anchors_2d": torch.empty((B, V, self.J, 2), dtype=torch.float32, device=dev),
             "anchors_valid": torch.empty((B, V, self.J), dtype=torch.bool, device=dev),
         }
@@ -191,10 +192,11 @@ class Pose3DEngine(_EngineBase):
         """-> preds [L+1, B, 16, 3] fp32 (cm): preds[0] MLP proposal, preds[1:] transformer layers.
         staged: MvfexEngine.forward(...)["staged"] of the SAME tensors (chained forward): skips the re-staging passes."""
         self._sync_params()
-        B, V = feats_final.shape[:2]
+        ref = feats_final if feats_final is not None else feats_init
+        B, V = ref.shape[:2]
         assert V == self.V
-        fi = feats_init.detach().float().contiguous()
-        ff = feats_final.detach().float().contiguous()
+        fi = feats_init.detach().float().contiguous() if feats_init is not None else None
+        ff = feats_final.detach().float().contiguous() if feats_final is not None else None
         ctm = None
         if self.camera_model.startswith("ego4view_rw"):
             if coord_trans_mat is None:
@@ -203,8 +205,8 @@ class Pose3DEngine(_EngineBase):
                 # the reference matmuls this against fp32 points (utils/camera_models.py:210): dtype error there too
                 raise RuntimeError("expected m1 and m2 to have the same dtype, but got: double != float")
             ctm = coord_trans_mat.contiguous()
-        preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=ff.device)
-        ws = self._workspace(B, ff.device)
+        preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=ref.device)
+        ws = self._workspace(B, ref.device)
         if staged is not None and staged["feat_refined"] is feats_final and (staged["feat"] is feats_init or not use_init):
             sampled = staged["init"] if use_init else staged["refined"]
             _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),

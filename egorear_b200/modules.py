@@ -464,10 +464,13 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
             return torch.cat((ff, fb), dim=1), [torch.cat((a, b), dim=1) for a, b in zip(bf, bb)]
         return self.heatmap_estimator_stereo_front.forward_backbone(img, return_feat=True)
 
-    def forward_from_feats(self, frame_feat_multi_view, backbone_feat_bottom_multi_view, heatmap_for_anchor=None):
-        """The hot path proper: backbone features in, (list_heatmap_pred, list_frame_feat) out (:284-437)."""
+    def forward_from_feats(self, frame_feat_multi_view, backbone_feat_bottom_multi_view, heatmap_for_anchor=None,
+                           want_feat_refined=True):
+        """The hot path proper: backbone features in, (list_heatmap_pred, list_frame_feat) out (:284-437).
+        want_feat_refined=False (chained forward with exported channels-last copies only): list_frame_feat[1] is None."""
         hfa = heatmap_for_anchor if isinstance(heatmap_for_anchor, torch.Tensor) else None
-        out = self.engine().forward(frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa)
+        out = self.engine().forward(frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa,
+                                    want_feat_refined=want_feat_refined)
         self.last_anchors = (out["anchors_2d"], out["anchors_valid"])
         self.last_staged = out.get("staged")
         return [out["hm_init"], out["hm_refined"]], [frame_feat_multi_view, out["feat_refined"]]
@@ -577,7 +580,8 @@ class EgoPoseFormerMVFEX(nn.Module):
     def forward_from_feats(self, feat, bfb, coord_trans_mat=None, origin_3d=None):
         if self._chain:
             self.heatmap_estimator.engine().export_staged(True)
-        list_hm, list_ff = self.heatmap_estimator.forward_from_feats(feat, bfb)
+        # the chained model returns (poses, heatmaps) only (:50-58): the refined features stay channels-last, internal
+        list_hm, list_ff = self.heatmap_estimator.forward_from_feats(feat, bfb, want_feat_refined=not self._chain)
         return self.pose3d_estimator(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, origin_3d,
                                      staged=self.heatmap_estimator.last_staged), list_hm
 

@@ -14,7 +14,7 @@ from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
 
 class HotPathPipeline:
     def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True,
-                 with_backbone=False, tf32_final=True):
+                 with_backbone=False, tf32_final=True, materialize_features=True):
         self.V, self.camera_model, self.precision = num_views, camera_model, precision
         self.heatmap = EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(num_views, camera_model), precision=precision,
                                                  build_backbone=with_backbone)
@@ -27,6 +27,9 @@ class HotPathPipeline:
         # chained forward: pose3d reuses the channels-last copies; tf32_final=False drops the TF32 copy of the refined
         # features (537 MB per 64 frames): conv_frame_feat.0 then reads the bf16 copy
         self.heatmap.engine().export_staged(True, tf32_final=tf32_final)
+        # materialize_features=False: like EgoPoseFormerMVFEX.forward (egoposeformer_mvf_ex.py:50-58), which returns poses
+        # and heatmaps only, the refined features are not written out in NCHW fp32 (list_ff[1] is None)
+        self.materialize_features = materialize_features
         self._lanes, self._next_lane, self._pending = None, 0, []
 
     def freeze(self):
@@ -38,7 +41,8 @@ class HotPathPipeline:
 
     @torch.no_grad()
     def forward(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None):
-        list_hm, list_ff = self.heatmap.forward_from_feats(feat, bfb, heatmap_for_anchor)
+        list_hm, list_ff = self.heatmap.forward_from_feats(feat, bfb, heatmap_for_anchor,
+                                                           want_feat_refined=self.materialize_features)
         B, V, J, H, W = list_hm[-1].shape
         pts2d, maxvals, valid = ops.get_max_preds(list_hm[-1].view(B * V, J, H, W), threshold=0.5, normalize=False)
         preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, staged=self.heatmap.last_staged)

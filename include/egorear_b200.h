@@ -187,6 +187,9 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
  * egr_pose3d_use_staged lets the NEXT egr_pose3d_forward skip re-staging its NCHW inputs (the hint is consumed by that
  * call; the NCHW pointers must still be the same tensors).  [V][B][64*64][128] layout. */
 int egr_mvfex_export_staged(egr_mvfex* h, int enable);   /* 0 off, 1 all three copies, 2 without the TF32 copy */
+/* With export enabled, egr_mvfex_forward accepts feat_refined == NULL (the chained EgoPoseFormerMVFEX.forward never
+ * returns the refined features, :50-58) and egr_pose3d_forward accepts NULL for an NCHW input whose staged copy was
+ * handed over with egr_pose3d_use_staged. */
 int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const float** refined_nhwc_tf32,
                      int* act_is_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward

@@ -216,3 +216,19 @@ def test_batch_invariance(precision, tol):
         assert rel_err(one["list_ff"][-1][0].cpu(), ff_full[i].cpu()) < tol
         d = float((one["pose3d"][0] - pose_full[i]).norm(dim=-1).mean())
         assert d < 0.01, "pose differs by %.3e cm between batch sizes" % d
+
+
+def test_pipeline_without_materialised_features():
+    """materialize_features=False (the chained model returns poses + heatmaps only, egoposeformer_mvf_ex.py:50-58): the
+    NCHW fp32 refined features are never written, pose3d lifts the channels-last copies; the joints are bit-identical."""
+    from egorear_b200 import synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    a = HotPathPipeline(4, "ego4view_syn", "bf16", dev, materialize_features=True)
+    b = HotPathPipeline(4, "ego4view_syn", "bf16", dev, materialize_features=False)
+    feat, bfb = [t.to(dev) for t in synth.synth_features(3, 4, seed=91)]
+    oa, ob = a(feat, bfb), b(feat, bfb)
+    assert ob["list_ff"][-1] is None and oa["list_ff"][-1] is not None
+    assert torch.equal(oa["packed"], ob["packed"])
+    for x, y in zip(oa["list_hm"], ob["list_hm"]):
+        assert torch.equal(x, y)
