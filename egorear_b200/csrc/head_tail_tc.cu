@@ -6,9 +6,10 @@
 // :579-583, with the preceding 1x1 conv commuted in front of the upsample).  The SIMT version spends 16 FMAs per
 // interpolated value on the 1x1 conv; here one CTA = 4 output rows = 256 pixels = two M=128 tcgen05 tiles:
 //   1. the (at most) 4 source rows of z are staged in shared memory (padded pixel stride, conflict-free LDS.128)
-//   2. thread t interpolates pixel t for all 128 channels in fp32, applies ReLU and writes the bf16 row straight
-//      into the K-major SWIZZLE_128B A tile
-//   3. one thread issues 2 x 8 tcgen05.mma (M=128, N=16, K=16) against the bf16 weight tile, accumulators in TMEM
+//   2. thread t interpolates pixel t in fp32 (64 channels = one k-block at a time), applies ReLU and writes the bf16
+//      row straight into the K-major SWIZZLE_128B A tile
+//   3. one thread issues 2 x 4 tcgen05.mma (M=128, N=16, K=16) per k-block against the bf16 weight tile, accumulators
+//      in TMEM; 71 KB of shared memory -> three CTAs per SM overlap each other's load / MMA / store phases
 //   4. tcgen05.ld gives thread t the 16 joint values of pixel t; 32 lanes = 32 consecutive x -> 128 B stores per joint
 #include "layout_ops.cuh"
 #include "tc_ptx.cuh"
@@ -19,8 +20,8 @@ namespace {
 
 constexpr int HT_FS = 32, HT_FO = 64, HT_C = 128, HT_STRIP = 4, HT_ROWS = 4, HT_NJ = 16;
 constexpr int HT_PST = 272;                                  // bytes per staged source pixel: 256 + 16
-constexpr int HT_OFF_A = 0;                                  // [2 M-tiles][2 k-blocks][128 rows][128 B] = 64 KB
-constexpr int HT_OFF_W = 2 * 2 * 128 * 128;                  // [2 k-blocks][16 rows][128 B]             =  4 KB
+constexpr int HT_OFF_A = 0;                                  // [2 M-tiles][128 rows][128 B] = 32 KB (one 64-channel k-block at a time)
+constexpr int HT_OFF_W = 2 * 128 * 128;                      // [2 k-blocks][16 rows][128 B] =  4 KB
 constexpr int HT_OFF_SRC = HT_OFF_W + 2 * 16 * 128;          // [4 rows x 32 px][272 B]
 constexpr int HT_OFF_BAR = HT_OFF_SRC + HT_ROWS * HT_FS * HT_PST;
 constexpr int HT_SMEM = HT_OFF_BAR + 64 + 1024 /*align*/;
@@ -78,7 +79,7 @@ __device__ __forceinline__ uint32_t interp_word(uint32_t a, uint32_t b, uint32_t
     return pack_relu_bf16x2(lo, hi);
 }
 
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias, int4 wsel,
                     int B, int J, float* __restrict__ hm, int64_t hm_bs, int64_t hm_gs, __nv_bfloat16* __restrict__ hm_t) {
     extern __shared__ __align__(1024) uint8_t ht_raw[];
@@ -133,7 +134,9 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- interpolate + ReLU: pixel `tid` -> row (tid & 127) of A tile (tid >> 7) ----
+    // ---- interpolate + ReLU: pixel `tid` -> row (tid & 127) of A tile (tid >> 7), one 64-channel k-block at a time ----
+    // (the A tiles hold a single k-block so that three CTAs fit an SM; the second half is interpolated once the MMAs of the
+    //  first have finished reading the tile - the other resident CTAs fill that wait)
     const int yy = tid >> 6, x = tid & 63;
     const int y = y0 + yy;
     {
@@ -145,40 +148,42 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
         const uint32_t p11 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i1) * HT_PST;
         const float w00 = cy.l0 * cx.l0, w01 = cy.l0 * cx.l1, w10 = cy.l1 * cx.l0, w11 = cy.l1 * cx.l1;
         const int r = tid & 127;
-        const uint32_t arow = smem_u32(sA) + (tid >> 7) * 32768 + r * 128;
+        const uint32_t arow = smem_u32(sA) + (tid >> 7) * 16384 + r * 128;
         const int sw = r & 7;
+#pragma unroll 1
+        for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
-        for (int pc = 0; pc < 16; ++pc) {
-            const uint4 a = lds128(p00 + pc * 16), bb = lds128(p01 + pc * 16);
-            const uint4 c = lds128(p10 + pc * 16), d = lds128(p11 + pc * 16);
-            uint4 o;
-            o.x = interp_word(a.x, bb.x, c.x, d.x, w00, w01, w10, w11);
-            o.y = interp_word(a.y, bb.y, c.y, d.y, w00, w01, w10, w11);
-            o.z = interp_word(a.z, bb.z, c.z, d.z, w00, w01, w10, w11);
-            o.w = interp_word(a.w, bb.w, c.w, d.w, w00, w01, w10, w11);
-            sts128(arow + (pc >> 3) * 16384 + (((pc & 7) ^ sw) << 4), o);
-        }
-    }
-    fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-        tc_fence_after();
-        constexpr uint32_t idesc = make_idesc(128, HT_NJ, false);
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb) {
-                const uint64_t da = make_smem_desc(smem_u32(sA + mt * 32768 + kb * 16384));
+            for (int pp = 0; pp < 8; ++pp) {
+                const int pc = kb * 8 + pp;
+                const uint4 a = lds128(p00 + pc * 16), bb = lds128(p01 + pc * 16);
+                const uint4 c = lds128(p10 + pc * 16), d = lds128(p11 + pc * 16);
+                uint4 o;
+                o.x = interp_word(a.x, bb.x, c.x, d.x, w00, w01, w10, w11);
+                o.y = interp_word(a.y, bb.y, c.y, d.y, w00, w01, w10, w11);
+                o.z = interp_word(a.z, bb.z, c.z, d.z, w00, w01, w10, w11);
+                o.w = interp_word(a.w, bb.w, c.w, d.w, w00, w01, w10, w11);
+                sts128(arow + ((pp ^ sw) << 4), o);
+            }
+            fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+            tc_fence_before();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+                constexpr uint32_t idesc = make_idesc(128, HT_NJ, false);
                 const uint64_t db = make_smem_desc(smem_u32(sW + kb * 2048));
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    tc_mma<false>(tmem_base + mt * HT_NJ, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                for (int mt = 0; mt < 2; ++mt) {
+                    const uint64_t da = make_smem_desc(smem_u32(sA + mt * 16384));
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+                        tc_mma<false>(tmem_base + mt * HT_NJ, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                }
+                tc_commit(smem_u32(bar));
             }
-        tc_commit(smem_u32(bar));
+            __syncwarp();
+            mbar_wait(smem_u32(bar), kb);      // k-block 0: the tile may be overwritten; k-block 1: accumulators complete
+        }
     }
-    __syncwarp();
-    mbar_wait(smem_u32(bar), 0);
     tc_fence_after();
     uint32_t v[16];
     tc_ld16_issue(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * HT_NJ, v);

@@ -248,9 +248,11 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
         for (int i = threadIdx.x; i < n16; i += 256) dst[i] = __ldg(src + i);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npix * FCH; i += 256) {
-        const int p = i / FCH, c = i - p * FCH;
-        s2[c * SLD + p] = s1[i];
+    if (out_nchw) {       // the transposed copy only serves the NCHW pass
+        for (int i = threadIdx.x; i < npix * FCH; i += 256) {
+            const int p = i / FCH, c = i - p * FCH;
+            s2[c * SLD + p] = s1[i];
+        }
     }
     // ---- channels-last copy: item = (pixel, 8 channels) ----
     if (out_nhwc || out_nhwc_tf32) {
@@ -477,7 +479,8 @@ int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;
-        const size_t fsmem = es * (FROWS * FS * FCH + FCH * 130);
+        // the transposed tile only serves the NCHW pass: without it the block needs half the shared memory
+        const size_t fsmem = es * (FROWS * FS * FCH + (out_nchw ? FCH * 130 : 0));
         dim3 fgrid(FO / FSTRIP, G * B);
         if (z_bf16) {
             auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
