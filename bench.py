@@ -192,7 +192,7 @@ class CpuPath:
             return self.model_ref.pose3d_forward(self.sd_p, lf[0], lf[-1], self.calib, "ego4view_syn")[-1]
 
 
-def cpu_baseline(budget_s=15.0, frames_per_step=2):
+def cpu_baseline(budget_s=12.0, frames_per_step=2):
     from egorear_b200 import synth
     cp = CpuPath()
     feat, bfb = synth.synth_features(frames_per_step, 4, seed=0)
@@ -201,7 +201,7 @@ def cpu_baseline(budget_s=15.0, frames_per_step=2):
     while True:
         cp.step(feat, bfb)
         n += frames_per_step
-        if time.time() - t0 > budget_s or n >= 64:
+        if time.time() - t0 > budget_s or n >= 256:
             break
     dt = time.time() - t0
     return {"value": n / dt, "unit": UNIT, "cores": cp.cores, "kind": cp.kind,
