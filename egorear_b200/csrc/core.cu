@@ -123,6 +123,7 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
     using namespace egr;
     EGR_CHECK(c && c->A && c->W && c->D, EGR_ERR_INVALID, "dense_stage: null descriptor / operand");
     if (int rc = require_device()) return rc;
+    gemm_tc_set_scratch(nullptr);       // standalone stage: library-owned split-K scratch of this stream
     GemmDesc d;
     d.A = c->A; d.W = c->W; d.bias = c->bias; d.D = c->D; d.aux = c->aux;
     d.M = c->M; d.N = c->N; d.K = c->K; d.lda = c->lda; d.ldd = c->ldd; d.amode = c->amode; d.epi = c->epi;

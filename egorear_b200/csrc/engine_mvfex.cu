@@ -166,6 +166,7 @@ struct Bufs {
     uint8_t* valid;
     float *tx, *tz, *toa, *tA, *tqkv, *to, *thid, *tpool, *tvb;     // batched token path
     float* refn32;                                                  // exported TF32 channels-last refined features
+    float* splitk;                                                  // split-K partial sums of the token GEMMs
 };
 
 enum TokPtr { TP_LNC_W, TP_LNC_B, TP_LNS_W, TP_LNS_B, TP_LNF_W, TP_LNF_B, TP_PN_W, TP_PN_B, TP_PTAB, TP_BFB_T, TP_BFB_B, TP_JQ,
@@ -209,6 +210,7 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
         b.tpool = (float*)c.take((int64_t)G * B * 512 * 4);
         b.tvb = (float*)c.take((int64_t)G * B * EMB * 4);
     }
+    b.splitk = (float*)c.take(SPLITK_SCRATCH_BYTES);
     if (o) *o = b;
     return c.off + 256;
 }
@@ -626,6 +628,7 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     cudaStream_t st = (cudaStream_t)stream;
     const int V = h->V, J = h->J, prec = h->prec, bf = (prec == EGR_PREC_BF16);
     int rc;
+    gemm_tc_set_scratch(w.splitk);
     EGR_MARK("stage_nhwc", st);
     // S0: NCHW fp32 -> view-major channels-last staging copy
     if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, bf, st))) return rc;
@@ -706,6 +709,7 @@ extern "C" int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float
     cudaStream_t st = (cudaStream_t)stream;
     const int bf = (h->prec == EGR_PREC_BF16), J = h->J;
     int rc;
+    gemm_tc_set_scratch(w.splitk);
     if ((rc = nchw_to_nhwc(feat_mv, w.Xh, B, h->V, FC, FHW, bf, st))) return rc;
     if ((rc = nchw_to_nhwc(frame_feat, w.Xown, B, 1, FC, FHW, bf, st))) return rc;
     if ((rc = cast_act(heatmap, w.hmT, bf, (int64_t)B * J * FHW, st))) return rc;

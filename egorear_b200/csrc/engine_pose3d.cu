@@ -143,6 +143,7 @@ struct PBufs {
     float *m0, *m1, *anch;
     uint8_t* valid;
     float *tx, *tz, *toa, *tA, *tqkv, *to, *thid, *tp3;     // batched token path
+    float* splitk;                                          // split-K partial sums
 };
 
 int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
@@ -173,6 +174,7 @@ int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
         b.thid = (float*)c.take(T * TOK_FF * 4);
         b.tp3 = (float*)c.take(T * 4 * 4);
     }
+    b.splitk = (float*)c.take(SPLITK_SCRATCH_BYTES);
     if (o) *o = b;
     return c.off + 256;
 }
@@ -426,6 +428,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     const int prec = p2_prec(h), bf = (prec == EGR_PREC_BF16);   // proposal-branch dtype
     const int VB = V * B;
     int rc;
+    gemm_tc_set_scratch(w.splitk);
     EGR_MARK("P_stage_nhwc", st);
     // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
     const float* sampled = h->use_init ? feats_init : feats_final;

@@ -51,6 +51,11 @@ int gemm_simt(const GemmDesc& d, int a_is_bf16, int d_is_bf16, cudaStream_t st);
 // tcgen05 + TMA path.  A, W both bf16 (kind::f16) or both fp32 read as TF32 (kind::tf32, in_is_f32); D bf16 or fp32.
 int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled; EGR_OK or error
+// split-K partial sums go to a caller-provided scratch of SPLITK_SCRATCH_BYTES (the engines carve it from their workspace,
+// so a forward performs no allocation and can be captured into a CUDA graph); without one (egr_dense_stage) the library
+// keeps one lazily allocated scratch per stream.  Thread-local; pass nullptr to clear.
+constexpr int64_t SPLITK_SCRATCH_BYTES = 32ll << 20;
+void gemm_tc_set_scratch(float* scratch);
 
 struct Up2Coef {
     int i0, i1;

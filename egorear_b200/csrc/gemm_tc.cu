@@ -451,7 +451,8 @@ std::mutex g_tc_mu;
 bool g_tc_ready = false;
 // split-K partial sums: one scratch buffer per launch stream (forwards of different streams may overlap)
 std::unordered_map<cudaStream_t, float*> g_splitk_scratch;
-constexpr int64_t SPLITK_SCRATCH_FLOATS = 8ll << 20;   // 32 MB
+constexpr int64_t SPLITK_SCRATCH_FLOATS = SPLITK_SCRATCH_BYTES / 4;
+thread_local float* t_scratch = nullptr;
 
 int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
            const cuuint32_t* box, const char* what, bool swizzle64 = false) {
@@ -496,6 +497,8 @@ int set_smem_attr_bn() {
 }
 
 }  // namespace
+
+void gemm_tc_set_scratch(float* scratch) { t_scratch = scratch; }
 
 int gemm_tc_init() {
     std::lock_guard<std::mutex> lk(g_tc_mu);
@@ -578,7 +581,9 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         p.ksplit = ks;
         p.partial = 1;
         p.part_stride = (int64_t)d.M * d.N;
-        {
+        if (t_scratch) {
+            p.D = t_scratch;
+        } else {
             std::lock_guard<std::mutex> lk(g_tc_mu);
             float*& sc = g_splitk_scratch[st];
             if (!sc) EGR_CUDA_OK(cudaMalloc(&sc, SPLITK_SCRATCH_FLOATS * sizeof(float)));

@@ -71,6 +71,49 @@ class HotPathPipeline:
             bfb[i:i + chunk].copy_(bb[-1])
         return feat, bfb
 
+    # ---- latency mode: the whole forward as one CUDA graph ----
+    def capture(self, B, with_coord_trans_mat=False):
+        """Capture the synchronous forward for batch size B into a CUDA graph (the ~95 launches of a step, with their
+        programmatic-dependent-launch edges, become one graph launch: what a real-time B=1 loop needs).  The forward
+        allocates nothing on the device side (workspaces are cached per lane, split-K scratch lives in the workspace), so
+        the capture is legal; weights must be frozen.  Use replay(feat, bfb) afterwards."""
+        dev = next(self.heatmap.parameters()).device
+        self.freeze()
+        eh, ep = self.heatmap.engine(), self.pose3d.engine()
+        lane = 1000 + B                                    # private workspaces: replays may interleave with eager calls
+        feat = torch.zeros((B, self.V, 128, 64, 64), dtype=torch.float32, device=dev)
+        bfb = torch.zeros((B, self.V, 512, 8, 8), dtype=torch.float32, device=dev)
+        ctm = torch.eye(4, device=dev).repeat(B, self.V, 1, 1).contiguous() if with_coord_trans_mat else None
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        eh.lane = ep.lane = lane
+        try:
+            with torch.cuda.stream(side):                  # warm-up outside the capture: workspaces, lazy inits
+                for _ in range(2):
+                    self.forward(feat, bfb, ctm)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.forward(feat, bfb, ctm)
+        finally:
+            eh.lane = ep.lane = 0
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        self._graphs[B] = (graph, feat, bfb, ctm, out)
+        return self
+
+    def replay(self, feat, bfb, coord_trans_mat=None):
+        """run the captured graph of this batch size on new inputs; returns the graph's static output tensors"""
+        graph, sf, sb, sc, out = self._graphs[feat.shape[0]]
+        sf.copy_(feat, non_blocking=True)
+        sb.copy_(bfb, non_blocking=True)
+        if sc is not None and coord_trans_mat is not None:
+            sc.copy_(coord_trans_mat, non_blocking=True)
+        graph.replay()
+        return out
+
     # ---- throughput mode: independent batches on alternating streams ----
     def forward_async(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None, world=1, lanes=2):
         """Same computation as forward(), enqueued on one of `lanes` internal streams (round robin), each with its own

@@ -232,3 +232,19 @@ def test_pipeline_without_materialised_features():
     assert torch.equal(oa["packed"], ob["packed"])
     for x, y in zip(oa["list_hm"], ob["list_hm"]):
         assert torch.equal(x, y)
+
+
+def test_pipeline_cuda_graph_replay():
+    """capture(B) / replay(): the whole forward as one CUDA graph (no device allocation inside the forward: cached
+    workspaces, split-K scratch carved from the workspace) returns exactly what the eager forward returns"""
+    from egorear_b200 import synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    pipe = HotPathPipeline(4, "ego4view_syn", "bf16", dev, materialize_features=False)
+    pipe.capture(2)
+    for seed in (5, 6):
+        feat, bfb = [t.to(dev) for t in synth.synth_features(2, 4, seed=seed)]
+        want = pipe(feat, bfb)
+        got = pipe.replay(feat, bfb)
+        torch.cuda.synchronize()
+        assert torch.equal(got["packed"], want["packed"]) and torch.equal(got["list_hm"][-1], want["list_hm"][-1])
