@@ -37,12 +37,15 @@ tok_sample_kernel(TokSampleArgs a) {
     const int64_t unit = (int64_t)blockIdx.x * 8 + wib;
     const int64_t total = (int64_t)a.G * a.B * a.J * a.V * NH;
     if (unit >= total) return;
+    // unit order (fastest first): head, refiner group, joint, view, frame.  The groups share the anchors, so the warps of
+    // one CTA gather around the same point of the same view map, and one (frame, view) map (1 MB) is sampled by
+    // neighbouring CTAs while it is resident in L2 / L1
     int64_t r = unit;
     const int h = (int)(r % NH); r /= NH;
-    const int v = (int)(r % a.V); r /= a.V;
+    const int g = (int)(r % a.G); r /= a.G;
     const int j = (int)(r % a.J); r /= a.J;
-    const int b = (int)(r % a.B);
-    const int g = (int)(r / a.B);
+    const int v = (int)(r % a.V);
+    const int b = (int)(r / a.V);
     const int64_t t = (int64_t)b * a.J + j, T_ = (int64_t)a.B * a.J;
     float* Arow = a.A + (((int64_t)g * T_ + t) * a.V + v) * a.KA;
     const bool ok = a.valid[((int64_t)b * a.V + v) * a.J + j] != 0;
