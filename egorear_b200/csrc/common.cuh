@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -91,6 +92,15 @@ template <> struct ActT<float> {
 template <> struct ActT<__nv_bfloat16> {
     static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+template <> struct ActT<__half> {
+    static __device__ __forceinline__ float ld(const __half* p) { return __half2float(*p); }
+    static __device__ __forceinline__ void st(__half* p, float v) {       // saturating (|x| > 65504 -> +-65504)
+        unsigned short h;
+        asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+        *reinterpret_cast<unsigned short*>(p) = h;
+    }
 };
 
 // fp32 -> nearest TF32 value (10-bit mantissa, ties away), kept in an fp32 container.  The tensor core TRUNCATES fp32

@@ -135,7 +135,8 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
     EGR_CHECK(d.epi >= EPI_NONE && d.epi <= EPI_RELU_ADDUP, EGR_ERR_INVALID, "dense_stage: epi %d", d.epi);
     cudaStream_t st = (cudaStream_t)stream;
     if (c->use_tc) {
-        return gemm_tc(d, c->a_is_bf16 ? 0 : 1, c->d_is_bf16, st);
+        // a_is_bf16 / d_is_bf16: 0 fp32, 1 bf16, 2 fp16
+        return gemm_tc(d, c->a_is_bf16, c->d_is_bf16, st);
     }
     return gemm_simt(d, c->a_is_bf16, c->d_is_bf16, st);
 }

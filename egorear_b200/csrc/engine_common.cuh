@@ -99,7 +99,7 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
         d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
         d.w_gs = w.stride();
         d.b_gs = w.N;
-        return gemm_tc(d, /*in_is_f32=*/1, /*d_is_bf16=*/0, st);
+        return gemm_tc(d, DT_F32, DT_F32, st);
     }
     d.W = tc ? (const void*)(w.bf16 + (int64_t)set_begin * w.stride())
              : (const void*)(w.f32 + (int64_t)set_begin * w.stride());
@@ -107,7 +107,7 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
     d.w_gs = w.stride();
     d.b_gs = w.N;
     const int d_bf16 = (bf && !out_f32) ? 1 : 0;
-    if (tc) return gemm_tc(d, 0, d_bf16, st);
+    if (tc) return gemm_tc(d, DT_BF16, d_bf16 ? DT_BF16 : DT_F32, st);
     return gemm_simt(d, bf ? 1 : 0, d_bf16, st);
 }
 

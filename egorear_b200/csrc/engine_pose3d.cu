@@ -460,7 +460,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     d.A = Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if (p2a_bf16_in) {      // bf16 x bf16 -> fp32 (rounded to TF32 for P2b)
         d.N = 64; d.K = PC; d.W = h->c0_bf16; d.bias = h->c0.bias;
-        if ((rc = gemm_tc(d, /*in_is_f32=*/0, /*d_is_bf16=*/0, st))) return rc;
+        if ((rc = gemm_tc(d, DT_BF16, DT_F32, st))) return rc;
     } else if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
     EGR_MARK("P2b", st);
     d = GemmDesc();

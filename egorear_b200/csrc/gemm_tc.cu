@@ -17,8 +17,10 @@
 // out-of-bounds part (the zero padding) is filled by the TMA unit.
 #include "gemm.cuh"
 #include "tc_ptx.cuh"
+#include <cuda_fp16.h>
 #include <mutex>
 #include <unordered_map>
+#include <type_traits>
 
 namespace egr {
 using namespace tcx;
@@ -81,18 +83,15 @@ template <> __device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16*
     u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
     *reinterpret_cast<uint4*>(p) = u;
 }
-template <typename TO> __device__ __forceinline__ void load8(const TO* p, float* v);
-template <> __device__ __forceinline__ void load8<float>(const float* p, float* v) {
-    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+template <> __device__ __forceinline__ void store8<__half>(__half* p, const float* v) {
+    // saturating: an out-of-range value becomes +-65504 instead of inf
+    uint4 u;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.z) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.w) : "f"(v[7]), "f"(v[6]));
+    *reinterpret_cast<uint4*>(p) = u;
 }
-template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float* v) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-}
-
 // 8 consecutive elements of TO as loaded (the ADDUP epilogue keeps gathers in flight in this raw form)
 template <typename TO> struct Raw8;
 template <> struct Raw8<__nv_bfloat16> {
@@ -102,6 +101,15 @@ template <> struct Raw8<__nv_bfloat16> {
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+};
+template <> struct Raw8<__half> {
+    uint4 u;
+    __device__ __forceinline__ void ld(const __half* p) { u = __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ void unpack(float* v) const {
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
     }
 };
 template <> struct Raw8<float> {
@@ -339,7 +347,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN, TF32);
+            constexpr uint32_t idesc = make_idesc_fmt(BM, BN, TF32 ? 2u : (std::is_same<TI, __half>::value ? 0u : 1u));
             int stage = 0, phase = 0, it = 0, w_group = -1, w_loads = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 const TileCoord tc = decode_tile(t, p);
@@ -454,10 +462,12 @@ std::unordered_map<cudaStream_t, float*> g_splitk_scratch;
 constexpr int64_t SPLITK_SCRATCH_FLOATS = SPLITK_SCRATCH_BYTES / 4;
 thread_local float* t_scratch = nullptr;
 
-int encode(CUtensorMap* tm, bool f32, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+int encode(CUtensorMap* tm, int dt, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
            const cuuint32_t* box, const char* what, bool swizzle64 = false) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+    const CUtensorMapDataType tdt = dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                  : dt == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r = g_encode(tm, tdt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
@@ -472,15 +482,19 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     EGR_LAUNCH((gemm_tc_kernel<BN, TI, TO>), grid, TC_THREADS, TcCfg<BN>::SMEM, st, tmA, tmB, tmD, p);
     return EGR_OK;
 }
-template <int BN, typename TI>
-int launch_tc_bn(bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
-    return out_bf16 ? launch_tc<BN, TI, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st) : launch_tc<BN, TI, float>(tmA, tmB, tmD, p, grid, st);
+// instantiated (operand, output) pairs: bf16 -> bf16 | fp32, fp16 -> fp16 | fp32, fp32 (TF32) -> fp32
+template <int BN>
+int launch_tc_bn(int in_dt, int out_dt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
+    if (in_dt == DT_F32) return launch_tc<BN, float, float>(tmA, tmB, tmD, p, grid, st);
+    if (in_dt == DT_BF16)
+        return out_dt == DT_BF16 ? launch_tc<BN, __nv_bfloat16, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st)
+                                 : launch_tc<BN, __nv_bfloat16, float>(tmA, tmB, tmD, p, grid, st);
+    return out_dt == DT_F16 ? launch_tc<BN, __half, __half>(tmA, tmB, tmD, p, grid, st) : launch_tc<BN, __half, float>(tmA, tmB, tmD, p, grid, st);
 }
-template <typename TI>
-int launch_tc_any(int bn, bool out_bf16, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
-    if (bn == 256) return launch_tc_bn<256, TI>(out_bf16, tmA, tmB, tmD, p, grid, st);
-    if (bn == 128) return launch_tc_bn<128, TI>(out_bf16, tmA, tmB, tmD, p, grid, st);
-    return launch_tc_bn<64, TI>(out_bf16, tmA, tmB, tmD, p, grid, st);
+int launch_tc_any(int bn, int in_dt, int out_dt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
+    if (bn == 256) return launch_tc_bn<256>(in_dt, out_dt, tmA, tmB, tmD, p, grid, st);
+    if (bn == 128) return launch_tc_bn<128>(in_dt, out_dt, tmA, tmB, tmD, p, grid, st);
+    return launch_tc_bn<64>(in_dt, out_dt, tmA, tmB, tmD, p, grid, st);
 }
 template <int BN, typename TI, typename TO>
 int set_smem_attr() {
@@ -491,7 +505,7 @@ template <int BN>
 int set_smem_attr_bn() {
     int rc;
     if ((rc = set_smem_attr<BN, __nv_bfloat16, float>()) || (rc = set_smem_attr<BN, __nv_bfloat16, __nv_bfloat16>()) ||
-        (rc = set_smem_attr<BN, float, float>()) || (rc = set_smem_attr<BN, float, __nv_bfloat16>()))
+        (rc = set_smem_attr<BN, float, float>()) || (rc = set_smem_attr<BN, __half, float>()) || (rc = set_smem_attr<BN, __half, __half>()))
         return rc;
     return EGR_OK;
 }
@@ -515,12 +529,14 @@ int gemm_tc_init() {
     return EGR_OK;
 }
 
-int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
+int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     if (!g_tc_ready) {
         if (int rc = gemm_tc_init()) return rc;
     }
     EGR_CHECK(d.M > 0 && d.N > 0 && d.K > 0 && d.groups > 0, EGR_ERR_INVALID, "gemm_tc: empty problem %d %d %d", d.M, d.N, d.K);
-    const bool f32 = in_is_f32 != 0;
+    EGR_CHECK((in_dt == DT_F32 || in_dt == DT_BF16 || in_dt == DT_F16) && (out_dt_req == DT_F32 || (out_dt_req == in_dt && in_dt != DT_F32)),
+              EGR_ERR_UNSUPPORTED, "gemm_tc: operand / output types %d -> %d (output is fp32 or the operands' 16-bit type)", in_dt, out_dt_req);
+    const bool f32 = in_dt == DT_F32;
     const int ES = f32 ? 4 : 2;                 // operand element size
     const int BK = ROW_BYTES / ES;              // elements per k-block
     const int AL = 16 / ES;                     // elements per 16 bytes (TMA stride granularity)
@@ -604,7 +620,7 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         const cuuint64_t str[3] = {(cuuint64_t)d.lda * ES, (cuuint64_t)(d.K / kblk > 1 ? d.kblk_stride : d.lda) * ES,
                                    (cuuint64_t)(d.groups > 1 ? d.a_gs : d.lda) * ES};
         const cuuint32_t box[4] = {(cuuint32_t)BK, BM, 1, 1};
-        if ((rc = encode(&tmA, f32, d.A, 4, dims, str, box, "A"))) return rc;
+        if ((rc = encode(&tmA, in_dt, d.A, 4, dims, str, box, "A"))) return rc;
     } else {
         const int Hout = d.Hin / 2, Wout = d.Win / 2, HW = Hout * Wout;
         EGR_CHECK(d.Cin % BK == 0 && d.K == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
@@ -621,16 +637,17 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         const cuuint64_t str[4] = {(cuuint64_t)2 * d.Cin * ES, (cuuint64_t)d.Win * d.Cin * ES, (cuuint64_t)2 * d.Win * d.Cin * ES,
                                    (cuuint64_t)d.Hin * d.Win * d.Cin * ES};
         const cuuint32_t box[5] = {(cuuint32_t)BK, (cuuint32_t)Wout, 1, (cuuint32_t)bh, (cuuint32_t)bimg};
-        if ((rc = encode(&tmA, f32, d.A, 5, dims, str, box, "A(conv3s2)"))) return rc;
+        if ((rc = encode(&tmA, in_dt, d.A, 5, dims, str, box, "A(conv3s2)"))) return rc;
     }
     {
         const cuuint64_t dims[3] = {(cuuint64_t)d.K, (cuuint64_t)d.N, (cuuint64_t)d.groups};
         const cuuint64_t str[2] = {(cuuint64_t)d.K * ES, (cuuint64_t)(d.groups > 1 ? d.w_gs : (int64_t)d.N * d.K) * ES};
         const cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)bn, 1};
-        if ((rc = encode(&tmB, f32, d.W, 3, dims, str, box, "W"))) return rc;
+        if ((rc = encode(&tmB, in_dt, d.W, 3, dims, str, box, "W"))) return rc;
     }
 
-    const bool out_bf16 = d_is_bf16 && !p.partial;
+    const int out_dt = p.partial ? (int)DT_F32 : out_dt_req;
+    const bool out_bf16 = out_dt != DT_F32;          // 16-bit output
     CUtensorMap tmD;
     {
         // output [groups | ksplit][M][ldd]: one TMA-store box = 32 rows x (128 B, or the warp's BN/2 columns when narrower)
@@ -643,7 +660,7 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
         const cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)d.M, (cuuint64_t)nz};
         const cuuint64_t str[2] = {(cuuint64_t)ldd * OB, (cuuint64_t)(nz > 1 ? zs : (int64_t)d.M * ldd) * OB};
         const cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
-        if ((rc = encode(&tmD, !out_bf16, p.D, 3, dims, str, box, "D", box_cols * OB == 64))) return rc;
+        if ((rc = encode(&tmD, out_dt, p.D, 3, dims, str, box, "D", box_cols * OB == 64))) return rc;
     }
     const int64_t total = (int64_t)d.groups * m_tiles * p.n_tiles * p.ksplit;
     const int grid = (int)(total < nsm ? total : nsm);
@@ -658,13 +675,15 @@ int gemm_tc(const GemmDesc& d, int in_is_f32, int d_is_bf16, cudaStream_t st) {
             p.ws_stages = (int)(a_stages < MAX_STAGES ? a_stages : MAX_STAGES);
         }
     }
-    rc = f32 ? launch_tc_any<float>(bn, out_bf16, tmA, tmB, tmD, p, grid, st)
-             : launch_tc_any<__nv_bfloat16>(bn, out_bf16, tmA, tmB, tmD, p, grid, st);
+    rc = launch_tc_any(bn, in_dt, out_dt, tmA, tmB, tmD, p, grid, st);
     if (rc) return rc;
     if (p.partial) {
         const int64_t tot = (int64_t)d.M * d.N;
         const int blocks = (int)ceil_div64(tot, 256);
-        if (d_is_bf16)
+        if (out_dt_req == DT_F16)
+            EGR_LAUNCH(splitk_finalize_kernel<__half>, blocks, 256, 0, st, reinterpret_cast<const float*>(p.D), p.part_stride, p.ksplit, d.bias,
+                       reinterpret_cast<__half*>(d.D), tot, d.N, d.epi, 0);
+        else if (out_dt_req == DT_BF16)
             EGR_LAUNCH(splitk_finalize_kernel<__nv_bfloat16>, blocks, 256, 0, st, reinterpret_cast<const float*>(p.D), p.part_stride, p.ksplit, d.bias,
                        reinterpret_cast<__nv_bfloat16*>(d.D), tot, d.N, d.epi, 0);
         else

@@ -115,9 +115,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // instruction descriptor: D fp32 (bit 4), A format bits 7-9 and B format bits 10-12 (1 = bf16, 2 = tf32), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool tf32) {
-    return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc_fmt(int m, int n, uint32_t fmt /*0 f16, 1 bf16, 2 tf32*/) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool tf32) { return make_idesc_fmt(m, n, tf32 ? 2u : 1u); }
 
 
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {

@@ -128,8 +128,8 @@ int egr_heatmap_head_1x1(const float* feat, const float* weight, const float* bi
  *   epi 0 none, 1 ReLU, 2 exact-erf GELU, 3 ReLU then + relu(bilinear_x2_align_corners(aux)) with
  *       aux [img][(Hout/2)*(Wout/2)][N] in D's dtype (the "offset_pred + frame_feat" of :715).
  *   groups independent problems at element strides a_gs / w_gs / b_gs / d_gs / aux_gs.
- *   use_tc 1: tcgen05 + TMA kernel, fp32 accumulate in TMEM; a_is_bf16 1: A and W bf16 (kind::f16),
- *             a_is_bf16 0: A and W fp32, multiplied as TF32 (kind::tf32);
+ *   use_tc 1: tcgen05 + TMA kernel, fp32 accumulate in TMEM; a_is_bf16 1: A and W bf16, 2: A and W fp16 (kind::f16),
+ *             a_is_bf16 0: A and W fp32, multiplied as TF32 (kind::tf32); d_is_bf16 0 fp32, else the operands' type;
  *   use_tc 0: fp32 SIMT kernel, W fp32, A fp32 or bf16.   d_is_bf16 selects the output dtype.
  * ------------------------------------------------------------------------------------------- */
 typedef struct egr_dense_desc {

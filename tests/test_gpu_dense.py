@@ -29,8 +29,9 @@ def dense(A, W, bias, D, M, N, K, lda, ldd, amode=0, epi=0, aux=None, kblk=0, kb
     d.kblk, d.kblk_stride = kblk, kblk_stride
     d.Hin, d.Win, d.Cin, d.Hout, d.Wout = Hin, Win, Cin, Hout, Wout
     d.groups, d.a_gs, d.w_gs, d.b_gs, d.d_gs, d.aux_gs = groups, a_gs, w_gs, b_gs, d_gs, aux_gs
-    d.a_is_bf16 = int(A.dtype == torch.bfloat16)
-    d.d_is_bf16 = int(D.dtype == torch.bfloat16)
+    code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+    d.a_is_bf16 = code[A.dtype]
+    d.d_is_bf16 = code[D.dtype]
     d.use_tc = use_tc
     _lib.check(lib.egr_dense_stage(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
@@ -195,3 +196,40 @@ def test_tc_tf32_conv3s2():
     want = torch.relu(ref).permute(0, 2, 3, 1).reshape(M, N).float()
     err = float((D - want).abs().max() / want.abs().max())
     assert err < 2e-3, err
+
+
+@pytest.mark.parametrize("M,N,K,epi,out_dtype", [(4096, 64, 128, 1, torch.float16), (700, 128, 96 + 32, 0, torch.float32),
+                                                  (64, 2048, 4096, 2, torch.float32)])
+def test_tc_fp16_plain(M, N, K, epi, out_dtype):
+    """fp16 operands through kind::f16 (pose3d proposal branch): TF32's 10-bit mantissa at half the bytes"""
+    g = torch.Generator(device="cuda").manual_seed(31)
+    A = torch.randn((M, K), generator=g, device="cuda").half()
+    W = (torch.randn((N, K), generator=g, device="cuda") * K ** -0.5).half()
+    bias = torch.randn((N,), device="cuda")
+    D = torch.full((M, N), float("nan"), device="cuda", dtype=out_dtype)
+    dense(A, W, bias, D, M, N, K, K, N, epi=epi)
+    want = act(A.double() @ W.double().t() + bias.double(), epi).float()
+    err = float((D.float() - want).abs().max() / want.abs().max())
+    assert err < (2e-3 if out_dtype == torch.float16 else 2e-4), err
+
+
+def test_tc_fp16_conv3s2_and_saturation():
+    Hin, Cin, N, n_img = 64, 64, 128, 2
+    g = torch.Generator(device="cuda").manual_seed(32)
+    x = torch.randn((n_img, Hin, Hin, Cin), generator=g, device="cuda").half()
+    w = (torch.randn((N, Cin, 3, 3), generator=g, device="cuda") * (9 * Cin) ** -0.5).half()
+    bias = torch.randn((N,), device="cuda")
+    Wp = w.permute(0, 2, 3, 1).contiguous().reshape(N, 9 * Cin)
+    M = n_img * (Hin // 2) ** 2
+    D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float16)
+    dense(x, Wp, bias, D, M, N, 9 * Cin, 0, N, amode=1, epi=1, Hin=Hin, Win=Hin, Cin=Cin)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), stride=2, padding=1)
+    want = torch.relu(ref).permute(0, 2, 3, 1).reshape(M, N).float()
+    assert float((D.float() - want).abs().max() / want.abs().max()) < 2e-3
+    # out-of-range results saturate to +-65504 instead of inf
+    A = torch.full((128, 64), 200.0, device="cuda", dtype=torch.float16)
+    W2 = torch.full((64, 64), 100.0, device="cuda", dtype=torch.float16)
+    W2[1::2] *= -1
+    D2 = torch.zeros((128, 64), device="cuda", dtype=torch.float16)
+    dense(A, W2, None, D2, 128, 64, 64, 64, 64)
+    assert torch.isfinite(D2).all() and float(D2.max()) == 65504.0 and float(D2.min()) == -65504.0
