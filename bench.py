@@ -58,19 +58,20 @@ STAGE_BYTES = {
     "F1c": lambda act, exp, B: 4 * 1024 * (512 + 128) * act,
     "R1a": lambda act, exp, B: 4 * 1024 * 256 * act,
     "R1b": lambda act, exp, B: 4 * 1024 * 256 * act,
-    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * ((0 if exp == 2 else 4) + act + (4 if exp else 0))),
+    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * ((0 if exp == 2 else 4) + act + (P2ACT[0] if exp else 0))),
     "H2a": lambda act, exp, B: 4 * (4096 * 128 + 1024 * 256) * act,
     "H2b": lambda act, exp, B: 4 * 1024 * 512 * act,
     "H2c": lambda act, exp, B: 4 * 1024 * 384 * act,
     "H2tail": lambda act, exp, B: 4 * (1024 * 128 * act + 15 * 4096 * 4),
-    "P_stage_nhwc": lambda act, exp, B: 0 if exp else 4 * 4096 * 128 * (4 + 4) + 4 * 4096 * 128 * (4 + act),
-    "P2a": lambda act, exp, B: 4 * 4096 * (128 + 64) * 4,
-    "P2b": lambda act, exp, B: 4 * (4096 * 64 + 1024 * 128) * 4,
-    "P2pool": lambda act, exp, B: 4 * (1024 + 256) * 128 * 4,
-    "P2c": lambda act, exp, B: 4 * 256 * (128 + 64) * 4,
-    "P2d": lambda act, exp, B: 4 * (256 * 64 + 64 * 128) * 4,
-    "P2mlp0": lambda act, exp, B: 2048 * 32768 * 4 // B + 4 * 64 * 128 * 4,
+    "P_stage_nhwc": lambda act, exp, B: 0 if exp else 4 * 4096 * 128 * (4 + P2ACT[0]) + 4 * 4096 * 128 * (4 + act),
+    "P2a": lambda act, exp, B: 4 * 4096 * (128 + 64) * P2ACT[0],
+    "P2b": lambda act, exp, B: 4 * (4096 * 64 + 1024 * 128) * P2ACT[0],
+    "P2pool": lambda act, exp, B: 4 * (1024 + 256) * 128 * P2ACT[0],
+    "P2c": lambda act, exp, B: 4 * 256 * (128 + 64) * P2ACT[0],
+    "P2d": lambda act, exp, B: 4 * (256 * 64 + 64 * 128) * P2ACT[0],
+    "P2mlp0": lambda act, exp, B: 2048 * 32768 * P2ACT[0] // B + 4 * 64 * 128 * P2ACT[0],
 }
+P2ACT = [4]      # bytes per element of the pose3d proposal branch: 4 (fp32 / TF32) or 2 (fp16, the bf16-mode default); set in main()
 TF32_STAGES = ("P2a", "P2b", "P2c", "P2d", "P2mlp0")     # kind::tf32: half the bf16 tensor rate (nominal ratio)
 
 
@@ -80,7 +81,7 @@ def stage_roofline(name, ms, B, act, exp, peaks):
     by = STAGE_BYTES[name](act, exp, B) * B if name in STAGE_BYTES else 0
     if not fl and not by:
         return None
-    tf_peak = peaks["tf_sust"] * (0.5 if name in TF32_STAGES else 1.0)
+    tf_peak = peaks["tf_sust"] * (0.5 if (name in TF32_STAGES and P2ACT[0] == 4) else 1.0)
     t_tensor = fl / (tf_peak * 1e12) if fl else 0.0
     t_hbm = by / (peaks["hbm"] * 1e9) if by else 0.0
     t_s = ms / 1e3
@@ -304,6 +305,7 @@ def main():
     if args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
         # mvfex_pose3d = the chained model (EgoPoseFormerMVFEX.forward returns poses + heatmaps): refined features internal
         pipe = HotPathPipeline(4, "ego4view_syn", args.precision, dev, materialize_features=(args.workload != "mvfex_pose3d"))
+        P2ACT[0] = 2 if pipe.pose3d.engine().proposal_dtype() == "f16" else 4
         nb = min(B, 64)
         feat_h, bfb_h = synth.synth_features(nb, 4, seed=100 + rank)        # [nb,4,128,64,64] = 8.4 MB/frame
         if nb < B:
@@ -507,7 +509,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision if args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e") else "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "frames_per_gpu_per_step": B, "precision": args.precision,
+            "config": {"workload": workload_name(args), "frames_per_gpu_per_step": B, "precision": args.precision + ("" if args.workload not in ("mvfex_pose3d", "pose3d") else
+                                                       " (pose3d proposal branch: %s)" % pipe.pose3d.engine().proposal_dtype()),
                        "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
                        "streams": ("%d lanes: independent batches alternate between internal streams" % args.lanes)
                        if join is not None else "1",

@@ -64,7 +64,8 @@ SIGNATURES = {
     "egr_mvfex_export_staged": (c_int, [c_void_p, c_int]),
     "egr_mvfex_staged": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int)]),
     "egr_pose3d_use_staged": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
-    "egr_pose3d_use_staged_final_bf16": (c_int, [c_void_p, c_void_p]),
+    "egr_pose3d_use_staged_final_f16": (c_int, [c_void_p, c_void_p]),
+    "egr_pose3d_proposal_dtype": (c_int, [c_void_p]),
     "egr_mvfex_debug_buffer": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
     "egr_pose3d_debug_buffer": (c_int, [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_int64)]),
     "egr_set_option": (c_int, [c_char_p, c_int]),

@@ -76,6 +76,7 @@ struct Carver {
 struct WMat {
     float* f32 = nullptr;
     __nv_bfloat16* bf16 = nullptr;
+    __half* f16 = nullptr;
     float* bias = nullptr;    // [sets][N]
     int N = 0, K = 0, sets = 0;
     const void* w(int prec_bf16_tc) const { return prec_bf16_tc ? (const void*)bf16 : (const void*)f32; }
@@ -87,6 +88,9 @@ extern int g_opt_tc;   // 1: bf16 precision uses the tcgen05 kernel; 0: bf16 act
 // internal stage precision on top of the public EGR_PREC_*: fp32 activations and weights through the tensor cores as
 // TF32 (10-bit mantissa, fp32 accumulate) — used where bf16 operands would eat the 0.1 mm MPJPE budget (pose3d P2)
 constexpr int PREC_TF32 = 2;
+// fp16 activations and weights (kind::f16): TF32's 10-bit mantissa at half the bytes and twice the MMA rate; range
+// |x| < 65504 (conversions saturate) — the default of the pose3d proposal branch in EGR_PREC_BF16 (option "pose_p2_fp16")
+constexpr int PREC_FP16 = 3;
 
 // run one dense stage in the handle's precision.  `out_f32`: the output stays fp32 even in bf16 mode.
 inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out_f32, cudaStream_t st) {
@@ -94,6 +98,13 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
     const bool tc = bf && g_opt_tc;
     d.N = w.N;
     d.K = w.K;
+    if (prec == PREC_FP16) {
+        d.W = w.f16 + (int64_t)set_begin * w.stride();
+        d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
+        d.w_gs = w.stride();
+        d.b_gs = w.N;
+        return gemm_tc(d, DT_F16, out_f32 ? DT_F32 : DT_F16, st);
+    }
     if (prec == PREC_TF32 && g_opt_tc) {
         d.W = w.f32 + (int64_t)set_begin * w.stride();
         d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;

@@ -13,6 +13,7 @@ namespace egr {
 int g_opt_tc = 1;
 int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
 extern int g_opt_pose_p2_bf16;
+extern int g_opt_pose_p2_fp16;
 extern int g_opt_ws;
 }
 using namespace egr;
@@ -43,9 +44,9 @@ struct egr_mvfex {
     MvfTokenW* d_tokw = nullptr;               // device [V]
     // batched token path (bf16 precision): token GEMM weights (fp32 rounded to TF32, sets = V) + per-refiner pointer tables
     bool export_staged = false;                // keep channels-last copies for a chained pose3d forward
-    bool export_tf32 = true;                   // ... including the TF32 copy of the refined features
+    int export_hp = 1;                         // high-precision copy of the refined features: 0 none, 1 fp32/TF32, 2 fp16
     const void *st_init = nullptr, *st_refined = nullptr;
-    const float* st_refined_tf32 = nullptr;
+    const void* st_refined_hp = nullptr;
     bool tokb = false;
     WMat tk_hp2, tk_fcq, tk_bfb, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
     const __nv_bfloat16** d_ptab16 = nullptr;  // device [4]: bf16 copies of the sampled position tables
@@ -165,7 +166,7 @@ struct Bufs {
     float *q1, *anch, *maxv;
     uint8_t* valid;
     float *tx, *tz, *toa, *tA, *tqkv, *to, *thid, *tpool, *tvb;     // batched token path
-    float* refn32;                                                  // exported TF32 channels-last refined features
+    void* refn_hp;                                                  // exported TF32 (fp32) or fp16 channels-last refined features
     float* splitk;                                                  // split-K partial sums of the token GEMMs
 };
 
@@ -197,7 +198,7 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.anch = (float*)c.take((int64_t)B * V * J * 2 * 4);
     b.maxv = (float*)c.take((int64_t)B * V * J * 4);
     b.valid = (uint8_t*)c.take((int64_t)B * V * J);
-    b.refn32 = (h->export_staged && h->export_tf32 && G == V) ? (float*)c.take((int64_t)G * B * FHW * FC * 4) : nullptr;
+    b.refn_hp = (h->export_staged && h->export_hp && G == V) ? c.take((int64_t)G * B * FHW * FC * (h->export_hp == 2 ? 2 : 4)) : nullptr;
     if (h->tokb) {
         const int64_t T = (int64_t)B * J;
         b.tx = (float*)c.take(G * T * EMB * 4);
@@ -407,7 +408,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st))) return rc;
     EGR_MARK("R1tail", st);
     // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output + channels-last copy for H2
-    if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, w.refn32, st))) return rc;
+    if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, w.refn_hp, h->export_hp == 2, st))) return rc;
     EGR_MARK("H2a", st);
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
@@ -451,6 +452,7 @@ void note_all(egr_mvfex* h, const Bufs& w, int B, int G) {
 
 extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "tc") { g_opt_tc = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "pose_p2_fp16") { g_opt_pose_p2_fp16 = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pose_p2_bf16") { g_opt_pose_p2_bf16 = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "ws") { g_opt_ws = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pdl") { g_opt_pdl = value ? 1 : 0; return EGR_OK; }
@@ -670,23 +672,24 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
                       (int64_t)V * J * FHW, (int64_t)J * FHW, feat_refined, (int64_t)V * FC * FHW, (int64_t)FC * FHW, st);
     if (rc) return rc;
     note_all(h, w, B, V);
-    h->st_init = w.Xh; h->st_refined = w.refn; h->st_refined_tf32 = w.refn32;
+    h->st_init = w.Xh; h->st_refined = w.refn; h->st_refined_hp = w.refn_hp;
     return EGR_OK;
 }
 
 extern "C" int egr_mvfex_export_staged(egr_mvfex* h, int enable) {
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_export_staged: null handle");
+    EGR_CHECK(enable >= 0 && enable <= 3, EGR_ERR_INVALID, "mvfex_export_staged: mode %d", enable);
     h->export_staged = enable != 0;
-    h->export_tf32 = enable != 2;
-    h->st_init = h->st_refined = nullptr; h->st_refined_tf32 = nullptr;
+    h->export_hp = (enable == 1) ? 1 : (enable == 3) ? 2 : 0;
+    h->st_init = h->st_refined = nullptr; h->st_refined_hp = nullptr;
     return EGR_OK;
 }
 
-extern "C" int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const float** refined_nhwc_tf32,
+extern "C" int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const void** refined_nhwc_hp,
                                 int* act_is_bf16) {
-    EGR_CHECK(h && init_nhwc && refined_nhwc && refined_nhwc_tf32 && act_is_bf16, EGR_ERR_INVALID, "mvfex_staged: null argument");
+    EGR_CHECK(h && init_nhwc && refined_nhwc && refined_nhwc_hp && act_is_bf16, EGR_ERR_INVALID, "mvfex_staged: null argument");
     EGR_CHECK(h->st_init, EGR_ERR_STATE, "mvfex_staged: no forward has run since export was enabled");
-    *init_nhwc = h->st_init; *refined_nhwc = h->st_refined; *refined_nhwc_tf32 = h->st_refined_tf32;
+    *init_nhwc = h->st_init; *refined_nhwc = h->st_refined; *refined_nhwc_hp = h->st_refined_hp;
     *act_is_bf16 = (h->prec == EGR_PREC_BF16);
     return EGR_OK;
 }

@@ -15,6 +15,7 @@ CamCalib make_calib(int cam_id, const float* calib_host);
 // (measured), which is the whole parity budget, so in EGR_PREC_BF16 the branch keeps fp32 activations and weights and
 // multiplies them as TF32 on the tensor cores (PREC_TF32); option "pose_p2_bf16" forces bf16 operands instead.
 int g_opt_pose_p2_bf16 = 0;
+int g_opt_pose_p2_fp16 = 1;    // EGR_PREC_BF16: fp16 instead of fp32/TF32 activations and weights in P2 (same 10-bit mantissa)
 }
 using namespace egr;
 
@@ -38,8 +39,7 @@ struct egr_pose3d {
     const void* st_sampled = nullptr;
     int st_sampled_bf16 = 0;
     const float* st_final_tf32 = nullptr;
-    const void* st_final_bf16 = nullptr;
-    __nv_bfloat16* c0_bf16 = nullptr;   // conv_frame_feat.0 weight for the bf16-input variant of P2a
+    const void* st_final_f16 = nullptr;
     // batched token path (bf16 precision)
     bool tokb = false;
     int KA = 0;
@@ -55,11 +55,12 @@ namespace {
 inline int p2_prec(const egr_pose3d* h) {
     if (h->prec != EGR_PREC_BF16) return EGR_PREC_FP32;
     if (g_opt_pose_p2_bf16) return EGR_PREC_BF16;
-    return g_opt_tc ? PREC_TF32 : EGR_PREC_FP32;
+    if (!g_opt_tc) return EGR_PREC_FP32;
+    return g_opt_pose_p2_fp16 ? PREC_FP16 : PREC_TF32;
 }
 
 int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3 2 mlp-permute*/, const std::string& key,
-                cudaStream_t st, bool tf32_operand = true) {
+                cudaStream_t st, bool tf32_operand = true, bool f16_operand = true) {
     m.N = N; m.K = K; m.sets = 1;
     int rc = EGR_OK;
     if ((rc = h->pool.alloc(&m.f32, (int64_t)N * K))) return rc;
@@ -75,7 +76,10 @@ int p_make_wmat(egr_pose3d* h, WMat& m, int N, int K, int kind /*0 plain 1 conv3
     if (p2_prec(h) == EGR_PREC_BF16) {
         if ((rc = h->pool.alloc(&m.bf16, (int64_t)N * K))) return rc;
         if ((rc = cast_bf16(m.f32, m.bf16, (int64_t)N * K, st))) return rc;
-    } else if (p2_prec(h) == PREC_TF32 && tf32_operand) {
+    } else if (p2_prec(h) == PREC_FP16 && f16_operand) {
+        if ((rc = h->pool.alloc(&m.f16, (int64_t)N * K))) return rc;
+        if ((rc = cast_f16(m.f32, m.f16, (int64_t)N * K, st))) return rc;
+    } else if (p2_prec(h) != EGR_PREC_FP32 && tf32_operand) {      // TF32 stage (also mlp_pred.1 of the fp16 branch)
         if ((rc = round_tf32_inplace(m.f32, (int64_t)N * K, st))) return rc;
     }
     return EGR_OK;
@@ -148,7 +152,7 @@ struct PBufs {
 
 int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
     const int64_t si = (h->prec == EGR_PREC_BF16) ? 2 : 4;          // sampled map
-    const int64_t s = (p2_prec(h) == EGR_PREC_BF16) ? 2 : 4;        // proposal branch
+    const int64_t s = (p2_prec(h) == EGR_PREC_BF16 || p2_prec(h) == PREC_FP16) ? 2 : 4;        // proposal branch
     const int64_t VB = (int64_t)h->V * B;
     Carver c(base, cap);
     PBufs b{};
@@ -346,19 +350,13 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
         if ((rc = gemm_tc_init())) return rc;
     }
     if ((rc = p_make_wmat(h, h->c0, 64, 128, 0, "conv_frame_feat.0", st))) return rc;
-    if (p2_prec(h) == PREC_TF32) {
-        const float* w0 = h->params.get("conv_frame_feat.0.weight", 64 * 128, &rc);
-        if (!w0) return rc;
-        if ((rc = h->pool.alloc(&h->c0_bf16, 64 * 128))) return rc;
-        if ((rc = cast_bf16(w0, h->c0_bf16, 64 * 128, st))) return rc;
-    }
     if ((rc = p_make_wmat(h, h->c2, 128, 9 * 64, 1, "conv_frame_feat.2", st))) return rc;
     if ((rc = p_make_wmat(h, h->c5, 64, 128, 0, "conv_frame_feat.5", st))) return rc;
     if ((rc = p_make_wmat(h, h->c7, 128, 9 * 64, 1, "conv_frame_feat.7", st))) return rc;
     const int K0 = h->V * PC * 64;
     if ((rc = p_make_wmat(h, h->m0, K0 / 16, K0, 2, "mlp_pred.0.0", st))) return rc;
-    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st, true))) return rc;
-    if ((rc = p_make_wmat(h, h->m2, 3 * h->J, K0 / 256, 0, "mlp_pred.2", st, false))) return rc;
+    if ((rc = p_make_wmat(h, h->m1, K0 / 256, K0 / 16, 0, "mlp_pred.1.0", st, true, false))) return rc;      // TF32 in both branches
+    if ((rc = p_make_wmat(h, h->m2, 3 * h->J, K0 / 256, 0, "mlp_pred.2", st, false, false))) return rc;     // fp32 SIMT
     PoseTokenW tw{};
     if ((rc = p_make_T(h, "query_gen_mlp.0", PE, 4, &tw.g0_T, st))) return rc;
     if ((rc = p_vec(h, "query_gen_mlp.0.bias", PE, &tw.g0_b))) return rc;
@@ -414,7 +412,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     if (int rc = require_device()) return rc;
     EGR_CHECK(h->packed, EGR_ERR_STATE, "pose3d_forward: parameters changed or never packed; call egr_pose3d_prepack");
     EGR_CHECK(B > 0 && preds && workspace, EGR_ERR_INVALID, "pose3d_forward: null pointer");
-    EGR_CHECK((feats_final || h->st_final_tf32 || h->st_final_bf16) && (feats_init || feats_final || h->st_sampled), EGR_ERR_INVALID,
+    EGR_CHECK((feats_final || h->st_final_tf32 || h->st_final_f16) && (feats_init || feats_final || h->st_sampled), EGR_ERR_INVALID,
               "pose3d_forward: a NULL NCHW input needs its staged channels-last copy (egr_pose3d_use_staged)");
     const int is_rw = (h->cam_model & 1);
     EGR_CHECK(!is_rw || coord_trans_mat, EGR_ERR_INVALID, "pose3d_forward: ego4view_rw* needs coord_trans_mat [B,V,4,4] fp32");
@@ -433,23 +431,23 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     // staging copies; the sampled map is frame_feats_init when use_pred_heatmap_init (:424-427)
     const float* sampled = h->use_init ? feats_init : feats_final;
     const int rnd = (prec == PREC_TF32);      // every operand of a tf32 stage is pre-rounded to the nearest TF32 value
+    const int f16 = (prec == PREC_FP16);
     // staged copies left by a chained mvfex forward replace the staging passes (one-shot)
     const void* st_s = h->st_sampled;
     const float* st_f = h->st_final_tf32;
     const int st_s_bf16 = h->st_sampled_bf16;
-    const void* st_fb = h->st_final_bf16;
-    h->st_sampled = nullptr; h->st_final_tf32 = nullptr; h->st_final_bf16 = nullptr;
+    const void* st_fh = h->st_final_f16;
+    h->st_sampled = nullptr; h->st_final_tf32 = nullptr; h->st_final_f16 = nullptr;
     const void* Xf = w.Xf;
-    const bool p2a_bf16_in = st_fb && rnd && h->c0_bf16 && !st_f;     // chained forward without the TF32 copy
     if (st_f && rnd) Xf = st_f;
-    else if (p2a_bf16_in) Xf = st_fb;
+    else if (st_fh && f16) Xf = st_fh;
     else {
         EGR_CHECK(feats_final, EGR_ERR_INVALID, "pose3d_forward: feats_final is NULL and its staged copy does not fit this precision");
-        if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, rnd ? 2 : bf, st))) return rc;
+        if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, f16 ? 3 : rnd ? 2 : bf, st))) return rc;
     }
     const void* Xs = Xf;
     if (st_s && st_s_bf16 == bfs) Xs = st_s;
-    else if (sampled != feats_final || bfs != bf || rnd) {
+    else if (sampled != feats_final || bfs != bf || rnd || f16) {
         EGR_CHECK(sampled, EGR_ERR_INVALID, "pose3d_forward: the sampled map is NULL and its staged copy does not fit this precision");
         if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
         Xs = w.Xi;
@@ -458,16 +456,13 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     // P2 conv_frame_feat
     GemmDesc d;
     d.A = Xf; d.lda = PC; d.M = VB * PHW; d.D = w.p0; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
-    if (p2a_bf16_in) {      // bf16 x bf16 -> fp32 (rounded to TF32 for P2b)
-        d.N = 64; d.K = PC; d.W = h->c0_bf16; d.bias = h->c0.bias;
-        if ((rc = gemm_tc(d, DT_BF16, DT_F32, st))) return rc;
-    } else if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
+    if ((rc = run_gemm(d, h->c0, 0, prec, false, st))) return rc;
     EGR_MARK("P2b", st);
     d = GemmDesc();
     d.A = w.p0; d.amode = A_CONV3S2; d.Hin = 64; d.Win = 64; d.Cin = 64; d.M = VB * 1024; d.D = w.p2; d.ldd = 128; d.epi = EPI_RELU; d.round_tf32 = rnd;
     if ((rc = run_gemm(d, h->c2, 0, prec, false, st))) return rc;
     EGR_MARK("P2pool", st);
-    if ((rc = maxpool2_nhwc(w.p2, w.p3, bf, VB, 32, 32, 128, st))) return rc;
+    if ((rc = maxpool2_nhwc(w.p2, w.p3, f16 ? 2 : bf, VB, 32, 32, 128, st))) return rc;
     EGR_MARK("P2c", st);
     d = GemmDesc();
     d.A = w.p3; d.lda = 128; d.M = VB * 256; d.D = w.p5; d.ldd = 64; d.epi = EPI_RELU; d.round_tf32 = rnd;
@@ -480,13 +475,13 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     // mlp_pred: K-split over the V view blocks of p7 ([V][B][64*128])
     d = GemmDesc();
     d.A = w.p7; d.lda = 64 * 128; d.kblk = 64 * 128; d.kblk_stride = (int64_t)B * 64 * 128; d.M = B; d.D = w.m0; d.ldd = h->m0.N;
-    d.epi = EPI_GELU; d.round_tf32 = rnd;
+    d.epi = EPI_GELU; d.round_tf32 = rnd || f16;      // operand of the TF32 mlp_pred.1
     if ((rc = run_gemm(d, h->m0, 0, prec, /*out_f32=*/true, st))) return rc;
     EGR_MARK("P2mlp12", st);
     {   // Linear(2048 -> 128) GELU on the tensor cores in the tf32 branch; the last Linear(128 -> 48) stays fp32 SIMT
         GemmDesc t;
         t.A = w.m0; t.lda = h->m1.K; t.M = B; t.D = w.m1; t.ldd = h->m1.N; t.epi = EPI_GELU;
-        if (rnd) {
+        if (rnd || f16) {
             if ((rc = run_gemm(t, h->m1, 0, PREC_TF32, true, st))) return rc;
         } else {
             t.N = h->m1.N; t.K = h->m1.K; t.W = h->m1.f32; t.bias = h->m1.bias;
@@ -525,10 +520,14 @@ extern "C" int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, in
     return EGR_OK;
 }
 
-extern "C" int egr_pose3d_use_staged_final_bf16(egr_pose3d* h, const void* final_nhwc_bf16) {
-    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_use_staged_final_bf16: null handle");
-    h->st_final_bf16 = final_nhwc_bf16;
+extern "C" int egr_pose3d_use_staged_final_f16(egr_pose3d* h, const void* final_nhwc_f16) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_use_staged_final_f16: null handle");
+    h->st_final_f16 = final_nhwc_f16;
     return EGR_OK;
+}
+
+extern "C" int egr_pose3d_proposal_dtype(egr_pose3d* h) {      // 0 fp32 (SIMT), 1 bf16, 2 TF32, 3 fp16
+    return h ? p2_prec(h) : -1;
 }
 
 extern "C" int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes) {

@@ -86,6 +86,7 @@ int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int ou
     dim3 grid(HW / 32, B * V);
     const size_t smem = sizeof(float) * C * 33;
     if (out_mode == 1) EGR_LAUNCH((nchw_to_nhwc_kernel<__nv_bfloat16, false>), grid, 256, smem, st, in, (__nv_bfloat16*)out, B, V, C, HW);
+    else if (out_mode == 3) EGR_LAUNCH((nchw_to_nhwc_kernel<__half, false>), grid, 256, smem, st, in, (__half*)out, B, V, C, HW);
     else if (out_mode == 2) EGR_LAUNCH((nchw_to_nhwc_kernel<float, true>), grid, 256, smem, st, in, (float*)out, B, V, C, HW);
     else EGR_LAUNCH((nchw_to_nhwc_kernel<float, false>), grid, 256, smem, st, in, (float*)out, B, V, C, HW);
     return EGR_OK;
@@ -226,7 +227,7 @@ template <> __device__ __forceinline__ void pack8_store<__nv_bfloat16>(__nv_bflo
 template <typename TZ>
 __global__ void __launch_bounds__(256)
 up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ out_nchw, int64_t o_bs, int64_t o_gs,
-                          TZ* __restrict__ out_nhwc, float* __restrict__ out_nhwc_tf32) {
+                          TZ* __restrict__ out_nhwc, void* __restrict__ out_nhwc_hp, int hp_f16) {
     constexpr int SLD = 130;                               // transposed tile row stride: conflict-free both ways
     extern __shared__ __align__(16) uint8_t fsm[];
     TZ* s1 = reinterpret_cast<TZ*>(fsm);                   // [FROWS*FS px][FCH]   as loaded
@@ -255,9 +256,11 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
         }
     }
     // ---- channels-last copy: item = (pixel, 8 channels) ----
-    if (out_nhwc || out_nhwc_tf32) {
+    if (out_nhwc || out_nhwc_hp) {
         TZ* o = out_nhwc ? out_nhwc + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH : nullptr;
-        float* o32 = out_nhwc_tf32 ? out_nhwc_tf32 + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH : nullptr;
+        const int64_t hp_off = ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH;
+        float* o32 = (out_nhwc_hp && !hp_f16) ? reinterpret_cast<float*>(out_nhwc_hp) + hp_off : nullptr;
+        __half* o16 = (out_nhwc_hp && hp_f16) ? reinterpret_cast<__half*>(out_nhwc_hp) + hp_off : nullptr;
 #pragma unroll 2
         for (int it = threadIdx.x; it < FSTRIP * FO * (FCH / 8); it += 256) {
             const int c8 = it & 15, px = it >> 4;
@@ -274,6 +277,14 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
 #pragma unroll
             for (int i = 0; i < 8; ++i) r[i] = fmaxf(ly0 * (lx0 * a[i] + lx1 * bb[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]), 0.f);
             if (o) pack8_store<TZ>(o + (int64_t)px * FCH + c8 * 8, r);
+            if (o16) {       // fp16, saturating
+                uint4 u;
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(r[1]), "f"(r[0]));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(r[3]), "f"(r[2]));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.z) : "f"(r[5]), "f"(r[4]));
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.w) : "f"(r[7]), "f"(r[6]));
+                *reinterpret_cast<uint4*>(o16 + (int64_t)px * FCH + c8 * 8) = u;
+            }
             if (o32) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] = round_tf32(r[i]);
@@ -475,7 +486,7 @@ up2_relu_dual_kernel(const TZ* __restrict__ z, int B, int Hs, int Ws, int C, flo
 }
 
 int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* out_nhwc, float* out_nhwc_tf32, cudaStream_t st) {
+                  int64_t o_gs, void* out_nhwc, void* out_nhwc_hp, int hp_f16, cudaStream_t st) {
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;
@@ -485,15 +496,15 @@ int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C
         if (z_bf16) {
             auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc, out_nhwc_tf32);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc, out_nhwc_hp, hp_f16);
         } else {
             auto k = up2_relu_dual_fast_kernel<float>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc, out_nhwc_tf32);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc, out_nhwc_hp, hp_f16);
         }
         return EGR_OK;
     }
-    EGR_CHECK(!out_nhwc_tf32, EGR_ERR_UNSUPPORTED, "up2_relu_dual: the TF32 channels-last export needs the 32x32x128 geometry");
+    EGR_CHECK(!out_nhwc_hp, EGR_ERR_UNSUPPORTED, "up2_relu_dual: the high-precision channels-last export needs the 32x32x128 geometry");
     const size_t smem = sizeof(float) * (size_t)C * (STRIP * Ws + 1);
     dim3 grid(2 * Hs / STRIP, G * B);
     if (z_bf16) {
@@ -532,6 +543,15 @@ template <> struct Vec16<__nv_bfloat16> {
     static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) { return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w)); }
 };
 
+template <> struct Vec16<__half> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ uint32_t m2(uint32_t a, uint32_t b) {
+        const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+        return *reinterpret_cast<const uint32_t*>(&r);
+    }
+    static __device__ __forceinline__ uint4 vmax(uint4 a, uint4 b) { return make_uint4(m2(a.x, b.x), m2(a.y, b.y), m2(a.z, b.z), m2(a.w, b.w)); }
+};
+
 template <typename T>
 __global__ void maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t total_vec, int H, int W, int C) {
     constexpr int VN = Vec16<T>::N;
@@ -550,13 +570,15 @@ __global__ void maxpool2_kernel(const T* __restrict__ in, T* __restrict__ out, i
     }
 }
 
-int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, int W, int C, cudaStream_t st) {
-    const int vn = is_bf16 ? 8 : 4;
+int maxpool2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int W, int C, cudaStream_t st) {
+    const int is_bf16 = (dt == 1);
+    const int vn = dt ? 8 : 4;
     EGR_CHECK(C % vn == 0, EGR_ERR_UNSUPPORTED, "maxpool2: C=%d", C);
     const int64_t total = n_img * (H / 2) * (W / 2) * (C / vn);
     if (total == 0) return EGR_OK;
     const int grid = (int)(ceil_div64(total, 256) < 148 * 32 ? ceil_div64(total, 256) : 148 * 32);
-    if (is_bf16) EGR_LAUNCH(maxpool2_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C);
+    if (dt == 2) EGR_LAUNCH(maxpool2_kernel<__half>, grid, 256, 0, st, (const __half*)in, (__half*)out, total, H, W, C);
+    else if (is_bf16) EGR_LAUNCH(maxpool2_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, total, H, W, C);
     else EGR_LAUNCH(maxpool2_kernel<float>, grid, 256, 0, st, (const float*)in, (float*)out, total, H, W, C);
     return EGR_OK;
 }
@@ -598,6 +620,18 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = __float2bfloat16_rn(in[i]);
 }
+__global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        ActT<__half>::st(out + i, in[i]);
+}
+int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t st) {
+    if (n == 0) return EGR_OK;
+    const int64_t g = ceil_div64(n, 256);
+    cast_f16_kernel<<<(int)(g < 148 * 64 ? g : 148 * 64), 256, 0, st>>>(in, out, n);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st) {
     if (n == 0) return EGR_OK;
     const int64_t g = ceil_div64(n, 256);

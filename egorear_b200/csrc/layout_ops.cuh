@@ -5,7 +5,7 @@
 namespace egr {
 
 // in  [B][V][C][HW] fp32 (NCHW per view)  ->  out [V][B][HW][C] (view-major, channels-last)
-// out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to the nearest TF32 value (operand of a kind::tf32 stage)
+// out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to the nearest TF32 value (operand of a kind::tf32 stage), 3 fp16
 int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_mode, cudaStream_t st);
 // fp32 -> activation dtype copy (float: plain copy)
 int cast_act(const float* in, void* out, int out_bf16, int64_t n, cudaStream_t st);
@@ -24,12 +24,13 @@ int head_tail_tc(const void* z, const float* w, const float* bias, const int* ws
 // R1 tail: z [g][B][Hs*Ws][C] -> relu(up2(z)) written twice:
 //   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output) and
 //   out_nhwc [g][B][4HsWs][C] in the activation dtype (input of the H2 3x3 conv)
-//   out_nhwc_tf32 (optional) [g][B][4HsWs][C] fp32 rounded to TF32 (operand of the pose3d proposal branch when chained)
+//   out_nhwc_hp (optional) [g][B][4HsWs][C] high-precision copy for the pose3d proposal branch when chained:
+//                 fp32 rounded to TF32 (hp_f16 = 0) or fp16 (hp_f16 = 1)
 int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* out_nhwc, float* out_nhwc_tf32, cudaStream_t st);
+                  int64_t o_gs, void* out_nhwc, void* out_nhwc_hp, int hp_f16, cudaStream_t st);
 
-// nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C]
-int maxpool2_nhwc(const void* in, void* out, int is_bf16, int64_t n_img, int H, int W, int C, cudaStream_t st);
+// nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C];  dt: 0 fp32, 1 bf16, 2 fp16
+int maxpool2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int W, int C, cudaStream_t st);
 
 // ---- one-time weight preparation (prepack) ----
 // conv weight [Cout][Cin][3][3] -> [Cout][ky][kx][Cin]
@@ -38,6 +39,8 @@ int repack_conv3(const float* w, float* out, int Cout, int Cin, cudaStream_t st)
 int round_tf32_inplace(float* p, int64_t n, cudaStream_t st);
 // fp32 -> bf16 copy
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st);
+// fp32 -> fp16 copy (saturating)
+int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t st);
 // [R][C] -> [C][R]
 int transpose2d(const float* in, float* out, int R, int C, cudaStream_t st);
 // C[M][N] = A[M][K] · B[K][N] (+ bias[N] broadcast when non-null); small prepack-time products, fp32

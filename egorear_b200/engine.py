@@ -113,11 +113,12 @@ class MvfexEngine(_EngineBase):
         _lib.check(self._lib.egr_mvfex_create(num_views, num_heatmap, float(heatmap_threshold), PREC[precision],
                                               ctypes.byref(self._h)))
 
-    def export_staged(self, enable=True, tf32_final=True):
+    def export_staged(self, enable=True, hp="tf32"):
         """keep channels-last copies of the input / refined features for a chained Pose3DEngine.forward(staged=...);
-        tf32_final=False drops the fp32/TF32 copy of the refined features (pose3d's first conv then reads the bf16 copy)"""
-        _lib.check(self._lib.egr_mvfex_export_staged(self._h, (1 if tf32_final else 2) if enable else 0))
-        self._export = bool(enable)
+        hp: high-precision copy of the refined features for pose3d's proposal branch: "tf32" (fp32), "f16" or None"""
+        mode = {"tf32": 1, None: 2, "f16": 3}[hp] if enable else 0
+        _lib.check(self._lib.egr_mvfex_export_staged(self._h, mode))
+        self._export, self._export_hp = bool(enable), hp
 
     def forward(self, feat, bfb, heatmap_for_anchor=None, want_feat_refined=True):
         """feat [B,V,128,64,64], bfb [B,V,512,8,8] fp32 CUDA ->
@@ -147,7 +148,9 @@ class MvfexEngine(_EngineBase):
             pi, pr, pt, bf = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
             _lib.check(self._lib.egr_mvfex_staged(self._h, ctypes.byref(pi), ctypes.byref(pr), ctypes.byref(pt), ctypes.byref(bf)))
             # device pointers into this engine's workspace: valid until its next forward
-            out["staged"] = {"init": pi.value, "refined": pr.value, "refined_tf32": pt.value, "bf16": bf.value,
+            hp = getattr(self, "_export_hp", "tf32")
+            out["staged"] = {"init": pi.value, "refined": pr.value, "refined_tf32": pt.value if hp == "tf32" else None,
+                             "refined_f16": pt.value if hp == "f16" else None, "bf16": bf.value,
                              "feat": feat_arg, "feat_refined": out["feat_refined"]}
         return out
 
@@ -188,6 +191,10 @@ class Pose3DEngine(_EngineBase):
                                                ctypes.c_void_p(tab.ctypes.data) if tab is not None else None,
                                                ctypes.byref(self._h)))
 
+    def proposal_dtype(self):
+        """operand type of the proposal branch: "fp32", "bf16", "tf32" or "f16" """
+        return ("fp32", "bf16", "tf32", "f16")[int(self._lib.egr_pose3d_proposal_dtype(self._h))]
+
     def forward(self, feats_init, feats_final, coord_trans_mat=None, staged=None, use_init=True):
         """-> preds [L+1, B, 16, 3] fp32 (cm): preds[0] MLP proposal, preds[1:] transformer layers.
         staged: MvfexEngine.forward(...)["staged"] of the SAME tensors (chained forward): skips the re-staging passes."""
@@ -211,8 +218,8 @@ class Pose3DEngine(_EngineBase):
             sampled = staged["init"] if use_init else staged["refined"]
             _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),
                                                        ctypes.c_void_p(staged["refined_tf32"]) if staged["refined_tf32"] else None))
-            if not staged["refined_tf32"] and staged["bf16"] and staged["refined"]:
-                _lib.check(self._lib.egr_pose3d_use_staged_final_bf16(self._h, ctypes.c_void_p(staged["refined"])))
+            if staged.get("refined_f16"):
+                _lib.check(self._lib.egr_pose3d_use_staged_final_f16(self._h, ctypes.c_void_p(staged["refined_f16"])))
         _lib.check(self._lib.egr_pose3d_forward(self._h, B, _ptr(fi), _ptr(ff), _ptr(ctm), _ptr(preds), _ptr(ws),
                                                 ws.numel(), _stream()))
         return preds

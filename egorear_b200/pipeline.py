@@ -14,7 +14,7 @@ from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
 
 class HotPathPipeline:
     def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True,
-                 with_backbone=False, tf32_final=True, materialize_features=True):
+                 with_backbone=False, materialize_features=True):
         self.V, self.camera_model, self.precision = num_views, camera_model, precision
         self.heatmap = EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(num_views, camera_model), precision=precision,
                                                  build_backbone=with_backbone)
@@ -24,9 +24,10 @@ class HotPathPipeline:
             synth.fill_state_dict(self.pose3d)
         self.heatmap = self.heatmap.to(device).eval()
         self.pose3d = self.pose3d.to(device).eval()
-        # chained forward: pose3d reuses the channels-last copies; tf32_final=False drops the TF32 copy of the refined
-        # features (537 MB per 64 frames): conv_frame_feat.0 then reads the bf16 copy
-        self.heatmap.engine().export_staged(True, tf32_final=tf32_final)
+        # chained forward: pose3d reuses the channels-last copies, incl. a high-precision copy of the refined features in
+        # the operand type of its proposal branch (fp16 by default in bf16 mode, else fp32 / TF32)
+        pd = self.pose3d.engine().proposal_dtype()
+        self.heatmap.engine().export_staged(True, hp="f16" if pd == "f16" else "tf32" if pd == "tf32" else None)
         # materialize_features=False: like EgoPoseFormerMVFEX.forward (egoposeformer_mvf_ex.py:50-58), which returns poses
         # and heatmaps only, the refined features are not written out in NCHW fp32 (list_ff[1] is None)
         self.materialize_features = materialize_features

@@ -181,16 +181,16 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
                               const float* bfb, float* hm_refined, float* feat_refined, void* workspace,
                               int64_t workspace_bytes, void* stream);
 /* Chaining (EgoPoseFormerMVFEX.forward, estimator/egoposeformer_mvf_ex.py:50-58: heatmap estimator -> pose3d):
- * with export enabled, egr_mvfex_forward keeps channels-last copies of its input features (activation dtype), of the
- * refined features (activation dtype) and of the refined features as fp32 rounded to TF32 in ITS workspace;
+ * with export enabled, egr_mvfex_forward keeps in ITS workspace channels-last copies of its input features (activation
+ * dtype), of the refined features (activation dtype) and - modes 1 / 3 - a high-precision copy of the refined features
+ * for pose3d's proposal branch: fp32 rounded to TF32 (mode 1) or fp16 (mode 3; same 10-bit mantissa, half the bytes).
  * egr_mvfex_staged returns them (valid until the next forward on this handle / workspace).  Passing them to
- * egr_pose3d_use_staged lets the NEXT egr_pose3d_forward skip re-staging its NCHW inputs (the hint is consumed by that
- * call; the NCHW pointers must still be the same tensors).  [V][B][64*64][128] layout. */
-int egr_mvfex_export_staged(egr_mvfex* h, int enable);   /* 0 off, 1 all three copies, 2 without the TF32 copy */
-/* With export enabled, egr_mvfex_forward accepts feat_refined == NULL (the chained EgoPoseFormerMVFEX.forward never
- * returns the refined features, :50-58) and egr_pose3d_forward accepts NULL for an NCHW input whose staged copy was
- * handed over with egr_pose3d_use_staged. */
-int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const float** refined_nhwc_tf32,
+ * egr_pose3d_use_staged / egr_pose3d_use_staged_final_f16 lets the NEXT egr_pose3d_forward skip re-staging its NCHW
+ * inputs (the hints are consumed by that call).  [V][B][64*64][128] layout.
+ * With export enabled, egr_mvfex_forward accepts feat_refined == NULL (the chained EgoPoseFormerMVFEX.forward never
+ * returns the refined features) and egr_pose3d_forward accepts NULL for an NCHW input whose staged copy was handed over. */
+int egr_mvfex_export_staged(egr_mvfex* h, int mode);   /* 0 off, 1 + TF32 copy, 2 activation-dtype copies only, 3 + fp16 copy */
+int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const void** refined_nhwc_hp,
                      int* act_is_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
  * ("q1", "xT", "t1", "ff", ...); EGR_ERR_INVALID for unknown names */
@@ -219,9 +219,11 @@ int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init, const floa
  * feats_final), bf16 or fp32 as flagged; final_nhwc_tf32: channels-last fp32 copy of feats_final rounded to TF32.
  * Either may be NULL.  One-shot: consumed by the next egr_pose3d_forward. */
 int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32);
-/* Alternative hint for feats_final: its channels-last bf16 copy (what egr_mvfex_export_staged(h, 2) leaves).  The first
- * proposal conv (conv_frame_feat.0) then multiplies bf16 operands; everything after it stays TF32.  One-shot. */
-int egr_pose3d_use_staged_final_bf16(egr_pose3d* h, const void* final_nhwc_bf16);
+/* Hint for feats_final when the proposal branch runs in fp16 (egr_pose3d_proposal_dtype == 3): its channels-last fp16
+ * copy (what egr_mvfex_export_staged(h, 3) leaves).  One-shot. */
+int egr_pose3d_use_staged_final_f16(egr_pose3d* h, const void* final_nhwc_f16);
+/* operand type of the proposal branch (conv_frame_feat + mlp_pred.0): 0 fp32 SIMT, 1 bf16, 2 TF32, 3 fp16 */
+int egr_pose3d_proposal_dtype(egr_pose3d* h);
 int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes);
 
 /* ---------------------------------------------------------------------------------------------
