@@ -43,7 +43,7 @@ STAGE_FLOPS = {
 # algorithmic HBM bytes per 4-view frame of every stage (act = bytes per activation element: 2 in bf16 mode; the pose3d
 # proposal branch P2* keeps fp32/TF32 activations; weights are counted once per batch for the one stage where they
 # dominate, P2mlp0).  `exp` = 1 when the forward also exports the TF32 channels-last refined features, 2 when in addition the NCHW fp32 refined
-# features are not materialised (chained model).
+# features are not materialised (chained model; with the fp16 proposal branch the fp16 copy is then the only one).
 STAGE_BYTES = {
     "stage_nhwc": lambda act, exp, B: 4 * 4096 * 128 * (4 + act),
     "H1a": lambda act, exp, B: 4 * 4096 * 128 * act * 2,
@@ -58,7 +58,8 @@ STAGE_BYTES = {
     "F1c": lambda act, exp, B: 4 * 1024 * (512 + 128) * act,
     "R1a": lambda act, exp, B: 4 * 1024 * 256 * act,
     "R1b": lambda act, exp, B: 4 * 1024 * 256 * act,
-    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * ((0 if exp == 2 else 4) + act + (P2ACT[0] if exp else 0))),
+    "R1tail": lambda act, exp, B: 4 * (1024 * 128 * act + 4096 * 128 * (
+        (0 if exp == 2 else 4) + (0 if (exp == 2 and P2ACT[0] == 2) else act) + (P2ACT[0] if exp else 0))),
     "H2a": lambda act, exp, B: 4 * (4096 * 128 + 1024 * 256) * act,
     "H2b": lambda act, exp, B: 4 * 1024 * 512 * act,
     "H2c": lambda act, exp, B: 4 * 1024 * 384 * act,

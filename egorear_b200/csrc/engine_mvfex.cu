@@ -45,6 +45,8 @@ struct egr_mvfex {
     // batched token path (bf16 precision): token GEMM weights (fp32 rounded to TF32, sets = V) + per-refiner pointer tables
     bool export_staged = false;                // keep channels-last copies for a chained pose3d forward
     int export_hp = 1;                         // high-precision copy of the refined features: 0 none, 1 fp32/TF32, 2 fp16
+    bool refn_f16_only = false;                // the fp16 copy is the only channels-last copy (H2a reads it too)
+    __half* h2_0_f16 = nullptr;                // conv_heatmap_layers.0.0 weights [V][256][9*128] in fp16
     const void *st_init = nullptr, *st_refined = nullptr;
     const void* st_refined_hp = nullptr;
     bool tokb = false;
@@ -189,7 +191,7 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.z = c.take((int64_t)Gh * B * 1024 * 128 * s);
     b.ff = c.take((int64_t)G * B * 1024 * 128 * s);
     b.r1a = c.take((int64_t)G * B * 1024 * 128 * s);
-    b.refn = c.take((int64_t)G * B * FHW * FC * s);
+    b.refn = (h->refn_f16_only && G == V) ? nullptr : c.take((int64_t)G * B * FHW * FC * s);
     b.hmT = c.take((int64_t)Gh * B * J * FHW * s);
     b.xT = c.take((int64_t)G * B * NPOS * 16 * s);
     b.h1t = c.take((int64_t)G * B * NPOS * 64 * s);
@@ -414,7 +416,12 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     d = GemmDesc();
     d.A = w.refn; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = B * 1024; d.D = w.b1; d.ldd = 256;
     d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256;
-    if ((rc = run_gemm(d, h->h2_0, r0, prec, false, st))) return rc;
+    if (!w.refn) {
+        // the refined features exist only as the fp16 channels-last copy shared with pose3d: fp16 operands, bf16 output
+        d.A = w.refn_hp; d.N = 256; d.K = 9 * FC; d.W = h->h2_0_f16 + (int64_t)r0 * 256 * 9 * FC; d.w_gs = (int64_t)256 * 9 * FC;
+        d.bias = h->h2_0.bias + r0 * 256; d.b_gs = 256;
+        if ((rc = gemm_tc(d, DT_F16, DT_BF16, st))) return rc;
+    } else if ((rc = run_gemm(d, h->h2_0, r0, prec, false, st))) return rc;
     EGR_MARK("H2b", st);
     d = GemmDesc();
     d.A = w.b1; d.lda = 256; d.M = B * 1024; d.D = w.c1; d.ldd = 256; d.epi = EPI_RELU;
@@ -537,6 +544,10 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
     if ((rc = make_wmat(h, h->r1_0, V, 128, 128, W_PLAIN, ref(".frame_feat_refined_proj_layers.0.0"), rp, st))) return rc;
     if ((rc = make_wmat(h, h->r1_3, V, 128, 128, W_PLAIN, ref(".frame_feat_refined_proj_layers.0.3"), rp, st))) return rc;
     if ((rc = make_wmat(h, h->h2_0, V, 256, 9 * 128, W_CONV3, ref(".conv_heatmap_layers.0.0"), rp, st))) return rc;
+    if (h->prec == EGR_PREC_BF16 && g_opt_tc) {
+        if ((rc = h->pool.alloc(&h->h2_0_f16, (int64_t)V * 256 * 9 * 128))) return rc;
+        if ((rc = cast_f16(h->h2_0.f32, h->h2_0_f16, (int64_t)V * 256 * 9 * 128, st))) return rc;
+    }
     if ((rc = make_wmat(h, h->h2_2, V, 256, 256, W_PLAIN, ref(".conv_heatmap_layers.0.2"), rp, st))) return rc;
     if ((rc = make_wmat(h, h->h2_5, V, 128, 256, W_PLAIN, ref(".conv_heatmap_layers.0.5"), rp, st))) return rc;
     if ((rc = h->pool.alloc(&h->h2_7w, (int64_t)V * J * 128))) return rc;
@@ -678,9 +689,11 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
 
 extern "C" int egr_mvfex_export_staged(egr_mvfex* h, int enable) {
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_export_staged: null handle");
-    EGR_CHECK(enable >= 0 && enable <= 3, EGR_ERR_INVALID, "mvfex_export_staged: mode %d", enable);
+    EGR_CHECK(enable >= 0 && enable <= 4, EGR_ERR_INVALID, "mvfex_export_staged: mode %d", enable);
+    EGR_CHECK(enable != 4 || (h->prec == EGR_PREC_BF16 && g_opt_tc), EGR_ERR_UNSUPPORTED, "mvfex_export_staged: mode 4 needs the tensor-core path");
     h->export_staged = enable != 0;
-    h->export_hp = (enable == 1) ? 1 : (enable == 3) ? 2 : 0;
+    h->export_hp = (enable == 1) ? 1 : (enable >= 3) ? 2 : 0;
+    h->refn_f16_only = enable == 4;
     h->st_init = h->st_refined = nullptr; h->st_refined_hp = nullptr;
     return EGR_OK;
 }

@@ -489,6 +489,7 @@ int launch_tc_bn(int in_dt, int out_dt, const CUtensorMap& tmA, const CUtensorMa
     if (in_dt == DT_BF16)
         return out_dt == DT_BF16 ? launch_tc<BN, __nv_bfloat16, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st)
                                  : launch_tc<BN, __nv_bfloat16, float>(tmA, tmB, tmD, p, grid, st);
+    if (out_dt == DT_BF16) return launch_tc<BN, __half, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st);
     return out_dt == DT_F16 ? launch_tc<BN, __half, __half>(tmA, tmB, tmD, p, grid, st) : launch_tc<BN, __half, float>(tmA, tmB, tmD, p, grid, st);
 }
 int launch_tc_any(int bn, int in_dt, int out_dt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
@@ -505,7 +506,8 @@ template <int BN>
 int set_smem_attr_bn() {
     int rc;
     if ((rc = set_smem_attr<BN, __nv_bfloat16, float>()) || (rc = set_smem_attr<BN, __nv_bfloat16, __nv_bfloat16>()) ||
-        (rc = set_smem_attr<BN, float, float>()) || (rc = set_smem_attr<BN, __half, float>()) || (rc = set_smem_attr<BN, __half, __half>()))
+        (rc = set_smem_attr<BN, float, float>()) || (rc = set_smem_attr<BN, __half, float>()) || (rc = set_smem_attr<BN, __half, __half>()) ||
+        (rc = set_smem_attr<BN, __half, __nv_bfloat16>()))
         return rc;
     return EGR_OK;
 }
@@ -534,8 +536,9 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
         if (int rc = gemm_tc_init()) return rc;
     }
     EGR_CHECK(d.M > 0 && d.N > 0 && d.K > 0 && d.groups > 0, EGR_ERR_INVALID, "gemm_tc: empty problem %d %d %d", d.M, d.N, d.K);
-    EGR_CHECK((in_dt == DT_F32 || in_dt == DT_BF16 || in_dt == DT_F16) && (out_dt_req == DT_F32 || (out_dt_req == in_dt && in_dt != DT_F32)),
-              EGR_ERR_UNSUPPORTED, "gemm_tc: operand / output types %d -> %d (output is fp32 or the operands' 16-bit type)", in_dt, out_dt_req);
+    EGR_CHECK((in_dt == DT_F32 || in_dt == DT_BF16 || in_dt == DT_F16) &&
+              (out_dt_req == DT_F32 || (out_dt_req == in_dt && in_dt != DT_F32) || (in_dt == DT_F16 && out_dt_req == DT_BF16)),
+              EGR_ERR_UNSUPPORTED, "gemm_tc: operand / output types %d -> %d (output: fp32, the operands' 16-bit type, or bf16 from fp16)", in_dt, out_dt_req);
     const bool f32 = in_dt == DT_F32;
     const int ES = f32 ? 4 : 2;                 // operand element size
     const int BK = ROW_BYTES / ES;              // elements per k-block

@@ -116,7 +116,7 @@ class MvfexEngine(_EngineBase):
     def export_staged(self, enable=True, hp="tf32"):
         """keep channels-last copies of the input / refined features for a chained Pose3DEngine.forward(staged=...);
         hp: high-precision copy of the refined features for pose3d's proposal branch: "tf32" (fp32), "f16" or None"""
-        mode = {"tf32": 1, None: 2, "f16": 3}[hp] if enable else 0
+        mode = {"tf32": 1, None: 2, "f16": 3, "f16_only": 4}[hp] if enable else 0
         _lib.check(self._lib.egr_mvfex_export_staged(self._h, mode))
         self._export, self._export_hp = bool(enable), hp
 
@@ -150,7 +150,7 @@ class MvfexEngine(_EngineBase):
             # device pointers into this engine's workspace: valid until its next forward
             hp = getattr(self, "_export_hp", "tf32")
             out["staged"] = {"init": pi.value, "refined": pr.value, "refined_tf32": pt.value if hp == "tf32" else None,
-                             "refined_f16": pt.value if hp == "f16" else None, "bf16": bf.value,
+                             "refined_f16": pt.value if hp in ("f16", "f16_only") else None, "bf16": bf.value,
                              "feat": feat_arg, "feat_refined": out["feat_refined"]}
         return out
 

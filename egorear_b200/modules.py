@@ -580,7 +580,8 @@ class EgoPoseFormerMVFEX(nn.Module):
     def forward_from_feats(self, feat, bfb, coord_trans_mat=None, origin_3d=None):
         if self._chain:
             pd = self.pose3d_estimator.engine().proposal_dtype()
-            self.heatmap_estimator.engine().export_staged(True, hp="f16" if pd == "f16" else "tf32" if pd == "tf32" else None)
+            hp = ("f16_only" if self.use_pred_heatmap_init else "f16") if pd == "f16" else "tf32" if pd == "tf32" else None
+            self.heatmap_estimator.engine().export_staged(True, hp=hp)
         # the chained model returns (poses, heatmaps) only (:50-58): the refined features stay channels-last, internal
         list_hm, list_ff = self.heatmap_estimator.forward_from_feats(feat, bfb, want_feat_refined=not self._chain)
         return self.pose3d_estimator(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, origin_3d,

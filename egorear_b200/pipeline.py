@@ -27,7 +27,9 @@ class HotPathPipeline:
         # chained forward: pose3d reuses the channels-last copies, incl. a high-precision copy of the refined features in
         # the operand type of its proposal branch (fp16 by default in bf16 mode, else fp32 / TF32)
         pd = self.pose3d.engine().proposal_dtype()
-        self.heatmap.engine().export_staged(True, hp="f16" if pd == "f16" else "tf32" if pd == "tf32" else None)
+        use_init = bool(getattr(self.pose3d, "use_pred_heatmap_init", True))
+        hp = ("f16_only" if use_init else "f16") if pd == "f16" else "tf32" if pd == "tf32" else None
+        self.heatmap.engine().export_staged(True, hp=hp)
         # materialize_features=False: like EgoPoseFormerMVFEX.forward (egoposeformer_mvf_ex.py:50-58), which returns poses
         # and heatmaps only, the refined features are not written out in NCHW fp32 (list_ff[1] is None)
         self.materialize_features = materialize_features

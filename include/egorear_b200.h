@@ -189,7 +189,9 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
  * inputs (the hints are consumed by that call).  [V][B][64*64][128] layout.
  * With export enabled, egr_mvfex_forward accepts feat_refined == NULL (the chained EgoPoseFormerMVFEX.forward never
  * returns the refined features) and egr_pose3d_forward accepts NULL for an NCHW input whose staged copy was handed over. */
-int egr_mvfex_export_staged(egr_mvfex* h, int mode);   /* 0 off, 1 + TF32 copy, 2 activation-dtype copies only, 3 + fp16 copy */
+/* mode 4: like 3, but the fp16 copy is the ONLY channels-last copy of the refined features (the refined heatmap head
+ * reads it too; egr_mvfex_staged returns refined_nhwc = NULL) - for a pose3d that samples the init features. */
+int egr_mvfex_export_staged(egr_mvfex* h, int mode);   /* 0 off, 1 + TF32 copy, 2 activation-dtype copies only, 3 + fp16 copy, 4 */
 int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const void** refined_nhwc_hp,
                      int* act_is_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
