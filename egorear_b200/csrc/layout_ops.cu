@@ -46,12 +46,24 @@ nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, in
         }
 }
 
-// bf16 output, C = 128: 64-pixel tiles.  Two channel rows are packed into bf16x2 words on the way into shared memory
+// 16-bit output (bf16 | fp16), C = 128: 64-pixel tiles.  Two channel rows are packed into 16x2 words on the way into shared memory
 // (tile[pair][pixel], odd stride), so the write phase reads conflict-free and every store instruction writes one full
 // 128 B line of a pixel's 256 B channel vector; reads are 2 x 128 B per channel row.
 constexpr int NT_PX = 64, NT_C = 128, NT_LD = NT_PX + 1;
+template <typename T16> __device__ __forceinline__ uint32_t pack16x2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack16x2<__nv_bfloat16>(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <> __device__ __forceinline__ uint32_t pack16x2<__half>(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+template <typename T16>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int V, int HW) {
+nchw_to_nhwc_16_kernel(const float* __restrict__ in, T16* __restrict__ out, int B, int V, int HW) {
     __shared__ uint32_t tile[(NT_C / 2) * NT_LD];
     pdl_trigger();
     pdl_wait();
@@ -64,9 +76,8 @@ nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict
     for (int cp = warp; cp < NT_C / 2; cp += 8) {
         const float* r0 = src + (int64_t)(2 * cp) * HW;
         const float a0 = __ldcs(r0), a1 = __ldcs(r0 + 32), b0 = __ldcs(r0 + HW), b1 = __ldcs(r0 + HW + 32);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(a0, b0), hi = __floats2bfloat162_rn(a1, b1);
-        tile[cp * NT_LD + lane] = *reinterpret_cast<uint32_t*>(&lo);
-        tile[cp * NT_LD + lane + 32] = *reinterpret_cast<uint32_t*>(&hi);
+        tile[cp * NT_LD + lane] = pack16x2<T16>(a0, b0);
+        tile[cp * NT_LD + lane + 32] = pack16x2<T16>(a1, b1);
     }
     __syncthreads();
     uint32_t* dst = reinterpret_cast<uint32_t*>(out + (((int64_t)v * B + b) * HW + p0) * NT_C);
@@ -78,8 +89,9 @@ nchw_to_nhwc_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict
 }
 
 int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_mode, cudaStream_t st) {
-    if (out_mode == 1 && C == NT_C && HW % NT_PX == 0) {
-        EGR_LAUNCH(nchw_to_nhwc_bf16_kernel, dim3(HW / NT_PX, B * V), 256, 0, st, in, (__nv_bfloat16*)out, B, V, HW);
+    if ((out_mode == 1 || out_mode == 3) && C == NT_C && HW % NT_PX == 0) {
+        if (out_mode == 1) EGR_LAUNCH(nchw_to_nhwc_16_kernel<__nv_bfloat16>, dim3(HW / NT_PX, B * V), 256, 0, st, in, (__nv_bfloat16*)out, B, V, HW);
+        else EGR_LAUNCH(nchw_to_nhwc_16_kernel<__half>, dim3(HW / NT_PX, B * V), 256, 0, st, in, (__half*)out, B, V, HW);
         return EGR_OK;
     }
     EGR_CHECK(HW % 32 == 0 && C * 33 * 4 <= 48 * 1024, EGR_ERR_UNSUPPORTED, "nchw_to_nhwc: HW=%d C=%d", HW, C);
