@@ -94,8 +94,8 @@ def stage_roofline(name, ms, B, act, exp, peaks):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"F1b": 546439168 + 241995776, "F1a": 268778240 + 482828544, "R1tail": 67367680 + 1285690000,
-               "stage_nhwc": 536962560 + 212386816, "H1tail": 67162880 + 49056768}      # profiles/r01e_ncu_summary.md
+NCU_TRAFFIC = {"F1b": 546443776 + 246109184, "R1tail": 67132160 + 209667072, "P2a": 268514560 + 102758912,
+               "P2b": 134458112 + 41757440}      # profiles/r01g_ncu_summary.md
 
 
 def load_peaks():

@@ -62,7 +62,7 @@ def stall_summary(path):
     h = rows[hi]
     ix = {n: i for i, n in enumerate(h)}
     stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
-    body = [r for r in rows[hi + 1:] if len(r) == len(h)]
+    body = [r for r in rows[hi + 1:] if len(r) == len(h) and r[0] != "Address"]      # several kernels: repeated headers
     tot = sum(int(r[ix["# Samples"]]) for r in body) or 1
     agg = {s: sum(int(r[ix[s]]) for r in body) for s in stalls}
     return ", ".join("%s %.0f%%" % (k[6:], 100.0 * v / tot) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:5] if v)

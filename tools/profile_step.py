@@ -18,12 +18,14 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--all-outputs", action="store_true", help="materialise the NCHW fp32 refined features (module outputs)")
     args = ap.parse_args()
     import torch
     from egorear_b200 import synth
     from egorear_b200.pipeline import HotPathPipeline
     dev = torch.device("cuda", 0)
-    pipe = HotPathPipeline(4, "ego4view_syn", args.precision, dev)
+    # default: the bench's headline configuration (chained model, refined features stay channels-last)
+    pipe = HotPathPipeline(4, "ego4view_syn", args.precision, dev, materialize_features=args.all_outputs)
     feat, bfb = synth.synth_features(min(args.batch, 64), 4, seed=100)
     if args.batch > 64:
         feat, bfb = feat.repeat(args.batch // 64, 1, 1, 1, 1), bfb.repeat(args.batch // 64, 1, 1, 1, 1)
