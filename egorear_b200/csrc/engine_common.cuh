@@ -93,7 +93,8 @@ constexpr int PREC_TF32 = 2;
 constexpr int PREC_FP16 = 3;
 
 // run one dense stage in the handle's precision.  `out_f32`: the output stays fp32 even in bf16 mode.
-inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out_f32, cudaStream_t st) {
+// `out16`: DT_F16 makes a bf16-mode tensor-core stage write fp16 instead of bf16 (interpolated right afterwards in half2).
+inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out_f32, cudaStream_t st, int out16 = DT_BF16) {
     const bool bf = (prec == EGR_PREC_BF16);
     const bool tc = bf && g_opt_tc;
     d.N = w.N;
@@ -118,7 +119,7 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
     d.w_gs = w.stride();
     d.b_gs = w.N;
     const int d_bf16 = (bf && !out_f32) ? 1 : 0;
-    if (tc) return gemm_tc(d, DT_BF16, d_bf16 ? DT_BF16 : DT_F32, st);
+    if (tc) return gemm_tc(d, DT_BF16, d_bf16 ? out16 : (int)DT_F32, st);
     return gemm_simt(d, bf ? 1 : 0, d_bf16, st);
 }
 

@@ -406,11 +406,14 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128;
     if ((rc = run_gemm(d, h->r1_0, r0, prec, false, st))) return rc;
     EGR_MARK("R1b", st);
+    // on the tensor-core path the pre-upsample maps z are written in fp16 so that the tails interpolate in half2
+    const bool z16 = bf && g_opt_tc;
     d.A = w.r1a; d.D = w.z; d.epi = EPI_NONE;
-    if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st))) return rc;
+    if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("R1tail", st);
-    // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output + channels-last copy for H2
-    if ((rc = up2_relu_dual(w.z, bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, w.refn_hp, h->export_hp == 2, st))) return rc;
+    // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output (optional) + channels-last copies for H2 / pose3d
+    if ((rc = up2_relu_dual(w.z, z16 ? 2 : bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, bf ? 1 : 3, w.refn_hp,
+                            h->export_hp == 2 ? 2 : 0, st))) return rc;
     EGR_MARK("H2a", st);
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
@@ -431,10 +434,10 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     d = GemmDesc();
     d.A = w.c1; d.lda = 256; d.M = B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
     d.groups = G; d.a_gs = (int64_t)B * 1024 * 256; d.d_gs = (int64_t)B * 1024 * 128;
-    if ((rc = run_gemm(d, h->h2_5, r0, prec, false, st))) return rc;
+    if ((rc = run_gemm(d, h->h2_5, r0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("H2tail", st);
     int wsel[4] = {r0, r0 + 1, r0 + 2, r0 + 3};
-    if ((rc = head_up_conv(w.z, bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
+    if ((rc = head_up_conv(w.z, z16 ? 2 : bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
         return rc;
     EGR_MARK(nullptr, st);
     return EGR_OK;
@@ -664,13 +667,14 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     if ((rc = run_gemm(d, h->h1_4, 0, prec, false, st))) return rc;
     EGR_MARK("H1d", st);
     d = GemmDesc();
+    const bool z16 = bf && g_opt_tc;     // pre-upsample maps in fp16 on the tensor-core path (half2 interpolation in the tails)
     d.A = w.c1; d.lda = 256; d.M = vpg * B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
     d.groups = G1; d.a_gs = (int64_t)vpg * B * 1024 * 256; d.d_gs = (int64_t)vpg * B * 1024 * 128;
-    if ((rc = run_gemm(d, h->h1_7, 0, prec, false, st))) return rc;
+    if ((rc = run_gemm(d, h->h1_7, 0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("H1tail", st);
     int wsel[4] = {0, 0, 1, 1};
     if (G1 == 1) wsel[2] = wsel[3] = 0;
-    if ((rc = head_up_conv(w.z, bf, h->h1_9w, h->h1_9b, wsel, B, V, 32, 32, FC, J, hm_init, (int64_t)V * J * FHW,
+    if ((rc = head_up_conv(w.z, z16 ? 2 : bf, h->h1_9w, h->h1_9b, wsel, B, V, 32, 32, FC, J, hm_init, (int64_t)V * J * FHW,
                            (int64_t)J * FHW, w.hmT, st))) return rc;
     EGR_MARK("D1", st);
     // D1: anchors from heatmap_for_anchor when given (:293-296), else from the init heatmap

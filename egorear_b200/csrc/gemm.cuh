@@ -51,7 +51,7 @@ int gemm_simt(const GemmDesc& d, int a_is_bf16, int d_is_bf16, cudaStream_t st);
 // element types of the tcgen05 path's operands / output
 enum DT : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 // tcgen05 + TMA path.  A, W both bf16 or both fp16 (kind::f16), or both fp32 read as TF32 (kind::tf32); fp32 accumulate.
-// D: fp32, the operands' 16-bit type, or bf16 from fp16 operands.  fp16 has TF32's 10-bit mantissa at half the bytes and twice the MMA rate; its
+// D: fp32, or bf16 / fp16 from 16-bit operands.  fp16 has TF32's 10-bit mantissa at half the bytes and twice the MMA rate; its
 // range (|x| < 65504) is the caller's responsibility (conversions saturate).
 int gemm_tc(const GemmDesc& d, int in_dt, int out_dt, cudaStream_t st);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled; EGR_OK or error

@@ -482,15 +482,18 @@ int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap&
     EGR_LAUNCH((gemm_tc_kernel<BN, TI, TO>), grid, TC_THREADS, TcCfg<BN>::SMEM, st, tmA, tmB, tmD, p);
     return EGR_OK;
 }
-// instantiated (operand, output) pairs: bf16 -> bf16 | fp32, fp16 -> fp16 | fp32, fp32 (TF32) -> fp32
+// instantiated (operand, output) pairs: bf16 | fp16 -> bf16 | fp16 | fp32, fp32 (TF32) -> fp32
+template <int BN, typename TI>
+int launch_tc_out(int out_dt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
+    if (out_dt == DT_BF16) return launch_tc<BN, TI, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st);
+    if (out_dt == DT_F16) return launch_tc<BN, TI, __half>(tmA, tmB, tmD, p, grid, st);
+    return launch_tc<BN, TI, float>(tmA, tmB, tmD, p, grid, st);
+}
 template <int BN>
 int launch_tc_bn(int in_dt, int out_dt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
     if (in_dt == DT_F32) return launch_tc<BN, float, float>(tmA, tmB, tmD, p, grid, st);
-    if (in_dt == DT_BF16)
-        return out_dt == DT_BF16 ? launch_tc<BN, __nv_bfloat16, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st)
-                                 : launch_tc<BN, __nv_bfloat16, float>(tmA, tmB, tmD, p, grid, st);
-    if (out_dt == DT_BF16) return launch_tc<BN, __half, __nv_bfloat16>(tmA, tmB, tmD, p, grid, st);
-    return out_dt == DT_F16 ? launch_tc<BN, __half, __half>(tmA, tmB, tmD, p, grid, st) : launch_tc<BN, __half, float>(tmA, tmB, tmD, p, grid, st);
+    if (in_dt == DT_BF16) return launch_tc_out<BN, __nv_bfloat16>(out_dt, tmA, tmB, tmD, p, grid, st);
+    return launch_tc_out<BN, __half>(out_dt, tmA, tmB, tmD, p, grid, st);
 }
 int launch_tc_any(int bn, int in_dt, int out_dt, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const TcParams& p, int grid, cudaStream_t st) {
     if (bn == 256) return launch_tc_bn<256>(in_dt, out_dt, tmA, tmB, tmD, p, grid, st);
@@ -507,7 +510,7 @@ int set_smem_attr_bn() {
     int rc;
     if ((rc = set_smem_attr<BN, __nv_bfloat16, float>()) || (rc = set_smem_attr<BN, __nv_bfloat16, __nv_bfloat16>()) ||
         (rc = set_smem_attr<BN, float, float>()) || (rc = set_smem_attr<BN, __half, float>()) || (rc = set_smem_attr<BN, __half, __half>()) ||
-        (rc = set_smem_attr<BN, __half, __nv_bfloat16>()))
+        (rc = set_smem_attr<BN, __half, __nv_bfloat16>()) || (rc = set_smem_attr<BN, __nv_bfloat16, __half>()))
         return rc;
     return EGR_OK;
 }
@@ -537,8 +540,8 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     }
     EGR_CHECK(d.M > 0 && d.N > 0 && d.K > 0 && d.groups > 0, EGR_ERR_INVALID, "gemm_tc: empty problem %d %d %d", d.M, d.N, d.K);
     EGR_CHECK((in_dt == DT_F32 || in_dt == DT_BF16 || in_dt == DT_F16) &&
-              (out_dt_req == DT_F32 || (out_dt_req == in_dt && in_dt != DT_F32) || (in_dt == DT_F16 && out_dt_req == DT_BF16)),
-              EGR_ERR_UNSUPPORTED, "gemm_tc: operand / output types %d -> %d (output: fp32, the operands' 16-bit type, or bf16 from fp16)", in_dt, out_dt_req);
+              (out_dt_req == DT_F32 || (in_dt != DT_F32 && (out_dt_req == DT_BF16 || out_dt_req == DT_F16))),
+              EGR_ERR_UNSUPPORTED, "gemm_tc: operand / output types %d -> %d (TF32 operands give fp32; 16-bit operands give fp32, bf16 or fp16)", in_dt, out_dt_req);
     const bool f32 = in_dt == DT_F32;
     const int ES = f32 ? 4 : 2;                 // operand element size
     const int BK = ROW_BYTES / ES;              // elements per k-block

@@ -1,4 +1,4 @@
-// Heatmap-head tail on the tensor cores (EGR_PREC_BF16, shipped geometry 32x32 -> 64x64, C = 128):
+// Heatmap-head tail on the tensor cores (EGR_PREC_BF16, shipped geometry 32x32 -> 64x64, C = 128; z in fp16):
 //
 //   hm[j][y][x] = sum_c W[j][c] * relu(up2_bilinear_align_corners(z)[y][x][c]) + b[j]        j < 15
 //
@@ -6,13 +6,14 @@
 // :579-583, with the preceding 1x1 conv commuted in front of the upsample).  The SIMT version spends 16 FMAs per
 // interpolated value on the 1x1 conv; here one CTA = 4 output rows = 256 pixels = two M=128 tcgen05 tiles:
 //   1. the (at most) 4 source rows of z are staged in shared memory (padded pixel stride, conflict-free LDS.128)
-//   2. thread t interpolates pixel t in fp32 (64 channels = one k-block at a time), applies ReLU and writes the bf16
-//      row straight into the K-major SWIZZLE_128B A tile
+//   2. thread t interpolates pixel t (64 channels = one k-block at a time) and applies ReLU in half2 arithmetic (z is
+//      fp16: two channels per HFMA2, no unpacking) and writes the fp16 row straight into the K-major SWIZZLE_128B A tile
 //   3. one thread issues 2 x 4 tcgen05.mma (M=128, N=16, K=16) per k-block against the bf16 weight tile, accumulators
 //      in TMEM; 71 KB of shared memory -> three CTAs per SM overlap each other's load / MMA / store phases
 //   4. tcgen05.ld gives thread t the 16 joint values of pixel t; 32 lanes = 32 consecutive x -> 128 B stores per joint
 #include "layout_ops.cuh"
 #include "tc_ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace egr {
 using namespace tcx;
@@ -54,33 +55,23 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
-// relu folded into the conversion
-__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     uint32_t r;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-    return r;
-}
-// relu(w00*a + w01*b + w10*c + w11*d) for the two bf16 halves of one 32-bit word each
-__device__ __forceinline__ uint32_t interp_word(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float w00, float w01,
-                                                float w10, float w11) {
-    float lo = w00 * __uint_as_float(a << 16);
-    float hi = w00 * __uint_as_float(a & 0xffff0000u);
-    lo = fmaf(w01, __uint_as_float(b << 16), lo);
-    hi = fmaf(w01, __uint_as_float(b & 0xffff0000u), hi);
-    lo = fmaf(w10, __uint_as_float(c << 16), lo);
-    hi = fmaf(w10, __uint_as_float(c & 0xffff0000u), hi);
-    lo = fmaf(w11, __uint_as_float(d << 16), lo);
-    hi = fmaf(w11, __uint_as_float(d & 0xffff0000u), hi);
-    return pack_relu_bf16x2(lo, hi);
+// relu(w00*a + w01*b + w10*c + w11*d) on one fp16x2 word
+__device__ __forceinline__ uint32_t interp_word(uint32_t a, uint32_t b, uint32_t c, uint32_t d, __half2 w00, __half2 w01,
+                                                __half2 w10, __half2 w11) {
+    const __half2 r = __hmax2(__hfma2(w11, *reinterpret_cast<const __half2*>(&d),
+                              __hfma2(w10, *reinterpret_cast<const __half2*>(&c),
+                              __hfma2(w01, *reinterpret_cast<const __half2*>(&b), __hmul2(w00, *reinterpret_cast<const __half2*>(&a))))),
+                              __float2half2_rn(0.f));
+    return *reinterpret_cast<const uint32_t*>(&r);
 }
 
 __global__ void __launch_bounds__(256, 3)
-head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias, int4 wsel,
+head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias, int4 wsel,
                     int B, int J, float* __restrict__ hm, int64_t hm_bs, int64_t hm_gs, __nv_bfloat16* __restrict__ hm_t) {
     extern __shared__ __align__(1024) uint8_t ht_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ht_raw) + 1023) & ~uintptr_t(1023));
@@ -106,13 +97,13 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
     }
     pdl_wait();
     if (tid < HT_NJ) sb[tid] = (tid < J) ? __ldg(bias + (int64_t)sel * J + tid) : 0.f;
-    {   // weight tile: fp32 [J][128] -> bf16 [2 k-blocks][16 rows][64], rows >= J zero
+    {   // weight tile: fp32 [J][128] -> fp16 [2 k-blocks][16 rows][64], rows >= J zero
         const int n = tid >> 4, piece = tid & 15;
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
         if (n < J) {
             const float4* src = reinterpret_cast<const float4*>(w + ((int64_t)sel * J + n) * HT_C + piece * 8);
             const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
-            u = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y), pack_bf16x2(f1.z, f1.w));
+            u = make_uint4(pack_f16x2(f0.x, f0.y), pack_f16x2(f0.z, f0.w), pack_f16x2(f1.x, f1.y), pack_f16x2(f1.z, f1.w));
         }
         const int kb = piece >> 3, pp = piece & 7;
         *reinterpret_cast<uint4*>(sW + kb * 2048 + n * 128 + ((pp ^ (n & 7)) << 4)) = u;
@@ -146,7 +137,8 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
         const uint32_t p01 = sS32 + ((cy.i0 - sr0) * HT_FS + cx.i1) * HT_PST;
         const uint32_t p10 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i0) * HT_PST;
         const uint32_t p11 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i1) * HT_PST;
-        const float w00 = cy.l0 * cx.l0, w01 = cy.l0 * cx.l1, w10 = cy.l1 * cx.l0, w11 = cy.l1 * cx.l1;
+        const __half2 w00 = __float2half2_rn(cy.l0 * cx.l0), w01 = __float2half2_rn(cy.l0 * cx.l1);
+        const __half2 w10 = __float2half2_rn(cy.l1 * cx.l0), w11 = __float2half2_rn(cy.l1 * cx.l1);
         const int r = tid & 127;
         const uint32_t arow = smem_u32(sA) + (tid >> 7) * 16384 + r * 128;
         const int sw = r & 7;
@@ -169,7 +161,7 @@ head_tail_tc_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
-                constexpr uint32_t idesc = make_idesc(128, HT_NJ, false);
+                constexpr uint32_t idesc = make_idesc_fmt(128, HT_NJ, 0u);      // fp16 operands
                 const uint64_t db = make_smem_desc(smem_u32(sW + kb * 2048));
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
@@ -226,7 +218,7 @@ int head_tail_tc(const void* z, const float* w, const float* bias, const int* ws
     }
     dim3 grid(HT_FO / HT_STRIP, G * B);
     const int4 sel = make_int4(wsel_host[0], wsel_host[1], wsel_host[2], wsel_host[3]);
-    EGR_LAUNCH(head_tail_tc_kernel, grid, 256, HT_SMEM, st, (const __nv_bfloat16*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs,
+    EGR_LAUNCH(head_tail_tc_kernel, grid, 256, HT_SMEM, st, (const __half*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs,
                (__nv_bfloat16*)hm_t);
     return EGR_OK;
 }

@@ -1,6 +1,7 @@
 // HBM-bound layout / resampling stages: NCHW->NHWC staging, bilinear x2 (align_corners=True) tails of the
 // heatmap heads and of the refined-feature projection, 2x2 max-pool, and one-time weight repacking.
 #include "layout_ops.cuh"
+#include <type_traits>
 
 namespace egr {
 
@@ -235,12 +236,42 @@ template <> __device__ __forceinline__ void pack8_store<__nv_bfloat16>(__nv_bflo
     *reinterpret_cast<uint4*>(p) = u;
 }
 
-// R1 tail, fast: relu(up2(z)) -> fp32 NCHW (float4 streaming stores) + channels-last TZ copy (16-byte stores)
+// R1 tail, fast: relu(up2(z)) -> fp32 NCHW (float4 streaming stores) and up to two channels-last copies (16-byte stores)
+// in bf16, fp16 or fp32 rounded to TF32.  With fp16 z (the tensor-core path) the channels-last pass interpolates in half2
+// arithmetic (HFMA2: two channels per instruction, no unpacking) - z already carries 16-bit rounding and the result is
+// stored in 16 bits, so fp16 arithmetic loses nothing that matters; the kernel is then bound by its stores.
+template <> __device__ __forceinline__ void unpack8<__half>(const __half* p, float* v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+template <> __device__ __forceinline__ void pack8_store<__half>(__half* p, const float* v) {
+    uint4 u;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(v[1]), "f"(v[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(v[3]), "f"(v[2]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.z) : "f"(v[5]), "f"(v[4]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.w) : "f"(v[7]), "f"(v[6]));
+    *reinterpret_cast<uint4*>(p) = u;
+}
+// store 8 channels-last values in the requested type: 0 fp32 rounded to TF32, 1 bf16, 2 fp16, 3 fp32 as is
+__device__ __forceinline__ void store8_dt(void* base, int64_t off, int dt, float* r) {
+    if (dt == 1) pack8_store<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(base) + off, r);
+    else if (dt == 2) pack8_store<__half>(reinterpret_cast<__half*>(base) + off, r);
+    else if (dt == 3) pack8_store<float>(reinterpret_cast<float*>(base) + off, r);
+    else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = round_tf32(r[i]);
+        pack8_store<float>(reinterpret_cast<float*>(base) + off, r);
+    }
+}
+
 template <typename TZ>
 __global__ void __launch_bounds__(256)
 up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ out_nchw, int64_t o_bs, int64_t o_gs,
-                          TZ* __restrict__ out_nhwc, void* __restrict__ out_nhwc_hp, int hp_f16) {
+                          void* __restrict__ cl0, int cl0_dt, void* __restrict__ cl1, int cl1_dt) {
     constexpr int SLD = 130;                               // transposed tile row stride: conflict-free both ways
+    constexpr bool HALF = std::is_same<TZ, __half>::value;
     extern __shared__ __align__(16) uint8_t fsm[];
     TZ* s1 = reinterpret_cast<TZ*>(fsm);                   // [FROWS*FS px][FCH]   as loaded
     TZ* s2 = s1 + FROWS * FS * FCH;                        // [FCH][SLD]           transposed
@@ -267,12 +298,9 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
             s2[c * SLD + p] = s1[i];
         }
     }
-    // ---- channels-last copy: item = (pixel, 8 channels) ----
-    if (out_nhwc || out_nhwc_hp) {
-        TZ* o = out_nhwc ? out_nhwc + ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH : nullptr;
-        const int64_t hp_off = ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH;
-        float* o32 = (out_nhwc_hp && !hp_f16) ? reinterpret_cast<float*>(out_nhwc_hp) + hp_off : nullptr;
-        __half* o16 = (out_nhwc_hp && hp_f16) ? reinterpret_cast<__half*>(out_nhwc_hp) + hp_off : nullptr;
+    // ---- channels-last copies: item = (pixel, 8 channels) ----
+    if (cl0 || cl1) {
+        const int64_t base = ((int64_t)img * FO * FO + (int64_t)y0 * FO) * FCH;
 #pragma unroll 2
         for (int it = threadIdx.x; it < FSTRIP * FO * (FCH / 8); it += 256) {
             const int c8 = it & 15, px = it >> 4;
@@ -281,26 +309,46 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
             const float ly0 = tab.l0[y0 + yy], ly1 = tab.l1[y0 + yy];
             const int xa = tab.i0[x], xb = tab.i1[x];
             const float lx0 = tab.l0[x], lx1 = tab.l1[x];
-            float a[8], bb[8], c[8], d[8], r[8];
-            unpack8<TZ>(s1 + (r0 * FS + xa) * FCH + c8 * 8, a);
-            unpack8<TZ>(s1 + (r0 * FS + xb) * FCH + c8 * 8, bb);
-            unpack8<TZ>(s1 + (r1 * FS + xa) * FCH + c8 * 8, c);
-            unpack8<TZ>(s1 + (r1 * FS + xb) * FCH + c8 * 8, d);
+            const int64_t off = base + (int64_t)px * FCH + c8 * 8;
+            if (HALF) {
+                const uint4 ua = *reinterpret_cast<const uint4*>(s1 + (r0 * FS + xa) * FCH + c8 * 8);
+                const uint4 ub = *reinterpret_cast<const uint4*>(s1 + (r0 * FS + xb) * FCH + c8 * 8);
+                const uint4 uc = *reinterpret_cast<const uint4*>(s1 + (r1 * FS + xa) * FCH + c8 * 8);
+                const uint4 ud = *reinterpret_cast<const uint4*>(s1 + (r1 * FS + xb) * FCH + c8 * 8);
+                const __half2 w00 = __float2half2_rn(ly0 * lx0), w01 = __float2half2_rn(ly0 * lx1);
+                const __half2 w10 = __float2half2_rn(ly1 * lx0), w11 = __float2half2_rn(ly1 * lx1);
+                const __half2 zero = __float2half2_rn(0.f);
+                const __half2* ha = reinterpret_cast<const __half2*>(&ua);
+                const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+                const __half2* hc = reinterpret_cast<const __half2*>(&uc);
+                const __half2* hd = reinterpret_cast<const __half2*>(&ud);
+                uint4 uo;
+                __half2* ho = reinterpret_cast<__half2*>(&uo);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = fmaxf(ly0 * (lx0 * a[i] + lx1 * bb[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]), 0.f);
-            if (o) pack8_store<TZ>(o + (int64_t)px * FCH + c8 * 8, r);
-            if (o16) {       // fp16, saturating
-                uint4 u;
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(r[1]), "f"(r[0]));
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(r[3]), "f"(r[2]));
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.z) : "f"(r[5]), "f"(r[4]));
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.w) : "f"(r[7]), "f"(r[6]));
-                *reinterpret_cast<uint4*>(o16 + (int64_t)px * FCH + c8 * 8) = u;
-            }
-            if (o32) {
+                for (int i = 0; i < 4; ++i)
+                    ho[i] = __hmax2(__hfma2(w11, hd[i], __hfma2(w10, hc[i], __hfma2(w01, hb[i], __hmul2(w00, ha[i])))), zero);
+                if (cl0 && cl0_dt == 2) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(cl0) + off) = uo;
+                if (cl1 && cl1_dt == 2) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(cl1) + off) = uo;
+                if ((cl0 && cl0_dt != 2) || (cl1 && cl1_dt != 2)) {
+                    float r[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = round_tf32(r[i]);
-                pack8_store<float>(o32 + (int64_t)px * FCH + c8 * 8, r);
+                    for (int i = 0; i < 4; ++i) { const float2 f = __half22float2(ho[i]); r[2 * i] = f.x; r[2 * i + 1] = f.y; }
+                    if (cl0 && cl0_dt != 2) store8_dt(cl0, off, cl0_dt, r);
+                    if (cl1 && cl1_dt != 2) store8_dt(cl1, off, cl1_dt, r);
+                }
+            } else {
+                float a[8], bb[8], c[8], d[8], r[8];
+                unpack8<TZ>(s1 + (r0 * FS + xa) * FCH + c8 * 8, a);
+                unpack8<TZ>(s1 + (r0 * FS + xb) * FCH + c8 * 8, bb);
+                unpack8<TZ>(s1 + (r1 * FS + xa) * FCH + c8 * 8, c);
+                unpack8<TZ>(s1 + (r1 * FS + xb) * FCH + c8 * 8, d);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = fmaxf(ly0 * (lx0 * a[i] + lx1 * bb[i]) + ly1 * (lx0 * c[i] + lx1 * d[i]), 0.f);
+                if (cl0) store8_dt(cl0, off, cl0_dt, r);
+                if (cl1) {
+                    // the TF32 store rounds r in place: keep it second when both are present (cl0 is never fp32 then)
+                    store8_dt(cl1, off, cl1_dt, r);
+                }
             }
         }
     }
@@ -419,8 +467,9 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st) {
     EGR_CHECK(J <= HJ && (2 * Hs) % STRIP == 0 && G <= 4, EGR_ERR_UNSUPPORTED, "head_up_conv: J=%d Hs=%d G=%d", J, Hs, G);
-    if (Hs == FS && Ws == FS && C == FCH && z_bf16 && g_opt_tc)      // tensor-core tail (head_tail_tc.cu)
+    if (Hs == FS && Ws == FS && C == FCH && z_bf16 == 2)      // tensor-core tail (head_tail_tc.cu): fp16 z, bf16 hm_t
         return head_tail_tc(z, w, bias, wsel_host, B, G, J, hm, hm_bs, hm_gs, hm_t, st);
+    EGR_CHECK(z_bf16 != 2, EGR_ERR_UNSUPPORTED, "head_up_conv: fp16 z needs the 32x32x128 geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;
         const size_t fsmem = sizeof(float) * FCH * HJ + es * FROWS * FS * 130;
@@ -497,25 +546,34 @@ up2_relu_dual_kernel(const TZ* __restrict__ z, int B, int Hs, int Ws, int C, flo
     }
 }
 
-int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* out_nhwc, void* out_nhwc_hp, int hp_f16, cudaStream_t st) {
+int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
+                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st) {
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
-        const size_t es = z_bf16 ? 2 : 4;
+        const size_t es = z_dt ? 2 : 4;
         // the transposed tile only serves the NCHW pass: without it the block needs half the shared memory
         const size_t fsmem = es * (FROWS * FS * FCH + (out_nchw ? FCH * 130 : 0));
         dim3 fgrid(FO / FSTRIP, G * B);
-        if (z_bf16) {
+        if (z_dt == 2) {
+            auto k = up2_relu_dual_fast_kernel<__half>;
+            EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __half*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt);
+        } else if (z_dt == 1) {
             auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, (__nv_bfloat16*)out_nhwc, out_nhwc_hp, hp_f16);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt);
         } else {
             auto k = up2_relu_dual_fast_kernel<float>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, (float*)out_nhwc, out_nhwc_hp, hp_f16);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt);
         }
         return EGR_OK;
     }
+    // general geometry (not on the shipped hot path): fp32 / bf16 z, one channels-last copy in z's type
+    void* out_nhwc = cl0;
+    void* out_nhwc_hp = cl1;
+    const int z_bf16 = z_dt;
+    EGR_CHECK(z_dt != 2 && (!cl0 || cl0_dt == (z_dt ? 1 : 3)), EGR_ERR_UNSUPPORTED, "up2_relu_dual: general geometry takes fp32 / bf16 z with a same-typed copy");
     EGR_CHECK(!out_nhwc_hp, EGR_ERR_UNSUPPORTED, "up2_relu_dual: the high-precision channels-last export needs the 32x32x128 geometry");
     const size_t smem = sizeof(float) * (size_t)C * (STRIP * Ws + 1);
     dim3 grid(2 * Hs / STRIP, G * B);

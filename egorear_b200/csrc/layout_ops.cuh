@@ -17,17 +17,16 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st);
 
-// the same tail on the tensor cores: bf16 z, 32x32 -> 64x64, C = 128 (head_tail_tc.cu); hm_t bf16
+// the same tail on the tensor cores: fp16 z (z_bf16 == 2 in head_up_conv), 32x32 -> 64x64, C = 128 (head_tail_tc.cu); hm_t bf16
 int head_tail_tc(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
                  int64_t hm_bs, int64_t hm_gs, void* hm_t, cudaStream_t st);
 
-// R1 tail: z [g][B][Hs*Ws][C] -> relu(up2(z)) written twice:
-//   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output) and
-//   out_nhwc [g][B][4HsWs][C] in the activation dtype (input of the H2 3x3 conv)
-//   out_nhwc_hp (optional) [g][B][4HsWs][C] high-precision copy for the pose3d proposal branch when chained:
-//                 fp32 rounded to TF32 (hp_f16 = 0) or fp16 (hp_f16 = 1)
-int up2_relu_dual(const void* z, int z_bf16, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* out_nhwc, void* out_nhwc_hp, int hp_f16, cudaStream_t st);
+// R1 tail: z [g][B][Hs*Ws][C] (z_dt: 0 fp32, 1 bf16, 2 fp16) -> relu(up2(z)) written to
+//   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output; optional) and up to two channels-last copies
+//   cl0 / cl1 [g][B][4HsWs][C] with their own element types (cl*_dt: 0 fp32 rounded to TF32, 1 bf16, 2 fp16, 3 fp32 as is): the input of
+//   the H2 3x3 conv and the high-precision copy of the pose3d proposal branch (one shared fp16 copy when chained)
+int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
+                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st);
 
 // nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C];  dt: 0 fp32, 1 bf16, 2 fp16
 int maxpool2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int W, int C, cudaStream_t st);
