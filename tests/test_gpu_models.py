@@ -248,3 +248,23 @@ def test_pipeline_cuda_graph_replay():
         got = pipe.replay(feat, bfb)
         torch.cuda.synchronize()
         assert torch.equal(got["packed"], want["packed"]) and torch.equal(got["list_hm"][-1], want["list_hm"][-1])
+
+
+@pytest.mark.parametrize("fp16", [0, 1])
+def test_pose3d_proposal_branch_types(case, fp16):
+    """the proposal branch in TF32 (fp32 activations, pre-rounded operands) and in fp16 (the bf16-mode default) both stay
+    within the 0.1 mm MPJPE budget of the standalone pose3d forward"""
+    from egorear_b200 import calib, engine
+    from oracle import model_ref
+    engine.set_option("pose_p2_fp16", fp16)
+    try:
+        m = build_pose3d("ego4view_syn", "bf16")
+        with torch.no_grad():
+            want = torch.stack(model_ref.pose3d_forward(m.state_dict(), case["feat"], case["lf"][1],
+                                                        calib.load_calibration(None), "ego4view_syn", None))
+            m = m.cuda()
+            assert m.engine().proposal_dtype() == ("f16" if fp16 else "tf32")
+            got = torch.stack(m(case["feat"].cuda(), case["lf"][1].cuda(), case["lh"][1].cuda(), None)).cpu()
+        assert mpjpe(got.numpy(), want.numpy()) < MPJPE_TOL
+    finally:
+        engine.set_option("pose_p2_fp16", 1)
