@@ -268,3 +268,40 @@ def test_pose3d_proposal_branch_types(case, fp16):
         assert mpjpe(got.numpy(), want.numpy()) < MPJPE_TOL
     finally:
         engine.set_option("pose_p2_fp16", 1)
+
+
+def test_no_writes_outside_outputs_and_workspace(monkeypatch):
+    """compute-sanitizer is not available on the GPU pool, so out-of-bounds WRITES are caught here: every tensor the
+    package allocates during a chained forward (outputs, workspaces, gathers) is carved out of a larger byte buffer with
+    256 KiB canaries on both sides, which must be untouched afterwards (ragged batch of 3, both output modes)."""
+    from egorear_b200 import synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    PAD = 256 * 1024
+    real_empty = torch.empty
+    guards = []
+
+    def canary_empty(*shape, dtype=torch.float32, device=None, **kw):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)):
+            shape = tuple(shape[0])
+        if device is None or torch.device(device).type != "cuda":
+            return real_empty(tuple(shape), dtype=dtype, device=device, **kw)
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * real_empty(0, dtype=dtype).element_size()
+        raw = torch.full((nbytes + 2 * PAD,), 0xAB, dtype=torch.uint8, device=device)
+        guards.append((raw, nbytes))
+        return raw[PAD:PAD + nbytes].view(dtype).view(*shape)
+
+    monkeypatch.setattr(torch, "empty", canary_empty)
+    feat, bfb = [t.to(dev) for t in synth.synth_features(3, 4, seed=13)]
+    for mat in (False, True):
+        pipe = HotPathPipeline(4, "ego4view_syn", "bf16", dev, materialize_features=mat)
+        out = pipe(feat, bfb)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out["packed"]).all()
+    monkeypatch.setattr(torch, "empty", real_empty)
+    assert len(guards) >= 10
+    for raw, nbytes in guards:
+        assert bool((raw[:PAD] == 0xAB).all()) and bool((raw[PAD + nbytes:] == 0xAB).all()), "write outside a %d-byte allocation" % nbytes
