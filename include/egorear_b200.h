@@ -39,11 +39,18 @@ extern "C" {
 
 /* precision of the dense conv/GEMM stages (token/attention math is always fp32) */
 #define EGR_PREC_FP32  0   /* fp32 SIMT kernels: reference-grade parity (<=1e-3 rel in fp32) */
-#define EGR_PREC_BF16  1   /* bf16 operands, fp32 accumulate in TMEM (tcgen05): stated looser bound */
+#define EGR_PREC_BF16  1   /* bf16 operands, fp32 accumulate in TMEM (tcgen05): stated looser bound; the stages that
+                            * need more than 8 mantissa bits (pose3d proposal branch, pre-upsample maps, token
+                            * Linears) run on fp16 / TF32 operands */
 
 const char* egr_last_error(void);
-/* process-wide switches, for debugging: "tc" (default 1) = EGR_PREC_BF16 uses the tcgen05 kernels;
- * 0 routes bf16 activations through the SIMT GEMM instead */
+/* process-wide switches (read when a handle is created / prepacked):
+ *   "tc" (1)            EGR_PREC_BF16 uses the tcgen05 kernels; 0 routes bf16 activations through the SIMT GEMM
+ *   "pdl" (1)           programmatic dependent launch between the library's kernels
+ *   "tok_batched" (1)   batched token path (token GEMMs on tcgen05) instead of the fused per-frame SIMT kernels
+ *   "pose_p2_fp16" (1)  pose3d proposal branch on fp16 operands; 0 = fp32 activations multiplied as TF32
+ *   "pose_p2_bf16" (0)  debugging: bf16 operands there (costs the whole 0.1 mm MPJPE budget)
+ *   "ws" (0)            weight-stationary mode of the tcgen05 GEMM (measured no gain) */
 int         egr_set_option(const char* key, int value);
 int         egr_version(void);
 /* stage profiler for bench.py: while enabled the engines record CUDA events between their stages on the launch
