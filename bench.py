@@ -433,6 +433,21 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     value = world * B * args.steps / (ms / 1e3)
+    # for transparency: the same loop on ONE stream (no overlap between consecutive batches)
+    single = None
+    if join is not None:
+        n1 = max(3, min(args.steps, 20))
+        torch.cuda.synchronize(dev)
+        egd.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(n1):
+            step_sync()
+        s1.record()
+        torch.cuda.synchronize(dev)
+        egd.barrier()
+        ms1 = egd.max_over_ranks(s0.elapsed_time(s1), dev)
+        single = {"value": world * B * n1 / (ms1 / 1e3), "ms_per_step": ms1 / n1, "steps": n1}
     extra = {}
     if args.workload == "rw_e2e":
         e = split["ev"]
@@ -517,7 +532,7 @@ def main():
                        if join is not None else "1",
                        "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "stages_ms": stages, "stage_roofline": stage_fracs}
+            "cpu_baseline": cpu, "stages_ms": stages, "stage_roofline": stage_fracs, "single_stream": single}
     line.update(extra)
     emit(line)
     egd.shutdown()
