@@ -210,6 +210,29 @@ def cpu_baseline(budget_s=12.0, frames_per_step=2):
             "sample": "%d frames (steps of %d) of the same workload, %.1f s, torch fp32 on %d host threads" % (n, frames_per_step, dt, cp.cores)}
 
 
+def cpu_baseline_eval(workload, budget_s=8.0):
+    """the oracle's numpy restatement of the wrappers' metric methods on one host core (the reference itself runs them
+    as per-sample Python loops over device tensors)"""
+    from egorear_b200 import synth
+    from oracle import metrics_ref as mr
+    if workload == "eval_pose":
+        n = 2048
+        a, b = synth.synth_eval_poses(n, 16, seed=0)
+        fn = lambda: mr.evaluate_pose(a, b)
+    else:
+        n = 16
+        a, b = synth.synth_eval_heatmaps(n, 4, 15, seed=0)
+        fn = lambda: mr.evaluate_heatmap(a, b)
+    fn()
+    done, t0 = 0, time.time()
+    while time.time() - t0 < budget_s and done < 64 * n:
+        fn()
+        done += n
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d units (steps of %d) through oracle/metrics_ref.py (numpy), %.1f s" % (done, n, dt)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -244,6 +267,10 @@ def workload_name(args):
             "pose3d": "ego4view_syn_pose3d lifting, batch %d/GPU" % args.batch,
             "generate_target": "generate_target sweep, 4 views x 16 joints, %d frames/step/GPU" % args.batch,
             "decode": "get_max_preds, 4 views x 15 joints, %d frames/step/GPU" % args.batch,
+            "eval_heatmap": "eval-time heatmap metrics (wrapper `evaluate`: L1, positive L1, MSE, arg-max MSE), 4 views x 15 joints, "
+                            "%d frames/step/GPU" % args.batch,
+            "eval_pose": "eval-time pose metrics (wrapper `evaluate_pose`: MPJPE, PA-MPJPE, PCK, AUC), 16 joints, "
+                         "%d poses/step/GPU" % args.batch,
             "rw_e2e": "ego4view_rw_heatmap_mvfex-n1_jqa + ego4view_rw_pose3d from images (PyTorch bf16-autocast backbone + hot path), "
                       "batch %d/GPU" % args.batch}[args.workload]
 
@@ -274,7 +301,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode", "rw_e2e"])
+    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode", "rw_e2e", "eval_heatmap", "eval_pose"])
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--lanes", type=int, default=3, help="streams alternated by the throughput loop (1 = one stream)")
@@ -283,11 +310,12 @@ def main():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {"mvfex_pose3d": 64, "mvfex": 64, "pose3d": 1024, "generate_target": 8192, "decode": 8192,
-                      "rw_e2e": 512}[args.workload]
+                      "rw_e2e": 512, "eval_heatmap": 2048, "eval_pose": 1 << 20}[args.workload]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    import numpy as np
     import torch
     from egorear_b200 import _lib, dist as egd, ops, synth
     from egorear_b200.pipeline import HotPathPipeline
@@ -393,6 +421,39 @@ def main():
             for _ in range(n):
                 out = step(kp_h.to(dev, non_blocking=True))
                 yield out[:, :, :, 0, 0].sum().cpu()                         # checksum read-back; maps stay on device
+    elif args.workload == "eval_heatmap":
+        from egorear_b200 import metrics
+        kp = torch.from_numpy(synth.synth_keypoints(B, 4, 15, seed=rank)).to(dev)
+        gt = ops.generate_target_batch(kp)                                   # [B,4,15,64,64], 2.0 GB at B=2048
+        gt_h = gt.cpu().pin_memory()
+        pred = gt * 0.9 + torch.randn(gt.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(rank)) * 0.03
+        in_bytes = gt_h.numel() * 4
+        l2_note = "inputs 2 x %.1f GB >> L2" % (in_bytes / 1e9)
+
+        def step(g=gt):
+            return metrics._heatmap_metrics(pred, g, 1.0, "bench")[0]     # per-frame errors stay on the device
+        e2e_api = "metrics.evaluate: targets uploaded from pinned host memory (they come from the data loader), per-frame errors read back"
+
+        def e2e_fn(n):
+            for _ in range(n):
+                m = metrics.evaluate(pred, gt_h.to(dev, non_blocking=True), "b")
+                yield torch.stack([m["b_l1_error_heatmap"], m["b_pos_l1_error_heatmap"]])
+    elif args.workload == "eval_pose":
+        from egorear_b200 import metrics
+        pr, gp = synth.synth_eval_poses(B, 16, seed=rank)
+        pr_h, gp_h = torch.from_numpy(pr).pin_memory(), torch.from_numpy(gp).pin_memory()
+        pr_d, gp_d = pr_h.to(dev), gp_h.to(dev)
+        in_bytes = gp_h.numel() * 4
+        l2_note = "inputs 2 x %.0f MB + 34 MB of results > 126 MB L2" % (in_bytes / 1e6)
+
+        def step(g=gp_d):
+            return metrics._pose_metrics(pr_d, g, 10.0, 150.0, metrics._AUC_THRESHOLDS, False, "bench")[0]
+        e2e_api = "metrics.evaluate_pose: ground truth uploaded from pinned host memory, the four per-sample metrics read back"
+
+        def e2e_fn(n):
+            for _ in range(n):
+                m = metrics.evaluate_pose(pr_d, gp_h.to(dev, non_blocking=True), "b")
+                yield torch.from_numpy(np.stack([v.astype(np.float64) for v in m.values()], 1))
     else:  # decode
         kp = torch.from_numpy(synth.synth_keypoints(B, 4, 15, seed=rank)).to(dev)
         hm = ops.generate_target_batch(kp).view(B * 4, 15, 64, 64)
@@ -516,10 +577,21 @@ def main():
                     "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "share_of_step": 1.0,
                     "ms_per_launch": t_s * 1e3}
 
+    elif rank == 0 and args.workload in ("eval_heatmap", "eval_pose"):
+        t_s = ms / 1e3 / args.steps
+        # algorithmic bytes: both maps of every (frame, view, joint) once + 16 B of partials | both poses + 4 doubles
+        per_unit = 2 * 4 * 15 * 4096 * 4 + 4 * 15 * 16 + 8 if args.workload == "eval_heatmap" else 2 * 16 * 3 * 4 + 32
+        ach = per_unit * B / t_s / 1e9
+        roofline = {"kernel": "eval_heatmap_kernel (+2 reductions)" if args.workload == "eval_heatmap" else "eval_pose_kernel",
+                    "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "traffic": None, "peak_source": peaks["src"], "share_of_step": 1.0, "ms_per_launch": t_s * 1e3}
+
     if rank != 0:
         egd.shutdown()
         return 0
     cpu = None
+    if world == 1 and not args.no_cpu_baseline and args.workload in ("eval_heatmap", "eval_pose"):
+        cpu = cpu_baseline_eval(args.workload)
     if world == 1 and not args.no_cpu_baseline and args.workload == "mvfex_pose3d":
         cpu = cpu_baseline()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

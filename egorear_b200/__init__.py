@@ -8,7 +8,7 @@ Everything computes through egorear_b200/libegorear_b200.so (C-ABI, include/egor
 import functools
 import importlib
 
-__all__ = ["patch", "PATCH_TABLE"]
+__all__ = ["patch", "PATCH_TABLE", "METHOD_PATCH_TABLE"]
 
 # reference module -> names rebound by patch() (reference file:line in INTEGRATION.md)
 PATCH_TABLE = {
@@ -28,6 +28,15 @@ PATCH_TABLE = {
     "pose_estimation.pl_wrappers.egoposeformer.pose_3d_mvf_ex": ["EgoPoseFormerMVFEX"],
 }
 
+# reference module -> {class: {method: egorear_b200.metrics function}}: the wrappers' eval-time metric methods
+# (per-sample Python loops with .cpu() syncs / numpy SVDs in the reference)
+METHOD_PATCH_TABLE = {
+    "pose_estimation.pl_wrappers.egoposeformer.heatmap": {"PoseHeatmapLightningModel": {"evaluate": "evaluate"}},
+    "pose_estimation.pl_wrappers.egoposeformer.heatmap_mvf_ex": {"PoseHeatmapMVFEXLightningModel": {"evaluate": "evaluate"}},
+    "pose_estimation.pl_wrappers.egoposeformer.pose_3d_mvf_ex": {
+        "Pose3DMVFEXLightningModel": {"evaluate_pose": "evaluate_pose", "evaluate_heatmap": "evaluate_heatmap"}},
+}
+
 _PRECISION_CLASSES = ("EgoPoseFormerHeatmapMVFEX", "HeatmapMVF", "EgoPoseFormerPose3D", "EgoPoseFormerMVFEX")
 
 
@@ -40,6 +49,13 @@ def _with_precision(cls, precision):
             super().__init__(*a, **k)
     _P.__name__, _P.__qualname__ = cls.__name__, cls.__qualname__
     return _P
+
+
+def _as_method(fn):
+    @functools.wraps(fn)
+    def method(self, *a, **k):
+        return fn(*a, **k)
+    return method
 
 
 def patch(precision="bf16", modules=None, strict=False):
@@ -74,4 +90,21 @@ def patch(precision="bf16", modules=None, strict=False):
             if hasattr(mod, n) or strict:
                 setattr(mod, n, repl[n])
                 done.setdefault(modname, []).append(n)
+    from . import metrics
+    for modname, classes in METHOD_PATCH_TABLE.items():
+        if modules is not None and modname not in modules:
+            continue
+        try:
+            mod = importlib.import_module(modname)
+        except Exception:
+            if strict:
+                raise
+            continue
+        for cname, methods in classes.items():
+            cls = getattr(mod, cname, None)
+            if cls is None:
+                continue
+            for mname, fname in methods.items():
+                setattr(cls, mname, _as_method(getattr(metrics, fname)))
+                done.setdefault(modname, []).append("%s.%s" % (cname, mname))
     return done

@@ -18,7 +18,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libegorear_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-parentheses", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-Wno-parentheses,-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 if os.environ.get("EGR_PTXAS_V"):
     FLAGS += ["-Xptxas", "-v"]
 

@@ -1,0 +1,239 @@
+// Eval-time metrics of the reference's Lightning wrappers, batched on the GPU:
+//   E1  heatmap metrics  pl_wrappers/egoposeformer/heatmap_mvf_ex.py:263-299 (`evaluate`) and
+//                        pl_wrappers/egoposeformer/pose_3d_mvf_ex.py:335-360 (`evaluate_heatmap`)
+//   E2  pose metrics     pl_wrappers/egoposeformer/pose_3d_mvf_ex.py:317-333 (`evaluate_pose`), which loops over the
+//                        batch in Python and runs numpy's SVD per sample (models/utils/pose_metric.py:104-167)
+// E1 is HBM-bound: the reference reads prediction and target maps about ten times (abs diff per view, the boolean
+// mask gathers of the per-sample Python loop, MSELoss, two get_max_preds); here one warp owns one (frame, view, joint)
+// map pair and reads each map exactly once (2 x 16 KiB), producing every statistic in the same pass.
+// E2 is tiny: one thread per sample, inputs staged through shared memory so the global loads are coalesced.
+#include "common.cuh"
+#include "eval_pose_math.cuh"
+
+namespace egr {
+
+// ---------------------------------------------------------------------------------------------
+// E1
+// ---------------------------------------------------------------------------------------------
+constexpr int EH_WARPS = 8;
+
+struct ArgBest {
+    float v; int i; bool nan;
+    __device__ __forceinline__ void init() { v = -INFINITY; i = 0x7fffffff; nan = false; }
+    // elements arrive in increasing index order within a lane: torch.max semantics (first maximum, NaN wins)
+    __device__ __forceinline__ void push(float x, int idx) {
+        if (!nan) {
+            if (x != x) { v = x; i = idx; nan = true; }
+            else if (x > v || i == 0x7fffffff) { v = x; i = idx; }
+        }
+    }
+    __device__ __forceinline__ void merge_warp() {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            const bool on = (ov != ov), bn = (v != v);
+            bool take;
+            if (on || bn) take = on && (!bn || oi < i);
+            else take = (ov > v) || (ov == v && oi < i);
+            if (take) { v = ov; i = oi; }
+        }
+    }
+};
+
+// part[m] = {sum |p-g|, sum_{g>0} |p-g|, sum (p-g)^2, masked squared pixel distance of the two arg-maxima}
+__global__ void __launch_bounds__(EH_WARPS * 32)
+eval_heatmap_kernel(const float* __restrict__ pred, int64_t pred_bs, const float* __restrict__ gt, int64_t gt_bs,
+                    int64_t n_maps, int maps_per_frame, int HW, int W, float threshold, float4* __restrict__ part) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_v4 = HW >> 2;
+    for (int64_t m = (int64_t)blockIdx.x * EH_WARPS + warp; m < n_maps; m += (int64_t)gridDim.x * EH_WARPS) {
+        const int64_t b = m / maps_per_frame;
+        const int64_t r = m - b * maps_per_frame;
+        const float4* ps = reinterpret_cast<const float4*>(pred + b * pred_bs + r * HW);
+        const float4* gs = reinterpret_cast<const float4*>(gt + b * gt_bs + r * HW);
+        float l1 = 0.f, pos = 0.f, sq = 0.f;
+        ArgBest bp, bg;
+        bp.init(); bg.init();
+        for (int i0 = 0; i0 < n_v4; i0 += 128) {
+            float4 p[4], g[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < n_v4) { p[u] = __ldcs(ps + i); g[u] = __ldcs(gs + i); }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + u * 32 + lane;
+                if (i < n_v4) {
+                    const float pe[4] = {p[u].x, p[u].y, p[u].z, p[u].w};
+                    const float ge[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float d = pe[k] - ge[k];
+                        const float a = fabsf(d);
+                        l1 += a;
+                        pos += (ge[k] > 0.f) ? a : 0.f;
+                        sq = fmaf(d, d, sq);
+                        bp.push(pe[k], (i << 2) + k);
+                        bg.push(ge[k], (i << 2) + k);
+                    }
+                }
+            }
+        }
+        l1 = warp_sum(l1); pos = warp_sum(pos); sq = warp_sum(sq);
+        bp.merge_warp(); bg.merge_warp();
+        if (lane == 0) {
+            // get_max_preds(threshold, normalize=False) on both; both point sets are multiplied by gt's validity mask
+            const float mk = (bg.v >= threshold) ? 1.f : 0.f;
+            const float dx = (float)(bp.i % W) * mk - (float)(bg.i % W) * mk;
+            const float dy = (float)(bp.i / W) * mk - (float)(bg.i / W) * mk;
+            part[m] = make_float4(l1, pos, sq, dx * dx + dy * dy);
+        }
+    }
+}
+
+// per frame: sums over its maps (fixed order, double) -> l1[b], pos_l1[b]; per-frame partials of the two global means
+__global__ void __launch_bounds__(128)
+eval_heatmap_frame_kernel(const float4* __restrict__ part, int64_t B, int maps_per_frame, float* __restrict__ l1,
+                          float* __restrict__ pos_l1, double2* __restrict__ frame_part) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const float4* p = part + b * maps_per_frame;
+    for (int i = 0; i < maps_per_frame; ++i) {
+        const float4 v = p[i];
+        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+    l1[b] = (float)s0;
+    pos_l1[b] = (float)s1;
+    frame_part[b] = make_double2(s2, s3);
+}
+
+// scalars[0] = mse_heatmap = sum (p-g)^2 / (B*maps*HW); scalars[1] = mse_pts2d = sum d^2 / (B*maps*2).  One block,
+// fixed reduction tree -> deterministic.
+__global__ void __launch_bounds__(1024)
+eval_heatmap_scalar_kernel(const double2* __restrict__ frame_part, int64_t B, double inv_n_elem, double inv_n_pts,
+                           float* __restrict__ scalars) {
+    pdl_trigger();
+    pdl_wait();
+    __shared__ double sh[2][32];
+    double a = 0, c = 0;
+    for (int64_t b = threadIdx.x; b < B; b += blockDim.x) { const double2 v = frame_part[b]; a += v.x; c += v.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a = sh[0][threadIdx.x]; c = sh[1][threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+        if (threadIdx.x == 0) { scalars[0] = (float)(a * inv_n_elem); scalars[1] = (float)(c * inv_n_pts); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// E2
+// ---------------------------------------------------------------------------------------------
+constexpr int EP_THREADS = 64;        // samples per block
+constexpr int EP_MAX_J = 32;
+constexpr int EP_MAX_AUC = 64;
+
+struct SmemRows {
+    const float* p;
+    __device__ __forceinline__ float operator()(int j, int c) const { return p[j * 3 + c]; }
+};
+
+__global__ void __launch_bounds__(EP_THREADS)
+eval_pose_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int64_t B, int J, float unit_scale,
+                 float pck_thr, const float* __restrict__ auc_thr, int n_auc, double* __restrict__ metrics,
+                 double* __restrict__ s1_hat) {
+    extern __shared__ float ep_smem[];
+    __shared__ float s_thr[EP_MAX_AUC];
+    pdl_trigger();
+    pdl_wait();
+    const int row = J * 3;
+    const int stride = row | 1;                      // odd word stride: conflict-free per-thread rows
+    float* sp = ep_smem;
+    float* sg = ep_smem + EP_THREADS * stride;
+    const int64_t b0 = (int64_t)blockIdx.x * EP_THREADS;
+    const int nb = (int)min((int64_t)EP_THREADS, B - b0);
+    for (int i = threadIdx.x; i < n_auc; i += EP_THREADS) s_thr[i] = auc_thr[i];
+    for (int i = threadIdx.x; i < nb * row; i += EP_THREADS) {       // coalesced: consecutive threads, consecutive words
+        const int s = i / row, e = i - s * row;
+        sp[s * stride + e] = __ldcs(pred + b0 * row + i);
+        sg[s * stride + e] = __ldcs(gt + b0 * row + i);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x >= nb) return;
+    const int64_t b = b0 + threadIdx.x;
+    SmemRows p{sp + threadIdx.x * stride}, g{sg + threadIdx.x * stride};
+    double out[4];
+    eval_pose_sample(p, g, J, unit_scale, pck_thr, s_thr, n_auc, out, s1_hat ? s1_hat + b * row : nullptr);
+    double2* mo = reinterpret_cast<double2*>(metrics + b * 4);
+    mo[0] = make_double2(out[0], out[1]);
+    mo[1] = make_double2(out[2], out[3]);
+}
+
+}  // namespace egr
+
+using namespace egr;
+
+extern "C" size_t egr_eval_heatmap_workspace_bytes(int64_t B, int V, int C) {
+    if (B < 0 || V <= 0 || C <= 0) return 0;
+    return (size_t)B * V * C * sizeof(float4) + (size_t)B * sizeof(double2) + 256;
+}
+
+extern "C" int egr_eval_heatmap(const float* pred, int64_t pred_batch_stride, const float* gt, int64_t gt_batch_stride,
+                                int64_t B, int V, int C, int H, int W, float threshold, float* l1, float* pos_l1,
+                                float* scalars, void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(B >= 0 && V > 0 && C > 0 && H > 0 && W > 0, EGR_ERR_INVALID, "eval_heatmap: heatmaps should be 5-ndim [B,V,C,H,W]");
+    EGR_CHECK((H * W) % 4 == 0, EGR_ERR_UNSUPPORTED, "eval_heatmap: H*W must be a multiple of 4");
+    const int64_t frame = (int64_t)V * C * H * W;
+    EGR_CHECK(pred_batch_stride >= frame && gt_batch_stride >= frame && pred_batch_stride % 4 == 0 && gt_batch_stride % 4 == 0,
+              EGR_ERR_INVALID, "eval_heatmap: batch strides must cover one [V,C,H,W] block and keep 16-byte alignment");
+    if (B == 0) return EGR_OK;
+    EGR_CHECK(pred && gt && l1 && pos_l1 && scalars && workspace, EGR_ERR_INVALID, "eval_heatmap: null pointer");
+    EGR_CHECK(((uintptr_t)pred % 16) == 0 && ((uintptr_t)gt % 16) == 0 && ((uintptr_t)workspace % 16) == 0, EGR_ERR_INVALID,
+              "eval_heatmap: pointers must be 16-byte aligned");
+    EGR_CHECK(workspace_bytes >= egr_eval_heatmap_workspace_bytes(B, V, C), EGR_ERR_INVALID, "eval_heatmap: workspace too small");
+    const int maps = V * C;
+    const int64_t n_maps = B * maps;
+    float4* part = reinterpret_cast<float4*>(workspace);
+    double2* fpart = reinterpret_cast<double2*>(part + n_maps);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<int64_t>(ceil_div64(n_maps, EH_WARPS), (int64_t)sm_count() * 8);
+    EGR_LAUNCH(eval_heatmap_kernel, grid, EH_WARPS * 32, 0, st, pred, pred_batch_stride, gt, gt_batch_stride, n_maps, maps,
+               H * W, W, threshold, part);
+    EGR_LAUNCH(eval_heatmap_frame_kernel, (int)ceil_div64(B, 128), 128, 0, st, (const float4*)part, B, maps, l1, pos_l1, fpart);
+    const double n_elem = (double)B * maps * H * W, n_pts = (double)B * maps * 2.0;
+    EGR_LAUNCH(eval_heatmap_scalar_kernel, 1, 1024, 0, st, (const double2*)fpart, B, 1.0 / n_elem, 1.0 / n_pts, scalars);
+    return EGR_OK;
+}
+
+extern "C" int egr_eval_pose(const float* pred, const float* gt, int64_t B, int J, float unit_scale, float pck_threshold,
+                             const float* auc_thresholds, int n_auc, double* metrics, double* s1_hat, void* stream) {
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(B >= 0 && J > 0, EGR_ERR_INVALID, "eval_pose: poses should be [B,J,3]");
+    EGR_CHECK(J <= EP_MAX_J, EGR_ERR_UNSUPPORTED, "eval_pose: at most %d joints", EP_MAX_J);
+    EGR_CHECK(n_auc >= 0 && n_auc <= EP_MAX_AUC, EGR_ERR_UNSUPPORTED, "eval_pose: at most %d AUC thresholds", EP_MAX_AUC);
+    if (B == 0) return EGR_OK;
+    EGR_CHECK(pred && gt && metrics && (n_auc == 0 || auc_thresholds), EGR_ERR_INVALID, "eval_pose: null pointer");
+    EGR_CHECK(((uintptr_t)metrics % 16) == 0, EGR_ERR_INVALID, "eval_pose: metrics must be 16-byte aligned");
+    const size_t smem = (size_t)2 * EP_THREADS * ((J * 3) | 1) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        EGR_CUDA_OK(cudaFuncSetAttribute(eval_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         2 * EP_THREADS * ((EP_MAX_J * 3) | 1) * (int)sizeof(float)));
+        attr_set = true;
+    }
+    EGR_LAUNCH(eval_pose_kernel, (int)ceil_div64(B, EP_THREADS), EP_THREADS, smem, (cudaStream_t)stream, pred, gt, B, J,
+               unit_scale, pck_threshold, auc_thresholds, n_auc, metrics, s1_hat);
+    return EGR_OK;
+}

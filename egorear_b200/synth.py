@@ -132,3 +132,54 @@ def synth_coord_trans_mat(B, seed=0, device="cpu"):
         M[:, v, :3, 3] = base_t[v] + noise[:, v]
         M[:, v, 3, 3] = 1.0
     return M.to(device)
+
+
+def synth_eval_poses(B, J=16, seed=0):
+    """(pred, gt) float32 [B,J,3] in cm for the eval-metric tests/bench: gt inside the body volume, pred = a random
+    similarity of gt plus joint noise whose scale varies per sample, so that PCK / AUC land strictly between 0 and 1.
+    Samples 0-3 are edge cases: exact match, point reflection, coplanar prediction, pure similarity."""
+    rng = np.random.default_rng(4000 + seed)
+    gt = rng.uniform(-60, 60, (B, J, 3))
+    gt[..., 2] -= 80.0
+    noise = rng.normal(0.0, 1.0, (B, J, 3)) * rng.uniform(0.2, 8.0, (B, 1, 1))
+    ang = rng.normal(0.0, 0.08, (B, 3))
+    ca, sa, cb, sb, cc, sc = (f(ang[:, i]) for i in range(3) for f in (np.cos, np.sin))
+    zero, one = np.zeros(B), np.ones(B)
+    Rx = np.stack([one, zero, zero, zero, ca, -sa, zero, sa, ca], -1).reshape(B, 3, 3)
+    Ry = np.stack([cb, zero, sb, zero, one, zero, -sb, zero, cb], -1).reshape(B, 3, 3)
+    Rz = np.stack([cc, -sc, zero, sc, cc, zero, zero, zero, one], -1).reshape(B, 3, 3)
+    R = Rz @ Ry @ Rx
+    mu = gt.mean(1, keepdims=True)
+    pred = np.einsum("bij,bkj->bki", R, gt - mu) * rng.uniform(0.9, 1.1, (B, 1, 1)) + mu + rng.normal(0, 2.0, (B, 1, 3)) + noise
+    if B > 0:
+        pred[0] = gt[0]
+    if B > 1:
+        pred[1] = -gt[1]
+    if B > 2:
+        pred[2, :, 2] = 0.0
+    if B > 3:
+        pred[3] = gt[3] * 2.5 + 7.0
+    return pred.astype(np.float32), gt.astype(np.float32)
+
+
+def synth_eval_heatmaps(B, V=2, C=15, hs=64, seed=0):
+    """(pred, gt) float32 [B,V,C,hs,hs]: gt = unit-peak Gaussians (sigma 1) at random cells, ~15 % of them off the map
+    (all-zero target -> invalid under the wrappers' threshold 1.0) and ~10 % attenuated below 1.0; pred = gt moved by
+    up to two cells, rescaled, plus dense noise (so arg-max positions differ and negative values occur)."""
+    rng = np.random.default_rng(5000 + seed)
+    yy, xx = np.meshgrid(np.arange(hs), np.arange(hs), indexing="ij")
+    n = B * V * C
+    cx = rng.integers(-8, hs + 8, n)
+    cy = rng.integers(-8, hs + 8, n)
+    amp = np.where(rng.uniform(size=n) < 0.1, 0.7, 1.0)
+    sx = cx + rng.integers(-2, 3, n)
+    sy = cy + rng.integers(-2, 3, n)
+    gt = np.zeros((n, hs, hs), np.float32)
+    pred = np.zeros((n, hs, hs), np.float32)
+    for i in range(n):
+        if 0 <= cx[i] < hs and 0 <= cy[i] < hs:
+            gt[i] = (amp[i] * np.exp(-((xx - cx[i]) ** 2 + (yy - cy[i]) ** 2) / 2.0)).astype(np.float32)
+            gt[i][gt[i] < 1e-4] = 0.0
+        pred[i] = (0.8 * np.exp(-((xx - sx[i]) ** 2 + (yy - sy[i]) ** 2) / 2.0)).astype(np.float32)
+    pred += rng.normal(0.0, 0.02, pred.shape).astype(np.float32)
+    return pred.reshape(B, V, C, hs, hs), gt.reshape(B, V, C, hs, hs)

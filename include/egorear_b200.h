@@ -24,6 +24,7 @@
 #ifndef EGOREAR_B200_H_
 #define EGOREAR_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -240,6 +241,38 @@ int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t
  * final 3D pose into one fp32 row per frame  [B, V*J2*2 + J3*3]  (672 B/frame for 4 views).
  * ------------------------------------------------------------------------------------------- */
 int egr_pack_joints(const float* preds2d, const float* pose3d, int B, int n2d, int n3d, float* packed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * E1  eval-time heatmap metrics
+ *     replaces pose_estimation/pl_wrappers/egoposeformer/heatmap_mvf_ex.py:263-299 (`evaluate`) and
+ *              pose_estimation/pl_wrappers/egoposeformer/pose_3d_mvf_ex.py:335-360 (`evaluate_heatmap`)
+ *   pred, gt  [B, V, C, H, W] float32; the [V,C,H,W] block of a frame is contiguous, consecutive frames are
+ *             *_batch_stride ELEMENTS apart (so the wrappers' view slices pred[:, 0:2] need no copy).
+ *   l1, pos_l1 [B] float32: sum over views/joints/pixels of |pred-gt|, and of the same where gt > 0.
+ *   scalars   [2] float32: {MSELoss(pred, gt), MSELoss of the arg-max pixel coordinates of pred and gt, both
+ *             multiplied by gt's validity mask (gt max >= threshold; the wrappers use threshold 1.0)}.
+ *   workspace: egr_eval_heatmap_workspace_bytes(B, V, C) bytes of device memory, 16-byte aligned.
+ *   Every map is read once (2 x H*W*4 bytes per (frame, view, joint)); reductions run in a fixed order.
+ * ------------------------------------------------------------------------------------------- */
+size_t egr_eval_heatmap_workspace_bytes(int64_t B, int V, int C);
+int egr_eval_heatmap(const float* pred, int64_t pred_batch_stride, const float* gt, int64_t gt_batch_stride, int64_t B,
+                     int V, int C, int H, int W, float threshold, float* l1, float* pos_l1, float* scalars,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * E2  eval-time pose metrics
+ *     replaces pose_estimation/pl_wrappers/egoposeformer/pose_3d_mvf_ex.py:317-333 (`evaluate_pose`):
+ *     batch_compute_similarity_transform_numpy (models/utils/pose_metric.py:104-167, a per-sample numpy SVD loop),
+ *     compute_mpjpe_batch / compute_pck_3d_batch / compute_auc_3d_batch (utils/loss.py:9-48).
+ *   pred, gt [B, J, 3] float32 contiguous, model units (cm); J <= 32.
+ *   metrics  [B, 4] float64: {MPJPE * unit_scale, PA-MPJPE * unit_scale, PCK(pck_threshold) * 100,
+ *            AUC(auc_thresholds) * 100}; PCK/AUC compare distances of the scaled poses (pred*unit_scale ...).
+ *            MPJPE/PCK/AUC are fp32 values widened; PA-MPJPE is float64 like the reference's numpy path.
+ *   auc_thresholds: DEVICE pointer to n_auc <= 64 float32 thresholds (np.linspace(0, 150, 31) in the reference).
+ *   s1_hat   [B, J, 3] float64 or NULL: the similarity-aligned prediction.
+ * ------------------------------------------------------------------------------------------- */
+int egr_eval_pose(const float* pred, const float* gt, int64_t B, int J, float unit_scale, float pck_threshold,
+                  const float* auc_thresholds, int n_auc, double* metrics, double* s1_hat, void* stream);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,23 @@ def import_functions():
                 get_max_preds_soft_pytorch=soft)
 
 
+def import_wrappers():
+    """The Lightning wrappers whose eval-time metric methods (evaluate / evaluate_pose / evaluate_heatmap) the golden
+    generator calls unbound.  pytorch_lightning is not installed: LightningModule -> nn.Module, ParallelStrategy -> object
+    (neither is touched by those methods)."""
+    install()
+    import torch.nn as nn
+    if "pytorch_lightning" not in sys.modules:
+        _stub("pytorch_lightning", LightningModule=nn.Module)
+        _stub("pytorch_lightning.strategies", ParallelStrategy=object)
+    from pose_estimation.pl_wrappers.egoposeformer.heatmap_mvf_ex import PoseHeatmapMVFEXLightningModel
+    from pose_estimation.pl_wrappers.egoposeformer.pose_3d_mvf_ex import Pose3DMVFEXLightningModel
+    from pose_estimation.models.utils import pose_metric
+    from pose_estimation.utils import loss as ref_loss
+    return dict(PoseHeatmapMVFEXLightningModel=PoseHeatmapMVFEXLightningModel,
+                Pose3DMVFEXLightningModel=Pose3DMVFEXLightningModel, pose_metric=pose_metric, loss=ref_loss)
+
+
 def load_model_cfg(name):
     import yaml
     cfg = yaml.safe_load(open(os.path.join(REF, "configs", name)))["model"]["init_args"]["model_cfg"]

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics")}
 
 
 def soft_inputs():

@@ -143,10 +143,40 @@ def golden_models(cls, gen_target):
     print("models:", {k: v.shape for k, v in out.items()})
 
 
+def golden_eval_metrics(w):
+    """eval-time metrics: the wrappers' own methods, called unbound on a stand-in `self` that
+    carries exactly the attributes they read (criteria, cm2mm, num_heatmap, get_anchors_2d_from_hm)."""
+    import types
+    H, P = w["PoseHeatmapMVFEXLightningModel"], w["Pose3DMVFEXLightningModel"]
+    out = {}
+    pred, gt = synth.synth_eval_poses(64, 16, seed=0)
+    self_p = types.SimpleNamespace(cm2mm=10)
+    m = P.evaluate_pose(self_p, torch.from_numpy(pred), torch.from_numpy(gt), "final")
+    for k, v in m.items():
+        out["pose_" + k] = np.asarray(v)
+    out["pose_s1_hat"] = w["pose_metric"].batch_compute_similarity_transform_numpy(torch.from_numpy(pred), torch.from_numpy(gt)).numpy()
+    ph, gh = synth.synth_eval_heatmaps(6, 4, 15, seed=0)
+    self_h = types.SimpleNamespace(criteria=torch.nn.MSELoss(reduction="mean"), num_heatmap=15)
+    self_h.get_anchors_2d_from_hm = lambda hm: H.get_anchors_2d_from_hm(self_h, hm)
+    for tag, sl in (("front", slice(0, 2)), ("back", slice(2, 4)), ("all", slice(0, 4))):
+        m = H.evaluate(self_h, torch.from_numpy(ph)[:, sl], torch.from_numpy(gh)[:, sl], tag)
+        for k, v in m.items():
+            out["hm_" + k] = v.numpy()
+    m = P.evaluate_heatmap(self_p, torch.from_numpy(ph), torch.from_numpy(gh), "p3d")
+    for k, v in m.items():
+        out["hm_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "eval_metrics.npz"), **out)
+    print("eval_metrics:", {k: (v.shape, v.dtype) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert ref_import.available(), "needs the reference checkout"
+    if "--metrics-only" in sys.argv:            # regenerate eval_metrics.npz alone
+        golden_eval_metrics(ref_import.import_wrappers())
+        sys.exit(0)
     fns = ref_import.import_functions()
     golden_generate_target(fns["generate_target"])
     golden_decode(fns["get_max_preds"])
     golden_soft(fns["get_max_preds_soft_pytorch"])
+    golden_eval_metrics(ref_import.import_wrappers())
     golden_models(ref_import.import_estimators(), fns["generate_target"])
