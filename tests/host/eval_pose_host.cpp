@@ -14,9 +14,11 @@ struct Rows {
 
 extern "C" void eval_pose_host(const float* pred, const float* gt, int64_t B, int J, float unit_scale, float pck_thr,
                                const float* auc_thr, int n_auc, double* metrics, double* s1_hat) {
+    bool sorted = true;
+    for (int i = 0; i + 1 < n_auc; ++i) sorted = sorted && (auc_thr[i] <= auc_thr[i + 1]);
     for (int64_t b = 0; b < B; ++b) {
         Rows p{pred + b * J * 3}, g{gt + b * J * 3};
-        egr::eval_pose_sample(p, g, J, unit_scale, pck_thr, auc_thr, n_auc, metrics + b * 4,
+        egr::eval_pose_sample(p, g, J, unit_scale, pck_thr, auc_thr, n_auc, sorted, metrics + b * 4,
                               s1_hat ? s1_hat + b * J * 3 : nullptr);
     }
 }

@@ -1,7 +1,7 @@
 """CPU: eval-time metrics.
 
   * oracle/metrics_ref.py is pinned to tests/golden/eval_metrics.npz (produced by the live reference's wrapper methods);
-  * the per-sample arithmetic the CUDA kernel runs (egorear_b200/csrc/eval_pose_math.cuh: Jacobi 3x3 SVD, Procrustes,
+  * the per-sample arithmetic the CUDA kernel runs (egorear_b200/csrc/eval_pose_math.cuh: float32 Jacobi 3x3 SVD, Procrustes,
     MPJPE / PCK / AUC) is compiled for the host (tests/host/eval_pose_host.cpp, test infrastructure) and checked against
     the oracle and the golden vectors, including rank-deficient inputs;
   * patch() rebinds the wrappers' metric methods.
@@ -80,7 +80,7 @@ def test_kernel_arithmetic_matches_golden_and_oracle(golden, host_lib):
     pred, gt = synth.synth_eval_poses(64, 16, seed=0)
     m, s = run_host(host_lib, pred, gt)
     assert np.allclose(m[:, 0], g["pose_final_mpjpe"], rtol=1e-6, atol=1e-5)
-    # the reference's SVD is LAPACK float32; ours is double: agreement to float32 accuracy of the aligned points (cm)
+    # float32 SVD on both sides (LAPACK there, Jacobi here): agreement to float32 accuracy of the aligned points (cm)
     assert np.allclose(s, g["pose_s1_hat"], rtol=0, atol=2e-4)
     assert np.allclose(m[:, 1], g["pose_final_pa_mpjpe"], rtol=1e-5, atol=2e-3)
     assert np.array_equal(m[:, 2].astype(np.float32), g["pose_final_pck_3d"])
@@ -112,9 +112,9 @@ def test_kernel_arithmetic_rank_deficient_and_reflection(host_lib):
     for b in range(6):
         want = ref64(pred[b], gt[b])
         if b == 4:
-            assert abs(np.linalg.norm(s[b] - gt[b], axis=-1).mean() - np.linalg.norm(want - gt[b], axis=-1).mean()) < 1e-6
+            assert abs(np.linalg.norm(s[b] - gt[b], axis=-1).mean() - np.linalg.norm(want - gt[b], axis=-1).mean()) < 5e-5
         else:
-            assert np.allclose(s[b], want, rtol=0, atol=1e-7), b
+            assert np.allclose(s[b], want, rtol=0, atol=5e-5), b     # float32 SVD (like the reference's), cm
     # the mirror cases really take the det < 0 branch: a reflection would fit exactly, the rotation cannot
     assert np.linalg.norm(s[2] - gt[2], axis=-1).mean() > 1.0
 

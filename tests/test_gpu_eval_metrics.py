@@ -26,7 +26,7 @@ def test_evaluate_pose_golden(metrics, golden):
     assert all(isinstance(v, np.ndarray) and v.shape == (64,) for v in m.values())
     assert m["final_mpjpe"].dtype == np.float32 and m["final_pa_mpjpe"].dtype == np.float64
     assert np.allclose(m["final_mpjpe"], g["pose_final_mpjpe"], rtol=1e-6, atol=1e-5)
-    # reference: LAPACK float32 SVD per sample; kernel: double Jacobi -> float32-level agreement (mm)
+    # float32 SVD on both sides (LAPACK per sample there, Jacobi here) -> float32-level agreement (mm)
     assert np.allclose(m["final_pa_mpjpe"], g["pose_final_pa_mpjpe"], rtol=1e-5, atol=2e-3)
     assert np.array_equal(m["final_pck_3d"], g["pose_final_pck_3d"])
     assert np.allclose(m["final_auc_3d"], g["pose_final_auc_3d"], rtol=1e-6)
