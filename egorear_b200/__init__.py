@@ -13,6 +13,7 @@ __all__ = ["patch", "PATCH_TABLE", "METHOD_PATCH_TABLE"]
 # reference module -> names rebound by patch() (reference file:line in INTEGRATION.md)
 PATCH_TABLE = {
     "pose_estimation.utils.loss": ["get_max_preds", "get_max_preds_soft_pytorch"],
+    "pose_estimation.utils.util": ["integrate_tensor_2d"],
     "generate_heatmap": ["generate_target"],
     "pose_estimation.models.utils.deform_attn": ["MSDeformAttn"],
     "pose_estimation.models.estimator.egoposeformer_heatmap": ["EgoPoseFormerHeatmap"],
@@ -70,7 +71,7 @@ def patch(precision="bf16", modules=None, strict=False):
     from . import _lib, modules as M, ops
     _lib.load()
     repl = {"get_max_preds": ops.get_max_preds, "generate_target": ops.generate_target,
-            "get_max_preds_soft_pytorch": ops.get_max_preds_soft_pytorch}
+            "get_max_preds_soft_pytorch": ops.get_max_preds_soft_pytorch, "integrate_tensor_2d": ops.integrate_tensor_2d}
     for name in set(n for names in PATCH_TABLE.values() for n in names):
         if name in repl:
             continue

@@ -44,6 +44,7 @@ SIGNATURES = {
     "egr_launch_count": (c_int64, []),
     "egr_generate_target": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, c_int, c_double, c_void_p, c_void_p]),
     "egr_decode_soft_argmax": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "egr_integrate_tensor_2d": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "egr_decode_argmax": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
     "egr_msda_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,

@@ -176,6 +176,67 @@ decode_soft_argmax_kernel(const float* __restrict__ hm, int64_t n_hm, int H, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// D1i  integral (soft-argmax) decoder: integrate_tensor_2d (pose_estimation/utils/util.py:80-109)
+//   v = hm * multiplier; softmax: p = softmax(v) over H*W, else p = relu(v); x = sum_w w * sum_h p, y = sum_h h * sum_w p,
+//   divided by the total mass in the relu variant (0/0 -> NaN like torch); returns the coordinates AND p.
+//   One warp per map: max pass, sums pass, write pass (passes 2 and 3 re-read the 16 KB map from L1/L2): HBM traffic is
+//   one read + one write of the map.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DEC_WARPS * 32)
+integrate_2d_kernel(const float* __restrict__ hm, int64_t n_hm, int H, int W, int softmax, float mult,
+                    float* __restrict__ coords, float* __restrict__ hm_out) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int HW = H * W, n_v4 = HW >> 2;
+    for (int64_t m = (int64_t)blockIdx.x * DEC_WARPS + warp; m < n_hm; m += (int64_t)gridDim.x * DEC_WARPS) {
+        const float4* src = reinterpret_cast<const float4*>(hm + m * (int64_t)HW);
+        float4* dst = hm_out ? reinterpret_cast<float4*>(hm_out + m * (int64_t)HW) : nullptr;
+        float mx = 0.f;
+        if (softmax) {
+            mx = -INFINITY;
+            for (int i = lane; i < n_v4; i += 32) {
+                const float4 v = __ldg(src + i);
+                mx = fmaxf(fmaxf(mx, fmaxf(v.x * mult, v.y * mult)), fmaxf(v.z * mult, v.w * mult));
+            }
+            mx = warp_max(mx);
+        }
+        float s = 0.f, sx = 0.f, sy = 0.f;
+        for (int i = lane; i < n_v4; i += 32) {
+            const float4 v = __ldg(src + i);
+            const int base = i << 2;                 // W % 4 == 0: the 4 values share a row
+            const int h = base / W, w0 = base - h * W;
+            float e0, e1, e2, e3;
+            if (softmax) {
+                // hm * multiplier is rounded BEFORE the softmax in the reference: no FMA contraction into (v*mult - mx)
+                e0 = expf(__fmul_rn(v.x, mult) - mx); e1 = expf(__fmul_rn(v.y, mult) - mx);
+                e2 = expf(__fmul_rn(v.z, mult) - mx); e3 = expf(__fmul_rn(v.w, mult) - mx);
+            } else {
+                e0 = fmaxf(v.x * mult, 0.f); e1 = fmaxf(v.y * mult, 0.f); e2 = fmaxf(v.z * mult, 0.f); e3 = fmaxf(v.w * mult, 0.f);
+                if (dst) __stcs(dst + i, make_float4(e0, e1, e2, e3));
+            }
+            const float es = (e0 + e1) + (e2 + e3);
+            s += es;
+            sy = fmaf(es, (float)h, sy);
+            sx += e0 * (float)w0 + e1 * (float)(w0 + 1) + e2 * (float)(w0 + 2) + e3 * (float)(w0 + 3);
+        }
+        s = warp_sum(s); sx = warp_sum(sx); sy = warp_sum(sy);
+        if (softmax && dst) {
+            for (int i = lane; i < n_v4; i += 32) {
+                const float4 v = __ldg(src + i);
+                __stcs(dst + i, make_float4(expf(__fmul_rn(v.x, mult) - mx) / s, expf(__fmul_rn(v.y, mult) - mx) / s,
+                                            expf(__fmul_rn(v.z, mult) - mx) / s, expf(__fmul_rn(v.w, mult) - mx) / s));
+            }
+        }
+        if (lane == 0) {
+            coords[m * 2 + 0] = sx / s;
+            coords[m * 2 + 1] = sy / s;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // H1'  1x1 conv C->J on NCHW fp32 (estimator/egoposeformer_heatmap.py:23,34-39)
 //   thread = 4 consecutive positions; loads are float4-coalesced per channel; weights broadcast from smem
 // ---------------------------------------------------------------------------------------------
@@ -320,6 +381,20 @@ extern "C" int egr_decode_argmax(const float* hm, int64_t N, int J, int H, int W
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
     EGR_LAUNCH(decode_argmax_kernel, grid, DEC_WARPS * 32, 0, (cudaStream_t)stream,
                hm, n_hm, H * W, W, 1.f / W, 1.f / H, H, threshold, normalize, preds, maxvals, valid, idx);
+    return EGR_OK;
+}
+
+extern "C" int egr_integrate_tensor_2d(const float* hm, int64_t N, int J, int H, int W, int softmax, float multiplier,
+                                       float* coords, float* hm_out, void* stream) {
+    if (int rc = require_device()) return rc;
+    EGR_CHECK(N >= 0 && J > 0 && H > 0 && W > 0, EGR_ERR_INVALID, "integrate_tensor_2d: heatmaps should be [B, J, H, W]");
+    EGR_CHECK(W % 4 == 0, EGR_ERR_UNSUPPORTED, "integrate_tensor_2d: W must be a multiple of 4");
+    if (N == 0) return EGR_OK;
+    EGR_CHECK(hm && coords, EGR_ERR_INVALID, "integrate_tensor_2d: null pointer");
+    EGR_CHECK(((uintptr_t)hm % 16) == 0 && ((uintptr_t)hm_out % 16) == 0, EGR_ERR_INVALID, "integrate_tensor_2d: pointers must be 16-byte aligned");
+    const int64_t n_hm = N * J;
+    const int grid = (int)std::min<int64_t>(ceil_div64(n_hm, DEC_WARPS), (int64_t)sm_count() * 16);
+    EGR_LAUNCH(integrate_2d_kernel, grid, DEC_WARPS * 32, 0, (cudaStream_t)stream, hm, n_hm, H, W, softmax, multiplier, coords, hm_out);
     return EGR_OK;
 }
 

@@ -3,6 +3,7 @@
 Same names, argument meaning and error behaviour as the reference functions:
 
   get_max_preds     <- pose_estimation/utils/loss.py:122-142
+  integrate_tensor_2d <- pose_estimation/utils/util.py:80-109
   generate_target   <- generate_heatmap.py:10-48
   ms_deform_attn    <- mmcv MultiScaleDeformableAttnFunction (models/utils/deform_attn.py:155-162)
   reproject_fisheye <- EgoPoseFormerPose3D._reproject_3d_to_2d (estimator/egoposeformer_mvf_ex.py:340-382)
@@ -68,6 +69,21 @@ def get_max_preds_soft_pytorch(batch_heatmaps, normalize=False):
     _lib.check(_lib.load().egr_decode_soft_argmax(_ptr(hm), B, J, H, W, int(bool(normalize)), _ptr(preds), _ptr(maxvals),
                                                   _stream()))
     return preds, maxvals
+
+
+def integrate_tensor_2d(heatmaps, softmax=True, multiplier=100.0):
+    """Drop-in for pose_estimation.utils.util.integrate_tensor_2d (:80-109): integral (soft-argmax) decoding.
+    -> coordinates [B, J, 2] (x, y) and the normalised heatmaps [B, J, H, W] (softmax(hm * multiplier) or relu)."""
+    _need_cuda(heatmaps, "integrate_tensor_2d")
+    batch_size, n_heatmaps, h, w = heatmaps.shape
+    hm = heatmaps.detach()
+    if hm.dtype != torch.float32 or not hm.is_contiguous():
+        hm = hm.float().contiguous()
+    coords = torch.empty((batch_size, n_heatmaps, 2), dtype=torch.float32, device=hm.device)
+    out = torch.empty_like(hm)
+    _lib.check(_lib.load().egr_integrate_tensor_2d(_ptr(hm), batch_size, n_heatmaps, h, w, int(bool(softmax)), float(multiplier),
+                                                   _ptr(coords), _ptr(out), _stream()))
+    return coords, out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -84,6 +84,15 @@ int egr_decode_soft_argmax(const float* hm, int64_t N, int J, int H, int W, int 
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * D1i integrate_tensor_2d                 replaces pose_estimation/utils/util.py:80-109 (integral soft-argmax decoder)
+ *   hm [N, J, H, W] float32; v = hm * multiplier; p = softmax(v) over H*W (softmax != 0) or relu(v);
+ *   coords [N, J, 2] float32 = (sum_w w * sum_h p, sum_h h * sum_w p), divided by sum p in the relu variant;
+ *   hm_out [N, J, H, W] float32 = p (second return value of the reference), or NULL.  W must be a multiple of 4.
+ * ------------------------------------------------------------------------------------------- */
+int egr_integrate_tensor_2d(const float* hm, int64_t N, int J, int H, int W, int softmax, float multiplier, float* coords,
+                            float* hm_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * D1  get_max_preds                       replaces pose_estimation/utils/loss.py:122-142
  *   hm [N, J, H, W] float32 -> preds [N, J, 2] float32 (x, y), maxvals [N, J] float32,
  *   valid [N, J] uint8 (torch.bool storage), idx [N, J] int32 flat argmax (may be NULL).

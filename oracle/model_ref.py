@@ -82,6 +82,21 @@ def get_max_preds_soft_pytorch(batch_heatmaps: Tensor, normalize: bool = False):
     return torch.cat([x, y], dim=2), maxvals
 
 
+def integrate_tensor_2d(heatmaps: Tensor, softmax: bool = True, multiplier: float = 100.0):
+    """integral decoder, utils/util.py:80-109: softmax (or relu) of hm * multiplier, marginal masses times the pixel
+    index; the relu variant divides by the total mass.  Returns (coordinates [B,J,2], normalised heatmaps)."""
+    B, J, H, W = heatmaps.shape
+    v = (heatmaps * multiplier).reshape(B, J, -1)
+    p = (F.softmax(v, dim=2) if softmax else F.relu(v)).reshape(B, J, H, W)
+    mass_x, mass_y = p.sum(dim=2), p.sum(dim=3)
+    x = (mass_x * torch.arange(W, dtype=torch.float32)).sum(dim=2, keepdim=True)
+    y = (mass_y * torch.arange(H, dtype=torch.float32)).sum(dim=2, keepdim=True)
+    if not softmax:
+        x = x / mass_x.sum(dim=2, keepdim=True)
+        y = y / mass_y.sum(dim=2, keepdim=True)
+    return torch.cat((x, y), dim=2).reshape(B, J, 2), p
+
+
 # ----------------------------------------------------------------------------------------------
 # mmcv ms_deform_attn_forward, single level            models/utils/deform_attn.py:155-162
 # ----------------------------------------------------------------------------------------------

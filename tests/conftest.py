@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics", "integrate_tensor_2d")}
 
 
 def soft_inputs():
@@ -29,6 +29,17 @@ def soft_inputs():
     hm[3, 0] = 0.25
     hm[3, 1] = 0.0; hm[3, 1, 5, 60] = 30.0
     hm[3, 2] = -50.0; hm[3, 2, 63, 0] = 40.0; hm[3, 2, 0, 63] = 40.0
+    return hm
+
+
+INTEGRATE_CASES = (("sm100", True, 100.0), ("sm1", True, 1.0), ("relu", False, 100.0))
+INTEGRATE_MAPS = ((0, 0), (1, 5), (2, 7), (3, 1), (3, 2), (3, 3))
+
+
+def integrate_inputs():
+    """tests/golden/make_golden.py::integrate_inputs"""
+    hm = soft_inputs()
+    hm[3, 3] = -1.0
     return hm
 
 

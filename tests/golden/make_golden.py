@@ -143,6 +143,32 @@ def golden_models(cls, gen_target):
     print("models:", {k: v.shape for k, v in out.items()})
 
 
+INTEGRATE_CASES = (("sm100", True, 100.0), ("sm1", True, 1.0), ("relu", False, 100.0))
+INTEGRATE_MAPS = ((0, 0), (1, 5), (2, 7), (3, 1), (3, 2), (3, 3))
+
+
+def integrate_inputs():
+    hm = soft_inputs()
+    hm[3, 3] = -1.0                                   # relu variant: zero mass -> NaN coordinates
+    return hm
+
+
+def golden_integrate():
+    """utils/util.py:80-109 (open3d, imported at the top of that module, is stubbed: not installed, not used here)"""
+    import types
+    ref_import.install()
+    sys.modules.setdefault("open3d", types.ModuleType("open3d"))
+    from pose_estimation.utils import util
+    hm = integrate_inputs()
+    out = {}
+    for tag, sm, mult in INTEGRATE_CASES:
+        c, p = util.integrate_tensor_2d(hm.clone(), softmax=sm, multiplier=mult)
+        out["coords_" + tag] = c.numpy()
+        out["maps_" + tag] = np.stack([p[b, j].numpy() for b, j in INTEGRATE_MAPS])
+    np.savez_compressed(os.path.join(HERE, "integrate_tensor_2d.npz"), **out)
+    print("integrate_tensor_2d:", {k: v.shape for k, v in out.items()})
+
+
 def golden_eval_metrics(w):
     """eval-time metrics: the wrappers' own methods, called unbound on a stand-in `self` that
     carries exactly the attributes they read (criteria, cm2mm, num_heatmap, get_anchors_2d_from_hm)."""
@@ -174,9 +200,13 @@ if __name__ == "__main__":
     if "--metrics-only" in sys.argv:            # regenerate eval_metrics.npz alone
         golden_eval_metrics(ref_import.import_wrappers())
         sys.exit(0)
+    if "--integrate-only" in sys.argv:
+        golden_integrate()
+        sys.exit(0)
     fns = ref_import.import_functions()
     golden_generate_target(fns["generate_target"])
     golden_decode(fns["get_max_preds"])
     golden_soft(fns["get_max_preds_soft_pytorch"])
     golden_eval_metrics(ref_import.import_wrappers())
+    golden_integrate()
     golden_models(ref_import.import_estimators(), fns["generate_target"])

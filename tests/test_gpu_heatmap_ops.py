@@ -156,3 +156,28 @@ def test_soft_argmax_decoder(ops, golden):
         ops.get_max_preds_soft_pytorch(big[0].cuda())
     e, _ = ops.get_max_preds_soft_pytorch(big[:0].cuda())
     assert e.shape == (0, 16, 2)
+
+
+def test_integrate_tensor_2d_golden_and_oracle(ops, golden):
+    """D1i integral decoder (utils/util.py:80-109) vs the live reference's vectors and the oracle"""
+    from conftest import INTEGRATE_CASES, INTEGRATE_MAPS, integrate_inputs
+    from oracle import model_ref
+    g = golden["integrate_tensor_2d"]
+    hm = integrate_inputs()
+    for tag, sm, mult in INTEGRATE_CASES:
+        c, p = ops.integrate_tensor_2d(hm.cuda(), softmax=sm, multiplier=mult)
+        assert c.shape == (4, 15, 2) and p.shape == hm.shape and c.is_cuda and p.is_cuda
+        assert np.allclose(c.cpu().numpy(), g["coords_" + tag], rtol=2e-6, atol=2e-5, equal_nan=True), tag
+        got = np.stack([p[b, j].cpu().numpy() for b, j in INTEGRATE_MAPS])
+        assert np.allclose(got, g["maps_" + tag], rtol=2e-6, atol=1e-35), tag
+    # seeded sweep incl. a non-square map, against the oracle; every softmax map sums to 1
+    gen = torch.Generator().manual_seed(3)
+    for shape, sm, mult in (((3, 16, 64, 64), True, 100.0), ((2, 5, 48, 32), True, 7.5), ((2, 5, 48, 32), False, 1.0)):
+        x = torch.rand(shape, generator=gen) - (0.0 if sm else 0.3)
+        c, p = ops.integrate_tensor_2d(x.cuda(), sm, mult)
+        rc, rp = model_ref.integrate_tensor_2d(x, sm, mult)
+        assert torch.allclose(c.cpu(), rc, rtol=2e-6, atol=2e-5) and torch.allclose(p.cpu(), rp, rtol=2e-6, atol=1e-35)
+        if sm:
+            assert torch.allclose(p.sum((2, 3)).cpu(), torch.ones(shape[:2]), atol=1e-5)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.integrate_tensor_2d(hm)

@@ -99,3 +99,21 @@ def test_soft_argmax_oracle_matches_golden(golden):
         fn = ref_import.import_functions()["get_max_preds_soft_pytorch"]
         p2, m2 = fn(hm.clone(), False)
         assert np.array_equal(p2.numpy(), g["preds_raw"]) and np.array_equal(m2.numpy(), g["maxvals_raw"])
+
+
+def test_integrate_tensor_2d_oracle_matches_golden(golden):
+    """oracle restatement of integrate_tensor_2d (utils/util.py:80-109) vs vectors from the live reference"""
+    from conftest import INTEGRATE_CASES, INTEGRATE_MAPS, integrate_inputs
+    from oracle import model_ref
+    g = golden["integrate_tensor_2d"]
+    hm = integrate_inputs()
+    for tag, sm, mult in INTEGRATE_CASES:
+        c, p = model_ref.integrate_tensor_2d(hm, sm, mult)
+        assert c.shape == (4, 15, 2) and p.shape == hm.shape
+        assert np.allclose(c.numpy(), g["coords_" + tag], rtol=1e-6, atol=1e-5, equal_nan=True)
+        got = np.stack([p[b, j].numpy() for b, j in INTEGRATE_MAPS])
+        assert np.allclose(got, g["maps_" + tag], rtol=1e-6, atol=0)
+    # known answers: constant map -> centre; one dominant cell -> that cell; zero relu mass -> NaN (0/0, like torch)
+    assert np.allclose(g["coords_sm1"][3, 0], [31.5, 31.5], atol=1e-4)
+    assert np.allclose(g["coords_sm100"][3, 1], [60.0, 5.0], atol=1e-4)
+    assert np.isnan(g["coords_relu"][3, 3]).all() and np.isfinite(g["coords_sm100"]).all()
