@@ -233,6 +233,32 @@ def cpu_baseline_eval(workload, budget_s=8.0):
             "sample": "%d units (steps of %d) through oracle/metrics_ref.py (numpy), %.1f s" % (done, n, dt)}
 
 
+def cpu_baseline_preprocess(budget_s=8.0):
+    """PIL + torchvision exactly as the reference's datasets call them (kind "reference") when importable, else the
+    oracle's numpy restatement; one host core, 4 views per frame."""
+    from egorear_b200 import synth
+    imgs = synth.synth_images(4, 872, 872, seed=0)
+    try:
+        from PIL import Image
+        from torchvision import transforms
+        tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+        pil = [Image.fromarray(i) for i in imgs]
+        fn = lambda: [tf(p.convert("RGB").resize([256, 256], Image.BICUBIC)).float().numpy() for p in pil]
+        kind, how = "reference", "PIL %s resize + torchvision ToTensor/Normalize" % __import__("PIL").__version__
+    except ImportError:
+        from oracle import preprocess_ref as pr
+        fn = lambda: [pr.preprocess(i)[0] for i in imgs]
+        kind, how = "port", "oracle/preprocess_ref.py (numpy)"
+    fn()
+    done, t0 = 0, time.time()
+    while time.time() - t0 < budget_s and done < 256:
+        fn()
+        done += 1
+    dt = time.time() - t0
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d frames x 4 views of 872x872 (decoded, in memory), %s, %.1f s" % (done, how, dt)}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
@@ -269,6 +295,7 @@ def workload_name(args):
             "decode": "get_max_preds, 4 views x 15 joints, %d frames/step/GPU" % args.batch,
             "eval_heatmap": "eval-time heatmap metrics (wrapper `evaluate`: L1, positive L1, MSE, arg-max MSE), 4 views x 15 joints, "
                             "%d frames/step/GPU" % args.batch,
+            "preprocess": "dataset preprocessing: PIL bicubic 872x872 -> 256x256 + ToTensor + Normalize, 4 views, %d frames/step/GPU" % args.batch,
             "eval_pose": "eval-time pose metrics (wrapper `evaluate_pose`: MPJPE, PA-MPJPE, PCK, AUC), 16 joints, "
                          "%d poses/step/GPU" % args.batch,
             "rw_e2e": "ego4view_rw_heatmap_mvfex-n1_jqa + ego4view_rw_pose3d from images (PyTorch bf16-autocast backbone + hot path), "
@@ -301,7 +328,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode", "rw_e2e", "eval_heatmap", "eval_pose"])
+    ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode", "rw_e2e", "eval_heatmap", "eval_pose", "preprocess"])
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--lanes", type=int, default=3, help="streams alternated by the throughput loop (1 = one stream)")
@@ -310,7 +337,7 @@ def main():
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {"mvfex_pose3d": 64, "mvfex": 64, "pose3d": 1024, "generate_target": 8192, "decode": 8192,
-                      "rw_e2e": 512, "eval_heatmap": 2048, "eval_pose": 1 << 20}[args.workload]
+                      "rw_e2e": 512, "eval_heatmap": 2048, "eval_pose": 1 << 20, "preprocess": 256}[args.workload]
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -438,6 +465,20 @@ def main():
             for _ in range(n):
                 m = metrics.evaluate(pred, gt_h.to(dev, non_blocking=True), "b")
                 yield torch.stack([m["b_l1_error_heatmap"], m["b_pos_l1_error_heatmap"]])
+    elif args.workload == "preprocess":
+        base = torch.from_numpy(synth.synth_images(8, 872, 872, seed=rank))
+        img_h = base.repeat((B * 4 + 7) // 8, 1, 1, 1)[: B * 4].view(B, 4, 872, 872, 3).contiguous().pin_memory()
+        img_d = img_h.to(dev)
+        in_bytes = img_h.numel()
+        l2_note = "decoded frames %.1f GB + output %.1f GB >> L2" % (in_bytes / 1e9, B * 4 * 3 * 256 * 256 * 4 / 1e9)
+
+        def step(im=img_d):
+            return ops.preprocess_images(im)
+        e2e_api = "ops.preprocess_images on decoded uint8 frames uploaded from pinned host memory, checksum read-back"
+
+        def e2e_fn(n):
+            for _ in range(n):
+                yield step(img_h.to(dev, non_blocking=True))[:, :, :, 0, 0].sum().cpu().view(1)
     elif args.workload == "eval_pose":
         from egorear_b200 import metrics
         pr, gp = synth.synth_eval_poses(B, 16, seed=rank)
@@ -577,6 +618,13 @@ def main():
                     "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "share_of_step": 1.0,
                     "ms_per_launch": t_s * 1e3}
 
+    elif rank == 0 and args.workload == "preprocess":
+        t_s = ms / 1e3 / args.steps
+        per_frame = 4 * (872 * 872 * 3 + 3 * 256 * 256 * 4)        # decoded frame read once + normalised tensor written once
+        ach = per_frame * B / t_s / 1e9
+        roofline = {"kernel": "preprocess_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm"], "traffic": None, "peak_source": peaks["src"], "share_of_step": 1.0,
+                    "ms_per_launch": t_s * 1e3}
     elif rank == 0 and args.workload in ("eval_heatmap", "eval_pose"):
         t_s = ms / 1e3 / args.steps
         # algorithmic bytes: both maps of every (frame, view, joint) once + 16 B of partials | both poses + 4 doubles
@@ -592,6 +640,8 @@ def main():
     cpu = None
     if world == 1 and not args.no_cpu_baseline and args.workload in ("eval_heatmap", "eval_pose"):
         cpu = cpu_baseline_eval(args.workload)
+    if world == 1 and not args.no_cpu_baseline and args.workload == "preprocess":
+        cpu = cpu_baseline_preprocess()
     if world == 1 and not args.no_cpu_baseline and args.workload == "mvfex_pose3d":
         cpu = cpu_baseline()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

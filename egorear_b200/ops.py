@@ -87,6 +87,42 @@ def integrate_tensor_2d(heatmaps, softmax=True, multiplier=100.0):
 
 
 # ------------------------------------------------------------------------------------------------
+# I1  dataset preprocessing
+# ------------------------------------------------------------------------------------------------
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def preprocess_images(images, size=(256, 256), mean=IMAGENET_MEAN, std=IMAGENET_STD, return_resized=False):
+    """What every reference dataset does per view (e.g. datasets/ego4view_rw/ego4view_rw_heatmap_mvf.py:40-41,96-99):
+    `Normalize(mean, std)(ToTensor()(img.resize(size, Image.BICUBIC)))`, batched and bit-exact with PIL + torchvision.
+
+    images: uint8 CUDA tensor [..., H, W, 3] of decoded RGB images (any leading dims, e.g. [B, V]).
+    -> float32 [..., 3, size[1], size[0]]; with return_resized also the resized uint8 images [..., size[1], size[0], 3].
+    `size` is (width, height) like PIL's."""
+    _need_cuda(images, "preprocess_images")
+    if images.dtype != torch.uint8 or images.ndim < 3 or images.shape[-1] != 3:
+        raise RuntimeError("egorear_b200.preprocess_images: expected uint8 [..., H, W, 3]")
+    lead = tuple(images.shape[:-3])
+    Hin, Win = int(images.shape[-3]), int(images.shape[-2])
+    Wout, Hout = int(size[0]), int(size[1])
+    img = images.detach().contiguous().view(-1, Hin, Win, 3)
+    N = img.shape[0]
+    out = torch.empty((N, 3, Hout, Wout), dtype=torch.float32, device=img.device)
+    res = torch.empty((N, Hout, Wout, 3), dtype=torch.uint8, device=img.device) if return_resized else None
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std])
+    lib = _lib.load()
+    for i in range(0, max(N, 1), 65535):
+        n = min(65535, N - i)
+        _lib.check(lib.egr_preprocess_images(_ptr(img[i:]) if n > 0 else None, n, Hin, Win, Hout, Wout, m, s,
+                                             _ptr(out[i:]) if n > 0 else None, _ptr(res[i:]) if res is not None and n > 0 else None,
+                                             _stream()))
+    out = out.view(lead + (3, Hout, Wout))
+    return (out, res.view(lead + (Hout, Wout, 3))) if return_resized else out
+
+
+# ------------------------------------------------------------------------------------------------
 # G1
 # ------------------------------------------------------------------------------------------------
 def _numpy_patch(sigma):

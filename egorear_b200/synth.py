@@ -183,3 +183,26 @@ def synth_eval_heatmaps(B, V=2, C=15, hs=64, seed=0):
         pred[i] = (0.8 * np.exp(-((xx - sx[i]) ** 2 + (yy - sy[i]) ** 2) / 2.0)).astype(np.float32)
     pred += rng.normal(0.0, 0.02, pred.shape).astype(np.float32)
     return pred.reshape(B, V, C, hs, hs), gt.reshape(B, V, C, hs, hs)
+
+
+def synth_images(N, H=872, W=872, seed=0):
+    """uint8 [N,H,W,3] stand-ins for decoded camera frames: smooth gradients + texture noise + saturated / black blocks
+    and one-pixel lines (the negative lobes of the bicubic kernel over- and undershoot there, exercising the 8-bit
+    clipping of both resampling passes)."""
+    rng = np.random.default_rng(6000 + seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, H), np.linspace(0, 1, W), indexing="ij")
+    out = np.empty((N, H, W, 3), np.uint8)
+    for n in range(N):
+        ph = rng.uniform(0, 6.28, 3)
+        fr = rng.uniform(2, 9, 3)
+        img = np.stack([127.5 + 127.5 * np.sin(fr[c] * (xx * (c + 1) + yy * (3 - c)) + ph[c]) for c in range(3)], -1)
+        img += rng.normal(0, 25, (H, W, 3))
+        img = np.clip(img, 0, 255)
+        for _ in range(6):
+            y0, x0 = rng.integers(0, max(H - 8, 1)), rng.integers(0, max(W - 8, 1))
+            h, w = rng.integers(2, max(H // 6, 3)), rng.integers(2, max(W // 6, 3))
+            img[y0:y0 + h, x0:x0 + w] = rng.choice([0.0, 255.0], 3)
+        img[rng.integers(0, H)] = 255.0
+        img[:, rng.integers(0, W)] = 0.0
+        out[n] = img.astype(np.uint8)
+    return out

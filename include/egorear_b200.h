@@ -283,6 +283,24 @@ int egr_eval_heatmap(const float* pred, int64_t pred_batch_stride, const float* 
 int egr_eval_pose(const float* pred, const float* gt, int64_t B, int J, float unit_scale, float pck_threshold,
                   const float* auc_thresholds, int n_auc, double* metrics, double* s1_hat, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * I1  image preprocessing
+ *     replaces, per image, `transform(Image.open(p).convert("RGB").resize([256, 256], Image.BICUBIC))` with
+ *     transform = Compose([ToTensor(), Normalize(mean, std)])
+ *     (pose_estimation/datasets/ego4view_rw/ego4view_rw_heatmap_mvf.py:40-41,96-99 and the five sibling datasets);
+ *     bit-exact with Pillow's 8-bit two-pass antialiased bicubic resampler + torchvision's float32 ops.
+ *   images     [N, Hin, Win, 3] uint8 decoded RGB (device), N <= 65535
+ *   out        [N, 3, Hout, Wout] float32 = ((resized / 255) - mean) / std
+ *   resized_u8 [N, Hout, Wout, 3] uint8 = the resized image itself, or NULL
+ *   mean3_host, std3_host: HOST pointers to 3 floats each.
+ * ------------------------------------------------------------------------------------------- */
+/* host-only helper (no device): Pillow's bicubic coefficient table for in_size -> out_size as the kernel uses it.
+ * *ksize = taps per output; bounds [out_size][2] = (first input index, tap count); kk [out_size][ksize] 22-bit fixed
+ * point.  bounds / kk may be NULL (query ksize first). */
+int egr_resample_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk);
+int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, int Win, int Hout, int Wout, const float* mean3_host,
+                          const float* std3_host, float* out, uint8_t* resized_u8, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics", "integrate_tensor_2d")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics", "integrate_tensor_2d", "preprocess")}
 
 
 def soft_inputs():
@@ -32,6 +32,7 @@ def soft_inputs():
     return hm
 
 
+PREPROCESS_CASES = ((872, 872, 256, 256), (480, 640, 256, 256), (100, 75, 256, 256), (256, 256, 256, 256), (301, 257, 64, 96))
 INTEGRATE_CASES = (("sm100", True, 100.0), ("sm1", True, 1.0), ("relu", False, 100.0))
 INTEGRATE_MAPS = ((0, 0), (1, 5), (2, 7), (3, 1), (3, 2), (3, 3))
 

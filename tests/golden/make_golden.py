@@ -169,6 +169,30 @@ def golden_integrate():
     print("integrate_tensor_2d:", {k: v.shape for k, v in out.items()})
 
 
+PREPROCESS_CASES = ((872, 872, 256, 256), (480, 640, 256, 256), (100, 75, 256, 256), (256, 256, 256, 256), (301, 257, 64, 96))
+
+
+def golden_preprocess():
+    """datasets/*: transform(Image.open(p).convert("RGB").resize([256, 256], Image.BICUBIC)) with the real PIL +
+    torchvision; inputs are regenerated from the seed by the tests, outputs are stored as a crop + a SHA-256 of the whole."""
+    import hashlib
+    from PIL import Image
+    from torchvision import transforms
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))])
+    out = {}
+    for i, (H, W, oh, ow) in enumerate(PREPROCESS_CASES):
+        img = synth.synth_images(1, H, W, seed=i)[0]
+        pil = Image.fromarray(img).convert("RGB").resize([ow, oh], Image.BICUBIC)
+        u8 = np.asarray(pil)
+        f = tf(pil).float().numpy()
+        out["u8_crop_%d" % i] = u8[: 48, : 48].copy()
+        out["f32_crop_%d" % i] = f[:, : 48, : 48].copy()
+        out["u8_sha_%d" % i] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(u8).tobytes()).digest(), np.uint8)
+        out["f32_sha_%d" % i] = np.frombuffer(hashlib.sha256(np.ascontiguousarray(f).tobytes()).digest(), np.uint8)
+    np.savez_compressed(os.path.join(HERE, "preprocess.npz"), **out)
+    print("preprocess:", {k: v.shape for k, v in out.items() if "crop" in k})
+
+
 def golden_eval_metrics(w):
     """eval-time metrics: the wrappers' own methods, called unbound on a stand-in `self` that
     carries exactly the attributes they read (criteria, cm2mm, num_heatmap, get_anchors_2d_from_hm)."""
@@ -203,10 +227,14 @@ if __name__ == "__main__":
     if "--integrate-only" in sys.argv:
         golden_integrate()
         sys.exit(0)
+    if "--preprocess-only" in sys.argv:
+        golden_preprocess()
+        sys.exit(0)
     fns = ref_import.import_functions()
     golden_generate_target(fns["generate_target"])
     golden_decode(fns["get_max_preds"])
     golden_soft(fns["get_max_preds_soft_pytorch"])
     golden_eval_metrics(ref_import.import_wrappers())
     golden_integrate()
+    golden_preprocess()
     golden_models(ref_import.import_estimators(), fns["generate_target"])

@@ -74,3 +74,19 @@ def test_oracle_not_imported_by_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_resample_coefficient_table_matches_oracle(lib):
+    """host logic of the preprocessing path (no device): the C++ restatement of Pillow's precompute_coeffs equals the
+    oracle's (which tests/test_oracle.py pins to PIL itself), for down-, up- and identity scaling"""
+    import ctypes
+    import numpy as np
+    from oracle import preprocess_ref as pr
+    for n_in, n_out in ((872, 256), (640, 256), (480, 256), (75, 256), (256, 256), (301, 64), (1000, 96), (7, 3), (3, 7)):
+        ks = ctypes.c_int(0)
+        assert lib.egr_resample_coeffs(n_in, n_out, ctypes.byref(ks), None, None) == 0
+        bounds = np.zeros((n_out, 2), np.int32)
+        kk = np.zeros((n_out, ks.value), np.int32)
+        assert lib.egr_resample_coeffs(n_in, n_out, ctypes.byref(ks), bounds.ctypes.data, kk.ctypes.data) == 0
+        rb, rk, rks = pr.precompute_coeffs(n_in, n_out)
+        assert ks.value == rks and np.array_equal(bounds, rb) and np.array_equal(kk, rk), (n_in, n_out)

@@ -117,3 +117,33 @@ def test_integrate_tensor_2d_oracle_matches_golden(golden):
     assert np.allclose(g["coords_sm1"][3, 0], [31.5, 31.5], atol=1e-4)
     assert np.allclose(g["coords_sm100"][3, 1], [60.0, 5.0], atol=1e-4)
     assert np.isnan(g["coords_relu"][3, 3]).all() and np.isfinite(g["coords_sm100"]).all()
+
+
+def test_preprocess_oracle_matches_golden(golden):
+    """oracle restatement of Pillow's bicubic resize + ToTensor + Normalize, bit-for-bit against PIL + torchvision vectors"""
+    import hashlib
+    from conftest import PREPROCESS_CASES
+    from egorear_b200 import synth
+    from oracle import preprocess_ref as pr
+    g = golden["preprocess"]
+    for i, (H, W, oh, ow) in enumerate(PREPROCESS_CASES):
+        img = synth.synth_images(1, H, W, seed=i)[0]
+        f, u8 = pr.preprocess(img, oh, ow)
+        assert u8.shape == (oh, ow, 3) and f.shape == (3, oh, ow) and f.dtype == np.float32
+        assert np.array_equal(u8[:48, :48], g["u8_crop_%d" % i])
+        assert np.array_equal(f[:, :48, :48].view(np.uint32), g["f32_crop_%d" % i].view(np.uint32))
+        assert hashlib.sha256(np.ascontiguousarray(u8).tobytes()).digest() == g["u8_sha_%d" % i].tobytes()
+        assert hashlib.sha256(np.ascontiguousarray(f).tobytes()).digest() == g["f32_sha_%d" % i].tobytes()
+    # the inputs exercise both clips of the 8-bit passes
+    u8 = pr.resize_bicubic_u8(synth.synth_images(1, 872, 872, seed=0)[0], 256, 256)
+    assert (u8 == 0).any() and (u8 == 255).any()
+    # identity size: Pillow skips the pass, the coefficient table reduces to the centre tap
+    img = synth.synth_images(1, 64, 48, seed=9)[0]
+    assert np.array_equal(pr.resize_bicubic_u8(img, 64, 48), img)
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    img = synth.synth_images(1, 333, 517, seed=11)[0]
+    want = np.asarray(Image.fromarray(img).resize([200, 120], Image.BICUBIC))
+    assert np.array_equal(pr.resize_bicubic_u8(img, 120, 200), want)
