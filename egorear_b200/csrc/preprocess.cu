@@ -21,7 +21,7 @@ namespace egr {
 namespace {
 
 constexpr int PP_PRECISION_BITS = 32 - 8 - 2;
-constexpr int PP_THREADS = 512;
+constexpr int PP_THREADS = 1024;
 
 double bicubic_filter(double x) {
     const double a = -0.5;
@@ -97,87 +97,157 @@ int get_table(int in_size, int out_size, const ResampleTable** out) {
 }
 
 __device__ __forceinline__ int clip8(int v) { return min(max(v >> PP_PRECISION_BITS, 0), 255); }
+// byte `i` (0..3, compile-time) of a word, zero-extended: one PRMT
+template <int I> __device__ __forceinline__ int byte_of(uint32_t w) { return (int)__byte_perm(w, 0u, 0x4440u + I); }
 
 struct PpParams {
     const uint8_t* img;           // [N][Hin][Win][3]
+    const uint8_t* img_end;       // one past the last byte of the whole input (aligned loads never cross it)
     float* out;                   // [N][3][Hout][Wout]
     uint8_t* out_u8;              // [N][Hout][Wout][3] or null
     const int* bx; const int* kx; const int* by; const int* ky;
     int Hin, Win, Hout, Wout, ksx, ksy, band, rows_max;
+    int siw, stw, wpo;            // word strides of the staged / intermediate rows (odd: conflict-free), words per output row
     float mean[3], stdv[3];
 };
 
+// aligned 32-bit load that never touches memory at or beyond `end` (only the very last word of the buffer is assembled
+// from byte loads)
+__device__ __forceinline__ uint32_t load_word_guarded(const uint32_t* p, const uint8_t* end) {
+    const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
+    if (b + 4 <= end) return __ldg(p);
+    uint32_t v = 0;
+    for (int i = 0; i < 4; ++i)
+        if (b + i < end) v |= (uint32_t)b[i] << (8 * i);
+    return v;
+}
+
+// Shared memory: LUT[3][256] fp32 | staged input rows (row r at word r*siw, byte 0 of the row on a word boundary) |
+// 8-bit intermediate rows (word stride stw) | 8-bit output rows of the band.
+// Horizontal pass: lane <-> input row, the warp walks the output columns, so bounds and coefficients are warp-uniform
+// and the lanes' word loads / byte stores hit 32 different banks (odd row strides).  Vertical pass: lane <-> 4
+// consecutive bytes of an intermediate row.  Last pass: one shared-memory LUT lookup per value ((u/255 - mean)/std has
+// only 3 x 256 possible results, computed once per CTA with the IEEE ops of the separate torch kernels).
 __global__ void __launch_bounds__(PP_THREADS)
 preprocess_kernel(const PpParams p) {
     extern __shared__ __align__(16) uint8_t pp_smem[];
     pdl_trigger();
     pdl_wait();
+    constexpr int NW = PP_THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = blockIdx.y;
     const int yy0 = blockIdx.x * p.band, yy1 = min(yy0 + p.band, p.Hout);
+    const int nb = yy1 - yy0;
     const int r0 = p.by[yy0 * 2];
     const int r1 = p.by[(yy1 - 1) * 2] + p.by[(yy1 - 1) * 2 + 1];      // bounds are monotonic in yy
     const int nrows = r1 - r0;
     const int row_bytes = p.Win * 3;
-    // ---- stage the contiguous byte range of input rows [r0, r1) with the same 16-byte phase as in global memory ----
-    const uint8_t* g0 = p.img + ((int64_t)n * p.Hin + r0) * row_bytes;
-    const int phase = (int)((uintptr_t)g0 & 15);
-    uint8_t* s_in = pp_smem + phase;
-    uint8_t* s_tmp = pp_smem + (((size_t)p.rows_max * row_bytes + 32 + 15) & ~(size_t)15);
-    const int total = nrows * row_bytes;
-    const int head = min((16 - phase) & 15, total);
-    const int n16 = (total - head) >> 4;
-    const int tail0 = head + (n16 << 4);
-    if ((int)threadIdx.x < head) s_in[threadIdx.x] = g0[threadIdx.x];
-    {
-        const uint4* gs = reinterpret_cast<const uint4*>(g0 + head);
-        uint4* ss = reinterpret_cast<uint4*>(s_in + head);
-        int i = threadIdx.x;
-        for (; i + 3 * PP_THREADS < n16; i += 4 * PP_THREADS) {          // 4 independent 128-bit loads per thread
-            const uint4 a = __ldg(gs + i), b = __ldg(gs + i + PP_THREADS), c = __ldg(gs + i + 2 * PP_THREADS),
-                        d = __ldg(gs + i + 3 * PP_THREADS);
-            ss[i] = a; ss[i + PP_THREADS] = b; ss[i + 2 * PP_THREADS] = c; ss[i + 3 * PP_THREADS] = d;
-        }
-        for (; i < n16; i += PP_THREADS) ss[i] = __ldg(gs + i);
-    }
-    if ((int)threadIdx.x < total - tail0) s_in[tail0 + threadIdx.x] = g0[tail0 + threadIdx.x];
-    __syncthreads();
-    // ---- horizontal pass: s_in rows -> s_tmp [nrows][Wout][3] (8-bit, like Pillow's intermediate image) ----
-    const int half = 1 << (PP_PRECISION_BITS - 1);
-    for (int idx = threadIdx.x; idx < nrows * p.Wout; idx += PP_THREADS) {
-        const int r = idx / p.Wout, xx = idx - r * p.Wout;
-        const int x0 = __ldg(p.bx + xx * 2), cnt = __ldg(p.bx + xx * 2 + 1);
-        const int* k = p.kx + xx * p.ksx;
-        const uint8_t* src = s_in + (r * p.Win + x0) * 3;
-        int a0 = half, a1 = half, a2 = half;
-        for (int t = 0; t < cnt; ++t) {
-            const int c = __ldg(k + t);
-            a0 += (int)src[t * 3 + 0] * c;
-            a1 += (int)src[t * 3 + 1] * c;
-            a2 += (int)src[t * 3 + 2] * c;
-        }
-        uint8_t* d = s_tmp + idx * 3;
-        d[0] = (uint8_t)clip8(a0); d[1] = (uint8_t)clip8(a1); d[2] = (uint8_t)clip8(a2);
-    }
-    __syncthreads();
-    // ---- vertical pass + ToTensor + Normalize: out[n][c][yy][xx], xx fastest ----
-    const int nb = yy1 - yy0;
-    for (int idx = threadIdx.x; idx < 3 * nb * p.Wout; idx += PP_THREADS) {
-        const int c = idx / (nb * p.Wout);
-        const int rem = idx - c * nb * p.Wout;
-        const int yl = rem / p.Wout, xx = rem - yl * p.Wout;
-        const int yy = yy0 + yl;
-        const int y0 = __ldg(p.by + yy * 2), cnt = __ldg(p.by + yy * 2 + 1);
-        const int* k = p.ky + yy * p.ksy;
-        const uint8_t* src = s_tmp + ((y0 - r0) * p.Wout + xx) * 3 + c;
-        int a = half;
-        for (int t = 0; t < cnt; ++t) a += (int)src[t * p.Wout * 3] * __ldg(k + t);
-        const int u = clip8(a);
-        if (p.out_u8) p.out_u8[(((int64_t)n * p.Hout + yy) * p.Wout + xx) * 3 + c] = (uint8_t)u;
+    float* lut = reinterpret_cast<float*>(pp_smem);
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(pp_smem + 3072);
+    uint32_t* s_tmp = s_in + (size_t)p.rows_max * p.siw + 4;
+    uint32_t* s_out = s_tmp + (size_t)p.rows_max * p.stw;
+
+    for (int i = threadIdx.x; i < 768; i += PP_THREADS) {
+        const int c = i >> 8;
         const float mean = (c == 0) ? p.mean[0] : (c == 1) ? p.mean[1] : p.mean[2];
         const float stdv = (c == 0) ? p.stdv[0] : (c == 1) ? p.stdv[1] : p.stdv[2];
         // ToTensor: u / 255 in float32; Normalize: (x - mean) / std, each op rounded like the separate torch kernels
-        const float x = __fdiv_rn((float)u, 255.0f);
-        __stcs(p.out + (((int64_t)n * 3 + c) * p.Hout + yy) * p.Wout + xx, __fdiv_rn(__fsub_rn(x, mean), stdv));
+        lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean), stdv);
+    }
+    // ---- stage input rows [r0, r1): warp <-> row, lanes <-> words; re-aligned with a funnel shift when the row does
+    //      not start on a word boundary in global memory ----
+    const int wpr = (row_bytes + 3) >> 2;
+    for (int r = warp; r < nrows; r += NW) {
+        const uint8_t* gr = p.img + ((int64_t)n * p.Hin + r0 + r) * row_bytes;
+        const int ph = (int)((uintptr_t)gr & 3);
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(gr - ph);
+        uint32_t* dst = s_in + (size_t)r * p.siw;
+        // words [0, nsafe) of this row lie entirely inside the input buffer (all of them except at the buffer's last word)
+        const int nsafe = (int)min((int64_t)wpr + 1, (int64_t)(p.img_end - reinterpret_cast<const uint8_t*>(gw)) >> 2);
+        if (ph == 0) {
+            const int nfast = min(wpr, nsafe);
+#pragma unroll 4
+            for (int j = lane; j < nfast; j += 32) dst[j] = __ldg(gw + j);
+            for (int j = nfast + lane; j < wpr; j += 32) dst[j] = load_word_guarded(gw + j, p.img_end);
+        } else {
+            const int nfast = min(wpr, nsafe - 1);               // needs word j + 1 as well
+#pragma unroll 4
+            for (int j = lane; j < nfast; j += 32) dst[j] = __funnelshift_r(__ldg(gw + j), __ldg(gw + j + 1), 8 * ph);
+            for (int j = max(nfast, 0) + lane; j < wpr; j += 32) {
+                const uint32_t lo = load_word_guarded(gw + j, p.img_end);
+                const uint32_t hi = (4 * j + 4 - ph < row_bytes) ? load_word_guarded(gw + j + 1, p.img_end) : 0u;
+                dst[j] = __funnelshift_r(lo, hi, 8 * ph);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- horizontal pass -> 8-bit intermediate rows (like Pillow's intermediate image) ----
+    const int half = 1 << (PP_PRECISION_BITS - 1);
+    const int n_rg = (nrows + 31) >> 5;
+    uint8_t* s_tmp8 = reinterpret_cast<uint8_t*>(s_tmp);
+    for (int it = warp; it < n_rg * p.Wout; it += NW) {
+        const int rg = it / p.Wout, xx = it - rg * p.Wout;
+        const int r = rg * 32 + lane;
+        const int x0 = __ldg(p.bx + xx * 2), cnt = __ldg(p.bx + xx * 2 + 1);
+        const int* k = p.kx + xx * p.ksx;
+        const int b0 = x0 * 3;
+        const int sh = (b0 & 3) * 8;
+        const uint32_t* row = s_in + (size_t)min(r, nrows - 1) * p.siw + (b0 >> 2);
+        int a0 = half, a1 = half, a2 = half;
+        uint32_t w0 = row[0];
+        for (int t0 = 0; t0 < cnt; t0 += 4) {            // 4 taps = 12 bytes = 3 re-aligned words per step
+            const uint32_t w1 = row[1], w2 = row[2], w3 = row[3];
+            row += 3;
+            const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+            w0 = w3;
+            const int k0 = __ldg(k + t0);
+            const int k1 = (t0 + 1 < cnt) ? __ldg(k + t0 + 1) : 0;
+            const int k2 = (t0 + 2 < cnt) ? __ldg(k + t0 + 2) : 0;
+            const int k3 = (t0 + 3 < cnt) ? __ldg(k + t0 + 3) : 0;
+            a0 += byte_of<0>(v0) * k0 + byte_of<3>(v0) * k1 + byte_of<2>(v1) * k2 + byte_of<1>(v2) * k3;
+            a1 += byte_of<1>(v0) * k0 + byte_of<0>(v1) * k1 + byte_of<3>(v1) * k2 + byte_of<2>(v2) * k3;
+            a2 += byte_of<2>(v0) * k0 + byte_of<1>(v1) * k1 + byte_of<0>(v2) * k2 + byte_of<3>(v2) * k3;
+        }
+        if (r < nrows) {
+            uint8_t* d = s_tmp8 + (size_t)r * p.stw * 4 + xx * 3;
+            d[0] = (uint8_t)clip8(a0); d[1] = (uint8_t)clip8(a1); d[2] = (uint8_t)clip8(a2);
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass -> 8-bit output rows of the band: warp <-> (row, 32-word chunk), lane <-> 4 bytes ----
+    const int nj = (p.wpo + 31) >> 5;
+    for (int it = warp; it < nb * nj; it += NW) {
+        const int yl = it / nj, j = (it - yl * nj) * 32 + lane;
+        const int yy = yy0 + yl;
+        const int y0 = __ldg(p.by + yy * 2), cnt = __ldg(p.by + yy * 2 + 1);
+        const int* k = p.ky + yy * p.ksy;
+        if (j < p.wpo) {
+            const uint32_t* src = s_tmp + (size_t)(y0 - r0) * p.stw + j;
+            int a0 = half, a1 = half, a2 = half, a3 = half;
+            for (int t = 0; t < cnt; ++t) {
+                const uint32_t w = src[(size_t)t * p.stw];
+                const int c = __ldg(k + t);
+                a0 += byte_of<0>(w) * c; a1 += byte_of<1>(w) * c; a2 += byte_of<2>(w) * c; a3 += byte_of<3>(w) * c;
+            }
+            s_out[yl * p.wpo + j] = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
+        }
+    }
+    __syncthreads();
+    // ---- ToTensor + Normalize through the LUT: out[n][c][yy][xx], one coalesced row per warp iteration ----
+    const uint8_t* s_out8 = reinterpret_cast<const uint8_t*>(s_out);
+    for (int row = warp; row < 3 * nb; row += NW) {
+        const int c = row / nb, yl = row - c * nb;
+        const uint8_t* src = s_out8 + (size_t)yl * p.wpo * 4 + c;
+        float* dst = p.out + (((int64_t)n * 3 + c) * p.Hout + yy0 + yl) * p.Wout;
+        const float* l = lut + c * 256;
+        for (int xx = lane; xx < p.Wout; xx += 32) __stcs(dst + xx, l[src[xx * 3]]);
+    }
+    if (p.out_u8) {
+        for (int yl = warp; yl < nb; yl += NW) {
+            uint8_t* dst = p.out_u8 + ((int64_t)n * p.Hout + yy0 + yl) * p.Wout * 3;
+            const uint8_t* src = s_out8 + (size_t)yl * p.wpo * 4;
+            for (int i = lane; i < p.Wout * 3; i += 32) dst[i] = src[i];
+        }
     }
 }
 
@@ -209,8 +279,12 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
     const ResampleTable *tx = nullptr, *ty = nullptr;
     if (int rc = get_table(Win, Wout, &tx)) return rc;
     if (int rc = get_table(Hin, Hout, &ty)) return rc;
-    // largest band of output rows whose input rows + intermediate rows fit in shared memory
+    EGR_CHECK(((uintptr_t)images & 3) == 0, EGR_ERR_INVALID, "preprocess: images must be 4-byte aligned");
+    // row strides in words, odd so that 32 lanes on 32 consecutive rows hit 32 different banks
     const int row_bytes = Win * 3;
+    const int siw = (((row_bytes + 3) >> 2) + 4) | 1;          // + slack: the tap loop reads up to 4 words past the last tap
+    const int wpo = (Wout * 3 + 3) >> 2;
+    const int stw = wpo | 1;
     auto rows_for = [&](int band) {
         int mx = 0;
         for (int y0 = 0; y0 < Hout; y0 += band) {
@@ -219,20 +293,26 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
         }
         return mx;
     };
-    auto smem_for = [&](int rows) { return (((size_t)rows * row_bytes + 32 + 15) & ~(size_t)15) + (size_t)rows * Wout * 3 + 16; };
+    auto smem_for = [&](int band, int rows) {
+        return (size_t)3072 + ((size_t)rows * siw + 4 + (size_t)rows * stw + (size_t)band * wpo) * 4 + 16;
+    };
+    // band of output rows per CTA: most output rows per 32-row pass of the horizontal stage among those that fit
     int band = 0, rows = 0;
-    for (int b : {16, 8, 4, 2, 1}) {          // fewest re-staged halo rows: the largest band that fits
+    double best = 0.0;
+    for (int b = 1; b <= std::min(Hout, 64); ++b) {
         const int r = rows_for(b);
-        if (smem_for(r) <= (size_t)200 * 1024) { band = b; rows = r; break; }
+        if (smem_for(b, r) > (size_t)226 * 1024) continue;
+        const double score = (double)b / ((r + 31) / 32);
+        if (score > best * 1.0001) { best = score; band = b; rows = r; }
     }
     EGR_CHECK(band > 0, EGR_ERR_UNSUPPORTED, "preprocess: %dx%d -> %dx%d does not fit in shared memory", Hin, Win, Hout, Wout);
-    const size_t smem = smem_for(rows);
-    EGR_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const size_t smem = smem_for(band, rows);
+    EGR_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     PpParams p{};
-    p.img = images; p.out = out; p.out_u8 = resized_u8;
+    p.img = images; p.img_end = images + (size_t)N * Hin * row_bytes; p.out = out; p.out_u8 = resized_u8;
     p.bx = tx->d_bounds; p.kx = tx->d_kk; p.by = ty->d_bounds; p.ky = ty->d_kk;
     p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout; p.ksx = tx->ksize; p.ksy = ty->ksize;
-    p.band = band; p.rows_max = rows;
+    p.band = band; p.rows_max = rows; p.siw = siw; p.stw = stw; p.wpo = wpo;
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean3_host[c]; p.stdv[c] = std3_host[c]; }
     EGR_LAUNCH(preprocess_kernel, dim3((Hout + band - 1) / band, (unsigned)N), PP_THREADS, smem, (cudaStream_t)stream, p);
     return EGR_OK;
