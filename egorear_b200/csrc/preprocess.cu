@@ -6,10 +6,19 @@
 // fixed-point coefficients: the coefficient tables are computed on the host in double exactly as precompute_coeffs /
 // normalize_coeffs_8bpc do, the kernel does the integer MACs, the clip to 8 bits, and the float32 (x/255 - mean)/std.
 //
-// One CTA = one band of output rows of one image: the input rows the band needs are staged in shared memory with
-// 128-bit loads (they are one contiguous byte range), the horizontal pass writes the 8-bit intermediate rows to shared
-// memory, the vertical pass reads them and writes the normalised NCHW fp32 rows coalesced.  HBM traffic = the decoded
-// image once (neighbouring bands re-read their halo rows from L2) + the output once.
+// One CTA = one band of output rows of one image, everything between the decoded image and the normalised tensor
+// stays in shared memory:
+//   stage      the input rows the band needs, de-interleaved into R/G/B byte planes (PRMT), rows on odd word strides
+//   horizontal lane <-> input row, the warp walks the output columns (bounds and coefficients warp-uniform, the 32
+//              lanes hit 32 banks); 4 taps of a channel are 4 consecutive bytes = one word, so the MACs are dp4a:
+//              each 22-bit coefficient is split into three signed 8-bit digits (k = d0 + 2^8 d1 + 2^16 d2, packed 4
+//              taps per word on the host), three exact int32 partial sums, recombined with shifts -> 0.75 IDP per MAC
+//              instead of PRMT + IMAD per MAC.  The 8-bit result (Pillow's intermediate image) is written transposed,
+//              [channel][column][row], so that the vertical taps are consecutive bytes too
+//   vertical   lane <-> output column, same dp4a scheme, clip, then ToTensor + Normalize as ONE shared-memory LUT
+//              lookup ((u/255 - mean)/std has 3 x 256 possible results, computed once per CTA with the IEEE ops of the
+//              separate torch kernels) and a coalesced NCHW store
+// HBM traffic = the decoded image once (neighbouring bands re-read their halo rows from L2) + the output once.
 #include "common.cuh"
 #include <mutex>
 #include <map>
@@ -32,11 +41,12 @@ double bicubic_filter(double x) {
 }
 
 struct ResampleTable {
-    int ksize = 0;
+    int ksize = 0, ks4 = 0;       // taps per output, 4-tap steps per output
     std::vector<int> bounds;      // [out][2] = (first input index, tap count)
     std::vector<int> kk;          // [out][ksize], fixed point
+    std::vector<uint32_t> digits; // [out][ks4][4]: the three signed-byte digit words of taps 4s..4s+3 (+ 1 pad word)
     int* d_bounds = nullptr;
-    int* d_kk = nullptr;
+    uint4* d_digits = nullptr;
 };
 
 // Resample.c precompute_coeffs (box = the whole image) + normalize_coeffs_8bpc
@@ -72,6 +82,22 @@ void build_table(int in_size, int out_size, ResampleTable& t) {
         t.bounds[xx * 2 + 0] = xmin;
         t.bounds[xx * 2 + 1] = xmax;
     }
+    // balanced base-256 digits: k = d0 + 256 d1 + 65536 d2 with d0, d1 in [-128, 127]; |k| <= ~1.1 * 2^22 so d2 fits too
+    t.ks4 = (ksize + 3) / 4;
+    t.digits.assign((size_t)out_size * t.ks4 * 4, 0u);
+    for (int xx = 0; xx < out_size; xx++)
+        for (int x = 0; x < t.bounds[xx * 2 + 1]; x++) {
+            const int kv = t.kk[(size_t)xx * ksize + x];
+            const int d0 = ((kv + 128) & 255) - 128;
+            const int k1 = (kv - d0) >> 8;
+            const int d1 = ((k1 + 128) & 255) - 128;
+            const int d2 = (k1 - d1) >> 8;
+            uint32_t* w = &t.digits[((size_t)xx * t.ks4 + x / 4) * 4];
+            const int sh = 8 * (x & 3);
+            w[0] |= (uint32_t)(d0 & 255) << sh;
+            w[1] |= (uint32_t)(d1 & 255) << sh;
+            w[2] |= (uint32_t)(d2 & 255) << sh;
+        }
 }
 
 std::mutex g_tab_mu;
@@ -87,9 +113,9 @@ int get_table(int in_size, int out_size, const ResampleTable** out) {
         ResampleTable t;
         build_table(in_size, out_size, t);
         EGR_CUDA_OK(cudaMalloc(&t.d_bounds, t.bounds.size() * sizeof(int)));
-        EGR_CUDA_OK(cudaMalloc(&t.d_kk, t.kk.size() * sizeof(int)));
+        EGR_CUDA_OK(cudaMalloc(&t.d_digits, t.digits.size() * sizeof(uint32_t)));
         EGR_CUDA_OK(cudaMemcpy(t.d_bounds, t.bounds.data(), t.bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
-        EGR_CUDA_OK(cudaMemcpy(t.d_kk, t.kk.data(), t.kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+        EGR_CUDA_OK(cudaMemcpy(t.d_digits, t.digits.data(), t.digits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         it = g_tabs.emplace(key, std::move(t)).first;
     }
     *out = &it->second;
@@ -97,22 +123,28 @@ int get_table(int in_size, int out_size, const ResampleTable** out) {
 }
 
 __device__ __forceinline__ int clip8(int v) { return min(max(v >> PP_PRECISION_BITS, 0), 255); }
-// byte `i` (0..3, compile-time) of a word, zero-extended: one PRMT
-template <int I> __device__ __forceinline__ int byte_of(uint32_t w) { return (int)__byte_perm(w, 0u, 0x4440u + I); }
+// 4 unsigned bytes (pixels) x 4 signed bytes (coefficient digits) + c
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 struct PpParams {
     const uint8_t* img;           // [N][Hin][Win][3]
     const uint8_t* img_end;       // one past the last byte of the whole input (aligned loads never cross it)
     float* out;                   // [N][3][Hout][Wout]
     uint8_t* out_u8;              // [N][Hout][Wout][3] or null
-    const int* bx; const int* kx; const int* by; const int* ky;
-    int Hin, Win, Hout, Wout, ksx, ksy, band, rows_max;
-    int siw, stw, wpo;            // word strides of the staged / intermediate rows (odd: conflict-free), words per output row
+    const int* bx; const uint4* dx; const int* by; const uint4* dy;
+    int Hin, Win, Hout, Wout, ks4x, ks4y, band, rows_max;
+    int siw;                      // words per staged plane row (odd)
+    int rpw;                      // words per [channel][column] line of the transposed intermediate (odd)
+    int xtab_in_smem;
     float mean[3], stdv[3];
 };
 
-// aligned 32-bit load that never touches memory at or beyond `end` (only the very last word of the buffer is assembled
-// from byte loads)
+// aligned 32-bit load that never touches memory at or beyond `end` (only the last word of the buffer is assembled from
+// byte loads)
 __device__ __forceinline__ uint32_t load_word_guarded(const uint32_t* p, const uint8_t* end) {
     const uint8_t* b = reinterpret_cast<const uint8_t*>(p);
     if (b + 4 <= end) return __ldg(p);
@@ -122,12 +154,14 @@ __device__ __forceinline__ uint32_t load_word_guarded(const uint32_t* p, const u
     return v;
 }
 
-// Shared memory: LUT[3][256] fp32 | staged input rows (row r at word r*siw, byte 0 of the row on a word boundary) |
-// 8-bit intermediate rows (word stride stw) | 8-bit output rows of the band.
-// Horizontal pass: lane <-> input row, the warp walks the output columns, so bounds and coefficients are warp-uniform
-// and the lanes' word loads / byte stores hit 32 different banks (odd row strides).  Vertical pass: lane <-> 4
-// consecutive bytes of an intermediate row.  Last pass: one shared-memory LUT lookup per value ((u/255 - mean)/std has
-// only 3 x 256 possible results, computed once per CTA with the IEEE ops of the separate torch kernels).
+// word j of an input row that starts `ph` bytes after the aligned word gw[0]
+__device__ __forceinline__ uint32_t row_word(const uint32_t* gw, int j, int ph, int nsafe, const uint8_t* end) {
+    if (ph == 0) return (j < nsafe) ? __ldg(gw + j) : load_word_guarded(gw + j, end);
+    const uint32_t lo = (j < nsafe) ? __ldg(gw + j) : load_word_guarded(gw + j, end);
+    const uint32_t hi = (j + 1 < nsafe) ? __ldg(gw + j + 1) : load_word_guarded(gw + j + 1, end);
+    return __funnelshift_r(lo, hi, 8 * ph);
+}
+
 __global__ void __launch_bounds__(PP_THREADS)
 preprocess_kernel(const PpParams p) {
     extern __shared__ __align__(16) uint8_t pp_smem[];
@@ -142,10 +176,13 @@ preprocess_kernel(const PpParams p) {
     const int r1 = p.by[(yy1 - 1) * 2] + p.by[(yy1 - 1) * 2 + 1];      // bounds are monotonic in yy
     const int nrows = r1 - r0;
     const int row_bytes = p.Win * 3;
+    // shared memory: LUT | x digit table (optional) | R, G, B planes of the staged rows | transposed intermediate
     float* lut = reinterpret_cast<float*>(pp_smem);
-    uint32_t* s_in = reinterpret_cast<uint32_t*>(pp_smem + 3072);
-    uint32_t* s_tmp = s_in + (size_t)p.rows_max * p.siw + 4;
-    uint32_t* s_out = s_tmp + (size_t)p.rows_max * p.stw;
+    uint4* xtab = reinterpret_cast<uint4*>(pp_smem + 3072);
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(xtab + (p.xtab_in_smem ? p.Wout * p.ks4x : 0));
+    const int plane = p.rows_max * p.siw + 2;                            // words per plane (+ slack for the realign read)
+    uint32_t* s_tmp = s_in + 3 * (size_t)plane;
+    uint8_t* s_tmp8 = reinterpret_cast<uint8_t*>(s_tmp);
 
     for (int i = threadIdx.x; i < 768; i += PP_THREADS) {
         const int c = i >> 8;
@@ -154,99 +191,93 @@ preprocess_kernel(const PpParams p) {
         // ToTensor: u / 255 in float32; Normalize: (x - mean) / std, each op rounded like the separate torch kernels
         lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean), stdv);
     }
-    // ---- stage input rows [r0, r1): warp <-> row, lanes <-> words; re-aligned with a funnel shift when the row does
-    //      not start on a word boundary in global memory ----
-    const int wpr = (row_bytes + 3) >> 2;
+    if (p.xtab_in_smem)
+        for (int i = threadIdx.x; i < p.Wout * p.ks4x; i += PP_THREADS) xtab[i] = __ldg(p.dx + i);
+    const uint4* xt = p.xtab_in_smem ? xtab : p.dx;
+
+    // ---- stage rows [r0, r1): warp <-> row, lane <-> group of 4 pixels = 3 words -> one word per colour plane ----
+    const int ngrp = (p.Win + 3) >> 2;
     for (int r = warp; r < nrows; r += NW) {
         const uint8_t* gr = p.img + ((int64_t)n * p.Hin + r0 + r) * row_bytes;
         const int ph = (int)((uintptr_t)gr & 3);
         const uint32_t* gw = reinterpret_cast<const uint32_t*>(gr - ph);
-        uint32_t* dst = s_in + (size_t)r * p.siw;
-        // words [0, nsafe) of this row lie entirely inside the input buffer (all of them except at the buffer's last word)
-        const int nsafe = (int)min((int64_t)wpr + 1, (int64_t)(p.img_end - reinterpret_cast<const uint8_t*>(gw)) >> 2);
-        if (ph == 0) {
-            const int nfast = min(wpr, nsafe);
-#pragma unroll 4
-            for (int j = lane; j < nfast; j += 32) dst[j] = __ldg(gw + j);
-            for (int j = nfast + lane; j < wpr; j += 32) dst[j] = load_word_guarded(gw + j, p.img_end);
-        } else {
-            const int nfast = min(wpr, nsafe - 1);               // needs word j + 1 as well
-#pragma unroll 4
-            for (int j = lane; j < nfast; j += 32) dst[j] = __funnelshift_r(__ldg(gw + j), __ldg(gw + j + 1), 8 * ph);
-            for (int j = max(nfast, 0) + lane; j < wpr; j += 32) {
-                const uint32_t lo = load_word_guarded(gw + j, p.img_end);
-                const uint32_t hi = (4 * j + 4 - ph < row_bytes) ? load_word_guarded(gw + j + 1, p.img_end) : 0u;
-                dst[j] = __funnelshift_r(lo, hi, 8 * ph);
-            }
+        // words [0, nsafe) counted from gw lie entirely inside the input buffer
+        const int nsafe = (int)min((int64_t)1 << 30, (int64_t)(p.img_end - reinterpret_cast<const uint8_t*>(gw)) >> 2);
+        uint32_t* dR = s_in + (size_t)r * p.siw;
+        uint32_t* dG = dR + plane;
+        uint32_t* dB = dG + plane;
+#pragma unroll 2
+        for (int g = lane; g < ngrp; g += 32) {
+            const uint32_t w0 = row_word(gw, 3 * g, ph, nsafe, p.img_end);
+            const uint32_t w1 = row_word(gw, 3 * g + 1, ph, nsafe, p.img_end);
+            const uint32_t w2 = row_word(gw, 3 * g + 2, ph, nsafe, p.img_end);
+            // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+            dR[g] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+            dG[g] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+            dB[g] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
         }
     }
     __syncthreads();
-    // ---- horizontal pass -> 8-bit intermediate rows (like Pillow's intermediate image) ----
+
+    // ---- horizontal pass: (row, column) -> 3 bytes of the transposed intermediate ----
     const int half = 1 << (PP_PRECISION_BITS - 1);
     const int n_rg = (nrows + 31) >> 5;
-    uint8_t* s_tmp8 = reinterpret_cast<uint8_t*>(s_tmp);
+    const int line = p.rpw * 4;                                          // bytes per [channel][column] line
     for (int it = warp; it < n_rg * p.Wout; it += NW) {
         const int rg = it / p.Wout, xx = it - rg * p.Wout;
         const int r = rg * 32 + lane;
         const int x0 = __ldg(p.bx + xx * 2), cnt = __ldg(p.bx + xx * 2 + 1);
-        const int* k = p.kx + xx * p.ksx;
-        const int b0 = x0 * 3;
-        const int sh = (b0 & 3) * 8;
-        const uint32_t* row = s_in + (size_t)min(r, nrows - 1) * p.siw + (b0 >> 2);
-        int a0 = half, a1 = half, a2 = half;
-        uint32_t w0 = row[0];
-        for (int t0 = 0; t0 < cnt; t0 += 4) {            // 4 taps = 12 bytes = 3 re-aligned words per step
-            const uint32_t w1 = row[1], w2 = row[2], w3 = row[3];
-            row += 3;
-            const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
-            w0 = w3;
-            const int k0 = __ldg(k + t0);
-            const int k1 = (t0 + 1 < cnt) ? __ldg(k + t0 + 1) : 0;
-            const int k2 = (t0 + 2 < cnt) ? __ldg(k + t0 + 2) : 0;
-            const int k3 = (t0 + 3 < cnt) ? __ldg(k + t0 + 3) : 0;
-            a0 += byte_of<0>(v0) * k0 + byte_of<3>(v0) * k1 + byte_of<2>(v1) * k2 + byte_of<1>(v2) * k3;
-            a1 += byte_of<1>(v0) * k0 + byte_of<0>(v1) * k1 + byte_of<3>(v1) * k2 + byte_of<2>(v2) * k3;
-            a2 += byte_of<2>(v0) * k0 + byte_of<1>(v1) * k1 + byte_of<0>(v2) * k2 + byte_of<3>(v2) * k3;
+        const int steps = (cnt + 3) >> 2;
+        const int sh = (x0 & 3) * 8;
+        const uint32_t* rowR = s_in + (size_t)min(r, nrows - 1) * p.siw + (x0 >> 2);
+        const uint32_t* rowG = rowR + plane;
+        const uint32_t* rowB = rowG + plane;
+        const uint4* tab = xt + xx * p.ks4x;
+        int r0a = 0, r1a = 0, r2a = 0, g0a = 0, g1a = 0, g2a = 0, b0a = 0, b1a = 0, b2a = 0;
+        uint32_t pr = rowR[0], pg = rowG[0], pb = rowB[0];
+        for (int s = 0; s < steps; ++s) {
+            const uint4 d = tab[s];
+            const uint32_t nr = rowR[s + 1], ng = rowG[s + 1], nbw = rowB[s + 1];
+            const uint32_t vr = __funnelshift_r(pr, nr, sh), vg = __funnelshift_r(pg, ng, sh), vb = __funnelshift_r(pb, nbw, sh);
+            pr = nr; pg = ng; pb = nbw;
+            r0a = dp4a_us(vr, d.x, r0a); r1a = dp4a_us(vr, d.y, r1a); r2a = dp4a_us(vr, d.z, r2a);
+            g0a = dp4a_us(vg, d.x, g0a); g1a = dp4a_us(vg, d.y, g1a); g2a = dp4a_us(vg, d.z, g2a);
+            b0a = dp4a_us(vb, d.x, b0a); b1a = dp4a_us(vb, d.y, b1a); b2a = dp4a_us(vb, d.z, b2a);
         }
         if (r < nrows) {
-            uint8_t* d = s_tmp8 + (size_t)r * p.stw * 4 + xx * 3;
-            d[0] = (uint8_t)clip8(a0); d[1] = (uint8_t)clip8(a1); d[2] = (uint8_t)clip8(a2);
+            uint8_t* dst = s_tmp8 + (size_t)xx * line + r;
+            dst[0] = (uint8_t)clip8(half + r0a + r1a * 256 + r2a * 65536);
+            dst[(size_t)p.Wout * line] = (uint8_t)clip8(half + g0a + g1a * 256 + g2a * 65536);
+            dst[(size_t)2 * p.Wout * line] = (uint8_t)clip8(half + b0a + b1a * 256 + b2a * 65536);
         }
     }
     __syncthreads();
-    // ---- vertical pass -> 8-bit output rows of the band: warp <-> (row, 32-word chunk), lane <-> 4 bytes ----
-    const int nj = (p.wpo + 31) >> 5;
-    for (int it = warp; it < nb * nj; it += NW) {
-        const int yl = it / nj, j = (it - yl * nj) * 32 + lane;
+
+    // ---- vertical pass + ToTensor + Normalize: warp <-> (channel, output row, 32-column chunk), lane <-> column ----
+    const int nchunk = (p.Wout + 31) >> 5;
+    for (int it = warp; it < 3 * nb * nchunk; it += NW) {
+        const int cy = it / nchunk, xx = (it - cy * nchunk) * 32 + lane;
+        const int c = cy / nb, yl = cy - c * nb;
         const int yy = yy0 + yl;
         const int y0 = __ldg(p.by + yy * 2), cnt = __ldg(p.by + yy * 2 + 1);
-        const int* k = p.ky + yy * p.ksy;
-        if (j < p.wpo) {
-            const uint32_t* src = s_tmp + (size_t)(y0 - r0) * p.stw + j;
-            int a0 = half, a1 = half, a2 = half, a3 = half;
-            for (int t = 0; t < cnt; ++t) {
-                const uint32_t w = src[(size_t)t * p.stw];
-                const int c = __ldg(k + t);
-                a0 += byte_of<0>(w) * c; a1 += byte_of<1>(w) * c; a2 += byte_of<2>(w) * c; a3 += byte_of<3>(w) * c;
+        const int steps = (cnt + 3) >> 2;
+        const int off = y0 - r0;
+        const int sh = (off & 3) * 8;
+        const uint4* tab = p.dy + yy * p.ks4y;
+        if (xx < p.Wout) {
+            const uint32_t* src = s_tmp + ((size_t)c * p.Wout + xx) * p.rpw + (off >> 2);
+            int a0 = 0, a1 = 0, a2 = 0;
+            uint32_t pw = src[0];
+            for (int s = 0; s < steps; ++s) {
+                const uint4 d = __ldg(tab + s);
+                const uint32_t nw = src[s + 1];
+                const uint32_t v = __funnelshift_r(pw, nw, sh);
+                pw = nw;
+                a0 = dp4a_us(v, d.x, a0); a1 = dp4a_us(v, d.y, a1); a2 = dp4a_us(v, d.z, a2);
             }
-            s_out[yl * p.wpo + j] = (uint32_t)clip8(a0) | ((uint32_t)clip8(a1) << 8) | ((uint32_t)clip8(a2) << 16) | ((uint32_t)clip8(a3) << 24);
-        }
-    }
-    __syncthreads();
-    // ---- ToTensor + Normalize through the LUT: out[n][c][yy][xx], one coalesced row per warp iteration ----
-    const uint8_t* s_out8 = reinterpret_cast<const uint8_t*>(s_out);
-    for (int row = warp; row < 3 * nb; row += NW) {
-        const int c = row / nb, yl = row - c * nb;
-        const uint8_t* src = s_out8 + (size_t)yl * p.wpo * 4 + c;
-        float* dst = p.out + (((int64_t)n * 3 + c) * p.Hout + yy0 + yl) * p.Wout;
-        const float* l = lut + c * 256;
-        for (int xx = lane; xx < p.Wout; xx += 32) __stcs(dst + xx, l[src[xx * 3]]);
-    }
-    if (p.out_u8) {
-        for (int yl = warp; yl < nb; yl += NW) {
-            uint8_t* dst = p.out_u8 + ((int64_t)n * p.Hout + yy0 + yl) * p.Wout * 3;
-            const uint8_t* src = s_out8 + (size_t)yl * p.wpo * 4;
-            for (int i = lane; i < p.Wout * 3; i += 32) dst[i] = src[i];
+            const int u = clip8(half + a0 + a1 * 256 + a2 * 65536);
+            __stcs(p.out + (((int64_t)n * 3 + c) * p.Hout + yy) * p.Wout + xx, lut[c * 256 + u]);
+            if (p.out_u8) p.out_u8[(((int64_t)n * p.Hout + yy) * p.Wout + xx) * 3 + c] = (uint8_t)u;
         }
     }
 }
@@ -280,11 +311,12 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
     if (int rc = get_table(Win, Wout, &tx)) return rc;
     if (int rc = get_table(Hin, Hout, &ty)) return rc;
     EGR_CHECK(((uintptr_t)images & 3) == 0, EGR_ERR_INVALID, "preprocess: images must be 4-byte aligned");
-    // row strides in words, odd so that 32 lanes on 32 consecutive rows hit 32 different banks
     const int row_bytes = Win * 3;
-    const int siw = (((row_bytes + 3) >> 2) + 4) | 1;          // + slack: the tap loop reads up to 4 words past the last tap
-    const int wpo = (Wout * 3 + 3) >> 2;
-    const int stw = wpo | 1;
+    // odd word strides: 32 lanes on 32 consecutive rows (horizontal) / columns (vertical) hit 32 different banks;
+    // + 2 words of slack: the tap loops read one word past the last step and the realign needs its successor
+    const int siw = (((Win + 3) >> 2) + 2) | 1;
+    const size_t xtab_bytes = (size_t)Wout * tx->ks4 * sizeof(uint4);
+    const int xtab_in_smem = xtab_bytes <= 24 * 1024;
     auto rows_for = [&](int band) {
         int mx = 0;
         for (int y0 = 0; y0 < Hout; y0 += band) {
@@ -293,26 +325,27 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
         }
         return mx;
     };
-    auto smem_for = [&](int band, int rows) {
-        return (size_t)3072 + ((size_t)rows * siw + 4 + (size_t)rows * stw + (size_t)band * wpo) * 4 + 16;
+    auto rpw_for = [&](int rows) { return (((rows + 3) >> 2) + 2) | 1; };
+    auto smem_for = [&](int rows) {
+        return (size_t)3072 + (xtab_in_smem ? xtab_bytes : 0) + (3 * ((size_t)rows * siw + 2) + (size_t)3 * Wout * rpw_for(rows)) * 4 + 16;
     };
     // band of output rows per CTA: most output rows per 32-row pass of the horizontal stage among those that fit
     int band = 0, rows = 0;
     double best = 0.0;
     for (int b = 1; b <= std::min(Hout, 64); ++b) {
         const int r = rows_for(b);
-        if (smem_for(b, r) > (size_t)226 * 1024) continue;
+        if (smem_for(r) > (size_t)226 * 1024) continue;
         const double score = (double)b / ((r + 31) / 32);
         if (score > best * 1.0001) { best = score; band = b; rows = r; }
     }
     EGR_CHECK(band > 0, EGR_ERR_UNSUPPORTED, "preprocess: %dx%d -> %dx%d does not fit in shared memory", Hin, Win, Hout, Wout);
-    const size_t smem = smem_for(band, rows);
+    const size_t smem = smem_for(rows);
     EGR_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     PpParams p{};
     p.img = images; p.img_end = images + (size_t)N * Hin * row_bytes; p.out = out; p.out_u8 = resized_u8;
-    p.bx = tx->d_bounds; p.kx = tx->d_kk; p.by = ty->d_bounds; p.ky = ty->d_kk;
-    p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout; p.ksx = tx->ksize; p.ksy = ty->ksize;
-    p.band = band; p.rows_max = rows; p.siw = siw; p.stw = stw; p.wpo = wpo;
+    p.bx = tx->d_bounds; p.dx = tx->d_digits; p.by = ty->d_bounds; p.dy = ty->d_digits;
+    p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout; p.ks4x = tx->ks4; p.ks4y = ty->ks4;
+    p.band = band; p.rows_max = rows; p.siw = siw; p.rpw = rpw_for(rows); p.xtab_in_smem = xtab_in_smem;
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean3_host[c]; p.stdv[c] = std3_host[c]; }
     EGR_LAUNCH(preprocess_kernel, dim3((Hout + band - 1) / band, (unsigned)N), PP_THREADS, smem, (cudaStream_t)stream, p);
     return EGR_OK;
