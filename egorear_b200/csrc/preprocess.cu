@@ -139,7 +139,8 @@ struct PpParams {
     int Hin, Win, Hout, Wout, ks4x, ks4y, band, rows_max;
     int siw;                      // words per staged plane row (odd)
     int rpw;                      // words per [channel][column] line of the transposed intermediate (odd)
-    int xtab_in_smem;
+    int off_xtab, off_in;         // byte offsets of the x digit table / the staged planes in shared memory
+    unsigned magic_nchunk;        // ceil(2^32 / chunks per output row)
     float mean[3], stdv[3];
 };
 
@@ -162,6 +163,8 @@ __device__ __forceinline__ uint32_t row_word(const uint32_t* gw, int j, int ph, 
     return __funnelshift_r(lo, hi, 8 * ph);
 }
 
+// XS: the x digit table fits in shared memory next to the data (the usual case); otherwise it is read through L1.
+template <bool XS>
 __global__ void __launch_bounds__(PP_THREADS)
 preprocess_kernel(const PpParams p) {
     extern __shared__ __align__(16) uint8_t pp_smem[];
@@ -176,10 +179,13 @@ preprocess_kernel(const PpParams p) {
     const int r1 = p.by[(yy1 - 1) * 2] + p.by[(yy1 - 1) * 2 + 1];      // bounds are monotonic in yy
     const int nrows = r1 - r0;
     const int row_bytes = p.Win * 3;
-    // shared memory: LUT | x digit table (optional) | R, G, B planes of the staged rows | transposed intermediate
+    // shared memory: LUT | y digits + bounds of the band | x bounds | x digit table (XS) | R, G, B planes | intermediate
     float* lut = reinterpret_cast<float*>(pp_smem);
-    uint4* xtab = reinterpret_cast<uint4*>(pp_smem + 3072);
-    uint32_t* s_in = reinterpret_cast<uint32_t*>(xtab + (p.xtab_in_smem ? p.Wout * p.ks4x : 0));
+    uint4* ytab = reinterpret_cast<uint4*>(pp_smem + 3072);
+    int2* sby = reinterpret_cast<int2*>(ytab + p.band * p.ks4y);
+    int2* sbx = sby + p.band;
+    uint4* xtab = reinterpret_cast<uint4*>(pp_smem + p.off_xtab);
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(pp_smem + p.off_in);
     const int plane = p.rows_max * p.siw + 2;                            // words per plane (+ slack for the realign read)
     uint32_t* s_tmp = s_in + 3 * (size_t)plane;
     uint8_t* s_tmp8 = reinterpret_cast<uint8_t*>(s_tmp);
@@ -191,9 +197,11 @@ preprocess_kernel(const PpParams p) {
         // ToTensor: u / 255 in float32; Normalize: (x - mean) / std, each op rounded like the separate torch kernels
         lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean), stdv);
     }
-    if (p.xtab_in_smem)
+    for (int i = threadIdx.x; i < nb * p.ks4y; i += PP_THREADS) ytab[i] = __ldg(p.dy + (size_t)yy0 * p.ks4y + i);
+    for (int i = threadIdx.x; i < nb; i += PP_THREADS) sby[i] = __ldg(reinterpret_cast<const int2*>(p.by) + yy0 + i);
+    for (int i = threadIdx.x; i < p.Wout; i += PP_THREADS) sbx[i] = __ldg(reinterpret_cast<const int2*>(p.bx) + i);
+    if (XS)
         for (int i = threadIdx.x; i < p.Wout * p.ks4x; i += PP_THREADS) xtab[i] = __ldg(p.dx + i);
-    const uint4* xt = p.xtab_in_smem ? xtab : p.dx;
 
     // ---- stage rows [r0, r1): warp <-> row, lane <-> group of 4 pixels = 3 words -> one word per colour plane ----
     const int ngrp = (p.Win + 3) >> 2;
@@ -206,15 +214,24 @@ preprocess_kernel(const PpParams p) {
         uint32_t* dR = s_in + (size_t)r * p.siw;
         uint32_t* dG = dR + plane;
         uint32_t* dB = dG + plane;
-#pragma unroll 2
-        for (int g = lane; g < ngrp; g += 32) {
-            const uint32_t w0 = row_word(gw, 3 * g, ph, nsafe, p.img_end);
-            const uint32_t w1 = row_word(gw, 3 * g + 1, ph, nsafe, p.img_end);
-            const uint32_t w2 = row_word(gw, 3 * g + 2, ph, nsafe, p.img_end);
-            // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
-            dR[g] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
-            dG[g] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
-            dB[g] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+        if (ph == 0 && 3 * ngrp <= nsafe) {              // aligned row, nowhere near the end of the buffer: plain loads
+#pragma unroll 4
+            for (int g = lane; g < ngrp; g += 32) {
+                const uint32_t w0 = __ldg(gw + 3 * g), w1 = __ldg(gw + 3 * g + 1), w2 = __ldg(gw + 3 * g + 2);
+                // bytes: R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+                dR[g] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+                dG[g] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+                dB[g] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+            }
+        } else {
+            for (int g = lane; g < ngrp; g += 32) {
+                const uint32_t w0 = row_word(gw, 3 * g, ph, nsafe, p.img_end);
+                const uint32_t w1 = row_word(gw, 3 * g + 1, ph, nsafe, p.img_end);
+                const uint32_t w2 = row_word(gw, 3 * g + 2, ph, nsafe, p.img_end);
+                dR[g] = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+                dG[g] = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+                dB[g] = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+            }
         }
     }
     __syncthreads();
@@ -223,32 +240,43 @@ preprocess_kernel(const PpParams p) {
     const int half = 1 << (PP_PRECISION_BITS - 1);
     const int n_rg = (nrows + 31) >> 5;
     const int line = p.rpw * 4;                                          // bytes per [channel][column] line
-    for (int it = warp; it < n_rg * p.Wout; it += NW) {
-        const int rg = it / p.Wout, xx = it - rg * p.Wout;
+    for (int rg = 0; rg < n_rg; ++rg) {
         const int r = rg * 32 + lane;
-        const int x0 = __ldg(p.bx + xx * 2), cnt = __ldg(p.bx + xx * 2 + 1);
-        const int steps = (cnt + 3) >> 2;
-        const int sh = (x0 & 3) * 8;
-        const uint32_t* rowR = s_in + (size_t)min(r, nrows - 1) * p.siw + (x0 >> 2);
-        const uint32_t* rowG = rowR + plane;
-        const uint32_t* rowB = rowG + plane;
-        const uint4* tab = xt + xx * p.ks4x;
-        int r0a = 0, r1a = 0, r2a = 0, g0a = 0, g1a = 0, g2a = 0, b0a = 0, b1a = 0, b2a = 0;
-        uint32_t pr = rowR[0], pg = rowG[0], pb = rowB[0];
-        for (int s = 0; s < steps; ++s) {
-            const uint4 d = tab[s];
-            const uint32_t nr = rowR[s + 1], ng = rowG[s + 1], nbw = rowB[s + 1];
-            const uint32_t vr = __funnelshift_r(pr, nr, sh), vg = __funnelshift_r(pg, ng, sh), vb = __funnelshift_r(pb, nbw, sh);
-            pr = nr; pg = ng; pb = nbw;
-            r0a = dp4a_us(vr, d.x, r0a); r1a = dp4a_us(vr, d.y, r1a); r2a = dp4a_us(vr, d.z, r2a);
-            g0a = dp4a_us(vg, d.x, g0a); g1a = dp4a_us(vg, d.y, g1a); g2a = dp4a_us(vg, d.z, g2a);
-            b0a = dp4a_us(vb, d.x, b0a); b1a = dp4a_us(vb, d.y, b1a); b2a = dp4a_us(vb, d.z, b2a);
-        }
-        if (r < nrows) {
-            uint8_t* dst = s_tmp8 + (size_t)xx * line + r;
-            dst[0] = (uint8_t)clip8(half + r0a + r1a * 256 + r2a * 65536);
-            dst[(size_t)p.Wout * line] = (uint8_t)clip8(half + g0a + g1a * 256 + g2a * 65536);
-            dst[(size_t)2 * p.Wout * line] = (uint8_t)clip8(half + b0a + b1a * 256 + b2a * 65536);
+        const uint32_t* rowbase = s_in + (size_t)min(r, nrows - 1) * p.siw;
+        for (int xx = warp; xx < p.Wout; xx += NW) {
+            const int2 bnd = sbx[xx];                                    // (first input column, taps): warp-uniform
+            const int steps = (bnd.y + 3) >> 2;
+            const int sh = (bnd.x & 3) * 8;
+            const uint32_t* rowR = rowbase + (bnd.x >> 2);
+            const uint32_t* rowG = rowR + plane;
+            const uint32_t* rowB = rowG + plane;
+            const uint4* tab = (XS ? xtab : p.dx) + xx * p.ks4x;
+            int r0a = 0, r1a = 0, r2a = 0, g0a = 0, g1a = 0, g2a = 0, b0a = 0, b1a = 0, b2a = 0;
+            uint32_t pr = rowR[0], pg = rowG[0], pb = rowB[0];
+#define EGR_PP_HSTEP(S)                                                                                     \
+            {                                                                                               \
+                const uint4 d = XS ? tab[S] : __ldg(tab + (S));                                             \
+                const uint32_t nr = rowR[(S) + 1], ng = rowG[(S) + 1], nbw = rowB[(S) + 1];                   \
+                const uint32_t vr = __funnelshift_r(pr, nr, sh), vg = __funnelshift_r(pg, ng, sh),          \
+                               vb = __funnelshift_r(pb, nbw, sh);                                           \
+                pr = nr; pg = ng; pb = nbw;                                                                 \
+                r0a = dp4a_us(vr, d.x, r0a); r1a = dp4a_us(vr, d.y, r1a); r2a = dp4a_us(vr, d.z, r2a);      \
+                g0a = dp4a_us(vg, d.x, g0a); g1a = dp4a_us(vg, d.y, g1a); g2a = dp4a_us(vg, d.z, g2a);      \
+                b0a = dp4a_us(vb, d.x, b0a); b1a = dp4a_us(vb, d.y, b1a); b2a = dp4a_us(vb, d.z, b2a);      \
+            }
+            if (steps == 4) {                 // 13-16 taps (e.g. 872 -> 256): straight-line
+                EGR_PP_HSTEP(0) EGR_PP_HSTEP(1) EGR_PP_HSTEP(2) EGR_PP_HSTEP(3)
+            } else {
+#pragma unroll 1
+                for (int s = 0; s < steps; ++s) EGR_PP_HSTEP(s)
+            }
+#undef EGR_PP_HSTEP
+            if (r < nrows) {
+                uint8_t* dst = s_tmp8 + (size_t)xx * line + r;
+                dst[0] = (uint8_t)clip8(half + r0a + r1a * 256 + r2a * 65536);
+                dst[(size_t)p.Wout * line] = (uint8_t)clip8(half + g0a + g1a * 256 + g2a * 65536);
+                dst[(size_t)2 * p.Wout * line] = (uint8_t)clip8(half + b0a + b1a * 256 + b2a * 65536);
+            }
         }
     }
     __syncthreads();
@@ -256,20 +284,23 @@ preprocess_kernel(const PpParams p) {
     // ---- vertical pass + ToTensor + Normalize: warp <-> (channel, output row, 32-column chunk), lane <-> column ----
     const int nchunk = (p.Wout + 31) >> 5;
     for (int it = warp; it < 3 * nb * nchunk; it += NW) {
-        const int cy = it / nchunk, xx = (it - cy * nchunk) * 32 + lane;
-        const int c = cy / nb, yl = cy - c * nb;
+        const int cy = (nchunk == 1) ? it : (int)__umulhi((unsigned)it, p.magic_nchunk);   // it / nchunk (exact for it < 2^16)
+        const int xx = (it - cy * nchunk) * 32 + lane;
+        const int c = (cy >= 2 * nb) ? 2 : (cy >= nb) ? 1 : 0;
+        const int yl = cy - c * nb;
         const int yy = yy0 + yl;
-        const int y0 = __ldg(p.by + yy * 2), cnt = __ldg(p.by + yy * 2 + 1);
-        const int steps = (cnt + 3) >> 2;
-        const int off = y0 - r0;
+        const int2 bnd = sby[yl];
+        const int steps = (bnd.y + 3) >> 2;
+        const int off = bnd.x - r0;
         const int sh = (off & 3) * 8;
-        const uint4* tab = p.dy + yy * p.ks4y;
+        const uint4* tab = ytab + yl * p.ks4y;
         if (xx < p.Wout) {
             const uint32_t* src = s_tmp + ((size_t)c * p.Wout + xx) * p.rpw + (off >> 2);
             int a0 = 0, a1 = 0, a2 = 0;
             uint32_t pw = src[0];
+#pragma unroll 4
             for (int s = 0; s < steps; ++s) {
-                const uint4 d = __ldg(tab + s);
+                const uint4 d = tab[s];
                 const uint32_t nw = src[s + 1];
                 const uint32_t v = __funnelshift_r(pw, nw, sh);
                 pw = nw;
@@ -316,7 +347,7 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
     // + 2 words of slack: the tap loops read one word past the last step and the realign needs its successor
     const int siw = (((Win + 3) >> 2) + 2) | 1;
     const size_t xtab_bytes = (size_t)Wout * tx->ks4 * sizeof(uint4);
-    const int xtab_in_smem = xtab_bytes <= 24 * 1024;
+    const bool xs = xtab_bytes <= 24 * 1024;
     auto rows_for = [&](int band) {
         int mx = 0;
         for (int y0 = 0; y0 < Hout; y0 += band) {
@@ -326,27 +357,42 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
         return mx;
     };
     auto rpw_for = [&](int rows) { return (((rows + 3) >> 2) + 2) | 1; };
-    auto smem_for = [&](int rows) {
-        return (size_t)3072 + (xtab_in_smem ? xtab_bytes : 0) + (3 * ((size_t)rows * siw + 2) + (size_t)3 * Wout * rpw_for(rows)) * 4 + 16;
+    // LUT | y digits, y bounds of the band, x bounds | (16-byte aligned) x digit table | planes | intermediate
+    auto off_xtab_for = [&](int band) {
+        return (3072 + (size_t)band * ty->ks4 * sizeof(uint4) + ((size_t)band + Wout) * sizeof(int2) + 15) & ~(size_t)15;
+    };
+    auto off_in_for = [&](int band) { return off_xtab_for(band) + (xs ? xtab_bytes : 0); };
+    auto smem_for = [&](int band, int rows) {
+        return off_in_for(band) + (3 * ((size_t)rows * siw + 2) + (size_t)3 * Wout * rpw_for(rows)) * 4 + 16;
     };
     // band of output rows per CTA: most output rows per 32-row pass of the horizontal stage among those that fit
     int band = 0, rows = 0;
     double best = 0.0;
     for (int b = 1; b <= std::min(Hout, 64); ++b) {
         const int r = rows_for(b);
-        if (smem_for(r) > (size_t)226 * 1024) continue;
+        if (smem_for(b, r) > (size_t)226 * 1024) continue;
         const double score = (double)b / ((r + 31) / 32);
         if (score > best * 1.0001) { best = score; band = b; rows = r; }
     }
     EGR_CHECK(band > 0, EGR_ERR_UNSUPPORTED, "preprocess: %dx%d -> %dx%d does not fit in shared memory", Hin, Win, Hout, Wout);
-    const size_t smem = smem_for(rows);
-    EGR_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    const int nchunk = (Wout + 31) / 32;
+    EGR_CHECK(3 * band * nchunk < 65536, EGR_ERR_UNSUPPORTED, "preprocess: output rows too wide (%d)", Wout);
+    const size_t smem = smem_for(band, rows);
     PpParams p{};
     p.img = images; p.img_end = images + (size_t)N * Hin * row_bytes; p.out = out; p.out_u8 = resized_u8;
     p.bx = tx->d_bounds; p.dx = tx->d_digits; p.by = ty->d_bounds; p.dy = ty->d_digits;
     p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout; p.ks4x = tx->ks4; p.ks4y = ty->ks4;
-    p.band = band; p.rows_max = rows; p.siw = siw; p.rpw = rpw_for(rows); p.xtab_in_smem = xtab_in_smem;
+    p.band = band; p.rows_max = rows; p.siw = siw; p.rpw = rpw_for(rows);
+    p.off_xtab = (int)off_xtab_for(band); p.off_in = (int)off_in_for(band);
+    p.magic_nchunk = (unsigned)(((uint64_t)1 << 32) / nchunk + 1);
     for (int c = 0; c < 3; ++c) { p.mean[c] = mean3_host[c]; p.stdv[c] = std3_host[c]; }
-    EGR_LAUNCH(preprocess_kernel, dim3((Hout + band - 1) / band, (unsigned)N), PP_THREADS, smem, (cudaStream_t)stream, p);
+    const dim3 grid((Hout + band - 1) / band, (unsigned)N);
+    if (xs) {
+        EGR_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        EGR_LAUNCH((preprocess_kernel<true>), grid, PP_THREADS, smem, (cudaStream_t)stream, p);
+    } else {
+        EGR_CUDA_OK(cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        EGR_LAUNCH((preprocess_kernel<false>), grid, PP_THREADS, smem, (cudaStream_t)stream, p);
+    }
     return EGR_OK;
 }
