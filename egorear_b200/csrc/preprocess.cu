@@ -240,6 +240,7 @@ preprocess_kernel(const PpParams p) {
     const int half = 1 << (PP_PRECISION_BITS - 1);
     const int n_rg = (nrows + 31) >> 5;
     const int line = p.rpw * 4;                                          // bytes per [channel][column] line
+    const int cstride = p.Wout * line;                                   // bytes per channel of the intermediate
     for (int rg = 0; rg < n_rg; ++rg) {
         const int r = rg * 32 + lane;
         const uint32_t* rowbase = s_in + (size_t)min(r, nrows - 1) * p.siw;
@@ -272,10 +273,10 @@ preprocess_kernel(const PpParams p) {
             }
 #undef EGR_PP_HSTEP
             if (r < nrows) {
-                uint8_t* dst = s_tmp8 + (size_t)xx * line + r;
+                uint8_t* dst = s_tmp8 + xx * line + r;
                 dst[0] = (uint8_t)clip8(half + r0a + r1a * 256 + r2a * 65536);
-                dst[(size_t)p.Wout * line] = (uint8_t)clip8(half + g0a + g1a * 256 + g2a * 65536);
-                dst[(size_t)2 * p.Wout * line] = (uint8_t)clip8(half + b0a + b1a * 256 + b2a * 65536);
+                dst[cstride] = (uint8_t)clip8(half + g0a + g1a * 256 + g2a * 65536);
+                dst[2 * cstride] = (uint8_t)clip8(half + b0a + b1a * 256 + b2a * 65536);
             }
         }
     }
@@ -283,12 +284,15 @@ preprocess_kernel(const PpParams p) {
 
     // ---- vertical pass + ToTensor + Normalize: warp <-> (channel, output row, 32-column chunk), lane <-> column ----
     const int nchunk = (p.Wout + 31) >> 5;
+    // 32-bit offsets from per-CTA base pointers (the host checks 3 * Hout * Wout < 2^31)
+    float* out_n = p.out + (int64_t)n * 3 * p.Hout * p.Wout + (int64_t)yy0 * p.Wout;
+    uint8_t* u8_n = p.out_u8 ? p.out_u8 + ((int64_t)n * p.Hout + yy0) * p.Wout * 3 : nullptr;
+    const int plane_out = p.Hout * p.Wout;
     for (int it = warp; it < 3 * nb * nchunk; it += NW) {
         const int cy = (nchunk == 1) ? it : (int)__umulhi((unsigned)it, p.magic_nchunk);   // it / nchunk (exact for it < 2^16)
         const int xx = (it - cy * nchunk) * 32 + lane;
         const int c = (cy >= 2 * nb) ? 2 : (cy >= nb) ? 1 : 0;
         const int yl = cy - c * nb;
-        const int yy = yy0 + yl;
         const int2 bnd = sby[yl];
         const int steps = (bnd.y + 3) >> 2;
         const int off = bnd.x - r0;
@@ -307,8 +311,8 @@ preprocess_kernel(const PpParams p) {
                 a0 = dp4a_us(v, d.x, a0); a1 = dp4a_us(v, d.y, a1); a2 = dp4a_us(v, d.z, a2);
             }
             const int u = clip8(half + a0 + a1 * 256 + a2 * 65536);
-            __stcs(p.out + (((int64_t)n * 3 + c) * p.Hout + yy) * p.Wout + xx, lut[c * 256 + u]);
-            if (p.out_u8) p.out_u8[(((int64_t)n * p.Hout + yy) * p.Wout + xx) * 3 + c] = (uint8_t)u;
+            __stcs(out_n + (c * plane_out + yl * p.Wout + xx), lut[c * 256 + u]);
+            if (u8_n) u8_n[(yl * p.Wout + xx) * 3 + c] = (uint8_t)u;
         }
     }
 }
@@ -376,6 +380,7 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
     }
     EGR_CHECK(band > 0, EGR_ERR_UNSUPPORTED, "preprocess: %dx%d -> %dx%d does not fit in shared memory", Hin, Win, Hout, Wout);
     const int nchunk = (Wout + 31) / 32;
+    EGR_CHECK((int64_t)3 * Hout * Wout < ((int64_t)1 << 31), EGR_ERR_UNSUPPORTED, "preprocess: output image too large");
     EGR_CHECK(3 * band * nchunk < 65536, EGR_ERR_UNSUPPORTED, "preprocess: output rows too wide (%d)", Wout);
     const size_t smem = smem_for(band, rows);
     PpParams p{};
