@@ -270,12 +270,9 @@ extern "C" int egr_eval_pose(const float* pred, const float* gt, int64_t B, int 
     EGR_CHECK(pred && gt && metrics && (n_auc == 0 || auc_thresholds), EGR_ERR_INVALID, "eval_pose: null pointer");
     EGR_CHECK(((uintptr_t)metrics % 16) == 0, EGR_ERR_INVALID, "eval_pose: metrics must be 16-byte aligned");
     const size_t smem = (size_t)2 * EP_THREADS * ((J * 3) | 1) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (smem > 48 * 1024)          // only the run-time-J variant with more than 31 joints needs the opt-in (per device)
         EGR_CUDA_OK(cudaFuncSetAttribute(eval_pose_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          2 * EP_THREADS * ((EP_MAX_J * 3) | 1) * (int)sizeof(float)));
-        attr_set = true;
-    }
     const int grid = (int)ceil_div64(B, EP_THREADS);
     if (J == 16)
         EGR_LAUNCH((eval_pose_kernel<16>), grid, EP_THREADS, smem, (cudaStream_t)stream, pred, gt, B, J, unit_scale,

@@ -293,6 +293,8 @@ int egr_eval_pose(const float* pred, const float* gt, int64_t B, int J, float un
  *   out        [N, 3, Hout, Wout] float32 = ((resized / 255) - mean) / std
  *   resized_u8 [N, Hout, Wout, 3] uint8 = the resized image itself, or NULL
  *   mean3_host, std3_host: HOST pointers to 3 floats each.
+ *   The first call for a given (Hin -> Hout, Win -> Wout) on a device allocates and uploads that geometry's coefficient
+ *   tables (a few KB, kept for the life of the process): make it outside CUDA-graph capture.
  * ------------------------------------------------------------------------------------------- */
 /* host-only helper (no device): Pillow's bicubic coefficient table for in_size -> out_size as the kernel uses it.
  * *ksize = taps per output; bounds [out_size][2] = (first input index, tap count); kk [out_size][ksize] 22-bit fixed
