@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics", "integrate_tensor_2d", "preprocess")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("generate_target", "get_max_preds", "get_max_preds_soft", "models", "eval_metrics", "integrate_tensor_2d", "preprocess", "pose3d_stereo")}
 
 
 def soft_inputs():

@@ -143,6 +143,34 @@ def golden_models(cls, gen_target):
     print("models:", {k: v.shape for k, v in out.items()})
 
 
+def golden_pose_stereo(cls, gen_target):
+    """2-view configs (ego4view_syn_pose3d_stereo_front.yaml / ..._stereo_back cameras): the stereo-front mvfex refinement
+    lifted by a 2-view EgoPoseFormerPose3D (mlp_pred.0.0 is then Linear(16384 -> 1024))."""
+    B = 1
+    feat, bfb = synth.synth_features(B, 4, seed=0)
+    kp = synth.synth_keypoints(B, 4, 16, seed=3)
+    hfa = torch.from_numpy(np.stack([[gen_target(kp[b, v], 872, 64, 16, 1.0)[1:] for v in range(4)] for b in range(B)]))
+    cfg2 = ref_import.load_model_cfg("ego4view_syn_heatmap_mvfex-n1_jqa_stereo_front.yaml")
+    m2 = cls["EgoPoseFormerHeatmapMVFEX"](**copy.deepcopy(cfg2)).eval()
+    synth.fill_state_dict(m2)
+    m2.forward_heatmap_feat_estimation = lambda img: (feat[:, :2], [None, None, None, bfb[:, :2]])
+    with torch.no_grad():
+        hp2, ff2 = m2(torch.zeros(B, 2, 3, 256, 256), heatmap_for_anchor=hfa[:, :2])
+    out = {}
+    c3 = ref_import.load_model_cfg("ego4view_syn_pose3d_stereo_front.yaml")
+    for cam, sl in (("ego4view_syn_stereo_front", slice(0, 2)), ("ego4view_syn_stereo_back", slice(2, 4))):
+        pc = copy.deepcopy(c3["pose3d_cfg"])
+        pc.update(dict(num_views=2, image_size=[256, 256], use_pred_heatmap_init=True, camera_model=cam))
+        p3 = cls["EgoPoseFormerPose3D"](**pc).eval()
+        synth.fill_state_dict(p3)
+        with torch.no_grad():
+            preds = p3(feat[:, sl], ff2[1], hp2[1], None)
+        out["pose_%s" % cam] = torch.stack(preds).numpy()
+        out["shape_mlp0_%s" % cam] = np.array(p3.state_dict()["mlp_pred.0.0.weight"].shape)
+    np.savez_compressed(os.path.join(HERE, "pose3d_stereo.npz"), **out)
+    print("pose3d_stereo:", {k: v.shape for k, v in out.items()}, out["shape_mlp0_ego4view_syn_stereo_front"])
+
+
 INTEGRATE_CASES = (("sm100", True, 100.0), ("sm1", True, 1.0), ("relu", False, 100.0))
 INTEGRATE_MAPS = ((0, 0), (1, 5), (2, 7), (3, 1), (3, 2), (3, 3))
 
@@ -230,6 +258,9 @@ if __name__ == "__main__":
     if "--preprocess-only" in sys.argv:
         golden_preprocess()
         sys.exit(0)
+    if "--pose-stereo-only" in sys.argv:
+        golden_pose_stereo(ref_import.import_estimators(), ref_import.import_functions()["generate_target"])
+        sys.exit(0)
     fns = ref_import.import_functions()
     golden_generate_target(fns["generate_target"])
     golden_decode(fns["get_max_preds"])
@@ -238,3 +269,4 @@ if __name__ == "__main__":
     golden_integrate()
     golden_preprocess()
     golden_models(ref_import.import_estimators(), fns["generate_target"])
+    golden_pose_stereo(ref_import.import_estimators(), fns["generate_target"])

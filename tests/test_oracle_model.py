@@ -18,7 +18,7 @@ def build_mvfex(V=4, precision="fp32"):
 
 
 def build_pose3d(camera_model="ego4view_syn", precision="fp32"):
-    m = modules.EgoPoseFormerPose3D(num_views=4, image_size=[256, 256], use_pred_heatmap_init=True, camera_model=camera_model,
+    m = modules.EgoPoseFormerPose3D(num_views=2 if "stereo" in camera_model else 4, image_size=[256, 256], use_pred_heatmap_init=True, camera_model=camera_model,
                                     precision=precision, **POSE_CFG)
     return synth.fill_state_dict(m).eval()
 
@@ -120,6 +120,31 @@ def test_oracle_pose3d_matches_golden(golden, mv4_oracle):
             d = (st["anchors_3d_after"] - preds[0]).numpy()
             assert np.allclose(d[..., 0], 12.0, atol=1e-4) and np.allclose(d[..., 1:], 0.0, atol=1e-4)
             assert 0.05 < float(st["anchors_valid"].float().mean()) < 0.95
+
+
+STEREO_CAMS = (("ego4view_syn_stereo_front", slice(0, 2)), ("ego4view_syn_stereo_back", slice(2, 4)))
+
+
+def stereo_case(golden, oracle_lib):
+    """2-view stereo-front refinement (oracle) whose features the 2-view pose3d lifts, as in make_golden.golden_pose_stereo"""
+    feat, bfb = synth.synth_features(1, 4, seed=0)
+    hfa = anchor_heatmaps(oracle_lib, golden["models"]["kp"])
+    with torch.no_grad():
+        lh2, lf2, _, _ = model_ref.mvfex_hot_path(build_mvfex(2).state_dict(), feat[:, :2], bfb[:, :2], hfa[:, :2])
+    return feat, lh2, lf2
+
+
+def test_oracle_pose3d_stereo_matches_golden(golden, oracle_lib):
+    """configs/ego4view_syn_pose3d_stereo_front.yaml (and the stereo-back camera pair): 2 views, mlp_pred.0.0 16384 -> 1024"""
+    feat, _, lf2 = stereo_case(golden, oracle_lib)
+    g = golden["pose3d_stereo"]
+    for cam, sl in STEREO_CAMS:
+        m = build_pose3d(cam)
+        assert tuple(m.state_dict()["mlp_pred.0.0.weight"].shape) == tuple(g["shape_mlp0_" + cam])
+        with torch.no_grad():
+            preds = model_ref.pose3d_forward(m.state_dict(), feat[:, sl], lf2[1], calib.load_calibration(None), cam, None)
+        mpjpe = np.linalg.norm(torch.stack(preds).numpy() - g["pose_" + cam], axis=-1).mean(axis=-1).max()
+        assert mpjpe < 1e-4, (cam, mpjpe)
 
 
 def test_msda_restatement_vs_grid_sample():
