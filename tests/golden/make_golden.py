@@ -158,13 +158,15 @@ def golden_pose_stereo(cls, gen_target):
         hp2, ff2 = m2(torch.zeros(B, 2, 3, 256, 256), heatmap_for_anchor=hfa[:, :2])
     out = {}
     c3 = ref_import.load_model_cfg("ego4view_syn_pose3d_stereo_front.yaml")
-    for cam, sl in (("ego4view_syn_stereo_front", slice(0, 2)), ("ego4view_syn_stereo_back", slice(2, 4))):
+    for cam, sl in (("ego4view_syn_stereo_front", slice(0, 2)), ("ego4view_syn_stereo_back", slice(2, 4)),
+                    ("ego4view_rw_stereo_front", slice(0, 2))):
         pc = copy.deepcopy(c3["pose3d_cfg"])
         pc.update(dict(num_views=2, image_size=[256, 256], use_pred_heatmap_init=True, camera_model=cam))
         p3 = cls["EgoPoseFormerPose3D"](**pc).eval()
         synth.fill_state_dict(p3)
+        ctm = synth.synth_coord_trans_mat(B, seed=5)[:, sl].contiguous() if "_rw" in cam else None
         with torch.no_grad():
-            preds = p3(feat[:, sl], ff2[1], hp2[1], None)
+            preds = p3(feat[:, sl], ff2[1], hp2[1], ctm)
         out["pose_%s" % cam] = torch.stack(preds).numpy()
         out["shape_mlp0_%s" % cam] = np.array(p3.state_dict()["mlp_pred.0.0.weight"].shape)
     np.savez_compressed(os.path.join(HERE, "pose3d_stereo.npz"), **out)

@@ -159,14 +159,15 @@ def test_pose3d_stereo_vs_oracle(golden, oracle_lib, precision):
     """2-view configs (ego4view_syn_pose3d_stereo_front.yaml and the stereo-back camera pair)"""
     from egorear_b200 import calib
     from oracle import model_ref
-    from test_oracle_model import STEREO_CAMS, stereo_case
+    from test_oracle_model import STEREO_CAMS, stereo_case, stereo_ctm
     feat, lh2, lf2 = stereo_case(golden, oracle_lib)
     for cam, sl in STEREO_CAMS:
         m = build_pose3d(cam, precision)
+        ctm = stereo_ctm(cam, sl)
         with torch.no_grad():
-            want = torch.stack(model_ref.pose3d_forward(m.state_dict(), feat[:, sl], lf2[1], calib.load_calibration(None), cam, None))
+            want = torch.stack(model_ref.pose3d_forward(m.state_dict(), feat[:, sl], lf2[1], calib.load_calibration(None), cam, ctm))
             m = m.cuda()
-            got = torch.stack(m(feat[:, sl].cuda(), lf2[1].cuda(), lh2[1].cuda(), None)).cpu()
+            got = torch.stack(m(feat[:, sl].cuda(), lf2[1].cuda(), lh2[1].cuda(), ctm.cuda() if ctm is not None else None)).cpu()
         d = mpjpe(got.numpy(), want.numpy())
         print("pose3d %s %s: MPJPE delta %.2e cm" % (cam, precision, d))
         assert d < MPJPE_TOL

@@ -122,7 +122,12 @@ def test_oracle_pose3d_matches_golden(golden, mv4_oracle):
             assert 0.05 < float(st["anchors_valid"].float().mean()) < 0.95
 
 
-STEREO_CAMS = (("ego4view_syn_stereo_front", slice(0, 2)), ("ego4view_syn_stereo_back", slice(2, 4)))
+STEREO_CAMS = (("ego4view_syn_stereo_front", slice(0, 2)), ("ego4view_syn_stereo_back", slice(2, 4)),
+               ("ego4view_rw_stereo_front", slice(0, 2)))
+
+
+def stereo_ctm(cam, sl):
+    return synth.synth_coord_trans_mat(1, seed=5)[:, sl].contiguous() if "_rw" in cam else None
 
 
 def stereo_case(golden, oracle_lib):
@@ -142,7 +147,8 @@ def test_oracle_pose3d_stereo_matches_golden(golden, oracle_lib):
         m = build_pose3d(cam)
         assert tuple(m.state_dict()["mlp_pred.0.0.weight"].shape) == tuple(g["shape_mlp0_" + cam])
         with torch.no_grad():
-            preds = model_ref.pose3d_forward(m.state_dict(), feat[:, sl], lf2[1], calib.load_calibration(None), cam, None)
+            preds = model_ref.pose3d_forward(m.state_dict(), feat[:, sl], lf2[1], calib.load_calibration(None), cam,
+                                             stereo_ctm(cam, sl))
         mpjpe = np.linalg.norm(torch.stack(preds).numpy() - g["pose_" + cam], axis=-1).mean(axis=-1).max()
         assert mpjpe < 1e-4, (cam, mpjpe)
 
