@@ -340,6 +340,10 @@ extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, 
     EGR_CHECK(N >= 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, EGR_ERR_INVALID, "preprocess: images should be [N, H, W, 3] uint8");
     EGR_CHECK(N <= 65535, EGR_ERR_UNSUPPORTED, "preprocess: at most 65535 images per call");
     EGR_CHECK(mean3_host && std3_host, EGR_ERR_INVALID, "preprocess: mean / std are required");
+    // PIL/Image.py (Pillow >= 11): strips more than 100x taller than wide that shrink vertically are resampled vertically
+    // FIRST, which changes the 8-bit intermediate; not a camera-frame geometry, so it is rejected rather than mis-ordered
+    EGR_CHECK(!((int64_t)Hin > (int64_t)Win * 100 && Hout < Hin), EGR_ERR_UNSUPPORTED,
+              "preprocess: %dx%d strips (height > 100 x width, shrinking) use Pillow's vertical-first order: unsupported", Hin, Win);
     if (N == 0) return EGR_OK;
     EGR_CHECK(images && out, EGR_ERR_INVALID, "preprocess: null pointer");
     const ResampleTable *tx = nullptr, *ty = nullptr;

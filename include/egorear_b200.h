@@ -293,6 +293,8 @@ int egr_eval_pose(const float* pred, const float* gt, int64_t B, int J, float un
  *   out        [N, 3, Hout, Wout] float32 = ((resized / 255) - mean) / std
  *   resized_u8 [N, Hout, Wout, 3] uint8 = the resized image itself, or NULL
  *   mean3_host, std3_host: HOST pointers to 3 floats each.
+ *   Strips with Hin > 100 * Win that shrink vertically return EGR_ERR_UNSUPPORTED: Pillow >= 11 resamples those
+ *   vertically first (PIL/Image.py, Image.resize), which changes the 8-bit intermediate image.
  *   The first call for a given (Hin -> Hout, Win -> Wout) on a device allocates and uploads that geometry's coefficient
  *   tables (a few KB, kept for the life of the process): make it outside CUDA-graph capture.
  * ------------------------------------------------------------------------------------------- */

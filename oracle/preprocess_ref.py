@@ -11,7 +11,8 @@ datasets/ego4view_rw/ego4view_rw_heatmap_mvf.py:40-41, 96-99):
 
 The arithmetic of `Image.resize(..., BICUBIC)` lives in a third-party dependency that is not under /root/reference:
 Pillow (unpinned in README.md:133; 12.2.0 in this image), src/libImaging/Resample.c.  Its published algorithm, restated
-here: two separable passes (horizontal first) over 8-bit data with an 8-bit intermediate image; per output index the
+here: two separable passes (horizontal first, except for Pillow's tall-strip rule, see vertical_first) over 8-bit data
+with an 8-bit intermediate image; per output index the
 bicubic kernel (a = -0.5, support 2) is stretched by the down-scaling factor (antialiasing), sampled at the input pixel
 centres inside [center - support, center + support], normalised in double and converted to fixed point with 22
 fractional bits; a pixel is clip8((2^21 + sum k_i * p_i) >> 22).  ToTensor divides by 255 in float32, Normalize subtracts
@@ -73,29 +74,49 @@ def _clip8(v):
     return np.clip(v >> PRECISION_BITS, 0, 255).astype(np.uint8)
 
 
-def resize_bicubic_u8(img, out_h, out_w):
-    """img uint8 [H, W, C] -> uint8 [out_h, out_w, C], bit-exact restatement of Image.resize((out_w, out_h), BICUBIC)."""
+def _pass_horizontal(img, out_w):
     H, W, C = img.shape
+    bounds, kk, _ = precompute_coeffs(W, out_w)
     src = img.astype(np.int64)
+    out = np.empty((H, out_w, C), np.uint8)
+    for xx in range(out_w):
+        x0, n = bounds[xx]
+        acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(src[:, x0:x0 + n, :], kk[xx, :n].astype(np.int64), axes=([1], [0]))
+        out[:, xx, :] = _clip8(acc)
+    return out
+
+
+def _pass_vertical(img, out_h):
+    H, W, C = img.shape
+    bounds, kk, _ = precompute_coeffs(H, out_h)
+    src = img.astype(np.int64)
+    out = np.empty((out_h, W, C), np.uint8)
+    for yy in range(out_h):
+        y0, n = bounds[yy]
+        acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(kk[yy, :n].astype(np.int64), src[y0:y0 + n], axes=([0], [0]))
+        out[yy] = _clip8(acc)
+    return out
+
+
+def vertical_first(in_h, in_w, out_h):
+    """PIL/Image.py (Pillow >= 11; 12.2.0 pinned here), Image.resize: very tall strips that shrink vertically are
+    resampled vertically first (`if self.size[1] > self.size[0] * 100 and size[1] < self.size[1]`).  Never true for
+    camera frames; the CUDA path rejects such inputs instead of silently using the other order."""
+    return in_h > in_w * 100 and out_h < in_h
+
+
+def resize_bicubic_u8(img, out_h, out_w):
+    """img uint8 [H, W, C] -> uint8 [out_h, out_w, C], bit-exact restatement of Image.resize((out_w, out_h), BICUBIC):
+    horizontal pass, 8-bit intermediate, vertical pass (a pass whose size does not change is skipped)."""
+    H, W, C = img.shape
+    if vertical_first(H, W, out_h):
+        img = _pass_vertical(img, out_h)
+        return _pass_horizontal(img, out_w) if out_w != W else img
     if out_w != W:
-        bounds, kk, _ = precompute_coeffs(W, out_w)
-        tmp = np.empty((H, out_w, C), np.uint8)
-        for xx in range(out_w):
-            x0, n = bounds[xx]
-            acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(src[:, x0:x0 + n, :], kk[xx, :n].astype(np.int64), axes=([1], [0]))
-            tmp[:, xx, :] = _clip8(acc)
-        src = tmp.astype(np.int64)
-    else:
-        tmp = img
+        img = _pass_horizontal(img, out_w)
     if out_h != H:
-        bounds, kk, _ = precompute_coeffs(H, out_h)
-        out = np.empty((out_h, src.shape[1], C), np.uint8)
-        for yy in range(out_h):
-            y0, n = bounds[yy]
-            acc = (1 << (PRECISION_BITS - 1)) + np.tensordot(kk[yy, :n].astype(np.int64), src[y0:y0 + n], axes=([0], [0]))
-            out[yy] = _clip8(acc)
-        return out
-    return tmp
+        img = _pass_vertical(img, out_h)
+    return img
 
 
 def to_tensor_normalize(u8, mean=IMAGENET_MEAN, std=IMAGENET_STD):

@@ -32,7 +32,7 @@ def test_preprocess_golden_bit_exact(ops, golden):
 
 
 @pytest.mark.parametrize("shape,size", [((2, 4, 218, 218), (64, 64)), ((3, 37, 53), (96, 40)), ((1, 1, 16, 500), (256, 8)),
-                                        ((5, 640, 3), (3, 256))])
+                                        ((5, 640, 7), (3, 256))])
 def test_preprocess_oracle_shapes(ops, shape, size):
     """leading batch/view dims, odd sizes (unaligned rows), extreme aspect ratios; other mean / std"""
     lead, (H, W) = shape[:-2], shape[-2:]
@@ -74,5 +74,7 @@ def test_preprocess_argument_validation(ops):
         ops.preprocess_images(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
     with pytest.raises(RuntimeError, match="uint8"):
         ops.preprocess_images(torch.zeros(1, 8, 8, 3).cuda())
+    with pytest.raises(RuntimeError, match="vertical-first"):         # Pillow's tall-strip rule is rejected, not mis-ordered
+        ops.preprocess_images(torch.zeros(1, 1000, 3, 3, dtype=torch.uint8).cuda(), size=(300, 7))
     out = ops.preprocess_images(torch.zeros(0, 8, 8, 3, dtype=torch.uint8).cuda(), size=(4, 4))
     assert out.shape == (0, 3, 4, 4)

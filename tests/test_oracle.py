@@ -147,3 +147,18 @@ def test_preprocess_oracle_matches_golden(golden):
     img = synth.synth_images(1, 333, 517, seed=11)[0]
     want = np.asarray(Image.fromarray(img).resize([200, 120], Image.BICUBIC))
     assert np.array_equal(pr.resize_bicubic_u8(img, 120, 200), want)
+
+
+def test_preprocess_oracle_vs_pil_random_geometries():
+    """seeded sweep of input / output sizes (down- and up-scaling, odd sizes, 1-pixel axes) against PIL itself"""
+    PIL = pytest.importorskip("PIL")
+    from PIL import Image
+    from egorear_b200 import synth
+    from oracle import preprocess_ref as pr
+    rng = np.random.default_rng(21)
+    geos = [(int(rng.integers(1, 400)), int(rng.integers(1, 400)), int(rng.integers(1, 200)), int(rng.integers(1, 200))) for _ in range(14)]
+    geos += [(872, 1, 256, 1), (1, 872, 1, 256), (2, 2, 255, 255), (1000, 3, 7, 300), (1000, 9, 500, 4), (1000, 10, 7, 300)]   # incl. Pillow's tall-strip rule
+    for H, W, oh, ow in geos:
+        img = synth.synth_images(1, H, W, seed=H * 1000 + W)[0]
+        want = np.asarray(Image.fromarray(img).resize([ow, oh], Image.BICUBIC))
+        assert np.array_equal(pr.resize_bicubic_u8(img, oh, ow), want), (H, W, oh, ow, PIL.__version__)
