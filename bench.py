@@ -14,7 +14,9 @@ public API with pinned-host inputs (H2D + D2H inside the timed region); roofline
 stage profiler of the library) against MEASURED_PEAKS.json; cpu_baseline = the CPU implementation on the host cores
 (live reference when /root/reference exists, else the oracle port) on a bounded sample.
 
-Other workloads (parity-test configs, not the headline): --workload generate_target | decode | pose3d | mvfex.
+Other workloads (parity-test configs, not the headline): --workload generate_target | decode | pose3d | mvfex | rw_e2e,
+and the widened rows of SURVEY §8f: eval_heatmap | eval_pose (eval-time metrics) and preprocess (PIL-exact resize +
+normalise); each prints the same JSON line with its own roofline, cpu_baseline and e2e.
 """
 import argparse
 import json
