@@ -55,6 +55,22 @@ def test_fails_loudly_without_gpu(lib):
         ops.get_max_preds(torch.zeros(1, 1, 64, 64))
     with pytest.raises(RuntimeError):
         ops.generate_target_batch(j)
+    # the widened entry points (eval metrics, integral decoder, preprocessing) behave the same way
+    f4 = np.zeros(16, np.float32)
+    m = (ctypes.c_float * 3)(0.5, 0.5, 0.5)
+    assert lib.egr_eval_pose(f4.ctypes.data, f4.ctypes.data, 1, 1, 10.0, 150.0, None, 0, f4.ctypes.data, None, None) == 2
+    assert lib.egr_eval_heatmap(f4.ctypes.data, 16, f4.ctypes.data, 16, 1, 1, 1, 4, 4, 1.0, f4.ctypes.data, f4.ctypes.data,
+                                f4.ctypes.data, f4.ctypes.data, 64, None) == 2
+    assert lib.egr_integrate_tensor_2d(f4.ctypes.data, 1, 1, 4, 4, 1, 100.0, f4.ctypes.data, None, None) == 2
+    assert lib.egr_preprocess_images(f4.ctypes.data, 1, 2, 2, 2, 2, m, m, f4.ctypes.data, None, None) == 2
+    assert b"no CPU fallback" in lib.egr_last_error()
+    from egorear_b200 import metrics
+    for call in (lambda: metrics.evaluate(torch.zeros(1, 2, 15, 64, 64), torch.zeros(1, 2, 15, 64, 64), "x"),
+                 lambda: metrics.evaluate_pose(torch.zeros(1, 16, 3), torch.zeros(1, 16, 3), "x"),
+                 lambda: ops.integrate_tensor_2d(torch.zeros(1, 1, 64, 64)),
+                 lambda: ops.preprocess_images(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            call()
 
 
 def test_argument_validation(lib):
