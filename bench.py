@@ -418,9 +418,9 @@ def main():
         def step(im=img, cm=ctm):
             e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             e[0].record()
-            f, b = pipe.backbone(im)
+            xh, b = pipe.backbone_staged(im)          # channels-last bf16 FPN output, handed over without re-staging
             e[1].record()
-            out = egd.gather_rows(pipe(f, b, cm)["packed"], world)
+            out = egd.gather_rows(pipe.forward(None, b, cm, feat_staged=xh)["packed"], world)
             e[2].record()
             split["ev"] = e
             return out

@@ -63,6 +63,7 @@ SIGNATURES = {
     "egr_mvfex_refiner_forward": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "egr_mvfex_export_staged": (c_int, [c_void_p, c_int]),
+    "egr_mvfex_use_staged_input": (c_int, [c_void_p, c_void_p]),
     "egr_mvfex_staged": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int)]),
     "egr_pose3d_use_staged": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "egr_pose3d_use_staged_final_f16": (c_int, [c_void_p, c_void_p]),

@@ -48,6 +48,7 @@ struct egr_mvfex {
     bool refn_f16_only = false;                // the fp16 copy is the only channels-last copy (H2a reads it too)
     __half* h2_0_f16 = nullptr;                // conv_heatmap_layers.0.0 weights [V][256][9*128] in fp16
     const void *st_init = nullptr, *st_refined = nullptr;
+    const void* in_staged = nullptr;           // one-shot: the caller's view-major channels-last bf16 copy of the input features
     const void* st_refined_hp = nullptr;
     bool tokb = false;
     WMat tk_hp2, tk_fcq, tk_bfb, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
@@ -631,7 +632,9 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_forward: null handle");
     if (int rc = require_device()) return rc;
     EGR_CHECK(h->packed, EGR_ERR_STATE, "mvfex_forward: parameters changed or never packed; call egr_mvfex_prepack");
-    EGR_CHECK(B > 0 && feat && bfb && hm_init && hm_refined && workspace, EGR_ERR_INVALID,
+    const void* in_staged = h->in_staged;
+    h->in_staged = nullptr;                                   // one-shot hint (egr_mvfex_use_staged_input)
+    EGR_CHECK(B > 0 && (feat || in_staged) && bfb && hm_init && hm_refined && workspace, EGR_ERR_INVALID,
               "mvfex_forward: null pointer / empty batch");
     EGR_CHECK(feat_refined || h->export_staged, EGR_ERR_INVALID,
               "mvfex_forward: feat_refined may be NULL only when the channels-last copies are exported (egr_mvfex_export_staged)");
@@ -646,8 +649,9 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     int rc;
     gemm_tc_set_scratch(w.splitk);
     EGR_MARK("stage_nhwc", st);
-    // S0: NCHW fp32 -> view-major channels-last staging copy
-    if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, bf, st))) return rc;
+    // S0: NCHW fp32 -> view-major channels-last staging copy; skipped when the producer already wrote that layout
+    if (in_staged) w.Xh = const_cast<void*>(in_staged);       // read-only from here on
+    else if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, bf, st))) return rc;
     EGR_MARK("H1a", st);
     // H1: init heads, one group per weight set (front: views 0-1, back: views 2-3), two views per group
     const int G1 = h->head_sets, vpg = V / G1;
@@ -688,6 +692,14 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     if (rc) return rc;
     note_all(h, w, B, V);
     h->st_init = w.Xh; h->st_refined = w.refn; h->st_refined_hp = w.refn_hp;
+    return EGR_OK;
+}
+
+extern "C" int egr_mvfex_use_staged_input(egr_mvfex* h, const void* feat_vmajor_nhwc_bf16) {
+    EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_use_staged_input: null handle");
+    EGR_CHECK(h->prec == EGR_PREC_BF16, EGR_ERR_UNSUPPORTED, "mvfex_use_staged_input: needs the bf16 precision (the staged copy is bf16)");
+    EGR_CHECK(((uintptr_t)feat_vmajor_nhwc_bf16 & 15) == 0, EGR_ERR_INVALID, "mvfex_use_staged_input: pointer must be 16-byte aligned");
+    h->in_staged = feat_vmajor_nhwc_bf16;
     return EGR_OK;
 }
 

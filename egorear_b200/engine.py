@@ -120,18 +120,26 @@ class MvfexEngine(_EngineBase):
         _lib.check(self._lib.egr_mvfex_export_staged(self._h, mode))
         self._export, self._export_hp = bool(enable), hp
 
-    def forward(self, feat, bfb, heatmap_for_anchor=None, want_feat_refined=True):
+    def forward(self, feat, bfb, heatmap_for_anchor=None, want_feat_refined=True, feat_staged=None):
         """feat [B,V,128,64,64], bfb [B,V,512,8,8] fp32 CUDA ->
         dict(hm_init, hm_refined [B,V,15,64,64], feat_refined [B,V,128,64,64], anchors_2d [B,V,15,2], anchors_valid).
-        want_feat_refined=False (needs export_staged): the NCHW fp32 refined features are not materialised (None)."""
+        want_feat_refined=False (needs export_staged): the NCHW fp32 refined features are not materialised (None).
+        feat_staged (bf16 precision only): the features as a channels-last bf16 producer leaves them, view-major
+        [V,B,64,64,128] contiguous; `feat` may then be None and the staging pass is skipped (egr_mvfex_use_staged_input)."""
         self._sync_params()
-        B, V = feat.shape[:2]
-        assert V == self.V and tuple(feat.shape[2:]) == (128, 64, 64) and tuple(bfb.shape[1:]) == (V, 512, 8, 8)
         feat_arg = feat
-        feat = feat.detach().float().contiguous()
+        if feat_staged is not None:
+            V, B = feat_staged.shape[:2]
+            assert feat_staged.dtype == torch.bfloat16 and feat_staged.is_contiguous() and tuple(feat_staged.shape[2:]) == (64, 64, 128)
+            feat = None
+        else:
+            B, V = feat.shape[:2]
+            assert tuple(feat.shape[2:]) == (128, 64, 64)
+            feat = feat.detach().float().contiguous()
+        assert V == self.V and tuple(bfb.shape) == (B, V, 512, 8, 8)
         bfb = bfb.detach().float().contiguous()
         hfa = heatmap_for_anchor.detach().float().contiguous() if isinstance(heatmap_for_anchor, torch.Tensor) else None
-        dev = feat.device
+        dev = bfb.device
         out = {
             "hm_init": torch.empty((B, V, self.J, 64, 64), dtype=torch.float32, device=dev),
             "hm_refined": torch.empty((B, V, self.J, 64, 64), dtype=torch.float32, device=dev),
@@ -140,6 +148,9 @@ class MvfexEngine(_EngineBase):
             "anchors_valid": torch.empty((B, V, self.J), dtype=torch.bool, device=dev),
         }
         ws = self._workspace(B, dev)
+        if feat_staged is not None:
+            _lib.check(self._lib.egr_mvfex_use_staged_input(self._h, _ptr(feat_staged)))
+            out["_keepalive"] = feat_staged          # the staged copies exported to a chained pose3d point into it
         _lib.check(self._lib.egr_mvfex_forward(self._h, B, _ptr(feat), _ptr(bfb), _ptr(hfa), _ptr(out["hm_init"]),
                                                _ptr(out["hm_refined"]), _ptr(out["feat_refined"]),
                                                _ptr(out["anchors_2d"]), _ptr(out["anchors_valid"]), _ptr(ws),
@@ -151,7 +162,8 @@ class MvfexEngine(_EngineBase):
             hp = getattr(self, "_export_hp", "tf32")
             out["staged"] = {"init": pi.value, "refined": pr.value, "refined_tf32": pt.value if hp == "tf32" else None,
                              "refined_f16": pt.value if hp in ("f16", "f16_only") else None, "bf16": bf.value,
-                             "feat": feat_arg, "feat_refined": out["feat_refined"]}
+                             "feat": None if feat_staged is not None else feat_arg, "feat_refined": out["feat_refined"],
+                             "B": B, "device": dev, "keepalive": feat_staged}
         return out
 
     def refiner_forward(self, r, heatmap, frame_feat, feat_mv, anchors_2d, anchors_valid, bfb):
@@ -200,7 +212,11 @@ class Pose3DEngine(_EngineBase):
         staged: MvfexEngine.forward(...)["staged"] of the SAME tensors (chained forward): skips the re-staging passes."""
         self._sync_params()
         ref = feats_final if feats_final is not None else feats_init
-        B, V = ref.shape[:2]
+        if ref is None:                    # fully chained: both feature maps only exist as the staged channels-last copies
+            assert staged is not None, "pose3d: feats_init / feats_final may both be None only with staged copies"
+            B, V, dev = staged["B"], self.V, staged["device"]
+        else:
+            B, V, dev = ref.shape[0], ref.shape[1], ref.device
         assert V == self.V
         fi = feats_init.detach().float().contiguous() if feats_init is not None else None
         ff = feats_final.detach().float().contiguous() if feats_final is not None else None
@@ -212,8 +228,8 @@ class Pose3DEngine(_EngineBase):
                 # the reference matmuls this against fp32 points (utils/camera_models.py:210): dtype error there too
                 raise RuntimeError("expected m1 and m2 to have the same dtype, but got: double != float")
             ctm = coord_trans_mat.contiguous()
-        preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=ref.device)
-        ws = self._workspace(B, ref.device)
+        preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=dev)
+        ws = self._workspace(B, dev)
         if staged is not None and staged["feat_refined"] is feats_final and (staged["feat"] is feats_init or not use_init):
             sampled = staged["init"] if use_init else staged["refined"]
             _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),

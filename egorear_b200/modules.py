@@ -465,15 +465,17 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
         return self.heatmap_estimator_stereo_front.forward_backbone(img, return_feat=True)
 
     def forward_from_feats(self, frame_feat_multi_view, backbone_feat_bottom_multi_view, heatmap_for_anchor=None,
-                           want_feat_refined=True):
+                           want_feat_refined=True, feat_staged=None):
         """The hot path proper: backbone features in, (list_heatmap_pred, list_frame_feat) out (:284-437).
-        want_feat_refined=False (chained forward with exported channels-last copies only): list_frame_feat[1] is None."""
+        want_feat_refined=False (chained forward with exported channels-last copies only): list_frame_feat[1] is None.
+        feat_staged: view-major channels-last bf16 features [V,B,64,64,128] straight from a channels-last bf16 backbone
+        (frame_feat_multi_view may then be None; see MvfexEngine.forward)."""
         hfa = heatmap_for_anchor if isinstance(heatmap_for_anchor, torch.Tensor) else None
         out = self.engine().forward(frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa,
-                                    want_feat_refined=want_feat_refined)
+                                    want_feat_refined=want_feat_refined, feat_staged=feat_staged)
         self.last_anchors = (out["anchors_2d"], out["anchors_valid"])
         self.last_staged = out.get("staged")
-        return [out["hm_init"], out["hm_refined"]], [frame_feat_multi_view, out["feat_refined"]]
+        return [out["hm_init"], out["hm_refined"]], [None if feat_staged is not None else frame_feat_multi_view, out["feat_refined"]]
 
     def forward(self, img, heatmap_for_anchor=None):
         if not self._has_backbone:

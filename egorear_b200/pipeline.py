@@ -43,9 +43,12 @@ class HotPathPipeline:
         return self
 
     @torch.no_grad()
-    def forward(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None):
-        list_hm, list_ff = self.heatmap.forward_from_feats(feat, bfb, heatmap_for_anchor,
-                                                           want_feat_refined=self.materialize_features)
+    def forward(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None, feat_staged=None):
+        """feat_staged: the features as backbone_staged() leaves them (view-major channels-last bf16); `feat` is then
+        ignored and the hot path starts without its staging pass."""
+        list_hm, list_ff = self.heatmap.forward_from_feats(None if feat_staged is not None else feat, bfb, heatmap_for_anchor,
+                                                           want_feat_refined=self.materialize_features,
+                                                           feat_staged=feat_staged)
         B, V, J, H, W = list_hm[-1].shape
         pts2d, maxvals, valid = ops.get_max_preds(list_hm[-1].view(B * V, J, H, W), threshold=0.5, normalize=False)
         preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, staged=self.heatmap.last_staged)
@@ -73,6 +76,30 @@ class HotPathPipeline:
             feat[i:i + chunk].copy_(f)                   # cast + back to the NCHW layout of the module interface
             bfb[i:i + chunk].copy_(bb[-1])
         return feat, bfb
+
+    @torch.no_grad()
+    def backbone_staged(self, img, chunk=128):
+        """backbone() for a chained forward (second half): the FPN output of a channels-last bf16 backbone
+        already IS the layout the hot path reads, so it is handed over as such instead of being cast back to NCHW fp32
+        and re-staged.  The two stereo backbones run on view-major batches (frames are independent: eval-mode BatchNorm).
+        -> (feat_staged bf16 [V,B,64,64,128] view-major channels-last, bfb fp32 [B,V,512,8,8])"""
+        assert self.V == 4 and self.precision == "bf16"
+        if not getattr(self, "_bb_cl", False):
+            for n in ("heatmap_estimator_stereo_front", "heatmap_estimator_stereo_back"):
+                getattr(self.heatmap, n).to(memory_format=torch.channels_last)
+            self._bb_cl = True
+        B = img.shape[0]
+        xh = torch.empty((self.V, B, 64, 64, 128), dtype=torch.bfloat16, device=img.device)
+        bfb = torch.empty((B, self.V, 512, 8, 8), dtype=torch.float32, device=img.device)
+        for p, name in enumerate(("heatmap_estimator_stereo_front", "heatmap_estimator_stereo_back")):
+            est = getattr(self.heatmap, name)
+            for i in range(0, B, chunk):
+                im = img[i:i + chunk, 2 * p:2 * p + 2].transpose(0, 1)             # [2, b, 3, H, W]: view-major batch
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    f, bb = est.forward_backbone(im)                              # f [2, b, 128, 64, 64], NHWC memory
+                xh[2 * p:2 * p + 2, i:i + chunk].copy_(f.permute(0, 1, 3, 4, 2))     # same memory order: a plain copy
+                bfb[i:i + chunk, 2 * p:2 * p + 2].copy_(bb[-1].transpose(0, 1))
+        return xh, bfb
 
     # ---- latency mode: the whole forward as one CUDA graph ----
     def capture(self, B, with_coord_trans_mat=False):

@@ -211,6 +211,12 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
 int egr_mvfex_export_staged(egr_mvfex* h, int mode);   /* 0 off, 1 + TF32 copy, 2 activation-dtype copies only, 3 + fp16 copy, 4 */
 int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const void** refined_nhwc_hp,
                      int* act_is_bf16);
+/* Input hint for a producer that already emits the layout the kernels read (a channels-last bf16 backbone):
+ * feat_vmajor_nhwc_bf16 = [V][B][64*64][128] bf16, view-major.  One-shot: the next egr_mvfex_forward skips its
+ * NCHW fp32 -> channels-last staging pass, reads this buffer instead (it must stay valid until that forward and any
+ * chained pose3d forward have completed) and accepts feat == NULL.  bf16 precision only; results are bit-identical to
+ * passing the fp32 NCHW tensor whose bf16 rounding this buffer holds. */
+int egr_mvfex_use_staged_input(egr_mvfex* h, const void* feat_vmajor_nhwc_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
  * ("q1", "xT", "t1", "ff", ...); EGR_ERR_INVALID for unknown names */
 int egr_mvfex_debug_buffer(egr_mvfex* h, const char* name, void** ptr, int64_t* bytes);

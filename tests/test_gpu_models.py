@@ -290,6 +290,48 @@ def test_pose3d_proposal_branch_types(case, fp16):
         engine.set_option("pose_p2_fp16", 1)
 
 
+def test_staged_input_is_bit_identical():
+    """egr_mvfex_use_staged_input: feeding the view-major channels-last bf16 copy a bf16 backbone leaves gives exactly
+    the results of feeding the fp32 NCHW tensor it was rounded from (the engine's own staging pass does that rounding),
+    with and without materialised NCHW outputs; the chained pose3d works with no NCHW feature tensor at all."""
+    from egorear_b200 import synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    feat, bfb = synth.synth_features(3, 4, seed=21)
+    feat, bfb = feat.to(dev), bfb.to(dev)
+    xh = feat.to(torch.bfloat16).permute(1, 0, 3, 4, 2).contiguous()          # [V, B, 64, 64, 128]
+    for mat in (False, True):
+        pipe = HotPathPipeline(4, "ego4view_syn", "bf16", dev, materialize_features=mat)
+        ref = pipe(feat, bfb)
+        got = pipe.forward(None, bfb, feat_staged=xh)
+        assert got["list_ff"][0] is None
+        assert torch.equal(got["packed"], ref["packed"])
+        for a, b in zip(got["list_hm"], ref["list_hm"]):
+            assert torch.equal(a, b)
+        assert torch.equal(got["list_pose3d"], ref["list_pose3d"]) if isinstance(ref["list_pose3d"], torch.Tensor) else \
+            all(torch.equal(a, b) for a, b in zip(got["list_pose3d"], ref["list_pose3d"]))
+        if mat:
+            assert torch.equal(got["list_ff"][1], ref["list_ff"][1])
+        again = pipe(feat, bfb)                                               # the hint is one-shot
+        assert torch.equal(again["packed"], ref["packed"])
+    with pytest.raises(RuntimeError, match="bf16 precision"):
+        HotPathPipeline(4, "ego4view_syn", "fp32", dev).forward(None, bfb, feat_staged=xh)
+
+
+def test_backbone_staged_matches_backbone():
+    """backbone_staged() (view-major batches, channels-last bf16 output kept as is) == backbone() (cast to NCHW fp32)"""
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    pipe = HotPathPipeline(4, "ego4view_rw", "bf16", dev, with_backbone=True, materialize_features=False)
+    img = torch.randn(3, 4, 3, 256, 256, generator=torch.Generator().manual_seed(4)).to(dev)
+    feat, bfb = pipe.backbone(img)
+    xh, bfb2 = pipe.backbone_staged(img)
+    assert xh.shape == (4, 3, 64, 64, 128) and xh.dtype == torch.bfloat16 and xh.is_contiguous()
+    back = xh.permute(1, 0, 4, 2, 3).float()
+    assert float((back - feat).abs().max()) <= 2e-2 * float(feat.abs().max())
+    assert float((bfb2 - bfb).abs().max()) <= 2e-2 * float(bfb.abs().max())
+
+
 def test_no_writes_outside_outputs_and_workspace(monkeypatch):
     """compute-sanitizer is not available on the GPU pool, so out-of-bounds WRITES are caught here: every tensor the
     package allocates during a chained forward (outputs, workspaces, gathers) is carved out of a larger byte buffer with
