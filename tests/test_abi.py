@@ -106,3 +106,12 @@ def test_resample_coefficient_table_matches_oracle(lib):
         assert lib.egr_resample_coeffs(n_in, n_out, ctypes.byref(ks), bounds.ctypes.data, kk.ctypes.data) == 0
         rb, rk, rks = pr.precompute_coeffs(n_in, n_out)
         assert ks.value == rks and np.array_equal(bounds, rb) and np.array_equal(kk, rk), (n_in, n_out)
+
+
+def test_header_is_plain_c():
+    """the ABI header must be consumable from C (cgo / JNI / ctypes generators): C99, no C++ constructs outside extern "C" """
+    import subprocess
+    src = '#include "include/egorear_b200.h"\nint main(void) { return 0; }\n'
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", ROOT, "-x", "c", "-"], input=src,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
