@@ -80,6 +80,7 @@ SIGNATURES = {
                                    c_void_p]),
     "egr_pack_joints": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "egr_resample_coeffs": (c_int, [c_int, c_int, POINTER(c_int), c_void_p, c_void_p]),
+    "egr_resample_digits": (c_int, [c_int, c_int, POINTER(c_int), c_void_p]),
     "egr_preprocess_images": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),
                                       c_void_p, c_void_p, c_void_p]),
     "egr_eval_heatmap_workspace_bytes": (ctypes.c_size_t, [c_int64, c_int, c_int]),

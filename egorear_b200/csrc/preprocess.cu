@@ -333,6 +333,16 @@ extern "C" int egr_resample_coeffs(int in_size, int out_size, int* ksize, int* b
     return EGR_OK;
 }
 
+// host-only: the packed signed-byte digit words the kernel's dp4a path reads ([out][ks4][4]: d0, d1, d2, pad)
+extern "C" int egr_resample_digits(int in_size, int out_size, int* ks4, uint32_t* digits) {
+    EGR_CHECK(in_size > 0 && out_size > 0 && ks4, EGR_ERR_INVALID, "resample_digits: sizes must be positive");
+    ResampleTable t;
+    build_table(in_size, out_size, t);
+    *ks4 = t.ks4;
+    if (digits) std::copy(t.digits.begin(), t.digits.end(), digits);
+    return EGR_OK;
+}
+
 extern "C" int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, int Win, int Hout, int Wout,
                                      const float* mean3_host, const float* std3_host, float* out, uint8_t* resized_u8,
                                      void* stream) {

@@ -308,6 +308,10 @@ int egr_eval_pose(const float* pred, const float* gt, int64_t B, int J, float un
  * *ksize = taps per output; bounds [out_size][2] = (first input index, tap count); kk [out_size][ksize] 22-bit fixed
  * point.  bounds / kk may be NULL (query ksize first). */
 int egr_resample_coeffs(int in_size, int out_size, int* ksize, int* bounds, int* kk);
+/* host-only: the same coefficients as the kernel's dp4a operands: *ks4 = ceil(ksize / 4) steps per output; digits
+ * [out_size][ks4][4] words = {d0, d1, d2, 0}, each packing the signed 8-bit digits of 4 consecutive taps, with
+ * k = d0 + 256 * d1 + 65536 * d2.  digits may be NULL (query ks4 first). */
+int egr_resample_digits(int in_size, int out_size, int* ks4, uint32_t* digits);
 int egr_preprocess_images(const uint8_t* images, int64_t N, int Hin, int Win, int Hout, int Wout, const float* mean3_host,
                           const float* std3_host, float* out, uint8_t* resized_u8, void* stream);
 

@@ -106,6 +106,21 @@ def test_resample_coefficient_table_matches_oracle(lib):
         assert lib.egr_resample_coeffs(n_in, n_out, ctypes.byref(ks), bounds.ctypes.data, kk.ctypes.data) == 0
         rb, rk, rks = pr.precompute_coeffs(n_in, n_out)
         assert ks.value == rks and np.array_equal(bounds, rb) and np.array_equal(kk, rk), (n_in, n_out)
+        # the kernel's dp4a operands: three signed 8-bit digits per coefficient, 4 taps per word, exact recombination
+        ks4 = ctypes.c_int(0)
+        assert lib.egr_resample_digits(n_in, n_out, ctypes.byref(ks4), None) == 0 and ks4.value == (rks + 3) // 4
+        dig = np.zeros((n_out, ks4.value, 4), np.uint32)
+        assert lib.egr_resample_digits(n_in, n_out, ctypes.byref(ks4), dig.ctypes.data) == 0
+        d = dig.view(np.int8).reshape(n_out, ks4.value, 4, 4).astype(np.int64)       # [out][step][word][tap]
+        rec = (d[:, :, 0] + 256 * d[:, :, 1] + 65536 * d[:, :, 2]).reshape(n_out, -1)
+        full = np.zeros_like(rec)
+        full[:, :rks] = rk
+        assert np.array_equal(rec, full) and not d[:, :, 3].any(), (n_in, n_out)
+        # dp4a emulation of one output row reproduces the int32 accumulator of the plain fixed-point sum
+        px = np.random.default_rng(n_in).integers(0, 256, rec.shape[1])
+        for xx in (0, n_out // 2, n_out - 1):
+            parts = [(px.reshape(-1, 4) * d[xx, :, w]).sum() for w in range(3)]
+            assert parts[0] + 256 * parts[1] + 65536 * parts[2] == (px * full[xx]).sum()
 
 
 def test_header_is_plain_c():
