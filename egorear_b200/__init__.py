@@ -66,8 +66,8 @@ def patch(precision="bf16", modules=None, strict=False):
     PATCH_TABLE that fails to import raises.  Returns {module name: [names rebound]}.
     Fails loudly (ImportError) when libegorear_b200.so has not been built.
     """
-    if precision not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
+    if precision not in ("bf16", "fp16", "fp32"):
+        raise ValueError("precision must be 'bf16', 'fp16' or 'fp32'")
     from . import _lib, modules as M, ops
     _lib.load()
     repl = {"get_max_preds": ops.get_max_preds, "generate_target": ops.generate_target,

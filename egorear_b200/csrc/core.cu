@@ -127,7 +127,8 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
     GemmDesc d;
     d.A = c->A; d.W = c->W; d.bias = c->bias; d.D = c->D; d.aux = c->aux;
     d.M = c->M; d.N = c->N; d.K = c->K; d.lda = c->lda; d.ldd = c->ldd; d.amode = c->amode; d.epi = c->epi;
-    d.kblk = c->kblk; d.kblk_stride = c->kblk_stride;
+    d.kblk = c->kblk; d.kblk_stride = c->kblk_stride; d.ka = c->ka;
+    EGR_CHECK(d.ka == 0 || c->use_tc, EGR_ERR_UNSUPPORTED, "dense_stage: split operands (ka) need the tensor-core kernel");
     d.Hin = c->Hin; d.Win = c->Win; d.Cin = c->Cin; d.Hout = c->Hout; d.Wout = c->Wout;
     d.groups = c->groups > 0 ? c->groups : 1;
     d.a_gs = c->a_gs; d.w_gs = c->w_gs; d.b_gs = c->b_gs; d.d_gs = c->d_gs; d.aux_gs = c->aux_gs;

@@ -79,18 +79,29 @@ struct WMat {
     __half* f16 = nullptr;
     float* bias = nullptr;    // [sets][N]
     int N = 0, K = 0, sets = 0;
+    int kw = 1;               // EGR_PREC_FP16: f16 holds [N][kw*K] = [W_hi | W_lo] when kw == 2 (split weights, gemm.cuh `ka`)
+    // fp32-grade token Linears (EGR_PREC_FP16): f32x3 [sets][N][3K] = [W_hi | W_hi | W_lo] in TF32 values; A is [x | x_lo]
+    float* f32x3 = nullptr;
     const void* w(int prec_bf16_tc) const { return prec_bf16_tc ? (const void*)bf16 : (const void*)f32; }
     int64_t stride() const { return (int64_t)N * K; }
 };
 
 extern int g_opt_tc;   // 1: bf16 precision uses the tcgen05 kernel; 0: bf16 activations through the SIMT kernel (debug)
+extern int g_opt_wsplit;   // EGR_PREC_FP16: 0 single fp16 weights, 1 (default) hi + lo pairs for 1x1 / Linear weights, 2 also the 3x3 convs
+extern int g_opt_tok3x;    // EGR_PREC_FP16: mvfex token Linears as "3x TF32" (default 1)
+
+inline bool is16(int prec) { return prec == EGR_PREC_BF16 || prec == EGR_PREC_FP16; }
+inline int act_code(int prec) { return prec == EGR_PREC_BF16 ? 1 : prec == EGR_PREC_FP16 ? 2 : 0; }     // 0 fp32, 1 bf16, 2 fp16
+inline int stage_mode(int prec) { return prec == EGR_PREC_FP16 ? 3 : prec == EGR_PREC_BF16 ? 1 : 0; }    // nchw_to_nhwc out_mode
 
 // internal stage precision on top of the public EGR_PREC_*: fp32 activations and weights through the tensor cores as
 // TF32 (10-bit mantissa, fp32 accumulate) — used where bf16 operands would eat the 0.1 mm MPJPE budget (pose3d P2)
 constexpr int PREC_TF32 = 2;
 // fp16 activations and weights (kind::f16): TF32's 10-bit mantissa at half the bytes and twice the MMA rate; range
 // |x| < 65504 (conversions saturate) — the default of the pose3d proposal branch in EGR_PREC_BF16 (option "pose_p2_fp16")
-constexpr int PREC_FP16 = 3;
+constexpr int PREC_FP16 = 3;      // == EGR_PREC_FP16 (public since round 2: every 16-bit dense stage in fp16, split 1x1 weights)
+// token Linears of EGR_PREC_FP16: "3x TF32" (see gemm.cuh `ka`), A buffers hold [x | x_lo] rows of 2K floats
+constexpr int PREC_TF32X3 = 4;
 
 // run one dense stage in the handle's precision.  `out_f32`: the output stays fp32 even in bf16 mode.
 // `out16`: DT_F16 makes a bf16-mode tensor-core stage write fp16 instead of bf16 (interpolated right afterwards in half2).
@@ -100,11 +111,22 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
     d.N = w.N;
     d.K = w.K;
     if (prec == PREC_FP16) {
-        d.W = w.f16 + (int64_t)set_begin * w.stride();
+        d.K = w.K * w.kw;
+        d.ka = (w.kw > 1) ? w.K : 0;
+        d.W = w.f16 + (int64_t)set_begin * w.stride() * w.kw;
         d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
-        d.w_gs = w.stride();
+        d.w_gs = w.stride() * w.kw;
         d.b_gs = w.N;
         return gemm_tc(d, DT_F16, out_f32 ? DT_F32 : DT_F16, st);
+    }
+    if (prec == PREC_TF32X3) {      // caller: d.lda = 2K (rows [x | x_lo])
+        d.K = 3 * w.K;
+        d.ka = 2 * w.K;
+        d.W = w.f32x3 + (int64_t)set_begin * w.stride() * 3;
+        d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
+        d.w_gs = w.stride() * 3;
+        d.b_gs = w.N;
+        return gemm_tc(d, DT_F32, DT_F32, st);
     }
     if (prec == PREC_TF32 && g_opt_tc) {
         d.W = w.f32 + (int64_t)set_begin * w.stride();

@@ -12,6 +12,8 @@
 namespace egr {
 int g_opt_tc = 1;
 int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
+int g_opt_wsplit = 1;
+int g_opt_tok3x = 1;
 extern int g_opt_pose_p2_bf16;
 extern int g_opt_pose_p2_fp16;
 extern int g_opt_ws;
@@ -51,6 +53,7 @@ struct egr_mvfex {
     const void* in_staged = nullptr;           // one-shot: the caller's view-major channels-last bf16 copy of the input features
     const void* st_refined_hp = nullptr;
     bool tokb = false;
+    bool tok3x = false;                        // EGR_PREC_FP16: token operand rows [x | x_lo], weights [W_hi | W_hi | W_lo]
     WMat tk_hp2, tk_fcq, tk_bfb, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
     const __nv_bfloat16** d_ptab16 = nullptr;  // device [4]: bf16 copies of the sampled position tables
     const float** d_ptrs = nullptr;            // device [TP_COUNT][4]
@@ -99,6 +102,13 @@ int make_wmat(egr_mvfex* h, WMat& m, int sets, int N, int K, WKind kind, KeyFn k
     if (h->prec == EGR_PREC_BF16) {
         if (int rc = h->pool.alloc(&m.bf16, (int64_t)sets * N * K)) return rc;
         if (int rc = cast_bf16(m.f32, m.bf16, (int64_t)sets * N * K, st)) return rc;
+    } else if (h->prec == EGR_PREC_FP16 && kind != W_PAD16) {
+        // fp16 operands; 1x1 / Linear weights as a hi + lo pair along K (gemm.cuh `ka`), the tensor-bound 3x3 convs single
+        const bool split = (kind == W_CONV3) ? g_opt_wsplit >= 2 : g_opt_wsplit >= 1;
+        m.kw = split ? 2 : 1;
+        if (int rc = h->pool.alloc(&m.f16, (int64_t)sets * N * K * m.kw)) return rc;
+        if (split) { if (int rc = split_f16(m.f32, m.f16, (int64_t)sets * N, K, st)) return rc; }
+        else if (int rc = cast_f16(m.f32, m.f16, (int64_t)sets * N * K, st)) return rc;
     }
     return EGR_OK;
 }
@@ -178,7 +188,9 @@ enum TokPtr { TP_LNC_W, TP_LNC_B, TP_LNS_W, TP_LNS_B, TP_LNF_W, TP_LNF_B, TP_PN_
 
 // carve the workspace for B frames and G refiner groups (G = V for the full forward, 1 for one refiner)
 int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, void* base, int64_t cap, Bufs* o) {
-    const int64_t s = (h->prec == EGR_PREC_BF16) ? 2 : 4;
+    const int64_t s = is16(h->prec) ? 2 : 4;
+    const bool f16m = h->prec == EGR_PREC_FP16;        // the activation copy of the refined features IS the fp16 copy pose3d reads
+    const int sp2 = h->tok3x ? 2 : 1;                  // token operand rows [x | x_lo]
     const int V = h->V, J = h->J;
     const int Gh = with_heads ? (V > G ? V : G) : G;   // heads run over all views
     Carver c(base, cap);
@@ -192,26 +204,26 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.z = c.take((int64_t)Gh * B * 1024 * 128 * s);
     b.ff = c.take((int64_t)G * B * 1024 * 128 * s);
     b.r1a = c.take((int64_t)G * B * 1024 * 128 * s);
-    b.refn = (h->refn_f16_only && G == V) ? nullptr : c.take((int64_t)G * B * FHW * FC * s);
+    b.refn = (!f16m && h->refn_f16_only && G == V) ? nullptr : c.take((int64_t)G * B * FHW * FC * s);
     b.hmT = c.take((int64_t)Gh * B * J * FHW * s);
     b.xT = c.take((int64_t)G * B * NPOS * 16 * s);
     b.h1t = c.take((int64_t)G * B * NPOS * 64 * s);
     b.t1 = c.take((int64_t)G * B * NPOS * 128 * s);
-    b.q1 = (float*)c.take((int64_t)G * B * J * EMB * 4);
+    b.q1 = (float*)c.take((int64_t)G * B * J * EMB * 4 * sp2);
     b.anch = (float*)c.take((int64_t)B * V * J * 2 * 4);
     b.maxv = (float*)c.take((int64_t)B * V * J * 4);
     b.valid = (uint8_t*)c.take((int64_t)B * V * J);
-    b.refn_hp = (h->export_staged && h->export_hp && G == V) ? c.take((int64_t)G * B * FHW * FC * (h->export_hp == 2 ? 2 : 4)) : nullptr;
+    b.refn_hp = (!f16m && h->export_staged && h->export_hp && G == V) ? c.take((int64_t)G * B * FHW * FC * (h->export_hp == 2 ? 2 : 4)) : nullptr;
     if (h->tokb) {
         const int64_t T = (int64_t)B * J;
-        b.tx = (float*)c.take(G * T * EMB * 4);
+        b.tx = (float*)c.take(G * T * EMB * 4 * sp2);
         b.tz = (float*)c.take(G * T * EMB * 4);
         b.toa = (float*)c.take(G * T * TOK_OA * 4);
-        b.tA = (float*)c.take(G * T * V * h->KA * 4);
+        b.tA = (float*)c.take(G * T * V * h->KA * 4 * sp2);
         b.tqkv = (float*)c.take(G * T * 3 * EMB * 4);
-        b.to = (float*)c.take(G * T * EMB * 4);
-        b.thid = (float*)c.take(G * T * TOK_FF * 4);
-        b.tpool = (float*)c.take((int64_t)G * B * 512 * 4);
+        b.to = (float*)c.take(G * T * EMB * 4 * sp2);
+        b.thid = (float*)c.take(G * T * TOK_FF * 4 * sp2);
+        b.tpool = (float*)c.take((int64_t)G * B * 512 * 4 * sp2);
         b.tvb = (float*)c.take((int64_t)G * B * EMB * 4);
     }
     b.splitk = (float*)c.take(SPLITK_SCRATCH_BYTES);
@@ -296,46 +308,52 @@ int run_tokens_batched(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const 
                        const float* anchors, const uint8_t* valid, cudaStream_t st) {
     const int J = h->J, V = h->V, E = EMB, KA = h->KA;
     const int T = B * J;
-    const int bf = (h->prec == EGR_PREC_BF16);
     const float* const* P = h->d_ptrs;
     auto ptr = [&](int which) { return P + which * 4 + r0; };
     int rc;
-    auto gemm = [&](const float* A, int K, const WMat& W, float* D, int epi, int rnd) {
+    // sp: EGR_PREC_FP16 runs the token Linears as "3x TF32" (gemm.cuh `ka`): every GEMM operand row is [x | x_lo] (2K floats),
+    // written by its producer kernel, or by tok_make_lo after a GEMM epilogue (`operand` outputs: ldd = 2N)
+    const int sp = h->tok3x ? 1 : 0;
+    const int tprec = sp ? PREC_TF32X3 : PREC_TF32;
+    auto gemm = [&](const float* A, int K, const WMat& W, float* D, int epi, int rnd, bool operand) -> int {
         GemmDesc d;
-        d.A = A; d.lda = K; d.M = T; d.D = D; d.ldd = W.N; d.epi = epi; d.round_tf32 = rnd;
-        d.groups = G; d.a_gs = (int64_t)T * K; d.d_gs = (int64_t)T * W.N;
-        return run_gemm(d, W, r0, PREC_TF32, true, st);
+        const int64_t ldd = (int64_t)W.N * ((sp && operand) ? 2 : 1);
+        d.A = A; d.lda = (int64_t)K * (1 + sp); d.M = T; d.D = D; d.ldd = ldd; d.epi = epi; d.round_tf32 = sp ? 0 : rnd;
+        d.groups = G; d.a_gs = (int64_t)T * K * (1 + sp); d.d_gs = (int64_t)T * ldd;
+        if (int r = run_gemm(d, W, r0, tprec, true, st)) return r;
+        return (sp && operand) ? tok_make_lo(D, (int64_t)G * T, W.N, st) : EGR_OK;
     };
     // heatmap_proj.2, + fc_bfb(avgpool) + joint embed, fc_query + ReLU
-    if ((rc = gemm(w.q1, E, h->tk_hp2, w.tz, EPI_NONE, 0))) return rc;
-    if ((rc = tok_avgpool(bfb, bfb_bs, bfb_gs, 64, w.tpool, G, B, 512, st))) return rc;
+    if ((rc = gemm(w.q1, E, h->tk_hp2, w.tz, EPI_NONE, 0, false))) return rc;
+    if ((rc = tok_avgpool(bfb, bfb_bs, bfb_gs, 64, w.tpool, G, B, 512, st, sp))) return rc;
     {
         GemmDesc d;
-        d.A = w.tpool; d.lda = 512; d.M = B; d.D = w.tvb; d.ldd = E; d.groups = G; d.a_gs = (int64_t)B * 512; d.d_gs = (int64_t)B * E;
-        if ((rc = run_gemm(d, h->tk_bfb, r0, PREC_TF32, true, st))) return rc;
+        d.A = w.tpool; d.lda = 512 * (1 + sp); d.M = B; d.D = w.tvb; d.ldd = E; d.groups = G; d.a_gs = (int64_t)B * 512 * (1 + sp);
+        d.d_gs = (int64_t)B * E;
+        if ((rc = run_gemm(d, h->tk_bfb, r0, tprec, true, st))) return rc;
     }
-    if ((rc = tok_add_query(w.tz, w.tvb, ptr(TP_JQ), w.to, G, B, J, E, st))) return rc;
-    if ((rc = gemm(w.to, E, h->tk_fcq, w.tx, EPI_RELU, 1))) return rc;
+    if ((rc = tok_add_query(w.tz, w.tvb, ptr(TP_JQ), w.to, G, B, J, E, st, sp))) return rc;
+    if ((rc = gemm(w.to, E, h->tk_fcq, w.tx, EPI_RELU, 1, true))) return rc;
     // A1: offsets + logits, sampling, folded value/output/fuse GEMM, residual + LN
-    if ((rc = gemm(w.tx, E, h->tk_sa, w.toa, EPI_NONE, 0))) return rc;
+    if ((rc = gemm(w.tx, E, h->tk_sa, w.toa, EPI_NONE, 0, false))) return rc;
     TokSampleArgs sa{};
     sa.G = G; sa.B = B; sa.V = V; sa.J = J; sa.H = FH; sa.W = FW; sa.E = E; sa.KA = KA; sa.oa = w.toa; sa.anchors = anchors;
-    sa.valid = valid; sa.X = w.Xh; sa.ptab = h->d_ptab16 + r0; sa.A = w.tA;
-    if ((rc = tok_sample(sa, bf, st))) return rc;
-    if ((rc = gemm(w.tA, V * KA, h->tk_c, w.tz, EPI_NONE, 0))) return rc;
-    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNC_W), ptr(TP_LNC_B), st))) return rc;
+    sa.valid = valid; sa.X = w.Xh; sa.ptab = h->d_ptab16 + r0; sa.A = w.tA; sa.split = sp;
+    if ((rc = tok_sample(sa, act_code(h->prec), st))) return rc;
+    if ((rc = gemm(w.tA, V * KA, h->tk_c, w.tz, EPI_NONE, 0, false))) return rc;
+    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNC_W), ptr(TP_LNC_B), st, sp))) return rc;
     // A2: joint self-attention
-    if ((rc = gemm(w.tx, E, h->tk_qkv, w.tqkv, EPI_NONE, 0))) return rc;
-    if ((rc = tok_attn(w.tqkv, w.to, G * B, J, E, st))) return rc;
-    if ((rc = gemm(w.to, E, h->tk_o, w.tz, EPI_NONE, 0))) return rc;
-    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNS_W), ptr(TP_LNS_B), st))) return rc;
+    if ((rc = gemm(w.tx, E, h->tk_qkv, w.tqkv, EPI_NONE, 0, false))) return rc;
+    if ((rc = tok_attn(w.tqkv, w.to, G * B, J, E, st, sp))) return rc;
+    if ((rc = gemm(w.to, E, h->tk_o, w.tz, EPI_NONE, 0, false))) return rc;
+    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNS_W), ptr(TP_LNS_B), st, sp))) return rc;
     // A3: FFN
-    if ((rc = gemm(w.tx, E, h->tk_f1, w.thid, EPI_GELU, 1))) return rc;
-    if ((rc = gemm(w.thid, TOK_FF, h->tk_f2, w.tz, EPI_NONE, 0))) return rc;
-    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNF_W), ptr(TP_LNF_B), st))) return rc;
+    if ((rc = gemm(w.tx, E, h->tk_f1, w.thid, EPI_GELU, 1, true))) return rc;
+    if ((rc = gemm(w.thid, TOK_FF, h->tk_f2, w.tz, EPI_NONE, 0, false))) return rc;
+    if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNF_W), ptr(TP_LNF_B), st, sp))) return rc;
     // post_norm + token image + T1 (1x1 15->64 ReLU, 1x1 64->128) in one tensor-core kernel
     return tok_head_tc(w.tx, G, B, J, ptr(TP_PN_W), ptr(TP_PN_B), h->t1_0.f32, h->t1_0.bias, h->t1_3.f32, h->t1_3.bias, r0,
-                       w.t1, st);
+                       w.t1, st, E * (1 + sp), h->prec == EGR_PREC_FP16);
 }
 
 // the refiner chain for G groups whose weights start at refiner r0
@@ -344,14 +362,17 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
                  int64_t hm_gs, float* feat_refined, int64_t ft_bs, int64_t ft_gs, cudaStream_t st) {
     const int prec = h->prec, J = h->J;
     const int bf = (prec == EGR_PREC_BF16);
+    const bool f16m = (prec == EGR_PREC_FP16);
     int rc;
     GemmDesc d;
     EGR_MARK("Q1a", st);
-    // Q1a: relu(heatmap_proj.0(heatmap))  [G][B*J][4096] -> [G][B*J][256] fp32
+    // Q1a: relu(heatmap_proj.0(heatmap))  [G][B*J][4096] -> [G][B*J][256] fp32 (rows [x | x_lo] for the 3x-TF32 token Linears)
     d = GemmDesc();
-    d.A = w.hmT; d.lda = FHW; d.M = B * J; d.D = w.q1; d.ldd = EMB; d.epi = EPI_RELU; d.round_tf32 = h->tokb ? 1 : 0;
-    d.groups = G; d.a_gs = (int64_t)B * J * FHW; d.d_gs = (int64_t)B * J * EMB;
+    const int q1w = EMB * (h->tok3x ? 2 : 1);
+    d.A = w.hmT; d.lda = FHW; d.M = B * J; d.D = w.q1; d.ldd = q1w; d.epi = EPI_RELU; d.round_tf32 = (h->tokb && !h->tok3x) ? 1 : 0;
+    d.groups = G; d.a_gs = (int64_t)B * J * FHW; d.d_gs = (int64_t)B * J * q1w;
     if ((rc = run_gemm(d, h->hp0, r0, prec, /*out_f32=*/true, st))) return rc;
+    if (h->tok3x && (rc = tok_make_lo(w.q1, (int64_t)G * B * J, EMB, st))) return rc;
     EGR_MARK("tokens", st);
     // Q1 rest + A1 A2 A3 + post_norm
     MvfTokenArgs ta{};
@@ -408,13 +429,13 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     if ((rc = run_gemm(d, h->r1_0, r0, prec, false, st))) return rc;
     EGR_MARK("R1b", st);
     // on the tensor-core path the pre-upsample maps z are written in fp16 so that the tails interpolate in half2
-    const bool z16 = bf && g_opt_tc;
+    const bool z16 = is16(prec) && g_opt_tc;
     d.A = w.r1a; d.D = w.z; d.epi = EPI_NONE;
     if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("R1tail", st);
     // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output (optional) + channels-last copies for H2 / pose3d
-    if ((rc = up2_relu_dual(w.z, z16 ? 2 : bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, bf ? 1 : 3, w.refn_hp,
-                            h->export_hp == 2 ? 2 : 0, st))) return rc;
+    if ((rc = up2_relu_dual(w.z, z16 ? 2 : bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, f16m ? 2 : bf ? 1 : 3, w.refn_hp,
+                            h->export_hp == 2 ? 2 : 0, st, f16m ? 1 : 0))) return rc;
     EGR_MARK("H2a", st);
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
@@ -438,7 +459,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     if ((rc = run_gemm(d, h->h2_5, r0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("H2tail", st);
     int wsel[4] = {r0, r0 + 1, r0 + 2, r0 + 3};
-    if ((rc = head_up_conv(w.z, z16 ? 2 : bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
+    if ((rc = head_up_conv(w.z, f16m ? 3 : z16 ? 2 : bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
         return rc;
     EGR_MARK(nullptr, st);
     return EGR_OK;
@@ -447,9 +468,9 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
 void note(egr_mvfex* h, const char* name, void* p, int64_t bytes) { h->dbg[name] = std::make_pair(p, bytes); }
 
 void note_all(egr_mvfex* h, const Bufs& w, int B, int G) {
-    const int64_t s = (h->prec == EGR_PREC_BF16) ? 2 : 4;
+    const int64_t s = is16(h->prec) ? 2 : 4;
     note(h, "Xh", w.Xh, (int64_t)h->V * B * FHW * FC * s);
-    note(h, "q1", w.q1, (int64_t)G * B * h->J * EMB * 4);
+    note(h, "q1", w.q1, (int64_t)G * B * h->J * EMB * 4 * (h->tok3x ? 2 : 1));
     note(h, "xT", w.xT, (int64_t)G * B * NPOS * 16 * s);
     note(h, "t1", w.t1, (int64_t)G * B * NPOS * 128 * s);
     note(h, "ff", w.ff, (int64_t)G * B * 1024 * 128 * s);
@@ -468,6 +489,8 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "ws") { g_opt_ws = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pdl") { g_opt_pdl = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "tok_batched") { g_opt_tok_batched = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "wsplit") { g_opt_wsplit = value < 0 ? 0 : value > 2 ? 2 : value; return EGR_OK; }
+    if (key && std::string(key) == "tok3x") { g_opt_tok3x = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }
 
@@ -476,12 +499,16 @@ extern "C" int egr_mvfex_create(int num_views, int num_heatmap, float heatmap_th
     EGR_CHECK(num_views == 2 || num_views == 4, EGR_ERR_UNSUPPORTED,
               "mvfex: num_views=%d (shipped configs use 4, or 2 for stereo-front)", num_views);
     EGR_CHECK(num_heatmap == 15, EGR_ERR_UNSUPPORTED, "mvfex: num_heatmap=%d (shipped configs use 15)", num_heatmap);
-    EGR_CHECK(precision == EGR_PREC_FP32 || precision == EGR_PREC_BF16, EGR_ERR_INVALID, "mvfex: precision %d", precision);
+    EGR_CHECK(precision == EGR_PREC_FP32 || precision == EGR_PREC_BF16 || precision == EGR_PREC_FP16, EGR_ERR_INVALID,
+              "mvfex: precision %d", precision);
+    EGR_CHECK(precision != EGR_PREC_FP16 || (g_opt_tc && g_opt_tok_batched), EGR_ERR_UNSUPPORTED,
+              "mvfex: EGR_PREC_FP16 is a tensor-core mode (options tc / tok_batched must be on)");
     if (int rc = require_device()) return rc;
     egr_mvfex* h = new egr_mvfex();
     h->V = num_views; h->J = num_heatmap; h->thr = heatmap_threshold; h->prec = precision;
     h->head_sets = (num_views == 2) ? 1 : 2;
-    h->tokb = (precision == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    h->tokb = is16(precision) && g_opt_tc && g_opt_tok_batched;
+    h->tok3x = precision == EGR_PREC_FP16 && g_opt_tok3x;
     h->KA = tok_ka(EMB, true);
     *out = h;
     return EGR_OK;
@@ -510,10 +537,13 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
     h->packed = false;
     const int V = h->V, J = h->J;
     int rc;
-    if (h->prec == EGR_PREC_BF16 && g_opt_tc) {
+    if (is16(h->prec) && g_opt_tc) {
         if ((rc = gemm_tc_init())) return rc;
     }
-    h->tokb = (h->prec == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    EGR_CHECK(h->prec != EGR_PREC_FP16 || (g_opt_tc && g_opt_tok_batched), EGR_ERR_UNSUPPORTED,
+              "mvfex: EGR_PREC_FP16 is a tensor-core mode (options tc / tok_batched must be on)");
+    h->tokb = is16(h->prec) && g_opt_tc && g_opt_tok_batched;
+    h->tok3x = h->prec == EGR_PREC_FP16 && g_opt_tok3x;
     h->KA = tok_ka(EMB, true);
     auto head = [&](const char* sub) { return [sub](int s) { return std::string(kHead[s]) + sub; }; };
     auto ref = [&](const char* sub) { return [sub](int s) { return std::string(kRefiner4[s]) + sub; }; };
@@ -601,17 +631,22 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
         std::vector<const __nv_bfloat16*> pt16(4, nullptr);
         for (int r = 0; r < V; ++r) {
             if (!h->has_ref[r]) continue;
-            __nv_bfloat16* t16 = nullptr;
+            __nv_bfloat16* t16 = nullptr;      // 16-bit copy in the activation type (fp16 values behind the bf16 pointer type in EGR_PREC_FP16)
             if ((rc = h->pool.alloc(&t16, (int64_t)V * FHW * E))) return rc;
-            if ((rc = cast_bf16(tok[r].layer.ptab, t16, (int64_t)V * FHW * E, st))) return rc;
+            if (h->prec == EGR_PREC_FP16) { if ((rc = cast_f16(tok[r].layer.ptab, reinterpret_cast<__half*>(t16), (int64_t)V * FHW * E, st))) return rc; }
+            else if ((rc = cast_bf16(tok[r].layer.ptab, t16, (int64_t)V * FHW * E, st))) return rc;
             pt16[r] = t16;
         }
         if ((rc = h->pool.alloc(&h->d_ptab16, 4))) return rc;
         EGR_CUDA_OK(cudaMemcpyAsync(h->d_ptab16, pt16.data(), sizeof(void*) * 4, cudaMemcpyHostToDevice, st));
         EGR_CUDA_OK(cudaStreamSynchronize(st));
         WMat* all[9] = {&h->tk_hp2, &h->tk_fcq, &h->tk_bfb, &h->tk_sa, &h->tk_c, &h->tk_qkv, &h->tk_o, &h->tk_f1, &h->tk_f2};
-        for (WMat* m : all)
-            if ((rc = round_tf32_inplace(m->f32, (int64_t)m->sets * m->N * m->K, st))) return rc;
+        for (WMat* m : all) {
+            if (h->tok3x) {     // [W_hi | W_hi | W_lo] along K, TF32 values in fp32 containers
+                if ((rc = h->pool.alloc(&m->f32x3, (int64_t)m->sets * m->N * m->K * 3))) return rc;
+                if ((rc = split3_tf32(m->f32, m->f32x3, (int64_t)m->sets * m->N, m->K, st))) return rc;
+            } else if ((rc = round_tf32_inplace(m->f32, (int64_t)m->sets * m->N * m->K, st))) return rc;
+        }
         if ((rc = h->pool.alloc(&h->d_ptrs, TP_COUNT * 4))) return rc;
         EGR_CUDA_OK(cudaMemcpyAsync(h->d_ptrs, ptrs.data(), sizeof(const float*) * TP_COUNT * 4, cudaMemcpyHostToDevice, st));
         EGR_CUDA_OK(cudaStreamSynchronize(st));      // ptrs / tok are host locals
@@ -646,12 +681,13 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
               (long long)workspace_bytes, (long long)need);
     cudaStream_t st = (cudaStream_t)stream;
     const int V = h->V, J = h->J, prec = h->prec, bf = (prec == EGR_PREC_BF16);
+    const bool f16m = (prec == EGR_PREC_FP16);
     int rc;
     gemm_tc_set_scratch(w.splitk);
     EGR_MARK("stage_nhwc", st);
     // S0: NCHW fp32 -> view-major channels-last staging copy; skipped when the producer already wrote that layout
     if (in_staged) w.Xh = const_cast<void*>(in_staged);       // read-only from here on
-    else if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, bf, st))) return rc;
+    else if ((rc = nchw_to_nhwc(feat, w.Xh, B, V, FC, FHW, stage_mode(prec), st))) return rc;
     EGR_MARK("H1a", st);
     // H1: init heads, one group per weight set (front: views 0-1, back: views 2-3), two views per group
     const int G1 = h->head_sets, vpg = V / G1;
@@ -671,14 +707,14 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
     if ((rc = run_gemm(d, h->h1_4, 0, prec, false, st))) return rc;
     EGR_MARK("H1d", st);
     d = GemmDesc();
-    const bool z16 = bf && g_opt_tc;     // pre-upsample maps in fp16 on the tensor-core path (half2 interpolation in the tails)
+    const bool z16 = is16(prec) && g_opt_tc;     // pre-upsample maps in fp16 on the tensor-core path (half2 interpolation in the tails)
     d.A = w.c1; d.lda = 256; d.M = vpg * B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
     d.groups = G1; d.a_gs = (int64_t)vpg * B * 1024 * 256; d.d_gs = (int64_t)vpg * B * 1024 * 128;
     if ((rc = run_gemm(d, h->h1_7, 0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("H1tail", st);
     int wsel[4] = {0, 0, 1, 1};
     if (G1 == 1) wsel[2] = wsel[3] = 0;
-    if ((rc = head_up_conv(w.z, z16 ? 2 : bf, h->h1_9w, h->h1_9b, wsel, B, V, 32, 32, FC, J, hm_init, (int64_t)V * J * FHW,
+    if ((rc = head_up_conv(w.z, f16m ? 3 : z16 ? 2 : bf, h->h1_9w, h->h1_9b, wsel, B, V, 32, 32, FC, J, hm_init, (int64_t)V * J * FHW,
                            (int64_t)J * FHW, w.hmT, st))) return rc;
     EGR_MARK("D1", st);
     // D1: anchors from heatmap_for_anchor when given (:293-296), else from the init heatmap
@@ -691,13 +727,13 @@ extern "C" int egr_mvfex_forward(egr_mvfex* h, int B, const float* feat, const f
                       (int64_t)V * J * FHW, (int64_t)J * FHW, feat_refined, (int64_t)V * FC * FHW, (int64_t)FC * FHW, st);
     if (rc) return rc;
     note_all(h, w, B, V);
-    h->st_init = w.Xh; h->st_refined = w.refn; h->st_refined_hp = w.refn_hp;
+    h->st_init = w.Xh; h->st_refined = w.refn; h->st_refined_hp = f16m ? w.refn : w.refn_hp;
     return EGR_OK;
 }
 
 extern "C" int egr_mvfex_use_staged_input(egr_mvfex* h, const void* feat_vmajor_nhwc_bf16) {
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_use_staged_input: null handle");
-    EGR_CHECK(h->prec == EGR_PREC_BF16, EGR_ERR_UNSUPPORTED, "mvfex_use_staged_input: needs the bf16 precision (the staged copy is bf16)");
+    EGR_CHECK(is16(h->prec), EGR_ERR_UNSUPPORTED, "mvfex_use_staged_input: needs the bf16 precision (the staged copy is bf16) or the fp16 precision (fp16 copy)");
     EGR_CHECK(((uintptr_t)feat_vmajor_nhwc_bf16 & 15) == 0, EGR_ERR_INVALID, "mvfex_use_staged_input: pointer must be 16-byte aligned");
     h->in_staged = feat_vmajor_nhwc_bf16;
     return EGR_OK;
@@ -706,7 +742,7 @@ extern "C" int egr_mvfex_use_staged_input(egr_mvfex* h, const void* feat_vmajor_
 extern "C" int egr_mvfex_export_staged(egr_mvfex* h, int enable) {
     EGR_CHECK(h, EGR_ERR_INVALID, "mvfex_export_staged: null handle");
     EGR_CHECK(enable >= 0 && enable <= 4, EGR_ERR_INVALID, "mvfex_export_staged: mode %d", enable);
-    EGR_CHECK(enable != 4 || (h->prec == EGR_PREC_BF16 && g_opt_tc), EGR_ERR_UNSUPPORTED, "mvfex_export_staged: mode 4 needs the tensor-core path");
+    EGR_CHECK(enable != 4 || (is16(h->prec) && g_opt_tc), EGR_ERR_UNSUPPORTED, "mvfex_export_staged: mode 4 needs the tensor-core path");
     h->export_staged = enable != 0;
     h->export_hp = (enable == 1) ? 1 : (enable >= 3) ? 2 : 0;
     h->refn_f16_only = enable == 4;
@@ -719,7 +755,7 @@ extern "C" int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void
     EGR_CHECK(h && init_nhwc && refined_nhwc && refined_nhwc_hp && act_is_bf16, EGR_ERR_INVALID, "mvfex_staged: null argument");
     EGR_CHECK(h->st_init, EGR_ERR_STATE, "mvfex_staged: no forward has run since export was enabled");
     *init_nhwc = h->st_init; *refined_nhwc = h->st_refined; *refined_nhwc_hp = h->st_refined_hp;
-    *act_is_bf16 = (h->prec == EGR_PREC_BF16);
+    *act_is_bf16 = act_code(h->prec);       // 0 fp32, 1 bf16, 2 fp16
     return EGR_OK;
 }
 
@@ -739,12 +775,12 @@ extern "C" int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float
     EGR_CHECK(need <= workspace_bytes, EGR_ERR_STATE, "mvfex_refiner_forward: workspace %lld B < required %lld B",
               (long long)workspace_bytes, (long long)need);
     cudaStream_t st = (cudaStream_t)stream;
-    const int bf = (h->prec == EGR_PREC_BF16), J = h->J;
+    const int J = h->J;
     int rc;
     gemm_tc_set_scratch(w.splitk);
-    if ((rc = nchw_to_nhwc(feat_mv, w.Xh, B, h->V, FC, FHW, bf, st))) return rc;
-    if ((rc = nchw_to_nhwc(frame_feat, w.Xown, B, 1, FC, FHW, bf, st))) return rc;
-    if ((rc = cast_act(heatmap, w.hmT, bf, (int64_t)B * J * FHW, st))) return rc;
+    if ((rc = nchw_to_nhwc(feat_mv, w.Xh, B, h->V, FC, FHW, stage_mode(h->prec), st))) return rc;
+    if ((rc = nchw_to_nhwc(frame_feat, w.Xown, B, 1, FC, FHW, stage_mode(h->prec), st))) return rc;
+    if ((rc = cast_act(heatmap, w.hmT, act_code(h->prec), (int64_t)B * J * FHW, st))) return rc;
     rc = run_refiners(h, B, 1, r, w, w.Xown, bfb, (int64_t)512 * 64, 0, anchors_2d, anchors_valid, hm_refined,
                       (int64_t)J * FHW, 0, feat_refined, (int64_t)FC * FHW, 0, st);
     if (rc) return rc;

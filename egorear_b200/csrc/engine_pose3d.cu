@@ -53,9 +53,10 @@ struct egr_pose3d {
 namespace {
 
 inline int p2_prec(const egr_pose3d* h) {
-    if (h->prec != EGR_PREC_BF16) return EGR_PREC_FP32;
-    if (g_opt_pose_p2_bf16) return EGR_PREC_BF16;
+    if (!is16(h->prec)) return EGR_PREC_FP32;
+    if (h->prec == EGR_PREC_BF16 && g_opt_pose_p2_bf16) return EGR_PREC_BF16;
     if (!g_opt_tc) return EGR_PREC_FP32;
+    if (h->prec == EGR_PREC_FP16) return PREC_FP16;
     return g_opt_pose_p2_fp16 ? PREC_FP16 : PREC_TF32;
 }
 
@@ -151,7 +152,7 @@ struct PBufs {
 };
 
 int64_t p_carve(const egr_pose3d* h, int B, void* base, int64_t cap, PBufs* o) {
-    const int64_t si = (h->prec == EGR_PREC_BF16) ? 2 : 4;          // sampled map
+    const int64_t si = is16(h->prec) ? 2 : 4;          // sampled map
     const int64_t s = (p2_prec(h) == EGR_PREC_BF16 || p2_prec(h) == PREC_FP16) ? 2 : 4;        // proposal branch
     const int64_t VB = (int64_t)h->V * B;
     Carver c(base, cap);
@@ -308,12 +309,15 @@ extern "C" int egr_pose3d_create(int num_views, int num_joints, int num_layers, 
     EGR_CHECK(camera_model >= 0 && camera_model <= 5, EGR_ERR_INVALID, "Unknown camera model !");
     const int need_v = (camera_model <= 1) ? 4 : 2;
     EGR_CHECK(num_views == need_v, EGR_ERR_INVALID, "pose3d: camera model %d needs num_views == %d", camera_model, need_v);
-    EGR_CHECK(precision == EGR_PREC_FP32 || precision == EGR_PREC_BF16, EGR_ERR_INVALID, "pose3d: precision %d", precision);
+    EGR_CHECK(precision == EGR_PREC_FP32 || precision == EGR_PREC_BF16 || precision == EGR_PREC_FP16, EGR_ERR_INVALID,
+              "pose3d: precision %d", precision);
+    EGR_CHECK(precision != EGR_PREC_FP16 || (g_opt_tc && g_opt_tok_batched), EGR_ERR_UNSUPPORTED,
+              "pose3d: EGR_PREC_FP16 is a tensor-core mode (options tc / tok_batched must be on)");
     if (int rc = require_device()) return rc;
     egr_pose3d* h = new egr_pose3d();
     h->V = num_views; h->J = num_joints; h->L = num_layers; h->cam_model = camera_model;
     h->use_init = use_pred_heatmap_init; h->prec = precision;
-    h->tokb = (precision == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    h->tokb = is16(precision) && g_opt_tc && g_opt_tok_batched;
     h->KA = tok_ka(PE, false);
     const int first = (camera_model >= 4) ? 2 : 0;   // stereo_back rigs start at back_left
     for (int v = 0; v < 4; ++v) {
@@ -377,7 +381,7 @@ extern "C" int egr_pose3d_prepack(egr_pose3d* h, void* stream) {
     if ((rc = h->pool.alloc(&h->d_w, 1))) return rc;
     EGR_CUDA_OK(cudaMemcpyAsync(h->d_w, &tw, sizeof(PoseTokenW), cudaMemcpyHostToDevice, st));
     h->tw_host = tw;
-    h->tokb = (h->prec == EGR_PREC_BF16) && g_opt_tc && g_opt_tok_batched;
+    h->tokb = is16(h->prec) && g_opt_tc && g_opt_tok_batched;
     if (h->tokb) {
         if ((rc = gemm_tc_init())) return rc;
         if ((rc = p_alloc_wmat(h, h->tk_g2, PE, PE, st)) || (rc = p_alloc_wmat(h, h->tk_g4, PE, PE, st))) return rc;
@@ -422,7 +426,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
               (long long)workspace_bytes, (long long)need);
     cudaStream_t st = (cudaStream_t)stream;
     const int V = h->V, J = h->J;
-    const int bfs = (h->prec == EGR_PREC_BF16);            // sampled-map dtype
+    const int bfs = act_code(h->prec);                     // sampled-map dtype: 0 fp32, 1 bf16, 2 fp16
     const int prec = p2_prec(h), bf = (prec == EGR_PREC_BF16);   // proposal-branch dtype
     const int VB = V * B;
     int rc;
@@ -446,10 +450,11 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
         if ((rc = nchw_to_nhwc(feats_final, w.Xf, B, V, PC, PHW, f16 ? 3 : rnd ? 2 : bf, st))) return rc;
     }
     const void* Xs = Xf;
+    const int pcode = f16 ? 2 : bf ? 1 : 0;                // dtype of Xf; it doubles as the sampled map only when both agree
     if (st_s && st_s_bf16 == bfs) Xs = st_s;
-    else if (sampled != feats_final || bfs != bf || rnd || f16) {
+    else if (sampled != feats_final || bfs != pcode || rnd || (f16 && bfs != 2)) {
         EGR_CHECK(sampled, EGR_ERR_INVALID, "pose3d_forward: the sampled map is NULL and its staged copy does not fit this precision");
-        if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs, st))) return rc;
+        if ((rc = nchw_to_nhwc(sampled, w.Xi, B, V, PC, PHW, bfs == 2 ? 3 : bfs, st))) return rc;
         Xs = w.Xi;
     }
     EGR_MARK("P2a", st);
@@ -502,10 +507,10 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
     if (h->tokb) {
         if ((rc = p_run_tokens_batched(h, B, w, Xs, bfs, coord_trans_mat, preds, h->tw_host, st))) return rc;
     } else {
-        if ((rc = launch_pose_tokens(ta, bfs, st))) return rc;
+        if ((rc = launch_pose_tokens(ta, bfs == 1, st))) return rc;
     }
     EGR_MARK(nullptr, st);
-    const int64_t s = bf ? 2 : 4;
+    const int64_t s = (bf || f16) ? 2 : 4;
     h->dbg["p7"] = std::make_pair(w.p7, (int64_t)VB * 64 * 128 * s);
     h->dbg["p0"] = std::make_pair(w.p0, (int64_t)VB * PHW * 64 * s);
     h->dbg["m0"] = std::make_pair((void*)w.m0, (int64_t)B * 2048 * 4);
@@ -516,7 +521,7 @@ extern "C" int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init,
 
 extern "C" int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32) {
     EGR_CHECK(h, EGR_ERR_INVALID, "pose3d_use_staged: null handle");
-    h->st_sampled = sampled_nhwc; h->st_sampled_bf16 = sampled_is_bf16 ? 1 : 0; h->st_final_tf32 = final_nhwc_tf32;
+    h->st_sampled = sampled_nhwc; h->st_sampled_bf16 = sampled_is_bf16; h->st_final_tf32 = final_nhwc_tf32;   // dtype code 0 fp32 / 1 bf16 / 2 fp16
     return EGR_OK;
 }
 

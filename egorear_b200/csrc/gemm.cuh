@@ -33,6 +33,14 @@ struct GemmDesc {
     int64_t lda = 0, ldd = 0;
     int amode = A_PLAIN, epi = EPI_NONE;
     int round_tf32 = 0;           // tcgen05 path, fp32 output: round to the nearest TF32 value (operand of the next tf32 stage)
+    // split operands (tcgen05 path): A has only `ka` columns and the k loop re-reads it from column 0 for k >= ka
+    // (ka < K <= 2*ka).  Two uses:
+    //   K = 2*ka, W = [W_hi | W_lo] (W_lo = rounding residual of W_hi in the operand type): D = A·(W_hi + W_lo)^T, the
+    //       weight rounding error is removed at the price of twice the MMAs (free for an HBM-bound stage);
+    //   K = 3*k0, ka = 2*k0, A = [x | x_lo], W = [W_hi | W_hi | W_lo]: the "3x" product x_hi·W_hi + x_lo·W_hi + x_hi·W_lo
+    //       (x is raw fp32, the tensor core truncates it to TF32 = x_hi; x_lo = tf32(x - x_hi)): fp32-grade token Linears.
+    // 0 = plain.
+    int ka = 0;
     // A_PLAIN K-split (pose3d flatten "(v c h w)"): k-blocks of kblk elements live kblk_stride apart
     int kblk = 0;
     int64_t kblk_stride = 0;

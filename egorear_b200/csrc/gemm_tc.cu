@@ -52,6 +52,7 @@ struct TcParams {
     int m_tiles, n_tiles, groups, ksplit, kb_total, kb_per_split;
     int amode;
     int kblk;                 // A_PLAIN: elements per outer k block (== K when there is no K split of A)
+    int ka;                   // A's own K: k >= ka re-reads A at k - ka (split weights [W_hi | W_lo]); == K otherwise
     int Cin, Wout, HWout;     // A_CONV3S2
     int epi;
     int round_out;            // fp32 output rounded to the nearest TF32 value
@@ -329,10 +330,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_expect_tx(full, stage_bytes);
                     const uint32_t sa = smem_base + w_bytes + stage * stage_bytes, sb = sa + C::STAGE_A;
                     const int k = kb * BK;
+                    const int k_a = (k >= p.ka) ? k - p.ka : k;      // split weights: the second half of K re-reads A
                     if (p.amode == A_PLAIN) {
-                        tma_load_4d(sa, &tmA, full, k % p.kblk, tc.mt * BM, k / p.kblk, tc.g);
+                        tma_load_4d(sa, &tmA, full, k_a % p.kblk, tc.mt * BM, k_a / p.kblk, tc.g);
                     } else {
-                        const int tap = k / p.Cin, ci = k - tap * p.Cin;
+                        const int tap = k_a / p.Cin, ci = k_a - tap * p.Cin;
                         const int ky = tap / 3, kx = tap - ky * 3;
                         // input pixel (2*oy + ky - 1, 2*ox + kx - 1) = pair index (oy + dy, ox + dx), parity (hp, wp)
                         const int wp = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
@@ -543,10 +545,12 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
               (out_dt_req == DT_F32 || (in_dt != DT_F32 && (out_dt_req == DT_BF16 || out_dt_req == DT_F16))),
               EGR_ERR_UNSUPPORTED, "gemm_tc: operand / output types %d -> %d (TF32 operands give fp32; 16-bit operands give fp32, bf16 or fp16)", in_dt, out_dt_req);
     const bool f32 = in_dt == DT_F32;
+    const int Ka = d.ka > 0 ? d.ka : d.K;       // A's own K (split operands: ka < K <= 2 * ka, the tail of K re-reads A from 0)
+    EGR_CHECK(d.ka == 0 || (d.ka < d.K && d.K <= 2 * d.ka), EGR_ERR_INVALID, "gemm_tc: split operands need ka < K <= 2 * ka (K=%d ka=%d)", d.K, d.ka);
     const int ES = f32 ? 4 : 2;                 // operand element size
     const int BK = ROW_BYTES / ES;              // elements per k-block
     const int AL = 16 / ES;                     // elements per 16 bytes (TMA stride granularity)
-    EGR_CHECK(d.K % BK == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d", d.K, BK);
+    EGR_CHECK(d.K % BK == 0 && Ka % BK == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: K=%d must be a multiple of %d", d.K, BK);
     EGR_CHECK(d.N % 64 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: N=%d must be a multiple of 64", d.N);
     EGR_CHECK((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(d.D) & 15) == 0, EGR_ERR_INVALID, "gemm_tc: operands must be 16-byte aligned");
@@ -585,7 +589,7 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
         }
     }
     TcParams p{};
-    p.M = d.M; p.N = d.N; p.K = d.K;
+    p.M = d.M; p.N = d.N; p.K = d.K; p.ka = Ka;
     p.m_tiles = m_tiles; p.n_tiles = d.N / bn; p.groups = d.groups;
     p.kb_total = kb_total;
     p.ksplit = 1; p.kb_per_split = p.kb_total;
@@ -617,19 +621,19 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     int rc;
     if (d.amode == A_PLAIN) {
-        const int kblk = d.kblk > 0 ? d.kblk : d.K;
-        EGR_CHECK(kblk % BK == 0 && d.K % kblk == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: kblk=%d", kblk);
+        const int kblk = d.kblk > 0 ? d.kblk : Ka;
+        EGR_CHECK(kblk % BK == 0 && Ka % kblk == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: kblk=%d", kblk);
         EGR_CHECK(d.lda % AL == 0 && d.a_gs % AL == 0 && d.kblk_stride % AL == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: A strides must be multiples of 16 bytes");
         p.kblk = kblk;
-        const cuuint64_t dims[4] = {(cuuint64_t)kblk, (cuuint64_t)d.M, (cuuint64_t)(d.K / kblk), (cuuint64_t)d.groups};
+        const cuuint64_t dims[4] = {(cuuint64_t)kblk, (cuuint64_t)d.M, (cuuint64_t)(Ka / kblk), (cuuint64_t)d.groups};
         // strides of size-1 dims are irrelevant but must be valid (multiple of 16 B)
-        const cuuint64_t str[3] = {(cuuint64_t)d.lda * ES, (cuuint64_t)(d.K / kblk > 1 ? d.kblk_stride : d.lda) * ES,
+        const cuuint64_t str[3] = {(cuuint64_t)d.lda * ES, (cuuint64_t)(Ka / kblk > 1 ? d.kblk_stride : d.lda) * ES,
                                    (cuuint64_t)(d.groups > 1 ? d.a_gs : d.lda) * ES};
         const cuuint32_t box[4] = {(cuuint32_t)BK, BM, 1, 1};
         if ((rc = encode(&tmA, in_dt, d.A, 4, dims, str, box, "A"))) return rc;
     } else {
         const int Hout = d.Hin / 2, Wout = d.Win / 2, HW = Hout * Wout;
-        EGR_CHECK(d.Cin % BK == 0 && d.K == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
+        EGR_CHECK(d.Cin % BK == 0 && Ka == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
                   "gemm_tc: conv geometry Cin=%d K=%d", d.Cin, d.K);
         EGR_CHECK(BM % Wout == 0 && (HW % BM == 0 || BM % HW == 0), EGR_ERR_UNSUPPORTED, "gemm_tc: conv output %dx%d does not tile by %d rows", Hout, Wout, BM);
         EGR_CHECK(d.M % HW == 0, EGR_ERR_INVALID, "gemm_tc: conv M=%d is not a whole number of %dx%d images", d.M, Hout, Wout);
@@ -675,7 +679,7 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     {
         const int64_t w_bytes = (int64_t)p.kb_total * bn * ROW_BYTES;
         const int64_t a_stages = (SMEM_RING - w_bytes) / (BM * ROW_BYTES);
-        if (g_opt_ws && d.amode == A_PLAIN && p.kblk == d.K && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
+        if (g_opt_ws && d.ka == 0 && d.amode == A_PLAIN && p.kblk == d.K && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
             total >= 2 * (int64_t)grid) {
             p.ws = 1;
             p.ws_stages = (int)(a_stages < MAX_STAGES ? a_stages : MAX_STAGES);

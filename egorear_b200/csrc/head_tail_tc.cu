@@ -14,6 +14,7 @@
 #include "layout_ops.cuh"
 #include "tc_ptx.cuh"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace egr {
 using namespace tcx;
@@ -22,10 +23,15 @@ namespace {
 constexpr int HT_FS = 32, HT_FO = 64, HT_C = 128, HT_STRIP = 4, HT_ROWS = 4, HT_NJ = 16;
 constexpr int HT_PST = 272;                                  // bytes per staged source pixel: 256 + 16
 constexpr int HT_OFF_A = 0;                                  // [2 M-tiles][128 rows][128 B] = 32 KB (one 64-channel k-block at a time)
-constexpr int HT_OFF_W = 2 * 128 * 128;                      // [2 k-blocks][16 rows][128 B] =  4 KB
-constexpr int HT_OFF_SRC = HT_OFF_W + 2 * 16 * 128;          // [4 rows x 32 px][272 B]
-constexpr int HT_OFF_BAR = HT_OFF_SRC + HT_ROWS * HT_FS * HT_PST;
-constexpr int HT_SMEM = HT_OFF_BAR + 64 + 1024 /*align*/;
+constexpr int HT_OFF_W = 2 * 128 * 128;                      // [2 k-blocks][16 rows][128 B] =  4 KB (+ 4 KB W_lo when PRECISE)
+// PRECISE (EGR_PREC_FP16): the 1x1 weights as an fp16 pair W_hi + W_lo (W_lo = fp16 of the rounding residual), twice the
+// MMAs against the same A tile: the weight rounding error of this last layer disappears; hm_t is written in fp16
+template <bool PRECISE> struct HtCfg {
+    static constexpr int W_BYTES = (PRECISE ? 2 : 1) * 2 * 16 * 128;
+    static constexpr int OFF_SRC = HT_OFF_W + W_BYTES;       // [4 rows x 32 px][272 B]
+    static constexpr int OFF_BAR = OFF_SRC + HT_ROWS * HT_FS * HT_PST;
+    static constexpr int SMEM = OFF_BAR + 64 + 1024 /*align*/;
+};
 constexpr uint32_t HT_TMEM_COLS = 32;
 
 struct HtUp {
@@ -70,9 +76,23 @@ __device__ __forceinline__ uint32_t interp_word(uint32_t a, uint32_t b, uint32_t
     return *reinterpret_cast<const uint32_t*>(&r);
 }
 
+// PRECISE: the same in fp32 arithmetic, one rounding (of the result) instead of one per HFMA2 plus the weights'
+__device__ __forceinline__ uint32_t interp_word_f32(uint32_t a, uint32_t b, uint32_t c, uint32_t d, float w00, float w01,
+                                                    float w10, float w11) {
+    const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&a)), fb = __half22float2(*reinterpret_cast<const __half2*>(&b));
+    const float2 fc = __half22float2(*reinterpret_cast<const __half2*>(&c)), fd = __half22float2(*reinterpret_cast<const __half2*>(&d));
+    const float lo = fmaxf(fmaf(w11, fd.x, fmaf(w10, fc.x, fmaf(w01, fb.x, w00 * fa.x))), 0.f);
+    const float hi = fmaxf(fmaf(w11, fd.y, fmaf(w10, fc.y, fmaf(w01, fb.y, w00 * fa.y))), 0.f);
+    return pack_f16x2(lo, hi);
+}
+
+template <bool PRECISE>
 __global__ void __launch_bounds__(256, 3)
 head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, const float* __restrict__ bias, int4 wsel,
-                    int B, int J, float* __restrict__ hm, int64_t hm_bs, int64_t hm_gs, __nv_bfloat16* __restrict__ hm_t) {
+                    int B, int J, float* __restrict__ hm, int64_t hm_bs, int64_t hm_gs, void* __restrict__ hm_t_) {
+    using HM_T = typename std::conditional<PRECISE, __half, __nv_bfloat16>::type;
+    HM_T* __restrict__ hm_t = reinterpret_cast<HM_T*>(hm_t_);
+    constexpr int HT_OFF_SRC = HtCfg<PRECISE>::OFF_SRC, HT_OFF_BAR = HtCfg<PRECISE>::OFF_BAR;
     extern __shared__ __align__(1024) uint8_t ht_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ht_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem + HT_OFF_A;
@@ -99,14 +119,21 @@ head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, c
     if (tid < HT_NJ) sb[tid] = (tid < J) ? __ldg(bias + (int64_t)sel * J + tid) : 0.f;
     {   // weight tile: fp32 [J][128] -> fp16 [2 k-blocks][16 rows][64], rows >= J zero
         const int n = tid >> 4, piece = tid & 15;
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u), ul = make_uint4(0u, 0u, 0u, 0u);
         if (n < J) {
             const float4* src = reinterpret_cast<const float4*>(w + ((int64_t)sel * J + n) * HT_C + piece * 8);
             const float4 f0 = __ldg(src), f1 = __ldg(src + 1);
             u = make_uint4(pack_f16x2(f0.x, f0.y), pack_f16x2(f0.z, f0.w), pack_f16x2(f1.x, f1.y), pack_f16x2(f1.z, f1.w));
+            if (PRECISE) {      // residual of the fp16 rounding, itself in fp16
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+                const float2 a = __half22float2(h[0]), b2 = __half22float2(h[1]), c = __half22float2(h[2]), d = __half22float2(h[3]);
+                ul = make_uint4(pack_f16x2(f0.x - a.x, f0.y - a.y), pack_f16x2(f0.z - b2.x, f0.w - b2.y),
+                                pack_f16x2(f1.x - c.x, f1.y - c.y), pack_f16x2(f1.z - d.x, f1.w - d.y));
+            }
         }
         const int kb = piece >> 3, pp = piece & 7;
         *reinterpret_cast<uint4*>(sW + kb * 2048 + n * 128 + ((pp ^ (n & 7)) << 4)) = u;
+        if (PRECISE) *reinterpret_cast<uint4*>(sW + 4096 + kb * 2048 + n * 128 + ((pp ^ (n & 7)) << 4)) = ul;
     }
     const int sr0 = ht_up(y0).i0;
     const int nsr = ht_up(y0 + HT_STRIP - 1).i1 - sr0 + 1;
@@ -137,8 +164,9 @@ head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, c
         const uint32_t p01 = sS32 + ((cy.i0 - sr0) * HT_FS + cx.i1) * HT_PST;
         const uint32_t p10 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i0) * HT_PST;
         const uint32_t p11 = sS32 + ((cy.i1 - sr0) * HT_FS + cx.i1) * HT_PST;
-        const __half2 w00 = __float2half2_rn(cy.l0 * cx.l0), w01 = __float2half2_rn(cy.l0 * cx.l1);
-        const __half2 w10 = __float2half2_rn(cy.l1 * cx.l0), w11 = __float2half2_rn(cy.l1 * cx.l1);
+        const float f00 = cy.l0 * cx.l0, f01 = cy.l0 * cx.l1, f10 = cy.l1 * cx.l0, f11 = cy.l1 * cx.l1;
+        const __half2 w00 = __float2half2_rn(f00), w01 = __float2half2_rn(f01);
+        const __half2 w10 = __float2half2_rn(f10), w11 = __float2half2_rn(f11);
         const int r = tid & 127;
         const uint32_t arow = smem_u32(sA) + (tid >> 7) * 16384 + r * 128;
         const int sw = r & 7;
@@ -150,10 +178,17 @@ head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, c
                 const uint4 a = lds128(p00 + pc * 16), bb = lds128(p01 + pc * 16);
                 const uint4 c = lds128(p10 + pc * 16), d = lds128(p11 + pc * 16);
                 uint4 o;
-                o.x = interp_word(a.x, bb.x, c.x, d.x, w00, w01, w10, w11);
-                o.y = interp_word(a.y, bb.y, c.y, d.y, w00, w01, w10, w11);
-                o.z = interp_word(a.z, bb.z, c.z, d.z, w00, w01, w10, w11);
-                o.w = interp_word(a.w, bb.w, c.w, d.w, w00, w01, w10, w11);
+                if (PRECISE) {
+                    o.x = interp_word_f32(a.x, bb.x, c.x, d.x, f00, f01, f10, f11);
+                    o.y = interp_word_f32(a.y, bb.y, c.y, d.y, f00, f01, f10, f11);
+                    o.z = interp_word_f32(a.z, bb.z, c.z, d.z, f00, f01, f10, f11);
+                    o.w = interp_word_f32(a.w, bb.w, c.w, d.w, f00, f01, f10, f11);
+                } else {
+                    o.x = interp_word(a.x, bb.x, c.x, d.x, w00, w01, w10, w11);
+                    o.y = interp_word(a.y, bb.y, c.y, d.y, w00, w01, w10, w11);
+                    o.z = interp_word(a.z, bb.z, c.z, d.z, w00, w01, w10, w11);
+                    o.w = interp_word(a.w, bb.w, c.w, d.w, w00, w01, w10, w11);
+                }
                 sts128(arow + ((pp ^ sw) << 4), o);
             }
             fence_async_smem();            // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
@@ -169,6 +204,11 @@ head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, c
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
                         tc_mma<false>(tmem_base + mt * HT_NJ, da + 2 * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                    if (PRECISE) {
+                        const uint64_t dl = make_smem_desc(smem_u32(sW + 4096 + kb * 2048));
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) tc_mma<false>(tmem_base + mt * HT_NJ, da + 2 * kk, dl + 2 * kk, idesc, 1u);
+                    }
                 }
                 tc_commit(smem_u32(bar));
             }
@@ -193,10 +233,10 @@ head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, c
     for (int j = 0; j < HT_NJ; ++j)
         if (j < J) o[(int64_t)j * HT_FO * HT_FO] = r[j];
     if (hm_t) {
-        __nv_bfloat16* ot = hm_t + ((int64_t)img * J) * HT_FO * HT_FO + (int64_t)y * HT_FO + x;
+        HM_T* ot = hm_t + ((int64_t)img * J) * HT_FO * HT_FO + (int64_t)y * HT_FO + x;
 #pragma unroll
         for (int j = 0; j < HT_NJ; ++j)
-            if (j < J) ot[(int64_t)j * HT_FO * HT_FO] = __float2bfloat16_rn(r[j]);
+            if (j < J) ActT<HM_T>::st(ot + (int64_t)j * HT_FO * HT_FO, r[j]);
     }
     tc_fence_before();
     __syncthreads();
@@ -209,17 +249,20 @@ head_tail_tc_kernel(const __half* __restrict__ z, const float* __restrict__ w, c
 }  // namespace
 
 int head_tail_tc(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
-                 int64_t hm_bs, int64_t hm_gs, void* hm_t, cudaStream_t st) {
+                 int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, cudaStream_t st) {
     EGR_CHECK(J <= HT_NJ && G <= 4, EGR_ERR_UNSUPPORTED, "head_tail_tc: J=%d G=%d", J, G);
     static bool attr_set = false;
     if (!attr_set) {
-        EGR_CUDA_OK(cudaFuncSetAttribute(head_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+        EGR_CUDA_OK(cudaFuncSetAttribute(head_tail_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HtCfg<false>::SMEM));
+        EGR_CUDA_OK(cudaFuncSetAttribute(head_tail_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HtCfg<true>::SMEM));
         attr_set = true;
     }
     dim3 grid(HT_FO / HT_STRIP, G * B);
     const int4 sel = make_int4(wsel_host[0], wsel_host[1], wsel_host[2], wsel_host[3]);
-    EGR_LAUNCH(head_tail_tc_kernel, grid, 256, HT_SMEM, st, (const __half*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs,
-               (__nv_bfloat16*)hm_t);
+    if (precise)
+        EGR_LAUNCH(head_tail_tc_kernel<true>, grid, 256, HtCfg<true>::SMEM, st, (const __half*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs, hm_t);
+    else
+        EGR_LAUNCH(head_tail_tc_kernel<false>, grid, 256, HtCfg<false>::SMEM, st, (const __half*)z, w, bias, sel, B, J, hm, hm_bs, hm_gs, hm_t);
     return EGR_OK;
 }
 

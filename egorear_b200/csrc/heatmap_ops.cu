@@ -12,12 +12,16 @@ namespace egr {
 // ---------------------------------------------------------------------------------------------
 constexpr int GT_WARPS = 8;
 constexpr int GT_MAX_PATCH = 31;
+// The Gaussian patch travels BY VALUE as a kernel parameter (3.8 KB, constant bank): no device-side cache that another
+// stream / device / sigma could overwrite while a launch is still reading it, no host->device copy (legal under stream
+// capture), nothing to free.
+struct GtPatch { float v[GT_MAX_PATCH * GT_MAX_PATCH]; };
 
 __global__ void __launch_bounds__(GT_WARPS * 32)
 generate_target_kernel(const double* __restrict__ joints, float* __restrict__ out, int64_t n_hm,
-                       double feat_stride, double tmp_size, int hs, int size, const float* __restrict__ patch) {
+                       double feat_stride, double tmp_size, int hs, int size, const __grid_constant__ GtPatch patch) {
     __shared__ float s_patch[GT_MAX_PATCH * GT_MAX_PATCH];
-    for (int i = threadIdx.x; i < size * size; i += blockDim.x) s_patch[i] = patch[i];
+    for (int i = threadIdx.x; i < size * size; i += blockDim.x) s_patch[i] = patch.v[i];
     __syncthreads();
 
     const int lane = threadIdx.x & 31;
@@ -148,11 +152,14 @@ decode_soft_argmax_kernel(const float* __restrict__ hm, int64_t n_hm, int H, int
     for (int64_t m = (int64_t)blockIdx.x * DEC_WARPS + warp; m < n_hm; m += (int64_t)gridDim.x * DEC_WARPS) {
         const float4* src = reinterpret_cast<const float4*>(hm + m * (int64_t)HW);
         float mx = -INFINITY;
+        bool nan = false;      // fmaxf drops NaN; torch.max / softmax propagate it (maxvals and both coordinates become NaN)
         for (int i = lane; i < n_v4; i += 32) {
             const float4 v = __ldg(src + i);
             mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            nan = nan || (v.x != v.x) || (v.y != v.y) || (v.z != v.z) || (v.w != v.w);
         }
         mx = warp_max(mx);
+        if (__any_sync(0xffffffffu, nan)) mx = __int_as_float(0x7fc00000);
         float s = 0.f, sx = 0.f, sy = 0.f;
         for (int i = lane; i < n_v4; i += 32) {
             const float4 v = __ldg(src + i);
@@ -196,11 +203,14 @@ integrate_2d_kernel(const float* __restrict__ hm, int64_t n_hm, int H, int W, in
         float mx = 0.f;
         if (softmax) {
             mx = -INFINITY;
+            bool nan = false;  // a NaN anywhere in the map makes the softmax (all of p and both coordinates) NaN, as in torch
             for (int i = lane; i < n_v4; i += 32) {
                 const float4 v = __ldg(src + i);
                 mx = fmaxf(fmaxf(mx, fmaxf(v.x * mult, v.y * mult)), fmaxf(v.z * mult, v.w * mult));
+                nan = nan || (v.x != v.x) || (v.y != v.y) || (v.z != v.z) || (v.w != v.w);
             }
             mx = warp_max(mx);
+            if (__any_sync(0xffffffffu, nan)) mx = __int_as_float(0x7fc00000);
         }
         float s = 0.f, sx = 0.f, sy = 0.f;
         for (int i = lane; i < n_v4; i += 32) {
@@ -213,7 +223,10 @@ integrate_2d_kernel(const float* __restrict__ hm, int64_t n_hm, int H, int W, in
                 e0 = expf(__fmul_rn(v.x, mult) - mx); e1 = expf(__fmul_rn(v.y, mult) - mx);
                 e2 = expf(__fmul_rn(v.z, mult) - mx); e3 = expf(__fmul_rn(v.w, mult) - mx);
             } else {
-                e0 = fmaxf(v.x * mult, 0.f); e1 = fmaxf(v.y * mult, 0.f); e2 = fmaxf(v.z * mult, 0.f); e3 = fmaxf(v.w * mult, 0.f);
+                // torch.relu keeps NaN (fmaxf would drop it)
+                const float m0 = v.x * mult, m1 = v.y * mult, m2 = v.z * mult, m3 = v.w * mult;
+                e0 = (m0 != m0) ? m0 : fmaxf(m0, 0.f); e1 = (m1 != m1) ? m1 : fmaxf(m1, 0.f);
+                e2 = (m2 != m2) ? m2 : fmaxf(m2, 0.f); e3 = (m3 != m3) ? m3 : fmaxf(m3, 0.f);
                 if (dst) __stcs(dst + i, make_float4(e0, e1, e2, e3));
             }
             const float es = (e0 + e1) + (e2 + e3);
@@ -317,14 +330,6 @@ static float sigma1_value(int d2) {
     return v;
 }
 
-// small device-side cache for the patch so repeated calls do not re-upload
-struct PatchCache {
-    float* dev = nullptr;
-    int size = 0;
-    double sigma = -1.0;
-    bool custom = false;
-};
-static thread_local PatchCache t_patch;
 
 extern "C" int egr_generate_target(const double* joints, float* out, int64_t n_maps, int J, double image_size,
                                    int heatmap_size, double sigma, const float* patch_host, void* stream) {
@@ -340,31 +345,28 @@ extern "C" int egr_generate_target(const double* joints, float* out, int64_t n_m
     EGR_CHECK(size <= GT_MAX_PATCH, EGR_ERR_UNSUPPORTED, "generate_target: patch %d > %d", size, GT_MAX_PATCH);
     if (n_maps == 0) return EGR_OK;
     EGR_CHECK(joints && out, EGR_ERR_INVALID, "generate_target: null pointer");
+    EGR_CHECK(((uintptr_t)out % 16) == 0 && ((uintptr_t)joints % 8) == 0, EGR_ERR_INVALID,
+              "generate_target: out must be 16-byte aligned (128-bit stores), joints 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
 
-    if (!t_patch.dev) EGR_CUDA_OK(cudaMalloc(&t_patch.dev, sizeof(float) * GT_MAX_PATCH * GT_MAX_PATCH));
-    if (patch_host || t_patch.custom || t_patch.sigma != sigma || t_patch.size != size) {
-        float h[GT_MAX_PATCH * GT_MAX_PATCH];
-        if (patch_host) {
-            memcpy(h, patch_host, sizeof(float) * size * size);
-        } else {
-            const int c = size / 2;
-            for (int y = 0; y < size; ++y)
-                for (int x = 0; x < size; ++x) {
-                    const int d2 = (x - c) * (x - c) + (y - c) * (y - c);
-                    h[y * size + x] = (sigma == 1.0) ? sigma1_value(d2)
-                                                     : expf(-(float)d2 / (float)(2.0 * sigma * sigma));
-                }
-        }
-        // pageable source: the copy is staged before the call returns
-        EGR_CUDA_OK(cudaMemcpyAsync(t_patch.dev, h, sizeof(float) * size * size, cudaMemcpyHostToDevice, st));
-        t_patch.size = size; t_patch.sigma = sigma; t_patch.custom = (patch_host != nullptr);
+    GtPatch h;
+    memset(&h, 0, sizeof(h));
+    if (patch_host) {
+        memcpy(h.v, patch_host, sizeof(float) * size * size);
+    } else {
+        const int c = size / 2;
+        for (int y = 0; y < size; ++y)
+            for (int x = 0; x < size; ++x) {
+                const int d2 = (x - c) * (x - c) + (y - c) * (y - c);
+                h.v[y * size + x] = (sigma == 1.0) ? sigma1_value(d2)
+                                                   : expf(-(float)d2 / (float)(2.0 * sigma * sigma));
+            }
     }
     const int64_t n_hm = n_maps * J;
     const int64_t want = ceil_div64(n_hm, GT_WARPS);
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
     generate_target_kernel<<<grid, GT_WARPS * 32, 0, st>>>(joints, out, n_hm, image_size / (double)heatmap_size,
-                                                            tmp_size, heatmap_size, size, t_patch.dev);
+                                                            tmp_size, heatmap_size, size, h);
     EGR_LAUNCHED();
     return EGR_OK;
 }
@@ -376,6 +378,7 @@ extern "C" int egr_decode_argmax(const float* hm, int64_t N, int J, int H, int W
     EGR_CHECK((H * W) % 4 == 0, EGR_ERR_UNSUPPORTED, "decode: H*W must be a multiple of 4");
     if (N == 0) return EGR_OK;
     EGR_CHECK(hm && preds && maxvals && valid, EGR_ERR_INVALID, "decode: null pointer");
+    EGR_CHECK(((uintptr_t)hm % 16) == 0, EGR_ERR_INVALID, "decode: hm must be 16-byte aligned (128-bit loads)");
     const int64_t n_hm = N * J;
     const int64_t want = ceil_div64(n_hm, DEC_WARPS);
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
@@ -405,6 +408,7 @@ extern "C" int egr_decode_soft_argmax(const float* hm, int64_t N, int J, int H, 
     EGR_CHECK(W % 4 == 0, EGR_ERR_UNSUPPORTED, "decode_soft: W must be a multiple of 4");
     if (N == 0) return EGR_OK;
     EGR_CHECK(hm && preds && maxvals, EGR_ERR_INVALID, "decode_soft: null pointer");
+    EGR_CHECK(((uintptr_t)hm % 16) == 0, EGR_ERR_INVALID, "decode_soft: hm must be 16-byte aligned (128-bit loads)");
     const int64_t n_hm = N * J;
     const int64_t want = ceil_div64(n_hm, DEC_WARPS);
     const int grid = (int)(want < (int64_t)sm_count() * 32 ? want : (int64_t)sm_count() * 32);
@@ -418,6 +422,9 @@ extern "C" int egr_heatmap_head_1x1(const float* feat, const float* weight, cons
     EGR_CHECK(J > 0 && J <= H1_JMAX, EGR_ERR_UNSUPPORTED, "heatmap_head_1x1: J=%d > %d", J, H1_JMAX);
     EGR_CHECK(HW % 4 == 0 && C > 0, EGR_ERR_UNSUPPORTED, "heatmap_head_1x1: HW %% 4 != 0");
     if (N == 0) return EGR_OK;
+    EGR_CHECK(feat && weight && bias && out, EGR_ERR_INVALID, "heatmap_head_1x1: null pointer");
+    EGR_CHECK(((uintptr_t)feat % 16) == 0 && ((uintptr_t)out % 16) == 0, EGR_ERR_INVALID,
+              "heatmap_head_1x1: feat / out must be 16-byte aligned (128-bit accesses)");
     const int64_t total = N * (HW / 4);
     const int64_t want = ceil_div64(total, 256);
     const int grid = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);

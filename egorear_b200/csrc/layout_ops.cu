@@ -269,7 +269,7 @@ __device__ __forceinline__ void store8_dt(void* base, int64_t off, int dt, float
 template <typename TZ>
 __global__ void __launch_bounds__(256)
 up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ out_nchw, int64_t o_bs, int64_t o_gs,
-                          void* __restrict__ cl0, int cl0_dt, void* __restrict__ cl1, int cl1_dt) {
+                          void* __restrict__ cl0, int cl0_dt, void* __restrict__ cl1, int cl1_dt, int fp32_interp) {
     constexpr int SLD = 130;                               // transposed tile row stride: conflict-free both ways
     constexpr bool HALF = std::is_same<TZ, __half>::value;
     extern __shared__ __align__(16) uint8_t fsm[];
@@ -310,7 +310,7 @@ up2_relu_dual_fast_kernel(const TZ* __restrict__ z, int B, float* __restrict__ o
             const int xa = tab.i0[x], xb = tab.i1[x];
             const float lx0 = tab.l0[x], lx1 = tab.l1[x];
             const int64_t off = base + (int64_t)px * FCH + c8 * 8;
-            if (HALF) {
+            if (HALF && !fp32_interp) {
                 const uint4 ua = *reinterpret_cast<const uint4*>(s1 + (r0 * FS + xa) * FCH + c8 * 8);
                 const uint4 ub = *reinterpret_cast<const uint4*>(s1 + (r0 * FS + xb) * FCH + c8 * 8);
                 const uint4 uc = *reinterpret_cast<const uint4*>(s1 + (r1 * FS + xa) * FCH + c8 * 8);
@@ -467,9 +467,9 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st) {
     EGR_CHECK(J <= HJ && (2 * Hs) % STRIP == 0 && G <= 4, EGR_ERR_UNSUPPORTED, "head_up_conv: J=%d Hs=%d G=%d", J, Hs, G);
-    if (Hs == FS && Ws == FS && C == FCH && z_bf16 == 2)      // tensor-core tail (head_tail_tc.cu): fp16 z, bf16 hm_t
-        return head_tail_tc(z, w, bias, wsel_host, B, G, J, hm, hm_bs, hm_gs, hm_t, st);
-    EGR_CHECK(z_bf16 != 2, EGR_ERR_UNSUPPORTED, "head_up_conv: fp16 z needs the 32x32x128 geometry");
+    if (Hs == FS && Ws == FS && C == FCH && z_bf16 >= 2)      // tensor-core tail (head_tail_tc.cu): fp16 z, bf16 (2) / fp16 (3) hm_t
+        return head_tail_tc(z, w, bias, wsel_host, B, G, J, hm, hm_bs, hm_gs, hm_t, z_bf16 == 3, st);
+    EGR_CHECK(z_bf16 < 2, EGR_ERR_UNSUPPORTED, "head_up_conv: fp16 z needs the 32x32x128 geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;
         const size_t fsmem = sizeof(float) * FCH * HJ + es * FROWS * FS * 130;
@@ -547,7 +547,7 @@ up2_relu_dual_kernel(const TZ* __restrict__ z, int B, int Hs, int Ws, int C, flo
 }
 
 int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st) {
+                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st, int fp32_interp) {
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_dt ? 2 : 4;
@@ -557,15 +557,15 @@ int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, 
         if (z_dt == 2) {
             auto k = up2_relu_dual_fast_kernel<__half>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __half*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __half*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt, fp32_interp);
         } else if (z_dt == 1) {
             auto k = up2_relu_dual_fast_kernel<__nv_bfloat16>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const __nv_bfloat16*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt, fp32_interp);
         } else {
             auto k = up2_relu_dual_fast_kernel<float>;
             EGR_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt);
+            EGR_LAUNCH(k, fgrid, 256, fsmem, st, (const float*)z, B, out_nchw, o_bs, o_gs, cl0, cl0_dt, cl1, cl1_dt, fp32_interp);
         }
         return EGR_OK;
     }
@@ -713,7 +713,48 @@ int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st) {
 __global__ void copy_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
 }
+__global__ void split_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n, int K) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K;
+        const int k = (int)(i - r * K);
+        const float w = in[i];
+        __half hi, lo;
+        ActT<__half>::st(&hi, w);
+        ActT<__half>::st(&lo, w - __half2float(hi));
+        out[r * 2 * K + k] = hi;
+        out[r * 2 * K + K + k] = lo;
+    }
+}
+int split_f16(const float* in, __half* out, int64_t R, int K, cudaStream_t st) {
+    const int64_t n = R * K;
+    if (n == 0) return EGR_OK;
+    const int64_t g = ceil_div64(n, 256);
+    split_f16_kernel<<<(int)(g < 148 * 64 ? g : 148 * 64), 256, 0, st>>>(in, out, n, K);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+__global__ void split3_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n, int K) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K;
+        const int k = (int)(i - r * K);
+        const float w = in[i];
+        const float hi = round_tf32(w);
+        out[r * 3 * K + k] = hi;
+        out[r * 3 * K + K + k] = hi;
+        out[r * 3 * K + 2 * K + k] = round_tf32(w - hi);
+    }
+}
+int split3_tf32(const float* in, float* out, int64_t R, int K, cudaStream_t st) {
+    const int64_t n = R * K;
+    if (n == 0) return EGR_OK;
+    const int64_t g = ceil_div64(n, 256);
+    split3_tf32_kernel<<<(int)(g < 148 * 64 ? g : 148 * 64), 256, 0, st>>>(in, out, n, K);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
 int cast_act(const float* in, void* out, int out_bf16, int64_t n, cudaStream_t st) {
+    if (out_bf16 == 2) return cast_f16(in, (__half*)out, n, st);
     if (out_bf16) return cast_bf16(in, (__nv_bfloat16*)out, n, st);
     if (n == 0) return EGR_OK;
     const int64_t g = ceil_div64(n, 256);

@@ -7,7 +7,7 @@ namespace egr {
 // in  [B][V][C][HW] fp32 (NCHW per view)  ->  out [V][B][HW][C] (view-major, channels-last)
 // out_mode: 0 fp32, 1 bf16, 2 fp32 rounded to the nearest TF32 value (operand of a kind::tf32 stage), 3 fp16
 int nchw_to_nhwc(const float* in, void* out, int B, int V, int C, int HW, int out_mode, cudaStream_t st);
-// fp32 -> activation dtype copy (float: plain copy)
+// fp32 -> activation dtype copy (out_bf16: 0 float = plain copy, 1 bf16, 2 fp16)
 int cast_act(const float* in, void* out, int out_bf16, int64_t n, cudaStream_t st);
 
 // Heatmap head tail over G groups of B images:  z [g][B][Hs*Ws][C] (pre-activation, channels-last)
@@ -17,16 +17,18 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st);
 
-// the same tail on the tensor cores: fp16 z (z_bf16 == 2 in head_up_conv), 32x32 -> 64x64, C = 128 (head_tail_tc.cu); hm_t bf16
+// the same tail on the tensor cores: fp16 z (z_bf16 == 2 / 3 in head_up_conv), 32x32 -> 64x64, C = 128 (head_tail_tc.cu);
+// hm_t bf16, or with precise != 0 (z_bf16 == 3, EGR_PREC_FP16) fp16 and the 1x1 weights as an fp16 hi + lo pair
 int head_tail_tc(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
-                 int64_t hm_bs, int64_t hm_gs, void* hm_t, cudaStream_t st);
+                 int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, cudaStream_t st);
 
 // R1 tail: z [g][B][Hs*Ws][C] (z_dt: 0 fp32, 1 bf16, 2 fp16) -> relu(up2(z)) written to
 //   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output; optional) and up to two channels-last copies
 //   cl0 / cl1 [g][B][4HsWs][C] with their own element types (cl*_dt: 0 fp32 rounded to TF32, 1 bf16, 2 fp16, 3 fp32 as is): the input of
 //   the H2 3x3 conv and the high-precision copy of the pose3d proposal branch (one shared fp16 copy when chained)
 int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st);
+                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st, int fp32_interp = 0);
+// fp32_interp: an fp16 z is interpolated in fp32 arithmetic (one rounding, EGR_PREC_FP16) instead of half2 (one per HFMA2)
 
 // nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C];  dt: 0 fp32, 1 bf16, 2 fp16
 int maxpool2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int W, int C, cudaStream_t st);
@@ -40,6 +42,10 @@ int round_tf32_inplace(float* p, int64_t n, cudaStream_t st);
 int cast_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t st);
 // fp32 -> fp16 copy (saturating)
 int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t st);
+// split weights of the EGR_PREC_FP16 stages: in [R][K] fp32 -> out [R][2K] fp16 = [hi | lo], hi = fp16(w), lo = fp16(w - hi)
+int split_f16(const float* in, __half* out, int64_t R, int K, cudaStream_t st);
+// "3x TF32" weights of the fp32-grade token Linears: out [R][3K] fp32 = [hi | hi | lo], hi = tf32(w), lo = tf32(w - hi)
+int split3_tf32(const float* in, float* out, int64_t R, int K, cudaStream_t st);
 // [R][C] -> [C][R]
 int transpose2d(const float* in, float* out, int R, int C, cudaStream_t st);
 // C[M][N] = A[M][K] · B[K][N] (+ bias[N] broadcast when non-null); small prepack-time products, fp32

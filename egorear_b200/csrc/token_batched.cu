@@ -24,7 +24,13 @@ __device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
     return r;
 }
 
-template <bool HAS_PTAB, int E>
+// two 16-bit values of the staged map -> fp32 (bf16: shifts; fp16: one cvt)
+template <bool F16> __device__ __forceinline__ void cvt16x2(uint32_t w, float& lo, float& hi) {
+    if (F16) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w)); lo = f.x; hi = f.y; }
+    else { lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u); }
+}
+
+template <bool HAS_PTAB, int E, bool F16>
 __global__ void __launch_bounds__(256, 4)
 tok_sample_kernel(TokSampleArgs a) {
     constexpr int NH = TOK_NH, P = TOK_P, HD = E / NH, RAWC = TOK_RAWC;
@@ -47,16 +53,21 @@ tok_sample_kernel(TokSampleArgs a) {
     const int v = (int)(r % a.V);
     const int b = (int)(r / a.V);
     const int64_t t = (int64_t)b * a.J + j, T_ = (int64_t)a.B * a.J;
-    float* Arow = a.A + (((int64_t)g * T_ + t) * a.V + v) * a.KA;
+    const int LO = a.V * a.KA;                                   // offset of the x_lo half of a split row
+    float* Arow = a.A + ((int64_t)g * T_ + t) * (int64_t)LO * (1 + a.split) + (int64_t)v * a.KA;
     const bool ok = a.valid[((int64_t)b * a.V + v) * a.J + j] != 0;
     if (h == 0) {     // validity column (carries output_proj's bias through the fold) + zero padding
         if (lane == 0) Arow[NH * RAWC + EX] = ok ? 1.f : 0.f;
         for (int c = NH * RAWC + EX + 1 + lane; c < a.KA; c += 32) Arow[c] = 0.f;
+        if (a.split) for (int c = NH * RAWC + EX + lane; c < a.KA; c += 32) Arow[LO + c] = 0.f;
     }
     if (!ok) {        // masked_fill(~anchors_valid, 0) after output_proj (:910 / :563): the whole row is zero
-        *reinterpret_cast<float4*>(Arow + h * RAWC + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (HAS_PTAB) *reinterpret_cast<float2*>(Arow + NH * RAWC + h * HD + lane * 2) = make_float2(0.f, 0.f);
-        else if (lane == 0) Arow[NH * RAWC + h] = 0.f;
+        for (int s2 = 0; s2 <= a.split; ++s2) {
+            float* R = Arow + s2 * LO;
+            *reinterpret_cast<float4*>(R + h * RAWC + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_PTAB) *reinterpret_cast<float2*>(R + NH * RAWC + h * HD + lane * 2) = make_float2(0.f, 0.f);
+            else if (lane == 0) R[NH * RAWC + h] = 0.f;
+        }
         return;
     }
     const float* oa = a.oa + ((int64_t)g * T_ + t) * TOK_OA;
@@ -102,13 +113,14 @@ tok_sample_kernel(TokSampleArgs a) {
 #pragma unroll
         for (int u = 0; u < UN; ++u) {
             const float coef = cf[u];
-            s8[0] = fmaf(coef, __uint_as_float(x[u].x << 16), s8[0]); s8[1] = fmaf(coef, __uint_as_float(x[u].x & 0xffff0000u), s8[1]);
-            s8[2] = fmaf(coef, __uint_as_float(x[u].y << 16), s8[2]); s8[3] = fmaf(coef, __uint_as_float(x[u].y & 0xffff0000u), s8[3]);
-            s8[4] = fmaf(coef, __uint_as_float(x[u].z << 16), s8[4]); s8[5] = fmaf(coef, __uint_as_float(x[u].z & 0xffff0000u), s8[5]);
-            s8[6] = fmaf(coef, __uint_as_float(x[u].w << 16), s8[6]); s8[7] = fmaf(coef, __uint_as_float(x[u].w & 0xffff0000u), s8[7]);
+            float f0, f1;
+            cvt16x2<F16>(x[u].x, f0, f1); s8[0] = fmaf(coef, f0, s8[0]); s8[1] = fmaf(coef, f1, s8[1]);
+            cvt16x2<F16>(x[u].y, f0, f1); s8[2] = fmaf(coef, f0, s8[2]); s8[3] = fmaf(coef, f1, s8[3]);
+            cvt16x2<F16>(x[u].z, f0, f1); s8[4] = fmaf(coef, f0, s8[4]); s8[5] = fmaf(coef, f1, s8[5]);
+            cvt16x2<F16>(x[u].w, f0, f1); s8[6] = fmaf(coef, f0, s8[6]); s8[7] = fmaf(coef, f1, s8[7]);
             if (HAS_PTAB) {
-                e4[0] = fmaf(coef, __uint_as_float(pu[u].x << 16), e4[0]); e4[1] = fmaf(coef, __uint_as_float(pu[u].x & 0xffff0000u), e4[1]);
-                e4[2] = fmaf(coef, __uint_as_float(pu[u].y << 16), e4[2]); e4[3] = fmaf(coef, __uint_as_float(pu[u].y & 0xffff0000u), e4[3]);
+                cvt16x2<F16>(pu[u].x, f0, f1); e4[0] = fmaf(coef, f0, e4[0]); e4[1] = fmaf(coef, f1, e4[1]);
+                cvt16x2<F16>(pu[u].y, f0, f1); e4[2] = fmaf(coef, f0, e4[2]); e4[3] = fmaf(coef, f1, e4[3]);
             } else {
                 wsum += coef;
             }
@@ -124,12 +136,25 @@ tok_sample_kernel(TokSampleArgs a) {
     }
     if (half == 0) {
         float4* o = reinterpret_cast<float4*>(Arow + h * RAWC + l16 * 8);
-        o[0] = make_float4(round_tf32(s8[0]), round_tf32(s8[1]), round_tf32(s8[2]), round_tf32(s8[3]));
-        o[1] = make_float4(round_tf32(s8[4]), round_tf32(s8[5]), round_tf32(s8[6]), round_tf32(s8[7]));
-        if (HAS_PTAB)
-            *reinterpret_cast<float4*>(Arow + NH * RAWC + h * HD + l16 * 4) =
-                make_float4(round_tf32(e4[0]), round_tf32(e4[1]), round_tf32(e4[2]), round_tf32(e4[3]));
-        else if (l16 == 0) Arow[NH * RAWC + h] = round_tf32(wsum);
+        if (a.split) {
+            o[0] = make_float4(s8[0], s8[1], s8[2], s8[3]);
+            o[1] = make_float4(s8[4], s8[5], s8[6], s8[7]);
+            float4* ol = reinterpret_cast<float4*>(Arow + LO + h * RAWC + l16 * 8);
+            ol[0] = make_float4(tf32_lo(s8[0]), tf32_lo(s8[1]), tf32_lo(s8[2]), tf32_lo(s8[3]));
+            ol[1] = make_float4(tf32_lo(s8[4]), tf32_lo(s8[5]), tf32_lo(s8[6]), tf32_lo(s8[7]));
+            if (HAS_PTAB) {
+                *reinterpret_cast<float4*>(Arow + NH * RAWC + h * HD + l16 * 4) = make_float4(e4[0], e4[1], e4[2], e4[3]);
+                *reinterpret_cast<float4*>(Arow + LO + NH * RAWC + h * HD + l16 * 4) =
+                    make_float4(tf32_lo(e4[0]), tf32_lo(e4[1]), tf32_lo(e4[2]), tf32_lo(e4[3]));
+            } else if (l16 == 0) { Arow[NH * RAWC + h] = wsum; Arow[LO + NH * RAWC + h] = tf32_lo(wsum); }
+        } else {
+            o[0] = make_float4(round_tf32(s8[0]), round_tf32(s8[1]), round_tf32(s8[2]), round_tf32(s8[3]));
+            o[1] = make_float4(round_tf32(s8[4]), round_tf32(s8[5]), round_tf32(s8[6]), round_tf32(s8[7]));
+            if (HAS_PTAB)
+                *reinterpret_cast<float4*>(Arow + NH * RAWC + h * HD + l16 * 4) =
+                    make_float4(round_tf32(e4[0]), round_tf32(e4[1]), round_tf32(e4[2]), round_tf32(e4[3]));
+            else if (l16 == 0) Arow[NH * RAWC + h] = round_tf32(wsum);
+        }
     }
 }
 
@@ -137,11 +162,16 @@ int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st) {
     const bool ptab = a.ptab != nullptr;
     EGR_CHECK((a.E == 256 && ptab) || (a.E == 128 && !ptab), EGR_ERR_UNSUPPORTED, "tok_sample: E=%d ptab=%d", a.E, (int)ptab);
     EGR_CHECK(a.KA == tok_ka(a.E, ptab), EGR_ERR_INVALID, "tok_sample: KA=%d", a.KA);
-    EGR_CHECK(act_bf16, EGR_ERR_UNSUPPORTED, "tok_sample: the batched token path samples the bf16 channels-last copy");
+    EGR_CHECK(act_bf16 == 1 || act_bf16 == 2, EGR_ERR_UNSUPPORTED, "tok_sample: the batched token path samples a 16-bit channels-last copy");
     const int64_t total = (int64_t)a.G * a.B * a.J * a.V * TOK_NH;
     const int blocks = (int)ceil_div64(total, 8);
-    if (ptab) EGR_LAUNCH((tok_sample_kernel<true, 256>), blocks, 256, 0, st, a);
-    else EGR_LAUNCH((tok_sample_kernel<false, 128>), blocks, 256, 0, st, a);
+    if (act_bf16 == 2) {
+        if (ptab) EGR_LAUNCH((tok_sample_kernel<true, 256, true>), blocks, 256, 0, st, a);
+        else EGR_LAUNCH((tok_sample_kernel<false, 128, true>), blocks, 256, 0, st, a);
+    } else {
+        if (ptab) EGR_LAUNCH((tok_sample_kernel<true, 256, false>), blocks, 256, 0, st, a);
+        else EGR_LAUNCH((tok_sample_kernel<false, 128, false>), blocks, 256, 0, st, a);
+    }
     return EGR_OK;
 }
 
@@ -150,7 +180,7 @@ int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st) {
 // =====================================================================================================
 template <int E>
 __global__ void __launch_bounds__(128)
-tok_attn_kernel(const float* __restrict__ qkv, float* __restrict__ o, int J) {
+tok_attn_kernel(const float* __restrict__ qkv, float* __restrict__ o, int J, int split) {
     constexpr int NH = TOK_NH, HD = E / NH, LD = HD + 1, MJ = 16;
     extern __shared__ float sm[];
     pdl_trigger();
@@ -200,23 +230,23 @@ tok_attn_kernel(const float* __restrict__ qkv, float* __restrict__ o, int J) {
         for (int d = lane; d < HD; d += 32) {
             float acc = 0.f;
             for (int jk = 0; jk < J; ++jk) acc = fmaf(pr[j * MJ + jk], v[jk * LD + d], acc);
-            o[(t0 + j) * E + h * HD + d] = round_tf32(acc);
+            tok_operand_store(o + (t0 + j) * E * (1 + split), h * HD + d, E, acc, split);
         }
     }
 }
 
-int tok_attn(const float* qkv, float* o, int n_frames, int J, int E, cudaStream_t st) {
+int tok_attn(const float* qkv, float* o, int n_frames, int J, int E, cudaStream_t st, int split) {
     EGR_CHECK(J <= 16 && (E == 128 || E == 256), EGR_ERR_UNSUPPORTED, "tok_attn: J=%d E=%d", J, E);
     const int HD = E / TOK_NH;
     const size_t smem = sizeof(float) * TOK_NH * (3 * 16 * (HD + 1) + 16 * 16);
     if (E == 256) {
         auto kfn = tok_attn_kernel<256>;
         EGR_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        EGR_LAUNCH(kfn, n_frames, 128, smem, st, qkv, o, J);
+        EGR_LAUNCH(kfn, n_frames, 128, smem, st, qkv, o, J, split);
     } else {
         auto kfn = tok_attn_kernel<128>;
         EGR_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        EGR_LAUNCH(kfn, n_frames, 128, smem, st, qkv, o, J);
+        EGR_LAUNCH(kfn, n_frames, 128, smem, st, qkv, o, J, split);
     }
     return EGR_OK;
 }
@@ -239,11 +269,12 @@ __device__ __forceinline__ void ln_row(const float* v_in, float (&v)[E / 32], fl
 template <int E>
 __global__ void __launch_bounds__(256)
 tok_add_ln_kernel(const float* __restrict__ res, const float* __restrict__ z, float* __restrict__ out, int64_t rows,
-                  int rows_per_group, const float* const* __restrict__ gamma, const float* const* __restrict__ beta) {
+                  int rows_per_group, const float* const* __restrict__ gamma, const float* const* __restrict__ beta, int split) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int64_t ldr = (int64_t)E * (1 + split);      // res / out rows: [x | x_lo] when split
     if (row >= rows) return;
     const int g = (int)(row / rows_per_group);
     const float* ga = gamma[g];
@@ -252,23 +283,23 @@ tok_add_ln_kernel(const float* __restrict__ res, const float* __restrict__ z, fl
 #pragma unroll
     for (int i = 0; i < E / 32; ++i) {
         const int c = lane + 32 * i;
-        v[i] = z[row * E + c] + (res ? res[row * E + c] : 0.f);
+        v[i] = z[row * E + c] + (res ? res[row * ldr + c] : 0.f);
     }
     float mean, rstd;
     ln_row<E>(nullptr, v, mean, rstd);
 #pragma unroll
     for (int i = 0; i < E / 32; ++i) {
         const int c = lane + 32 * i;
-        out[row * E + c] = round_tf32((v[i] - mean) * rstd * __ldg(ga + c) + __ldg(be + c));
+        tok_operand_store(out + row * ldr, c, E, (v[i] - mean) * rstd * __ldg(ga + c) + __ldg(be + c), split);
     }
 }
 
 int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per_group, int E, const float* const* gamma,
-               const float* const* beta, cudaStream_t st) {
+               const float* const* beta, cudaStream_t st, int split) {
     const int64_t rows = (int64_t)G * rows_per_group;
     const int blocks = (int)ceil_div64(rows, 8);
-    if (E == 256) EGR_LAUNCH(tok_add_ln_kernel<256>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta);
-    else if (E == 128) EGR_LAUNCH(tok_add_ln_kernel<128>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta);
+    if (E == 256) EGR_LAUNCH(tok_add_ln_kernel<256>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta, split);
+    else if (E == 128) EGR_LAUNCH(tok_add_ln_kernel<128>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta, split);
     else return fail(EGR_ERR_UNSUPPORTED, "tok_add_ln: E=%d", E);
     return EGR_OK;
 }
@@ -319,7 +350,7 @@ int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int
 // mvfex jqa query input (HeatmapMVF.forward :655-665): x0 = embed_j + fc_bfb(avgpool(bfb)) + heatmap_proj(heatmap_j)
 // =====================================================================================================
 __global__ void __launch_bounds__(256)
-tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* __restrict__ pooled, int B, int C) {
+tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* __restrict__ pooled, int B, int C, int split) {
     // hw == 64: a half-warp per channel, one float4 per lane (256 B per channel, coalesced), 4 shuffle steps
     pdl_trigger();
     pdl_wait();
@@ -332,30 +363,49 @@ tok_avgpool_kernel(const float* __restrict__ bfb, int64_t bfb_bs, int64_t bfb_gs
         float s = (v.x + v.y) + (v.z + v.w);
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (l16 == 0) pooled[(int64_t)blockIdx.x * C + c] = round_tf32(s / (float)hw);
+        if (l16 == 0) tok_operand_store(pooled + (int64_t)blockIdx.x * C * (1 + split), c, C, s / (float)hw, split);
     }
 }
-int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st) {
+int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st, int split) {
     EGR_CHECK(hw == 64 && C % 64 == 0, EGR_ERR_UNSUPPORTED, "tok_avgpool: hw=%d C=%d (stride-32 map of a 256x256 image is 8x8)", hw, C);
-    EGR_LAUNCH(tok_avgpool_kernel, dim3(G * B, 4), 256, 0, st, bfb, bfb_bs, bfb_gs, hw, pooled, B, C);
+    EGR_LAUNCH(tok_avgpool_kernel, dim3(G * B, 4), 256, 0, st, bfb, bfb_bs, bfb_gs, hw, pooled, B, C, split);
     return EGR_OK;
 }
 
 __global__ void __launch_bounds__(256)
 tok_add_query_kernel(const float* __restrict__ y0, const float* __restrict__ vb, const float* const* __restrict__ jq,
-                     float* __restrict__ x0, int B, int J, int E) {
+                     float* __restrict__ x0, int B, int J, int E, int split) {
     pdl_trigger();
     pdl_wait();
     const int g = blockIdx.x / B;
     const float* q = jq[g];
     const int64_t base = (int64_t)blockIdx.x * J * E;
     for (int i = threadIdx.x; i < J * E; i += 256) {
-        const int n = i % E;
-        x0[base + i] = round_tf32(__ldg(q + i) + vb[(int64_t)blockIdx.x * E + n] + y0[base + i]);
+        const int j = i / E, n = i - j * E;
+        tok_operand_store(x0 + ((int64_t)blockIdx.x * J + j) * E * (1 + split), n, E,
+                          __ldg(q + i) + vb[(int64_t)blockIdx.x * E + n] + y0[base + i], split);
     }
 }
-int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st) {
-    EGR_LAUNCH(tok_add_query_kernel, G * B, 256, 0, st, y0, vb, jq, x0, B, J, E);
+int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st, int split) {
+    EGR_LAUNCH(tok_add_query_kernel, G * B, 256, 0, st, y0, vb, jq, x0, B, J, E, split);
+    return EGR_OK;
+}
+
+__global__ void __launch_bounds__(256)
+tok_make_lo_kernel(float* __restrict__ buf, int64_t n, int K) {
+    pdl_trigger();
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // one float4 of the x half
+    if (i * 4 >= n) return;
+    const int64_t e = i * 4, r = e / K;
+    const int c = (int)(e - r * K);
+    const float4 x = *reinterpret_cast<const float4*>(buf + r * 2 * K + c);
+    *reinterpret_cast<float4*>(buf + r * 2 * K + K + c) = make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w));
+}
+int tok_make_lo(float* buf, int64_t rows, int K, cudaStream_t st) {
+    EGR_CHECK(K % 4 == 0, EGR_ERR_UNSUPPORTED, "tok_make_lo: K=%d", K);
+    const int64_t n = rows * K;
+    EGR_LAUNCH(tok_make_lo_kernel, (int)ceil_div64(n / 4, 256), 256, 0, st, buf, n, K);
     return EGR_OK;
 }
 

@@ -34,6 +34,7 @@ __host__ __device__ constexpr int tok_ka(int E, bool has_ptab) {
 //   A       [G][T][V][KA] fp32, rounded to TF32
 struct TokSampleArgs {
     int G, B, V, J, H, W, E, KA;
+    int split;                          // rows of A are [x | x_lo] (2*V*KA floats), see tok_operand_store
     const float* oa;
     const float* anchors;
     const uint8_t* valid;
@@ -41,15 +42,30 @@ struct TokSampleArgs {
     const __nv_bfloat16* const* ptab;   // device array [G] of bf16 tables, or null
     float* A;
 };
-int tok_sample(const TokSampleArgs& a, int act_bf16, cudaStream_t st);
+int tok_sample(const TokSampleArgs& a, int act_bf16 /*1 bf16, 2 fp16*/, cudaStream_t st);
+
+// Operand layout of the fp32-grade ("3x TF32") token Linears of EGR_PREC_FP16 (gemm.cuh `ka`): a producer called with
+// split != 0 writes rows of 2K floats [x | x_lo]: x raw fp32 (the tensor core truncates it to TF32 = x_hi) and
+// x_lo = tf32(x - x_hi); with split == 0 it writes one row of K floats rounded to the nearest TF32 value.
+#if defined(__CUDACC__)
+__device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float x) { return round_tf32(x - tf32_trunc(x)); }
+__device__ __forceinline__ void tok_operand_store(float* row, int c, int lo_off, float v, int split) {
+    if (split) { row[c] = v; row[lo_off + c] = tf32_lo(v); }
+    else row[c] = round_tf32(v);
+}
+#endif
+// x_lo halves of rows produced by a GEMM epilogue: buf [rows][2K], cols [K, 2K) = tf32_lo(cols [0, K))
+int tok_make_lo(float* buf, int64_t rows, int K, cudaStream_t st);
 
 // joint self-attention (SpatialMHA / EgoformerSpatialMHA): qkv [G*B*J][3E] (q | k | v) -> o [G*B*J][E], rounded
-int tok_attn(const float* qkv, float* o, int n_frames /*G*B*/, int J, int E, cudaStream_t st);
+int tok_attn(const float* qkv, float* o, int n_frames /*G*B*/, int J, int E, cudaStream_t st, int split = 0);
 
 // out[row] = LayerNorm(res[row] + z[row]) * gamma[g] + beta[g]   (res may be null), rounded to TF32.
 //   rows = G * rows_per_group; gamma / beta are device arrays of G pointers
+//   split: res / out rows are [x | x_lo] (2E floats; z stays a plain GEMM output of E floats)
 int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per_group, int E, const float* const* gamma,
-               const float* const* beta, cudaStream_t st);
+               const float* const* beta, cudaStream_t st, int split = 0);
 
 // mvfex post_norm + token image: LN rows of x [G][B][J][E] -> xT [G][B][E][16] (pos-major, joint-minor, col 15 = 0)
 int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int E, const float* const* gamma,
@@ -58,16 +74,17 @@ int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int
 // the same post_norm + token image followed by TransformerHeadLayer's two 1x1 convs (the second commuted in front of the
 // upsample) in one tcgen05 kernel (token_head_tc.cu):  x [G][B][J][256] -> t1 [G][B][256 pos][128] bf16
 //   w0 [sets][64][16] (15 padded to 16), b0 [sets][64], w3 [sets][128][64], b3 [sets][128]; group g uses set r0 + g
+//   ldx: row stride of x in floats (256, or 512 for [x | x_lo] rows); f16: hidden / W3 / t1 in fp16 with W3 as a hi + lo pair
 int tok_head_tc(const float* x, int G, int B, int J, const float* const* gamma, const float* const* beta, const float* w0,
-                const float* b0, const float* w3, const float* b3, int r0, void* t1, cudaStream_t st);
+                const float* b0, const float* w3, const float* b3, int r0, void* t1, cudaStream_t st, int ldx = 256, int f16 = 0);
 
 // mvfex jqa query input (HeatmapMVF.forward :655-665), in three steps:
 //   tok_avgpool:   pooled[g][b][512] = adaptive_avg_pool2d(bfb[g][b], 1), rounded     (bfb of group g, frame b at
 //                  bfb + g*bfb_gs + b*bfb_bs: [512][hw])
 //   (token GEMM)   vb[g][b][E] = fc_bfb(pooled)
 //   tok_add_query: x0[g][b][j][:] = y0[g][b][j][:] + vb[g][b][:] + joint_query_embed[g][j][:], rounded
-int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st);
-int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st);
+int tok_avgpool(const float* bfb, int64_t bfb_bs, int64_t bfb_gs, int hw, float* pooled, int G, int B, int C, cudaStream_t st, int split = 0);
+int tok_add_query(const float* y0, const float* vb, const float* const* jq, float* x0, int G, int B, int J, int E, cudaStream_t st, int split = 0);
 
 // pose3d: P3 reprojection of the proposal + first query_gen Linear(4 -> E) + ReLU
 struct PoseQueryArgs {

@@ -13,7 +13,8 @@ import torch
 from . import _lib
 from .ops import _ptr, _stream, calib_table
 
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "fp16": 3}      # EGR_PREC_* (include/egorear_b200.h)
+ACT_DTYPE = {"bf16": torch.bfloat16, "fp16": torch.float16}
 CAMERA_MODEL_ID = {"ego4view_syn": 0, "ego4view_rw": 1, "ego4view_syn_stereo_front": 2, "ego4view_rw_stereo_front": 3,
                    "ego4view_syn_stereo_back": 4, "ego4view_rw_stereo_back": 5}
 
@@ -35,8 +36,9 @@ class _EngineBase:
         self._tensors = {}
         self._sig = None
         self._ws_lanes = {}          # lane -> cached workspace tensor (concurrent forwards on different streams)
-        self.lane = 0
+        self.lane = 0                # lane of the LAST forward (debug_buffer reads its workspace); forwards take `lane=` explicitly
         self.frozen = False
+        self._calls = 0
 
     def _fn(self, name):
         return getattr(self._lib, "egr_%s_%s" % (self._prefix, name))
@@ -65,8 +67,17 @@ class _EngineBase:
             self._tensors[k] = t
         self._sig = None
 
+    def invalidate(self):
+        """parameters were changed behind the module's back (in-place edits outside load_state_dict / .to()): re-pack"""
+        self._sig = None
+
     def _sync_params(self):
-        if self.frozen and self._sig is not None:
+        """Re-register + re-pack when a parameter changed.  The owning module invalidates on load_state_dict / .to() /
+        .cuda() / .float() (`_EngineOwner`); on top of that the version counters of all tensors (~570 for mvfex) are
+        compared on the first call and then every 32nd one, so that an in-place edit is not missed for long while the
+        common eval loop does not walk the list per forward.  frozen: never re-checked."""
+        self._calls += 1
+        if self._sig is not None and (self.frozen or self._calls % 32 != 1):
             return
         sig = self._signature()
         if sig == self._sig:
@@ -79,14 +90,17 @@ class _EngineBase:
                 keep.append(d)
             _lib.check(self._fn("set_param")(self._h, k.encode(), _ptr(d), d.numel()))
         self._keep = keep
-        _lib.check(self._fn("prepack")(self._h, _stream()))
+        any_t = next(iter(self._tensors.values()))
+        with torch.cuda.device_of(any_t):              # the parameters' device, not whatever is current
+            _lib.check(self._fn("prepack")(self._h, _stream(any_t)))
         self._sig = sig
 
-    def _workspace(self, B, device):
+    def _workspace(self, B, device, lane=0):
         need = int(self._fn("workspace_bytes")(self._h, B))
-        ws = self._ws_lanes.get(self.lane)
+        self.lane = lane
+        ws = self._ws_lanes.get(lane)
         if ws is None or ws.numel() < need or ws.device != device:
-            ws = self._ws_lanes[self.lane] = torch.empty(need, dtype=torch.uint8, device=device)
+            ws = self._ws_lanes[lane] = torch.empty(need, dtype=torch.uint8, device=device)
         return ws
 
     @property
@@ -120,7 +134,7 @@ class MvfexEngine(_EngineBase):
         _lib.check(self._lib.egr_mvfex_export_staged(self._h, mode))
         self._export, self._export_hp = bool(enable), hp
 
-    def forward(self, feat, bfb, heatmap_for_anchor=None, want_feat_refined=True, feat_staged=None):
+    def forward(self, feat, bfb, heatmap_for_anchor=None, want_feat_refined=True, feat_staged=None, lane=0):
         """feat [B,V,128,64,64], bfb [B,V,512,8,8] fp32 CUDA ->
         dict(hm_init, hm_refined [B,V,15,64,64], feat_refined [B,V,128,64,64], anchors_2d [B,V,15,2], anchors_valid).
         want_feat_refined=False (needs export_staged): the NCHW fp32 refined features are not materialised (None).
@@ -130,7 +144,9 @@ class MvfexEngine(_EngineBase):
         feat_arg = feat
         if feat_staged is not None:
             V, B = feat_staged.shape[:2]
-            assert feat_staged.dtype == torch.bfloat16 and feat_staged.is_contiguous() and tuple(feat_staged.shape[2:]) == (64, 64, 128)
+            if self.precision not in ACT_DTYPE:
+                raise RuntimeError("feat_staged needs the bf16 precision (bf16 copy) or the fp16 precision (fp16 copy)")
+            assert feat_staged.dtype == ACT_DTYPE[self.precision] and feat_staged.is_contiguous() and tuple(feat_staged.shape[2:]) == (64, 64, 128)
             feat = None
         else:
             B, V = feat.shape[:2]
@@ -147,14 +163,15 @@ class MvfexEngine(_EngineBase):
             "anchors_2d": torch.empty((B, V, self.J, 2), dtype=torch.float32, device=dev),
             "anchors_valid": torch.empty((B, V, self.J), dtype=torch.bool, device=dev),
         }
-        ws = self._workspace(B, dev)
+        ws = self._workspace(B, dev, lane)
         if feat_staged is not None:
             _lib.check(self._lib.egr_mvfex_use_staged_input(self._h, _ptr(feat_staged)))
             out["_keepalive"] = feat_staged          # the staged copies exported to a chained pose3d point into it
-        _lib.check(self._lib.egr_mvfex_forward(self._h, B, _ptr(feat), _ptr(bfb), _ptr(hfa), _ptr(out["hm_init"]),
-                                               _ptr(out["hm_refined"]), _ptr(out["feat_refined"]),
-                                               _ptr(out["anchors_2d"]), _ptr(out["anchors_valid"]), _ptr(ws),
-                                               ws.numel(), _stream()))
+        with torch.cuda.device_of(bfb):
+            _lib.check(self._lib.egr_mvfex_forward(self._h, B, _ptr(feat), _ptr(bfb), _ptr(hfa), _ptr(out["hm_init"]),
+                                                   _ptr(out["hm_refined"]), _ptr(out["feat_refined"]),
+                                                   _ptr(out["anchors_2d"]), _ptr(out["anchors_valid"]), _ptr(ws),
+                                                   ws.numel(), _stream(bfb)))
         if getattr(self, "_export", False):
             pi, pr, pt, bf = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
             _lib.check(self._lib.egr_mvfex_staged(self._h, ctypes.byref(pi), ctypes.byref(pr), ctypes.byref(pt), ctypes.byref(bf)))
@@ -180,9 +197,10 @@ class MvfexEngine(_EngineBase):
         hm = torch.empty((B, self.J, 64, 64), dtype=torch.float32, device=dev)
         ft = torch.empty((B, 128, 64, 64), dtype=torch.float32, device=dev)
         ws = self._workspace(B, dev)
-        _lib.check(self._lib.egr_mvfex_refiner_forward(self._h, r, B, _ptr(heatmap), _ptr(frame_feat), _ptr(feat_mv),
-                                                       _ptr(a2), _ptr(av), _ptr(bfb), _ptr(hm), _ptr(ft), _ptr(ws),
-                                                       ws.numel(), _stream()))
+        with torch.cuda.device_of(heatmap):
+            _lib.check(self._lib.egr_mvfex_refiner_forward(self._h, r, B, _ptr(heatmap), _ptr(frame_feat), _ptr(feat_mv),
+                                                           _ptr(a2), _ptr(av), _ptr(bfb), _ptr(hm), _ptr(ft), _ptr(ws),
+                                                           ws.numel(), _stream(heatmap)))
         return hm, ft
 
 
@@ -207,7 +225,7 @@ class Pose3DEngine(_EngineBase):
         """operand type of the proposal branch: "fp32", "bf16", "tf32" or "f16" """
         return ("fp32", "bf16", "tf32", "f16")[int(self._lib.egr_pose3d_proposal_dtype(self._h))]
 
-    def forward(self, feats_init, feats_final, coord_trans_mat=None, staged=None, use_init=True):
+    def forward(self, feats_init, feats_final, coord_trans_mat=None, staged=None, use_init=True, lane=0):
         """-> preds [L+1, B, 16, 3] fp32 (cm): preds[0] MLP proposal, preds[1:] transformer layers.
         staged: MvfexEngine.forward(...)["staged"] of the SAME tensors (chained forward): skips the re-staging passes."""
         self._sync_params()
@@ -227,15 +245,21 @@ class Pose3DEngine(_EngineBase):
             if coord_trans_mat.dtype != torch.float32:
                 # the reference matmuls this against fp32 points (utils/camera_models.py:210): dtype error there too
                 raise RuntimeError("expected m1 and m2 to have the same dtype, but got: double != float")
+            if not coord_trans_mat.is_cuda or coord_trans_mat.device != dev:
+                raise RuntimeError("coord_trans_mat must live on the features' CUDA device (%s)" % dev)
+            if tuple(coord_trans_mat.shape) != (B, V, 4, 4):
+                # the kernel strides by the model's camera count; the reference indexes [:, v] and would fail differently
+                raise RuntimeError("coord_trans_mat must be [B=%d, n_cams=%d, 4, 4], got %s" % (B, V, tuple(coord_trans_mat.shape)))
             ctm = coord_trans_mat.contiguous()
         preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=dev)
-        ws = self._workspace(B, dev)
+        ws = self._workspace(B, dev, lane)
         if staged is not None and staged["feat_refined"] is feats_final and (staged["feat"] is feats_init or not use_init):
             sampled = staged["init"] if use_init else staged["refined"]
             _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),
                                                        ctypes.c_void_p(staged["refined_tf32"]) if staged["refined_tf32"] else None))
             if staged.get("refined_f16"):
                 _lib.check(self._lib.egr_pose3d_use_staged_final_f16(self._h, ctypes.c_void_p(staged["refined_f16"])))
-        _lib.check(self._lib.egr_pose3d_forward(self._h, B, _ptr(fi), _ptr(ff), _ptr(ctm), _ptr(preds), _ptr(ws),
-                                                ws.numel(), _stream()))
+        with torch.cuda.device_of(preds):
+            _lib.check(self._lib.egr_pose3d_forward(self._h, B, _ptr(fi), _ptr(ff), _ptr(ctm), _ptr(preds), _ptr(ws),
+                                                    ws.numel(), _stream(preds)))
         return preds

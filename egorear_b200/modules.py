@@ -30,6 +30,49 @@ from .engine import MvfexEngine, Pose3DEngine
 _VIEWS4 = ("front_left", "front_right", "back_left", "back_right")
 
 
+class _EngineOwner:
+    """Mixin of the three modules that own a C engine (HeatmapMVF standalone, EgoPoseFormerHeatmapMVFEX,
+    EgoPoseFormerPose3D): keeps the pointers the engine registered in step with the module's parameters.
+    .to() / .cuda() / .float() re-create the tensors -> re-register; load_state_dict writes in place -> re-pack;
+    forward under training mode with grad enabled raises instead of failing later with an opaque autograd error
+    (the engines are inference-only: they detach everything)."""
+    _engine = None
+
+    def _engine_params(self):
+        raise NotImplementedError
+
+    def _make_engine(self):
+        raise NotImplementedError
+
+    def engine(self):
+        if self._engine is None:
+            self._engine = self._make_engine()
+            self._engine.set_params(self._engine_params())
+            if not getattr(self, "_egr_hooked", False):
+                self.register_load_state_dict_post_hook(
+                    lambda module, incompatible_keys: module._engine.invalidate() if module._engine is not None else None)
+                self._egr_hooked = True
+        return self._engine
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if self._engine is not None:       # tensors were re-created (.cuda(), .float(), ...): re-register
+            st = self._engine_params()
+            if all(v.is_cuda for v in st.values()):
+                self._engine.set_params(st)
+            else:
+                self._engine = None        # moved off the GPU: the engine is rebuilt when it comes back
+        return out
+
+    def _check_inference(self):
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError(
+                "egorear_b200.%s.forward is inference-only (the CUDA engine detaches its inputs and parameters): call "
+                ".eval() or run under torch.no_grad().  For `run.py fit` keep the reference classes for this module "
+                "(egorear_b200.patch(modules=[...]) without it); the training-side kernels live in egorear_b200.train."
+                % type(self).__name__)
+
+
 def _seq_conv(spec):
     """spec: list of ("conv", cin, cout, k, s, p) | "relu" | "up" | "pool" -> nn.Sequential with the reference's indices."""
     layers = []
@@ -339,7 +382,7 @@ class TransformerHeadLayer(nn.Module):                           # egoposeformer
 # ------------------------------------------------------------------------------------------------------
 # HeatmapMVF                                                   egoposeformer_heatmap_mvf_ex.py:442-731
 # ------------------------------------------------------------------------------------------------------
-class HeatmapMVF(nn.Module):
+class HeatmapMVF(_EngineOwner, nn.Module):
     def __init__(self, input_dims, embed_dims, num_former_layers, image_size, feat_down_stride, detach_heatmap_feat,
                  mvf_transformer_cfg, heatmap_threshold, num_views, num_heatmap, joint_query_adaptation=False,
                  joint_query_adaptation_multi_view=False, joint_query_only=False, use_1by1_conv=False,
@@ -380,21 +423,24 @@ class HeatmapMVF(nn.Module):
         self._precision = precision
         self._engine = None   # standalone use (not owned by an EgoPoseFormerHeatmapMVFEX)
 
+    def _engine_params(self):
+        return {"heatmap_refiner_front_left." + k: v for k, v in self.state_dict(keep_vars=True).items() if v.is_floating_point()}
+
+    def _make_engine(self):
+        return MvfexEngine(self.num_views, self.num_heatmap, self.heatmap_threshold, self._precision)
+
     def forward(self, heatmap, frame_feat, frame_feat_multi_view, anchors_2d, anchors_valid, backbone_feat_bottom,
                 backbone_feat_bottom_multi_view):
-        if self._engine is None:
-            self._engine = MvfexEngine(self.num_views, self.num_heatmap, self.heatmap_threshold, self._precision)
-            self._engine.set_params({"heatmap_refiner_front_left." + k: v for k, v in self.state_dict(keep_vars=True).items()
-                                     if v.is_floating_point()})
-        hm, ft = self._engine.refiner_forward(0, heatmap, frame_feat, frame_feat_multi_view, anchors_2d, anchors_valid,
-                                              backbone_feat_bottom)
+        self._check_inference()
+        hm, ft = self.engine().refiner_forward(0, heatmap, frame_feat, frame_feat_multi_view, anchors_2d, anchors_valid,
+                                               backbone_feat_bottom)
         return [hm], [ft]
 
 
 # ------------------------------------------------------------------------------------------------------
 # EgoPoseFormerHeatmapMVFEX                                     egoposeformer_heatmap_mvf_ex.py:27-437
 # ------------------------------------------------------------------------------------------------------
-class EgoPoseFormerHeatmapMVFEX(nn.Module):
+class EgoPoseFormerHeatmapMVFEX(_EngineOwner, nn.Module):
     def __init__(self, num_views, image_size, num_heatmap, feat_down_stride, heatmap_threshold, encoder_cfg, mvf_cfg,
                  camera_model, full_training=False, detach_heatmap_feat=False, detach_heatmap_feat_init=False,
                  use_pred_heatmap_init=False, no_detach_feat_init=False, precision="bf16", build_backbone=True, **kwargs):
@@ -433,21 +479,10 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
         return {k: v for k, v in self.state_dict(keep_vars=True).items()
                 if not k.startswith("heatmap_estimator_") and v.is_floating_point()}
 
-    def engine(self):
-        if self._engine is None:
-            self._engine = MvfexEngine(self.num_views, self.num_heatmap, self.heatmap_threshold, self._precision)
-            self._engine.set_params(self.hot_path_state())
-        return self._engine
+    _engine_params = hot_path_state
 
-    def _apply(self, fn, *a, **k):
-        out = super()._apply(fn, *a, **k)
-        if self._engine is not None:       # tensors were re-created (.cuda(), .float(), ...): re-register
-            st = self.hot_path_state()
-            if all(v.is_cuda for v in st.values()):
-                self._engine.set_params(st)
-            else:
-                self._engine = None        # moved off the GPU: the engine is rebuilt when it comes back
-        return out
+    def _make_engine(self):
+        return MvfexEngine(self.num_views, self.num_heatmap, self.heatmap_threshold, self._precision)
 
     def get_anchors_2d_from_hm(self, heatmap):           # :128-143
         with torch.no_grad():
@@ -465,14 +500,15 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
         return self.heatmap_estimator_stereo_front.forward_backbone(img, return_feat=True)
 
     def forward_from_feats(self, frame_feat_multi_view, backbone_feat_bottom_multi_view, heatmap_for_anchor=None,
-                           want_feat_refined=True, feat_staged=None):
+                           want_feat_refined=True, feat_staged=None, lane=0):
         """The hot path proper: backbone features in, (list_heatmap_pred, list_frame_feat) out (:284-437).
         want_feat_refined=False (chained forward with exported channels-last copies only): list_frame_feat[1] is None.
         feat_staged: view-major channels-last bf16 features [V,B,64,64,128] straight from a channels-last bf16 backbone
         (frame_feat_multi_view may then be None; see MvfexEngine.forward)."""
+        self._check_inference()
         hfa = heatmap_for_anchor if isinstance(heatmap_for_anchor, torch.Tensor) else None
         out = self.engine().forward(frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa,
-                                    want_feat_refined=want_feat_refined, feat_staged=feat_staged)
+                                    want_feat_refined=want_feat_refined, feat_staged=feat_staged, lane=lane)
         self.last_anchors = (out["anchors_2d"], out["anchors_valid"])
         self.last_staged = out.get("staged")
         return [out["hm_init"], out["hm_refined"]], [None if feat_staged is not None else frame_feat_multi_view, out["feat_refined"]]
@@ -491,7 +527,7 @@ class EgoPoseFormerHeatmapMVFEX(nn.Module):
 # ------------------------------------------------------------------------------------------------------
 # EgoPoseFormerPose3D / EgoPoseFormerMVFEX                         egoposeformer_mvf_ex.py:22-452
 # ------------------------------------------------------------------------------------------------------
-class EgoPoseFormerPose3D(nn.Module):
+class EgoPoseFormerPose3D(_EngineOwner, nn.Module):
     def __init__(self, num_views, image_size, use_pred_heatmap_init, num_joints, input_dims, embed_dims, mlp_dims,
                  mlp_dropout, num_mlp_layers, transformer_cfg, num_former_layers, num_pred_mlp_layers, camera_model,
                  feat_down_stride, coor_norm_max, coor_norm_min, conv_heatmap_dim_init, norm_mlp_pred=False,
@@ -541,28 +577,18 @@ class EgoPoseFormerPose3D(nn.Module):
         return {k: v for k, v in self.state_dict(keep_vars=True).items()
                 if v.is_floating_point() and not k.startswith("coor_")}
 
-    def engine(self):
-        if self._engine is None:
-            self._engine = Pose3DEngine(self.num_views, self.num_joints, len(self.layers), self.camera_model,
-                                        self.use_pred_heatmap_init, self._precision, self._calib)
-            self._engine.set_params(self.hot_path_state())
-        return self._engine
+    _engine_params = hot_path_state
 
-    def _apply(self, fn, *a, **k):
-        out = super()._apply(fn, *a, **k)
-        if self._engine is not None:
-            st = self.hot_path_state()
-            if all(v.is_cuda for v in st.values()):
-                self._engine.set_params(st)
-            else:
-                self._engine = None
-        return out
+    def _make_engine(self):
+        return Pose3DEngine(self.num_views, self.num_joints, len(self.layers), self.camera_model,
+                            self.use_pred_heatmap_init, self._precision, self._calib)
 
-    def forward(self, frame_feats_init, frame_feats_final, heatmap, coord_trans_mat=None, origin_3d=None, staged=None):
+    def forward(self, frame_feats_init, frame_feats_final, heatmap, coord_trans_mat=None, origin_3d=None, staged=None, lane=0):
         # `heatmap` and `origin_3d` are accepted and unused, as in the reference's shipped configuration (:434-439)
         # `staged` (not in the reference): channels-last copies left by a chained EgoPoseFormerHeatmapMVFEX forward
+        self._check_inference()
         preds = self.engine().forward(frame_feats_init, frame_feats_final, coord_trans_mat, staged=staged,
-                                      use_init=self.use_pred_heatmap_init)
+                                      use_init=self.use_pred_heatmap_init, lane=lane)
         return [preds[i] for i in range(preds.shape[0])]
 
 

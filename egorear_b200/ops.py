@@ -19,8 +19,9 @@ from . import _lib
 from .calib import CAMERA_NAMES, cameras_for
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(t=None):
+    """the current stream of t's device (of the current device without t)"""
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device if t is not None else None).cuda_stream)
 
 
 def _ptr(t):
@@ -30,6 +31,22 @@ def _ptr(t):
 def _need_cuda(t, name):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise RuntimeError("egorear_b200.%s: expected a CUDA tensor (there is no CPU fallback)" % name)
+
+
+def _on(t):
+    """context: make t's device current for the launch (a tensor on cuda:1 while cuda:0 is current must not launch there)"""
+    return torch.cuda.device_of(t)
+
+
+def _aligned16(t):
+    """the 128-bit kernels need 16-byte aligned bases: a contiguous view at an odd storage offset is copied"""
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+def _same_device(name, ref, *others):
+    for o in others:
+        if o is not None and isinstance(o, torch.Tensor) and o.device != ref.device:
+            raise RuntimeError("egorear_b200.%s: tensors live on different devices (%s vs %s)" % (name, ref.device, o.device))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -44,13 +61,15 @@ def get_max_preds(heatmaps, threshold=0.5, normalize=False, return_index=False):
     hm = heatmaps.detach()
     if hm.dtype != torch.float32 or not hm.is_contiguous():
         hm = hm.float().contiguous()
+    hm = _aligned16(hm)
     preds = torch.empty((B, J, 2), dtype=torch.float32, device=hm.device)
     maxvals = torch.empty((B, J, 1), dtype=torch.float32, device=hm.device)
     valid = torch.empty((B, J, 1), dtype=torch.bool, device=hm.device)
     idx = torch.empty((B, J), dtype=torch.int32, device=hm.device) if return_index else None
     lib = _lib.load()
-    _lib.check(lib.egr_decode_argmax(_ptr(hm), B, J, H, W, float(threshold), int(bool(normalize)), _ptr(preds),
-                                     _ptr(maxvals), _ptr(valid), _ptr(idx), _stream()))
+    with _on(hm):
+        _lib.check(lib.egr_decode_argmax(_ptr(hm), B, J, H, W, float(threshold), int(bool(normalize)), _ptr(preds),
+                                         _ptr(maxvals), _ptr(valid), _ptr(idx), _stream(hm)))
     out = (preds, maxvals.squeeze(), valid.squeeze())      # loss.py:142 squeezes size-1 dims
     return out + (idx,) if return_index else out
 
@@ -64,10 +83,12 @@ def get_max_preds_soft_pytorch(batch_heatmaps, normalize=False):
     hm = batch_heatmaps.detach()
     if hm.dtype != torch.float32 or not hm.is_contiguous():
         hm = hm.float().contiguous()
+    hm = _aligned16(hm)
     preds = torch.empty((B, J, 2), dtype=torch.float32, device=hm.device)
     maxvals = torch.empty((B, J, 1), dtype=torch.float32, device=hm.device)
-    _lib.check(_lib.load().egr_decode_soft_argmax(_ptr(hm), B, J, H, W, int(bool(normalize)), _ptr(preds), _ptr(maxvals),
-                                                  _stream()))
+    with _on(hm):
+        _lib.check(_lib.load().egr_decode_soft_argmax(_ptr(hm), B, J, H, W, int(bool(normalize)), _ptr(preds), _ptr(maxvals),
+                                                      _stream(hm)))
     return preds, maxvals
 
 
@@ -79,10 +100,12 @@ def integrate_tensor_2d(heatmaps, softmax=True, multiplier=100.0):
     hm = heatmaps.detach()
     if hm.dtype != torch.float32 or not hm.is_contiguous():
         hm = hm.float().contiguous()
+    hm = _aligned16(hm)
     coords = torch.empty((batch_size, n_heatmaps, 2), dtype=torch.float32, device=hm.device)
     out = torch.empty_like(hm)
-    _lib.check(_lib.load().egr_integrate_tensor_2d(_ptr(hm), batch_size, n_heatmaps, h, w, int(bool(softmax)), float(multiplier),
-                                                   _ptr(coords), _ptr(out), _stream()))
+    with _on(hm):
+        _lib.check(_lib.load().egr_integrate_tensor_2d(_ptr(hm), batch_size, n_heatmaps, h, w, int(bool(softmax)), float(multiplier),
+                                                       _ptr(coords), _ptr(out), _stream(hm)))
     return coords, out
 
 
@@ -115,9 +138,10 @@ def preprocess_images(images, size=(256, 256), mean=IMAGENET_MEAN, std=IMAGENET_
     lib = _lib.load()
     for i in range(0, max(N, 1), 65535):
         n = min(65535, N - i)
-        _lib.check(lib.egr_preprocess_images(_ptr(img[i:]) if n > 0 else None, n, Hin, Win, Hout, Wout, m, s,
-                                             _ptr(out[i:]) if n > 0 else None, _ptr(res[i:]) if res is not None and n > 0 else None,
-                                             _stream()))
+        with _on(img):
+            _lib.check(lib.egr_preprocess_images(_ptr(img[i:]) if n > 0 else None, n, Hin, Win, Hout, Wout, m, s,
+                                                 _ptr(out[i:]) if n > 0 else None, _ptr(res[i:]) if res is not None and n > 0 else None,
+                                                 _stream(img)))
     out = out.view(lead + (3, Hout, Wout))
     return (out, res.view(lead + (Hout, Wout, 3))) if return_resized else out
 
@@ -155,10 +179,12 @@ def generate_target_batch(joints, image_size=872, heatmap_size=64, sigma=1, out=
         out = torch.empty(shape, dtype=torch.float32, device=joints.device)
     else:
         assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == n_maps * J * heatmap_size ** 2
+        _same_device("generate_target_batch", joints, out)
     patch = _numpy_patch(sigma)
     lib = _lib.load()
-    _lib.check(lib.egr_generate_target(_ptr(joints), _ptr(out), n_maps, J, float(image_size), int(heatmap_size),
-                                       float(sigma), ctypes.c_void_p(patch.ctypes.data), _stream()))
+    with _on(joints):
+        _lib.check(lib.egr_generate_target(_ptr(joints), _ptr(out), n_maps, J, float(image_size), int(heatmap_size),
+                                           float(sigma), ctypes.c_void_p(patch.ctypes.data), _stream(joints)))
     return out
 
 
@@ -187,9 +213,11 @@ def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations,
     value = value.float().contiguous()
     loc = sampling_locations.float().contiguous()
     aw = attention_weights.float().contiguous()
+    _same_device("ms_deform_attn", value, loc, aw)
     out = torch.empty((B, Q, nh * hd), dtype=torch.float32, device=value.device)
     lib = _lib.load()
-    _lib.check(lib.egr_msda_forward(_ptr(value), B, H, W, nh, hd, _ptr(loc), _ptr(aw), Q, P, _ptr(out), _stream()))
+    with _on(value):
+        _lib.check(lib.egr_msda_forward(_ptr(value), B, H, W, nh, hd, _ptr(loc), _ptr(aw), Q, P, _ptr(out), _stream(value)))
     return out
 
 
@@ -233,15 +261,22 @@ def reproject_fisheye(pts3d, camera_model, coord_trans_mat=None, calib=None):
         if coord_trans_mat.dtype != torch.float32:
             # utils/camera_models.py:210 matmuls the matrix against fp32 points: a float64 matrix is a dtype error there
             raise RuntimeError("expected m1 and m2 to have the same dtype, but got: double != float")
+        if not coord_trans_mat.is_cuda or coord_trans_mat.device != pts3d.device:
+            raise RuntimeError("egorear_b200.reproject_fisheye: coord_trans_mat must live on pts3d's CUDA device")
+        if tuple(coord_trans_mat.shape) != (B, len(names), 4, 4):
+            # the kernel strides by the model's camera count (the reference indexes [:, v])
+            raise RuntimeError("egorear_b200.reproject_fisheye: coord_trans_mat must be [B=%d, n_cams=%d, 4, 4], got %s"
+                               % (B, len(names), tuple(coord_trans_mat.shape)))
         coord_trans_mat = coord_trans_mat.contiguous()
     a2 = torch.empty((B, len(names), J, 2), dtype=torch.float32, device=pts3d.device)
     av = torch.empty((B, len(names), J), dtype=torch.bool, device=pts3d.device)
     tab = calib_table(calib) if calib is not None else None
     lib = _lib.load()
-    _lib.check(lib.egr_reproject_fisheye(_ptr(pts3d), B, J, ids, len(names), int(is_rw),
-                                         _ptr(coord_trans_mat) if is_rw else None,
-                                         ctypes.c_void_p(tab.ctypes.data) if tab is not None else None,
-                                         _ptr(a2), _ptr(av), _stream()))
+    with _on(pts3d):
+        _lib.check(lib.egr_reproject_fisheye(_ptr(pts3d), B, J, ids, len(names), int(is_rw),
+                                             _ptr(coord_trans_mat) if is_rw else None,
+                                             ctypes.c_void_p(tab.ctypes.data) if tab is not None else None,
+                                             _ptr(a2), _ptr(av), _stream(pts3d)))
     return a2, av
 
 
@@ -250,12 +285,14 @@ def heatmap_head_1x1(feat, weight, bias):
     _need_cuda(feat, "heatmap_head_1x1")
     N, C, H, W = feat.shape
     J = weight.shape[0]
-    feat = feat.float().contiguous()
+    feat = _aligned16(feat.float().contiguous())
     w = weight.detach().reshape(J, C).float().contiguous()
     b = bias.detach().float().contiguous()
+    _same_device("heatmap_head_1x1", feat, w, b)
     out = torch.empty((N, J, H, W), dtype=torch.float32, device=feat.device)
     lib = _lib.load()
-    _lib.check(lib.egr_heatmap_head_1x1(_ptr(feat), _ptr(w), _ptr(b), N, C, H * W, J, _ptr(out), _stream()))
+    with _on(feat):
+        _lib.check(lib.egr_heatmap_head_1x1(_ptr(feat), _ptr(w), _ptr(b), N, C, H * W, J, _ptr(out), _stream(feat)))
     return out
 
 
@@ -264,7 +301,9 @@ def pack_joints(preds2d, pose3d):
     B = preds2d.shape[0]
     p2 = preds2d.reshape(B, -1).float().contiguous()
     p3 = pose3d.reshape(B, -1).float().contiguous()
+    _same_device("pack_joints", p2, p3)
     out = torch.empty((B, p2.shape[1] + p3.shape[1]), dtype=torch.float32, device=p2.device)
     lib = _lib.load()
-    _lib.check(lib.egr_pack_joints(_ptr(p2), _ptr(p3), B, p2.shape[1], p3.shape[1], _ptr(out), _stream()))
+    with _on(p2):
+        _lib.check(lib.egr_pack_joints(_ptr(p2), _ptr(p3), B, p2.shape[1], p3.shape[1], _ptr(out), _stream(p2)))
     return out

@@ -43,15 +43,16 @@ class HotPathPipeline:
         return self
 
     @torch.no_grad()
-    def forward(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None, feat_staged=None):
-        """feat_staged: the features as backbone_staged() leaves them (view-major channels-last bf16); `feat` is then
-        ignored and the hot path starts without its staging pass."""
+    def forward(self, feat, bfb, coord_trans_mat=None, heatmap_for_anchor=None, feat_staged=None, lane=0):
+        """feat_staged: the features as backbone_staged() leaves them (view-major channels-last, 16-bit activation type);
+        `feat` is then ignored and the hot path starts without its staging pass.  lane: which cached workspace pair the
+        engines use (forwards that may be in flight at the same time on different streams need different lanes)."""
         list_hm, list_ff = self.heatmap.forward_from_feats(None if feat_staged is not None else feat, bfb, heatmap_for_anchor,
                                                            want_feat_refined=self.materialize_features,
-                                                           feat_staged=feat_staged)
+                                                           feat_staged=feat_staged, lane=lane)
         B, V, J, H, W = list_hm[-1].shape
         pts2d, maxvals, valid = ops.get_max_preds(list_hm[-1].view(B * V, J, H, W), threshold=0.5, normalize=False)
-        preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, staged=self.heatmap.last_staged)
+        preds3d = self.pose3d(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, staged=self.heatmap.last_staged, lane=lane)
         packed = ops.pack_joints(pts2d.view(B, V * J * 2), preds3d[-1])
         return dict(packed=packed, joints2d=pts2d.view(B, V, J, 2), pose3d=preds3d[-1], list_hm=list_hm, list_ff=list_ff,
                     list_pose3d=preds3d)
@@ -83,19 +84,21 @@ class HotPathPipeline:
         already IS the layout the hot path reads, so it is handed over as such instead of being cast back to NCHW fp32
         and re-staged.  The two stereo backbones run on view-major batches (frames are independent: eval-mode BatchNorm).
         -> (feat_staged bf16 [V,B,64,64,128] view-major channels-last, bfb fp32 [B,V,512,8,8])"""
-        assert self.V == 4 and self.precision == "bf16"
+        from .engine import ACT_DTYPE
+        assert self.V == 4 and self.precision in ACT_DTYPE
+        adt = ACT_DTYPE[self.precision]
         if not getattr(self, "_bb_cl", False):
             for n in ("heatmap_estimator_stereo_front", "heatmap_estimator_stereo_back"):
                 getattr(self.heatmap, n).to(memory_format=torch.channels_last)
             self._bb_cl = True
         B = img.shape[0]
-        xh = torch.empty((self.V, B, 64, 64, 128), dtype=torch.bfloat16, device=img.device)
+        xh = torch.empty((self.V, B, 64, 64, 128), dtype=adt, device=img.device)
         bfb = torch.empty((B, self.V, 512, 8, 8), dtype=torch.float32, device=img.device)
         for p, name in enumerate(("heatmap_estimator_stereo_front", "heatmap_estimator_stereo_back")):
             est = getattr(self.heatmap, name)
             for i in range(0, B, chunk):
                 im = img[i:i + chunk, 2 * p:2 * p + 2].transpose(0, 1)             # [2, b, 3, H, W]: view-major batch
-                with torch.autocast("cuda", dtype=torch.bfloat16):
+                with torch.autocast("cuda", dtype=adt):
                     f, bb = est.forward_backbone(im)                              # f [2, b, 128, 64, 64], NHWC memory
                 xh[2 * p:2 * p + 2, i:i + chunk].copy_(f.permute(0, 1, 3, 4, 2))     # same memory order: a plain copy
                 bfb[i:i + chunk, 2 * p:2 * p + 2].copy_(bb[-1].transpose(0, 1))
@@ -109,7 +112,6 @@ class HotPathPipeline:
         the capture is legal; weights must be frozen.  Use replay(feat, bfb) afterwards."""
         dev = next(self.heatmap.parameters()).device
         self.freeze()
-        eh, ep = self.heatmap.engine(), self.pose3d.engine()
         lane = 1000 + B                                    # private workspaces: replays may interleave with eager calls
         feat = torch.zeros((B, self.V, 128, 64, 64), dtype=torch.float32, device=dev)
         bfb = torch.zeros((B, self.V, 512, 8, 8), dtype=torch.float32, device=dev)
@@ -117,18 +119,14 @@ class HotPathPipeline:
         cur = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(cur)
-        eh.lane = ep.lane = lane
-        try:
-            with torch.cuda.stream(side):                  # warm-up outside the capture: workspaces, lazy inits
-                for _ in range(2):
-                    self.forward(feat, bfb, ctm)
-            cur.wait_stream(side)
-            torch.cuda.synchronize(dev)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self.forward(feat, bfb, ctm)
-        finally:
-            eh.lane = ep.lane = 0
+        with torch.cuda.stream(side):                      # warm-up outside the capture: workspaces, lazy inits
+            for _ in range(2):
+                self.forward(feat, bfb, ctm, lane=lane)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward(feat, bfb, ctm, lane=lane)
         if not hasattr(self, "_graphs"):
             self._graphs = {}
         self._graphs[B] = (graph, feat, bfb, ctm, out)
@@ -160,16 +158,11 @@ class HotPathPipeline:
         self._next_lane = (k + 1) % lanes
         st = self._lanes[k]
         st.wait_stream(cur)                                # inputs were produced on the caller's stream
-        eh, ep = self.heatmap.engine(), self.pose3d.engine()
-        eh.lane = ep.lane = k + 1                          # lane 0 is the synchronous forward()
-        try:
-            with torch.cuda.stream(st):
-                out = self.forward(feat, bfb, coord_trans_mat, heatmap_for_anchor)
-                out["gathered"] = egd.gather_rows(out["packed"], world)
-                ev = torch.cuda.Event()
-                ev.record(st)
-        finally:
-            eh.lane = ep.lane = 0
+        with torch.cuda.stream(st):                        # lane 0 is the synchronous forward()
+            out = self.forward(feat, bfb, coord_trans_mat, heatmap_for_anchor, lane=k + 1)
+            out["gathered"] = egd.gather_rows(out["packed"], world)
+            ev = torch.cuda.Event()
+            ev.record(st)
         out["event"] = ev
         return out
 

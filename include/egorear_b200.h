@@ -40,9 +40,14 @@ extern "C" {
 
 /* precision of the dense conv/GEMM stages (token/attention math is always fp32) */
 #define EGR_PREC_FP32  0   /* fp32 SIMT kernels: reference-grade parity (<=1e-3 rel in fp32) */
-#define EGR_PREC_BF16  1   /* bf16 operands, fp32 accumulate in TMEM (tcgen05): stated looser bound; the stages that
-                            * need more than 8 mantissa bits (pose3d proposal branch, pre-upsample maps, token
-                            * Linears) run on fp16 / TF32 operands */
+#define EGR_PREC_BF16  1   /* bf16 operands, fp32 accumulate in TMEM (tcgen05): stated looser bound 1e-2 (measured 7e-3);
+                            * the stages that need more than 8 mantissa bits (pose3d proposal branch, pre-upsample
+                            * maps, token Linears) run on fp16 / TF32 operands */
+#define EGR_PREC_FP16  3   /* the tensor-core mode inside the fp32 parity bound: every 16-bit stage on fp16 operands
+                            * (10-bit mantissa, same bytes and MMA rate as bf16; conversions saturate at +-65504 - the
+                            * range is the one assumption), 1x1 / Linear weights as an fp16 hi + lo pair (no weight
+                            * rounding error, twice the MMAs on HBM-bound stages), token Linears as "3x TF32"
+                            * (x_hi W_hi + x_lo W_hi + x_hi W_lo: fp32-grade) */
 
 const char* egr_last_error(void);
 /* process-wide switches (read when a handle is created / prepacked):
@@ -51,7 +56,9 @@ const char* egr_last_error(void);
  *   "tok_batched" (1)   batched token path (token GEMMs on tcgen05) instead of the fused per-frame SIMT kernels
  *   "pose_p2_fp16" (1)  pose3d proposal branch on fp16 operands; 0 = fp32 activations multiplied as TF32
  *   "pose_p2_bf16" (0)  debugging: bf16 operands there (costs the whole 0.1 mm MPJPE budget)
- *   "ws" (0)            weight-stationary mode of the tcgen05 GEMM (measured no gain) */
+ *   "ws" (0)            weight-stationary mode of the tcgen05 GEMM (measured no gain)
+ *   "wsplit" (1)        EGR_PREC_FP16: 0 single fp16 weights, 1 hi + lo pairs for 1x1 / Linear weights, 2 also the 3x3 convs
+ *   "tok3x" (1)         EGR_PREC_FP16: mvfex token Linears as "3x TF32" (fp32-grade); 0 = plain TF32 as in EGR_PREC_BF16 */
 int         egr_set_option(const char* key, int value);
 int         egr_version(void);
 /* stage profiler for bench.py: while enabled the engines record CUDA events between their stages on the launch
@@ -159,6 +166,10 @@ typedef struct egr_dense_desc {
     int32_t groups;
     int64_t a_gs, w_gs, b_gs, d_gs, aux_gs;
     int32_t a_is_bf16, d_is_bf16, use_tc;
+    /* split operands (use_tc only; 0 = plain): A has `ka` columns and the k loop re-reads it from column 0 for k >= ka
+     * (ka < K <= 2*ka).  K = 2*ka with W = [W_hi | W_lo] multiplies A by the weight AND its rounding residual (no weight
+     * rounding error); K = 3*k0, ka = 2*k0, A = [x | x_lo], W = [W_hi | W_hi | W_lo] is the fp32-grade "3x TF32" product */
+    int32_t ka;
 } egr_dense_desc;
 int egr_dense_stage(const egr_dense_desc* desc, void* stream);
 
@@ -209,13 +220,16 @@ int egr_mvfex_refiner_forward(egr_mvfex* h, int r, int B, const float* heatmap, 
 /* mode 4: like 3, but the fp16 copy is the ONLY channels-last copy of the refined features (the refined heatmap head
  * reads it too; egr_mvfex_staged returns refined_nhwc = NULL) - for a pose3d that samples the init features. */
 int egr_mvfex_export_staged(egr_mvfex* h, int mode);   /* 0 off, 1 + TF32 copy, 2 activation-dtype copies only, 3 + fp16 copy, 4 */
+/* *act_is_bf16 receives the element type of init_nhwc / refined_nhwc: 0 fp32, 1 bf16, 2 fp16 (EGR_PREC_FP16, where the
+ * activation copy of the refined features already is the fp16 copy: refined_nhwc_hp == refined_nhwc in every mode) */
 int egr_mvfex_staged(egr_mvfex* h, const void** init_nhwc, const void** refined_nhwc, const void** refined_nhwc_hp,
                      int* act_is_bf16);
 /* Input hint for a producer that already emits the layout the kernels read (a channels-last bf16 backbone):
  * feat_vmajor_nhwc_bf16 = [V][B][64*64][128] bf16, view-major.  One-shot: the next egr_mvfex_forward skips its
  * NCHW fp32 -> channels-last staging pass, reads this buffer instead (it must stay valid until that forward and any
- * chained pose3d forward have completed) and accepts feat == NULL.  bf16 precision only; results are bit-identical to
- * passing the fp32 NCHW tensor whose bf16 rounding this buffer holds. */
+ * chained pose3d forward have completed) and accepts feat == NULL.  16-bit precisions only (bf16 values under
+ * EGR_PREC_BF16, fp16 values under EGR_PREC_FP16); results are bit-identical to passing the fp32 NCHW tensor whose
+ * rounding this buffer holds. */
 int egr_mvfex_use_staged_input(egr_mvfex* h, const void* feat_vmajor_nhwc_bf16);
 /* test/debug: pointer + byte size of a named intermediate inside the workspace of the last forward
  * ("q1", "xT", "t1", "ff", ...); EGR_ERR_INVALID for unknown names */
@@ -241,7 +255,7 @@ int egr_pose3d_forward(egr_pose3d* h, int B, const float* feats_init, const floa
                        const float* coord_trans_mat, float* preds, void* workspace, int64_t workspace_bytes,
                        void* stream);
 /* sampled_nhwc: channels-last copy of the map the transformer samples (feats_init when use_pred_heatmap_init, else
- * feats_final), bf16 or fp32 as flagged; final_nhwc_tf32: channels-last fp32 copy of feats_final rounded to TF32.
+ * feats_final), element type as flagged (sampled_is_bf16: 0 fp32, 1 bf16, 2 fp16); final_nhwc_tf32: channels-last fp32 copy of feats_final rounded to TF32.
  * Either may be NULL.  One-shot: consumed by the next egr_pose3d_forward. */
 int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_is_bf16, const float* final_nhwc_tf32);
 /* Hint for feats_final when the proposal branch runs in fp16 (egr_pose3d_proposal_dtype == 3): its channels-last fp16

@@ -1,6 +1,7 @@
 """ORACLE helper (test infrastructure): import the LIVE reference from /root/reference on a CUDA-less host.
 
-Only usable in the build container (the GPU box has no /root/reference).  Used by
+In the build container this is the checkout; the GPU box has no /root/reference, but it receives the git-ignored file
+copy oracle/_ref/ (oracle/make_ref.py), which bench.py's CPU arm times there (`kind: "reference"`).  Used by
 tests/golden/make_golden.py to generate the committed fixtures and by tests/test_oracle_*.py (skipped
 when the checkout is absent) to pin oracle/model_ref.py and oracle/gt_decode.c against the reference.
 
@@ -17,11 +18,21 @@ import types
 import torch
 import torch.nn.functional as F
 
-REF = os.environ.get("EGOREAR_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the checkout itself in the build container; on the GPU box the git-ignored file copy oracle/_ref/ that
+# oracle/make_ref.py (run by __graft_entry__.build()) leaves behind and gpurun ships with the snapshot
+_CANDIDATES = [os.environ.get("EGOREAR_REFERENCE"), "/root/reference", os.path.join(_HERE, "_ref")]
+REF = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "pose_estimation"))), "/root/reference")
+FORCE_CPU = False      # bench.py's CPU arm on the GPU box: keep the camera model's tensors on the host
 
 
 def available():
     return os.path.isdir(os.path.join(REF, "pose_estimation"))
+
+
+def is_copy():
+    """True when the reference in use is the shipped file copy (oracle/_ref) rather than the checkout"""
+    return os.path.abspath(REF) == os.path.abspath(os.path.join(_HERE, "_ref"))
 
 
 def _stub(name, **attrs):
@@ -74,7 +85,7 @@ def import_estimators():
     from pose_estimation.models.estimator import EgoPoseFormerHeatmap, EgoPoseFormerHeatmapMVFEX, EgoPoseFormerMVFEX
     from pose_estimation.models.estimator.egoposeformer_mvf_ex import EgoPoseFormerPose3D
     from pose_estimation.models.estimator.egoposeformer_heatmap_mvf_ex import HeatmapMVF
-    if not torch.cuda.is_available():
+    if FORCE_CPU or not torch.cuda.is_available():
         import pose_estimation.utils.camera_models as cm
         if not getattr(cm, "_egr_cpu_shim", False):
             real = torch.tensor

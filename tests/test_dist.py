@@ -89,4 +89,4 @@ def test_patch_rebinds_reference_names():
             else:
                 sys.modules[k] = v
     with pytest.raises(ValueError):
-        egorear_b200.patch(precision="fp16")
+        egorear_b200.patch(precision="fp8")
