@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "4-view frames/sec (heatmap+pose3d fwd)"
+# the tensor-core precision that is INSIDE the fp32 parity bound (<= 1e-3 relative): fp16 operands, split 1x1 weights,
+# 3x-TF32 token Linears (include/egorear_b200.h EGR_PREC_FP16); "bf16" is the looser-bound mode of round 1
+DEFAULT_PRECISION = "fp16"
 UNIT = "frames/s"
 
 # algorithmic FLOPs per 4-view frame of every dense stage (2*M*N*K, with the 1x1 convs that follow a bilinear x2
@@ -84,7 +87,9 @@ def stage_roofline(name, ms, B, act, exp, peaks):
     by = STAGE_BYTES[name](act, exp, B) * B if name in STAGE_BYTES else 0
     if not fl and not by:
         return None
-    tf_peak = peaks["tf_sust"] * (0.5 if (name in TF32_STAGES and P2ACT[0] == 4) else 1.0)
+    # stage times are CUDA-event intervals of a few-step pass, i.e. kernels timed (almost) alone: the tensor denominator is the
+    # BURST cuBLAS figure; the seconds-long `sustained` block of the line is judged against the sustained one
+    tf_peak = peaks["tf_burst"] * (0.5 if (name in TF32_STAGES and P2ACT[0] == 4) else 1.0)
     t_tensor = fl / (tf_peak * 1e12) if fl else 0.0
     t_hbm = by / (peaks["hbm"] * 1e9) if by else 0.0
     t_s = ms / 1e3
@@ -95,9 +100,15 @@ def stage_roofline(name, ms, B, act, exp, peaks):
     return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"]}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/)
-NCU_TRAFFIC = {"F1b": 546443776 + 246109184, "R1tail": 67132160 + 209667072, "P2a": 268514560 + 102758912,
-               "P2b": 134458112 + 41757440}      # profiles/r01g_ncu_summary.md
+def load_ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage kernels, from the committed `ncu --set full`
+    capture of this workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py --traffic from the .ncu-rep)"""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return {k: int(v["dram_read_bytes"]) + int(v["dram_write_bytes"]) for k, v in d.get("stages", {}).items()}, d.get("source")
+    except Exception:
+        return {}, None
 
 
 def load_peaks():
@@ -147,9 +158,10 @@ class ClockSampler(threading.Thread):
 # CPU implementation of the path (cpu_baseline leg and --impl reference arm)
 # --------------------------------------------------------------------------------------------------------
 class CpuPath:
-    """the reference's own modules when /root/reference exists (kind 'reference'), else the oracle port (kind 'port')"""
+    """the reference's own modules when a checkout (build container) or its file copy oracle/_ref (GPU box) is present
+    (kind 'reference'), else the oracle port (kind 'port')"""
 
-    def __init__(self, workload="mvfex_pose3d"):
+    def __init__(self, camera_model="ego4view_syn"):
         import torch
         from egorear_b200 import calib, synth
         from egorear_b200.configs import heatmap_mvfex_cfg, pose3d_cfg
@@ -159,29 +171,36 @@ class CpuPath:
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
         self.calib = calib.load_calibration(None)
+        self.cam = camera_model
         self.kind = "port"
-        hm = synth.fill_state_dict(EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(), precision="fp32", build_backbone=False))
-        p3 = synth.fill_state_dict(EgoPoseFormerPose3D(**pose3d_cfg(), precision="fp32"))
+        self.how = "oracle/model_ref.py (torch fp32 restatement)"
+        hm = synth.fill_state_dict(EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(4, camera_model), precision="fp32", build_backbone=False))
+        p3 = synth.fill_state_dict(EgoPoseFormerPose3D(**pose3d_cfg(4, camera_model), precision="fp32"))
         self.sd_h, self.sd_p = hm.state_dict(), p3.state_dict()
         self.ref_h = self.ref_p = None
         if ref_import.available():
             try:
                 import copy
+                ref_import.FORCE_CPU = True          # the GPU box has CUDA: keep the camera model's tensors on the host
                 cls = ref_import.import_estimators()
-                cfg = ref_import.load_model_cfg("ego4view_syn_heatmap_mvfex-n1_jqa.yaml")
+                rw = camera_model.startswith("ego4view_rw")
+                cfg = ref_import.load_model_cfg("ego4view_%s_heatmap_mvfex-n1_jqa.yaml" % ("rw" if rw else "syn"))
                 self.ref_h = cls["EgoPoseFormerHeatmapMVFEX"](**copy.deepcopy(cfg)).eval()
                 self.ref_h.load_state_dict({**self.ref_h.state_dict(), **self.sd_h}, strict=True)
-                c3 = ref_import.load_model_cfg("ego4view_syn_pose3d.yaml")["pose3d_cfg"]
-                c3.update(dict(num_views=4, image_size=[256, 256], use_pred_heatmap_init=True, camera_model="ego4view_syn"))
+                c3 = ref_import.load_model_cfg("ego4view_%s_pose3d.yaml" % ("rw" if rw else "syn"))["pose3d_cfg"]
+                c3.update(dict(num_views=4, image_size=[256, 256], use_pred_heatmap_init=True, camera_model=camera_model))
                 self.ref_p = cls["EgoPoseFormerPose3D"](**c3).eval()
                 self.ref_p.load_state_dict(self.sd_p, strict=True)
-                self.get_max_preds = ref_import.import_functions()["get_max_preds"]
+                fns = ref_import.import_functions()
+                self.get_max_preds = fns["get_max_preds"]
                 self.kind = "reference"
+                self.how = "the reference's own modules (%s; mmcv op -> grid_sample shim)" % (
+                    "file copy oracle/_ref" if ref_import.is_copy() else "checkout")
             except Exception as e:      # fall back to the port, say why
                 sys.stderr.write("bench: live reference unusable (%s); timing the oracle port\n" % e)
                 self.ref_h = self.ref_p = None
 
-    def step(self, feat, bfb):
+    def mvfex(self, feat, bfb):
         torch = self.torch
         with torch.no_grad():
             if self.ref_h is not None:
@@ -189,27 +208,116 @@ class CpuPath:
                 lh, lf = self.ref_h(torch.zeros(feat.shape[0], 4, 3, 1, 1))
                 B, V, J, H, W = lh[-1].shape
                 self.get_max_preds(lh[-1].view(B * V, J, H, W), 0.5, False)
-                return self.ref_p(lf[0], lf[-1], lh[-1])[-1]
+                return lh, lf
             lh, lf, _, _ = self.model_ref.mvfex_hot_path(self.sd_h, feat, bfb)
             B, V, J, H, W = lh[-1].shape
             self.model_ref.get_max_preds(lh[-1].view(B * V, J, H, W), 0.5, False)
-            return self.model_ref.pose3d_forward(self.sd_p, lf[0], lf[-1], self.calib, "ego4view_syn")[-1]
+            return lh, lf
+
+    def pose3d(self, fi, ff, ctm=None):
+        with self.torch.no_grad():
+            if self.ref_p is not None:
+                return self.ref_p(fi, ff, None, ctm)[-1]
+            return self.model_ref.pose3d_forward(self.sd_p, fi, ff, self.calib, self.cam, ctm)[-1]
+
+    def step(self, feat, bfb, ctm=None):
+        lh, lf = self.mvfex(feat, bfb)
+        return self.pose3d(lf[0], lf[-1], ctm)
 
 
-def cpu_baseline(budget_s=12.0, frames_per_step=2):
-    from egorear_b200 import synth
-    cp = CpuPath()
-    feat, bfb = synth.synth_features(frames_per_step, 4, seed=0)
-    cp.step(feat, bfb)                           # warm-up
+def _timed(fn, unit_per_call, budget_s, max_units):
+    fn()                                         # warm-up
     n, t0 = 0, time.time()
     while True:
-        cp.step(feat, bfb)
-        n += frames_per_step
-        if time.time() - t0 > budget_s or n >= 256:
+        fn()
+        n += unit_per_call
+        if time.time() - t0 > budget_s or n >= max_units:
             break
-    dt = time.time() - t0
+    return n, time.time() - t0
+
+
+def cpu_baseline(workload="mvfex_pose3d", budget_s=12.0):
+    """the CPU implementation of the workload on the host cores, bounded sample; batch sizes per BASELINE.md section 4
+    (mvfex B=4, pose3d B=32): the reference's modules when a checkout or its file copy oracle/_ref is present, else the port"""
+    import torch
+    from egorear_b200 import synth
+    if workload in ("generate_target", "decode"):
+        return cpu_baseline_gt_decode(workload, min(budget_s, 8.0))
+    cam = "ego4view_rw" if workload == "rw_e2e" else "ego4view_syn"
+    cp = CpuPath(cam)
+    if workload == "pose3d":
+        fps = 32
+        g = torch.Generator().manual_seed(0)
+        fi = torch.relu(torch.randn((fps, 4, 128, 64, 64), generator=g))
+        ff = torch.relu(torch.randn((fps, 4, 128, 64, 64), generator=g))
+        fn = lambda: cp.pose3d(fi, ff)
+        what = "pose3d lifting"
+    else:
+        fps = 4
+        feat, bfb = synth.synth_features(fps, 4, seed=0)
+        ctm = synth.synth_coord_trans_mat(fps, seed=0) if cam == "ego4view_rw" else None
+        if workload == "mvfex":
+            fn = lambda: cp.mvfex(feat, bfb)
+            what = "mvfex hot path + decode"
+        else:
+            fn = lambda: cp.step(feat, bfb, ctm)
+            what = "mvfex hot path + decode + pose3d lifting" + (" (backbone excluded)" if workload == "rw_e2e" else "")
+    n, dt = _timed(fn, fps, budget_s, 512)
     return {"value": n / dt, "unit": UNIT, "cores": cp.cores, "kind": cp.kind,
-            "sample": "%d frames (steps of %d) of the same workload, %.1f s, torch fp32 on %d host threads" % (n, frames_per_step, dt, cp.cores)}
+            "sample": "%d frames (steps of %d): %s, %s, torch fp32 on %d host threads, %.1f s" % (n, fps, what, cp.how, cp.cores, dt)}
+
+
+def cpu_baseline_gt_decode(workload, budget_s=8.0):
+    """generate_target as shipped (numpy, one call per camera as in the main loop of generate_heatmap.py:58-68) on one
+    core when the reference is present, else the C oracle; get_max_preds through torch on all cores"""
+    import numpy as np
+    import torch
+    from egorear_b200 import synth
+    from oracle import model_ref, ref_import
+    if workload == "decode":
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        n = 64
+        hm = torch.randn((n * 4, 15, 64, 64), generator=torch.Generator().manual_seed(0))
+        kind, fn = "port", (lambda: model_ref.get_max_preds(hm, 0.5, True))
+        how = "oracle/model_ref.get_max_preds (the reference's torch lines restated)"
+        if ref_import.available():
+            try:
+                ref_fn = ref_import.import_functions()["get_max_preds"]
+                kind, fn, how = "reference", (lambda: ref_fn(hm, 0.5, True)), "utils/loss.py:get_max_preds"
+            except Exception:
+                pass
+        done, dt = _timed(fn, n, budget_s, 1 << 16)
+        return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": "%d frames (steps of %d) x 4 views x 15 joints, %s, torch on %d threads, %.1f s" % (done, n, how, cores, dt)}
+    n = 64
+    kp = synth.synth_keypoints(n, 4, 16, seed=0)
+    kind, how, fn = "port", "oracle/gt_decode.c (C restatement)", None
+    if ref_import.available():
+        try:
+            gen = ref_import.import_functions()["generate_target"]
+            fn = lambda: [gen(kp[f, v], 872, 64, 16, 1.0) for f in range(n) for v in range(4)]
+            kind, how = "reference", "generate_heatmap.generate_target (numpy, one call per camera as in its main loop)"
+        except Exception:
+            fn = None
+    if fn is None:
+        import ctypes
+        import subprocess
+        so = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        if not os.path.exists(so):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+        orc = ctypes.CDLL(so)
+        orc.orc_gaussian_patch.argtypes = [ctypes.c_double, ctypes.c_int, ctypes.c_void_p]
+        orc.orc_generate_target.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_double,
+                                            ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+        patch = np.zeros((7, 7), np.float32)
+        orc.orc_gaussian_patch(1.0, 7, patch.ctypes.data)
+        out = np.empty((n, 4, 16, 64, 64), np.float32)
+        kpc = np.ascontiguousarray(kp)
+        fn = lambda: orc.orc_generate_target(kpc.ctypes.data, out.ctypes.data, n * 4, 16, 872.0, 64, 1.0, patch.ctypes.data)
+    done, dt = _timed(fn, n, budget_s, 1 << 16)
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "%d frames (steps of %d) x 4 views x 16 joints, %s, one core, %.1f s" % (done, n, how, dt)}
 
 
 def cpu_baseline_eval(workload, budget_s=8.0):
@@ -267,11 +375,11 @@ def run_reference_arm(args):
         return 0
     from egorear_b200 import synth
     cp = CpuPath()
-    fps = 2
+    fps = 4                                      # the CPU arm runs the mvfex path at batch 4
     feat, bfb = synth.synth_features(fps, 4, seed=0)
     for _ in range(max(1, min(args.warmup, 2))):
         cp.step(feat, bfb)
-    steps = max(1, min(args.steps, 8))           # bounded: each step is a 2-frame sample of the workload
+    steps = max(1, min(args.steps, 8))           # bounded: each step is a 4-frame sample of the workload
     t0 = time.time()
     for _ in range(steps):
         cp.step(feat, bfb)
@@ -282,7 +390,7 @@ def run_reference_arm(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "sample_frames_per_step": fps, "note": "CPU implementation on host cores"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cp.cores, "kind": cp.kind,
-                             "sample": "%d steps x %d frames, torch fp32, %d host threads" % (steps, fps, cp.cores)},
+                             "sample": "%d steps x %d frames, %s, torch fp32, %d host threads" % (steps, fps, cp.how, cp.cores)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
     return 0
@@ -332,7 +440,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="mvfex_pose3d", choices=["mvfex_pose3d", "mvfex", "pose3d", "generate_target", "decode", "rw_e2e", "eval_heatmap", "eval_pose", "preprocess"])
     ap.add_argument("--batch", type=int, default=None, help="frames per GPU per step")
-    ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("EGR_PRECISION", DEFAULT_PRECISION), choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--sustain-s", type=float, default=3.0, help="seconds of the extra back-to-back loop behind the `sustained` block (0 = off)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed parity block (oracle on a sample of the batch)")
     ap.add_argument("--lanes", type=int, default=3, help="streams alternated by the throughput loop (1 = one stream)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option key=int (egr_set_option), e.g. pdl=0")
@@ -357,7 +467,9 @@ def main():
         _lib.check(lib.egr_set_option(k.encode(), int(v)))
     peaks = load_peaks()
     B = args.batch
-    act = 2 if args.precision == "bf16" else 4
+    act = 2 if args.precision in ("bf16", "fp16") else 4
+    ncu_traffic, ncu_source = load_ncu_traffic()
+    parity_fn = None
     e2e_fn = None
 
     if args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
@@ -393,7 +505,40 @@ def main():
         in_bytes = feat_h.numel() * 4 + bfb_h.numel() * 4
         l2_note = "inputs %.0f MB + activations >> 126 MB L2 (no flush needed)" % (in_bytes / 1e6)
 
-        if args.workload == "mvfex_pose3d":
+        if args.workload != "pose3d" and not args.no_parity:
+            def parity_fn():
+                # untimed: the step that is timed, checked against the oracle on a seeded sample of its frames
+                from egorear_b200 import calib
+                from oracle import parity
+                pm = pipe
+                out = pm(feat, bfb)
+                idx = parity.sample_indices(B, 8, seed=7)
+                sd_h = {k: v.cpu() for k, v in pm.heatmap.state_dict().items()}
+                sd_p = {k: v.cpu() for k, v in pm.pose3d.state_dict().items()}
+                return parity.hot_path_parity(out, pm.heatmap.last_anchors[0], idx, feat_h[idx], bfb_h[idx], sd_h, sd_p,
+                                              calib.load_calibration(None), "ego4view_syn")
+        elif not args.no_parity:
+            def parity_fn():
+                from egorear_b200 import calib
+                from oracle import parity
+                idx = parity.sample_indices(B, 8, seed=7)
+                preds = pipe.pose3d(feat, ff, None)
+                ii = torch.as_tensor(idx, device=dev)
+                return parity.pose3d_parity(preds[-1], idx, feat[ii].cpu(), ff[ii].cpu(),
+                                            {k: v.cpu() for k, v in pipe.pose3d.state_dict().items()},
+                                            calib.load_calibration(None), "ego4view_syn")
+
+        if args.workload == "mvfex_pose3d" and args.precision in ("bf16", "fp16"):
+            # e2e input = what a channels-last half-precision backbone leaves on the host side of the boundary: the
+            # view-major channels-last 16-bit feature maps (4.2 MB/frame instead of 8.4 MB of NCHW fp32) + the fp32 bottom map
+            feat_st_h = pipe.stage_host_features(feat_h).pin_memory()
+            in_bytes = feat_st_h.numel() * 2 + bfb_h.numel() * 4
+            e2e_api = ("HotPathPipeline.infer_host_batches on pinned view-major channels-last %s features (H2D of batch i+1 "
+                       "overlaps the forward of batch i)" % args.precision)
+
+            def e2e_fn(n):
+                return pipe.infer_host_batches(((feat_st_h, bfb_h) for _ in range(n)), world)
+        elif args.workload == "mvfex_pose3d":
             e2e_api = "HotPathPipeline.infer_host_batches (H2D of batch i+1 overlaps the forward of batch i)"
 
             def e2e_fn(n):
@@ -427,6 +572,20 @@ def main():
         pipe.freeze()
         in_bytes = img_h.numel() * 4 + ctm_h.numel() * 4
         l2_note = "images %.0f MB + activations >> 126 MB L2" % (in_bytes / 1e6)
+        if not args.no_parity:
+            def parity_fn():
+                # hot path only (the backbone is PyTorch on both sides): the staged features the backbone left, as fp32 NCHW
+                from egorear_b200 import calib
+                from oracle import parity
+                xh, b = pipe.backbone_staged(img)
+                out = pipe.forward(None, b, ctm, feat_staged=xh)
+                idx = parity.sample_indices(B, 8, seed=7)
+                ii = torch.as_tensor(idx, device=dev)
+                feat_s = xh[:, ii].permute(1, 0, 4, 2, 3).float().cpu().contiguous()
+                sd_h = {k: v.cpu() for k, v in pipe.heatmap.state_dict().items() if "heatmap_estimator_" not in k}
+                sd_p = {k: v.cpu() for k, v in pipe.pose3d.state_dict().items()}
+                return parity.hot_path_parity(out, pipe.heatmap.last_anchors[0], idx, feat_s, b[ii].cpu(), sd_h, sd_p,
+                                              calib.load_calibration(None), "ego4view_rw", ctm_h[idx])
         e2e_api = "backbone + HotPathPipeline.forward on freshly uploaded images"
 
         def e2e_fn(n):
@@ -558,6 +717,35 @@ def main():
         extra = {"backbone_ms": e[0].elapsed_time(e[1]), "hot_path_ms": e[1].elapsed_time(e[2]),
                  "hot_path_frames_per_s": world * B / (e[1].elapsed_time(e[2]) / 1e3)}
 
+    # ---- sustained: the same step back to back for >= sustain_s seconds (clocks settle under the ~1 kW power cap) ----
+    sustained = None
+    if args.sustain_s > 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e"):
+        n_s = max(args.steps, int(args.sustain_s / max(ms / 1e3 / args.steps, 1e-6)) + 1)
+        samp2 = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+        torch.cuda.synchronize(dev)
+        egd.barrier()
+        samp2.start()
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        for _ in range(n_s):
+            step()
+        if join is not None:
+            join()
+        u1.record()
+        torch.cuda.synchronize(dev)
+        samp2.stop_flag = True
+        samp2.join(timeout=2)
+        egd.barrier()
+        ms_s = egd.max_over_ranks(u0.elapsed_time(u1), dev)
+        sustained = {"value": world * B * n_s / (ms_s / 1e3), "ms_per_step": ms_s / n_s, "steps": n_s, "seconds": ms_s / 1e3,
+                     "clocks": samp2.result()}
+        if args.workload in ("mvfex_pose3d", "mvfex"):
+            # whole-step tensor-pipe fraction: SURVEY 8d algorithmic FLOPs (21.02 G mvfex + 1.106 G lifting per frame)
+            gf = 21.02 + (1.106 if args.workload == "mvfex_pose3d" else 0.0)
+            tfs = gf * 1e9 * B * n_s / (ms_s / 1e3) / 1e12
+            sustained["algorithmic_tflops"] = tfs
+            sustained["frac_of_sustained_tensor_peak"] = tfs / peaks["tf_sust"]
+
     # ---- e2e: pinned host inputs -> H2D -> hot path -> D2H of the step's result, every step (device-timed) ----
     e2e = None
     if e2e_fn is not None:
@@ -608,8 +796,9 @@ def main():
         dense = [k for k in stages if per_stage[k] is not None]
         top = max(dense, key=stages.get)
         roofline = dict(per_stage[top])
-        roofline.update({"kernel": top, "traffic": NCU_TRAFFIC.get(top),
-                         "peak_source": peaks["src"] + (" (sustained bf16 GEMM)" if roofline["bound"] == "tensor" else " (copy)"),
+        roofline.update({"kernel": top, "traffic": ncu_traffic.get(top), "traffic_source": ncu_source,
+                         "peak_source": peaks["src"] + (" (burst bf16 GEMM: the stage is event-timed inside a %d-step pass)" % n_prof
+                                                        if roofline["bound"] == "tensor" else " (copy)"),
                          "share_of_step": stages[top] / total, "ms_per_launch": stages[top]})
         stage_fracs = {k: {"bound": r["bound"], "frac": round(r["frac"], 3)} for k, r in per_stage.items() if r}
     elif rank == 0 and args.workload in ("generate_target", "decode"):
@@ -639,16 +828,23 @@ def main():
     if rank != 0:
         egd.shutdown()
         return 0
+    par = None
+    if parity_fn is not None and world == 1:
+        try:
+            par = parity_fn()
+        except Exception as e:      # the parity block must never take the measurement down with it
+            par = {"error": "%s: %s" % (type(e).__name__, e)}
     cpu = None
     if world == 1 and not args.no_cpu_baseline and args.workload in ("eval_heatmap", "eval_pose"):
         cpu = cpu_baseline_eval(args.workload)
-    if world == 1 and not args.no_cpu_baseline and args.workload == "preprocess":
+    elif world == 1 and not args.no_cpu_baseline and args.workload == "preprocess":
         cpu = cpu_baseline_preprocess()
-    if world == 1 and not args.no_cpu_baseline and args.workload == "mvfex_pose3d":
-        cpu = cpu_baseline()
+    elif world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.workload)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": args.precision if args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e") else "f32", "data": "synthetic",
+            "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.precision] if args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e") else "f32",
+            "data": "synthetic",
             "config": {"workload": workload_name(args), "frames_per_gpu_per_step": B, "precision": args.precision + ("" if args.workload not in ("mvfex_pose3d", "pose3d") else
                                                        " (pose3d proposal branch: %s)" % pipe.pose3d.engine().proposal_dtype()),
                        "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
@@ -656,7 +852,8 @@ def main():
                        if join is not None else "1",
                        "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "stages_ms": stages, "stage_roofline": stage_fracs, "single_stream": single}
+            "cpu_baseline": cpu, "parity": par, "sustained": sustained, "stages_ms": stages, "stage_roofline": stage_fracs,
+            "single_stream": single}
     line.update(extra)
     emit(line)
     egd.shutdown()

@@ -253,7 +253,12 @@ class Pose3DEngine(_EngineBase):
             ctm = coord_trans_mat.contiguous()
         preds = torch.empty((self.L + 1, B, self.J, 3), dtype=torch.float32, device=dev)
         ws = self._workspace(B, dev, lane)
-        if staged is not None and staged["feat_refined"] is feats_final and (staged["feat"] is feats_init or not use_init):
+        def same(a, b):      # the tensors cross an operator boundary: compare storage, not Python identity
+            if a is None or b is None:
+                return a is None and b is None
+            return a.data_ptr() == b.data_ptr() and a.shape == b.shape
+        if staged is not None and staged["B"] == B and same(staged["feat_refined"], feats_final) and \
+                (same(staged["feat"], feats_init) or not use_init):
             sampled = staged["init"] if use_init else staged["refined"]
             _lib.check(self._lib.egr_pose3d_use_staged(self._h, ctypes.c_void_p(sampled), int(staged["bf16"]),
                                                        ctypes.c_void_p(staged["refined_tf32"]) if staged["refined_tf32"] else None))

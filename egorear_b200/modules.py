@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import ops, torch_ops
 from .calib import load_calibration
 from .engine import MvfexEngine, Pose3DEngine
 
@@ -37,6 +37,23 @@ class _EngineOwner:
     forward under training mode with grad enabled raises instead of failing later with an opaque autograd error
     (the engines are inference-only: they detach everything)."""
     _engine = None
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        # key under which the egr::* operators find this module (weak registry): a plain int, so that a traced forward
+        # (torch.compile) reads it as a constant
+        self._egr_key = torch_ops.register_module(self)
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None               # a C handle: rebuilt lazily by the copy
+        return st
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._engine = None
+        self._egr_hooked = False
+        self._egr_key = torch_ops.register_module(self)      # copy.deepcopy / pickle: the copy gets its own key and engine
 
     def _engine_params(self):
         raise NotImplementedError
@@ -432,8 +449,8 @@ class HeatmapMVF(_EngineOwner, nn.Module):
     def forward(self, heatmap, frame_feat, frame_feat_multi_view, anchors_2d, anchors_valid, backbone_feat_bottom,
                 backbone_feat_bottom_multi_view):
         self._check_inference()
-        hm, ft = self.engine().refiner_forward(0, heatmap, frame_feat, frame_feat_multi_view, anchors_2d, anchors_valid,
-                                               backbone_feat_bottom)
+        hm, ft = torch.ops.egr.mvfex_refiner_forward(self._egr_key, heatmap, frame_feat, frame_feat_multi_view, anchors_2d,
+                                                     anchors_valid, backbone_feat_bottom)
         return [hm], [ft]
 
 
@@ -507,11 +524,13 @@ class EgoPoseFormerHeatmapMVFEX(_EngineOwner, nn.Module):
         (frame_feat_multi_view may then be None; see MvfexEngine.forward)."""
         self._check_inference()
         hfa = heatmap_for_anchor if isinstance(heatmap_for_anchor, torch.Tensor) else None
-        out = self.engine().forward(frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa,
-                                    want_feat_refined=want_feat_refined, feat_staged=feat_staged, lane=lane)
-        self.last_anchors = (out["anchors_2d"], out["anchors_valid"])
-        self.last_staged = out.get("staged")
-        return [out["hm_init"], out["hm_refined"]], [None if feat_staged is not None else frame_feat_multi_view, out["feat_refined"]]
+        hm_init, hm_refined, feat_refined, a2, av = torch.ops.egr.mvfex_forward(
+            self._egr_key, None if feat_staged is not None else frame_feat_multi_view, backbone_feat_bottom_multi_view, hfa,
+            feat_staged, bool(want_feat_refined), int(lane))
+        if not torch.compiler.is_compiling():          # debugging / test conveniences, not part of the traced graph
+            self.last_anchors = (a2, av)
+        return [hm_init, hm_refined], [None if feat_staged is not None else frame_feat_multi_view,
+                                       feat_refined if want_feat_refined else None]
 
     def forward(self, img, heatmap_for_anchor=None):
         if not self._has_backbone:
@@ -585,10 +604,12 @@ class EgoPoseFormerPose3D(_EngineOwner, nn.Module):
 
     def forward(self, frame_feats_init, frame_feats_final, heatmap, coord_trans_mat=None, origin_3d=None, staged=None, lane=0):
         # `heatmap` and `origin_3d` are accepted and unused, as in the reference's shipped configuration (:434-439)
-        # `staged` (not in the reference): channels-last copies left by a chained EgoPoseFormerHeatmapMVFEX forward
+        # `staged` (not in the reference): the EgoPoseFormerHeatmapMVFEX whose forward produced the inputs - its
+        # channels-last copies are then lifted directly (they are matched against the tensors passed here by address)
         self._check_inference()
-        preds = self.engine().forward(frame_feats_init, frame_feats_final, coord_trans_mat, staged=staged,
-                                      use_init=self.use_pred_heatmap_init, lane=lane)
+        chain = staged._egr_key if staged is not None else 0
+        preds = torch.ops.egr.pose3d_forward(self._egr_key, chain, frame_feats_init, frame_feats_final, heatmap,
+                                             coord_trans_mat, int(lane))
         return [preds[i] for i in range(preds.shape[0])]
 
 
@@ -613,7 +634,7 @@ class EgoPoseFormerMVFEX(nn.Module):
         # the chained model returns (poses, heatmaps) only (:50-58): the refined features stay channels-last, internal
         list_hm, list_ff = self.heatmap_estimator.forward_from_feats(feat, bfb, want_feat_refined=not self._chain)
         return self.pose3d_estimator(list_ff[0], list_ff[-1], list_hm[-1], coord_trans_mat, origin_3d,
-                                     staged=self.heatmap_estimator.last_staged), list_hm
+                                     staged=self.heatmap_estimator), list_hm
 
     def forward(self, img, coord_trans_mat=None, origin_3d=None):
         list_hm, list_ff = self.heatmap_estimator(img)

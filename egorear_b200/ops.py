@@ -8,7 +8,9 @@ Same names, argument meaning and error behaviour as the reference functions:
   ms_deform_attn    <- mmcv MultiScaleDeformableAttnFunction (models/utils/deform_attn.py:155-162)
   reproject_fisheye <- EgoPoseFormerPose3D._reproject_3d_to_2d (estimator/egoposeformer_mvf_ex.py:340-382)
 
-Everything runs on the current CUDA device through libegorear_b200.so; there is no CPU path.
+Everything runs on the tensors' CUDA device through libegorear_b200.so; there is no CPU path.  The public functions go
+through the `egr::*` torch.library operators of torch_ops.py (so `torch.compile` of a model that calls them records one
+opaque node each, run.py:7-9); the `_*_impl` functions below are the operator bodies: the ctypes calls.
 """
 import ctypes
 
@@ -17,6 +19,7 @@ import torch
 
 from . import _lib
 from .calib import CAMERA_NAMES, cameras_for
+from . import torch_ops  # noqa: F401  (registers the egr::* operators)
 
 
 def _stream(t=None):
@@ -57,6 +60,14 @@ def get_max_preds(heatmaps, threshold=0.5, normalize=False, return_index=False):
     assert isinstance(heatmaps, torch.Tensor), 'heatmaps should be a torch.Tensor'
     assert heatmaps.ndim == 4, 'heatmaps should be 4-ndim'
     _need_cuda(heatmaps, "get_max_preds")
+    if return_index:
+        preds, maxvals, valid, idx = _decode_argmax_impl(heatmaps, threshold, normalize, True)
+        return preds, maxvals.squeeze(), valid.squeeze(), idx
+    preds, maxvals, valid = torch.ops.egr.decode_argmax(heatmaps, float(threshold), bool(normalize))
+    return preds, maxvals.squeeze(), valid.squeeze()      # loss.py:142 squeezes size-1 dims
+
+
+def _decode_argmax_impl(heatmaps, threshold, normalize, return_index=False):
     B, J, H, W = heatmaps.shape
     hm = heatmaps.detach()
     if hm.dtype != torch.float32 or not hm.is_contiguous():
@@ -70,8 +81,7 @@ def get_max_preds(heatmaps, threshold=0.5, normalize=False, return_index=False):
     with _on(hm):
         _lib.check(lib.egr_decode_argmax(_ptr(hm), B, J, H, W, float(threshold), int(bool(normalize)), _ptr(preds),
                                          _ptr(maxvals), _ptr(valid), _ptr(idx), _stream(hm)))
-    out = (preds, maxvals.squeeze(), valid.squeeze())      # loss.py:142 squeezes size-1 dims
-    return out + (idx,) if return_index else out
+    return (preds, maxvals, valid, idx) if return_index else (preds, maxvals, valid)
 
 
 def get_max_preds_soft_pytorch(batch_heatmaps, normalize=False):
@@ -79,6 +89,10 @@ def get_max_preds_soft_pytorch(batch_heatmaps, normalize=False):
     -> preds [B, J, 2] (expected x, y under softmax over H*W), maxvals [B, J, 1]."""
     assert len(batch_heatmaps.shape) == 4, 'batch_images should be 4-ndim (B, J, H, W)'
     _need_cuda(batch_heatmaps, "get_max_preds_soft_pytorch")
+    return torch.ops.egr.decode_soft_argmax(batch_heatmaps, bool(normalize))
+
+
+def _decode_soft_argmax_impl(batch_heatmaps, normalize):
     B, J, H, W = batch_heatmaps.shape
     hm = batch_heatmaps.detach()
     if hm.dtype != torch.float32 or not hm.is_contiguous():
@@ -96,6 +110,10 @@ def integrate_tensor_2d(heatmaps, softmax=True, multiplier=100.0):
     """Drop-in for pose_estimation.utils.util.integrate_tensor_2d (:80-109): integral (soft-argmax) decoding.
     -> coordinates [B, J, 2] (x, y) and the normalised heatmaps [B, J, H, W] (softmax(hm * multiplier) or relu)."""
     _need_cuda(heatmaps, "integrate_tensor_2d")
+    return torch.ops.egr.integrate_tensor_2d(heatmaps, bool(softmax), float(multiplier))
+
+
+def _integrate_tensor_2d_impl(heatmaps, softmax, multiplier):
     batch_size, n_heatmaps, h, w = heatmaps.shape
     hm = heatmaps.detach()
     if hm.dtype != torch.float32 or not hm.is_contiguous():
@@ -172,6 +190,12 @@ def generate_target_batch(joints, image_size=872, heatmap_size=64, sigma=1, out=
         joints = joints.cuda(non_blocking=True)
     joints = joints.contiguous()
     assert joints.shape[-1] == 2 and joints.ndim >= 2
+    if out is None:
+        return torch.ops.egr.generate_target(joints, float(image_size), int(heatmap_size), float(sigma))
+    return _generate_target_impl(joints, image_size, heatmap_size, sigma, out)
+
+
+def _generate_target_impl(joints, image_size, heatmap_size, sigma, out):
     J = joints.shape[-2]
     n_maps = joints.numel() // (J * 2)
     shape = tuple(joints.shape[:-1]) + (heatmap_size, heatmap_size)
@@ -205,11 +229,20 @@ def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations,
     _, Q, _, n_levels, P, _ = sampling_locations.shape
     if n_levels != 1:
         raise NotImplementedError("egorear_b200.ms_deform_attn: single-level only (n_levels=%d)" % n_levels)
-    if isinstance(spatial_shapes, torch.Tensor):
+    if isinstance(spatial_shapes, torch.Tensor) and not torch.compiler.is_compiling():
         H, W = int(spatial_shapes[0, 0]), int(spatial_shapes[0, 1])
+    elif isinstance(spatial_shapes, torch.Tensor):
+        # under torch.compile reading the buffer would be a graph break: the reference only uses square single-level maps
+        H = W = int(round(L ** 0.5))
     else:
         H, W = int(spatial_shapes[0][0]), int(spatial_shapes[0][1])
     assert H * W == L
+    return torch.ops.egr.msda_forward(value, H, W, sampling_locations, attention_weights)
+
+
+def _msda_impl(value, H, W, sampling_locations, attention_weights):
+    B, L, nh, hd = value.shape
+    _, Q, _, n_levels, P, _ = sampling_locations.shape
     value = value.float().contiguous()
     loc = sampling_locations.float().contiguous()
     aw = attention_weights.float().contiguous()
@@ -283,6 +316,10 @@ def reproject_fisheye(pts3d, camera_model, coord_trans_mat=None, calib=None):
 def heatmap_head_1x1(feat, weight, bias):
     """1x1 conv head of EgoPoseFormerHeatmap on [N,C,H,W] fp32 (estimator/egoposeformer_heatmap.py:34-39)."""
     _need_cuda(feat, "heatmap_head_1x1")
+    return torch.ops.egr.heatmap_head_1x1(feat, weight, bias)
+
+
+def _heatmap_head_1x1_impl(feat, weight, bias):
     N, C, H, W = feat.shape
     J = weight.shape[0]
     feat = _aligned16(feat.float().contiguous())
@@ -298,6 +335,10 @@ def heatmap_head_1x1(feat, weight, bias):
 
 def pack_joints(preds2d, pose3d):
     """[B, ...] 2D joints + [B, J3, 3] pose -> packed fp32 [B, n2d+n3d] row per frame (all-gather payload)."""
+    return torch.ops.egr.pack_joints(preds2d, pose3d)
+
+
+def _pack_joints_impl(preds2d, pose3d):
     B = preds2d.shape[0]
     p2 = preds2d.reshape(B, -1).float().contiguous()
     p3 = pose3d.reshape(B, -1).float().contiguous()

@@ -20,7 +20,7 @@ def _ptr(t):
 
 
 def dense(A, W, bias, D, M, N, K, lda, ldd, amode=0, epi=0, aux=None, kblk=0, kblk_stride=0, Hin=0, Win=0, Cin=0, Hout=0,
-          Wout=0, groups=1, a_gs=0, w_gs=0, b_gs=0, d_gs=0, aux_gs=0, use_tc=1):
+          Wout=0, groups=1, a_gs=0, w_gs=0, b_gs=0, d_gs=0, aux_gs=0, use_tc=1, ka=0):
     from egorear_b200 import _lib
     lib = _lib.load()
     d = _lib.DenseDesc()
@@ -33,6 +33,7 @@ def dense(A, W, bias, D, M, N, K, lda, ldd, amode=0, epi=0, aux=None, kblk=0, kb
     d.a_is_bf16 = code[A.dtype]
     d.d_is_bf16 = code[D.dtype]
     d.use_tc = use_tc
+    d.ka = ka
     _lib.check(lib.egr_dense_stage(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
 
@@ -233,3 +234,73 @@ def test_tc_fp16_conv3s2_and_saturation():
     D2 = torch.zeros((128, 64), device="cuda", dtype=torch.float16)
     dense(A, W2, None, D2, 128, 64, 64, 64, 64)
     assert torch.isfinite(D2).all() and float(D2.max()) == 65504.0 and float(D2.min()) == -65504.0
+
+
+def _split16(w):
+    hi = w.half()
+    lo = (w - hi.float()).half()
+    return hi, lo
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(4096, 256, 128, 1), (1000, 128, 256, 4), (960, 256, 4096, 4)])
+def test_tc_fp16_split_weights(M, N, K, groups):
+    """EGR_PREC_FP16 dense stage: W = [W_hi | W_lo] along K (K' = 2K, ka = K: the k loop re-reads A): the result equals
+    A_fp16 x W_fp32 to fp32-accumulation accuracy, i.e. the weight rounding error is gone (a single fp16 W is ~5e-4 off)"""
+    g = torch.Generator(device="cuda").manual_seed(41)
+    A = torch.randn((groups, M, K), generator=g, device="cuda").half()
+    W = torch.randn((groups, N, K), generator=g, device="cuda") * K ** -0.5
+    bias = torch.randn((groups, N), device="cuda")
+    hi, lo = _split16(W)
+    Ws = torch.cat([hi, lo], dim=2).contiguous()                       # [g][N][2K]
+    D = torch.full((groups, M, N), float("nan"), device="cuda")
+    dense(A, Ws, bias, D, M, N, 2 * K, K, N, epi=1, groups=groups, a_gs=M * K, w_gs=N * 2 * K, b_gs=N, d_gs=M * N, ka=K)
+    want = torch.relu(torch.einsum("gmk,gnk->gmn", A.double(), W.double()) + bias.double()[:, None, :]).float()
+    err = float((D - want).abs().max() / want.abs().max())
+    single = torch.relu(torch.einsum("gmk,gnk->gmn", A.double(), hi.double()) + bias.double()[:, None, :]).float()
+    err_single = float((single - want).abs().max() / want.abs().max())
+    print("split-weight rel err %.2e (single fp16 weight: %.2e)" % (err, err_single))
+    assert err < 2e-5 and err < 0.2 * err_single
+
+
+def test_tc_fp16_split_weights_conv3s2():
+    Hin, Cin, N, n_img = 64, 128, 256, 3
+    g = torch.Generator(device="cuda").manual_seed(42)
+    x = torch.randn((n_img, Hin, Hin, Cin), generator=g, device="cuda").half()
+    w = torch.randn((N, Cin, 3, 3), generator=g, device="cuda") * (9 * Cin) ** -0.5
+    bias = torch.randn((N,), device="cuda")
+    Wp = w.permute(0, 2, 3, 1).contiguous().reshape(N, 9 * Cin)
+    hi, lo = _split16(Wp)
+    Ws = torch.cat([hi, lo], dim=1).contiguous()
+    M = n_img * (Hin // 2) ** 2
+    D = torch.full((M, N), float("nan"), device="cuda")
+    dense(x, Ws, bias, D, M, N, 2 * 9 * Cin, 0, N, amode=1, epi=1, Hin=Hin, Win=Hin, Cin=Cin, ka=9 * Cin)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), stride=2, padding=1)
+    want = torch.relu(ref).permute(0, 2, 3, 1).reshape(M, N).float()
+    assert float((D - want).abs().max() / want.abs().max()) < 2e-5
+
+
+def tf32_rna(x):
+    """nearest TF32 value, ties away (cvt.rna.tf32.f32)"""
+    u = x.contiguous().view(torch.int32)
+    return ((u + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K,groups", [(960, 256, 256, 4), (960, 256, 3200, 4), (64, 256, 512, 4)])
+def test_tc_tf32x3(M, N, K, groups):
+    """the fp32-grade token Linear of EGR_PREC_FP16: rows [x | x_lo] (x raw fp32: the tensor core truncates it to TF32),
+    weights [W_hi | W_hi | W_lo], K' = 3K with ka = 2K.  Error vs float64 ~1e-6, three orders below plain TF32."""
+    g = torch.Generator(device="cuda").manual_seed(43)
+    X = torch.randn((groups, M, K), generator=g, device="cuda")
+    W = torch.randn((groups, N, K), generator=g, device="cuda") * K ** -0.5
+    x_hi = tf32_trunc(X)
+    A = torch.cat([X, tf32_rna(X - x_hi)], dim=2).contiguous()          # [g][M][2K]
+    w_hi = tf32_rna(W)
+    Ws = torch.cat([w_hi, w_hi, tf32_rna(W - w_hi)], dim=2).contiguous()   # [g][N][3K]
+    D = torch.full((groups, M, N), float("nan"), device="cuda")
+    dense(A, Ws, None, D, M, N, 3 * K, 2 * K, N, groups=groups, a_gs=M * 2 * K, w_gs=N * 3 * K, d_gs=M * N, ka=2 * K)
+    want = torch.einsum("gmk,gnk->gmn", X.double(), W.double()).float()
+    err = float((D - want).abs().max() / want.abs().max())
+    plain = torch.einsum("gmk,gnk->gmn", tf32_rna(X).double(), w_hi.double()).float()
+    err_plain = float((plain - want).abs().max() / want.abs().max())
+    print("3xTF32 rel err %.2e (plain TF32: %.2e)" % (err, err_plain))
+    assert err < 5e-6 and err < 0.05 * err_plain

@@ -181,3 +181,62 @@ def test_integrate_tensor_2d_golden_and_oracle(ops, golden):
             assert torch.allclose(p.sum((2, 3)).cpu(), torch.ones(shape[:2]), atol=1e-5)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.integrate_tensor_2d(hm)
+
+
+def test_soft_decoders_propagate_nan():
+    """a NaN in a map makes maxvals and both coordinates NaN, like torch.max / softmax in the reference
+    (utils/loss.py:145-177, utils/util.py:80-109); the other maps are untouched"""
+    from egorear_b200 import ops
+    from oracle import model_ref
+    g = torch.Generator().manual_seed(5)
+    hm = torch.randn((2, 3, 64, 64), generator=g)
+    hm[1, 2, 17, 40] = float("nan")
+    p, m = ops.get_max_preds_soft_pytorch(hm.cuda())
+    rp, rm = model_ref.get_max_preds_soft_pytorch(hm)
+    assert torch.isnan(p[1, 2]).all() and torch.isnan(m[1, 2]).all() and torch.isnan(rp[1, 2]).all()
+    ok = torch.ones((2, 3), dtype=torch.bool); ok[1, 2] = False
+    assert torch.allclose(p.cpu()[ok], rp[ok], rtol=1e-4, atol=1e-3)
+    for softmax in (True, False):
+        c, pr = ops.integrate_tensor_2d(hm.cuda(), softmax=softmax, multiplier=3.0)
+        rc, rpr = model_ref.integrate_tensor_2d(hm, softmax=softmax, multiplier=3.0)
+        assert torch.isnan(c[1, 2]).all() and torch.isnan(rc[1, 2]).all()
+        assert torch.allclose(c.cpu()[ok], rc[ok], rtol=1e-4, atol=1e-3)
+        assert not torch.isnan(c.cpu()[ok]).any()
+
+
+def test_misaligned_views_are_handled():
+    """a contiguous view whose storage offset is not a multiple of 16 bytes must not fault the 128-bit kernels"""
+    from egorear_b200 import ops
+    from oracle import model_ref
+    g = torch.Generator().manual_seed(6)
+    base = torch.randn((1 + 2 * 15 * 4096,), generator=g)
+    hm_c = base[1:].view(2, 15, 64, 64)
+    hm = base.cuda()[1:].view(2, 15, 64, 64)
+    assert hm.data_ptr() % 16 != 0 and hm.is_contiguous()
+    p, m, v = ops.get_max_preds(hm, 0.5, True)
+    rp, rm, rv = model_ref.get_max_preds(hm_c, 0.5, True)
+    assert torch.equal(p.cpu(), rp) and torch.equal(v.cpu(), rv)
+    ps, ms = ops.get_max_preds_soft_pytorch(hm)
+    assert torch.allclose(ps.cpu(), model_ref.get_max_preds_soft_pytorch(hm_c)[0], rtol=1e-4, atol=1e-3)
+    torch.cuda.synchronize()
+
+
+def test_generate_target_streams_and_sigmas():
+    """the Gaussian patch travels by value, so concurrent calls on two streams with different sigmas cannot
+    overwrite each other's patch (there used to be one thread-local device buffer)"""
+    from egorear_b200 import ops, synth
+    kp = torch.from_numpy(synth.synth_keypoints(256, 4, 16, seed=2)).cuda()
+    want1 = ops.generate_target_batch(kp, sigma=1).clone()
+    want2 = ops.generate_target_batch(kp, sigma=2).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for it in range(8):
+        with torch.cuda.stream(s1):
+            a = ops.generate_target_batch(kp, sigma=1)
+        with torch.cuda.stream(s2):
+            b = ops.generate_target_batch(kp, sigma=2)
+        outs.append((a, b))
+    torch.cuda.synchronize()
+    for a, b in outs:
+        assert torch.equal(a, want1) and torch.equal(b, want2)
