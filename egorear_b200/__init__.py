@@ -59,8 +59,13 @@ def _as_method(fn):
     return method
 
 
-def patch(precision="bf16", modules=None, strict=False):
+def patch(precision="fp16", modules=None, strict=False, datasets=False):
     """Rebind the hot-path names inside the reference's modules to the B200 implementations.
+
+    precision: "fp16" (tensor cores, inside the fp32 parity bound), "bf16" (tensor cores, stated looser bound) or "fp32"
+    (SIMT, reference-grade).  datasets=True additionally moves the datasets' resize + normalise and heatmap-target loading
+    to the GPU (egorear_b200/datasets.py): the dataset modules' call sites are substituted and the three wrapper classes
+    get an `on_after_batch_transfer` hook that finishes the batch on the device.
 
     Only modules that can be imported (or are already in sys.modules) are touched; with strict=True a module of
     PATCH_TABLE that fails to import raises.  Returns {module name: [names rebound]}.
@@ -108,4 +113,12 @@ def patch(precision="bf16", modules=None, strict=False):
             for mname, fname in methods.items():
                 setattr(cls, mname, _as_method(getattr(metrics, fname)))
                 done.setdefault(modname, []).append("%s.%s" % (cname, mname))
+            if datasets:
+                from . import datasets as egd
+                cls.on_after_batch_transfer = egd.on_after_batch_transfer
+                done.setdefault(modname, []).append("%s.on_after_batch_transfer" % cname)
+    if datasets:
+        from . import datasets as egd
+        for name in egd.patch_datasets(strict=strict):
+            done.setdefault(name, []).extend(["Image", "transforms", "np"])
     return done

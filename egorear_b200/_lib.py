@@ -80,6 +80,12 @@ SIGNATURES = {
     "egr_pose3d_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
     "egr_pack_joints": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "egr_backbone_create": (c_int, [c_int, c_int, POINTER(c_void_p)]),
+    "egr_backbone_destroy": (c_int, [c_void_p]),
+    "egr_backbone_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64]),
+    "egr_backbone_prepack": (c_int, [c_void_p, c_void_p]),
+    "egr_backbone_workspace_bytes": (c_int64, [c_void_p, c_int]),
+    "egr_backbone_forward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "egr_resample_coeffs": (c_int, [c_int, c_int, POINTER(c_int), c_void_p, c_void_p]),
     "egr_resample_digits": (c_int, [c_int, c_int, POINTER(c_int), c_void_p]),
     "egr_preprocess_images": (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float),

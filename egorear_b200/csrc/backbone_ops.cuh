@@ -1,0 +1,21 @@
+// Backbone-side kernels around the tcgen05 conv stages (declarations; see backbone_ops.cu).
+#pragma once
+#include "common.cuh"
+
+namespace egr {
+
+constexpr int STEM_K = 192;     // 7*7*3 = 147 taps x channels, zero padded to a multiple of the 64-element k-block
+
+// img [B][V][3][H][W] fp32 -> out [V][B][(H/2)*(W/2)][STEM_K] 16-bit (dt: 1 bf16, 2 fp16): rows of the 7x7 stride-2 pad-3 stem conv
+int stem_im2col(const float* img, void* out, int dt, int B, int V, int H, int W, cudaStream_t st);
+// nn.MaxPool2d(3, stride 2, padding 1) on channels-last [img][H][W][C] 16-bit -> [img][H/2][W/2][C]
+int maxpool3s2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int W, int C, cudaStream_t st);
+// in [V][B][HW][C] 16-bit -> out [B][V][C][HW] fp32
+int bottom_to_nchw(const void* in, float* out, int dt, int B, int V, int HW, int C, cudaStream_t st);
+// eval-mode BatchNorm folded into the conv in front of it: w_out[n][k] = w[n][k] * g[n] / sqrt(var[n] + eps), b_out[n] = beta[n] - mean[n] * (..)
+int bn_fold(const float* w, const float* gamma, const float* beta, const float* mean, const float* var, float eps, float* w_out,
+            float* b_out, int N, int K, cudaStream_t st);
+// stem weight [N][3][7][7] -> [N][STEM_K] in im2col order (ky, kx, c), zero padded
+int stem_repack(const float* w, float* out, int N, cudaStream_t st);
+
+}  // namespace egr

@@ -132,8 +132,8 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
     d.Hin = c->Hin; d.Win = c->Win; d.Cin = c->Cin; d.Hout = c->Hout; d.Wout = c->Wout;
     d.groups = c->groups > 0 ? c->groups : 1;
     d.a_gs = c->a_gs; d.w_gs = c->w_gs; d.b_gs = c->b_gs; d.d_gs = c->d_gs; d.aux_gs = c->aux_gs;
-    EGR_CHECK(d.amode == A_PLAIN || d.amode == A_CONV3S2, EGR_ERR_INVALID, "dense_stage: amode %d", d.amode);
-    EGR_CHECK(d.epi >= EPI_NONE && d.epi <= EPI_RELU_ADDUP, EGR_ERR_INVALID, "dense_stage: epi %d", d.epi);
+    EGR_CHECK(d.amode >= A_PLAIN && d.amode <= A_CONV3S1, EGR_ERR_INVALID, "dense_stage: amode %d", d.amode);
+    EGR_CHECK(d.epi >= EPI_NONE && d.epi <= EPI_ADDUP_RELU, EGR_ERR_INVALID, "dense_stage: epi %d", d.epi);
     cudaStream_t st = (cudaStream_t)stream;
     if (c->use_tc) {
         // a_is_bf16 / d_is_bf16: 0 fp32, 1 bf16, 2 fp16

@@ -14,6 +14,8 @@ namespace egr {
 enum AMode : int {
     A_PLAIN = 0,      // A[m][k] = A[(k / kblk) * kblk_stride + m * lda + (k % kblk)]
     A_CONV3S2 = 1,    // 3x3, stride 2, pad 1 over NHWC [img][Hin][Win][Cin]; k = (ky*3+kx)*Cin + ci
+                      // (K == Cin: only the centre tap = a 1x1 stride-2 conv, ResNet's downsample branch)
+    A_CONV3S1 = 2,    // 3x3, stride 1, pad 1 over NHWC [img][Hin][Win][Cin] (tensor-core path only): output Hin x Win
 };
 
 enum Epi : int {
@@ -21,6 +23,8 @@ enum Epi : int {
     EPI_RELU = 1,        // relu(acc + bias)
     EPI_GELU = 2,        // exact-erf gelu(acc + bias)
     EPI_RELU_ADDUP = 3,  // relu(acc + bias) + relu(bilinear_x2_align_corners(aux))   (T1 -> R1 input)
+    EPI_ADD_RELU = 4,    // relu(acc + bias + aux[m][n])                              (ResNet BasicBlock: + identity; tcgen05 path)
+    EPI_ADDUP_RELU = 5,  // relu(acc + bias + bilinear_x2_align_corners(aux))         (FPN fuse conv, low-res half commuted; tcgen05 path)
 };
 
 struct GemmDesc {
@@ -28,7 +32,7 @@ struct GemmDesc {
     const void* W = nullptr;      // weights (float for SIMT, bf16 for tcgen05)
     const float* bias = nullptr;  // [N] fp32 or null
     void* D = nullptr;            // output (float or bf16)
-    const void* aux = nullptr;    // EPI_RELU_ADDUP: [img][(Hout/2)*(Wout/2)][N] pre-activation map
+    const void* aux = nullptr;    // EPI_RELU_ADDUP / EPI_ADDUP_RELU: [img][(Hout/2)*(Wout/2)][N] map; EPI_ADD_RELU: [M][N] (same type as D)
     int M = 0, N = 0, K = 0;
     int64_t lda = 0, ldd = 0;
     int amode = A_PLAIN, epi = EPI_NONE;

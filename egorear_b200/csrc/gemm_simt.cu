@@ -169,6 +169,9 @@ static int launch_simt(const GemmDesc& d, cudaStream_t st) {
 int gemm_simt(const GemmDesc& d, int a_is_bf16, int d_is_bf16, cudaStream_t st) {
     EGR_CHECK(d.M > 0 && d.N > 0 && d.K > 0, EGR_ERR_INVALID, "gemm: empty problem %d %d %d", d.M, d.N, d.K);
     EGR_CHECK(d.K % SBK == 0, EGR_ERR_UNSUPPORTED, "gemm_simt: K=%d must be a multiple of %d", d.K, SBK);
+    EGR_CHECK((d.amode == A_PLAIN || d.amode == A_CONV3S2) && d.epi <= EPI_RELU_ADDUP && d.ka == 0 &&
+              !(d.amode == A_CONV3S2 && d.K == d.Cin), EGR_ERR_UNSUPPORTED,
+              "gemm_simt: amode %d / epi %d / split operands exist on the tensor-core path only", d.amode, d.epi);
     EGR_CHECK(d.N % 4 == 0 || d.ldd % 4 != 0 || true, EGR_ERR_UNSUPPORTED, "gemm_simt: N");
     if (d.amode == A_CONV3S2)
         EGR_CHECK(d.Cin % SBK == 0 && d.K == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,

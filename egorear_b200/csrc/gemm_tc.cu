@@ -53,7 +53,8 @@ struct TcParams {
     int amode;
     int kblk;                 // A_PLAIN: elements per outer k block (== K when there is no K split of A)
     int ka;                   // A's own K: k >= ka re-reads A at k - ka (split weights [W_hi | W_lo]); == K otherwise
-    int Cin, Wout, HWout;     // A_CONV3S2
+    int Cin, Wout, HWout;     // A_CONV3S2 / A_CONV3S1 (output geometry; == input geometry for the stride-1 conv)
+    int tap_fixed;            // A_CONV3S2 with K == Cin: the centre tap only (1x1 stride-2 conv); -1 otherwise
     int epi;
     int round_out;            // fp32 output rounded to the nearest TF32 value
     int partial;              // split-K: raw fp32 partial sums to D + ks * part_stride, no bias / activation
@@ -154,7 +155,13 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
     float wy0 = 0.f, wy1 = 0.f, wx0 = 0.f, wx1 = 0.f;
     const TO* aux = nullptr;
     bool row_ok = false;
-    if (EPI == EPI_RELU_ADDUP) {
+    constexpr bool UPE = (EPI == EPI_RELU_ADDUP || EPI == EPI_ADDUP_RELU);      // bilinear-x2 source gathered per row
+    if (EPI == EPI_ADD_RELU) {
+        const int m = m_w0 + lane;
+        row_ok = m < p.M;
+        if (row_ok) aux = reinterpret_cast<const TO*>(p.aux) + (int64_t)tc.g * p.aux_gs + (int64_t)m * p.N;
+    }
+    if (UPE) {
         const int m = m_w0 + lane;
         row_ok = m < p.M;
         if (row_ok) {
@@ -176,9 +183,9 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
         uint32_t (&cur)[32] = v[c & 1];
         // ADDUP: the 4 bilinear sources of the chunk's columns are gathered (L2) while the TMEM load is in flight;
         // bf16 keeps the whole chunk in flight (16 x 16 B), fp32 one 8-column group at a time
-        constexpr int PF = (EPI == EPI_RELU_ADDUP) ? ((OUT_B == 2) ? 4 : 1) : 1;
+        constexpr int PF = UPE ? ((OUT_B == 2) ? 4 : 1) : 1;
         Raw8<TO> ax[PF][4];
-        if (EPI == EPI_RELU_ADDUP && PF == 4 && row_ok) {
+        if (UPE && PF == 4 && row_ok) {
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
                 const int col = n_base + c * 32 + gq * 8;
@@ -219,7 +226,19 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = gelu_erf(x[i]);
             }
-            if (EPI == EPI_RELU_ADDUP) {
+            if (EPI == EPI_ADD_RELU) {
+                if (row_ok) {
+                    float a8[8];
+                    Raw8<TO> r8;
+                    r8.ld(aux + n0 + j);
+                    r8.unpack(a8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] += a8[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+            }
+            if (UPE) {
                 if (row_ok) {
                     float a00[8], a01[8], a10[8], a11[8];
                     constexpr int PFI = (PF == 4) ? 1 : 0;
@@ -232,8 +251,13 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float u = wy0 * (wx0 * a00[i] + wx1 * a01[i]) + wy1 * (wx0 * a10[i] + wx1 * a11[i]);
-                        x[i] += fmaxf(u, 0.f);
+                        if (EPI == EPI_RELU_ADDUP) x[i] += fmaxf(u, 0.f);
+                        else x[i] += u;
                     }
+                }
+                if (EPI == EPI_ADDUP_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
                 }
             }
             if (ROUND) {
@@ -319,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 // conv tile geometry (rows of all groups form one contiguous image list)
                 int img0 = 0, oy0 = 0;
-                if (p.amode == A_CONV3S2) {
+                if (p.amode != A_PLAIN) {
                     const long long gm0 = (long long)tc.g * p.M + (long long)tc.mt * BM;
                     img0 = (int)(gm0 / p.HWout);
                     oy0 = (int)(gm0 % p.HWout) / p.Wout;
@@ -333,8 +357,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int k_a = (k >= p.ka) ? k - p.ka : k;      // split weights: the second half of K re-reads A
                     if (p.amode == A_PLAIN) {
                         tma_load_4d(sa, &tmA, full, k_a % p.kblk, tc.mt * BM, k_a / p.kblk, tc.g);
-                    } else {
+                    } else if (p.amode == A_CONV3S1) {
+                        // tap (ky,kx) of the tile's output pixels = the same box shifted by (ky-1, kx-1); the zero padding is
+                        // the TMA unit's out-of-bounds fill (x = -1 / W, y = -1 / H of each image)
                         const int tap = k_a / p.Cin, ci = k_a - tap * p.Cin;
+                        const int ky = tap / 3, kx = tap - ky * 3;
+                        tma_load_4d(sa, &tmA, full, ci, kx - 1, oy0 + ky - 1, img0);
+                    } else {
+                        int tap = k_a / p.Cin;
+                        const int ci = k_a - tap * p.Cin;
+                        if (p.tap_fixed >= 0) tap = p.tap_fixed;
                         const int ky = tap / 3, kx = tap - ky * 3;
                         // input pixel (2*oy + ky - 1, 2*ox + kx - 1) = pair index (oy + dy, ox + dx), parity (hp, wp)
                         const int wp = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
@@ -421,6 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (epi == EPI_RELU) EGR_EPI(EPI_RELU, false);
                 else if (epi == EPI_GELU) EGR_EPI(EPI_GELU, false);
                 else if (epi == EPI_RELU_ADDUP) EGR_EPI(EPI_RELU_ADDUP, false);
+                else if (sizeof(TO) == 2 && epi == EPI_ADD_RELU) EGR_EPI(EPI_ADD_RELU, false);          // backbone stages: 16-bit outputs only
+                else if (sizeof(TO) == 2 && epi == EPI_ADDUP_RELU) EGR_EPI(EPI_ADDUP_RELU, false);
                 else EGR_EPI(EPI_NONE, false);
             }
 #undef EGR_EPI
@@ -555,12 +589,14 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     EGR_CHECK((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0 &&
               (reinterpret_cast<uintptr_t>(d.D) & 15) == 0, EGR_ERR_INVALID, "gemm_tc: operands must be 16-byte aligned");
     EGR_CHECK(d.ldd % 8 == 0 && d.d_gs % 8 == 0, EGR_ERR_UNSUPPORTED, "gemm_tc: ldd / d_gs must be multiples of 8 elements");
-    if (d.epi == EPI_RELU_ADDUP) EGR_CHECK(d.aux && d.Hout > 0 && d.Wout > 0, EGR_ERR_INVALID, "gemm_tc: ADDUP needs aux + geometry");
+    if (d.epi == EPI_RELU_ADDUP || d.epi == EPI_ADDUP_RELU) EGR_CHECK(d.aux && d.Hout > 0 && d.Wout > 0, EGR_ERR_INVALID, "gemm_tc: ADDUP needs aux + geometry");
+    if (d.epi == EPI_ADD_RELU || d.epi == EPI_ADDUP_RELU)
+        EGR_CHECK(d.aux && out_dt_req != DT_F32, EGR_ERR_UNSUPPORTED, "gemm_tc: the residual epilogues need aux and a 16-bit output");
 
     const int nsm = sm_count();
     const int m_tiles = ceil_div(d.M, BM);
     const int kb_total = d.K / BK;
-    const bool can_split = d.epi != EPI_RELU_ADDUP && d.groups == 1 && d.ldd == d.N && kb_total >= 32;
+    const bool can_split = d.epi != EPI_RELU_ADDUP && d.epi != EPI_ADD_RELU && d.epi != EPI_ADDUP_RELU && d.groups == 1 && d.ldd == d.N && kb_total >= 32;
     auto split_of = [&](int64_t base_tiles) {      // deterministic split-K factor for a skinny problem (1 = none)
         if (!can_split || base_tiles * 4 > nsm) return 1;
         int ks = (int)(nsm / base_tiles);
@@ -631,10 +667,26 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
                                    (cuuint64_t)(d.groups > 1 ? d.a_gs : d.lda) * ES};
         const cuuint32_t box[4] = {(cuuint32_t)BK, BM, 1, 1};
         if ((rc = encode(&tmA, in_dt, d.A, 4, dims, str, box, "A"))) return rc;
+    } else if (d.amode == A_CONV3S1) {
+        const int H = d.Hin, W = d.Win, HW = H * W;
+        EGR_CHECK(d.Cin % BK == 0 && Ka == 9 * d.Cin, EGR_ERR_UNSUPPORTED, "gemm_tc: conv3s1 geometry Cin=%d K=%d", d.Cin, d.K);
+        EGR_CHECK(W <= 256 && BM % W == 0 && (HW % BM == 0 || BM % HW == 0), EGR_ERR_UNSUPPORTED, "gemm_tc: conv3s1 output %dx%d does not tile by %d rows", H, W, BM);
+        EGR_CHECK(d.M % HW == 0, EGR_ERR_INVALID, "gemm_tc: conv M=%d is not a whole number of %dx%d images", d.M, H, W);
+        EGR_CHECK(d.groups == 1 || (d.a_gs == (int64_t)d.M * d.Cin && d.M % BM == 0), EGR_ERR_UNSUPPORTED,
+                  "gemm_tc: conv groups must be contiguous image blocks");
+        const int bh = (HW >= BM) ? BM / W : H;
+        const int bimg = (HW >= BM) ? 1 : BM / HW;
+        p.Cin = d.Cin; p.Wout = W; p.HWout = HW; p.tap_fixed = -1;
+        const int64_t n_img = (int64_t)d.groups * (d.M / HW);
+        const cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
+        const cuuint64_t str[3] = {(cuuint64_t)d.Cin * ES, (cuuint64_t)W * d.Cin * ES, (cuuint64_t)H * W * d.Cin * ES};
+        const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)W, (cuuint32_t)bh, (cuuint32_t)bimg};
+        if ((rc = encode(&tmA, in_dt, d.A, 4, dims, str, box, "A(conv3s1)"))) return rc;
     } else {
         const int Hout = d.Hin / 2, Wout = d.Win / 2, HW = Hout * Wout;
-        EGR_CHECK(d.Cin % BK == 0 && Ka == 9 * d.Cin && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
+        EGR_CHECK(d.Cin % BK == 0 && (Ka == 9 * d.Cin || Ka == d.Cin) && d.Hin % 2 == 0 && d.Win % 2 == 0, EGR_ERR_UNSUPPORTED,
                   "gemm_tc: conv geometry Cin=%d K=%d", d.Cin, d.K);
+        p.tap_fixed = (Ka == d.Cin) ? 4 : -1;        // K == Cin: centre tap only = 1x1 stride-2 conv
         EGR_CHECK(BM % Wout == 0 && (HW % BM == 0 || BM % HW == 0), EGR_ERR_UNSUPPORTED, "gemm_tc: conv output %dx%d does not tile by %d rows", Hout, Wout, BM);
         EGR_CHECK(d.M % HW == 0, EGR_ERR_INVALID, "gemm_tc: conv M=%d is not a whole number of %dx%d images", d.M, Hout, Wout);
         EGR_CHECK(d.groups == 1 || (d.a_gs == (int64_t)(d.M / HW) * d.Hin * d.Win * d.Cin && d.M % BM == 0), EGR_ERR_UNSUPPORTED,

@@ -204,6 +204,33 @@ class MvfexEngine(_EngineBase):
         return hm, ft
 
 
+class BackboneEngine(_EngineBase):
+    """ResnetBackbone.forward of the stereo estimators on the tcgen05 conv stages: images in, the staged
+    16-bit channels-last FPN map + the fp32 stride-32 map out (egr_backbone_*)."""
+    _prefix = "backbone"
+
+    def __init__(self, num_views=4, precision="bf16"):
+        super().__init__()
+        if precision not in ACT_DTYPE:
+            raise RuntimeError("egorear_b200: the backbone engine runs in the tensor-core precisions (bf16 / fp16); fp32 keeps the PyTorch backbone")
+        self.V, self.precision = num_views, precision
+        _lib.check(self._lib.egr_backbone_create(num_views, PREC[precision], ctypes.byref(self._h)))
+
+    def forward(self, img, lane=0):
+        """img [B,V,3,256,256] fp32 CUDA -> (feat_staged [V,B,64,64,128] 16-bit, bfb [B,V,512,8,8] fp32)"""
+        self._sync_params()
+        B, V = img.shape[:2]
+        assert V == self.V and tuple(img.shape[2:]) == (3, 256, 256), "backbone engine: img must be [B, %d, 3, 256, 256]" % self.V
+        img = img.detach().float().contiguous()
+        dev = img.device
+        feat = torch.empty((V, B, 64, 64, 128), dtype=ACT_DTYPE[self.precision], device=dev)
+        bfb = torch.empty((B, V, 512, 8, 8), dtype=torch.float32, device=dev)
+        ws = self._workspace(B, dev, lane)
+        with torch.cuda.device_of(img):
+            _lib.check(self._lib.egr_backbone_forward(self._h, B, _ptr(img), _ptr(feat), _ptr(bfb), _ptr(ws), ws.numel(), _stream(img)))
+        return feat, bfb
+
+
 class Pose3DEngine(_EngineBase):
     """EgoPoseFormerPose3D.forward."""
     _prefix = "pose3d"

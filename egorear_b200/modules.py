@@ -25,7 +25,7 @@ import torch.nn.functional as F
 
 from . import ops, torch_ops
 from .calib import load_calibration
-from .engine import MvfexEngine, Pose3DEngine
+from .engine import BackboneEngine, MvfexEngine, Pose3DEngine
 
 _VIEWS4 = ("front_left", "front_right", "back_left", "back_right")
 
@@ -47,6 +47,8 @@ class _EngineOwner:
     def __getstate__(self):
         st = dict(self.__dict__)
         st["_engine"] = None               # a C handle: rebuilt lazily by the copy
+        if "_bb_engine" in st:
+            st["_bb_engine"] = None
         return st
 
     def __setstate__(self, state):
@@ -66,8 +68,11 @@ class _EngineOwner:
             self._engine = self._make_engine()
             self._engine.set_params(self._engine_params())
             if not getattr(self, "_egr_hooked", False):
-                self.register_load_state_dict_post_hook(
-                    lambda module, incompatible_keys: module._engine.invalidate() if module._engine is not None else None)
+                def _invalidate(module, incompatible_keys):
+                    for e in (module._engine, getattr(module, "_bb_engine", None)):
+                        if e is not None:
+                            e.invalidate()
+                self.register_load_state_dict_post_hook(_invalidate)
                 self._egr_hooked = True
         return self._engine
 
@@ -460,8 +465,17 @@ class HeatmapMVF(_EngineOwner, nn.Module):
 class EgoPoseFormerHeatmapMVFEX(_EngineOwner, nn.Module):
     def __init__(self, num_views, image_size, num_heatmap, feat_down_stride, heatmap_threshold, encoder_cfg, mvf_cfg,
                  camera_model, full_training=False, detach_heatmap_feat=False, detach_heatmap_feat_init=False,
-                 use_pred_heatmap_init=False, no_detach_feat_init=False, precision="bf16", build_backbone=True, **kwargs):
+                 use_pred_heatmap_init=False, no_detach_feat_init=False, precision="bf16", build_backbone=True,
+                 backbone_impl="torch", **kwargs):
+        """backbone_impl (not in the reference): "torch" = the PyTorch ResNet18+FPN modules run as in the reference (the
+        features exist as NCHW fp32 tensors and are returned in list_frame_feat[0]); "egr" = the backbone engine
+        (tcgen05 conv stages, 16-bit precisions): the FPN map goes to the hot path as its staged channels-last copy and
+        list_frame_feat[0] is None."""
         super().__init__()
+        if backbone_impl not in ("torch", "egr"):
+            raise ValueError("backbone_impl must be 'torch' or 'egr'")
+        self.backbone_impl = backbone_impl
+        self._bb_engine = None
         if num_views not in (2, 4):
             raise NotImplementedError("egorear_b200: num_views must be 4 or 2 (no shipped config uses 3)")
         self.num_views, self.num_heatmap = num_views, num_heatmap
@@ -501,6 +515,39 @@ class EgoPoseFormerHeatmapMVFEX(_EngineOwner, nn.Module):
     def _make_engine(self):
         return MvfexEngine(self.num_views, self.num_heatmap, self.heatmap_threshold, self._precision)
 
+    # -- backbone engine --
+    def backbone_state(self):
+        """state_dict entries the backbone engine consumes: conv weights / biases and the BN affine + running statistics of
+        both encoders (not num_batches_tracked, not the estimators' own unused 1x1 heads)"""
+        return {k: v for k, v in self.state_dict(keep_vars=True).items()
+                if k.startswith("heatmap_estimator_") and ".encoder." in k and v.is_floating_point()}
+
+    def backbone_engine(self):
+        if not self._has_backbone:
+            raise RuntimeError("built with build_backbone=False: there are no backbone parameters")
+        if self._bb_engine is None:
+            self._bb_engine = BackboneEngine(self.num_views, self._precision)
+            self._bb_engine.set_params(self.backbone_state())
+            self.engine()                   # installs the load_state_dict hook, which invalidates both engines
+        return self._bb_engine
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        if self._bb_engine is not None:
+            st = self.backbone_state()
+            if all(v.is_cuda for v in st.values()):
+                self._bb_engine.set_params(st)
+            else:
+                self._bb_engine = None
+        return out
+
+    def forward_backbone_staged(self, img, lane=0):
+        """img [B,V,3,256,256] -> (feat_staged [V,B,64,64,128] 16-bit channels-last view-major, bfb [B,V,512,8,8] fp32)
+        through the backbone engine (eval-mode BatchNorm folded into the convs)"""
+        if self.heatmap_estimator_stereo_front.training:
+            raise RuntimeError("egorear_b200: the backbone engine folds eval-mode BatchNorm; call .eval() first")
+        return torch.ops.egr.backbone_forward(self._egr_key, img, int(lane))
+
     def get_anchors_2d_from_hm(self, heatmap):           # :128-143
         with torch.no_grad():
             B, V, C, H, W = heatmap.shape
@@ -535,6 +582,9 @@ class EgoPoseFormerHeatmapMVFEX(_EngineOwner, nn.Module):
     def forward(self, img, heatmap_for_anchor=None):
         if not self._has_backbone:
             raise RuntimeError("built with build_backbone=False: call forward_from_feats(feat, bfb)")
+        if self.backbone_impl == "egr":
+            xh, bfb = self.forward_backbone_staged(img)
+            return self.forward_from_feats(None, bfb, heatmap_for_anchor, feat_staged=xh)
         if self.full_training:
             feat, bb = self.forward_heatmap_feat_estimation(img)
         else:

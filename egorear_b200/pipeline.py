@@ -14,8 +14,11 @@ from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
 
 class HotPathPipeline:
     def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True,
-                 with_backbone=False, materialize_features=True):
+                 with_backbone=False, materialize_features=True, backbone_impl="egr"):
+        """backbone_impl: "egr" = the backbone engine (tcgen05 conv stages) behind backbone_staged(); "torch" = the PyTorch
+        modules under autocast (round 1)"""
         self.V, self.camera_model, self.precision = num_views, camera_model, precision
+        self.backbone_impl = backbone_impl
         self.heatmap = EgoPoseFormerHeatmapMVFEX(**heatmap_mvfex_cfg(num_views, camera_model), precision=precision,
                                                  build_backbone=with_backbone)
         self.pose3d = EgoPoseFormerPose3D(**pose3d_cfg(num_views, camera_model), precision=precision)
@@ -86,6 +89,17 @@ class HotPathPipeline:
         -> (feat_staged bf16 [V,B,64,64,128] view-major channels-last, bfb fp32 [B,V,512,8,8])"""
         from .engine import ACT_DTYPE
         assert self.V == 4 and self.precision in ACT_DTYPE
+        if self.backbone_impl == "egr":
+            B = img.shape[0]
+            if B <= chunk * 4:
+                return self.heatmap.forward_backbone_staged(img)
+            xh = torch.empty((self.V, B, 64, 64, 128), dtype=ACT_DTYPE[self.precision], device=img.device)
+            bfb = torch.empty((B, self.V, 512, 8, 8), dtype=torch.float32, device=img.device)
+            for i in range(0, B, chunk * 4):
+                f, b = self.heatmap.forward_backbone_staged(img[i:i + chunk * 4])
+                xh[:, i:i + chunk * 4].copy_(f)
+                bfb[i:i + chunk * 4].copy_(b)
+            return xh, bfb
         adt = ACT_DTYPE[self.precision]
         if not getattr(self, "_bb_cl", False):
             for n in ("heatmap_estimator_stereo_front", "heatmap_estimator_stereo_back"):

@@ -176,6 +176,20 @@ def _(module_key, heatmap, frame_feat, feat_mv, anchors_2d, anchors_valid, bfb):
             frame_feat.new_empty(tuple(frame_feat.shape), dtype=torch.float32))
 
 
+@torch.library.custom_op("egr::backbone_forward", mutates_args=())
+def backbone_forward(module_key: int, img: Tensor, lane: int) -> Tuple[Tensor, Tensor]:
+    """ResnetBackbone.forward of both stereo estimators -> (feat_staged [V,B,64,64,128] 16-bit, bfb [B,V,512,8,8])"""
+    return _module(module_key).backbone_engine().forward(img, lane=lane)
+
+
+@backbone_forward.register_fake
+def _(module_key, img, lane):
+    B, V = img.shape[:2]
+    m = _MODULES.get(int(module_key))
+    dt = torch.float16 if (m is not None and getattr(m, "_precision", "bf16") == "fp16") else torch.bfloat16
+    return img.new_empty((V, B, 64, 64, 128), dtype=dt), img.new_empty((B, V, 512, 8, 8), dtype=torch.float32)
+
+
 @torch.library.custom_op("egr::pose3d_forward", mutates_args=())
 def pose3d_forward(module_key: int, chain_key: int, feats_init: Optional[Tensor], feats_final: Optional[Tensor],
                    heatmap: Optional[Tensor], coord_trans_mat: Optional[Tensor], lane: int) -> Tensor:

@@ -148,9 +148,13 @@ int egr_heatmap_head_1x1(const float* feat, const float* weight, const float* bi
  * / nn.Linear + activation of the reference stacks (e.g. estimator/egoposeformer_heatmap_mvf_ex.py:525-532).
  *   activations are channels-last: A row m = pixel (img, y, x), K = channels; W is [N][K] (3x3: [N][ky][kx][Cin]).
  *   amode 0: plain rows (lda); with kblk > 0 the K axis is split in blocks of kblk elements kblk_stride apart.
- *   amode 1: implicit 3x3 stride-2 pad-1 conv over [img][Hin][Win][Cin]; M = n_img*(Hin/2)*(Win/2), K = 9*Cin.
+ *   amode 1: implicit 3x3 stride-2 pad-1 conv over [img][Hin][Win][Cin]; M = n_img*(Hin/2)*(Win/2), K = 9*Cin
+ *            (use_tc: K = Cin selects the centre tap only = a 1x1 stride-2 conv, ResNet's downsample branch).
+ *   amode 2: implicit 3x3 stride-1 pad-1 conv (use_tc only); M = n_img*Hin*Win, K = 9*Cin  (models/backbones/resnet.py).
  *   epi 0 none, 1 ReLU, 2 exact-erf GELU, 3 ReLU then + relu(bilinear_x2_align_corners(aux)) with
- *       aux [img][(Hout/2)*(Wout/2)][N] in D's dtype (the "offset_pred + frame_feat" of :715).
+ *       aux [img][(Hout/2)*(Wout/2)][N] in D's dtype (the "offset_pred + frame_feat" of :715);
+ *       use_tc, 16-bit D only: 4 relu(acc + bias + aux[M][N]) (BasicBlock residual), 5 relu(acc + bias +
+ *       bilinear_x2_align_corners(aux)) (EfficientFPN fuse conv with its low-resolution half commuted in front of the upsample).
  *   groups independent problems at element strides a_gs / w_gs / b_gs / d_gs / aux_gs.
  *   use_tc 1: tcgen05 + TMA kernel, fp32 accumulate in TMEM; a_is_bf16 1: A and W bf16, 2: A and W fp16 (kind::f16),
  *             a_is_bf16 0: A and W fp32, multiplied as TF32 (kind::tf32); d_is_bf16 0 fp32, else the operands' type;
@@ -261,6 +265,26 @@ int egr_pose3d_use_staged(egr_pose3d* h, const void* sampled_nhwc, int sampled_i
 /* Hint for feats_final when the proposal branch runs in fp16 (egr_pose3d_proposal_dtype == 3): its channels-last fp16
  * copy (what egr_mvfex_export_staged(h, 3) leaves).  One-shot. */
 int egr_pose3d_use_staged_final_f16(egr_pose3d* h, const void* final_nhwc_f16);
+/* ---------------------------------------------------------------------------------------------
+ * backbone engine: ResnetBackbone.forward of the two stereo estimators
+ *   (pose_estimation/models/backbones/resnet.py:6-152: torchvision ResNet18 + EfficientFPN, eval mode, BN folded) on the
+ *   tcgen05 conv stages.  Parameters by state_dict key of EgoPoseFormerHeatmapMVFEX
+ *   ("heatmap_estimator_stereo_front.encoder.backbone.layer_s2.0.weight", ... incl. the BN running statistics).
+ *   egr_backbone_forward: img [B, V, 3, 256, 256] f32 ->
+ *     feat_staged [V, B, 64*64, 128] 16-bit (bf16 under EGR_PREC_BF16, fp16 under EGR_PREC_FP16): exactly what
+ *       egr_mvfex_use_staged_input takes - the FPN map never exists in NCHW fp32;
+ *     bfb [B, V, 512, 8, 8] f32: the stride-32 ResNet map (`backbone_feat_bottom` of the jqa query).
+ *   EGR_PREC_FP32 is refused (EGR_ERR_UNSUPPORTED): the fp32 path keeps the PyTorch backbone.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct egr_backbone egr_backbone;
+int egr_backbone_create(int num_views, int precision, egr_backbone** out);
+int egr_backbone_destroy(egr_backbone* h);
+int egr_backbone_set_param(egr_backbone* h, const char* key, const float* ptr, int64_t numel);
+int egr_backbone_prepack(egr_backbone* h, void* stream);
+int64_t egr_backbone_workspace_bytes(egr_backbone* h, int B);
+int egr_backbone_forward(egr_backbone* h, int B, const float* img, void* feat_staged, float* bfb, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
 /* operand type of the proposal branch (conv_frame_feat + mlp_pred.0): 0 fp32 SIMT, 1 bf16, 2 TF32, 3 fp16 */
 int egr_pose3d_proposal_dtype(egr_pose3d* h);
 int egr_pose3d_debug_buffer(egr_pose3d* h, const char* name, void** ptr, int64_t* bytes);

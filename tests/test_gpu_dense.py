@@ -304,3 +304,64 @@ def test_tc_tf32x3(M, N, K, groups):
     err_plain = float((plain - want).abs().max() / want.abs().max())
     print("3xTF32 rel err %.2e (plain TF32: %.2e)" % (err, err_plain))
     assert err < 5e-6 and err < 0.05 * err_plain
+
+
+@pytest.mark.parametrize("H,Cin,N,n_img,groups", [(64, 64, 64, 3, 1), (32, 128, 128, 4, 2), (16, 256, 256, 8, 1), (8, 512, 512, 6, 2),
+                                                   (64, 128, 128, 2, 1)])
+def test_tc_conv3s1(H, Cin, N, n_img, groups):
+    """implicit 3x3 stride-1 pad-1 conv (ResNet18 BasicBlock convs, EfficientFPN fpn_convs; models/backbones/resnet.py): one
+    4-D TMA box per tap, the zero padding is the unit's out-of-bounds fill in x and y of every image"""
+    g = torch.Generator(device="cuda").manual_seed(51)
+    x = torch.randn((groups, n_img, H, H, Cin), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((groups, N, Cin, 3, 3), generator=g, device="cuda") * (9 * Cin) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn((groups, N), device="cuda")
+    Wp = w.permute(0, 1, 3, 4, 2).contiguous().reshape(groups, N, 9 * Cin)
+    M = n_img * H * H
+    D = torch.full((groups, M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dense(x, Wp, bias, D, M, N, 9 * Cin, 0, N, amode=2, epi=1, Hin=H, Win=H, Cin=Cin, groups=groups,
+          a_gs=M * Cin, w_gs=N * 9 * Cin, b_gs=N, d_gs=M * N)
+    for gi in range(groups):
+        ref = F.conv2d(x[gi].double().permute(0, 3, 1, 2), w[gi].double(), bias[gi].double(), stride=1, padding=1)
+        want = torch.relu(ref).permute(0, 2, 3, 1).reshape(M, N).float()
+        check(D[gi], want, torch.bfloat16)
+
+
+def test_tc_conv1x1_stride2_centre_tap():
+    """ResNet's downsample branch: 1x1 stride-2 conv = the 3x3 stride-2 mode with K == Cin (centre tap only)"""
+    Hin, Cin, N, n_img = 64, 64, 128, 4
+    g = torch.Generator(device="cuda").manual_seed(52)
+    x = torch.randn((n_img, Hin, Hin, Cin), generator=g, device="cuda").to(torch.bfloat16)
+    w = (torch.randn((N, Cin), generator=g, device="cuda") * Cin ** -0.5).to(torch.bfloat16)
+    bias = torch.randn((N,), device="cuda")
+    M = n_img * (Hin // 2) ** 2
+    D = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dense(x, w, bias, D, M, N, Cin, 0, N, amode=1, epi=0, Hin=Hin, Win=Hin, Cin=Cin)
+    want = (x[:, ::2, ::2].double().reshape(M, Cin) @ w.double().t() + bias.double()).float()
+    check(D, want, torch.bfloat16)
+
+
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float16])
+def test_tc_residual_epilogues(out_dtype):
+    """epi 4: relu(acc + bias + aux[M][N]) (BasicBlock: out += identity; relu) on a conv3s1 stage; epi 5: relu(acc + bias +
+    up2(aux)) (EfficientFPN fuse conv with its low-resolution half commuted in front of the upsample)"""
+    H, Cin, N, n_img = 32, 128, 128, 3
+    g = torch.Generator(device="cuda").manual_seed(53)
+    x = torch.randn((n_img, H, H, Cin), generator=g, device="cuda").to(out_dtype)
+    w = (torch.randn((N, Cin, 3, 3), generator=g, device="cuda") * (9 * Cin) ** -0.5).to(out_dtype)
+    bias = torch.randn((N,), device="cuda")
+    M = n_img * H * H
+    idn = torch.randn((M, N), generator=g, device="cuda").to(out_dtype)
+    D = torch.full((M, N), float("nan"), device="cuda", dtype=out_dtype)
+    dense(x, w.permute(0, 2, 3, 1).contiguous().reshape(N, 9 * Cin), bias, D, M, N, 9 * Cin, 0, N, amode=2, epi=4, aux=idn,
+          Hin=H, Win=H, Cin=Cin)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), stride=1, padding=1).permute(0, 2, 3, 1).reshape(M, N)
+    check(D, torch.relu(ref + idn.double()).float(), torch.bfloat16)
+    # epi 5 on a 1x1 conv
+    K = 128
+    A = torch.randn((M, K), generator=g, device="cuda").to(out_dtype)
+    W = (torch.randn((N, K), generator=g, device="cuda") * K ** -0.5).to(out_dtype)
+    low = torch.randn((n_img, H // 2, H // 2, N), generator=g, device="cuda").to(out_dtype)
+    D2 = torch.full((M, N), float("nan"), device="cuda", dtype=out_dtype)
+    dense(A, W, bias, D2, M, N, K, K, N, epi=5, aux=low, Hout=H, Wout=H)
+    up = F.interpolate(low.double().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1).reshape(M, N)
+    check(D2, torch.relu(A.double() @ W.double().t() + bias.double() + up).float(), torch.bfloat16)
