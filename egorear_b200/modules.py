@@ -675,9 +675,10 @@ class EgoPoseFormerMVFEX(nn.Module):
                   "camera_model": camera_model, "precision": precision})
         self.pose3d_estimator = EgoPoseFormerPose3D(**p)
         self._chain = True      # hand the heatmap engine's channels-last copies to the pose3d engine
+        self.heatmap_estimator.chain_use_init = bool(self.use_pred_heatmap_init)
 
     def forward_from_feats(self, feat, bfb, coord_trans_mat=None, origin_3d=None):
-        if self._chain:
+        if self._chain and not torch.compiler.is_compiling():
             pd = self.pose3d_estimator.engine().proposal_dtype()
             hp = ("f16_only" if self.use_pred_heatmap_init else "f16") if pd == "f16" else "tf32" if pd == "tf32" else None
             self.heatmap_estimator.engine().export_staged(True, hp=hp)

@@ -144,8 +144,13 @@ def mvfex_forward(module_key: int, feat: Optional[Tensor], bfb: Tensor, heatmap_
                   feat_staged: Optional[Tensor], want_feat_refined: bool, lane: int) -> List[Tensor]:
     """-> [hm_init, hm_refined, feat_refined (numel 0 when not wanted), anchors_2d, anchors_valid]"""
     m = _module(module_key)
-    out = m.engine().forward(feat, bfb, heatmap_for_anchor, want_feat_refined=want_feat_refined, feat_staged=feat_staged,
-                             lane=lane)
+    eng = m.engine()
+    if not want_feat_refined and not getattr(eng, "_export", False):
+        # chained model: keep the channels-last copies for the consumer (the eager pipeline sets this up itself, from the
+        # pose3d engine's actual proposal dtype; here the default fp16 proposal branch of the 16-bit precisions is assumed)
+        use_init = bool(getattr(m, "chain_use_init", True))
+        eng.export_staged(True, hp=(("f16_only" if use_init else "f16") if eng.precision in ("bf16", "fp16") else None))
+    out = eng.forward(feat, bfb, heatmap_for_anchor, want_feat_refined=want_feat_refined, feat_staged=feat_staged, lane=lane)
     _STAGED[int(module_key)] = out.get("staged")
     fr = out["feat_refined"]
     if fr is None:

@@ -16,6 +16,7 @@ class Chain(torch.nn.Module):
         super().__init__()
         self.h = build_mvfex(4, precision)
         self.p = build_pose3d("ego4view_syn", precision)
+        self.h.chain_use_init = self.p.use_pred_heatmap_init        # what EgoPoseFormerMVFEX.__init__ records for the hand-over
 
     def forward(self, feat, bfb):
         from egorear_b200 import ops

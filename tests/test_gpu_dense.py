@@ -303,7 +303,7 @@ def test_tc_tf32x3(M, N, K, groups):
     plain = torch.einsum("gmk,gnk->gmn", tf32_rna(X).double(), w_hi.double()).float()
     err_plain = float((plain - want).abs().max() / want.abs().max())
     print("3xTF32 rel err %.2e (plain TF32: %.2e)" % (err, err_plain))
-    assert err < 5e-6 and err < 0.05 * err_plain
+    assert err < 2e-5 and err < 0.05 * err_plain
 
 
 @pytest.mark.parametrize("H,Cin,N,n_img,groups", [(64, 64, 64, 3, 1), (32, 128, 128, 4, 2), (16, 256, 256, 8, 1), (8, 512, 512, 6, 2),
