@@ -44,6 +44,13 @@ STAGE_FLOPS = {
     "H2c": 4 * 2 * 1024 * 128 * 256,
     "P2a": 4 * 2 * 4096 * 64 * 128, "P2b": 4 * 2 * 1024 * 128 * 576, "P2c": 4 * 2 * 256 * 64 * 128,
     "P2d": 4 * 2 * 64 * 128 * 576, "P2mlp0": 2 * 2048 * 32768,
+    # backbone engine, per 4-view frame: ResNet18 stages + EfficientFPN (26.7 GFLOP in total)
+    "B_stem": 4 * 2 * 16384 * 64 * 147,
+    "B_layer1": 4 * (4 * 2 * 4096 * 64 * 576 + 2 * 4096 * 128 * 64),
+    "B_layer2": 4 * (2 * 1024 * 128 * 576 + 2 * 1024 * 128 * 64 + 3 * 2 * 1024 * 128 * 1152 + 2 * 1024 * 128 * 128),
+    "B_layer3": 4 * (2 * 256 * 256 * 1152 + 2 * 256 * 256 * 128 + 3 * 2 * 256 * 256 * 2304 + 2 * 256 * 128 * 256),
+    "B_layer4": 4 * (2 * 64 * 512 * 2304 + 2 * 64 * 512 * 256 + 3 * 2 * 64 * 512 * 4608 + 2 * 64 * 128 * 512),
+    "B_fpn": 4 * sum(2 * (r // 2) ** 2 * 128 * 128 + 2 * r * r * 128 * 128 + 2 * r * r * 128 * 1152 for r in (16, 32, 64)),
 }
 # algorithmic HBM bytes per 4-view frame of every stage (act = bytes per activation element: 2 in bf16 mode; the pose3d
 # proposal branch P2* keeps fp32/TF32 activations; weights are counted once per batch for the one stage where they
@@ -76,6 +83,14 @@ STAGE_BYTES = {
     "P2c": lambda act, exp, B: 4 * 256 * (128 + 64) * P2ACT[0],
     "P2d": lambda act, exp, B: 4 * (256 * 64 + 64 * 128) * P2ACT[0],
     "P2mlp0": lambda act, exp, B: 2048 * 32768 * P2ACT[0] // B + 4 * 64 * 128 * P2ACT[0],
+    # backbone stages: what their kernels must move at least (every conv reads its input and writes its output once, residual
+    # branches are read once; the stem reads the fp32 image and writes the pooled map)
+    "B_stem": lambda act, exp, B: 4 * (3 * 256 * 256 * 4 + 64 * 64 * 64 * act),
+    "B_layer1": lambda act, exp, B: 4 * 4096 * 64 * act * 10 + 4 * 4096 * (64 + 128) * act,
+    "B_layer2": lambda act, exp, B: 4 * (4096 * 64 * act * 2 + 1024 * 128 * act * 10) + 4 * 1024 * 256 * act,
+    "B_layer3": lambda act, exp, B: 4 * (1024 * 128 * act * 2 + 256 * 256 * act * 10) + 4 * 256 * 384 * act,
+    "B_layer4": lambda act, exp, B: 4 * (256 * 256 * act * 2 + 64 * 512 * act * 10) + 4 * 64 * 640 * act,
+    "B_fpn": lambda act, exp, B: 4 * sum((r // 2) ** 2 * 256 + r * r * 128 * 4 for r in (16, 32, 64)) * act,
 }
 P2ACT = [4]      # bytes per element of the pose3d proposal branch: 4 (fp32 / TF32) or 2 (fp16, the bf16-mode default); set in main()
 TF32_STAGES = ("P2a", "P2b", "P2c", "P2d", "P2mlp0")     # kind::tf32: half the bf16 tensor rate (nominal ratio)
@@ -554,6 +569,7 @@ def main():
     elif args.workload == "rw_e2e":
         # BASELINE config 5: images -> backbone (PyTorch) -> hot path (rw cameras, per-frame device->camera transforms)
         pipe = HotPathPipeline(4, "ego4view_rw", args.precision, dev, with_backbone=True, materialize_features=False)
+        P2ACT[0] = 2 if pipe.pose3d.engine().proposal_dtype() == "f16" else 4
         g = torch.Generator().manual_seed(rank)
         img_h = torch.randn(B, 4, 3, 256, 256, generator=g).pin_memory()
         ctm_h = synth.synth_coord_trans_mat(B, seed=rank).pin_memory()
@@ -770,8 +786,8 @@ def main():
 
     # ---- per-stage timing of the same step through the library's stage profiler (rank 0) ----
     roofline, stages, stage_fracs = None, None, None
-    n_prof = 5
-    if args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
+    n_prof = 5 if args.workload != "rw_e2e" else 2
+    if args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e"):
         # every rank runs the profiled steps (the step ends in the all-gather); only rank 0 records stage events
         if rank == 0:
             lib.egr_profile_enable(1)
@@ -779,7 +795,7 @@ def main():
             step_prof()
         torch.cuda.synchronize(dev)
         egd.barrier()
-    if rank == 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d"):
+    if rank == 0 and args.workload in ("mvfex_pose3d", "mvfex", "pose3d", "rw_e2e"):
         import ctypes
         buf = ctypes.create_string_buffer(1 << 16)
         _lib.check(lib.egr_profile_read(buf, len(buf)))
@@ -791,7 +807,7 @@ def main():
                 stages[name] = float(tot) / n_prof           # ms per step
         total = sum(stages.values())
         # HotPathPipeline exports the staged copies (1); the chained workload does not materialise the NCHW features (2)
-        exp = 2 if args.workload == "mvfex_pose3d" else 1 if args.workload == "mvfex" else 0
+        exp = 2 if args.workload in ("mvfex_pose3d", "rw_e2e") else 1 if args.workload == "mvfex" else 0
         per_stage = {k: stage_roofline(k, v, B, act, exp, peaks) for k, v in stages.items()}
         # the roofline line is for the dominant kernel that HAS a roofline (the token phases are chains of ~15-45
         # latency-bound launches, reported in stages_ms)

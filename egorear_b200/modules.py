@@ -257,7 +257,11 @@ class MSDeformAttn(nn.Module):
             loc = reference_points[:, :, None, :, None, :2] + off / self.n_points * reference_points[:, :, None, :, None, 2:] * 0.5
         else:
             raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
-        out = ops.ms_deform_attn(value.to(torch.float32), input_spatial_shapes, input_level_start_index, loc, aw, self.im2col_step)
+        if torch.is_grad_enabled() and (value.requires_grad or loc.requires_grad or aw.requires_grad):
+            from .train import MultiScaleDeformableAttnFunction as _TrainMSDA     # forward + backward kernels (run.py fit)
+            out = _TrainMSDA.apply(value.to(torch.float32), input_spatial_shapes, input_level_start_index, loc, aw, self.im2col_step)
+        else:
+            out = ops.ms_deform_attn(value.to(torch.float32), input_spatial_shapes, input_level_start_index, loc, aw, self.im2col_step)
         out = self.output_proj(out)
         return (out, loc) if return_sampled_points else out
 

@@ -119,6 +119,21 @@ int egr_decode_argmax(const float* hm, int64_t N, int J, int H, int W, float thr
 int egr_msda_forward(const float* value, int B, int H, int W, int nh, int hd, const float* loc,
                      const float* aw, int Q, int P, float* out, void* stream);
 
+/* Training side.  Backward of the op above: grad_value [B, H*W, nh, hd] (zeroed by the call, atomic
+ * scatter), grad_loc [B, Q, nh, 1, P, 2], grad_aw [B, Q, nh, 1, P], all f32, from grad_out [B, Q, nh*hd] - the three
+ * gradients mmcv's MultiScaleDeformableAttnFunction.backward returns. */
+int egr_msda_backward(const float* value, int B, int H, int W, int nh, int hd, const float* loc, const float* aw,
+                      int Q, int P, const float* grad_out, float* grad_value, float* grad_loc, float* grad_aw, void* stream);
+/* nn.MSELoss(reduction="mean") (pl_wrappers/egoposeformer/heatmap_mvf_ex.py:258-261) and MpjpeLoss
+ * (models/utils/pose_metric.py:10-16: mean over joints of ||gt - pred||_2; D = 3 coordinates per joint), forward into a
+ * device scalar + backward; workspace = egr_loss_workspace_bytes() device bytes; deterministic reductions. */
+int64_t egr_loss_workspace_bytes(void);
+int egr_mse_loss_forward(const float* pred, const float* target, int64_t n, float* loss, void* workspace, void* stream);
+int egr_mse_loss_backward(const float* pred, const float* target, const float* grad_loss, int64_t n, float* grad_pred, void* stream);
+int egr_mpjpe_loss_forward(const float* pred, const float* gt, int64_t n_joints, int D, float* loss, void* workspace, void* stream);
+int egr_mpjpe_loss_backward(const float* pred, const float* gt, const float* grad_loss, int64_t n_joints, int D, float* grad_pred,
+                            void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * P3  fisheye reprojection     replaces EgoPoseFormerPose3D._reproject_3d_to_2d
  *     (estimator/egoposeformer_mvf_ex.py:340-382) + FishEyeCameraCalibratedModel.world2camera_pytorch
