@@ -101,6 +101,53 @@ maxpool3s2_kernel(const T16* __restrict__ in, T16* __restrict__ out, int64_t n_i
     }
 }
 
+template <typename T16> __device__ __forceinline__ float2 bb_unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 bb_unpack2<__nv_bfloat16>(uint32_t w) {
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 bb_unpack2<__half>(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+template <typename T16> __device__ __forceinline__ uint32_t bb_pack2_relu(float lo, float hi) {
+    return bb_pack2<T16>(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+}
+
+// thread = (output pixel, 8 channels): 16-byte accesses, consecutive lanes = consecutive channel groups of a pixel row
+template <typename T16>
+__global__ void __launch_bounds__(256)
+up2_add_relu_kernel(const T16* __restrict__ hi, const T16* __restrict__ low, T16* __restrict__ out, int64_t n_img, int R, int C) {
+    pdl_trigger();
+    pdl_wait();
+    const int CV = C >> 3, Rs = R >> 1;
+    const int64_t total = n_img * R * R * CV;
+    const float scale = (float)(Rs - 1) / (float)(R - 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        int64_t r = i / CV;
+        const int x = (int)(r % R); r /= R;
+        const int y = (int)(r % R);
+        const int64_t im = r / R;
+        const float sy = scale * (float)y, sx = scale * (float)x;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < Rs - 1 ? 1 : 0), x1 = x0 + (x0 < Rs - 1 ? 1 : 0);
+        const float ly1 = sy - (float)y0, lx1 = sx - (float)x0, ly0 = 1.f - ly1, lx0 = 1.f - lx1;
+        const uint4* lb = reinterpret_cast<const uint4*>(low + im * (int64_t)Rs * Rs * C) + cv;
+        const uint4 a = __ldg(lb + ((int64_t)y0 * Rs + x0) * CV), b = __ldg(lb + ((int64_t)y0 * Rs + x1) * CV);
+        const uint4 c = __ldg(lb + ((int64_t)y1 * Rs + x0) * CV), d = __ldg(lb + ((int64_t)y1 * Rs + x1) * CV);
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi) + i);
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w}, cvv[4] = {c.x, c.y, c.z, c.w},
+                       dv[4] = {d.x, d.y, d.z, d.w}, hv[4] = {h.x, h.y, h.z, h.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 fa = bb_unpack2<T16>(av[e]), fb = bb_unpack2<T16>(bv[e]), fc = bb_unpack2<T16>(cvv[e]), fd = bb_unpack2<T16>(dv[e]);
+            const float2 fh = bb_unpack2<T16>(hv[e]);
+            const float u0 = ly0 * (lx0 * fa.x + lx1 * fb.x) + ly1 * (lx0 * fc.x + lx1 * fd.x);
+            const float u1 = ly0 * (lx0 * fa.y + lx1 * fb.y) + ly1 * (lx0 * fc.y + lx1 * fd.y);
+            o[e] = bb_pack2_relu<T16>(fh.x + u0, fh.y + u1);
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 template <typename T16>
 __global__ void __launch_bounds__(256)
 bottom_to_nchw_kernel(const T16* __restrict__ in, float* __restrict__ out, int B, int V, int HW, int C) {
@@ -164,6 +211,15 @@ int maxpool3s2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int
     const int64_t total = n_img * (H / 2) * (W / 2) * (C / 8);
     if (dt == 2) EGR_LAUNCH(maxpool3s2_kernel<__half>, grid_for(total), 256, 0, st, (const __half*)in, (__half*)out, n_img, H, W, C);
     else EGR_LAUNCH(maxpool3s2_kernel<__nv_bfloat16>, grid_for(total), 256, 0, st, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, n_img, H, W, C);
+    return EGR_OK;
+}
+
+int up2_add_relu_nhwc(const void* hi, const void* low, void* out, int dt, int64_t n_img, int R, int C, cudaStream_t st) {
+    EGR_CHECK(C % 8 == 0 && R % 2 == 0 && (dt == 1 || dt == 2), EGR_ERR_UNSUPPORTED, "up2_add_relu: C=%d R=%d dt=%d", C, R, dt);
+    const int64_t total = n_img * R * R * (C / 8);
+    if (dt == 2) EGR_LAUNCH(up2_add_relu_kernel<__half>, grid_for(total), 256, 0, st, (const __half*)hi, (const __half*)low, (__half*)out, n_img, R, C);
+    else EGR_LAUNCH(up2_add_relu_kernel<__nv_bfloat16>, grid_for(total), 256, 0, st, (const __nv_bfloat16*)hi, (const __nv_bfloat16*)low,
+                    (__nv_bfloat16*)out, n_img, R, C);
     return EGR_OK;
 }
 

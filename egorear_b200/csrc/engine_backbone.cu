@@ -15,6 +15,10 @@
 #include "engine_common.cuh"
 #include "backbone_ops.cuh"
 
+namespace egr {
+int g_opt_stem_fused = 1;      // option "stem_fused": 0 = im2col buffer + plain GEMM (the first version, kept as a cross-check)
+int g_opt_fpn_epi = 0;         // option "fpn_epi": 1 = FPN fuse conv with the upsample-add gathered in its epilogue (slower, see forward)
+}
 using namespace egr;
 
 static const char* kEnc[2] = {"heatmap_estimator_stereo_front.encoder.", "heatmap_estimator_stereo_back.encoder."};
@@ -106,7 +110,7 @@ int64_t bb_carve(const egr_backbone* h, int B, void* base, int64_t cap, BbBufs* 
     const int64_t VB = (int64_t)h->V * B, e = 2;
     Carver c(base, cap);
     BbBufs b{};
-    b.col = c.take(VB * 128 * 128 * STEM_K * e);
+    b.col = g_opt_stem_fused ? nullptr : c.take(VB * 128 * 128 * STEM_K * e);
     b.s2 = c.take(VB * 128 * 128 * 64 * e);
     for (int l = 0; l < 4; ++l) {
         const int64_t n = VB * kRes[l] * kRes[l] * kCh[l] * e;
@@ -217,11 +221,18 @@ extern "C" int egr_backbone_forward(egr_backbone* h, int B, const float* img, vo
         else { d.Hin = Hin; d.Win = Hin; d.Cin = Cin; d.a_gs = IMGS * Hin * Hin * Cin; }
         if (epi == EPI_ADD_RELU) d.aux_gs = M * W.N;
         if (epi == EPI_ADDUP_RELU) { d.Hout = Hout; d.Wout = Hout; d.aux_gs = IMGS * (Hout / 2) * (Hout / 2) * W.N; }
+        d.ws = 1;       // weight-stationary wherever the slab fits beside >= 4 A stages (layer1's N = 64 convs, the 1x1 convs)
         return run_gemm(d, W, 0, prec, false, st);
     };
     EGR_MARK("B_stem", st);
-    if ((rc = stem_im2col(img, w.col, dt, B, V, IMG, IMG, st))) return rc;
-    if ((rc = conv(w.col, A_PLAIN, 0, STEM_K, h->stem, w.s2, EPI_RELU, nullptr, 128))) return rc;
+    if (g_opt_stem_fused && (int64_t)V * B <= 65535) {
+        // one tensor-core kernel: im2col rows are built in shared memory (stem_tc.cu)
+        const void* w16 = (prec == EGR_PREC_FP16) ? (const void*)h->stem.f16 : (const void*)h->stem.bf16;
+        if ((rc = stem_tc(img, w16, h->stem.bias, dt, B, V, vpg, w.s2, st))) return rc;
+    } else {
+        if ((rc = stem_im2col(img, w.col, dt, B, V, IMG, IMG, st))) return rc;
+        if ((rc = conv(w.col, A_PLAIN, 0, STEM_K, h->stem, w.s2, EPI_RELU, nullptr, 128))) return rc;
+    }
     if ((rc = maxpool3s2_nhwc(w.s2, w.x[0], dt, (int64_t)V * B, 128, 128, 64, st))) return rc;
     const void* x = w.x[0];       // input of the current layer
     for (int l = 0; l < 4; ++l) {
@@ -254,7 +265,14 @@ extern "C" int egr_backbone_forward(egr_backbone* h, int B, const float* img, vo
         const int R = kRes[i];
         // low-resolution half of the fuse conv, BEFORE the upsample (no bias, no activation)
         if ((rc = conv(top, A_PLAIN, 0, 128, h->fuse_lo[i], w.low[i], EPI_NONE, nullptr, kRes[i + 1]))) return rc;
-        if ((rc = conv(w.lat[i], A_PLAIN, 0, 128, h->fuse_hi[i], w.f[i], EPI_ADDUP_RELU, w.low[i], R))) return rc;
+        if (g_opt_fpn_epi) {
+            // one kernel: the upsampled half is gathered in the GEMM epilogue (row-per-lane gathers: L1-wavefront bound, measured
+            // 1.02 ms at 64^2 for 128 frames vs 0.27 + 0.2 ms for the two-kernel form below)
+            if ((rc = conv(w.lat[i], A_PLAIN, 0, 128, h->fuse_hi[i], w.f[i], EPI_ADDUP_RELU, w.low[i], R))) return rc;
+        } else {
+            if ((rc = conv(w.lat[i], A_PLAIN, 0, 128, h->fuse_hi[i], w.f[i], EPI_NONE, nullptr, R))) return rc;
+            if ((rc = up2_add_relu_nhwc(w.f[i], w.low[i], w.f[i], dt, (int64_t)V * B, R, 128, st))) return rc;
+        }
         void* out = (i == 2) ? w.g[0] : (i == 1) ? w.g[1] : feat_staged;      // level 0 IS the staged input of the hot path
         if ((rc = conv(w.f[i], A_CONV3S1, R, 128, h->fpn[i], out, EPI_RELU, nullptr, R))) return rc;
         top = out;

@@ -17,6 +17,8 @@ int g_opt_tok3x = 1;
 extern int g_opt_pose_p2_bf16;
 extern int g_opt_pose_p2_fp16;
 extern int g_opt_ws;
+extern int g_opt_stem_fused;
+extern int g_opt_fpn_epi;
 }
 using namespace egr;
 
@@ -491,6 +493,8 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "tok_batched") { g_opt_tok_batched = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "wsplit") { g_opt_wsplit = value < 0 ? 0 : value > 2 ? 2 : value; return EGR_OK; }
     if (key && std::string(key) == "tok3x") { g_opt_tok3x = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "stem_fused") { g_opt_stem_fused = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "fpn_epi") { g_opt_fpn_epi = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }
 

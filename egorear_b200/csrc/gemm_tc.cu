@@ -731,8 +731,9 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     {
         const int64_t w_bytes = (int64_t)p.kb_total * bn * ROW_BYTES;
         const int64_t a_stages = (SMEM_RING - w_bytes) / (BM * ROW_BYTES);
-        if (g_opt_ws && d.ka == 0 && d.amode == A_PLAIN && p.kblk == d.K && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
-            total >= 2 * (int64_t)grid) {
+        const bool ws_ok = d.ka == 0 && (d.amode != A_PLAIN || p.kblk == d.K) && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
+                           total >= 2 * (int64_t)grid;
+        if (ws_ok && (d.ws || (g_opt_ws && d.amode == A_PLAIN))) {
             p.ws = 1;
             p.ws_stages = (int)(a_stages < MAX_STAGES ? a_stages : MAX_STAGES);
         }

@@ -76,3 +76,25 @@ def test_model_forward_with_backbone_engine_matches_torch_backbone():
         lh_e, lf_e = m(img)
     assert lf_e[0] is None and lf_t[0] is not None
     assert rel(lh_e[0], lh_t[0]) < 3e-2 and rel(lh_e[1], lh_t[1]) < 3e-2
+
+
+def test_stem_variants_agree():
+    """the fused tensor-core stem (im2col rows built in shared memory) vs the im2col-buffer + plain-GEMM form, and the FPN
+    fuse step as GEMM + coalesced kernel vs gathered in the GEMM epilogue: same weights, same 16-bit rounding points"""
+    from egorear_b200 import engine
+    m = build("bf16")
+    img = torch.randn((2, 4, 3, 256, 256), generator=torch.Generator().manual_seed(8)).cuda()
+    with torch.no_grad():
+        base, bfb0 = m.forward_backbone_staged(img)
+        try:
+            engine.set_option("stem_fused", 0)
+            a, bfb1 = m.forward_backbone_staged(img)
+        finally:
+            engine.set_option("stem_fused", 1)
+        try:
+            engine.set_option("fpn_epi", 1)
+            b, _ = m.forward_backbone_staged(img)
+        finally:
+            engine.set_option("fpn_epi", 0)
+    assert rel(a.float(), base.float()) < 5e-3 and rel(bfb1, bfb0) < 5e-3       # summation order inside the k-blocks only
+    assert rel(b.float(), base.float()) < 1e-2                                   # one 16-bit rounding of the pre-activation more / less
