@@ -75,7 +75,31 @@ def main():
     ap.add_argument("--plain-ms", type=float, default=None)
     ap.add_argument("--note", default="")
     ap.add_argument("--rep", action="append", default=[])
+    ap.add_argument("--traffic-json", default=None,
+                    help="also write {stage: dram bytes per launch} of the --rep captures (name = bench.py stage name) to this file; "
+                         "bench.py reads profiles/ncu_traffic.json for roofline.traffic")
     a = ap.parse_args()
+    if a.traffic_json:
+        import json
+        import os
+        stages = {}
+        for spec in a.rep:
+            name, path = spec.split("=", 1)
+            ms = rep_metrics(path)
+            if not ms:
+                continue
+            d = ms[0]
+
+            def num(k):
+                v, u = d.get(k, ("0", ""))
+                x = float(v.replace(",", ""))
+                return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0)
+            dur, du = d.get("gpu__time_duration.sum", ("0", "us"))
+            dur = float(dur.replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(du, 1.0)
+            stages[name] = {"kernel": short(d["Kernel Name"], 120), "dram_read_bytes": int(num("dram__bytes_read.sum")),
+                            "dram_write_bytes": int(num("dram__bytes_write.sum")), "duration_us_under_ncu": dur,
+                            "file": os.path.basename(path)}
+        json.dump({"source": a.title, "stages": stages}, open(a.traffic_json, "w"), indent=1)
     L = launches(a.launches)
     tot = sum(x[3] for x in L)
     print("# %s\n" % a.title)
