@@ -25,6 +25,7 @@
 namespace egr {
 using namespace tcx;
 int g_opt_ws = 0;      // weight-stationary mode of gemm_tc (option "ws"): measured no gain on B200, off by default
+int g_opt_conv_prefetch = 1;   // option "conv_prefetch": L2 prefetch of the next tile's input rows in the 3x3 stride-1 conv
 namespace {
 
 constexpr int BM = 128;
@@ -55,6 +56,7 @@ struct TcParams {
     int ka;                   // A's own K: k >= ka re-reads A at k - ka (split weights [W_hi | W_lo]); == K otherwise
     int Cin, Wout, HWout;     // A_CONV3S2 / A_CONV3S1 (output geometry; == input geometry for the stride-1 conv)
     int tap_fixed;            // A_CONV3S2 with K == Cin: the centre tap only (1x1 stride-2 conv); -1 otherwise
+    int pf_rows;              // A_CONV3S1: rows per TMA box when the NEXT tile of this CTA is prefetched into L2 (0 = off)
     int epi;
     int round_out;            // fp32 output rounded to the nearest TF32 value
     int partial;              // split-K: raw fp32 partial sums to D + ks * part_stride, no bias / activation
@@ -347,6 +349,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const long long gm0 = (long long)tc.g * p.M + (long long)tc.mt * BM;
                     img0 = (int)(gm0 / p.HWout);
                     oy0 = (int)(gm0 % p.HWout) / p.Wout;
+                }
+                if (p.pf_rows > 0 && tc.nt == 0 && tc.ks == 0) {
+                    // 3x3 stride-1 conv streaming its input from HBM: a tile's 9 taps are 9 boxes over the same (bh + 2) input rows,
+                    // first touched ~one ring depth (< 1 tile) before they are needed - too late to hide a DRAM miss (ncu: tensor
+                    // pipe 18 %, DRAM 15 %, L2 24 %: nothing busy).  Warm L2 with the rows of this CTA's NEXT tile now.
+                    const int tn = t + gridDim.x;
+                    if (tn < total_tiles) {
+                        const TileCoord nc = decode_tile(tn, p);
+                        const long long gm = (long long)nc.g * p.M + (long long)nc.mt * BM;
+                        const int nimg = (int)(gm / p.HWout), noy = (int)(gm % p.HWout) / p.Wout;
+                        for (int ci = 0; ci < p.Cin; ci += BK) {
+                            tma_prefetch_4d(&tmA, ci, 0, noy - 1, nimg);
+                            tma_prefetch_4d(&tmA, ci, 0, noy - 1 + p.pf_rows, nimg);
+                        }
+                    }
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -677,6 +694,7 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
         const int bh = (HW >= BM) ? BM / W : H;
         const int bimg = (HW >= BM) ? 1 : BM / HW;
         p.Cin = d.Cin; p.Wout = W; p.HWout = HW; p.tap_fixed = -1;
+        p.pf_rows = (g_opt_conv_prefetch && HW >= BM && bh >= 2) ? bh : 0;
         const int64_t n_img = (int64_t)d.groups * (d.M / HW);
         const cuuint64_t dims[4] = {(cuuint64_t)d.Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_img};
         const cuuint64_t str[3] = {(cuuint64_t)d.Cin * ES, (cuuint64_t)W * d.Cin * ES, (cuuint64_t)H * W * d.Cin * ES};
