@@ -1,7 +1,7 @@
 """egorear_b200 — B200-native (sm_100a) hot path of EgoRear behind the reference's module interfaces.
 
     import egorear_b200
-    egorear_b200.patch(precision="bf16")      # swap the hot path under an imported EgoRear checkout
+    egorear_b200.patch(precision="fp16")      # swap the hot path under an imported EgoRear checkout
 
 Everything computes through egorear_b200/libegorear_b200.so (C-ABI, include/egorear_b200.h); there is no CPU fallback.
 """

@@ -25,7 +25,10 @@
 namespace egr {
 using namespace tcx;
 int g_opt_ws = 0;      // weight-stationary mode of gemm_tc (option "ws"): measured no gain on B200, off by default
-int g_opt_conv_prefetch = 1;   // option "conv_prefetch": L2 prefetch of the next tile's input rows in the 3x3 stride-1 conv
+// option "conv_prefetch": L2 prefetch (cp.async.bulk.prefetch.tensor) of the next tile's input rows in the 3x3 stride-1 conv.
+// Measured on the backbone at 512 frames: layer1 7.18 -> 8.10 ms, FPN 7.34 -> 7.63 ms: the convs are not waiting on DRAM
+// misses (what bounds them is the 9x re-read of the input through L2 -> shared memory), so it is off by default.
+int g_opt_conv_prefetch = 0;
 namespace {
 
 constexpr int BM = 128;
@@ -351,9 +354,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     oy0 = (int)(gm0 % p.HWout) / p.Wout;
                 }
                 if (p.pf_rows > 0 && tc.nt == 0 && tc.ks == 0) {
-                    // 3x3 stride-1 conv streaming its input from HBM: a tile's 9 taps are 9 boxes over the same (bh + 2) input rows,
-                    // first touched ~one ring depth (< 1 tile) before they are needed - too late to hide a DRAM miss (ncu: tensor
-                    // pipe 18 %, DRAM 15 %, L2 24 %: nothing busy).  Warm L2 with the rows of this CTA's NEXT tile now.
+                    // experiment (off by default, see g_opt_conv_prefetch): warm L2 with the input rows of this CTA's NEXT tile
                     const int tn = t + gridDim.x;
                     if (tn < total_tiles) {
                         const TileCoord nc = decode_tile(tn, p);

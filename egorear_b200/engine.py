@@ -121,7 +121,7 @@ class MvfexEngine(_EngineBase):
     """Everything EgoPoseFormerHeatmapMVFEX.forward does after the backbones."""
     _prefix = "mvfex"
 
-    def __init__(self, num_views=4, num_heatmap=15, heatmap_threshold=0.5, precision="bf16"):
+    def __init__(self, num_views=4, num_heatmap=15, heatmap_threshold=0.5, precision="fp16"):
         super().__init__()
         self.V, self.J, self.precision = num_views, num_heatmap, precision
         _lib.check(self._lib.egr_mvfex_create(num_views, num_heatmap, float(heatmap_threshold), PREC[precision],
@@ -209,7 +209,7 @@ class BackboneEngine(_EngineBase):
     16-bit channels-last FPN map + the fp32 stride-32 map out (egr_backbone_*)."""
     _prefix = "backbone"
 
-    def __init__(self, num_views=4, precision="bf16"):
+    def __init__(self, num_views=4, precision="fp16"):
         super().__init__()
         if precision not in ACT_DTYPE:
             raise RuntimeError("egorear_b200: the backbone engine runs in the tensor-core precisions (bf16 / fp16); fp32 keeps the PyTorch backbone")
@@ -236,7 +236,7 @@ class Pose3DEngine(_EngineBase):
     _prefix = "pose3d"
 
     def __init__(self, num_views=4, num_joints=16, num_layers=3, camera_model="ego4view_syn", use_pred_heatmap_init=True,
-                 precision="bf16", calib=None):
+                 precision="fp16", calib=None):
         super().__init__()
         if camera_model not in CAMERA_MODEL_ID:
             raise ValueError('Unknown camera model !')

@@ -412,7 +412,7 @@ class HeatmapMVF(_EngineOwner, nn.Module):
     def __init__(self, input_dims, embed_dims, num_former_layers, image_size, feat_down_stride, detach_heatmap_feat,
                  mvf_transformer_cfg, heatmap_threshold, num_views, num_heatmap, joint_query_adaptation=False,
                  joint_query_adaptation_multi_view=False, joint_query_only=False, use_1by1_conv=False,
-                 precision="bf16"):
+                 precision="fp16"):
         super().__init__()
         if not joint_query_adaptation or joint_query_adaptation_multi_view or joint_query_only or use_1by1_conv:
             raise NotImplementedError("egorear_b200: only the shipped jqa configuration (joint_query_adaptation=True, "
@@ -469,7 +469,7 @@ class HeatmapMVF(_EngineOwner, nn.Module):
 class EgoPoseFormerHeatmapMVFEX(_EngineOwner, nn.Module):
     def __init__(self, num_views, image_size, num_heatmap, feat_down_stride, heatmap_threshold, encoder_cfg, mvf_cfg,
                  camera_model, full_training=False, detach_heatmap_feat=False, detach_heatmap_feat_init=False,
-                 use_pred_heatmap_init=False, no_detach_feat_init=False, precision="bf16", build_backbone=True,
+                 use_pred_heatmap_init=False, no_detach_feat_init=False, precision="fp16", build_backbone=True,
                  backbone_impl="torch", **kwargs):
         """backbone_impl (not in the reference): "torch" = the PyTorch ResNet18+FPN modules run as in the reference (the
         features exist as NCHW fp32 tensors and are returned in list_frame_feat[0]); "egr" = the backbone engine
@@ -604,7 +604,7 @@ class EgoPoseFormerPose3D(_EngineOwner, nn.Module):
     def __init__(self, num_views, image_size, use_pred_heatmap_init, num_joints, input_dims, embed_dims, mlp_dims,
                  mlp_dropout, num_mlp_layers, transformer_cfg, num_former_layers, num_pred_mlp_layers, camera_model,
                  feat_down_stride, coor_norm_max, coor_norm_min, conv_heatmap_dim_init, norm_mlp_pred=False,
-                 use_mlp_avgpool=True, use_mlp_heatmap=False, camera_calib_file_dir_path=None, precision="bf16", **kwargs):
+                 use_mlp_avgpool=True, use_mlp_heatmap=False, camera_calib_file_dir_path=None, precision="fp16", **kwargs):
         super().__init__()
         if use_mlp_avgpool or use_mlp_heatmap:
             raise NotImplementedError("egorear_b200: only the conv-MLP proposal branch (use_mlp_avgpool=False, "
@@ -668,7 +668,7 @@ class EgoPoseFormerPose3D(_EngineOwner, nn.Module):
 
 
 class EgoPoseFormerMVFEX(nn.Module):
-    def __init__(self, num_views, image_size, camera_model, heatmap_mvf_cfg, pose3d_cfg, precision="bf16", **kwargs):
+    def __init__(self, num_views, image_size, camera_model, heatmap_mvf_cfg, pose3d_cfg, precision="fp16", **kwargs):
         super().__init__()
         h = dict(heatmap_mvf_cfg)
         h.update({"num_views": num_views, "image_size": image_size, "camera_model": camera_model, "precision": precision})

@@ -13,7 +13,7 @@ from .modules import EgoPoseFormerHeatmapMVFEX, EgoPoseFormerPose3D
 
 
 class HotPathPipeline:
-    def __init__(self, num_views=4, camera_model="ego4view_syn", precision="bf16", device="cuda", synthetic_weights=True,
+    def __init__(self, num_views=4, camera_model="ego4view_syn", precision="fp16", device="cuda", synthetic_weights=True,
                  with_backbone=False, materialize_features=True, backbone_impl="egr"):
         """backbone_impl: "egr" = the backbone engine (tcgen05 conv stages) behind backbone_staged(); "torch" = the PyTorch
         modules under autocast (round 1)"""

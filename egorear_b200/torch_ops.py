@@ -191,7 +191,7 @@ def backbone_forward(module_key: int, img: Tensor, lane: int) -> Tuple[Tensor, T
 def _(module_key, img, lane):
     B, V = img.shape[:2]
     m = _MODULES.get(int(module_key))
-    dt = torch.float16 if (m is not None and getattr(m, "_precision", "bf16") == "fp16") else torch.bfloat16
+    dt = torch.float16 if (m is not None and getattr(m, "_precision", "fp16") != "bf16") else torch.bfloat16
     return img.new_empty((V, B, 64, 64, 128), dtype=dt), img.new_empty((B, V, 512, 8, 8), dtype=torch.float32)
 
 
