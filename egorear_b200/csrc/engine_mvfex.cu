@@ -20,6 +20,7 @@ extern int g_opt_ws;
 extern int g_opt_stem_fused;
 extern int g_opt_fpn_epi;
 extern int g_opt_conv_prefetch;
+extern int g_opt_pair;
 }
 using namespace egr;
 
@@ -497,6 +498,7 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "stem_fused") { g_opt_stem_fused = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "fpn_epi") { g_opt_fpn_epi = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "conv_prefetch") { g_opt_conv_prefetch = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "pair") { g_opt_pair = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }
 

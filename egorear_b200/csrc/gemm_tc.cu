@@ -29,6 +29,7 @@ int g_opt_ws = 0;      // weight-stationary mode of gemm_tc (option "ws"): measu
 // Measured on the backbone at 512 frames: layer1 7.18 -> 8.10 ms, FPN 7.34 -> 7.63 ms: the convs are not waiting on DRAM
 // misses (what bounds them is the 9x re-read of the input through L2 -> shared memory), so it is off by default.
 int g_opt_conv_prefetch = 0;
+int g_opt_pair = 1;            // option "pair": split weights as [A | W_hi | W_lo] ring stages (BN <= 128) instead of the K wrap
 namespace {
 
 constexpr int BM = 128;
@@ -60,6 +61,9 @@ struct TcParams {
     int Cin, Wout, HWout;     // A_CONV3S2 / A_CONV3S1 (output geometry; == input geometry for the stride-1 conv)
     int tap_fixed;            // A_CONV3S2 with K == Cin: the centre tap only (1x1 stride-2 conv); -1 otherwise
     int pf_rows;              // A_CONV3S1: rows per TMA box when the NEXT tile of this CTA is prefetched into L2 (0 = off)
+    // split weights, paired form (K == 2*ka, BN <= 128): a ring stage holds [A | W_hi | W_lo] of one k-block, the k loop runs
+    // over ka only and every A tile is multiplied by both weight tiles - A crosses L2 -> shared memory once instead of twice
+    int pair, pair_stages, k_lo;
     int epi;
     int round_out;            // fp32 output rounded to the nearest TF32 value
     int partial;              // split-K: raw fp32 partial sums to D + ks * part_stride, no bias / activation
@@ -303,9 +307,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * MAX_STAGES;
     const uint32_t tfull0 = empty0 + 8 * MAX_STAGES, tempty0 = tfull0 + 16;
     const uint32_t wfull = tempty0 + 16, wempty = wfull + 8;
-    const int n_stages = p.ws ? p.ws_stages : C::STAGES;
+    const int n_stages = p.ws ? p.ws_stages : p.pair ? p.pair_stages : C::STAGES;
     const uint32_t w_bytes = p.ws ? (uint32_t)p.kb_total * C::STAGE_B : 0u;      // resident weight slab in front of the ring
-    const uint32_t stage_bytes = p.ws ? (uint32_t)C::STAGE_A : (uint32_t)C::STAGE;
+    const uint32_t stage_bytes = p.ws ? (uint32_t)C::STAGE_A : (uint32_t)(C::STAGE + (p.pair ? C::STAGE_B : 0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.groups * p.m_tiles * p.n_tiles * p.ksplit;
@@ -392,6 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tma_load_5d(sa, &tmA, full, ci + wp * p.Cin, dx, hp, oy0 + dy, img0);
                     }
                     if (!p.ws) tma_load_3d(sb, &tmB, full, k, tc.nt * BN, tc.g);
+                    if (p.pair) tma_load_3d(sb + C::STAGE_B, &tmB, full, k + p.k_lo, tc.nt * BN, tc.g);      // W_lo tile of the same k-block
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -424,6 +429,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int kk = 0; kk < 4; ++kk) {
                         // one MMA consumes 32 B of K (16 bf16 / 8 tf32): +32 B inside the 128 B swizzle row (encoded >> 4)
                         tc_mma<TF32>(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                    }
+                    if (p.pair) {
+                        const uint64_t dl = make_smem_desc(sb + C::STAGE_B);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) tc_mma<TF32>(tmem_d, da + 2 * kk, dl + 2 * kk, idesc, 1u);
                     }
                     tc_commit(empty0 + 8 * stage);
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
@@ -743,6 +753,14 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
         const cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
         if ((rc = encode(&tmD, out_dt, p.D, 3, dims, str, box, "D", box_cols * OB == 64))) return rc;
     }
+    // split weights: pair W_hi / W_lo in one ring stage when the tile is narrow enough to keep >= 4 stages
+    if (g_opt_pair && d.ka > 0 && d.K == 2 * d.ka && bn <= 128 && p.ksplit == 1) {
+        p.pair = 1;
+        p.pair_stages = SMEM_RING / (BM * ROW_BYTES + 2 * bn * ROW_BYTES);
+        p.k_lo = Ka;
+        p.kb_total = Ka / BK;
+        p.kb_per_split = p.kb_total;
+    }
     const int64_t total = (int64_t)d.groups * m_tiles * p.n_tiles * p.ksplit;
     const int grid = (int)(total < nsm ? total : nsm);
     // weight-stationary when the group's whole weight slab fits beside >= 4 A stages and every CTA walks several tiles:
@@ -750,7 +768,7 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     {
         const int64_t w_bytes = (int64_t)p.kb_total * bn * ROW_BYTES;
         const int64_t a_stages = (SMEM_RING - w_bytes) / (BM * ROW_BYTES);
-        const bool ws_ok = d.ka == 0 && (d.amode != A_PLAIN || p.kblk == d.K) && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
+        const bool ws_ok = d.ka == 0 && !p.pair && (d.amode != A_PLAIN || p.kblk == d.K) && p.n_tiles == 1 && p.ksplit == 1 && a_stages >= 4 &&
                            total >= 2 * (int64_t)grid;
         if (ws_ok && (d.ws || (g_opt_ws && d.amode == A_PLAIN))) {
             p.ws = 1;

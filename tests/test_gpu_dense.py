@@ -242,8 +242,10 @@ def _split16(w):
     return hi, lo
 
 
-@pytest.mark.parametrize("M,N,K,groups", [(4096, 256, 128, 1), (1000, 128, 256, 4), (960, 256, 4096, 4)])
-def test_tc_fp16_split_weights(M, N, K, groups):
+@pytest.mark.parametrize("pair", [1, 0])
+@pytest.mark.parametrize("M,N,K,groups", [(4096, 256, 128, 1), (1000, 128, 256, 4), (960, 256, 4096, 4), (148 * 128 + 77, 128, 128, 2),
+                                          (40000, 256, 256, 1)])
+def test_tc_fp16_split_weights(M, N, K, groups, pair):
     """EGR_PREC_FP16 dense stage: W = [W_hi | W_lo] along K (K' = 2K, ka = K: the k loop re-reads A): the result equals
     A_fp16 x W_fp32 to fp32-accumulation accuracy, i.e. the weight rounding error is gone (a single fp16 W is ~5e-4 off)"""
     g = torch.Generator(device="cuda").manual_seed(41)
@@ -253,7 +255,13 @@ def test_tc_fp16_split_weights(M, N, K, groups):
     hi, lo = _split16(W)
     Ws = torch.cat([hi, lo], dim=2).contiguous()                       # [g][N][2K]
     D = torch.full((groups, M, N), float("nan"), device="cuda")
-    dense(A, Ws, bias, D, M, N, 2 * K, K, N, epi=1, groups=groups, a_gs=M * K, w_gs=N * 2 * K, b_gs=N, d_gs=M * N, ka=K)
+    from egorear_b200 import engine
+    # pair=1: ring stages [A | W_hi | W_lo] (tiles up to 128 wide: A crosses L2 -> smem once); pair=0: the K wrap (A re-read)
+    engine.set_option("pair", pair)
+    try:
+        dense(A, Ws, bias, D, M, N, 2 * K, K, N, epi=1, groups=groups, a_gs=M * K, w_gs=N * 2 * K, b_gs=N, d_gs=M * N, ka=K)
+    finally:
+        engine.set_option("pair", 1)
     want = torch.relu(torch.einsum("gmk,gnk->gmn", A.double(), W.double()) + bias.double()[:, None, :]).float()
     err = float((D - want).abs().max() / want.abs().max())
     single = torch.relu(torch.einsum("gmk,gnk->gmn", A.double(), hi.double()) + bias.double()[:, None, :]).float()
