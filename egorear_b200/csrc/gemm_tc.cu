@@ -29,7 +29,8 @@ int g_opt_ws = 0;      // weight-stationary mode of gemm_tc (option "ws"): measu
 // Measured on the backbone at 512 frames: layer1 7.18 -> 8.10 ms, FPN 7.34 -> 7.63 ms: the convs are not waiting on DRAM
 // misses (what bounds them is the 9x re-read of the input through L2 -> shared memory), so it is off by default.
 int g_opt_conv_prefetch = 0;
-int g_opt_pair = 1;            // option "pair": split weights as [A | W_hi | W_lo] ring stages (BN <= 128) instead of the K wrap
+int g_opt_pair = 0;            // option "pair": split weights as [A | W_hi | W_lo] ring stages (BN <= 128) instead of the K wrap
+                               // (-0.4 % step time; off by default: every parity figure in DESIGN.md was taken with the K wrap)
 namespace {
 
 constexpr int BM = 128;

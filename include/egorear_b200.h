@@ -58,7 +58,12 @@ const char* egr_last_error(void);
  *   "pose_p2_bf16" (0)  debugging: bf16 operands there (costs the whole 0.1 mm MPJPE budget)
  *   "ws" (0)            weight-stationary mode of the tcgen05 GEMM (measured no gain)
  *   "wsplit" (1)        EGR_PREC_FP16: 0 single fp16 weights, 1 hi + lo pairs for 1x1 / Linear weights, 2 also the 3x3 convs
- *   "tok3x" (1)         EGR_PREC_FP16: mvfex token Linears as "3x TF32" (fp32-grade); 0 = plain TF32 as in EGR_PREC_BF16 */
+ *   "tok3x" (1)         EGR_PREC_FP16: mvfex token Linears as "3x TF32" (fp32-grade); 0 = plain TF32 as in EGR_PREC_BF16
+ *   "pair" (0)          split weights as paired ring stages [A | W_hi | W_lo] (tiles <= 128 wide: A crosses L2 -> smem once)
+ *                       instead of a second k pass over A; -0.4 % step time, other rounding order
+ *   "stem_fused" (1)    backbone stem as the fused tcgen05 kernel; 0 = im2col buffer + plain GEMM
+ *   "fpn_epi" (0)       backbone FPN upsample-add in the fuse conv's epilogue (measured slower)
+ *   "conv_prefetch" (0) 3x3 s1 convs prefetch the next tile's rows into L2 (measured slower) */
 int         egr_set_option(const char* key, int value);
 int         egr_version(void);
 /* stage profiler for bench.py: while enabled the engines record CUDA events between their stages on the launch

@@ -261,7 +261,7 @@ def test_tc_fp16_split_weights(M, N, K, groups, pair):
     try:
         dense(A, Ws, bias, D, M, N, 2 * K, K, N, epi=1, groups=groups, a_gs=M * K, w_gs=N * 2 * K, b_gs=N, d_gs=M * N, ka=K)
     finally:
-        engine.set_option("pair", 1)
+        engine.set_option("pair", 0)
     want = torch.relu(torch.einsum("gmk,gnk->gmn", A.double(), W.double()) + bias.double()[:, None, :]).float()
     err = float((D - want).abs().max() / want.abs().max())
     single = torch.relu(torch.einsum("gmk,gnk->gmn", A.double(), hi.double()) + bias.double()[:, None, :]).float()
