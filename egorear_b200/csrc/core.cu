@@ -1,6 +1,7 @@
 // Error plumbing, device check and misc C-ABI entry points.
 #include "common.cuh"
 #include "gemm.cuh"
+#include "layout_ops.cuh"
 #include <mutex>
 #include <vector>
 #include <map>
@@ -140,4 +141,18 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
         return gemm_tc(d, c->a_is_bf16, c->d_is_bf16, st);
     }
     return gemm_simt(d, c->a_is_bf16, c->d_is_bf16, st);
+}
+
+extern "C" int egr_head_tail_stage(const void* z, const float* w, const float* bias, const int32_t* wsel, int B, int G, int J,
+                                   float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, int impl, void* stream) {
+    using namespace egr;
+    EGR_CHECK(z && w && bias && wsel && hm, EGR_ERR_INVALID, "head_tail_stage: null operand");
+    EGR_CHECK(B > 0 && G > 0 && G <= 4 && J > 0 && J <= 16, EGR_ERR_INVALID, "head_tail_stage: B=%d G=%d J=%d", B, G, J);
+    EGR_CHECK((uintptr_t)z % 16 == 0 && (uintptr_t)w % 16 == 0, EGR_ERR_INVALID, "head_tail_stage: z and w must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    int sel[4] = {0, 0, 0, 0};
+    for (int g = 0; g < G; ++g) sel[g] = wsel[g];
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl) return head_tail_mma(z, w, bias, sel, B, G, J, hm, hm_bs, hm_gs, hm_t, precise, st);
+    return head_tail_tc(z, w, bias, sel, B, G, J, hm, hm_bs, hm_gs, hm_t, precise, st);
 }

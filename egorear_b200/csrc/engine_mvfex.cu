@@ -499,6 +499,7 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "fpn_epi") { g_opt_fpn_epi = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "conv_prefetch") { g_opt_conv_prefetch = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pair") { g_opt_pair = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "tail_mma") { g_opt_tail_mma = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }
 

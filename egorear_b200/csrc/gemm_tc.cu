@@ -335,8 +335,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_wait();         // everything above overlapped the previous kernel's tail; global memory from here on
 
     if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+        // ================= TMA producer (the whole warp runs the loop, one elected lane issues: tc_ptx.cuh elect_one) =================
+        {
             int stage = 0, phase = 0, w_group = -1, w_loads = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(t, p);
@@ -345,9 +345,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (p.ws && tc.g != w_group) {
                     // new weight set: wait until every MMA that read the previous slab has completed, then reload it
                     if (w_loads > 0) mbar_wait(wempty, (w_loads - 1) & 1);
-                    mbar_expect_tx(wfull, w_bytes);
-                    for (int kb = 0; kb < p.kb_total; ++kb)
-                        tma_load_3d(smem_base + kb * C::STAGE_B, &tmB, wfull, kb * BK, tc.nt * BN, tc.g);
+                    if (elect_one()) {
+                        mbar_expect_tx(wfull, w_bytes);
+                        for (int kb = 0; kb < p.kb_total; ++kb)
+                            tma_load_3d(smem_base + kb * C::STAGE_B, &tmB, wfull, kb * BK, tc.nt * BN, tc.g);
+                    }
+                    __syncwarp();
                     w_group = tc.g;
                     ++w_loads;
                 }
@@ -365,27 +368,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const TileCoord nc = decode_tile(tn, p);
                         const long long gm = (long long)nc.g * p.M + (long long)nc.mt * BM;
                         const int nimg = (int)(gm / p.HWout), noy = (int)(gm % p.HWout) / p.Wout;
-                        for (int ci = 0; ci < p.Cin; ci += BK) {
-                            tma_prefetch_4d(&tmA, ci, 0, noy - 1, nimg);
-                            tma_prefetch_4d(&tmA, ci, 0, noy - 1 + p.pf_rows, nimg);
+                        if (elect_one()) {
+                            for (int ci = 0; ci < p.Cin; ci += BK) {
+                                tma_prefetch_4d(&tmA, ci, 0, noy - 1, nimg);
+                                tma_prefetch_4d(&tmA, ci, 0, noy - 1 + p.pf_rows, nimg);
+                            }
                         }
+                        __syncwarp();
                     }
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
                     const uint32_t full = full0 + 8 * stage;
-                    mbar_expect_tx(full, stage_bytes);
                     const uint32_t sa = smem_base + w_bytes + stage * stage_bytes, sb = sa + C::STAGE_A;
                     const int k = kb * BK;
                     const int k_a = (k >= p.ka) ? k - p.ka : k;      // split weights: the second half of K re-reads A
+                    // A-tile coordinates of this k-block (c4 unused by the 4-D modes)
+                    int c0, c1, c2, c3, c4 = 0;
                     if (p.amode == A_PLAIN) {
-                        tma_load_4d(sa, &tmA, full, k_a % p.kblk, tc.mt * BM, k_a / p.kblk, tc.g);
+                        c0 = k_a % p.kblk; c1 = tc.mt * BM; c2 = k_a / p.kblk; c3 = tc.g;
                     } else if (p.amode == A_CONV3S1) {
                         // tap (ky,kx) of the tile's output pixels = the same box shifted by (ky-1, kx-1); the zero padding is
                         // the TMA unit's out-of-bounds fill (x = -1 / W, y = -1 / H of each image)
                         const int tap = k_a / p.Cin, ci = k_a - tap * p.Cin;
                         const int ky = tap / 3, kx = tap - ky * 3;
-                        tma_load_4d(sa, &tmA, full, ci, kx - 1, oy0 + ky - 1, img0);
+                        c0 = ci; c1 = kx - 1; c2 = oy0 + ky - 1; c3 = img0;
                     } else {
                         int tap = k_a / p.Cin;
                         const int ci = k_a - tap * p.Cin;
@@ -394,17 +401,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // input pixel (2*oy + ky - 1, 2*ox + kx - 1) = pair index (oy + dy, ox + dx), parity (hp, wp)
                         const int wp = (kx == 1) ? 0 : 1, dx = (kx == 0) ? -1 : 0;
                         const int hp = (ky == 1) ? 0 : 1, dy = (ky == 0) ? -1 : 0;
-                        tma_load_5d(sa, &tmA, full, ci + wp * p.Cin, dx, hp, oy0 + dy, img0);
+                        c0 = ci + wp * p.Cin; c1 = dx; c2 = hp; c3 = oy0 + dy; c4 = img0;
                     }
-                    if (!p.ws) tma_load_3d(sb, &tmB, full, k, tc.nt * BN, tc.g);
-                    if (p.pair) tma_load_3d(sb + C::STAGE_B, &tmB, full, k + p.k_lo, tc.nt * BN, tc.g);      // W_lo tile of the same k-block
+                    if (elect_one()) {
+                        mbar_expect_tx(full, stage_bytes);
+                        if (p.amode == A_CONV3S2) tma_load_5d(sa, &tmA, full, c0, c1, c2, c3, c4);
+                        else tma_load_4d(sa, &tmA, full, c0, c1, c2, c3);
+                        if (!p.ws) tma_load_3d(sb, &tmB, full, k, tc.nt * BN, tc.g);
+                        if (p.pair) tma_load_3d(sb + C::STAGE_B, &tmB, full, k + p.k_lo, tc.nt * BN, tc.g);      // W_lo tile of the same k-block
+                    }
+                    __syncwarp();
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
+        // ================= MMA issuer (the whole warp runs the loop, one elected lane issues) =================
+        {
             constexpr uint32_t idesc = make_idesc_fmt(BM, BN, TF32 ? 2u : (std::is_same<TI, __half>::value ? 0u : 1u));
             int stage = 0, phase = 0, it = 0, w_group = -1, w_loads = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
@@ -426,25 +439,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t sa = smem_base + w_bytes + stage * stage_bytes;
                     const uint32_t sb = p.ws ? smem_base + kb * C::STAGE_B : sa + C::STAGE_A;
                     const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sb);
+                    const uint64_t dl = make_smem_desc(sb + C::STAGE_B);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        // one MMA consumes 32 B of K (16 bf16 / 8 tf32): +32 B inside the 128 B swizzle row (encoded >> 4)
-                        tc_mma<TF32>(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-                    }
-                    if (p.pair) {
-                        const uint64_t dl = make_smem_desc(sb + C::STAGE_B);
+                        for (int kk = 0; kk < 4; ++kk) {
+                            // one MMA consumes 32 B of K (16 bf16 / 8 tf32): +32 B inside the 128 B swizzle row (encoded >> 4)
+                            tc_mma<TF32>(tmem_d, da + 2 * kk, db + 2 * kk, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                        }
+                        if (p.pair) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) tc_mma<TF32>(tmem_d, da + 2 * kk, dl + 2 * kk, idesc, 1u);
+                            for (int kk = 0; kk < 4; ++kk) tc_mma<TF32>(tmem_d, da + 2 * kk, dl + 2 * kk, idesc, 1u);
+                        }
+                        tc_commit(empty0 + 8 * stage);
                     }
-                    tc_commit(empty0 + 8 * stage);
+                    __syncwarp();
                     if (++stage == n_stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull0 + 8 * acc);
-                if (p.ws) {
-                    // last tile of this CTA that uses the resident slab: release it once these MMAs have completed
-                    const int tn = t + gridDim.x;
-                    if (tn < total_tiles && decode_tile(tn, p).g != tc.g) tc_commit(wempty);
+                // last tile of this CTA that uses the resident slab: release it once these MMAs have completed
+                const int tn = t + gridDim.x;
+                const bool release_w = p.ws && tn < total_tiles && decode_tile(tn, p).g != tc.g;
+                if (elect_one()) {
+                    tc_commit(tfull0 + 8 * acc);
+                    if (release_w) tc_commit(wempty);
                 }
+                __syncwarp();
             }
         }
     } else {
@@ -528,12 +546,13 @@ constexpr int64_t SPLITK_SCRATCH_FLOATS = SPLITK_SCRATCH_BYTES / 4;
 thread_local float* t_scratch = nullptr;
 
 int encode(CUtensorMap* tm, int dt, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box, const char* what, bool swizzle64 = false) {
+           const cuuint32_t* box, const char* what, bool swizzle64 = false, bool no_swizzle = false) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     const CUtensorMapDataType tdt = dt == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                   : dt == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     CUresult r = g_encode(tm, tdt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(EGR_ERR_CUDA, "cuTensorMapEncodeTiled(%s) failed with CUresult %d (rank %d, dims %llu %llu %llu, box %u %u %u)",
@@ -583,6 +602,16 @@ int set_smem_attr_bn() {
 }  // namespace
 
 void gemm_tc_set_scratch(float* scratch) { t_scratch = scratch; }
+
+// tiled tensor map (SWIZZLE_128B, or unswizzled rows) for the other TMA kernels of the library (head_tail_mma.cu)
+int tc_encode_tiled(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const char* what, bool no_swizzle) {
+    if (int rc = gemm_tc_init()) return rc;
+    cuuint64_t d[5], s[5];
+    cuuint32_t b[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; if (i + 1 < rank) s[i] = strides_bytes[i]; }
+    return encode(tm, dt, base, rank, d, s, b, what, false, no_swizzle);
+}
 
 int gemm_tc_init() {
     std::lock_guard<std::mutex> lk(g_tc_mu);

@@ -4,6 +4,8 @@
 #include <type_traits>
 
 namespace egr {
+int g_opt_tail_mma = 1;     // option "tail_mma": head tails on head_tail_mma.cu (0 = head_tail_tc.cu)
+
 
 extern int g_opt_tc;
 
@@ -467,8 +469,10 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
                  int Hs, int Ws, int C, int J, float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t,
                  cudaStream_t st) {
     EGR_CHECK(J <= HJ && (2 * Hs) % STRIP == 0 && G <= 4, EGR_ERR_UNSUPPORTED, "head_up_conv: J=%d Hs=%d G=%d", J, Hs, G);
-    if (Hs == FS && Ws == FS && C == FCH && z_bf16 >= 2)      // tensor-core tail (head_tail_tc.cu): fp16 z, bf16 (2) / fp16 (3) hm_t
+    if (Hs == FS && Ws == FS && C == FCH && z_bf16 >= 2) {    // tensor-core tails: fp16 z, bf16 (2) / fp16 (3) hm_t
+        if (g_opt_tail_mma) return head_tail_mma(z, w, bias, wsel_host, B, G, J, hm, hm_bs, hm_gs, hm_t, z_bf16 == 3, st);
         return head_tail_tc(z, w, bias, wsel_host, B, G, J, hm, hm_bs, hm_gs, hm_t, z_bf16 == 3, st);
+    }
     EGR_CHECK(z_bf16 < 2, EGR_ERR_UNSUPPORTED, "head_up_conv: fp16 z needs the 32x32x128 geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_bf16 ? 2 : 4;

@@ -21,6 +21,11 @@ int head_up_conv(const void* z, int z_bf16, const float* w, const float* bias, c
 // hm_t bf16, or with precise != 0 (z_bf16 == 3, EGR_PREC_FP16) fp16 and the 1x1 weights as an fp16 hi + lo pair
 int head_tail_tc(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
                  int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, cudaStream_t st);
+// second generation (head_tail_mma.cu, option "tail_mma", default): the bilinear upsample as a tcgen05.mma against integer
+// interpolation matrices (z read as an MN-major operand), fp32 row blend, then the 1x1 conv; persistent, TMA-fed
+int head_tail_mma(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
+                  int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, cudaStream_t st);
+extern int g_opt_tail_mma;
 
 // R1 tail: z [g][B][Hs*Ws][C] (z_dt: 0 fp32, 1 bf16, 2 fp16) -> relu(up2(z)) written to
 //   out_nchw[b*o_bs + g*o_gs + (c*H + y)*W + x] fp32 (module output; optional) and up to two channels-last copies

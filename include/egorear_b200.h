@@ -63,7 +63,8 @@ const char* egr_last_error(void);
  *                       instead of a second k pass over A; -0.4 % step time, other rounding order
  *   "stem_fused" (1)    backbone stem as the fused tcgen05 kernel; 0 = im2col buffer + plain GEMM
  *   "fpn_epi" (0)       backbone FPN upsample-add in the fuse conv's epilogue (measured slower)
- *   "conv_prefetch" (0) 3x3 s1 convs prefetch the next tile's rows into L2 (measured slower) */
+ *   "conv_prefetch" (0) 3x3 s1 convs prefetch the next tile's rows into L2 (measured slower)
+ *   "tail_mma" (1)      heatmap-head tails with the bilinear upsample on the tensor cores; 0 = CUDA-core interpolation */
 int         egr_set_option(const char* key, int value);
 int         egr_version(void);
 /* stage profiler for bench.py: while enabled the engines record CUDA events between their stages on the launch
@@ -196,6 +197,19 @@ typedef struct egr_dense_desc {
     int32_t ka;
 } egr_dense_desc;
 int egr_dense_stage(const egr_dense_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heatmap-head tail as a stage (what the mvfex engine runs after H1d / H2c; exposed for the stage-level parity tests):
+ *   `nn.Upsample(2, bilinear, align_corners=True), ReLU, Conv2d(128, J, 1)`     egoposeformer_heatmap_mvf_ex.py:108-110, :579-583
+ *   z     [G][B][32*32][128] fp16, channels-last pre-activations; w [n_sets][J][128] fp32, bias [n_sets][J] fp32,
+ *         group g uses weight set wsel[g] (G <= 4, J <= 16)
+ *   hm    fp32, element (b, g, j, y, x) at b*hm_bs + g*hm_gs + (j*64 + y)*64 + x
+ *   hm_t  optional 16-bit copy [G][B][J][64*64]: bf16 (precise 0) or fp16 (precise 1)
+ *   precise 1: 1x1 weights as an fp16 hi + lo pair, fp32 interpolation (EGR_PREC_FP16); impl 1: tensor-core interpolation
+ *   (head_tail_mma.cu), 0: CUDA-core interpolation (head_tail_tc.cu)
+ * ------------------------------------------------------------------------------------------- */
+int egr_head_tail_stage(const void* z, const float* w, const float* bias, const int32_t* wsel, int B, int G, int J,
+                        float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, int impl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * mvfex engine: everything EgoPoseFormerHeatmapMVFEX.forward does after the backbones
