@@ -423,7 +423,7 @@ def workload_name(args):
             "preprocess": "dataset preprocessing: PIL bicubic 872x872 -> 256x256 + ToTensor + Normalize, 4 views, %d frames/step/GPU" % args.batch,
             "eval_pose": "eval-time pose metrics (wrapper `evaluate_pose`: MPJPE, PA-MPJPE, PCK, AUC), 16 joints, "
                          "%d poses/step/GPU" % args.batch,
-            "rw_e2e": "ego4view_rw_heatmap_mvfex-n1_jqa + ego4view_rw_pose3d from images (PyTorch bf16-autocast backbone + hot path), "
+            "rw_e2e": "ego4view_rw_heatmap_mvfex-n1_jqa + ego4view_rw_pose3d from images (ResNet18 + EfficientFPN on the backbone engine + hot path), "
                       "batch %d/GPU" % args.batch}[args.workload]
 
 
@@ -567,7 +567,7 @@ def main():
                     b = bfb_h.to(dev, non_blocking=True)
                     yield step(f, b).cpu()
     elif args.workload == "rw_e2e":
-        # BASELINE config 5: images -> backbone (PyTorch) -> hot path (rw cameras, per-frame device->camera transforms)
+        # BASELINE config 5: images -> backbone engine -> hot path (rw cameras, per-frame device->camera transforms)
         pipe = HotPathPipeline(4, "ego4view_rw", args.precision, dev, with_backbone=True, materialize_features=False)
         P2ACT[0] = 2 if pipe.pose3d.engine().proposal_dtype() == "f16" else 4
         g = torch.Generator().manual_seed(rank)
@@ -586,11 +586,10 @@ def main():
             split["ev"] = e
             return out
         pipe.freeze()
-        in_bytes = img_h.numel() * 4 + ctm_h.numel() * 4
-        l2_note = "images %.0f MB + activations >> 126 MB L2" % (in_bytes / 1e6)
+        l2_note = "images %.0f MB + activations >> 126 MB L2" % ((img_h.numel() * 4 + ctm_h.numel() * 4) / 1e6)
         if not args.no_parity:
             def parity_fn():
-                # hot path only (the backbone is PyTorch on both sides): the staged features the backbone left, as fp32 NCHW
+                # hot path only (backbone parity: tests/test_gpu_backbone.py): the staged features the backbone left, as fp32 NCHW
                 from egorear_b200 import calib
                 from oracle import parity
                 xh, b = pipe.backbone_staged(img)
@@ -602,11 +601,17 @@ def main():
                 sd_p = {k: v.cpu() for k, v in pipe.pose3d.state_dict().items()}
                 return parity.hot_path_parity(out, pipe.heatmap.last_anchors[0], idx, feat_s, b[ii].cpu(), sd_h, sd_p,
                                               calib.load_calibration(None), "ego4view_rw", ctm_h[idx])
-        e2e_api = "backbone + HotPathPipeline.forward on freshly uploaded images"
+        # end to end as the data loader sees it: DECODED uint8 frames (256x256 RGB, 0.8 MB per 4-view frame) in pinned host
+        # memory -> H2D on a copy stream (overlapping the previous batch) -> resize/ToTensor/Normalize on the GPU -> backbone
+        # engine -> hot path -> packed joints read back
+        u8_h = torch.from_numpy(synth.synth_images(8, 256, 256, seed=rank)).repeat((B * 4 + 7) // 8, 1, 1, 1)[: B * 4]
+        u8_h = u8_h.view(B, 4, 256, 256, 3).contiguous().pin_memory()
+        in_bytes = u8_h.numel() + ctm_h.numel() * 4
+        e2e_api = ("HotPathPipeline.infer_host_batches on pinned decoded uint8 frames [B,4,256,256,3]: H2D of batch i+1 overlaps "
+                   "batch i; ops.preprocess_images + backbone engine + hot path on the device")
 
         def e2e_fn(n):
-            for _ in range(n):
-                yield step(img_h.to(dev, non_blocking=True), ctm_h.to(dev, non_blocking=True)).cpu()
+            yield from pipe.infer_host_batches(((u8_h, ctm_h) for _ in range(n)), world)
     elif args.workload == "generate_target":
         kp_h = torch.from_numpy(synth.synth_keypoints(B, 4, 16, seed=rank)).pin_memory()
         kp = kp_h.to(dev)

@@ -204,7 +204,11 @@ class HotPathPipeline:
 
         `batches` iterates (feat, bfb[, coord_trans_mat]) pinned-host tensors; feat is either fp32 [B,V,128,64,64] or the
         staged 16-bit [V,B,64,64,128] of stage_host_features (4.2 instead of 8.4 MB per frame over PCIe, and no staging
-        pass on the device).  The host->device copy of batch i+1 runs on a copy stream while batch i is computed (two device
+        pass on the device).  With a backbone (`with_backbone=True`) a batch may instead be (frames[, coord_trans_mat]) with
+        `frames` the DECODED uint8 images [B,V,H,W,3] a data loader holds after PNG/JPEG decode (0.8 MB per 4-view frame at
+        256x256): resize + ToTensor + Normalize (ops.preprocess_images, PIL-exact), the backbone engine and the hot path all
+        run on the device, as the dataset-side drop-in (egorear_b200/datasets.py) arranges under the reference's run.py.
+        The host->device copy of batch i+1 runs on a copy stream while batch i is computed (two device
         input slots, events both ways), so a step costs max(copy, compute) instead of their sum; the device->host read of
         the packed joints is the only synchronisation per batch.
         """
@@ -241,7 +245,17 @@ class HotPathPipeline:
                 upload(cur_i + 1, nxt)                   # overlaps with the forward below
             s = cur_i & 1
             main.wait_event(copied[s])
-            f, b = slots[s][0], slots[s][1]
+            f = slots[s][0]
+            if f.dtype == torch.uint8:                           # decoded frames: GPU preprocessing + backbone engine
+                from . import ops
+                ctm = slots[s][1] if len(slots[s]) > 1 else None
+                xh, b = self.backbone_staged(ops.preprocess_images(f))
+                packed = self.forward(None, b, ctm, feat_staged=xh)["packed"]
+                consumed[s].record(main)
+                yield egd.gather_rows(packed, world).cpu()
+                i += 1
+                continue
+            b = slots[s][1]
             ctm = slots[s][2] if len(slots[s]) > 2 else None
             if f.dtype in (torch.bfloat16, torch.float16):       # staged: read in place (also by the chained pose3d sampling)
                 packed = self.forward(None, b, ctm, feat_staged=f)["packed"]

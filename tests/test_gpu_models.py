@@ -377,6 +377,27 @@ def test_backbone_staged_matches_backbone():
     assert float((bfb2 - bfb).abs().max()) <= 2e-2 * float(bfb.abs().max())
 
 
+def test_pipeline_host_frames_match_sync_forward():
+    """infer_host_batches on DECODED uint8 frames (+ per-frame device->camera transforms): H2D prefetch, GPU preprocessing,
+    backbone engine, hot path == the same three calls made synchronously; frames of another size are resized on the GPU"""
+    from egorear_b200 import ops, synth
+    from egorear_b200.pipeline import HotPathPipeline
+    dev = torch.device("cuda", 0)
+    pipe = HotPathPipeline(4, "ego4view_rw", "fp16", dev, with_backbone=True, materialize_features=False)
+    host = []
+    for i, hw in enumerate((256, 256, 320)):
+        fr = torch.from_numpy(synth.synth_images(8, hw, hw, seed=70 + i)).view(2, 4, hw, hw, 3).contiguous().pin_memory()
+        host.append((fr, synth.synth_coord_trans_mat(2, seed=70 + i).pin_memory()))
+    want = []
+    for fr, ctm in host:
+        xh, b = pipe.backbone_staged(ops.preprocess_images(fr.to(dev)))
+        want.append(pipe.forward(None, b, ctm.to(dev), feat_staged=xh)["packed"].cpu())
+    got = list(pipe.infer_host_batches(iter(host)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert torch.isfinite(g).all() and torch.equal(g, w)
+
+
 def test_no_writes_outside_outputs_and_workspace(monkeypatch):
     """compute-sanitizer is not available on the GPU pool, so out-of-bounds WRITES are caught here: every tensor the
     package allocates during a chained forward (outputs, workspaces, gathers) is carved out of a larger byte buffer with
