@@ -82,6 +82,7 @@ struct WMat {
     int kw = 1;               // EGR_PREC_FP16: f16 holds [N][kw*K] = [W_hi | W_lo] when kw == 2 (split weights, gemm.cuh `ka`)
     // fp32-grade token Linears (EGR_PREC_FP16): f32x3 [sets][N][3K] = [W_hi | W_hi | W_lo] in TF32 values; A is [x | x_lo]
     float* f32x3 = nullptr;
+    __half* f16x3 = nullptr;  // the same product on fp16 pairs: [sets][N][3K] = [W_hi | W_hi | W_lo] fp16, A rows [x_hi | x_lo] fp16
     const void* w(int prec_bf16_tc) const { return prec_bf16_tc ? (const void*)bf16 : (const void*)f32; }
     int64_t stride() const { return (int64_t)N * K; }
 };
@@ -102,6 +103,9 @@ constexpr int PREC_TF32 = 2;
 constexpr int PREC_FP16 = 3;      // == EGR_PREC_FP16 (public since round 2: every 16-bit dense stage in fp16, split 1x1 weights)
 // token Linears of EGR_PREC_FP16: "3x TF32" (see gemm.cuh `ka`), A buffers hold [x | x_lo] rows of 2K floats
 constexpr int PREC_TF32X3 = 4;
+// the folded memory-projection GEMM (K = 3200, by far the largest token GEMM) runs the same three-term product on fp16 pairs:
+// 21 mantissa bits per operand at half the L2 -> smem traffic and twice the MMA rate; fp32 output
+constexpr int PREC_F16X3 = 5;
 
 // run one dense stage in the handle's precision.  `out_f32`: the output stays fp32 even in bf16 mode.
 // `out16`: DT_F16 makes a bf16-mode tensor-core stage write fp16 instead of bf16 (interpolated right afterwards in half2).
@@ -127,6 +131,15 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
         d.w_gs = w.stride() * 3;
         d.b_gs = w.N;
         return gemm_tc(d, DT_F32, DT_F32, st);
+    }
+    if (prec == PREC_F16X3) {       // caller: d.A fp16 rows [x_hi | x_lo], d.lda = 2K
+        d.K = 3 * w.K;
+        d.ka = 2 * w.K;
+        d.W = w.f16x3 + (int64_t)set_begin * w.stride() * 3;
+        d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
+        d.w_gs = w.stride() * 3;
+        d.b_gs = w.N;
+        return gemm_tc(d, DT_F16, DT_F32, st);
     }
     if (prec == PREC_TF32 && g_opt_tc) {
         d.W = w.f32 + (int64_t)set_begin * w.stride();

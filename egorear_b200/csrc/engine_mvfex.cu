@@ -14,6 +14,7 @@ int g_opt_tc = 1;
 int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
 int g_opt_wsplit = 1;
 int g_opt_tok3x = 1;
+int g_opt_fold16 = 1;      // option "fold16": EGR_PREC_FP16 runs the folded memory-projection GEMM (K = 3200) on fp16 pairs instead of 3x TF32
 extern int g_opt_pose_p2_bf16;
 extern int g_opt_pose_p2_fp16;
 extern int g_opt_ws;
@@ -74,6 +75,7 @@ enum WKind { W_PLAIN, W_CONV3, W_PAD16 };
 template <typename KeyFn>
 int make_wmat(egr_mvfex* h, WMat& m, int sets, int N, int K, WKind kind, KeyFn key, const bool* present, cudaStream_t st) {
     m.N = N; m.K = K; m.sets = sets;
+    m.f32x3 = nullptr; m.f16x3 = nullptr;      // derived copies of an earlier prepack went with the pool
     if (int rc = h->pool.alloc(&m.f32, (int64_t)sets * N * K)) return rc;
     if (int rc = h->pool.alloc(&m.bias, (int64_t)sets * N)) return rc;
     EGR_CUDA_OK(cudaMemsetAsync(m.f32, 0, sizeof(float) * sets * N * K, st));
@@ -342,9 +344,15 @@ int run_tokens_batched(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const 
     if ((rc = gemm(w.tx, E, h->tk_sa, w.toa, EPI_NONE, 0, false))) return rc;
     TokSampleArgs sa{};
     sa.G = G; sa.B = B; sa.V = V; sa.J = J; sa.H = FH; sa.W = FW; sa.E = E; sa.KA = KA; sa.oa = w.toa; sa.anchors = anchors;
-    sa.valid = valid; sa.X = w.Xh; sa.ptab = h->d_ptab16 + r0; sa.A = w.tA; sa.split = sp;
+    const bool fold16 = sp && h->tk_c.f16x3 != nullptr;      // sampled operand as fp16 pairs [x_hi | x_lo] (PREC_F16X3)
+    sa.valid = valid; sa.X = w.Xh; sa.ptab = h->d_ptab16 + r0; sa.A = w.tA; sa.split = fold16 ? 2 : sp;
     if ((rc = tok_sample(sa, act_code(h->prec), st))) return rc;
-    if ((rc = gemm(w.tA, V * KA, h->tk_c, w.tz, EPI_NONE, 0, false))) return rc;
+    if (fold16) {
+        GemmDesc d;
+        d.A = w.tA; d.lda = (int64_t)V * KA * 2; d.M = T; d.D = w.tz; d.ldd = h->tk_c.N; d.epi = EPI_NONE;
+        d.groups = G; d.a_gs = (int64_t)T * V * KA * 2; d.d_gs = (int64_t)T * h->tk_c.N;
+        if ((rc = run_gemm(d, h->tk_c, r0, PREC_F16X3, true, st))) return rc;
+    } else if ((rc = gemm(w.tA, V * KA, h->tk_c, w.tz, EPI_NONE, 0, false))) return rc;
     if ((rc = tok_add_ln(w.tx, w.tz, w.tx, G, T, E, ptr(TP_LNC_W), ptr(TP_LNC_B), st, sp))) return rc;
     // A2: joint self-attention
     if ((rc = gemm(w.tx, E, h->tk_qkv, w.tqkv, EPI_NONE, 0, false))) return rc;
@@ -499,6 +507,7 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "fpn_epi") { g_opt_fpn_epi = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "conv_prefetch") { g_opt_conv_prefetch = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pair") { g_opt_pair = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "fold16") { g_opt_fold16 = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "tail_mma") { g_opt_tail_mma = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
 }
@@ -655,6 +664,11 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
                 if ((rc = h->pool.alloc(&m->f32x3, (int64_t)m->sets * m->N * m->K * 3))) return rc;
                 if ((rc = split3_tf32(m->f32, m->f32x3, (int64_t)m->sets * m->N, m->K, st))) return rc;
             } else if ((rc = round_tf32_inplace(m->f32, (int64_t)m->sets * m->N * m->K, st))) return rc;
+        }
+        if (h->tok3x && g_opt_fold16 && (V * h->KA) % 64 == 0) {
+            WMat* m = &h->tk_c;
+            if ((rc = h->pool.alloc(&m->f16x3, (int64_t)m->sets * m->N * m->K * 3))) return rc;
+            if ((rc = split3_f16(m->f32, m->f16x3, (int64_t)m->sets * m->N, m->K, st))) return rc;
         }
         if ((rc = h->pool.alloc(&h->d_ptrs, TP_COUNT * 4))) return rc;
         EGR_CUDA_OK(cudaMemcpyAsync(h->d_ptrs, ptrs.data(), sizeof(const float*) * TP_COUNT * 4, cudaMemcpyHostToDevice, st));

@@ -757,6 +757,26 @@ int split3_tf32(const float* in, float* out, int64_t R, int K, cudaStream_t st) 
     return EGR_OK;
 }
 
+__global__ void split3_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int64_t n, int K) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K;
+        const int k = (int)(i - r * K);
+        const float w = in[i];
+        const __half hi = __float2half_rn(w);
+        out[r * 3 * K + k] = hi;
+        out[r * 3 * K + K + k] = hi;
+        out[r * 3 * K + 2 * K + k] = __float2half_rn(w - __half2float(hi));
+    }
+}
+int split3_f16(const float* in, __half* out, int64_t R, int K, cudaStream_t st) {
+    const int64_t n = R * K;
+    if (n == 0) return EGR_OK;
+    const int64_t g = ceil_div64(n, 256);
+    split3_f16_kernel<<<(int)(g < 148 * 64 ? g : 148 * 64), 256, 0, st>>>(in, out, n, K);
+    EGR_LAUNCHED();
+    return EGR_OK;
+}
+
 int cast_act(const float* in, void* out, int out_bf16, int64_t n, cudaStream_t st) {
     if (out_bf16 == 2) return cast_f16(in, (__half*)out, n, st);
     if (out_bf16) return cast_bf16(in, (__nv_bfloat16*)out, n, st);

@@ -51,6 +51,8 @@ int cast_f16(const float* in, __half* out, int64_t n, cudaStream_t st);
 int split_f16(const float* in, __half* out, int64_t R, int K, cudaStream_t st);
 // "3x TF32" weights of the fp32-grade token Linears: out [R][3K] fp32 = [hi | hi | lo], hi = tf32(w), lo = tf32(w - hi)
 int split3_tf32(const float* in, float* out, int64_t R, int K, cudaStream_t st);
+// fp16 flavour of the same product: [R][K] fp32 -> [R][3K] fp16 = [W_hi | W_hi | W_lo], A rows [x_hi | x_lo] fp16 (half the bytes)
+int split3_f16(const float* in, __half* out, int64_t R, int K, cudaStream_t st);
 // [R][C] -> [C][R]
 int transpose2d(const float* in, float* out, int R, int C, cudaStream_t st);
 // C[M][N] = A[M][K] · B[K][N] (+ bias[N] broadcast when non-null); small prepack-time products, fp32

@@ -25,6 +25,14 @@ __device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
 }
 
 // two 16-bit values of the staged map -> fp32 (bf16: shifts; fp16: one cvt)
+// fp16 pair of an fp32 value: hi = fp16(x), lo = fp16(x - hi) (operand rows [x_hi | x_lo] of the fp16 three-term product)
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 template <bool F16> __device__ __forceinline__ void cvt16x2(uint32_t w, float& lo, float& hi) {
     if (F16) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w)); lo = f.x; hi = f.y; }
     else { lo = __uint_as_float(w << 16); hi = __uint_as_float(w & 0xffff0000u); }
@@ -56,12 +64,30 @@ tok_sample_kernel(TokSampleArgs a) {
     const int LO = a.V * a.KA;                                   // offset of the x_lo half of a split row
     float* Arow = a.A + ((int64_t)g * T_ + t) * (int64_t)LO * (1 + a.split) + (int64_t)v * a.KA;
     const bool ok = a.valid[((int64_t)b * a.V + v) * a.J + j] != 0;
+    // split == 2: the row is an fp16 pair [x_hi | x_lo] of 2 * LO halfs (operand of the fp16 three-term fold GEMM)
+    __half* Hrow = reinterpret_cast<__half*>(a.A) + ((int64_t)g * T_ + t) * (int64_t)LO * 2 + (int64_t)v * a.KA;
+    if (a.split == 2) {
+        const __half zero = __float2half_rn(0.f);
+        if (h == 0) {
+            if (lane == 0) { Hrow[NH * RAWC + EX] = __float2half_rn(ok ? 1.f : 0.f); Hrow[LO + NH * RAWC + EX] = zero; }
+            for (int c = NH * RAWC + EX + 1 + lane; c < a.KA; c += 32) { Hrow[c] = zero; Hrow[LO + c] = zero; }
+        }
+        if (!ok) {
+            for (int s2 = 0; s2 < 2; ++s2) {
+                __half* R = Hrow + s2 * LO;
+                *reinterpret_cast<uint2*>(R + h * RAWC + lane * 4) = make_uint2(0u, 0u);
+                if (HAS_PTAB) *reinterpret_cast<uint32_t*>(R + NH * RAWC + h * HD + lane * 2) = 0u;
+                else if (lane == 0) R[NH * RAWC + h] = zero;
+            }
+            return;
+        }
+    } else
     if (h == 0) {     // validity column (carries output_proj's bias through the fold) + zero padding
         if (lane == 0) Arow[NH * RAWC + EX] = ok ? 1.f : 0.f;
         for (int c = NH * RAWC + EX + 1 + lane; c < a.KA; c += 32) Arow[c] = 0.f;
         if (a.split) for (int c = NH * RAWC + EX + lane; c < a.KA; c += 32) Arow[LO + c] = 0.f;
     }
-    if (!ok) {        // masked_fill(~anchors_valid, 0) after output_proj (:910 / :563): the whole row is zero
+    if (!ok && a.split != 2) {        // masked_fill(~anchors_valid, 0) after output_proj (:910 / :563): the whole row is zero
         for (int s2 = 0; s2 <= a.split; ++s2) {
             float* R = Arow + s2 * LO;
             *reinterpret_cast<float4*>(R + h * RAWC + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -134,7 +160,23 @@ tok_sample_kernel(TokSampleArgs a) {
     } else {
         wsum += __shfl_xor_sync(0xffffffffu, wsum, 16);
     }
-    if (half == 0) {
+    if (half == 0 && a.split == 2) {
+        uint4 hi, lo;
+        split_h2(s8[0], s8[1], hi.x, lo.x); split_h2(s8[2], s8[3], hi.y, lo.y);
+        split_h2(s8[4], s8[5], hi.z, lo.z); split_h2(s8[6], s8[7], hi.w, lo.w);
+        *reinterpret_cast<uint4*>(Hrow + h * RAWC + l16 * 8) = hi;
+        *reinterpret_cast<uint4*>(Hrow + LO + h * RAWC + l16 * 8) = lo;
+        if (HAS_PTAB) {
+            uint2 eh, el;
+            split_h2(e4[0], e4[1], eh.x, el.x); split_h2(e4[2], e4[3], eh.y, el.y);
+            *reinterpret_cast<uint2*>(Hrow + NH * RAWC + h * HD + l16 * 4) = eh;
+            *reinterpret_cast<uint2*>(Hrow + LO + NH * RAWC + h * HD + l16 * 4) = el;
+        } else if (l16 == 0) {
+            const __half wh = __float2half_rn(wsum);
+            Hrow[NH * RAWC + h] = wh;
+            Hrow[LO + NH * RAWC + h] = __float2half_rn(wsum - __half2float(wh));
+        }
+    } else if (half == 0) {
         float4* o = reinterpret_cast<float4*>(Arow + h * RAWC + l16 * 8);
         if (a.split) {
             o[0] = make_float4(s8[0], s8[1], s8[2], s8[3]);

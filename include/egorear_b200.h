@@ -64,6 +64,8 @@ const char* egr_last_error(void);
  *   "stem_fused" (1)    backbone stem as the fused tcgen05 kernel; 0 = im2col buffer + plain GEMM
  *   "fpn_epi" (0)       backbone FPN upsample-add in the fuse conv's epilogue (measured slower)
  *   "conv_prefetch" (0) 3x3 s1 convs prefetch the next tile's rows into L2 (measured slower)
+ *   "fold16" (1)        EGR_PREC_FP16: the folded memory-projection GEMM of the mvfex tokens on fp16 pairs ([x_hi | x_lo] x
+ *                       [W_hi | W_hi | W_lo]) instead of 3x TF32: same three-term product at half the bytes
  *   "tail_mma" (1)      heatmap-head tails with the bilinear upsample on the tensor cores; 0 = CUDA-core interpolation */
 int         egr_set_option(const char* key, int value);
 int         egr_version(void);
