@@ -290,9 +290,8 @@ int p_run_tokens_batched(egr_pose3d* h, int B, const PBufs& w, const void* Xs, i
         if ((rc = tok_add_ln(w.tx, w.tz, w.tx, 1, T, E, P + 2, P + 3, st))) return rc;
         if ((rc = gemm(w.tx, E, t.f1, w.thid, EPI_GELU, 1))) return rc;
         if ((rc = gemm(w.thid, TOK_FF, t.f2, w.tz, EPI_NONE, 0))) return rc;
-        if ((rc = tok_add_ln(w.tx, w.tz, w.tx, 1, T, E, P + 4, P + 5, st))) return rc;
-        // post_norm[l] -> reg_mlp[l] -> + anchors (after the in-place quirk)
-        if ((rc = tok_add_ln(nullptr, w.tx, w.to, 1, T, E, P + 6, P + 7, st))) return rc;
+        // FFN residual + norm, and post_norm[l] of the result in the same launch -> reg_mlp[l] -> + anchors (after the in-place quirk)
+        if ((rc = tok_add_ln(w.tx, w.tz, w.tx, 1, T, E, P + 4, P + 5, st, 0, w.to, P + 6, P + 7))) return rc;
         if ((rc = gemm(w.to, E, t.r0, w.tz, EPI_GELU, 0))) return rc;
         if ((rc = pose_reg_out(w.tz, tw.r2_T[l], tw.r2_b[l], w.tp3, preds + (int64_t)(l + 1) * T * 3, T, E, st))) return rc;
     }

@@ -311,7 +311,8 @@ __device__ __forceinline__ void ln_row(const float* v_in, float (&v)[E / 32], fl
 template <int E>
 __global__ void __launch_bounds__(256)
 tok_add_ln_kernel(const float* __restrict__ res, const float* __restrict__ z, float* __restrict__ out, int64_t rows,
-                  int rows_per_group, const float* const* __restrict__ gamma, const float* const* __restrict__ beta, int split) {
+                  int rows_per_group, const float* const* __restrict__ gamma, const float* const* __restrict__ beta, int split,
+                  float* __restrict__ out2, const float* const* __restrict__ gamma2, const float* const* __restrict__ beta2) {
     pdl_trigger();
     pdl_wait();
     const int lane = threadIdx.x & 31;
@@ -332,16 +333,30 @@ tok_add_ln_kernel(const float* __restrict__ res, const float* __restrict__ z, fl
 #pragma unroll
     for (int i = 0; i < E / 32; ++i) {
         const int c = lane + 32 * i;
-        tok_operand_store(out + row * ldr, c, E, (v[i] - mean) * rstd * __ldg(ga + c) + __ldg(be + c), split);
+        v[i] = (v[i] - mean) * rstd * __ldg(ga + c) + __ldg(be + c);
+        tok_operand_store(out + row * ldr, c, E, v[i], split);
+    }
+    if (out2) {      // a second LayerNorm of the row just written (pose3d: post_norm[l] of the layer output), as stored
+        const float* g2 = gamma2[g];
+        const float* b2 = beta2[g];
+#pragma unroll
+        for (int i = 0; i < E / 32; ++i) v[i] = split ? v[i] : round_tf32(v[i]);
+        ln_row<E>(nullptr, v, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < E / 32; ++i) {
+            const int c = lane + 32 * i;
+            tok_operand_store(out2 + row * ldr, c, E, (v[i] - mean) * rstd * __ldg(g2 + c) + __ldg(b2 + c), split);
+        }
     }
 }
 
 int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per_group, int E, const float* const* gamma,
-               const float* const* beta, cudaStream_t st, int split) {
+               const float* const* beta, cudaStream_t st, int split, float* out2, const float* const* gamma2,
+               const float* const* beta2) {
     const int64_t rows = (int64_t)G * rows_per_group;
     const int blocks = (int)ceil_div64(rows, 8);
-    if (E == 256) EGR_LAUNCH(tok_add_ln_kernel<256>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta, split);
-    else if (E == 128) EGR_LAUNCH(tok_add_ln_kernel<128>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta, split);
+    if (E == 256) EGR_LAUNCH(tok_add_ln_kernel<256>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta, split, out2, gamma2, beta2);
+    else if (E == 128) EGR_LAUNCH(tok_add_ln_kernel<128>, blocks, 256, 0, st, res, z, out, rows, rows_per_group, gamma, beta, split, out2, gamma2, beta2);
     else return fail(EGR_ERR_UNSUPPORTED, "tok_add_ln: E=%d", E);
     return EGR_OK;
 }

@@ -64,8 +64,10 @@ int tok_attn(const float* qkv, float* o, int n_frames /*G*B*/, int J, int E, cud
 // out[row] = LayerNorm(res[row] + z[row]) * gamma[g] + beta[g]   (res may be null), rounded to TF32.
 //   rows = G * rows_per_group; gamma / beta are device arrays of G pointers
 //   split: res / out rows are [x | x_lo] (2E floats; z stays a plain GEMM output of E floats)
+//   out2 (optional): out2[row] = LayerNorm(out[row]) * gamma2[g] + beta2[g] in the same launch
 int tok_add_ln(const float* res, const float* z, float* out, int G, int rows_per_group, int E, const float* const* gamma,
-               const float* const* beta, cudaStream_t st, int split = 0);
+               const float* const* beta, cudaStream_t st, int split = 0, float* out2 = nullptr,
+               const float* const* gamma2 = nullptr, const float* const* beta2 = nullptr);
 
 // mvfex post_norm + token image: LN rows of x [G][B][J][E] -> xT [G][B][E][16] (pos-major, joint-minor, col 15 = 0)
 int tok_ln_image(const float* x, void* xT, int xT_bf16, int G, int B, int J, int E, const float* const* gamma,
