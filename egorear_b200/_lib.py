@@ -26,7 +26,8 @@ class DenseDesc(ctypes.Structure):
                 ("groups", ctypes.c_int32),
                 ("a_gs", c_int64), ("w_gs", c_int64), ("b_gs", c_int64), ("d_gs", c_int64), ("aux_gs", c_int64),
                 ("a_is_bf16", ctypes.c_int32), ("d_is_bf16", ctypes.c_int32), ("use_tc", ctypes.c_int32),
-                ("ka", ctypes.c_int32)]
+                ("ka", ctypes.c_int32),
+                ("out_pair", ctypes.c_int32)]
 
 
 class EgrError(RuntimeError):

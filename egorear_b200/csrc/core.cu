@@ -128,7 +128,7 @@ extern "C" int egr_dense_stage(const egr_dense_desc* c, void* stream) {
     GemmDesc d;
     d.A = c->A; d.W = c->W; d.bias = c->bias; d.D = c->D; d.aux = c->aux;
     d.M = c->M; d.N = c->N; d.K = c->K; d.lda = c->lda; d.ldd = c->ldd; d.amode = c->amode; d.epi = c->epi;
-    d.kblk = c->kblk; d.kblk_stride = c->kblk_stride; d.ka = c->ka;
+    d.kblk = c->kblk; d.kblk_stride = c->kblk_stride; d.ka = c->ka; d.out_pair = c->out_pair;
     EGR_CHECK(d.ka == 0 || c->use_tc, EGR_ERR_UNSUPPORTED, "dense_stage: split operands (ka) need the tensor-core kernel");
     d.Hin = c->Hin; d.Win = c->Win; d.Cin = c->Cin; d.Hout = c->Hout; d.Wout = c->Wout;
     d.groups = c->groups > 0 ? c->groups : 1;

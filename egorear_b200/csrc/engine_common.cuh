@@ -132,14 +132,14 @@ inline int run_gemm(GemmDesc d, const WMat& w, int set_begin, int prec, bool out
         d.b_gs = w.N;
         return gemm_tc(d, DT_F32, DT_F32, st);
     }
-    if (prec == PREC_F16X3) {       // caller: d.A fp16 rows [x_hi | x_lo], d.lda = 2K
+    if (prec == PREC_F16X3) {       // caller: d.A fp16 rows [x_hi | x_lo] (a pair output of the previous stage), d.lda = 2K
         d.K = 3 * w.K;
         d.ka = 2 * w.K;
         d.W = w.f16x3 + (int64_t)set_begin * w.stride() * 3;
         d.bias = w.bias ? w.bias + (int64_t)set_begin * w.N : nullptr;
         d.w_gs = w.stride() * 3;
         d.b_gs = w.N;
-        return gemm_tc(d, DT_F16, DT_F32, st);
+        return gemm_tc(d, DT_F16, out_f32 ? DT_F32 : DT_F16, st);
     }
     if (prec == PREC_TF32 && g_opt_tc) {
         d.W = w.f32 + (int64_t)set_begin * w.stride();

@@ -14,6 +14,7 @@ int g_opt_tc = 1;
 int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
 int g_opt_wsplit = 1;
 int g_opt_tok3x = 1;
+int g_opt_asplit = 1;      // option "asplit": EGR_PREC_FP16 keeps the five 32x32 activations of the refine path as fp16 pairs [hi | lo]
 int g_opt_fold16 = 1;      // option "fold16": EGR_PREC_FP16 runs the folded memory-projection GEMM (K = 3200) on fp16 pairs instead of 3x TF32
 extern int g_opt_pose_p2_bf16;
 extern int g_opt_pose_p2_fp16;
@@ -58,6 +59,7 @@ struct egr_mvfex {
     const void* in_staged = nullptr;           // one-shot: the caller's view-major channels-last bf16 copy of the input features
     const void* st_refined_hp = nullptr;
     bool tokb = false;
+    bool asplit = false;                       // EGR_PREC_FP16: F1b / F1c / R1a / H2a / H2b write [hi | lo] pairs, their consumers read them (PREC_F16X3)
     bool tok3x = false;                        // EGR_PREC_FP16: token operand rows [x | x_lo], weights [W_hi | W_hi | W_lo]
     WMat tk_hp2, tk_fcq, tk_bfb, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
     const __nv_bfloat16** d_ptab16 = nullptr;  // device [4]: bf16 copies of the sampled position tables
@@ -205,11 +207,12 @@ int64_t carve(const egr_mvfex* h, int B, int G, bool with_heads, bool own_copy, 
     b.Xown = own_copy ? c.take((int64_t)G * B * FHW * FC * s) : nullptr;
     b.h1a = with_heads ? c.take((int64_t)V * B * FHW * FC * s) : nullptr;
     b.a1 = c.take((int64_t)G * B * FHW * 256 * s);
-    b.b1 = c.take((int64_t)Gh * B * 1024 * 512 * s);
-    b.c1 = c.take((int64_t)Gh * B * 1024 * 256 * s);
+    const int ap = h->asplit ? 2 : 1;                  // pair tensors: rows [hi | lo]
+    b.b1 = c.take((int64_t)Gh * B * 1024 * 512 * s * ap);
+    b.c1 = c.take((int64_t)Gh * B * 1024 * 256 * s * ap);
     b.z = c.take((int64_t)Gh * B * 1024 * 128 * s);
-    b.ff = c.take((int64_t)G * B * 1024 * 128 * s);
-    b.r1a = c.take((int64_t)G * B * 1024 * 128 * s);
+    b.ff = c.take((int64_t)G * B * 1024 * 128 * s * ap);
+    b.r1a = c.take((int64_t)G * B * 1024 * 128 * s * ap);
     b.refn = (!f16m && h->refn_f16_only && G == V) ? nullptr : c.take((int64_t)G * B * FHW * FC * s);
     b.hmT = c.take((int64_t)Gh * B * J * FHW * s);
     b.xT = c.take((int64_t)G * B * NPOS * 16 * s);
@@ -423,27 +426,32 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     EGR_MARK("F1b", st);
     // F1b: 3x3 s2 (256->512) ReLU -> 32x32
     d = GemmDesc();
-    d.A = w.a1; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = 256; d.M = B * 1024; d.D = w.b1; d.ldd = 512;
-    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * 256; d.d_gs = (int64_t)B * 1024 * 512;
+    // asplit (EGR_PREC_FP16): the 32x32 activations of the refine path travel as fp16 pairs [hi | lo] (GemmDesc.out_pair) and
+    // are consumed as split operands (PREC_F16X3): five of the fourteen 10-bit roundings between the input features and the
+    // refined heatmap disappear
+    const int ap = h->asplit ? 2 : 1;
+    const int cprec = h->asplit ? PREC_F16X3 : prec;      // consumer of a pair tensor
+    d.A = w.a1; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = 256; d.M = B * 1024; d.D = w.b1; d.ldd = 512 * ap;
+    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * 256; d.d_gs = (int64_t)B * 1024 * 512 * ap; d.out_pair = h->asplit;
     if ((rc = run_gemm(d, h->f1_2, r0, prec, false, st))) return rc;
     EGR_MARK("F1c", st);
     // F1c: 1x1(512->128) ReLU, fused with "+ offset_pred": + relu(up2(t1))   (:715 offset_pred + frame_feat)
     d = GemmDesc();
-    d.A = w.b1; d.lda = 512; d.M = B * 1024; d.D = w.ff; d.ldd = 128; d.epi = EPI_RELU_ADDUP; d.aux = w.t1;
-    d.Hout = 32; d.Wout = 32; d.groups = G; d.a_gs = (int64_t)B * 1024 * 512; d.d_gs = (int64_t)B * 1024 * 128;
-    d.aux_gs = (int64_t)B * NPOS * 128;
-    if ((rc = run_gemm(d, h->f1_4, r0, prec, false, st))) return rc;
+    d.A = w.b1; d.lda = 512 * ap; d.M = B * 1024; d.D = w.ff; d.ldd = 128 * ap; d.epi = EPI_RELU_ADDUP; d.aux = w.t1;
+    d.Hout = 32; d.Wout = 32; d.groups = G; d.a_gs = (int64_t)B * 1024 * 512 * ap; d.d_gs = (int64_t)B * 1024 * 128 * ap;
+    d.aux_gs = (int64_t)B * NPOS * 128; d.out_pair = h->asplit;
+    if ((rc = run_gemm(d, h->f1_4, r0, cprec, false, st))) return rc;
     EGR_MARK("R1a", st);
     // R1a: 1x1(128->128) ReLU @32x32 ; R1b: second 1x1 commuted in front of the upsample
     d = GemmDesc();
-    d.A = w.ff; d.lda = 128; d.M = B * 1024; d.D = w.r1a; d.ldd = 128; d.epi = EPI_RELU;
-    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128;
-    if ((rc = run_gemm(d, h->r1_0, r0, prec, false, st))) return rc;
+    d.A = w.ff; d.lda = 128 * ap; d.M = B * 1024; d.D = w.r1a; d.ldd = 128 * ap; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128 * ap; d.out_pair = h->asplit;
+    if ((rc = run_gemm(d, h->r1_0, r0, cprec, false, st))) return rc;
     EGR_MARK("R1b", st);
     // on the tensor-core path the pre-upsample maps z are written in fp16 so that the tails interpolate in half2
     const bool z16 = is16(prec) && g_opt_tc;
-    d.A = w.r1a; d.D = w.z; d.epi = EPI_NONE;
-    if ((rc = run_gemm(d, h->r1_3, r0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
+    d.A = w.r1a; d.D = w.z; d.ldd = 128; d.d_gs = (int64_t)B * 1024 * 128; d.epi = EPI_NONE; d.out_pair = 0;
+    if ((rc = run_gemm(d, h->r1_3, r0, cprec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("R1tail", st);
     // R1c: relu(up2(.)) -> refined features: fp32 NCHW module output (optional) + channels-last copies for H2 / pose3d
     if ((rc = up2_relu_dual(w.z, z16 ? 2 : bf, B, G, 32, 32, FC, feat_refined, ft_bs, ft_gs, w.refn, f16m ? 2 : bf ? 1 : 3, w.refn_hp,
@@ -451,8 +459,8 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     EGR_MARK("H2a", st);
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
-    d.A = w.refn; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = B * 1024; d.D = w.b1; d.ldd = 256;
-    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256;
+    d.A = w.refn; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = B * 1024; d.D = w.b1; d.ldd = 256 * ap;
+    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256 * ap; d.out_pair = h->asplit;
     if (!w.refn) {
         // the refined features exist only as the fp16 channels-last copy shared with pose3d: fp16 operands, bf16 output
         d.A = w.refn_hp; d.N = 256; d.K = 9 * FC; d.W = h->h2_0_f16 + (int64_t)r0 * 256 * 9 * FC; d.w_gs = (int64_t)256 * 9 * FC;
@@ -461,14 +469,14 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     } else if ((rc = run_gemm(d, h->h2_0, r0, prec, false, st))) return rc;
     EGR_MARK("H2b", st);
     d = GemmDesc();
-    d.A = w.b1; d.lda = 256; d.M = B * 1024; d.D = w.c1; d.ldd = 256; d.epi = EPI_RELU;
-    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 256;
-    if ((rc = run_gemm(d, h->h2_2, r0, prec, false, st))) return rc;
+    d.A = w.b1; d.lda = 256 * ap; d.M = B * 1024; d.D = w.c1; d.ldd = 256 * ap; d.epi = EPI_RELU;
+    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 256 * ap; d.out_pair = h->asplit;
+    if ((rc = run_gemm(d, h->h2_2, r0, cprec, false, st))) return rc;
     EGR_MARK("H2c", st);
     d = GemmDesc();
-    d.A = w.c1; d.lda = 256; d.M = B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
-    d.groups = G; d.a_gs = (int64_t)B * 1024 * 256; d.d_gs = (int64_t)B * 1024 * 128;
-    if ((rc = run_gemm(d, h->h2_5, r0, prec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
+    d.A = w.c1; d.lda = 256 * ap; d.M = B * 1024; d.D = w.z; d.ldd = 128; d.epi = EPI_NONE;
+    d.groups = G; d.a_gs = (int64_t)B * 1024 * 256 * ap; d.d_gs = (int64_t)B * 1024 * 128;
+    if ((rc = run_gemm(d, h->h2_5, r0, cprec, false, st, z16 ? DT_F16 : DT_BF16))) return rc;
     EGR_MARK("H2tail", st);
     int wsel[4] = {r0, r0 + 1, r0 + 2, r0 + 3};
     if ((rc = head_up_conv(w.z, f16m ? 3 : z16 ? 2 : bf, h->h2_7w, h->h2_7b, wsel, B, G, 32, 32, FC, J, hm_refined, hm_bs, hm_gs, nullptr, st)))
@@ -507,6 +515,7 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "fpn_epi") { g_opt_fpn_epi = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "conv_prefetch") { g_opt_conv_prefetch = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pair") { g_opt_pair = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "asplit") { g_opt_asplit = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "fold16") { g_opt_fold16 = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "tail_mma") { g_opt_tail_mma = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
@@ -527,6 +536,7 @@ extern "C" int egr_mvfex_create(int num_views, int num_heatmap, float heatmap_th
     h->head_sets = (num_views == 2) ? 1 : 2;
     h->tokb = is16(precision) && g_opt_tc && g_opt_tok_batched;
     h->tok3x = precision == EGR_PREC_FP16 && g_opt_tok3x;
+    h->asplit = precision == EGR_PREC_FP16 && g_opt_asplit && g_opt_wsplit >= 1;
     h->KA = tok_ka(EMB, true);
     *out = h;
     return EGR_OK;
@@ -562,6 +572,7 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
               "mvfex: EGR_PREC_FP16 is a tensor-core mode (options tc / tok_batched must be on)");
     h->tokb = is16(h->prec) && g_opt_tc && g_opt_tok_batched;
     h->tok3x = h->prec == EGR_PREC_FP16 && g_opt_tok3x;
+    h->asplit = h->prec == EGR_PREC_FP16 && g_opt_asplit && g_opt_wsplit >= 1;
     h->KA = tok_ka(EMB, true);
     auto head = [&](const char* sub) { return [sub](int s) { return std::string(kHead[s]) + sub; }; };
     auto ref = [&](const char* sub) { return [sub](int s) { return std::string(kRefiner4[s]) + sub; }; };
@@ -602,6 +613,13 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
     }
     if ((rc = make_wmat(h, h->h2_2, V, 256, 256, W_PLAIN, ref(".conv_heatmap_layers.0.2"), rp, st))) return rc;
     if ((rc = make_wmat(h, h->h2_5, V, 128, 256, W_PLAIN, ref(".conv_heatmap_layers.0.5"), rp, st))) return rc;
+    if (h->asplit) {      // consumers of pair tensors: [W_hi | W_hi | W_lo] against A = [x_hi | x_lo]
+        WMat* cons[5] = {&h->f1_4, &h->r1_0, &h->r1_3, &h->h2_2, &h->h2_5};
+        for (WMat* m : cons) {
+            if ((rc = h->pool.alloc(&m->f16x3, (int64_t)m->sets * m->N * m->K * 3))) return rc;
+            if ((rc = split3_f16(m->f32, m->f16x3, (int64_t)m->sets * m->N, m->K, st))) return rc;
+        }
+    }
     if ((rc = h->pool.alloc(&h->h2_7w, (int64_t)V * J * 128))) return rc;
     if ((rc = h->pool.alloc(&h->h2_7b, (int64_t)V * J))) return rc;
     std::vector<MvfTokenW> tok(V);

@@ -45,6 +45,10 @@ struct GemmDesc {
     //       (x is raw fp32, the tensor core truncates it to TF32 = x_hi; x_lo = tf32(x - x_hi)): fp32-grade token Linears.
     // 0 = plain.
     int ka = 0;
+    // pair output (tcgen05 path, fp16 output): the row of D is [hi (N) | lo (N)] with hi = fp16(y), lo = fp16(y - hi): the
+    // consumer reads it as the split operand A = [x_hi | x_lo] (ka = 2N) - no activation rounding between the two stages.
+    // ldd >= 2N.
+    int out_pair = 0;
     // weight-stationary hint (tcgen05 path): keep the group's whole [BN x K] weight slab resident in shared memory and stream
     // A tiles only, when the slab leaves room for >= 4 A stages.  Pays off where the weight re-fetch per tile is a large share of
     // the L2 -> SM traffic: the N = 64 3x3 convs of ResNet layer1 (72 KB slab vs 144 KB of A per tile).

@@ -67,6 +67,7 @@ struct TcParams {
     int pair, pair_stages, k_lo;
     int epi;
     int round_out;            // fp32 output rounded to the nearest TF32 value
+    int out_pair;             // 16-bit output rows [hi (N) | lo (N)], lo = residual of the rounding of hi
     int partial;              // split-K: raw fp32 partial sums to D + ks * part_stride, no bias / activation
     int64_t part_stride;
     const float* bias;
@@ -103,6 +104,37 @@ template <> __device__ __forceinline__ void store8<__half>(__half* p, const floa
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.z) : "f"(v[5]), "f"(v[4]));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.w) : "f"(v[7]), "f"(v[6]));
     *reinterpret_cast<uint4*>(p) = u;
+}
+// residuals of the 16-bit rounding of 8 values, themselves rounded to TO (the `lo` half of a pair output)
+template <typename TO> __device__ __forceinline__ uint4 resid8(const float* v);
+template <> __device__ __forceinline__ uint4 resid8<float>(const float*) { return make_uint4(0u, 0u, 0u, 0u); }
+template <> __device__ __forceinline__ uint4 resid8<__nv_bfloat16>(const float* v) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = v[i] - __bfloat162float(__float2bfloat16_rn(v[i]));
+    __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]), b = __floats2bfloat162_rn(r[2], r[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(r[4], r[5]), d = __floats2bfloat162_rn(r[6], r[7]);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+    u.z = *reinterpret_cast<uint32_t*>(&c); u.w = *reinterpret_cast<uint32_t*>(&d);
+    return u;
+}
+template <> __device__ __forceinline__ uint4 resid8<__half>(const float* v) {
+    uint32_t h[4];
+    uint4 u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+        r[2 * i] = v[2 * i] - f.x; r[2 * i + 1] = v[2 * i + 1] - f.y;
+    }
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.x) : "f"(r[1]), "f"(r[0]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.y) : "f"(r[3]), "f"(r[2]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.z) : "f"(r[5]), "f"(r[4]));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u.w) : "f"(r[7]), "f"(r[6]));
+    return u;
 }
 // 8 consecutive elements of TO as loaded (the ADDUP epilogue keeps gathers in flight in this raw form)
 template <typename TO> struct Raw8;
@@ -145,7 +177,7 @@ __device__ __forceinline__ TileCoord decode_tile(int t, const TcParams& p) {
 // shared-memory copy of the tile's bias slice, activation, conversion, 16-byte st.shared into a swizzled staging tile
 // [32 rows][SW bytes], and one TMA store per staged group: the async proxy writes whole 128-byte row segments and
 // clips rows >= M, so the epilogue warps spend no instructions on global addressing.
-template <int BN, typename TO, int EPI, bool ROUND>
+template <int BN, typename TO, int EPI, bool ROUND, bool PAIR = false>
 __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* tmD, const TileCoord& tc, uint32_t taddr,
                                          const float* sbias, uint8_t* stage, uint32_t tempty_bar, int lane, int q,
                                          int half) {
@@ -187,6 +219,8 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
         }
     }
     uint32_t v[2][32];
+    constexpr bool pair_out = PAIR && (OUT_B == 2);
+    uint4 lo[pair_out ? CPG * 4 : 1];          // pair output: the residuals of one store group, stored after its `hi` box
     tc_ld32_issue(taddr, v[0]);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
@@ -278,6 +312,7 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
             if (OUT_B == 2) {
                 const int k = sub * 4 + j / 8;
                 store8<TO>(reinterpret_cast<TO*>(stage + lane * SW + ((k ^ swz) << 4)), x);
+                if (pair_out) lo[pair_out ? k : 0] = resid8<TO>(x);
             } else {
                 const int k = j / 4;
                 *reinterpret_cast<float4*>(stage + lane * SW + ((k ^ swz) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
@@ -288,6 +323,16 @@ __device__ __forceinline__ void epi_tile(const TcParams& p, const CUtensorMap* t
             fence_async_smem();
             __syncwarp();
             if (lane == 0) tma_store_3d(tmD, smem_u32(stage), n0 - sub * 32, m_w0, dz);
+            if (OUT_B == 2 && pair_out) {
+                // the `lo` box of the same columns, N further along the row, through the same staging tile
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < CPG * 4; ++k) *reinterpret_cast<uint4*>(stage + lane * SW + ((k ^ swz) << 4)) = lo[pair_out ? k : 0];
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tma_store_3d(tmD, smem_u32(stage), p.N + n0 - sub * 32, m_w0, dz);
+            }
         }
     }
 }
@@ -496,6 +541,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else if (epi == EPI_GELU) EGR_EPI(EPI_GELU, (sizeof(TO) == 4));
                 else if (epi == EPI_RELU_ADDUP) EGR_EPI(EPI_RELU_ADDUP, (sizeof(TO) == 4));
                 else EGR_EPI(EPI_NONE, (sizeof(TO) == 4));
+            } else if (std::is_same<TO, __half>::value && p.out_pair) {
+                // pair output [hi | lo] (split activations between two fp16 stages): the epilogues that feed such stages
+                if (epi == EPI_RELU) epi_tile<BN, TO, EPI_RELU, false, true>(p, &tmD, tc, taddr, sbias, stage, tempty, lane, q, half);
+                else if (epi == EPI_RELU_ADDUP) epi_tile<BN, TO, EPI_RELU_ADDUP, false, true>(p, &tmD, tc, taddr, sbias, stage, tempty, lane, q, half);
+                else epi_tile<BN, TO, EPI_NONE, false, true>(p, &tmD, tc, taddr, sbias, stage, tempty, lane, q, half);
             } else {
                 if (epi == EPI_RELU) EGR_EPI(EPI_RELU, false);
                 else if (epi == EPI_GELU) EGR_EPI(EPI_GELU, false);
@@ -651,6 +701,9 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     if (d.epi == EPI_ADD_RELU || d.epi == EPI_ADDUP_RELU)
         EGR_CHECK(d.aux && out_dt_req != DT_F32, EGR_ERR_UNSUPPORTED, "gemm_tc: the residual epilogues need aux and a 16-bit output");
 
+    EGR_CHECK(!d.out_pair || (out_dt_req == DT_F16 && in_dt == DT_F16 && d.ldd >= 2 * (int64_t)d.N &&
+                              (d.epi == EPI_NONE || d.epi == EPI_RELU || d.epi == EPI_RELU_ADDUP)), EGR_ERR_UNSUPPORTED,
+              "gemm_tc: pair output needs fp16 operands and output, ldd >= 2N and epilogue none / ReLU / ReLU + up2");
     const int nsm = sm_count();
     const int m_tiles = ceil_div(d.M, BM);
     const int kb_total = d.K / BK;
@@ -687,7 +740,7 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
     p.m_tiles = m_tiles; p.n_tiles = d.N / bn; p.groups = d.groups;
     p.kb_total = kb_total;
     p.ksplit = 1; p.kb_per_split = p.kb_total;
-    p.amode = d.amode; p.epi = d.epi; p.round_out = d.round_tf32;
+    p.amode = d.amode; p.epi = d.epi; p.round_out = d.round_tf32; p.out_pair = d.out_pair;
     p.bias = d.bias; p.b_gs = d.b_gs;
     p.D = d.D; p.ldd = d.ldd; p.d_gs = d.d_gs;
     p.aux = d.aux; p.aux_gs = d.aux_gs; p.Hout_e = d.Hout; p.Wout_e = d.Wout;
@@ -778,7 +831,7 @@ int gemm_tc(const GemmDesc& d, int in_dt, int out_dt_req, cudaStream_t st) {
         const int nz = p.partial ? p.ksplit : d.groups;
         const int64_t zs = p.partial ? p.part_stride : d.d_gs;
         EGR_CHECK((ldd * OB) % 16 == 0 && (nz == 1 || (zs * OB) % 16 == 0), EGR_ERR_UNSUPPORTED, "gemm_tc: D strides must be multiples of 16 bytes");
-        const cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)d.M, (cuuint64_t)nz};
+        const cuuint64_t dims[3] = {(cuuint64_t)d.N * (d.out_pair ? 2 : 1), (cuuint64_t)d.M, (cuuint64_t)nz};
         const cuuint64_t str[2] = {(cuuint64_t)ldd * OB, (cuuint64_t)(nz > 1 ? zs : (int64_t)d.M * ldd) * OB};
         const cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
         if ((rc = encode(&tmD, out_dt, p.D, 3, dims, str, box, "D", box_cols * OB == 64))) return rc;

@@ -64,6 +64,9 @@ const char* egr_last_error(void);
  *   "stem_fused" (1)    backbone stem as the fused tcgen05 kernel; 0 = im2col buffer + plain GEMM
  *   "fpn_epi" (0)       backbone FPN upsample-add in the fuse conv's epilogue (measured slower)
  *   "conv_prefetch" (0) 3x3 s1 convs prefetch the next tile's rows into L2 (measured slower)
+ *   "asplit" (1)        EGR_PREC_FP16: the five 32x32 activations of the refine path (F1b, F1c, R1a, H2a, H2b outputs) are
+ *                       written as fp16 pairs [hi | lo] and read as split operands: five fewer 10-bit roundings on the way
+ *                       to the refined heatmap (8.8e-4 -> 6.5e-4 typical) for ~8 % of the step
  *   "fold16" (1)        EGR_PREC_FP16: the folded memory-projection GEMM of the mvfex tokens on fp16 pairs ([x_hi | x_lo] x
  *                       [W_hi | W_hi | W_lo]) instead of 3x TF32: same three-term product at half the bytes
  *   "tail_mma" (1)      heatmap-head tails with the bilinear upsample on the tensor cores; 0 = CUDA-core interpolation */
@@ -197,6 +200,10 @@ typedef struct egr_dense_desc {
      * (ka < K <= 2*ka).  K = 2*ka with W = [W_hi | W_lo] multiplies A by the weight AND its rounding residual (no weight
      * rounding error); K = 3*k0, ka = 2*k0, A = [x | x_lo], W = [W_hi | W_hi | W_lo] is the fp32-grade "3x TF32" product */
     int32_t ka;
+    /* pair output (use_tc, 16-bit D): the row of D is [hi (N) | lo (N)], lo = the rounding residual of hi in D's type;
+     * ldd >= 2N.  Read by the next stage as the split operand A = [x_hi | x_lo] (its ka = 2N, K = 3N with
+     * W = [W_hi | W_hi | W_lo]): no activation rounding between the two stages */
+    int32_t out_pair;
 } egr_dense_desc;
 int egr_dense_stage(const egr_dense_desc* desc, void* stream);
 

@@ -20,7 +20,7 @@ def _ptr(t):
 
 
 def dense(A, W, bias, D, M, N, K, lda, ldd, amode=0, epi=0, aux=None, kblk=0, kblk_stride=0, Hin=0, Win=0, Cin=0, Hout=0,
-          Wout=0, groups=1, a_gs=0, w_gs=0, b_gs=0, d_gs=0, aux_gs=0, use_tc=1, ka=0):
+          Wout=0, groups=1, a_gs=0, w_gs=0, b_gs=0, d_gs=0, aux_gs=0, use_tc=1, ka=0, out_pair=0):
     from egorear_b200 import _lib
     lib = _lib.load()
     d = _lib.DenseDesc()
@@ -34,6 +34,7 @@ def dense(A, W, bias, D, M, N, K, lda, ldd, amode=0, epi=0, aux=None, kblk=0, kb
     d.d_is_bf16 = code[D.dtype]
     d.use_tc = use_tc
     d.ka = ka
+    d.out_pair = out_pair
     _lib.check(lib.egr_dense_stage(ctypes.byref(d), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
 
@@ -375,3 +376,37 @@ def test_tc_residual_epilogues(out_dtype):
     dense(A, W, bias, D2, M, N, K, K, N, epi=5, aux=low, Hout=H, Wout=H)
     up = F.interpolate(low.double().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1).reshape(M, N)
     check(D2, torch.relu(A.double() @ W.double().t() + bias.double() + up).float(), torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(4096, 128, 256, 1), (1000, 256, 128, 0), (148 * 128 + 77, 128, 512, 1), (2048, 512, 128, 0)])
+def test_tc_fp16_pair_chain(M, N, K, epi):
+    """split ACTIVATIONS between two fp16 stages: stage 1 writes its output as the pair [hi | lo] (out_pair), stage 2 reads it
+    as A = [x_hi | x_lo] against W = [W_hi | W_hi | W_lo] (ka = 2N, K' = 3N).  The chain then equals the float64 chain of the
+    same fp16 INPUT to fp32-accumulation accuracy: no rounding of the intermediate, none of either weight matrix."""
+    g = torch.Generator(device="cuda").manual_seed(44)
+    A = torch.randn((M, K), generator=g, device="cuda").half()
+    W1 = torch.randn((N, K), generator=g, device="cuda") * K ** -0.5
+    b1 = torch.randn((N,), generator=g, device="cuda")
+    N2 = 128
+    W2 = torch.randn((N2, N), generator=g, device="cuda") * N ** -0.5
+    b2 = torch.randn((N2,), generator=g, device="cuda")
+    h1, l1 = _split16(W1)
+    mid = torch.full((M, 2 * N), float("nan"), device="cuda", dtype=torch.float16)
+    dense(A, torch.cat([h1, l1], dim=1).contiguous(), b1, mid, M, N, 2 * K, K, 2 * N, epi=epi, ka=K, out_pair=1)
+    y1 = torch.einsum("mk,nk->mn", A.double(), W1.double()) + b1.double()
+    if epi == 1:
+        y1 = torch.relu(y1)
+    hi, lo = mid[:, :N].double(), mid[:, N:].double()
+    assert torch.isfinite(mid).all()
+    err_mid = float((hi + lo - y1).abs().max() / y1.abs().max())
+    err_hi = float((hi - y1).abs().max() / y1.abs().max())
+    assert err_mid < 2e-5 and err_hi > 10 * err_mid
+    h2, l2 = _split16(W2)
+    out = torch.full((M, N2), float("nan"), device="cuda")
+    dense(mid, torch.cat([h2, h2, l2], dim=1).contiguous(), b2, out, M, N2, 3 * N, 2 * N, N2, ka=2 * N)
+    want = (torch.einsum("mk,nk->mn", y1, W2.double()) + b2.double()).float()
+    err = float((out - want).abs().max() / want.abs().max())
+    single = (torch.einsum("mk,nk->mn", hi, W2.double()) + b2.double()).float()
+    err_single = float((single - want).abs().max() / want.abs().max())
+    print("pair chain rel err %.2e (rounded intermediate: %.2e)" % (err, err_single))
+    assert err < 3e-5 and err < 0.2 * err_single
