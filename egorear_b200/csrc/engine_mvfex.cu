@@ -14,7 +14,7 @@ int g_opt_tc = 1;
 int g_opt_tok_batched = 1;     // EGR_PREC_BF16: batched token path (token GEMMs on tcgen05, TF32) instead of the fused SIMT kernel
 int g_opt_wsplit = 1;
 int g_opt_tok3x = 1;
-int g_opt_asplit = 1;      // option "asplit": EGR_PREC_FP16 keeps the five 32x32 activations of the refine path as fp16 pairs [hi | lo]
+int g_opt_asplit = 1;      // option "asplit": EGR_PREC_FP16 keeps four (1) / five (2: also the 512-channel F1b output) 32x32 activations of the refine path as fp16 pairs [hi | lo]
 int g_opt_fold16 = 1;      // option "fold16": EGR_PREC_FP16 runs the folded memory-projection GEMM (K = 3200) on fp16 pairs instead of 3x TF32
 extern int g_opt_pose_p2_bf16;
 extern int g_opt_pose_p2_fp16;
@@ -59,7 +59,7 @@ struct egr_mvfex {
     const void* in_staged = nullptr;           // one-shot: the caller's view-major channels-last bf16 copy of the input features
     const void* st_refined_hp = nullptr;
     bool tokb = false;
-    bool asplit = false;                       // EGR_PREC_FP16: F1b / F1c / R1a / H2a / H2b write [hi | lo] pairs, their consumers read them (PREC_F16X3)
+    int asplit = 0;                            // EGR_PREC_FP16: 1 = F1c / R1a / H2a / H2b write [hi | lo] pairs, their consumers read them (PREC_F16X3); 2 = F1b too
     bool tok3x = false;                        // EGR_PREC_FP16: token operand rows [x | x_lo], weights [W_hi | W_hi | W_lo]
     WMat tk_hp2, tk_fcq, tk_bfb, tk_sa, tk_c, tk_qkv, tk_o, tk_f1, tk_f2;
     const __nv_bfloat16** d_ptab16 = nullptr;  // device [4]: bf16 copies of the sampled position tables
@@ -431,21 +431,24 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     // refined heatmap disappear
     const int ap = h->asplit ? 2 : 1;
     const int cprec = h->asplit ? PREC_F16X3 : prec;      // consumer of a pair tensor
-    d.A = w.a1; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = 256; d.M = B * 1024; d.D = w.b1; d.ldd = 512 * ap;
-    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * 256; d.d_gs = (int64_t)B * 1024 * 512 * ap; d.out_pair = h->asplit;
+    // the 512-channel F1b output only with asplit >= 2: its pair costs F1b + F1c 0.1 ms (and F1b's epilogue 9 % of its tensor
+    // rate) for one rounding out of fourteen
+    const int ap1 = h->asplit >= 2 ? 2 : 1;
+    d.A = w.a1; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = 256; d.M = B * 1024; d.D = w.b1; d.ldd = 512 * ap1;
+    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * 256; d.d_gs = (int64_t)B * 1024 * 512 * ap1; d.out_pair = h->asplit >= 2;
     if ((rc = run_gemm(d, h->f1_2, r0, prec, false, st))) return rc;
     EGR_MARK("F1c", st);
     // F1c: 1x1(512->128) ReLU, fused with "+ offset_pred": + relu(up2(t1))   (:715 offset_pred + frame_feat)
     d = GemmDesc();
-    d.A = w.b1; d.lda = 512 * ap; d.M = B * 1024; d.D = w.ff; d.ldd = 128 * ap; d.epi = EPI_RELU_ADDUP; d.aux = w.t1;
-    d.Hout = 32; d.Wout = 32; d.groups = G; d.a_gs = (int64_t)B * 1024 * 512 * ap; d.d_gs = (int64_t)B * 1024 * 128 * ap;
-    d.aux_gs = (int64_t)B * NPOS * 128; d.out_pair = h->asplit;
-    if ((rc = run_gemm(d, h->f1_4, r0, cprec, false, st))) return rc;
+    d.A = w.b1; d.lda = 512 * ap1; d.M = B * 1024; d.D = w.ff; d.ldd = 128 * ap; d.epi = EPI_RELU_ADDUP; d.aux = w.t1;
+    d.Hout = 32; d.Wout = 32; d.groups = G; d.a_gs = (int64_t)B * 1024 * 512 * ap1; d.d_gs = (int64_t)B * 1024 * 128 * ap;
+    d.aux_gs = (int64_t)B * NPOS * 128; d.out_pair = h->asplit ? 1 : 0;
+    if ((rc = run_gemm(d, h->f1_4, r0, h->asplit >= 2 ? PREC_F16X3 : prec, false, st))) return rc;
     EGR_MARK("R1a", st);
     // R1a: 1x1(128->128) ReLU @32x32 ; R1b: second 1x1 commuted in front of the upsample
     d = GemmDesc();
     d.A = w.ff; d.lda = 128 * ap; d.M = B * 1024; d.D = w.r1a; d.ldd = 128 * ap; d.epi = EPI_RELU;
-    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128 * ap; d.out_pair = h->asplit;
+    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 128 * ap; d.out_pair = h->asplit ? 1 : 0;
     if ((rc = run_gemm(d, h->r1_0, r0, cprec, false, st))) return rc;
     EGR_MARK("R1b", st);
     // on the tensor-core path the pre-upsample maps z are written in fp16 so that the tails interpolate in half2
@@ -460,7 +463,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     // H2a: 3x3 s2 (128->256) ReLU ; H2b: 1x1(256->256) ReLU ; H2c: 1x1(256->128) (commuted) ; tail: up2, ReLU, 1x1->15
     d = GemmDesc();
     d.A = w.refn; d.amode = A_CONV3S2; d.Hin = FH; d.Win = FW; d.Cin = FC; d.M = B * 1024; d.D = w.b1; d.ldd = 256 * ap;
-    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256 * ap; d.out_pair = h->asplit;
+    d.epi = EPI_RELU; d.groups = G; d.a_gs = (int64_t)B * FHW * FC; d.d_gs = (int64_t)B * 1024 * 256 * ap; d.out_pair = h->asplit ? 1 : 0;
     if (!w.refn) {
         // the refined features exist only as the fp16 channels-last copy shared with pose3d: fp16 operands, bf16 output
         d.A = w.refn_hp; d.N = 256; d.K = 9 * FC; d.W = h->h2_0_f16 + (int64_t)r0 * 256 * 9 * FC; d.w_gs = (int64_t)256 * 9 * FC;
@@ -470,7 +473,7 @@ int run_refiners(egr_mvfex* h, int B, int G, int r0, const Bufs& w, const void* 
     EGR_MARK("H2b", st);
     d = GemmDesc();
     d.A = w.b1; d.lda = 256 * ap; d.M = B * 1024; d.D = w.c1; d.ldd = 256 * ap; d.epi = EPI_RELU;
-    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 256 * ap; d.out_pair = h->asplit;
+    d.groups = G; d.a_gs = d.d_gs = (int64_t)B * 1024 * 256 * ap; d.out_pair = h->asplit ? 1 : 0;
     if ((rc = run_gemm(d, h->h2_2, r0, cprec, false, st))) return rc;
     EGR_MARK("H2c", st);
     d = GemmDesc();
@@ -515,7 +518,7 @@ extern "C" int egr_set_option(const char* key, int value) {
     if (key && std::string(key) == "fpn_epi") { g_opt_fpn_epi = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "conv_prefetch") { g_opt_conv_prefetch = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "pair") { g_opt_pair = value ? 1 : 0; return EGR_OK; }
-    if (key && std::string(key) == "asplit") { g_opt_asplit = value ? 1 : 0; return EGR_OK; }
+    if (key && std::string(key) == "asplit") { g_opt_asplit = value < 0 ? 0 : value > 2 ? 2 : value; return EGR_OK; }
     if (key && std::string(key) == "fold16") { g_opt_fold16 = value ? 1 : 0; return EGR_OK; }
     if (key && std::string(key) == "tail_mma") { g_opt_tail_mma = value ? 1 : 0; return EGR_OK; }
     return fail(EGR_ERR_INVALID, "unknown option '%s'", key ? key : "(null)");
@@ -536,7 +539,7 @@ extern "C" int egr_mvfex_create(int num_views, int num_heatmap, float heatmap_th
     h->head_sets = (num_views == 2) ? 1 : 2;
     h->tokb = is16(precision) && g_opt_tc && g_opt_tok_batched;
     h->tok3x = precision == EGR_PREC_FP16 && g_opt_tok3x;
-    h->asplit = precision == EGR_PREC_FP16 && g_opt_asplit && g_opt_wsplit >= 1;
+    h->asplit = (precision == EGR_PREC_FP16 && g_opt_wsplit >= 1) ? g_opt_asplit : 0;
     h->KA = tok_ka(EMB, true);
     *out = h;
     return EGR_OK;
@@ -572,7 +575,7 @@ extern "C" int egr_mvfex_prepack(egr_mvfex* h, void* stream) {
               "mvfex: EGR_PREC_FP16 is a tensor-core mode (options tc / tok_batched must be on)");
     h->tokb = is16(h->prec) && g_opt_tc && g_opt_tok_batched;
     h->tok3x = h->prec == EGR_PREC_FP16 && g_opt_tok3x;
-    h->asplit = h->prec == EGR_PREC_FP16 && g_opt_asplit && g_opt_wsplit >= 1;
+    h->asplit = (h->prec == EGR_PREC_FP16 && g_opt_wsplit >= 1) ? g_opt_asplit : 0;
     h->KA = tok_ka(EMB, true);
     auto head = [&](const char* sub) { return [sub](int s) { return std::string(kHead[s]) + sub; }; };
     auto ref = [&](const char* sub) { return [sub](int s) { return std::string(kRefiner4[s]) + sub; }; };

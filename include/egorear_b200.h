@@ -64,9 +64,9 @@ const char* egr_last_error(void);
  *   "stem_fused" (1)    backbone stem as the fused tcgen05 kernel; 0 = im2col buffer + plain GEMM
  *   "fpn_epi" (0)       backbone FPN upsample-add in the fuse conv's epilogue (measured slower)
  *   "conv_prefetch" (0) 3x3 s1 convs prefetch the next tile's rows into L2 (measured slower)
- *   "asplit" (1)        EGR_PREC_FP16: the five 32x32 activations of the refine path (F1b, F1c, R1a, H2a, H2b outputs) are
- *                       written as fp16 pairs [hi | lo] and read as split operands: five fewer 10-bit roundings on the way
- *                       to the refined heatmap (8.8e-4 -> 6.5e-4 typical) for ~8 % of the step
+ *   "asplit" (1)        EGR_PREC_FP16: 32x32 activations of the refine path are written as fp16 pairs [hi | lo] and read as
+ *                       split operands: 1 = the F1c, R1a, H2a, H2b outputs (four fewer 10-bit roundings on the way to the
+ *                       refined heatmap, ~5 % of the step), 2 = also the 512-channel F1b output (+4 %), 0 = none
  *   "fold16" (1)        EGR_PREC_FP16: the folded memory-projection GEMM of the mvfex tokens on fp16 pairs ([x_hi | x_lo] x
  *                       [W_hi | W_hi | W_lo]) instead of 3x TF32: same three-term product at half the bytes
  *   "tail_mma" (1)      heatmap-head tails with the bilinear upsample on the tensor cores; 0 = CUDA-core interpolation */

@@ -3,7 +3,7 @@ and vs the golden vectors of the live reference.
 
 Bounds (BASELINE.json north_star): heatmaps / features <= 1e-3 relative (max|a-b| / max|ref|) in fp32 (measured 3e-6).  The
 tensor-core modes: fp16 precision (fp16 operands, split 1x1 weights,
-3x-TF32 token Linears, refine-path activations as fp16 pairs) also 1e-3 (measured 5.6e-4 / 6.9e-4; the margin and the
+3x-TF32 token Linears, four refine-path activations as fp16 pairs) also 1e-3 (measured 5.6e-4 / 6.9e-4; the margin and the
 faster `asplit=0` variant are discussed in tests/test_gpu_parity_bench.py), bf16 1e-2 (measured 7e-3); 3D joints <= 0.01 cm
 MPJPE delta.
 """

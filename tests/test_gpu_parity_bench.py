@@ -6,11 +6,12 @@ frames — frames are independent.  Next to the bounds on heatmaps
 fraction of decoded 2D joints whose argmax cell equals the reference's and the largest displacement of the rest.
 
 Bounds: fp32 <= 1e-3 relative (measured 3e-6).  fp16 (the default tensor-core mode: fp16 operands, split 1x1 weights, 3x-TF32 /
-fp16-pair token Linears, and the five 32x32 activations of the refine path kept as fp16 pairs, option `asplit`) <= 1e-3:
-measured 6.3e-4 / 8.5e-4 at B = 64, 5.7e-4 / 8.0e-4 at B = 512.  The margin is real but not wide: nine independent 10-bit
-roundings are left between the input features and the refined heatmap, and the max-norm of a 16-frame sample scatters by
-+-15 % with the sample and with the summation order of any kernel on the path.  Without the pairs (`asplit=0`, 9 % faster:
-fourteen roundings) the same cases measure 9.6e-4 ... 1.1e-3, i.e. AT the line - that variant states 1.5e-3
+fp16-pair token Linears, and four 32x32 activations of the refine path kept as fp16 pairs, option `asplit`) <= 1e-3:
+measured 6.3e-4 / 9.1e-4 at B = 64, 5.7e-4 / 8.1e-4 at B = 512, 5.6e-4 / 6.9e-4 at B = 2.  The margin is real but not wide:
+ten independent 10-bit roundings are left between the input features and the refined heatmap, and the max-norm of a 16-frame
+sample scatters by +-15 % with the sample and with the summation order of any kernel on the path.  `asplit=2` (the 512-channel
+F1b output as a pair too) measures 8.5e-4 at B = 64 for another 3 % of the step; without any pairs (`asplit=0`, 7 % faster:
+fourteen roundings) the same case measures 9.9e-4 ... 1.1e-3, i.e. AT the line - that variant states 1.5e-3
 (test_config2_b64_fp16_without_activation_pairs).  bf16 states 1e-2 (measured 5.7e-3 / 8.4e-3).  3D joints of the CHAINED
 model (GPU features -> GPU lifting vs oracle features -> oracle lifting): <= 0.1 mm MPJPE delta in fp32 and fp16 (measured
 0.04 mm); the bf16 mode does not meet that end to end (measured 0.18-0.21 mm: its feature error feeds the lifting) and states
