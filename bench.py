@@ -873,7 +873,8 @@ def main():
                        "weights": "random-init (name-seeded), shipped architecture", "l2": l2_note,
                        "streams": ("%d lanes: independent batches alternate between internal streams" % args.lanes)
                        if join is not None else "1",
-                       "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)"},
+                       "collective": "1 NCCL all-gather of the packed joints per step" if world > 1 else "none (1 GPU)",
+                       "options": dict(kv.split("=", 1) for kv in args.opt) if args.opt else "library defaults"},
             "clocks": sampler.result(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu, "parity": par, "sustained": sustained, "stages_ms": stages, "stage_roofline": stage_fracs,
             "single_stream": single}
