@@ -198,6 +198,12 @@ class HotPathPipeline:
         from .engine import ACT_DTYPE
         return feat.to(ACT_DTYPE[self.precision]).permute(1, 0, 3, 4, 2).contiguous()
 
+    def stage_host_bottom(self, bfb):
+        """the stride-32 map [B,V,512,8,8] in the 16-bit activation type for the trip across PCIe (it only feeds an 8x8 average
+        pool + fc_bfb: the rounding is averaged over 64 values); infer_host_batches widens it back to fp32 on the device"""
+        from .engine import ACT_DTYPE
+        return bfb.to(ACT_DTYPE[self.precision]).contiguous()
+
     @torch.no_grad()
     def infer_host_batches(self, batches, world=1):
         """End-to-end serving loop over HOST batches: yields the packed joints of every batch as a CPU tensor.
@@ -256,6 +262,8 @@ class HotPathPipeline:
                 i += 1
                 continue
             b = slots[s][1]
+            if b.dtype in (torch.bfloat16, torch.float16):       # stage_host_bottom: widened on the device
+                b = b.float()
             ctm = slots[s][2] if len(slots[s]) > 2 else None
             if f.dtype in (torch.bfloat16, torch.float16):       # staged: read in place (also by the chained pose3d sampling)
                 packed = self.forward(None, b, ctm, feat_staged=f)["packed"]
