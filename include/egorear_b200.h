@@ -50,7 +50,9 @@ extern "C" {
                             * (x_hi W_hi + x_lo W_hi + x_hi W_lo: fp32-grade) */
 
 const char* egr_last_error(void);
-/* process-wide switches (read when a handle is created / prepacked):
+/* process-wide switches.  Plain ints: set them before creating handles and not concurrently with launches ("tc", "wsplit",
+ * "tok3x", "asplit", "fold16", "tok_batched", "pose_p2_*" are read when a handle is created / prepacked; "pdl", "pair",
+ * "ws", "tail_mma", "stem_fused", "fpn_epi", "conv_prefetch" at every launch):
  *   "tc" (1)            EGR_PREC_BF16 uses the tcgen05 kernels; 0 routes bf16 activations through the SIMT GEMM
  *   "pdl" (1)           programmatic dependent launch between the library's kernels
  *   "tok_batched" (1)   batched token path (token GEMMs on tcgen05) instead of the fused per-frame SIMT kernels
