@@ -164,3 +164,22 @@ def test_msda_restatement_vs_grid_sample():
     a = model_ref.ms_deform_attn(value, H, W, loc, aw)
     b = _MSDAGridSample.apply(value, torch.tensor([[H, W]]), torch.tensor([0]), loc, aw, 32)
     assert rel_err(a.numpy(), b.numpy()) < 1e-5
+
+
+def test_msda_restatement_vs_transformers_deformable_detr():
+    """second, independent opinion on the un-vendored mmcv op: Hugging Face's pure-PyTorch
+    `MultiScaleDeformableAttention` of Deformable DETR (same MSDA definition, written by other people) on the same inputs,
+    single level as in EgoRear, at both map sizes the hot path samples (64x64, 32x32), with points outside the map"""
+    mod = pytest.importorskip("transformers.models.deformable_detr.modeling_deformable_detr")
+    msda = mod.MultiScaleDeformableAttention()
+    g = torch.Generator().manual_seed(5)
+    B, nh, hd, Q, P = 2, 4, 32, 15, 16
+    for shapes in ([(64, 64)], [(32, 32)]):
+        (H, W), = shapes
+        value = torch.randn((B, H * W, nh, hd), generator=g)
+        loc = torch.rand((B, Q, nh, 1, P, 2), generator=g) * 1.3 - 0.15       # some points outside the map
+        aw = torch.softmax(torch.randn((B, Q, nh, P), generator=g), -1).view(B, Q, nh, 1, P)
+        ours = model_ref.ms_deform_attn(value, H, W, loc, aw)
+        theirs = msda(value, shapes, torch.tensor(shapes), torch.tensor([0]), loc, aw, 64)
+        assert theirs.shape == ours.shape
+        assert rel_err(ours.numpy(), theirs.numpy()) < 1e-5
