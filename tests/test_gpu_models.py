@@ -42,6 +42,32 @@ def case(golden, oracle_lib):
     return dict(B=B, feat=feat, bfb=bfb, hfa=hfa, lh=lh, lf=lf, a2=a2, av=av, stages=st)
 
 
+@pytest.mark.parametrize("opts", [{"asplit": 0}, {"asplit": 2}, {"fold16": 0}, {"tail_mma": 0}, {"tok3x": 0, "asplit": 0}])
+def test_mvfex_fp16_option_variants(case, opts):
+    """every switch of the fp16 mode keeps a correct path behind it (stated bound of the loosest variant: 1.5e-3; plain-TF32
+    token Linears, `tok3x=0`, are the 10-bit mode that motivated the 3x product: 2e-3)"""
+    from egorear_b200 import engine
+    defaults = {"asplit": 1, "fold16": 1, "tail_mma": 1, "tok3x": 1}
+    for k, v in opts.items():
+        engine.set_option(k, v)
+    try:
+        m = build_mvfex(4, "fp16").cuda()
+        with torch.no_grad():
+            lh, lf = m.forward_from_feats(case["feat"].cuda(), case["bfb"].cuda(), case["hfa"].cuda())
+            torch.cuda.synchronize()
+    finally:
+        for k in opts:
+            engine.set_option(k, defaults[k])
+    a2, av = m.last_anchors
+    assert torch.equal(a2.cpu(), case["a2"]) and torch.equal(av.cpu(), case["av"])
+    e_init = rel_err(lh[0].cpu().numpy(), case["lh"][0].numpy())
+    e_ref = rel_err(lh[1].cpu().numpy(), case["lh"][1].numpy())
+    e_feat = rel_err(lf[1].cpu().numpy(), case["lf"][1].numpy())
+    print("mvfex fp16 %s: rel err hm_init %.2e hm_refined %.2e feat_refined %.2e" % (opts, e_init, e_ref, e_feat))
+    tol = 2e-3 if opts.get("tok3x") == 0 else 1.5e-3
+    assert e_init < tol and e_ref < tol and e_feat < tol
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL), ("fp16", FP16_TOL)])
 def test_mvfex_vs_oracle(case, golden, precision, tol):
     m = build_mvfex(4, precision).cuda()
