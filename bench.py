@@ -12,7 +12,8 @@ Frames shard across ranks with no other collective ("scaling": "weak", fixed 64 
 Rank 0 prints ONE JSON line: value = whole-job frames/s with inputs resident in HBM; e2e = the same through the
 public API with pinned-host inputs (H2D + D2H inside the timed region); roofline = dominant kernel (CUDA events,
 stage profiler of the library) against MEASURED_PEAKS.json; cpu_baseline = the CPU implementation on the host cores
-(live reference when /root/reference exists, else the oracle port) on a bounded sample.
+(the reference's own modules from /root/reference or its file copy oracle/_ref, else the oracle port) on a bounded sample;
+parity = the oracle on 8 sampled frames of the timed batch (untimed); sustained = the same step back to back for >= 3 s.
 
 Other workloads (parity-test configs, not the headline): --workload generate_target | decode | pose3d | mvfex | rw_e2e,
 and the widened rows of SURVEY §8f: eval_heatmap | eval_pose (eval-time metrics) and preprocess (PIL-exact resize +
@@ -30,7 +31,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "4-view frames/sec (heatmap+pose3d fwd)"
 # the tensor-core precision that is INSIDE the fp32 parity bound (<= 1e-3 relative): fp16 operands, split 1x1 weights,
-# 3x-TF32 token Linears (include/egorear_b200.h EGR_PREC_FP16); "bf16" is the looser-bound mode of round 1
+# 3x-TF32 / fp16-pair token Linears, activation pairs on the refine path (include/egorear_b200.h EGR_PREC_FP16);
+# "bf16" is the looser-bound mode of round 1
 DEFAULT_PRECISION = "fp16"
 UNIT = "frames/s"
 
