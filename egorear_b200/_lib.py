@@ -62,6 +62,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p]),
     "egr_heatmap_head_1x1": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "egr_dense_stage": (c_int, [POINTER(DenseDesc), c_void_p]),
+    "egr_up2_relu_stage": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "egr_head_tail_stage": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64,
                                     c_void_p, c_int, c_int, c_void_p]),
     "egr_mvfex_create": (c_int, [c_int, c_int, c_float, c_int, POINTER(c_void_p)]),

@@ -156,3 +156,17 @@ extern "C" int egr_head_tail_stage(const void* z, const float* w, const float* b
     if (impl) return head_tail_mma(z, w, bias, sel, B, G, J, hm, hm_bs, hm_gs, hm_t, precise, st);
     return head_tail_tc(z, w, bias, sel, B, G, J, hm, hm_bs, hm_gs, hm_t, precise, st);
 }
+
+extern "C" int egr_up2_relu_stage(const void* z, int n_img, void* out, int out_f16, int impl, void* stream) {
+    using namespace egr;
+    EGR_CHECK(z && out && n_img > 0, EGR_ERR_INVALID, "up2_relu_stage: null operand / n_img=%d", n_img);
+    EGR_CHECK((uintptr_t)z % 16 == 0 && (uintptr_t)out % 16 == 0, EGR_ERR_INVALID, "up2_relu_stage: z and out must be 16-byte aligned");
+    if (int rc = require_device()) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl) return up2_relu_mma(z, n_img, out, out_f16, st);
+    const int keep = g_opt_tail_mma;      // route up2_relu_dual to its CUDA-core kernel
+    g_opt_tail_mma = 0;
+    const int rc = up2_relu_dual(z, 2, n_img, 1, 32, 32, 128, nullptr, 0, 0, out, out_f16 ? 2 : 1, nullptr, 0, st, out_f16 ? 1 : 0);
+    g_opt_tail_mma = keep;
+    return rc;
+}

@@ -328,6 +328,170 @@ head_tail_mma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_const
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// R1 tail on the same machinery: refn = relu(up2_bilinear_align_corners(z)) as a 16-bit channels-last map (the input of the
+// H2 3x3 conv, and in EGR_PREC_FP16 the copy pose3d samples).  MMA-1 and the fp32 blend are those of the head tail; the
+// K-major SWIZZLE_128B tile the blend writes is exactly the layout a bulk tensor store takes, so the unit leaves as two
+// [128 px][64 ch] boxes - no second MMA, no staging pass.
+constexpr int U2_OFF_PAT = 0;
+constexpr int U2_OFF_A2 = U2_OFF_PAT + 3 * 8192;           // [2 channel halves][128 rows][128 B]
+constexpr int U2_OFF_Z = U2_OFF_A2 + 2 * 16384;            // two stages
+constexpr int U2_STAGES = 2;
+constexpr int U2_OFF_BAR = U2_OFF_Z + U2_STAGES * M2_ZSTAGE;
+constexpr int U2_SMEM = U2_OFF_BAR + 64 + 1024 /*align*/;
+static_assert(2 * (U2_SMEM + 1024) <= 233472, "two CTAs per SM");
+
+template <bool OUT_F16>
+__global__ void __launch_bounds__(M2_THREADS, 2)
+up2_relu_mma_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmO, int n_img) {
+    extern __shared__ __align__(1024) uint8_t m2_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(m2_raw) + 1023) & ~uintptr_t(1023));
+    const uint32_t sbase = smem_u32(smem);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + U2_OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    const uint32_t z_full0 = smem_u32(bars), z_empty0 = z_full0 + 16, pq_full = z_full0 + 32, pq_drained = z_full0 + 40;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_units = n_img * 32;
+
+    if (tid == 0) {
+        for (int s2 = 0; s2 < U2_STAGES; ++s2) { mbar_init(z_full0 + 8 * s2, 1); mbar_init(z_empty0 + 8 * s2, 1); }
+        mbar_init(pq_full, 1); mbar_init(pq_drained, M2_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmZ)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), M2_TMEM_COLS);
+    for (int i = tid; i < 3 * 8192 / 16; i += M2_THREADS) reinterpret_cast<uint4*>(smem + U2_OFF_PAT)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tid < 192) {      // the x-interpolation blocks [X][X][Y] of head_tail_mma_kernel
+        const int blk = tid >> 6, x = tid & 63;
+        int i0, rem;
+        up_int(x, i0, rem);
+        const int k0 = (blk == 2 ? M2_FS : 0) + i0;
+        __half* row = reinterpret_cast<__half*>(smem + U2_OFF_PAT + blk * 8192 + x * 128);
+        row[((((k0 >> 3) ^ (x & 7)) << 3)) + (k0 & 7)] = __float2half_rn((float)(M2_FO - 1 - rem));
+        if (rem) {
+            const int k1 = k0 + 1;
+            row[((((k1 >> 3) ^ (x & 7)) << 3)) + (k1 & 7)] = __float2half_rn((float)rem);
+        }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    if (warp == 0) {
+        int stage = 0, phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const M2Unit un = m2_unit(0, u, n_img);
+            mbar_wait(z_empty0 + 8 * stage, phase ^ 1);
+            const uint32_t full = z_full0 + 8 * stage;
+            const uint32_t dst = sbase + U2_OFF_Z + stage * M2_ZSTAGE;
+            const int px0 = un.img * (M2_FS * M2_FS) + un.base * M2_FS;
+            if (elect_one()) {
+                mbar_expect_tx(full, M2_ZSTAGE);
+                tma_load_3d(dst, &tmZ, full, 0, px0, 0);
+                tma_load_3d(dst + M2_ZHALF, &tmZ, full, 64, px0, 0);
+            }
+            __syncwarp();
+            if (++stage == U2_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc1 = make_idesc_fmt(128, M2_C, 0u) | (1u << 16);      // B operand MN-major
+        int stage = 0, phase = 0, it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+            const M2Unit un = m2_unit(0, u, n_img);
+            mbar_wait(z_full0 + 8 * stage, phase);
+            mbar_wait(pq_drained, (it & 1) ^ 1);      // the epilogue has read the previous unit's P / Q
+            tc_fence_after();
+            const uint64_t da = make_smem_desc(sbase + U2_OFF_PAT + un.pat * 8192);
+            const uint64_t dz = make_smem_desc_mn(sbase + U2_OFF_Z + stage * M2_ZSTAGE, M2_ZHALF);
+            if (elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) tc_mma<false>(tmem_base + M2_COL_P, da + 2 * kk, dz + 128 * kk, idesc1, kk ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) tc_mma<false>(tmem_base + M2_COL_Q, da + 2 * kk, dz + 256 + 128 * kk, idesc1, kk ? 1u : 0u);
+                tc_commit(z_empty0 + 8 * stage);
+                tc_commit(pq_full);
+            }
+            __syncwarp();
+            if (++stage == U2_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        const int r = q * 32 + lane, yy = r >> 6;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t a2row = sbase + U2_OFF_A2 + half * 16384 + r * 128;
+        const float inv = 1.f / (float)((M2_FO - 1) * (M2_FO - 1));
+        const bool issuer = (e == 0) && (lane == 0);
+        int it = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+            const M2Unit un = m2_unit(0, u, n_img);
+            int iy, remy;
+            up_int(un.y0 + yy, iy, remy);
+            const float fy0 = (float)(M2_FO - 1 - remy) * inv, fy1 = (float)remy * inv;
+            mbar_wait(pq_full, it & 1);
+            tc_fence_after();
+            // the tile is the source of the previous unit's bulk stores: wait until they have read it
+            if (issuer) tma_store_wait_read();
+            named_bar_sync_1<M2_EPI_WARPS * 32>();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t vp[16], vq[16];
+                tc_ld16_issue(lane_addr + M2_COL_P + half * 64 + c * 16, vp);
+                tc_ld16_issue(lane_addr + M2_COL_Q + half * 64 + c * 16, vq);
+                tc_ld16_wait(vp);
+                tc_ld16_wait(vq);
+                if (c == 3) {      // every accumulator column of this warp is in registers: the next unit's MMA may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(pq_drained);
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = j * 8 + k * 2;
+                        float a = fy0 * __uint_as_float(vp[i]), b2 = fy0 * __uint_as_float(vp[i + 1]);
+                        if (remy) {
+                            a = fmaf(fy1, __uint_as_float(vq[i]), a);
+                            b2 = fmaf(fy1, __uint_as_float(vq[i + 1]), b2);
+                        }
+                        if (OUT_F16) {
+                            o[k] = pack_relu_f16x2(a, b2);
+                        } else {
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, 0.f), fmaxf(b2, 0.f));
+                            o[k] = *reinterpret_cast<const uint32_t*>(&h);
+                        }
+                    }
+                    const int pp = c * 2 + j;
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a2row + ((pp ^ (r & 7)) << 4)), "r"(o[0]), "r"(o[1]),
+                                 "r"(o[2]), "r"(o[3]) : "memory");
+                }
+            }
+            fence_async_smem();
+            named_bar_sync_1<M2_EPI_WARPS * 32>();
+            if (issuer) {
+                const int px = un.img * (M2_FO * M2_FO) + un.y0 * M2_FO;      // rows y0, y0 + 1 = 128 consecutive pixels
+                tma_store_3d(&tmO, sbase + U2_OFF_A2, 0, px, 0);
+                tma_store_3d(&tmO, sbase + U2_OFF_A2 + 16384, 64, px, 0);
+            }
+        }
+        if (issuer) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, M2_TMEM_COLS);
+    }
+}
+
 }  // namespace
 
 int head_tail_mma(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
@@ -372,6 +536,36 @@ int head_tail_mma(const void* z, const float* w, const float* bias, const int* w
         EGR_LAUNCH(head_tail_mma_kernel<true>, grid, M2_THREADS, M2_SMEM, st, tmZ, tmO, tmT, w, bias, sel, B, G, J, hm_t ? 1 : 0);
     else
         EGR_LAUNCH(head_tail_mma_kernel<false>, grid, M2_THREADS, M2_SMEM, st, tmZ, tmO, tmT, w, bias, sel, B, G, J, hm_t ? 1 : 0);
+    return EGR_OK;
+}
+
+
+// relu(up2(z)) -> one 16-bit channels-last map (R1 tail when no other output is wanted); returns EGR_ERR_UNSUPPORTED-free:
+// callers check the shape / alignment conditions themselves (layout_ops.cu up2_relu_dual)
+int up2_relu_mma(const void* z, int n_img, void* out, int out_f16, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        EGR_CUDA_OK(cudaFuncSetAttribute(up2_relu_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM));
+        EGR_CUDA_OK(cudaFuncSetAttribute(up2_relu_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U2_SMEM));
+        attr_set = true;
+    }
+    CUtensorMap tmZ, tmO;
+    int rc;
+    {
+        const uint64_t dims[3] = {(uint64_t)M2_C, (uint64_t)n_img * M2_FS * M2_FS, 1};
+        const uint64_t str[2] = {(uint64_t)M2_C * 2, (uint64_t)n_img * M2_FS * M2_FS * M2_C * 2};
+        const uint32_t box[3] = {64, (uint32_t)M2_ZPX, 1};
+        if ((rc = tc_encode_tiled(&tmZ, DT_F16, z, 3, dims, str, box, "up2 z", false))) return rc;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)M2_C, (uint64_t)n_img * M2_FO * M2_FO, 1};
+        const uint64_t str[2] = {(uint64_t)M2_C * 2, (uint64_t)n_img * M2_FO * M2_FO * M2_C * 2};
+        const uint32_t box[3] = {64, 128, 1};
+        if ((rc = tc_encode_tiled(&tmO, out_f16 ? DT_F16 : DT_BF16, out, 3, dims, str, box, "up2 out", false))) return rc;
+    }
+    const int grid = std::min(2 * sm_count(), n_img * 32);
+    if (out_f16) EGR_LAUNCH(up2_relu_mma_kernel<true>, grid, M2_THREADS, U2_SMEM, st, tmZ, tmO, n_img);
+    else EGR_LAUNCH(up2_relu_mma_kernel<false>, grid, M2_THREADS, U2_SMEM, st, tmZ, tmO, n_img);
     return EGR_OK;
 }
 

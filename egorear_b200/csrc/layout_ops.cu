@@ -557,6 +557,11 @@ int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, 
         const size_t es = z_dt ? 2 : 4;
         // the transposed tile only serves the NCHW pass: without it the block needs half the shared memory
         const size_t fsmem = es * (FROWS * FS * FCH + (out_nchw ? FCH * 130 : 0));
+        // only the 16-bit channels-last map is wanted (chained forward, refined features not materialised): the bilinear
+        // upsample as a tcgen05.mma (head_tail_mma.cu), the blended tile leaves as bulk tensor stores
+        if (g_opt_tail_mma && z_dt == 2 && !out_nchw && !cl1 && cl0 && (cl0_dt == 1 || cl0_dt == 2) &&
+            ((uintptr_t)z % 16) == 0 && ((uintptr_t)cl0 % 16) == 0)
+            return up2_relu_mma(z, G * B, cl0, cl0_dt == 2, st);
         dim3 fgrid(FO / FSTRIP, G * B);
         if (z_dt == 2) {
             auto k = up2_relu_dual_fast_kernel<__half>;

@@ -25,6 +25,8 @@ int head_tail_tc(const void* z, const float* w, const float* bias, const int* ws
 // interpolation matrices (z read as an MN-major operand), fp32 row blend, then the 1x1 conv; persistent, TMA-fed
 int head_tail_mma(const void* z, const float* w, const float* bias, const int* wsel_host, int B, int G, int J, float* hm,
                   int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, cudaStream_t st);
+// R1 tail on the same kernel family: relu(up2(z)) -> ONE 16-bit channels-last map (z fp16 [n_img][32*32][128])
+int up2_relu_mma(const void* z, int n_img, void* out, int out_f16, cudaStream_t st);
 extern int g_opt_tail_mma;
 
 // R1 tail: z [g][B][Hs*Ws][C] (z_dt: 0 fp32, 1 bf16, 2 fp16) -> relu(up2(z)) written to

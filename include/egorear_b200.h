@@ -221,6 +221,12 @@ int egr_dense_stage(const egr_dense_desc* desc, void* stream);
  * ------------------------------------------------------------------------------------------- */
 int egr_head_tail_stage(const void* z, const float* w, const float* bias, const int32_t* wsel, int B, int G, int J,
                         float* hm, int64_t hm_bs, int64_t hm_gs, void* hm_t, int precise, int impl, void* stream);
+/* The refined-feature tail as a stage: out = relu(bilinear_x2_align_corners(z)) as a 16-bit channels-last map
+ *   (`nn.Upsample(2, bilinear, align_corners=True), ReLU` of frame_feat_refined_proj_layers, egoposeformer_heatmap_mvf_ex.py:553-560,
+ *   with the following 1x1 conv commuted in front of the upsample).
+ *   z [n_img][32*32][128] fp16; out [n_img][64*64][128] fp16 (out_f16 1) or bf16 (0); impl 1: tensor-core interpolation
+ *   (head_tail_mma.cu), 0: CUDA-core kernel (fp32 interpolation when out_f16) */
+int egr_up2_relu_stage(const void* z, int n_img, void* out, int out_f16, int impl, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * mvfex engine: everything EgoPoseFormerHeatmapMVFEX.forward does after the backbones

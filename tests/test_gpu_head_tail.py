@@ -72,3 +72,32 @@ def test_head_tail_impls_agree_exactly_on_grid_points():
     want = torch.einsum("gbpc,jc->bgjp", corner, w[0].double())
     got = hm1[:, :, :, [0, 0, 63, 63], [0, 63, 0, 63]].double()
     assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("out_f16", [1, 0])
+@pytest.mark.parametrize("n_img", [1, 5, 256])
+def test_up2_relu_stage(n_img, out_f16, impl):
+    """R1 tail: relu(up2(z)) as a 16-bit channels-last map, both implementations against float64 torch (one rounding of the
+    result: <= 2^-11 relative for fp16 + the fp32 interpolation arithmetic, 2^-8 for bf16)"""
+    from egorear_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(21 + n_img)
+    z = torch.randn((n_img, 1024, 128), generator=g, device="cuda").half()
+    dt = torch.float16 if out_f16 else torch.bfloat16
+    out = torch.full((n_img, 4096, 128), float("nan"), device="cuda", dtype=dt)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.egr_up2_relu_stage(ctypes.c_void_p(z.data_ptr()), n_img, ctypes.c_void_p(out.data_ptr()), out_f16, impl, st))
+    torch.cuda.synchronize()
+    x = z.double().reshape(n_img, 32, 32, 128).permute(0, 3, 1, 2)
+    ref = torch.relu(F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)).permute(0, 2, 3, 1).reshape(n_img, 4096, 128)
+    assert torch.isfinite(out).all()
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    # element by element: the correctly interpolated value rounded once (2^-11 / 2^-8 relative) + 5e-6 absolute for the
+    # CUDA-core kernel's fp32 source coordinates (scale * dst in float, as PyTorch computes them; the tensor-core kernel's
+    # integer weights are exact)
+    rtol = 5e-4 if out_f16 else 4e-3
+    excess = float(((out.double() - ref).abs() - rtol * ref.abs()).max())
+    print("up2_relu impl %d f16 %d n %d: max err / max ref %.2e, worst excess over %.0e relative: %.2e" % (impl, out_f16, n_img, err, rtol, excess))
+    # (the CUDA-core kernel interpolates a bf16-mode map in half2 arithmetic: one rounding per HFMA2)
+    assert excess < (1e-7 if impl else 5e-6 if out_f16 else 5e-3)
