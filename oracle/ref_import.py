@@ -36,7 +36,11 @@ def is_copy():
 
 
 def _stub(name, **attrs):
+    import importlib.machinery
     m = types.ModuleType(name)
+    # a real spec: other packages probe optional dependencies with importlib.util.find_spec(name), which raises on a module
+    # whose __spec__ is None (transformers does that for timm)
+    m.__spec__ = importlib.machinery.ModuleSpec(name, loader=None)
     m.__dict__.update(attrs)
     sys.modules[name] = m
     return m
