@@ -164,9 +164,6 @@ extern "C" int egr_up2_relu_stage(const void* z, int n_img, void* out, int out_f
     if (int rc = require_device()) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl) return up2_relu_mma(z, n_img, out, out_f16, st);
-    const int keep = g_opt_tail_mma;      // route up2_relu_dual to its CUDA-core kernel
-    g_opt_tail_mma = 0;
-    const int rc = up2_relu_dual(z, 2, n_img, 1, 32, 32, 128, nullptr, 0, 0, out, out_f16 ? 2 : 1, nullptr, 0, st, out_f16 ? 1 : 0);
-    g_opt_tail_mma = keep;
-    return rc;
+    return up2_relu_dual(z, 2, n_img, 1, 32, 32, 128, nullptr, 0, 0, out, out_f16 ? 2 : 1, nullptr, 0, st, out_f16 ? 1 : 0,
+                         /*allow_mma=*/false);
 }

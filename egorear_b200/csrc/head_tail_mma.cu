@@ -34,8 +34,6 @@
 
 namespace egr {
 using namespace tcx;
-int tc_encode_tiled(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, const char* what, bool no_swizzle);      // gemm_tc.cu
 namespace {
 
 constexpr int M2_FS = 32, M2_FO = 64, M2_C = 128, M2_NJ = 16;

@@ -551,7 +551,7 @@ up2_relu_dual_kernel(const TZ* __restrict__ z, int B, int Hs, int Ws, int C, flo
 }
 
 int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st, int fp32_interp) {
+                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st, int fp32_interp, bool allow_mma) {
     EGR_CHECK((2 * Hs) % STRIP == 0, EGR_ERR_UNSUPPORTED, "up2_relu_dual: geometry");
     if (Hs == FS && Ws == FS && C == FCH) {
         const size_t es = z_dt ? 2 : 4;
@@ -559,7 +559,7 @@ int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, 
         const size_t fsmem = es * (FROWS * FS * FCH + (out_nchw ? FCH * 130 : 0));
         // only the 16-bit channels-last map is wanted (chained forward, refined features not materialised): the bilinear
         // upsample as a tcgen05.mma (head_tail_mma.cu), the blended tile leaves as bulk tensor stores
-        if (g_opt_tail_mma && z_dt == 2 && !out_nchw && !cl1 && cl0 && (cl0_dt == 1 || cl0_dt == 2) &&
+        if (allow_mma && g_opt_tail_mma && z_dt == 2 && !out_nchw && !cl1 && cl0 && (cl0_dt == 1 || cl0_dt == 2) &&
             ((uintptr_t)z % 16) == 0 && ((uintptr_t)cl0 % 16) == 0)
             return up2_relu_mma(z, G * B, cl0, cl0_dt == 2, st);
         dim3 fgrid(FO / FSTRIP, G * B);

@@ -34,8 +34,10 @@ extern int g_opt_tail_mma;
 //   cl0 / cl1 [g][B][4HsWs][C] with their own element types (cl*_dt: 0 fp32 rounded to TF32, 1 bf16, 2 fp16, 3 fp32 as is): the input of
 //   the H2 3x3 conv and the high-precision copy of the pose3d proposal branch (one shared fp16 copy when chained)
 int up2_relu_dual(const void* z, int z_dt, int B, int G, int Hs, int Ws, int C, float* out_nchw, int64_t o_bs,
-                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st, int fp32_interp = 0);
+                  int64_t o_gs, void* cl0, int cl0_dt, void* cl1, int cl1_dt, cudaStream_t st, int fp32_interp = 0,
+                  bool allow_mma = true);
 // fp32_interp: an fp16 z is interpolated in fp32 arithmetic (one rounding, EGR_PREC_FP16) instead of half2 (one per HFMA2)
+// allow_mma: take the tensor-core kernel (up2_relu_mma) when only cl0 is wanted and option "tail_mma" is on
 
 // nn.MaxPool2d(2) on channels-last [img][H][W][C] -> [img][H/2][W/2][C];  dt: 0 fp32, 1 bf16, 2 fp16
 int maxpool2_nhwc(const void* in, void* out, int dt, int64_t n_img, int H, int W, int C, cudaStream_t st);

@@ -4,6 +4,9 @@
 #include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is resolved at run time (no -lcuda)
 
 namespace egr {
+// tiled tensor map (SWIZZLE_128B, or unswizzled rows) for the TMA kernels outside gemm_tc.cu; dt = DT_F32 / DT_BF16 / DT_F16
+int tc_encode_tiled(CUtensorMap* tm, int dt, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const char* what, bool no_swizzle);      // gemm_tc.cu
 namespace tcx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
